@@ -1,0 +1,542 @@
+"""CPU oracle for the CL-SLAM online-adaptation hot path.  TEST INFRASTRUCTURE ONLY.
+
+This file is a *restatement* (functional, state-dict driven, plain PyTorch fp32 on the CPU)
+of what the reference computes on the path SURVEY.md section 8 names.  It exists so that
+the CUDA product path in ``clslam_b200/`` can be checked on a machine where the reference
+checkout (``/root/reference``) is absent.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it.  Nothing in
+``clslam_b200/`` imports it, and the product path has no CPU fallback.
+
+Pinning: the reference ships no tests or golden vectors for this path, so
+the oracle is pinned against *outputs of the reference itself* executed in the build
+container: ``oracle/make_golden.py`` imports ``/root/reference`` unmodified, runs
+``DepthPosePrediction._process_batch`` / ``adapt`` / ``predict_pose`` on seeded inputs and
+commits the results under ``tests/golden/``; ``tests/test_oracle_golden.py`` compares this
+file against those fixtures.
+
+The arithmetic of the reference lives in third-party ``torch`` / ``torchvision``
+(requirements.txt:5-6 pins torch==1.10.0, torchvision==0.11.1; this image has 2.11.0); the
+oracle calls the same ``torch.nn.functional`` primitives, which is why it is a "port" and
+not a re-derivation.
+
+Citations are ``file:line`` relative to ``/root/reference/depth_pose_prediction/``.
+"""
+from __future__ import annotations
+
+import math
+import time
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+StateDict = Dict[str, Tensor]
+
+FRAME_IDS = (0, -1, 1)          # depth_pose_prediction.py:75
+DEC_CH = (16, 32, 64, 128, 256)  # networks/depth_decoder.py:28
+ENC_CH = (64, 64, 128, 256, 512)  # networks/resnet_encoder.py:99
+NET_NAMES = ('depth_encoder', 'depth_decoder', 'pose_encoder', 'pose_decoder')
+
+
+# --------------------------------------------------------------------------------------
+# Parameters: deterministic synthetic weights with the reference's state-dict key names
+# --------------------------------------------------------------------------------------
+
+def _resnet18_layout(in_ch: int) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(key, shape, kind) for a torchvision ResNet-18 trunk as wrapped by
+    networks/resnet_encoder.py:79-113 (keys are prefixed ``resnet.``)."""
+    spec: List[Tuple[str, Tuple[int, ...], str]] = []
+
+    def bn(prefix: str, c: int) -> None:
+        spec.append((prefix + '.weight', (c,), 'bn_gamma'))
+        spec.append((prefix + '.bias', (c,), 'bn_beta'))
+        spec.append((prefix + '.running_mean', (c,), 'bn_mean'))
+        spec.append((prefix + '.running_var', (c,), 'bn_var'))
+        spec.append((prefix + '.num_batches_tracked', (), 'bn_count'))
+
+    spec.append(('resnet.conv1.weight', (64, in_ch, 7, 7), 'conv'))
+    bn('resnet.bn1', 64)
+    planes_in = 64
+    for li, planes in enumerate((64, 128, 256, 512), start=1):
+        for bi in range(2):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            p = f'resnet.layer{li}.{bi}'
+            spec.append((p + '.conv1.weight', (planes, planes_in, 3, 3), 'conv'))
+            bn(p + '.bn1', planes)
+            spec.append((p + '.conv2.weight', (planes, planes, 3, 3), 'conv'))
+            bn(p + '.bn2', planes)
+            if stride != 1 or planes_in != planes:
+                spec.append((p + '.downsample.0.weight', (planes, planes_in, 1, 1), 'conv'))
+                bn(p + '.downsample.1', planes)
+            planes_in = planes
+    spec.append(('resnet.fc.weight', (1000, 512), 'fc'))
+    spec.append(('resnet.fc.bias', (1000,), 'fc_bias'))
+    return spec
+
+
+def _depth_decoder_layout() -> List[Tuple[str, Tuple[int, ...], str]]:
+    """networks/depth_decoder.py:30-46: creation order upconv_4_0 ... upconv_0_1, dispconv_0..3."""
+    spec = []
+    for i in range(4, -1, -1):
+        cin0 = ENC_CH[-1] if i == 4 else DEC_CH[i + 1]
+        spec.append((f'upconv_{i}_0.conv.conv.weight', (DEC_CH[i], cin0, 3, 3), 'convb'))
+        spec.append((f'upconv_{i}_0.conv.conv.bias', (DEC_CH[i],), 'bias'))
+        cin1 = DEC_CH[i] + (ENC_CH[i - 1] if i > 0 else 0)
+        spec.append((f'upconv_{i}_1.conv.conv.weight', (DEC_CH[i], cin1, 3, 3), 'convb'))
+        spec.append((f'upconv_{i}_1.conv.conv.bias', (DEC_CH[i],), 'bias'))
+    for s in range(4):
+        spec.append((f'dispconv_{s}.conv.weight', (1, DEC_CH[s], 3, 3), 'convb'))
+        spec.append((f'dispconv_{s}.conv.bias', (1,), 'bias'))
+    return spec
+
+
+def _pose_decoder_layout() -> List[Tuple[str, Tuple[int, ...], str]]:
+    """networks/pose_decoder.py:27-30 with num_input_features=1, num_frames_to_predict_for=2."""
+    return [
+        ('squeeze.weight', (256, 512, 1, 1), 'convb'), ('squeeze.bias', (256,), 'bias'),
+        ('pose_0.weight', (256, 256, 3, 3), 'convb'), ('pose_0.bias', (256,), 'bias'),
+        ('pose_1.weight', (256, 256, 3, 3), 'convb'), ('pose_1.bias', (256,), 'bias'),
+        ('pose_2.weight', (12, 256, 1, 1), 'convb'), ('pose_2.bias', (12,), 'bias'),
+    ]
+
+
+def net_layouts() -> Dict[str, List[Tuple[str, Tuple[int, ...], str]]]:
+    return {
+        'depth_encoder': _resnet18_layout(3),
+        'depth_decoder': _depth_decoder_layout(),
+        'pose_encoder': _resnet18_layout(6),
+        'pose_decoder': _pose_decoder_layout(),
+    }
+
+
+def make_params(seed: int = 0, dtype: torch.dtype = torch.float32) -> Dict[str, StateDict]:
+    """Deterministic synthetic weights for the four nets, keyed like the reference's
+    state dicts.  Not the reference's init (that depends on module
+    construction order); the golden script loads *these* tensors into the reference."""
+    g = torch.Generator().manual_seed(1000003 * seed + 17)
+    out: Dict[str, StateDict] = {}
+    for net, layout in net_layouts().items():
+        sd: StateDict = {}
+        for key, shape, kind in layout:
+            if kind == 'conv':      # encoder convs, bias-free (kaiming fan_out like torchvision)
+                fan_out = shape[0] * shape[2] * shape[3]
+                t = torch.randn(shape, generator=g) * math.sqrt(2.0 / fan_out)
+            elif kind == 'convb':   # decoder convs (nn.Conv2d default bound 1/sqrt(fan_in))
+                fan_in = shape[1] * shape[2] * shape[3]
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan_in)
+            elif kind == 'bias':
+                t = (torch.rand(shape, generator=g) * 2 - 1) * 0.05
+            elif kind == 'bn_gamma':
+                t = 1.0 + 0.1 * (torch.rand(shape, generator=g) * 2 - 1)
+            elif kind == 'bn_beta':
+                t = 0.05 * (torch.rand(shape, generator=g) * 2 - 1)
+            elif kind == 'bn_mean':
+                t = 0.1 * (torch.rand(shape, generator=g) * 2 - 1)
+            elif kind == 'bn_var':
+                t = 1.0 + 0.2 * (torch.rand(shape, generator=g) * 2 - 1)
+            elif kind == 'bn_count':
+                sd[key] = torch.tensor(0, dtype=torch.long)
+                continue
+            elif kind == 'fc':
+                t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(shape[1])
+            elif kind == 'fc_bias':
+                t = torch.zeros(shape)
+            else:
+                raise AssertionError(kind)
+            sd[key] = t.to(dtype)
+        out[net] = sd
+    return out
+
+
+def trainable_keys() -> List[Tuple[str, str]]:
+    """The 36 tensors ``adapt`` updates (encoders frozen, depth_pose_prediction.py:807-827),
+    in the order torch.optim.Adam sees them (models dict order, :183-203)."""
+    keys = []
+    for net in ('depth_decoder', 'pose_decoder'):
+        for key, _, kind in net_layouts()[net]:
+            keys.append((net, key))
+    return keys
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic input batch
+# --------------------------------------------------------------------------------------
+
+def kitti_intrinsics(height: int, width: int, scale: int) -> Tuple[np.ndarray, np.ndarray]:
+    """datasets/kitti.py:65-66 normalised K, scaled per datasets/utils.py:104-110."""
+    k = np.array([[0.58, 0, 0.5, 0], [0, 1.92, 0.5, 0], [0, 0, 1, 0], [0, 0, 0, 1]],
+                 dtype=np.float32)
+    k = k.copy()
+    k[0, :] *= width // (2 ** scale)
+    k[1, :] *= height // (2 ** scale)
+    return k, np.linalg.pinv(k)
+
+
+def make_batch(batch: int, height: int, width: int, seed: int = 0, coherent: bool = False,
+               ) -> Dict[object, Tensor]:
+    """Batch dict with the reference schema.  ``coherent`` makes the three frames shifted,
+    blurred copies of one random image so that warps land in-image and the
+    min-reprojection is not all-identity."""
+    g = torch.Generator().manual_seed(7919 * seed + 3)
+    out: Dict[object, Tensor] = {'index': torch.arange(batch, dtype=torch.long)}
+    if coherent:
+        base = torch.rand(batch, 3, height + 16, width + 32, generator=g)
+        for _ in range(3):
+            base = F.avg_pool2d(F.pad(base, (2, 2, 2, 2), mode='reflect'), 5, 1)
+        base = (base - base.amin()) / (base.amax() - base.amin())
+        frames = {}
+        for f, dx in ((-1, 10), (0, 16), (1, 23)):
+            frames[f] = base[:, :, 8:8 + height, dx:dx + width].contiguous()
+    else:
+        frames = {f: torch.rand(batch, 3, height, width, generator=g) for f in (-1, 0, 1)}
+    for f in (-1, 0, 1):
+        for s in range(4):
+            img = frames[f] if s == 0 else F.avg_pool2d(frames[f], 2 ** s)
+            out[('rgb', f, s)] = img.contiguous()
+            out[('rgb_aug', f, s)] = img.clone()
+    for s in range(4):
+        k, ik = kitti_intrinsics(height, width, s)
+        out[('camera_matrix', s)] = torch.from_numpy(k).unsqueeze(0).repeat(batch, 1, 1)
+        out[('inv_camera_matrix', s)] = torch.from_numpy(ik).unsqueeze(0).repeat(batch, 1, 1)
+    for f in (0, 1):
+        out[('relative_distance', f)] = (torch.rand(batch, generator=g, dtype=torch.float64) + 0.5)
+    return out
+
+
+def make_noise(batch: int, height: int, width: int, seed: int = 0, n_scales: int = 4) -> List[Tensor]:
+    """Stand-in for the ``torch.randn`` tie-break draws (depth_pose_prediction.py:1055-1056):
+    one (B,2,H,W) standard-normal tensor per scale, in scale order."""
+    g = torch.Generator().manual_seed(104729 * seed + 11)
+    return [torch.randn(batch, 2, height, width, generator=g) for _ in range(n_scales)]
+
+
+# --------------------------------------------------------------------------------------
+# Networks
+# --------------------------------------------------------------------------------------
+
+def _bn_eval(x: Tensor, sd: StateDict, p: str) -> Tensor:
+    return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'],
+                        sd[p + '.bias'], training=False, momentum=0.1, eps=1e-5)
+
+
+def _basic_block(x: Tensor, sd: StateDict, p: str, stride: int) -> Tensor:
+    """torchvision BasicBlock."""
+    y = F.conv2d(x, sd[p + '.conv1.weight'], None, stride, 1)
+    y = F.relu(_bn_eval(y, sd, p + '.bn1'))
+    y = F.conv2d(y, sd[p + '.conv2.weight'], None, 1, 1)
+    y = _bn_eval(y, sd, p + '.bn2')
+    if (p + '.downsample.0.weight') in sd:
+        x = _bn_eval(F.conv2d(x, sd[p + '.downsample.0.weight'], None, stride, 0), sd,
+                     p + '.downsample.1')
+    return F.relu(y + x)
+
+
+def encoder_forward(sd: StateDict, image: Tensor) -> List[Tensor]:
+    """networks/resnet_encoder.py:115-125 (BatchNorm in eval mode, as in ``adapt``)."""
+    x = (image - 0.45) / 0.225
+    x = F.conv2d(x, sd['resnet.conv1.weight'], None, 2, 3)
+    feats = [F.relu(_bn_eval(x, sd, 'resnet.bn1'))]
+    x = F.max_pool2d(feats[0], 3, 2, 1)
+    for li in range(1, 5):
+        for bi in range(2):
+            x = _basic_block(x, sd, f'resnet.layer{li}.{bi}', 2 if (li > 1 and bi == 0) else 1)
+        feats.append(x)
+    return feats
+
+
+def _conv3x3_reflect(x: Tensor, w: Tensor, b: Tensor) -> Tensor:
+    """networks/layers.py:28-48."""
+    return F.conv2d(F.pad(x, (1, 1, 1, 1), mode='reflect'), w, b)
+
+
+def depth_decoder_forward(sd: StateDict, feats: Sequence[Tensor],
+                          scales: Sequence[int] = (0, 1, 2, 3)) -> Dict[Tuple[str, int], Tensor]:
+    """networks/depth_decoder.py:51-71."""
+    out = {}
+    x = feats[-1]
+    for i in range(4, -1, -1):
+        x = F.elu(_conv3x3_reflect(x, sd[f'upconv_{i}_0.conv.conv.weight'],
+                                   sd[f'upconv_{i}_0.conv.conv.bias']))
+        if i > 0:
+            x = F.interpolate(x, size=feats[i - 1].shape[2:], mode='nearest')
+            x = torch.cat([x, feats[i - 1]], 1)
+        else:
+            x = F.interpolate(x, scale_factor=2, mode='nearest')
+        x = F.elu(_conv3x3_reflect(x, sd[f'upconv_{i}_1.conv.conv.weight'],
+                                   sd[f'upconv_{i}_1.conv.conv.bias']))
+        if i in scales:
+            out[('disp', i)] = torch.sigmoid(
+                _conv3x3_reflect(x, sd[f'dispconv_{i}.conv.weight'], sd[f'dispconv_{i}.conv.bias']))
+    return out
+
+
+def pose_decoder_forward(sd: StateDict, f4: Tensor) -> Tuple[Tensor, Tensor]:
+    """networks/pose_decoder.py:37-54 -> (axis_angle, translation), each (B,2,1,3)."""
+    x = F.relu(F.conv2d(f4, sd['squeeze.weight'], sd['squeeze.bias']))
+    x = F.relu(F.conv2d(x, sd['pose_0.weight'], sd['pose_0.bias'], 1, 1))
+    x = F.relu(F.conv2d(x, sd['pose_1.weight'], sd['pose_1.bias'], 1, 1))
+    x = F.conv2d(x, sd['pose_2.weight'], sd['pose_2.bias'])
+    x = 0.01 * x.mean(3).mean(2).view(-1, 2, 1, 6)
+    return x[..., :3], x[..., 3:]
+
+
+# --------------------------------------------------------------------------------------
+# SE(3), geometry, warp
+# --------------------------------------------------------------------------------------
+
+def rodrigues(aa: Tensor) -> Tensor:
+    """utils.py:74-117: (B,1,3) axis-angle -> (B,4,4) rotation."""
+    theta = aa.norm(dim=2, keepdim=True)
+    n = aa / (theta + 1e-7)
+    c, s = torch.cos(theta), torch.sin(theta)
+    big_c = 1 - c
+    x, y, z = (n[..., k].unsqueeze(1) for k in range(3))
+    rows = [
+        [x * (x * big_c) + c, x * (y * big_c) - z * s, z * (x * big_c) + y * s],
+        [x * (y * big_c) + z * s, y * (y * big_c) + c, y * (z * big_c) - x * s],
+        [z * (x * big_c) - y * s, y * (z * big_c) + x * s, z * (z * big_c) + c],
+    ]
+    rot = torch.zeros(aa.shape[0], 4, 4, dtype=aa.dtype)
+    for r in range(3):
+        for col in range(3):
+            rot[:, r, col] = rows[r][col].reshape(-1)
+    rot[:, 3, 3] = 1
+    return rot
+
+
+def se3_from_params(aa: Tensor, t: Tensor, invert: bool) -> Tensor:
+    """utils.py:34-71: M = T.R, or R^T.T(-t) when ``invert``."""
+    rot = rodrigues(aa)
+    tv = t.reshape(-1, 3)
+    if invert:
+        rot = rot.transpose(1, 2)
+        tv = -tv
+    trans = torch.eye(4, dtype=aa.dtype).repeat(aa.shape[0], 1, 1)
+    trans = trans.clone()
+    trans[:, :3, 3] = tv
+    return rot @ trans if invert else trans @ rot
+
+
+def disp_to_depth(disp: Tensor, min_depth: Optional[float], max_depth: Optional[float]) -> Tensor:
+    """utils.py:120-142."""
+    if min_depth is None and max_depth is None:
+        return 1 / disp
+    if max_depth is None:
+        return min_depth / disp
+    lo, hi = 1 / max_depth, 1 / min_depth
+    return 1 / (lo + (hi - lo) * disp)
+
+
+def reproject_grid(depth: Tensor, k: Tensor, inv_k: Tensor, cam_t: Tensor) -> Tensor:
+    """networks/layers.py:74-79 + :93-104 -> normalised sampling grid (B,H,W,2)."""
+    b, _, h, w = depth.shape
+    vs, us = torch.meshgrid(torch.arange(h, dtype=depth.dtype), torch.arange(w, dtype=depth.dtype),
+                            indexing='ij')
+    pix = torch.stack([us.reshape(-1), vs.reshape(-1), torch.ones(h * w, dtype=depth.dtype)], 0)
+    rays = inv_k[:, :3, :3] @ pix.unsqueeze(0).expand(b, -1, -1)
+    pts = torch.cat([depth.view(b, 1, -1) * rays, torch.ones(b, 1, h * w, dtype=depth.dtype)], 1)
+    proj = (k @ cam_t)[:, :3, :] @ pts
+    uv = proj[:, :2, :] / (proj[:, 2:3, :] + 1e-7)
+    uv = uv.view(b, 2, h, w).permute(0, 2, 3, 1)
+    gx = (uv[..., 0] / (w - 1) - 0.5) * 2
+    gy = (uv[..., 1] / (h - 1) - 0.5) * 2
+    return torch.stack([gx, gy], -1)
+
+
+def ssim_loss_map(pred: Tensor, target: Tensor) -> Tensor:
+    """networks/layers.py:123-137."""
+    x = F.pad(pred, (1, 1, 1, 1), mode='reflect')
+    y = F.pad(target, (1, 1, 1, 1), mode='reflect')
+    mu_x, mu_y = F.avg_pool2d(x, 3, 1), F.avg_pool2d(y, 3, 1)
+    sig_x = F.avg_pool2d(x * x, 3, 1) - mu_x ** 2
+    sig_y = F.avg_pool2d(y * y, 3, 1) - mu_y ** 2
+    sig_xy = F.avg_pool2d(x * y, 3, 1) - mu_x * mu_y
+    num = (2 * mu_x * mu_y + 0.01 ** 2) * (2 * sig_xy + 0.03 ** 2)
+    den = (mu_x ** 2 + mu_y ** 2 + 0.01 ** 2) * (sig_x + sig_y + 0.03 ** 2)
+    return torch.clamp((1 - num / den) / 2, 0, 1)
+
+
+def photometric_error(pred: Tensor, target: Tensor) -> Tensor:
+    """depth_pose_prediction.py:1178-1192 -> (B,1,H,W)."""
+    l1 = (target - pred).abs().mean(1, True)
+    return 0.85 * ssim_loss_map(pred, target).mean(1, True) + 0.15 * l1
+
+
+def smoothness_reference_quirk(norm_disp: Tensor, img: Tensor) -> Tensor:
+    """depth_pose_prediction.py:1148-1176 *as executed* with an all-true mask:
+    the first masked_select flattens the edge-weighted gradients to 1-D, after which the
+    per-sample loop indexes that flat vector by sample number, so "sample i" receives the
+    x- and y-terms at row 0, column i of batch element 0."""
+    b = norm_disp.shape[0]
+    gx = (norm_disp[:, :, :, :-1] - norm_disp[:, :, :, 1:]).abs()
+    gy = (norm_disp[:, :, :-1, :] - norm_disp[:, :, 1:, :]).abs()
+    gx = gx * torch.exp(-(img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, True))
+    gy = gy * torch.exp(-(img[:, :, :-1, :] - img[:, :, 1:, :]).abs().mean(1, True))
+    return gx.reshape(-1)[:b] + gy.reshape(-1)[:b]
+
+
+def smoothness_intended(norm_disp: Tensor, img: Tensor) -> Tensor:
+    """The monodepth2 per-sample edge-aware smoothness the reference meant to compute."""
+    gx = (norm_disp[:, :, :, :-1] - norm_disp[:, :, :, 1:]).abs()
+    gy = (norm_disp[:, :, :-1, :] - norm_disp[:, :, 1:, :]).abs()
+    gx = gx * torch.exp(-(img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, True))
+    gy = gy * torch.exp(-(img[:, :, :-1, :] - img[:, :, 1:, :]).abs().mean(1, True))
+    return gx.flatten(1).mean(1) + gy.flatten(1).mean(1)
+
+
+# --------------------------------------------------------------------------------------
+# The path: _process_batch / adapt / predict_pose
+# --------------------------------------------------------------------------------------
+
+class OracleConfig:
+    def __init__(self, height: int, width: int, batch_size: int, min_depth: Optional[float] = 0.1,
+                 max_depth: Optional[float] = None, disparity_smoothness: float = 1e-3,
+                 velocity_loss_scaling: Optional[float] = 0.05, learning_rate: float = 1e-4,
+                 scales: Sequence[int] = (0, 1, 2, 3), smooth_mode: str = 'reference') -> None:
+        self.height, self.width, self.batch_size = height, width, batch_size
+        self.min_depth, self.max_depth = min_depth, max_depth
+        self.disparity_smoothness = disparity_smoothness
+        self.velocity_loss_scaling = velocity_loss_scaling
+        self.learning_rate = learning_rate
+        self.scales = tuple(scales)
+        self.smooth_mode = smooth_mode
+
+
+def predict_poses(params: Dict[str, StateDict], batch: Dict[object, Tensor]) -> Dict[object, Tensor]:
+    """depth_pose_prediction.py:938-974."""
+    out = {}
+    for f in FRAME_IDS[1:]:
+        pair = (batch[('rgb_aug', f, 0)], batch[('rgb_aug', 0, 0)]) if f < 0 else \
+               (batch[('rgb_aug', 0, 0)], batch[('rgb_aug', f, 0)])
+        f4 = encoder_forward(params['pose_encoder'], torch.cat(pair, 1))[-1]
+        aa, t = pose_decoder_forward(params['pose_decoder'], f4)
+        aa, t = aa[:, 0], t[:, 0]
+        out[('axis_angle', 0, f)] = aa
+        out[('translation', 0, f)] = t
+        out[('cam_T_cam', 0, f)] = se3_from_params(aa, t, invert=f < 0)
+    return out
+
+
+def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg: OracleConfig,
+                  noise: Sequence[Tensor], sample_weights: Optional[Tensor] = None,
+                  ) -> Tuple[Dict[object, Tensor], Dict[str, Tensor]]:
+    """depth_pose_prediction.py:906-923 (+ :976-1120).  ``noise[s]`` replaces the
+    ``torch.randn`` draw of scale s (unscaled standard normal, (B,2,H,W))."""
+    h, w = cfg.height, cfg.width
+    outputs: Dict[object, Tensor] = {}
+    feats = encoder_forward(params['depth_encoder'], batch[('rgb_aug', 0, 0)])
+    outputs.update(depth_decoder_forward(params['depth_decoder'], feats, cfg.scales))
+    outputs.update(predict_poses(params, batch))
+
+    bsz = outputs[('disp', cfg.scales[0])].shape[0]
+    if sample_weights is None:
+        sample_weights = torch.ones(cfg.batch_size) / cfg.batch_size
+    k, inv_k = batch[('camera_matrix', 0)], batch[('inv_camera_matrix', 0)]
+    target = batch[('rgb', 0, 0)]
+
+    losses: Dict[str, Tensor] = {}
+    total = torch.zeros(1)
+    for si, s in enumerate(cfg.scales):
+        disp_full = F.interpolate(outputs[('disp', s)], [h, w], mode='bilinear', align_corners=False)
+        depth = disp_to_depth(disp_full, cfg.min_depth, cfg.max_depth)
+        outputs[('depth', s)] = depth
+        for f in FRAME_IDS[1:]:
+            grid = reproject_grid(depth, k, inv_k, outputs[('cam_T_cam', 0, f)])
+            outputs[('rgb', f, s)] = F.grid_sample(batch[('rgb', f, 0)], grid, mode='bilinear',
+                                                    padding_mode='border', align_corners=True)
+        reproj = torch.cat([photometric_error(outputs[('rgb', f, s)], target) for f in FRAME_IDS[1:]], 1)
+        ident = torch.cat([photometric_error(batch[('rgb', f, 0)], target) for f in FRAME_IDS[1:]], 1)
+        ident = ident + noise[si] * 0.00001
+        best, _ = torch.min(torch.cat([ident, reproj], 1), dim=1)
+        reproj_loss = (best.mean(2).mean(1) * sample_weights).sum()
+        losses[f'reprojection_loss/scale_{s}'] = reproj_loss
+
+        disp = outputs[('disp', s)]
+        norm_disp = disp / (disp.mean(2, True).mean(3, True) + 1e-7)
+        if cfg.smooth_mode == 'reference':
+            smooth = smoothness_reference_quirk(norm_disp, batch[('rgb', 0, s)])
+        else:
+            smooth = smoothness_intended(norm_disp, batch[('rgb', 0, s)])
+        smooth = (smooth * sample_weights).sum()
+        losses[f'smooth_loss/scale_{s}'] = smooth
+        reg = cfg.disparity_smoothness / (2 ** s) * smooth
+        losses[f'reg_loss/scale_{s}'] = reg
+        losses[f'depth_loss/scale_{s}'] = reproj_loss + reg
+        total = total + (reproj_loss + reg)
+    total = total / len(cfg.scales)
+
+    if cfg.velocity_loss_scaling is not None and cfg.velocity_loss_scaling > 0:
+        vel = torch.zeros(bsz)
+        for f_dist, f_pose in ((0, -1), (1, 1)):      # depth_pose_prediction.py:1133-1144
+            gt = batch[('relative_distance', f_dist)].abs().reshape(-1)
+            pred = torch.linalg.norm(outputs[('translation', 0, f_pose)], dim=-1).reshape(-1)
+            vel = vel + (pred - gt).abs().to(vel.dtype)
+        vel = cfg.velocity_loss_scaling * (vel / 2)
+        vel = (vel * sample_weights).sum()
+        losses['velocity_loss'] = vel
+        total = total + vel
+    # depth_pose_prediction.py:1101-1113: 'depth_loss' is the same tensor object as 'loss'
+    # (in-place add), so it includes the velocity term.
+    losses['depth_loss'] = total
+    losses['loss'] = total
+    if math.isnan(float(total.detach())):
+        raise RuntimeError('NaN loss')
+    return outputs, losses
+
+
+def predict_pose(params: Dict[str, StateDict], image_0: Tensor, image_1: Tensor) -> Tensor:
+    """depth_pose_prediction.py:628-664 (B=1, invert=False) -> (4,4)."""
+    with torch.no_grad():
+        f4 = encoder_forward(params['pose_encoder'], torch.cat([image_0, image_1], 1))[-1]
+        aa, t = pose_decoder_forward(params['pose_decoder'], f4)
+        return se3_from_params(aa[:, 0], t[:, 0], invert=False)[0]
+
+
+class OracleAdapter:
+    """``adapt(training_data, steps)`` of depth_pose_prediction.py:291-319 with the encoders
+    frozen (:807-827) and torch.optim.Adam over the 36 decoder tensors (:203, :311-313)."""
+
+    def __init__(self, params: Dict[str, StateDict], cfg: OracleConfig) -> None:
+        self.cfg = cfg
+        self.params = {n: {k: v.clone() for k, v in sd.items()} for n, sd in params.items()}
+        self.trainable = []
+        for net, key in trainable_keys():
+            t = self.params[net][key]
+            t.requires_grad_(True)
+            self.trainable.append(t)
+        self.optimizer = torch.optim.Adam(self.trainable, cfg.learning_rate)
+
+    def step(self, batch: Dict[object, Tensor], noise: Sequence[Tensor],
+             sample_weights: Optional[Tensor] = None):
+        outputs, losses = process_batch(self.params, batch, self.cfg, noise, sample_weights)
+        self.optimizer.zero_grad()
+        losses['loss'].backward()
+        self.optimizer.step()
+        return outputs, losses
+
+    def grads(self) -> Dict[Tuple[str, str], Tensor]:
+        return {nk: t.grad.detach().clone() for nk, t in zip(trainable_keys(), self.trainable)}
+
+
+def time_adapt_steps(batch_size: int, height: int, width: int, steps: int, warmup: int,
+                     threads: Optional[int] = None) -> Dict[str, float]:
+    """CPU baseline leg of bench.py: the oracle's adapt step (fwd+loss+bwd+Adam) timed with
+    perf_counter on the host cores.  Returns seconds per step (median, best) and threads."""
+    if threads is not None:
+        torch.set_num_threads(threads)
+    cfg = OracleConfig(height, width, batch_size)
+    adapter = OracleAdapter(make_params(0), cfg)
+    batch = make_batch(batch_size, height, width, seed=1)
+    noise = make_noise(batch_size, height, width, seed=1)
+    for _ in range(warmup):
+        adapter.step(batch, noise)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        adapter.step(batch, noise)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    return {'median_s': times[len(times) // 2], 'best_s': times[0],
+            'threads': torch.get_num_threads()}

@@ -1,0 +1,203 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference checkout does not
+travel to the GPU box):
+
+    python oracle/make_golden.py            # writes tests/golden/<case>.npz
+
+What it does: imports ``depth_pose_prediction.DepthPosePrediction`` from /root/reference
+with three stub modules for absent plotting/demosaic deps, loads the
+oracle's deterministic synthetic weights into the reference's own nn.Modules via
+``load_state_dict``, replaces the tie-break ``torch.randn`` draw by the oracle's seeded noise
+tensors, and records what the reference returns from ``_process_batch`` (outputs + 19
+losses), the 36 gradients after ``backward``, the weights after one and two ``adapt`` steps
+and ``predict_pose``.  Inputs are NOT stored: they are regenerated from seeds by
+``oracle.clslam_oracle.make_params/make_batch/make_noise``; an input checksum is stored to
+detect RNG drift.
+"""
+from __future__ import annotations
+
+import contextlib
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import clslam_oracle as orc  # noqa: E402
+
+REFERENCE = '/root/reference'
+
+CASES = {
+    # name: (B, H, W, coherent, max_depth, seed)
+    'small_b2': (2, 64, 96, False, None, 1),
+    'small_b3_coherent': (3, 64, 96, True, None, 2),
+    'small_b1_maxdepth': (1, 64, 96, True, 80.0, 3),
+    'full_b1': (1, 192, 640, False, None, 4),
+    'full_b2_coherent': (2, 192, 640, True, None, 5),
+}
+
+
+class _Stub(types.ModuleType):
+    def __getattr__(self, name):
+        if name.startswith('__'):
+            raise AttributeError(name)
+        return _Stub(name)
+
+    def __call__(self, *a, **k):
+        return None
+
+
+def import_reference():
+    sys.path.insert(0, REFERENCE)
+    for name in ('matplotlib', 'matplotlib.pyplot', 'colour_demosaicing'):
+        try:
+            __import__(name)
+        except Exception:
+            sys.modules[name] = _Stub(name)
+    from datasets.config import Dataset
+    from depth_pose_prediction import DepthPosePrediction
+    from depth_pose_prediction.config import DepthPosePrediction as Cfg
+    return Dataset, Cfg, DepthPosePrediction
+
+
+def build_reference(batch, height, width, max_depth):
+    Dataset, Cfg, DepthPosePrediction = import_reference()
+    ds = Dataset(dataset='Kitti', config_file=Path('x'), dataset_path=None, scales=(0, 1, 2, 3),
+                 height=height, width=width, frame_ids=(0, -1, 1))
+    cfg = Cfg(config_file=Path('x'), train_set=(0,), val_set=(9,), resnet_depth=18, resnet_pose=18,
+              resnet_pretrained=False, scales=(0, 1, 2, 3), learning_rate=1e-4,
+              scheduler_step_size=15, batch_size=batch, num_workers=0, num_epochs=1, min_depth=0.1,
+              max_depth=max_depth, disparity_smoothness=1e-3, velocity_loss_scaling=0.05,
+              mask_dynamic=False, log_path=Path('/tmp/clslam_golden_log'), save_frequency=-1,
+              save_val_depth=False, save_val_depth_batches=0, multiple_gpus=False, gpu_ids=None,
+              load_weights_folder=None, use_wandb=False)
+    pred = DepthPosePrediction(ds, cfg)
+    params = orc.make_params(0)
+    for name in orc.NET_NAMES:
+        pred.models[name].load_state_dict(params[name])
+    return pred, params
+
+
+@contextlib.contextmanager
+def injected_noise(noise_list):
+    """Make the reference's torch.randn(shape, device=...) (depth_pose_prediction.py:1055)
+    return the oracle's seeded tensors, in call order."""
+    real = torch.randn
+    queue = list(noise_list)
+
+    def fake(*shape, **kw):
+        t = queue.pop(0)
+        want = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+        assert tuple(t.shape) == want, (t.shape, want)
+        return t.clone()
+
+    torch.randn = fake
+    try:
+        yield
+    finally:
+        torch.randn = real
+
+
+def sample_flat(t: torch.Tensor, n: int = 64) -> np.ndarray:
+    flat = t.detach().reshape(-1)
+    idx = torch.linspace(0, flat.numel() - 1, min(n, flat.numel())).long()
+    return flat[idx].numpy().copy()
+
+
+def run_case(name, spec, out_dir: Path):
+    b, h, w, coherent, max_depth, seed = spec
+    torch.manual_seed(0)
+    pred, params = build_reference(b, h, w, max_depth)
+    batch = orc.make_batch(b, h, w, seed=seed, coherent=coherent)
+    noise = orc.make_noise(b, h, w, seed=seed)
+    rec = {}
+    rec['meta'] = np.array([b, h, w, int(coherent), -1.0 if max_depth is None else max_depth, seed],
+                           dtype=np.float64)
+    rec['input_checksum'] = np.array(
+        [float(sum(v.double().sum() for k, v in batch.items() if isinstance(k, tuple))),
+         float(sum(v.double().sum() for sd in params.values() for v in sd.values())),
+         float(sum(n.double().sum() for n in noise))], dtype=np.float64)
+
+    # ---- iteration 1: same-weights outputs, losses, gradients (adapt mode, encoders frozen)
+    pred._set_adapt(freeze_encoder=True)
+    with injected_noise(noise):
+        outputs, losses = pred._process_batch(dict(batch))
+    pred.optimizer.zero_grad()
+    losses['loss'].backward()
+    for s in range(4):
+        rec[f'disp_{s}'] = outputs[('disp', s)].detach().numpy()
+    sub = 1 if h * w <= 64 * 96 else 4
+    for s in range(4):
+        rec[f'depth_{s}_sub'] = outputs[('depth', s)].detach()[:, :, ::sub, ::sub].numpy()
+        for f in (-1, 1):
+            rec[f'rgb_{f}_{s}_sub'] = outputs[('rgb', f, s)].detach()[:, :, ::sub, ::sub].numpy()
+    rec['subsample'] = np.array([sub])
+    for f in (-1, 1):
+        rec[f'axis_angle_{f}'] = outputs[('axis_angle', 0, f)].detach().numpy()
+        rec[f'translation_{f}'] = outputs[('translation', 0, f)].detach().numpy()
+        rec[f'cam_T_cam_{f}'] = outputs[('cam_T_cam', 0, f)].detach().numpy()
+    for k, v in losses.items():
+        rec['loss:' + k] = v.detach().reshape(-1).numpy()
+    assert losses['depth_loss'] is losses['loss']            # SURVEY.md A.8 aliasing
+
+    grads = {}
+    for net in ('depth_decoder', 'pose_decoder'):
+        named = dict(pred.models[net].named_parameters())
+        for key, _, _ in orc.net_layouts()[net]:
+            g = named[key].grad
+            assert g is not None, (net, key)
+            grads[(net, key)] = g
+            rec[f'grad_norm:{net}:{key}'] = np.array([float(g.double().norm())])
+            rec[f'grad_sample:{net}:{key}'] = sample_flat(g)
+    for net in ('depth_encoder', 'pose_encoder'):
+        assert all(p.grad is None for p in pred.models[net].parameters())
+
+    # ---- Adam update 1, then a second full adapt step (weights after 1 and 2 updates)
+    pred.optimizer.step()
+    for net in ('depth_decoder', 'pose_decoder'):
+        sd = pred.models[net].state_dict()
+        for key, _, _ in orc.net_layouts()[net]:
+            delta = sd[key] - params[net][key]
+            rec[f'delta1_sample:{net}:{key}'] = sample_flat(delta)
+    with injected_noise(noise):
+        out2, losses2 = pred.adapt(dict(batch), dict(batch), steps=1)
+    rec['loss2'] = losses2['loss'].detach().reshape(-1).numpy()
+    rec['disp2_0_sub'] = out2[('disp', 0)].detach()[:, :, ::4, ::4].numpy()
+    for f in (-1, 1):
+        rec[f'translation2_{f}'] = out2[('translation', 0, f)].detach().numpy()
+        rec[f'axis_angle2_{f}'] = out2[('axis_angle', 0, f)].detach().numpy()
+
+    # ---- predict_pose with the ORIGINAL weights (loop-closure path, :628-664)
+    for n in orc.NET_NAMES:
+        pred.models[n].load_state_dict(params[n])
+    pred.is_trained = True
+    tr, cov = pred.predict_pose(batch[('rgb', 0, 0)][0], batch[('rgb', 1, 0)][0], as_numpy=True)
+    rec['predict_pose'] = tr
+    assert np.array_equal(cov, np.eye(6, dtype=cov.dtype))
+
+    # ---- the 512-d replay-buffer feature Slam.step reads (slam/slam.py:143-147)
+    pred._set_eval()
+    with torch.no_grad():
+        f4 = pred.models['depth_encoder'](batch[('rgb', 0, 0)][:1])[4]
+        rec['buffer_feature'] = f4.mean(-1).mean(-1).numpy()
+
+    out_dir.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(out_dir / f'{name}.npz', **rec)
+    print(f'{name}: loss={float(losses["loss"]):.6f} keys={len(rec)}')
+
+
+def main():
+    out_dir = ROOT / 'tests' / 'golden'
+    only = sys.argv[1:]
+    for name, spec in CASES.items():
+        if only and name not in only:
+            continue
+        run_case(name, spec, out_dir)
+
+
+if __name__ == '__main__':
+    main()
