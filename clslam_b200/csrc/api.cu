@@ -1,0 +1,41 @@
+// Error reporting and launch accounting shared by all entry points.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace clslam {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int finish_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: CUDA error %d (%s)", what, (int)e, cudaGetErrorString(e));
+    return -100 - (int)e;
+  }
+  return 0;
+}
+
+}  // namespace clslam
+
+extern "C" {
+const char* clslam_last_error(void) { return clslam::g_err; }
+int clslam_abi_version(void) { return CLSLAM_ABI_VERSION; }
+long long clslam_launch_count(void) { return clslam::g_launches.load(); }
+int clslam_set_device(int device) {
+  const cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { clslam::set_error("set_device(%d): %s", device, cudaGetErrorString(e)); return -100 - (int)e; }
+  return 0;
+}
+}

@@ -1,0 +1,418 @@
+// Convolution stack of the adaptation hot path: forward, dgrad, wgrad as implicit GEMMs over the
+// fp32 tile kernel in gemm_core.cuh.  See include/clslam_b200.h for the contract and the
+// reference call sites each entry point replaces.
+#include "conv_ops.cuh"
+#include "gemm_core.cuh"
+
+namespace clslam {
+
+// =========================== operand policies ===============================================
+
+// A of forward: rows = output pixels, k = (r,s,ci)
+struct AFwd {
+  ConvIn c;
+  int M, K;
+  template <int R> struct Frag {
+    int n[KContigMap<R>::kVec], oh[KContigMap<R>::kVec], ow[KContigMap<R>::kVec];
+    float4 r[KContigMap<R>::kVec];
+  };
+  template <int R> __device__ void init(Frag<R>& f, int m0, int tid) const {
+    using Map = KContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int m = m0 + Map::row(tid, v);
+      if (Map::valid(tid, v) && m < M) {
+        const int hw = c.ho * c.wo;
+        f.n[v] = m / hw;
+        const int rem = m - f.n[v] * hw;
+        f.oh[v] = rem / c.wo;
+        f.ow[v] = rem - f.oh[v] * c.wo;
+      } else {
+        f.n[v] = -1; f.oh[v] = 0; f.ow[v] = 0;
+      }
+    }
+  }
+  template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
+    using Map = KContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int k = k0 + Map::k4(tid, v) * 4;
+      f.r[v] = (f.n[v] >= 0 && k < k_end) ? conv_in_load(c, f.n[v], f.oh[v], f.ow[v], k) : f4zero();
+    }
+  }
+  template <int R> __device__ void commit(const Frag<R>& f, float* S, int ld, int tid) const {
+    KContigMap<R>::commit(S, ld, tid, f.r);
+  }
+};
+
+// B of forward: rows = output channels, W[co][K] K-contiguous
+struct BWeightK {
+  const float* w;
+  int N, K;
+  template <int R> struct Frag { const float* p[KContigMap<R>::kVec]; float4 r[KContigMap<R>::kVec]; };
+  template <int R> __device__ void init(Frag<R>& f, int n0, int tid) const {
+    using Map = KContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int n = n0 + Map::row(tid, v);
+      f.p[v] = (Map::valid(tid, v) && n < N) ? w + (size_t)n * K : nullptr;
+    }
+  }
+  template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
+    using Map = KContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int k = k0 + Map::k4(tid, v) * 4;
+      f.r[v] = (f.p[v] != nullptr && k < k_end) ? ld4(f.p[v] + k) : f4zero();
+    }
+  }
+  template <int R> __device__ void commit(const Frag<R>& f, float* S, int ld, int tid) const {
+    KContigMap<R>::commit(S, ld, tid, f.r);
+  }
+};
+
+// A of dgrad: rows = dX pixels, k = (r,s,co)
+struct ADgrad {
+  DgradIn g;
+  int M, K;
+  template <int R> struct Frag {
+    int n[KContigMap<R>::kVec], oh[KContigMap<R>::kVec], ow[KContigMap<R>::kVec];
+    float4 r[KContigMap<R>::kVec];
+  };
+  template <int R> __device__ void init(Frag<R>& f, int m0, int tid) const {
+    using Map = KContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int m = m0 + Map::row(tid, v);
+      if (Map::valid(tid, v) && m < M) {
+        const int hw = g.hl * g.wl;
+        f.n[v] = m / hw;
+        const int rem = m - f.n[v] * hw;
+        f.oh[v] = rem / g.wl;
+        f.ow[v] = rem - f.oh[v] * g.wl;
+      } else {
+        f.n[v] = -1; f.oh[v] = 0; f.ow[v] = 0;
+      }
+    }
+  }
+  template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
+    using Map = KContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int k = k0 + Map::k4(tid, v) * 4;
+      f.r[v] = (f.n[v] >= 0 && k < k_end) ? dgrad_in_load(g, f.n[v], f.oh[v], f.ow[v], k) : f4zero();
+    }
+  }
+  template <int R> __device__ void commit(const Frag<R>& f, float* S, int ld, int tid) const {
+    KContigMap<R>::commit(S, ld, tid, f.r);
+  }
+};
+
+// B of dgrad: B[k=(tap,co)][n=ci] = W[co][tap][ci]  (ci contiguous)
+struct BWeightDgrad {
+  const float* w;
+  int N;        // number of input channels produced (c1 for UPCAT)
+  int ci_full;  // row length of the weight tensor
+  int co, taps;
+};
+
+}  // namespace clslam
+
+// The B-of-dgrad and the wgrad operands need the tile origin at fetch time; to keep one kernel
+// signature they store it in the Frag at init().
+namespace clslam {
+
+struct BWeightDgradOp {
+  BWeightDgrad b;
+  template <int R> struct Frag { int n0; float4 r[RContigMap<R>::kVec]; };
+  template <int R> __device__ void init(Frag<R>& f, int n0, int) const { f.n0 = n0; }
+  template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
+    using Map = RContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int k = k0 + Map::kk(tid, v);
+      const int n = f.n0 + Map::r4(tid, v);
+      if (Map::valid(tid, v) && k < k_end && n < b.N) {
+        const int tap = k / b.co, o = k - tap * b.co;
+        f.r[v] = ld4(b.w + ((size_t)o * b.taps + tap) * b.ci_full + n);
+      } else {
+        f.r[v] = f4zero();
+      }
+    }
+  }
+  template <int R> __device__ void commit(const Frag<R>& f, float* S, int ld, int tid) const {
+    RContigMap<R>::commit(S, ld, tid, f.r);
+  }
+};
+
+// A of wgrad: A[m=co][k=pixel] = dz[pixel][co]   (co contiguous)
+struct AWgradDz {
+  const float* dz;
+  int co, P;
+  template <int R> struct Frag { int m0; float4 r[RContigMap<R>::kVec]; };
+  template <int R> __device__ void init(Frag<R>& f, int m0, int) const { f.m0 = m0; }
+  template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
+    using Map = RContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int p = k0 + Map::kk(tid, v);
+      const int m = f.m0 + Map::r4(tid, v);
+      f.r[v] = (Map::valid(tid, v) && p < k_end && m < co) ? ld4(dz + (size_t)p * co + m) : f4zero();
+    }
+  }
+  template <int R> __device__ void commit(const Frag<R>& f, float* S, int ld, int tid) const {
+    RContigMap<R>::commit(S, ld, tid, f.r);
+  }
+};
+
+// B of wgrad: B[k=pixel][n=(r,s,ci)] = gathered layer input
+struct BWgradIn {
+  ConvIn c;
+  int Kw;   // kh*kw*ci
+  template <int R> struct Frag { int n0; float4 r[RContigMap<R>::kVec]; };
+  template <int R> __device__ void init(Frag<R>& f, int n0, int) const { f.n0 = n0; }
+  template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
+    using Map = RContigMap<R>;
+#pragma unroll
+    for (int v = 0; v < Map::kVec; ++v) {
+      const int p = k0 + Map::kk(tid, v);
+      const int kidx = f.n0 + Map::r4(tid, v);
+      if (Map::valid(tid, v) && p < k_end && kidx < Kw) {
+        const int hw = c.ho * c.wo;
+        const int n = p / hw;
+        const int rem = p - n * hw;
+        const int oh = rem / c.wo;
+        f.r[v] = conv_in_load(c, n, oh, rem - oh * c.wo, kidx);
+      } else {
+        f.r[v] = f4zero();
+      }
+    }
+  }
+  template <int R> __device__ void commit(const Frag<R>& f, float* S, int ld, int tid) const {
+    RContigMap<R>::commit(S, ld, tid, f.r);
+  }
+};
+
+// =========================== epilogues ======================================================
+
+struct EpiFwd {
+  static constexpr bool kBias = false;
+  float* y; const float* scale; const float* shift; const float* res;
+  int N, act;
+  __device__ void store(int m, int n, const float (&v)[4]) const {
+    float o[4];
+    const size_t off = (size_t)m * N + n;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = v[j];
+      if (scale) t *= scale[n + j];
+      if (shift) t += shift[n + j];
+      if (res) t += res[off + j];
+      o[j] = act_apply(t, act);
+    }
+    *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __device__ void store_bias(int, float) const {}
+};
+
+struct EpiDgrad {
+  static constexpr bool kBias = false;
+  float* dzp; const float* y_prev; int act_prev;
+  const float* disp_dz; const float* disp_w;
+  int N;          // channels of dX
+  int h, w;       // dX spatial dims (for the dispconv term)
+  __device__ void store(int m, int n, const float (&v)[4]) const {
+    float o[4] = {v[0], v[1], v[2], v[3]};
+    if (disp_dz) {
+      const int hw = h * w;
+      const int b = m / hw, rem = m - b * hw;
+      const int hh = rem / w, ww = rem - hh * w;
+      const float4 d = dispconv_dgrad_at(disp_dz, disp_w, b, hh, ww, h, w, N, n);
+      o[0] += d.x; o[1] += d.y; o[2] += d.z; o[3] += d.w;
+    }
+    const size_t off = (size_t)m * N + n;
+    if (y_prev) {
+      const float4 yv = *reinterpret_cast<const float4*>(y_prev + off);
+      o[0] *= act_grad_from_output(yv.x, act_prev);
+      o[1] *= act_grad_from_output(yv.y, act_prev);
+      o[2] *= act_grad_from_output(yv.z, act_prev);
+      o[3] *= act_grad_from_output(yv.w, act_prev);
+    }
+    *reinterpret_cast<float4*>(dzp + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __device__ void store_bias(int, float) const {}
+};
+
+struct EpiWgrad {
+  static constexpr bool kBias = true;
+  float* dw; float* db; int N;
+  __device__ void store(int m, int n, const float (&v)[4]) const {
+    *reinterpret_cast<float4*>(dw + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  __device__ void store_bias(int m, float v) const { if (db) db[m] = v; }
+};
+
+// =========================== launch plumbing ================================================
+
+struct TilePlan { int cfg; int bm, bn; int gx, gy, splits, k_chunk; };
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0)
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// cfg: 0 = 128x64, 1 = 64x64, 2 = 128x32, 3 = 256x16, 4 = 32x64, 5 = 16x64
+static TilePlan plan_tiles(int M, int N, int K, bool allow_split) {
+  TilePlan p{};
+  if (N <= 16) { p.cfg = (M <= 16) ? 5 : 3; }
+  else if (N <= 32) { p.cfg = (M <= 32) ? 4 : 2; }
+  else if (M <= 16) p.cfg = 5;
+  else if (M <= 32) p.cfg = 4;
+  else if (M <= 64 || (long long)((M + 127) / 128) * ((N + 63) / 64) < num_sms()) p.cfg = (M <= 32) ? 4 : 1;
+  else p.cfg = 0;
+  static const int bms[6] = {128, 64, 128, 256, 32, 16};
+  static const int bns[6] = {64, 64, 32, 16, 64, 64};
+  p.bm = bms[p.cfg]; p.bn = bns[p.cfg];
+  if (p.cfg == 1 && (long long)((M + 63) / 64) * ((N + 63) / 64) * 4 < num_sms() && M <= 256) { p.cfg = 4; p.bm = 32; }
+  p.gx = (M + p.bm - 1) / p.bm;
+  p.gy = (N + p.bn - 1) / p.bn;
+  p.splits = 1;
+  const int k_tiles = (K + kBK - 1) / kBK;
+  if (allow_split) {
+    const long long tiles = (long long)p.gx * p.gy;
+    const int target = 2 * num_sms();
+    if (tiles < target && k_tiles >= 8) {
+      int s = (int)((target + tiles - 1) / tiles);
+      const int max_s = k_tiles / 4;            // at least 4 k-tiles (64 k) per split
+      if (s > max_s) s = max_s;
+      if (s > 64) s = 64;
+      if (s < 1) s = 1;
+      p.splits = s;
+    }
+  }
+  const int tiles_per_split = (k_tiles + p.splits - 1) / p.splits;
+  p.k_chunk = tiles_per_split * kBK;
+  p.splits = (k_tiles + tiles_per_split - 1) / tiles_per_split;
+  return p;
+}
+
+template <class AOp, class BOp, class Epi>
+static int launch_gemm(const TilePlan& p, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K,
+                       float* ws, long long ws_bytes, cudaStream_t st, const char* what) {
+  const bool has_bias = Epi::kBias;
+  if (p.splits > 1) {
+    const long long need = ((long long)p.splits * M * N + (has_bias ? (long long)p.splits * M : 0)) * 4;
+    if (ws == nullptr || ws_bytes < need) { set_error("%s: workspace too small (%lld < %lld)", what, ws_bytes, need); return -2; }
+  }
+  dim3 grid(p.gx, p.gy, p.splits), block(kGemmThreads);
+  switch (p.cfg) {
+    case 0: gemm_tile_kernel<128, 64, 8, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 1: gemm_tile_kernel<64, 64, 4, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 2: gemm_tile_kernel<128, 32, 4, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 3: gemm_tile_kernel<256, 16, 4, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 4: gemm_tile_kernel<32, 64, 2, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
+    default: gemm_tile_kernel<16, 64, 1, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
+  }
+  int rc = finish_launch(what);
+  if (rc) return rc;
+  if (p.splits > 1) {
+    const long long total4 = (long long)M * N / 4;
+    int blocks = (int)((total4 + 255) / 256);
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    if (blocks < 1) blocks = 1;
+    splitk_reduce_kernel<Epi><<<blocks, 256, 0, st>>>(e, ws, M, N, p.splits);
+    rc = finish_launch(what);
+  }
+  return rc;
+}
+
+static int check_desc(const clslam_conv_desc* d, const char* what) {
+  if (!d) { set_error("%s: null descriptor", what); return -1; }
+  if (d->ci % 4 != 0 || d->co % 4 != 0) { set_error("%s: channels must be multiples of 4 (ci=%d co=%d)", what, d->ci, d->co); return -1; }
+  if (d->in_mode == CLSLAM_IN_UPCAT && (d->c1 % 4 != 0 || d->c1 <= 0 || d->c1 > d->ci || d->stride != 1)) { set_error("%s: bad UPCAT", what); return -1; }
+  if (d->pad_mode == CLSLAM_PAD_REFLECT && !(d->kh == 3 && d->kw == 3 && d->pad == 1 && d->stride == 1 && d->hi >= 2 && d->wi >= 2)) { set_error("%s: reflect padding needs 3x3/s1/p1", what); return -1; }
+  const int eh = (d->hi + 2 * d->pad - d->kh) / d->stride + 1, ew = (d->wi + 2 * d->pad - d->kw) / d->stride + 1;
+  if (eh != d->ho || ew != d->wo) { set_error("%s: output size mismatch (%dx%d vs %dx%d)", what, d->ho, d->wo, eh, ew); return -1; }
+  return 0;
+}
+
+}  // namespace clslam
+
+using namespace clslam;
+
+extern "C" {
+
+long long clslam_conv_fwd_workspace_bytes(const clslam_conv_desc* d) {
+  if (check_desc(d, "conv_fwd_ws")) return -1;
+  const int M = d->n * d->ho * d->wo, N = d->co, K = d->kh * d->kw * d->ci;
+  const TilePlan p = plan_tiles(M, N, K, true);
+  return p.splits > 1 ? (long long)p.splits * M * N * 4 : 0;
+}
+
+int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const float* scale,
+                    const float* shift, const float* residual, float* y, void* workspace, long long workspace_bytes,
+                    void* stream) {
+  if (int rc = check_desc(d, "conv_fwd")) return rc;
+  const int M = d->n * d->ho * d->wo, N = d->co, K = d->kh * d->kw * d->ci;
+  AFwd a{make_conv_in(*d, x, x2), M, K};
+  BWeightK b{w, N, K};
+  EpiFwd e{y, scale, shift, residual, N, d->act};
+  const TilePlan p = plan_tiles(M, N, K, true);
+  return launch_gemm(p, a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_fwd");
+}
+
+static void dgrad_dims(const clslam_conv_desc* d, int& M, int& N, int& K, DgradIn& g, const float* dz) {
+  g.dz = dz; g.n = d->n; g.h = d->ho; g.w = d->wo; g.co = d->co;
+  g.kh = d->kh; g.kw = d->kw; g.pad = d->pad; g.pad_mode = d->pad_mode;
+  g.up = d->in_mode == CLSLAM_IN_UPCAT;
+  g.hl = g.up ? d->h1 : d->hi; g.wl = g.up ? d->w1 : d->wi;
+  M = d->n * g.hl * g.wl;
+  N = g.up ? d->c1 : d->ci;
+  K = d->kh * d->kw * d->co;
+}
+
+long long clslam_conv_dgrad_workspace_bytes(const clslam_conv_desc* d) {
+  if (check_desc(d, "conv_dgrad_ws")) return -1;
+  int M, N, K; DgradIn g; dgrad_dims(d, M, N, K, g, nullptr);
+  const TilePlan p = plan_tiles(M, N, K, true);
+  return p.splits > 1 ? (long long)p.splits * M * N * 4 : 0;
+}
+
+int clslam_conv_dgrad(const clslam_conv_desc* d, const float* dz, const float* w, const float* y_prev, int act_prev,
+                      const float* disp_dz, const float* disp_w, float* dz_prev, void* workspace,
+                      long long workspace_bytes, void* stream) {
+  if (int rc = check_desc(d, "conv_dgrad")) return rc;
+  if (d->stride != 1 || d->hi != d->ho || d->wi != d->wo) { set_error("conv_dgrad: only stride-1 'same' convolutions"); return -1; }
+  if (disp_dz && d->in_mode == CLSLAM_IN_UPCAT) { set_error("conv_dgrad: dispconv term needs a PLAIN input"); return -1; }
+  int M, N, K; DgradIn g; dgrad_dims(d, M, N, K, g, dz);
+  ADgrad a{g, M, K};
+  BWeightDgradOp b{{w, N, d->ci, d->co, d->kh * d->kw}};
+  EpiDgrad e{dz_prev, y_prev, act_prev, disp_dz, disp_w, N, g.hl, g.wl};
+  const TilePlan p = plan_tiles(M, N, K, true);
+  return launch_gemm(p, a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_dgrad");
+}
+
+long long clslam_conv_wgrad_workspace_bytes(const clslam_conv_desc* d) {
+  if (check_desc(d, "conv_wgrad_ws")) return -1;
+  const int M = d->co, N = d->kh * d->kw * d->ci, K = d->n * d->ho * d->wo;
+  const TilePlan p = plan_tiles(M, N, K, true);
+  return p.splits > 1 ? ((long long)p.splits * M * N + (long long)p.splits * M) * 4 : 0;
+}
+
+int clslam_conv_wgrad(const clslam_conv_desc* d, const float* x, const float* x2, const float* dz, float* dw, float* db,
+                      void* workspace, long long workspace_bytes, void* stream) {
+  if (int rc = check_desc(d, "conv_wgrad")) return rc;
+  const int M = d->co, N = d->kh * d->kw * d->ci, K = d->n * d->ho * d->wo;
+  AWgradDz a{dz, d->co, K};
+  BWgradIn b{make_conv_in(*d, x, x2), N};
+  EpiWgrad e{dw, db, N};
+  const TilePlan p = plan_tiles(M, N, K, true);
+  return launch_gemm(p, a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_wgrad");
+}
+
+}  // extern "C"

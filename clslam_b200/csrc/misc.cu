@@ -1,0 +1,314 @@
+// Memory-bound helpers of the conv stack: image staging, max-pool, the one-channel dispconv
+// (forward / wgrad / dgrad) and the flat Adam update.
+#include "conv_ops.cuh"
+
+namespace clslam {
+
+// ---- (x - 0.45) / 0.225, NCHW -> NHWC, channel padding ------------------------------------
+__global__ void __launch_bounds__(256)
+stage_images_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n, int hw,
+                    int c_pad) {
+  const size_t total = (size_t)n * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t img = i / hw, px = i - img * hw;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    const float* pa = a + img * 3 * hw + px;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (ld1(pa + (size_t)c * hw) - 0.45f) / 0.225f;
+    if (b) {
+      const float* pb = b + img * 3 * hw + px;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[3 + c] = (ld1(pb + (size_t)c * hw) - 0.45f) / 0.225f;
+    }
+    float4* o = reinterpret_cast<float4*>(out + i * c_pad);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    if (c_pad == 8) o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
+// ---- 3x3 / s2 / p1 max pool, NHWC ----------------------------------------------------------
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int hi, int wi, int c, int ho, int wo) {
+  const int c4 = c / 4;
+  const size_t total = (size_t)n * ho * wo * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c4) * 4;
+    size_t p = i / c4;
+    const int ow = (int)(p % wo); p /= wo;
+    const int oh = (int)(p % ho);
+    const int b = (int)(p / ho);
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 + r - 1;
+      if (ih < 0 || ih >= hi) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 + s - 1;
+        if (iw < 0 || iw >= wi) continue;
+        const float4 v = ld4(x + (((size_t)b * hi + ih) * wi + iw) * c + cc);
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<float4*>(y + i * 4) = m;
+  }
+}
+
+// ---- dispconv forward: reflect 3x3 -> 1 channel, + bias, sigmoid ---------------------------
+// G = ci/4 lanes cooperate on one pixel (each owns 4 channels), 32/G pixels per warp.
+template <int G>
+__global__ void __launch_bounds__(256)
+dispconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                    float* __restrict__ y, int n, int h, int wd) {
+  constexpr int CI = G * 4;
+  constexpr int PPW = 32 / G;
+  const int lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
+  float4 wr[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wr[t] = ld4(w + t * CI + sub * 4);
+  const float bv = ld1(bias);
+  const size_t total = (size_t)n * h * wd;
+  const size_t warp_id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp_id * PPW; base < total; base += n_warps * PPW) {
+    const size_t p = base + grp;
+    float acc = 0.f;
+    if (p < total) {
+      const int ww = (int)(p % wd);
+      const int hh = (int)((p / wd) % h);
+      const int b = (int)(p / ((size_t)wd * h));
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int ih = reflect_idx(hh + r - 1, h);
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int iw = reflect_idx(ww + s - 1, wd);
+          const float4 v = ld4(x + (((size_t)b * h + ih) * wd + iw) * CI + sub * 4);
+          const float4 k = wr[r * 3 + s];
+          acc = fmaf(v.x, k.x, acc); acc = fmaf(v.y, k.y, acc); acc = fmaf(v.z, k.z, acc); acc = fmaf(v.w, k.w, acc);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (sub == 0 && p < total) y[p] = act_apply(acc + bv, CLSLAM_ACT_SIGMOID);
+  }
+}
+
+// ---- dispconv wgrad: dW[tap][ci] = sum_p dz[p] * x_reflect[p + tap][ci], db = sum_p dz[p] ---
+// per-block partials -> ws[block][9*ci + 1]; reduced in fixed order by dispconv_wgrad_reduce.
+template <int G>
+__global__ void __launch_bounds__(256)
+dispconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ ws, int n, int h,
+                      int wd) {
+  constexpr int CI = G * 4;
+  constexpr int PPW = 32 / G;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % G, grp = lane / G;
+  float4 acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = f4zero();
+  float bsum = 0.f;
+  const size_t total = (size_t)n * h * wd;
+  const size_t warp_id = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t base = warp_id * PPW; base < total; base += n_warps * PPW) {
+    const size_t p = base + grp;
+    if (p >= total) continue;
+    const float g = ld1(dz + p);
+    const int ww = (int)(p % wd);
+    const int hh = (int)((p / wd) % h);
+    const int b = (int)(p / ((size_t)wd * h));
+    if (sub == 0) bsum += g;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = reflect_idx(hh + r - 1, h);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = reflect_idx(ww + s - 1, wd);
+        const float4 v = ld4(x + (((size_t)b * h + ih) * wd + iw) * CI + sub * 4);
+        float4& a = acc[r * 3 + s];
+        a.x = fmaf(g, v.x, a.x); a.y = fmaf(g, v.y, a.y); a.z = fmaf(g, v.z, a.z); a.w = fmaf(g, v.w, a.w);
+      }
+    }
+  }
+  // reduce the PPW pixel groups of each warp (lanes with equal `sub`)
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+      acc[t].x += __shfl_xor_sync(0xffffffffu, acc[t].x, o);
+      acc[t].y += __shfl_xor_sync(0xffffffffu, acc[t].y, o);
+      acc[t].z += __shfl_xor_sync(0xffffffffu, acc[t].z, o);
+      acc[t].w += __shfl_xor_sync(0xffffffffu, acc[t].w, o);
+    }
+  }
+  bsum = warp_sum(bsum);
+  __shared__ float red[8][9 * CI + 1];
+  if (lane < G) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      float* d = &red[warp][t * CI + lane * 4];
+      d[0] = acc[t].x; d[1] = acc[t].y; d[2] = acc[t].z; d[3] = acc[t].w;
+    }
+  }
+  if (lane == 0) red[warp][9 * CI] = bsum;
+  __syncthreads();
+  for (int i = threadIdx.x; i < 9 * CI + 1; i += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) s += red[wv][i];
+    ws[(size_t)blockIdx.x * (9 * CI + 1) + i] = s;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+dispconv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int blocks,
+                             int ci) {
+  const int len = 9 * ci + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < blocks; ++b) s += ws[(size_t)b * len + i];
+    if (i < 9 * ci) dw[i] = s; else if (db) db[0] = s;
+  }
+}
+
+// ---- dispconv dgrad when it is the only consumer: dz_prev = act'(y_prev) * dX ---------------
+__global__ void __launch_bounds__(256)
+dispconv_dgrad_act_kernel(const float* __restrict__ dz, const float* __restrict__ w, const float* __restrict__ y_prev,
+                          int act_prev, float* __restrict__ dz_prev, int n, int h, int wd, int ci) {
+  const int c4 = ci / 4;
+  const size_t total = (size_t)n * h * wd * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c4) * 4;
+    size_t p = i / c4;
+    const int ww = (int)(p % wd); p /= wd;
+    const int hh = (int)(p % h);
+    const int b = (int)(p / h);
+    float4 g = dispconv_dgrad_at(dz, w, b, hh, ww, h, wd, ci, cc);
+    const float4 yv = ld4(y_prev + i * 4);
+    g.x *= act_grad_from_output(yv.x, act_prev);
+    g.y *= act_grad_from_output(yv.y, act_prev);
+    g.z *= act_grad_from_output(yv.z, act_prev);
+    g.w *= act_grad_from_output(yv.w, act_prev);
+    *reinterpret_cast<float4*>(dz_prev + i * 4) = g;
+  }
+}
+
+// ---- Adam (torch.optim.Adam single-tensor math, no weight decay / amsgrad) ------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, double lr, double beta1, double beta2, double eps_d, int step_host,
+            const int* __restrict__ step_dev) {
+  // step_dev holds the number of updates done BEFORE this one (adam_tick_kernel bumps it after)
+  const int step = step_dev ? (*step_dev + 1) : step_host;
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  const float neg_step_size = (float)(-(lr / bc1));
+  const float bc2_sqrt = (float)sqrt(bc2);
+  const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), eps = (float)eps_d;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i];
+    float mi = m[i], vi = v[i];
+    mi = mi + w1 * (gi - mi);                            // exp_avg.lerp_(grad, 1 - beta1)
+    vi = vi * b2 + w2 * gi * gi;                         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = p[i] + neg_step_size * mi / denom;            // param.addcdiv_(exp_avg, denom, value=-step_size)
+    m[i] = mi; v[i] = vi;
+  }
+}
+__global__ void adam_tick_kernel(int* step_dev) { *step_dev += 1; }
+
+static int grid_for(size_t work, int per_block = 256, int cap = 148 * 8) {
+  size_t b = (work + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > (size_t)cap) b = cap;
+  return (int)b;
+}
+
+}  // namespace clslam
+
+using namespace clslam;
+
+extern "C" {
+
+int clslam_stage_images(const float* img_a, const float* img_b, float* out_nhwc, int n, int h, int w, int c_pad,
+                        void* stream) {
+  if (!(c_pad == 4 || c_pad == 8) || (img_b && c_pad != 8)) { set_error("stage_images: c_pad must be 4 (one image) or 8 (two)"); return -1; }
+  stage_images_kernel<<<grid_for((size_t)n * h * w), 256, 0, as_stream(stream)>>>(img_a, img_b, out_nhwc, n, h * w, c_pad);
+  return finish_launch("stage_images");
+}
+
+int clslam_maxpool3x3s2(const float* x, float* y, int n, int hi, int wi, int c, void* stream) {
+  if (c % 4) { set_error("maxpool: c %% 4 != 0"); return -1; }
+  const int ho = (hi + 2 - 3) / 2 + 1, wo = (wi + 2 - 3) / 2 + 1;
+  maxpool_kernel<<<grid_for((size_t)n * ho * wo * (c / 4)), 256, 0, as_stream(stream)>>>(x, y, n, hi, wi, c, ho, wo);
+  return finish_launch("maxpool");
+}
+
+int clslam_dispconv_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int w_, int ci,
+                        void* stream) {
+  const size_t px = (size_t)n * h * w_;
+  cudaStream_t st = as_stream(stream);
+  switch (ci) {
+    case 16: dispconv_fwd_kernel<4><<<grid_for(px, 64), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
+    case 32: dispconv_fwd_kernel<8><<<grid_for(px, 32), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
+    case 64: dispconv_fwd_kernel<16><<<grid_for(px, 16), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
+    case 128: dispconv_fwd_kernel<32><<<grid_for(px, 8), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
+    default: set_error("dispconv_fwd: ci must be 16/32/64/128 (got %d)", ci); return -1;
+  }
+  return finish_launch("dispconv_fwd");
+}
+
+static int dispconv_wgrad_blocks(int n, int h, int w_, int ci) {
+  const size_t px = (size_t)n * h * w_;
+  const int ppb = 8 * (32 / (ci / 4));          // pixels per block-iteration
+  size_t b = (px + (size_t)ppb * 16 - 1) / ((size_t)ppb * 16);
+  if (b < 1) b = 1;
+  if (b > 296) b = 296;
+  return (int)b;
+}
+
+long long clslam_dispconv_wgrad_workspace_bytes(int n, int h, int w_, int ci) {
+  return (long long)dispconv_wgrad_blocks(n, h, w_, ci) * (9 * ci + 1) * 4;
+}
+
+int clslam_dispconv_wgrad(const float* x, const float* dz, float* dw, float* db, int n, int h, int w_, int ci,
+                          void* workspace, long long workspace_bytes, void* stream) {
+  const int blocks = dispconv_wgrad_blocks(n, h, w_, ci);
+  if (!workspace || workspace_bytes < (long long)blocks * (9 * ci + 1) * 4) { set_error("dispconv_wgrad: workspace too small"); return -2; }
+  float* ws = (float*)workspace;
+  cudaStream_t st = as_stream(stream);
+  switch (ci) {
+    case 16: dispconv_wgrad_kernel<4><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
+    case 32: dispconv_wgrad_kernel<8><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
+    case 64: dispconv_wgrad_kernel<16><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
+    case 128: dispconv_wgrad_kernel<32><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
+    default: set_error("dispconv_wgrad: ci must be 16/32/64/128 (got %d)", ci); return -1;
+  }
+  if (int rc = finish_launch("dispconv_wgrad")) return rc;
+  dispconv_wgrad_reduce_kernel<<<grid_for(9 * ci + 1), 256, 0, st>>>(ws, dw, db, blocks, ci);
+  return finish_launch("dispconv_wgrad_reduce");
+}
+
+int clslam_dispconv_dgrad_act(const float* dz, const float* w, const float* y_prev, int act_prev, float* dz_prev, int n,
+                              int h, int w_, int ci, void* stream) {
+  if (ci % 4) { set_error("dispconv_dgrad: ci %% 4 != 0"); return -1; }
+  dispconv_dgrad_act_kernel<<<grid_for((size_t)n * h * w_ * (ci / 4)), 256, 0, as_stream(stream)>>>(dz, w, y_prev, act_prev,
+                                                                                                 dz_prev, n, h, w_, ci);
+  return finish_launch("dispconv_dgrad_act");
+}
+
+int clslam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr,
+                     double beta1, double beta2, double eps, int step, int* step_dev, void* stream) {
+  cudaStream_t st = as_stream(stream);
+  adam_kernel<<<grid_for((size_t)n, 256 * 4), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step,
+                                                           step_dev);
+  if (int rc = finish_launch("adam")) return rc;
+  if (step_dev) {
+    adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+    return finish_launch("adam_tick");
+  }
+  return 0;
+}
+
+}  // extern "C"

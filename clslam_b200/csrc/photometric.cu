@@ -1,0 +1,424 @@
+// Fused photometric chain: up-sample disparity -> depth -> back-project -> SE(3) -> project ->
+// border-clipped bilinear warp -> SSIM + L1 -> auto-mask min, and its hand-derived backward.
+// HBM-bound: each CTA owns a 32x16 pixel tile, stages the warped images of the tile + halo in
+// shared memory once and evaluates all 3x3 stencils from there.  See include/clslam_b200.h.
+#include "photo_ops.cuh"
+
+namespace clslam {
+
+constexpr int kPhotoThreads = 256;
+// forward: 1-pixel halo
+constexpr int kFW = kPhotoTW + 2, kFH = kPhotoTH + 2, kFN = kFW * kFH;
+// backward: 2-pixel halo for the warped image, 1-pixel halo for the SSIM coefficient maps
+constexpr int kBW = kPhotoTW + 4, kBH = kPhotoTH + 4, kBN = kBW * kBH;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// image coordinate read by padded coordinate `i` (reflection, then clamped for tiles that overhang)
+__device__ __forceinline__ int pad_coord(int i, int size) { return clampi(reflect_idx(i, size), 0, size - 1); }
+
+__device__ __forceinline__ float block_sum(float v, float* red /*[8]*/) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < kPhotoThreads / 32; ++i) s += red[i];
+  }
+  return s;   // valid on thread 0
+}
+
+// 0.85 * mean_c SSIM + 0.15 * mean_c L1 at local position (ly, lx) of the haloed tiles
+template <int LW>
+__device__ __forceinline__ float reproj_error(const float* xs /*[3][..][LW]*/, const float* ys, int plane, int ly, int lx) {
+  float ssim_sum = 0.f, l1_sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const float* xp = xs + c * plane;
+    const float* yp = ys + c * plane;
+    float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const float xv = xp[(ly + dy) * LW + lx + dx], yv = yp[(ly + dy) * LW + lx + dx];
+        sx += xv; sy += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
+      }
+    ssim_sum += clamp01(ssim_stats(sx, sy, sxx, syy, sxy).val);
+    l1_sum += fabsf(yp[ly * LW + lx] - xp[ly * LW + lx]);
+  }
+  return 0.85f * (ssim_sum / 3.f) + 0.15f * (l1_sum / 3.f);
+}
+
+// ---- identity (auto-mask) candidates -------------------------------------------------------
+__global__ void __launch_bounds__(kPhotoThreads)
+photo_identity_kernel(const float* __restrict__ target, const float* __restrict__ sources, float* __restrict__ identity,
+                      int b, int h, int w, int tiles_x) {
+  __shared__ float tg[3 * kFN];
+  __shared__ float sr[3 * kFN];
+  const int bb = blockIdx.y;
+  const int tx0 = (blockIdx.x % tiles_x) * kPhotoTW, ty0 = (blockIdx.x / tiles_x) * kPhotoTH;
+  const size_t hw = (size_t)h * w;
+  for (int i = threadIdx.x; i < kFN; i += kPhotoThreads) {
+    const int ly = i / kFW, lx = i - ly * kFW;
+    const size_t off = (size_t)pad_coord(ty0 + ly - 1, h) * w + pad_coord(tx0 + lx - 1, w);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tg[c * kFN + i] = ld1(target + ((size_t)bb * 3 + c) * hw + off);
+  }
+  for (int f = 0; f < 2; ++f) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFN; i += kPhotoThreads) {
+      const int ly = i / kFW, lx = i - ly * kFW;
+      const size_t off = (size_t)pad_coord(ty0 + ly - 1, h) * w + pad_coord(tx0 + lx - 1, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) sr[c * kFN + i] = ld1(sources + (((size_t)f * b + bb) * 3 + c) * hw + off);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int lx = threadIdx.x % kPhotoTW, ly = (threadIdx.x / kPhotoTW) * 2 + j;
+      const int x = tx0 + lx, y = ty0 + ly;
+      if (x < w && y < h) identity[((size_t)bb * 2 + f) * hw + (size_t)y * w + x] = reproj_error<kFW>(sr, tg, kFN, ly + 1, lx + 1);
+    }
+  }
+}
+
+// ---- forward --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPhotoThreads)
+photo_fwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
+  __shared__ float tg[3 * kFN];
+  __shared__ float wx[2 * 3 * kFN];
+  __shared__ float red[8];
+  __shared__ float geo[16 + 24];           // inv_K (4x4), proj (2 x 3x4)
+  const int s = blockIdx.y / a.b, bb = blockIdx.y % a.b;
+  const int h = a.h, w = a.w, hs = h >> s, ws = w >> s;
+  const int tile = blockIdx.x;
+  const int tx0 = (tile % tiles_x) * kPhotoTW, ty0 = (tile / tiles_x) * kPhotoTH;
+  const size_t hw = (size_t)h * w;
+  if (threadIdx.x < 16) geo[threadIdx.x] = a.inv_k[bb * 16 + threadIdx.x];
+  else if (threadIdx.x < 40) {
+    const int i = threadIdx.x - 16, f = i / 12;
+    geo[threadIdx.x] = a.proj[((size_t)f * a.b + bb) * 12 + (i - f * 12)];
+  }
+  __syncthreads();
+  const float* disp_b = a.disp[s] + (size_t)bb * hs * ws;
+  float* depth_out = a.depth[s];
+  float* warped_out = a.warped[s];
+  for (int i = threadIdx.x; i < kFN; i += kPhotoThreads) {
+    const int ly = i / kFW, lx = i - ly * kFW;
+    const int py = ty0 + ly - 1, px = tx0 + lx - 1;
+    const int y = pad_coord(py, h), x = pad_coord(px, w);
+    const size_t off = (size_t)y * w + x;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tg[c * kFN + i] = ld1(a.target + ((size_t)bb * 3 + c) * hw + off);
+    const float d = disp_upsample(disp_b, hs, ws, h, w, y, x);
+    const float depth = depth_from_disp(d, a.depth_mode, a.min_depth, a.max_depth);
+    const bool interior = (py == y) && (px == x) && ly >= 1 && ly <= kPhotoTH && lx >= 1 && lx <= kPhotoTW;
+    if (interior && depth_out) depth_out[(size_t)bb * hw + off] = depth;
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      WarpGeom g;
+      warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
+      const Taps t = make_taps(g.ix, g.iy, h, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float v = sample_plane(a.sources + (((size_t)f * a.b + bb) * 3 + c) * hw, w, t);
+        wx[(f * 3 + c) * kFN + i] = v;
+        if (interior && warped_out) warped_out[(((size_t)f * a.b + bb) * 3 + c) * hw + off] = v;
+      }
+    }
+  }
+  __syncthreads();
+  float local = 0.f;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int lx = threadIdx.x % kPhotoTW, ly = (threadIdx.x / kPhotoTW) * 2 + j;
+    const int x = tx0 + lx, y = ty0 + ly;
+    if (x < w && y < h) {
+      const size_t off = (size_t)y * w + x;
+      float best = ld1(a.identity + ((size_t)bb * 2 + 0) * hw + off);
+      float c1 = ld1(a.identity + ((size_t)bb * 2 + 1) * hw + off);
+      if (a.noise[s]) {
+        best += ld1(a.noise[s] + ((size_t)bb * 2 + 0) * hw + off) * 0.00001f;
+        c1 += ld1(a.noise[s] + ((size_t)bb * 2 + 1) * hw + off) * 0.00001f;
+      }
+      int arg = 0;
+      if (c1 < best) { best = c1; arg = 1; }
+      const float r0 = reproj_error<kFW>(wx, tg, kFN, ly + 1, lx + 1);
+      if (r0 < best) { best = r0; arg = 2; }
+      const float r1 = reproj_error<kFW>(wx + 3 * kFN, tg, kFN, ly + 1, lx + 1);
+      if (r1 < best) { best = r1; arg = 3; }
+      a.argmin[s][(size_t)bb * hw + off] = (unsigned char)arg;
+      local += best;
+    }
+  }
+  const float total = block_sum(local, red);
+  if (threadIdx.x == 0) a.loss_partials[((size_t)s * a.b + bb) * tiles + tile] = total;
+}
+
+// ---- backward -------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPhotoThreads)
+photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
+  constexpr int kCW = kFW, kCN = kFN;      // coefficient maps cover tile + 1
+  __shared__ float tg[3 * kBN];
+  __shared__ float wx[3 * kBN];
+  __shared__ float coef[9 * kCN];          // [c][alpha,beta,gamma][pos]
+  __shared__ float red[8 * 12];
+  __shared__ float geo[16 + 24];
+  const int s = blockIdx.y / a.b, bb = blockIdx.y % a.b;
+  const int h = a.h, w = a.w, hs = h >> s, ws = w >> s;
+  const int tile = blockIdx.x;
+  const int tx0 = (tile % tiles_x) * kPhotoTW, ty0 = (tile / tiles_x) * kPhotoTH;
+  const size_t hw = (size_t)h * w;
+  if (threadIdx.x < 16) geo[threadIdx.x] = a.inv_k[bb * 16 + threadIdx.x];
+  else if (threadIdx.x < 40) {
+    const int i = threadIdx.x - 16, f = i / 12;
+    geo[threadIdx.x] = a.proj[((size_t)f * a.b + bb) * 12 + (i - f * 12)];
+  }
+  const float* disp_b = a.disp[s] + (size_t)bb * hs * ws;
+  const unsigned char* amin = a.argmin[s] + (size_t)bb * hw;
+  // d(loss)/d(min-reprojection value at a pixel): w_b / (n_scales * H * W)
+  const float g0 = ld1(a.sample_w + bb) / ((float)a.n_scales * (float)h * (float)w);
+
+  for (int i = threadIdx.x; i < kBN; i += kPhotoThreads) {
+    const int ly = i / kBW, lx = i - ly * kBW;
+    const size_t off = (size_t)pad_coord(ty0 + ly - 2, h) * w + pad_coord(tx0 + lx - 2, w);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) tg[c * kBN + i] = ld1(a.target + ((size_t)bb * 3 + c) * hw + off);
+  }
+  __syncthreads();
+
+  float ddepth[2] = {0.f, 0.f};
+  float dval[2] = {0.f, 0.f}, depthv[2] = {0.f, 0.f};
+  for (int f = 0; f < 2; ++f) {
+    const float* src = a.sources + ((size_t)f * a.b + bb) * 3 * hw;
+    // phase 1: warped source on tile + 2
+    for (int i = threadIdx.x; i < kBN; i += kPhotoThreads) {
+      const int ly = i / kBW, lx = i - ly * kBW;
+      const int y = pad_coord(ty0 + ly - 2, h), x = pad_coord(tx0 + lx - 2, w);
+      const float d = disp_upsample(disp_b, hs, ws, h, w, y, x);
+      const float depth = depth_from_disp(d, a.depth_mode, a.min_depth, a.max_depth);
+      WarpGeom g;
+      warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
+      const Taps t = make_taps(g.ix, g.iy, h, w);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) wx[c * kBN + i] = sample_plane(src + (size_t)c * hw, w, t);
+    }
+    __syncthreads();
+    // phase 2: SSIM gradient coefficients at window centres p on tile + 1 (in-image, selected by argmin)
+    for (int i = threadIdx.x; i < kCN; i += kPhotoThreads) {
+      const int ly = i / kCW, lx = i - ly * kCW;
+      const int py = ty0 + ly - 1, px = tx0 + lx - 1;
+      const bool on = py >= 0 && py < h && px >= 0 && px < w && amin[(size_t)py * w + px] == 2 + f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float al = 0.f, be = 0.f, ga = 0.f;
+        if (on) {
+          const float* xp = wx + c * kBN;
+          const float* yp = tg + c * kBN;
+          float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
+#pragma unroll
+          for (int dy = 0; dy <= 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx <= 2; ++dx) {
+              const float xv = xp[(ly + dy) * kBW + lx + dx], yv = yp[(ly + dy) * kBW + lx + dx];
+              sx += xv; sy += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
+            }
+          const SsimStats st = ssim_stats(sx, sy, sxx, syy, sxy);
+          if (st.val >= 0.f && st.val <= 1.f) {          // clamp backward passes inside [0, 1]
+            const float gm = g0 * (0.85f / 3.f);
+            const float inv9d = 1.f / (9.f * st.d);
+            const float nd = st.n / st.d;
+            al = -gm * inv9d * (st.mu_y * (st.a2 - st.a1) - nd * st.mu_x * (st.b2 - st.b1));
+            be = gm * inv9d * nd * st.b1;
+            ga = -gm * inv9d * st.a1;
+          }
+        }
+        coef[(c * 3 + 0) * kCN + i] = al;
+        coef[(c * 3 + 1) * kCN + i] = be;
+        coef[(c * 3 + 2) * kCN + i] = ga;
+      }
+    }
+    __syncthreads();
+    // phase 3: gradient wrt the warped pixel -> sampling coordinates -> depth and projection
+    float dP[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) dP[k] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int lx = threadIdx.x % kPhotoTW, ly = (threadIdx.x / kPhotoTW) * 2 + j;
+      const int x = tx0 + lx, y = ty0 + ly;
+      if (x >= w || y >= h) continue;
+      const float d = disp_upsample(disp_b, hs, ws, h, w, y, x);
+      const float depth = depth_from_disp(d, a.depth_mode, a.min_depth, a.max_depth);
+      dval[j] = d; depthv[j] = depth;
+      WarpGeom g;
+      warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
+      const Taps t = make_taps(g.ix, g.iy, h, w);
+      const bool sel = amin[(size_t)y * w + x] == 2 + f;
+      float gix = 0.f, giy = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float xq = wx[c * kBN + (ly + 2) * kBW + lx + 2];
+        const float yq = tg[c * kBN + (ly + 2) * kBW + lx + 2];
+        float al = 0.f, be = 0.f, ga = 0.f;
+#pragma unroll
+        for (int dy = -1; dy <= 1; ++dy) {
+          const float wy = refl_box_weight(y, y + dy, h);
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const float wgt = wy * refl_box_weight(x, x + dx, w);
+            const int ci = (ly + 1 + dy) * kCW + lx + 1 + dx;
+            al += wgt * coef[(c * 3 + 0) * kCN + ci];
+            be += wgt * coef[(c * 3 + 1) * kCN + ci];
+            ga += wgt * coef[(c * 3 + 2) * kCN + ci];
+          }
+        }
+        float gxc = al + be * xq + ga * yq;
+        if (sel) {
+          const float diff = yq - xq;                     // |target - pred|: d/dpred = -sgn(target - pred)
+          gxc -= g0 * (0.15f / 3.f) * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
+        }
+        float dix, diy;
+        sample_plane_grad(src + (size_t)c * hw, w, t, dix, diy);
+        gix += gxc * dix;
+        giy += gxc * diy;
+      }
+      const float dpx = gix * g.mx, dpy = giy * g.my;   // (W-1)/2 * 2/(W-1) cancel
+      float dp[3];
+      dp[0] = dpx / g.z;
+      dp[1] = dpy / g.z;
+      dp[2] = -(dpx * g.px + dpy * g.py) / g.z;
+      const float* P = geo + 16 + f * 12;
+      float dd = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) dd += (P[0 * 4 + c] * dp[0] + P[1 * 4 + c] * dp[1] + P[2 * 4 + c] * dp[2]) * g.ray[c];
+      ddepth[j] += dd;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        dP[r * 4 + 0] += dp[r] * g.X[0];
+        dP[r * 4 + 1] += dp[r] * g.X[1];
+        dP[r * 4 + 2] += dp[r] * g.X[2];
+        dP[r * 4 + 3] += dp[r];
+      }
+    }
+    // block-reduce the 12 projection gradients of this frame
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const float v = warp_sum(dP[k]);
+      if (lane == 0) red[warp * 12 + k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 12) {
+      float sum = 0.f;
+#pragma unroll
+      for (int wv = 0; wv < 8; ++wv) sum += red[wv * 12 + threadIdx.x];
+      a.dproj_partials[((((size_t)s * tiles + tile) * 2 + f) * a.b + bb) * 12 + threadIdx.x] = sum;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int lx = threadIdx.x % kPhotoTW, ly = (threadIdx.x / kPhotoTW) * 2 + j;
+    const int x = tx0 + lx, y = ty0 + ly;
+    if (x < w && y < h)
+      a.ddisp_full[s][(size_t)bb * hw + (size_t)y * w + x] =
+          ddepth[j] * depth_grad(dval[j], depthv[j], a.depth_mode, a.min_depth, a.max_depth);
+  }
+}
+
+// ---- transpose of the bilinear up-sampling + smoothness terms + sigmoid' -------------------
+__global__ void __launch_bounds__(256)
+disp_grad_kernel(const float* __restrict__ ddisp_full, const float* __restrict__ disp, const float* __restrict__ smooth_grad,
+                 int b_global, int has_sample0, int b, int h, int w, int scale, float* __restrict__ dz) {
+  const int hs = h >> scale, ws = w >> scale;
+  const int f = 1 << scale;
+  const size_t total = (size_t)b * hs * ws;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % ws);
+    const int r = (int)((i / ws) % hs);
+    const int bb = (int)(i / ((size_t)ws * hs));
+    const float* src = ddisp_full + (size_t)bb * h * w;
+    float g = 0.f;
+    if (scale == 0) {
+      g = src[(size_t)r * w + j];
+    } else {
+      const int y_lo = max(0, f * (r - 1)), y_hi = min(h, f * (r + 2));
+      const int x_lo = max(0, f * (j - 1)), x_hi = min(w, f * (j + 2));
+      for (int y = y_lo; y < y_hi; ++y) {
+        const UpCoef cy = up_coef(y, hs, h);
+        const float wy = (cy.i0 == r ? cy.l0 : 0.f) + (cy.i1 == r ? cy.l1 : 0.f);
+        if (wy == 0.f) continue;
+        float row = 0.f;
+        for (int x = x_lo; x < x_hi; ++x) {
+          const UpCoef cx = up_coef(x, ws, w);
+          const float wxv = (cx.i0 == j ? cx.l0 : 0.f) + (cx.i1 == j ? cx.l1 : 0.f);
+          if (wxv != 0.f) row += wxv * src[(size_t)y * w + x];
+        }
+        g += wy * row;
+      }
+    }
+    if (has_sample0 && bb == 0 && smooth_grad) {
+      const float* sg = smooth_grad + (size_t)scale * (2 * (b_global + 1) + 1);
+      g += sg[2 * (b_global + 1)];
+      if (r < 2 && j <= b_global) g += sg[r * (b_global + 1) + j];
+    }
+    const float dv = disp[i];
+    dz[i] = g * dv * (1.f - dv);
+  }
+}
+
+}  // namespace clslam
+
+using namespace clslam;
+
+extern "C" {
+
+int clslam_photo_tiles(int h, int w) { return ((w + kPhotoTW - 1) / kPhotoTW) * ((h + kPhotoTH - 1) / kPhotoTH); }
+
+int clslam_photo_identity(const float* target, const float* sources, float* identity, int b, int h, int w, void* stream) {
+  if (h < 2 || w < 2) { set_error("photo_identity: image too small"); return -1; }
+  const int tiles_x = (w + kPhotoTW - 1) / kPhotoTW;
+  dim3 grid(clslam_photo_tiles(h, w), b);
+  photo_identity_kernel<<<grid, kPhotoThreads, 0, as_stream(stream)>>>(target, sources, identity, b, h, w, tiles_x);
+  return finish_launch("photo_identity");
+}
+
+static int check_photo(const clslam_photo_args* a, const char* what) {
+  if (!a) { set_error("%s: null args", what); return -1; }
+  if (a->n_scales < 1 || a->n_scales > 4 || a->b < 1 || a->h < 2 || a->w < 2) { set_error("%s: bad dims", what); return -1; }
+  if ((a->h % (1 << (a->n_scales - 1))) || (a->w % (1 << (a->n_scales - 1)))) { set_error("%s: h, w must be divisible by 2^(n_scales-1)", what); return -1; }
+  if ((long long)a->b * a->n_scales > 65535) { set_error("%s: b * n_scales > 65535", what); return -1; }
+  return 0;
+}
+
+int clslam_photo_fwd(const clslam_photo_args* a, void* stream) {
+  if (int rc = check_photo(a, "photo_fwd")) return rc;
+  const int tiles_x = (a->w + kPhotoTW - 1) / kPhotoTW, tiles = clslam_photo_tiles(a->h, a->w);
+  dim3 grid(tiles, a->b * a->n_scales);
+  photo_fwd_kernel<<<grid, kPhotoThreads, 0, as_stream(stream)>>>(*a, tiles_x, tiles);
+  return finish_launch("photo_fwd");
+}
+
+int clslam_photo_bwd(const clslam_photo_args* a, void* stream) {
+  if (int rc = check_photo(a, "photo_bwd")) return rc;
+  const int tiles_x = (a->w + kPhotoTW - 1) / kPhotoTW, tiles = clslam_photo_tiles(a->h, a->w);
+  dim3 grid(tiles, a->b * a->n_scales);
+  photo_bwd_kernel<<<grid, kPhotoThreads, 0, as_stream(stream)>>>(*a, tiles_x, tiles);
+  return finish_launch("photo_bwd");
+}
+
+int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* smooth_grad, int b_global, int has_sample0,
+                     int b, int h, int w, int scale, float* dz_disp, void* stream) {
+  const size_t total = (size_t)b * (h >> scale) * (w >> scale);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  disp_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ddisp_full, disp, smooth_grad, b_global, has_sample0, b, h, w, scale,
+                                                         dz_disp);
+  return finish_launch("disp_grad");
+}
+
+}  // extern "C"

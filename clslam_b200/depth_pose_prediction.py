@@ -1,0 +1,576 @@
+"""Drop-in ``DepthPosePrediction`` for CL-SLAM's online adaptation, running on hand-written
+sm_100a CUDA through the C ABI in ``include/clslam_b200.h``.
+
+Mirrors the surface of ``depth_pose_prediction/depth_pose_prediction.py:38`` that
+``slam/slam.py`` uses: constructor ``(dataset_config, config, use_online)``,
+``adapt`` (:291), ``_process_batch`` (:906), ``predict_pose`` (:628), ``load_model`` (:705),
+``save_model`` (:669), ``_set_eval`` / ``_set_adapt`` (:802, :807), attributes ``models``,
+``device``, ``min_depth``, ``max_depth``, the batch-dict schema and the 19 loss keys
+(SURVEY.md App. C).  There is no CPU / PyTorch fallback: compute methods raise when CUDA or the
+extension is missing.
+"""
+from __future__ import annotations
+
+import shutil
+import warnings
+from pathlib import Path
+from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor, nn, optim
+
+from . import _lib as L
+from .engine import AdaptEngine, EncoderRunner, Plan, PreparedEncoder, _p
+from .networks import DepthDecoder, FlatParams, PoseDecoder, ResnetEncoder
+from .sharding import global_sample_weights, shard_range
+
+LOSS_SLOTS = {'reprojection_loss': 0, 'smooth_loss': 4, 'reg_loss': 8, 'depth_loss': 12}
+
+
+class FlatAdam:
+    """torch.optim.Adam-shaped facade (state_dict format, param_groups, LR scheduler target) over
+    the fused flat-buffer Adam kernel.  The wrapped torch optimiser is never stepped; it only
+    carries hyper-parameters and the (de)serialisation format of depth_pose_prediction.py:691-697."""
+
+    def __init__(self, all_params: List[nn.Parameter], lr: float, flat: FlatParams, trainable: List[nn.Parameter]):
+        self.torch_optimizer = optim.Adam(all_params, lr)
+        self.flat = flat
+        self.trainable = trainable      # the 36 decoder tensors, in flat-buffer order (weight, bias, ...)
+        self._spans = []                # (param, offset, numel, is_weight, info)
+        for (net, path), info in flat.index.items():
+            self._spans.append((info, True))
+            self._spans.append((info, False))
+
+    @property
+    def param_groups(self):
+        return self.torch_optimizer.param_groups
+
+    def _state_views(self, buf: Tensor):
+        out = []
+        for info, is_w in self._spans:
+            if is_w:
+                out.append(FlatParams.view_weight(buf, info))
+            else:
+                out.append(buf[info['b_off']:info['b_off'] + info['co']])
+        return out
+
+    def state_dict(self):
+        steps = int(self.flat.step_dev.item())
+        st = self.torch_optimizer.state
+        if steps > 0:
+            for p, m, v in zip(self.trainable, self._state_views(self.flat.exp_avg), self._state_views(self.flat.exp_avg_sq)):
+                st[p] = {'step': torch.tensor(float(steps)), 'exp_avg': m.detach().clone().contiguous(),
+                         'exp_avg_sq': v.detach().clone().contiguous()}
+        return self.torch_optimizer.state_dict()
+
+    def load_state_dict(self, sd) -> None:
+        self.torch_optimizer.load_state_dict(sd)
+        st = self.torch_optimizer.state
+        steps = 0
+        with torch.no_grad():
+            for p, m, v in zip(self.trainable, self._state_views(self.flat.exp_avg), self._state_views(self.flat.exp_avg_sq)):
+                if p in st and 'exp_avg' in st[p]:
+                    m.copy_(st[p]['exp_avg']); v.copy_(st[p]['exp_avg_sq'])
+                    steps = max(steps, int(float(st[p]['step'])))
+            self.flat.step_dev.fill_(steps)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.flat.grads.zero_()
+
+
+class DepthPosePrediction:
+    def __init__(self, dataset_config, config, use_online: bool = False, *, data_parallel: bool = False,
+                 use_cuda_graph: bool = True, emit_outputs: bool = True, device: Optional[torch.device] = None):
+        # Parameters (same names as the reference, :41-68) --------------------------------------
+        self.config_file = config.config_file
+        self.dataset_type = dataset_config.dataset
+        self.dataset_path = dataset_config.dataset_path
+        self.height = dataset_config.height
+        self.width = dataset_config.width
+        self.train_set = config.train_set
+        self.val_set = config.val_set
+        self.resnet_depth = config.resnet_depth
+        self.resnet_pose = config.resnet_pose
+        self.resnet_pretrained = config.resnet_pretrained
+        self.scales = tuple(config.scales)
+        self.learning_rate = config.learning_rate
+        self.scheduler_step_size = config.scheduler_step_size
+        self.batch_size = config.batch_size
+        self.num_workers = config.num_workers
+        self.num_epochs = config.num_epochs
+        self.min_depth = config.min_depth
+        self.max_depth = config.max_depth
+        self.disparity_smoothness = config.disparity_smoothness
+        self.velocity_loss_scaling = config.velocity_loss_scaling
+        self.mask_dynamic = config.mask_dynamic
+        self.log_path = config.log_path
+        self.save_frequency = config.save_frequency
+        self.save_val_depth = config.save_val_depth
+        self.save_val_depth_batches = config.save_val_depth_batches
+        self.multiple_gpus = config.multiple_gpus
+        self.gpu_ids = config.gpu_ids
+        self.load_weights_folder = config.load_weights_folder
+        self.use_wandb = False
+        self.is_trained = False
+        self.frame_ids = (0, -1, 1)          # :75
+        self.num_pose_frames = 2
+        self.epoch = 0
+
+        self._validate_sets(dataset_config)
+        if use_online:
+            raise NotImplementedError('use_online=True (second network copy, :139-152) is SURVEY.md 8(f) row 4')
+        if self.mask_dynamic:
+            raise NotImplementedError('mask_dynamic=True (pre-training masks, :1064-1068) is SURVEY.md 8(f) row 3')
+        if self.multiple_gpus:
+            raise ValueError('nn.DataParallel (multiple_gpus) is replaced by data_parallel=True: one process per '
+                             'GPU under torch.distributed (SURVEY.md 8e)')
+        if self.load_weights_folder is not None:
+            self.load_weights_folder = Path(self.load_weights_folder).absolute()
+        self.use_online = False
+        self.online_models: Dict[str, nn.Module] = {}
+        self.online_optimizer = None
+
+        # Device / process group ------------------------------------------------------------------
+        self.rank, self.world = 0, 1
+        if data_parallel:
+            import torch.distributed as dist
+            if not dist.is_initialized():
+                raise RuntimeError('data_parallel=True needs an initialised torch.distributed process group')
+            self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.data_parallel = data_parallel
+        if device is not None:
+            self.device = torch.device(device)
+        elif torch.cuda.is_available():
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        else:
+            self.device = torch.device('cpu')      # parameter containers / checkpoints only; compute raises
+        self.use_cuda_graph = use_cuda_graph
+        self.emit_outputs = emit_outputs
+
+        # Networks (parameter containers; arithmetic lives in the CUDA kernels) --------------------
+        self.models: Dict[str, nn.Module] = {}
+        self.models['depth_encoder'] = ResnetEncoder(self.resnet_depth, self.resnet_pretrained, device=self.device)
+        self.models['depth_decoder'] = DepthDecoder(self.models['depth_encoder'].num_ch_encoder, self.scales)
+        self.models['pose_encoder'] = ResnetEncoder(self.resnet_pose, self.resnet_pretrained, self.num_pose_frames,
+                                                    device=self.device)
+        self.models['pose_decoder'] = PoseDecoder()
+        self._flat = FlatParams(self.models['depth_decoder'], self.models['pose_decoder'], self.device)
+        self.models['depth_encoder'].bind(lambda x: self._run_encoder('depth_encoder', x))
+        self.models['pose_encoder'].bind(lambda x: self._run_encoder('pose_encoder', x))
+
+        self.parameters_to_train: List[nn.Parameter] = []
+        for m in self.models.values():
+            self.parameters_to_train += list(m.parameters())
+        trainable = list(self.models['depth_decoder'].parameters()) + list(self.models['pose_decoder'].parameters())
+        self.optimizer = FlatAdam(self.parameters_to_train, self.learning_rate, self._flat, trainable)
+        self.lr_scheduler = optim.lr_scheduler.StepLR(self.optimizer.torch_optimizer, self.scheduler_step_size, 0.1)
+        self.train_loader, self.val_loader = None, None
+
+        # Runtime state ---------------------------------------------------------------------------
+        self._prep: Dict[str, PreparedEncoder] = {}
+        self._engines: Dict[int, AdaptEngine] = {}
+        self._enc_runners: Dict[Tuple[str, int, int, int], EncoderRunner] = {}
+        self._pose_runner = None
+        self._graphs: Dict[Tuple, Any] = {}
+        self._steps_run: Dict[int, int] = {}
+        self.noise_provider: Optional[Callable[[int, Tuple[int, ...]], Tensor]] = None
+        self.stage_all_inputs = True          # move every dict value to the device like :916-917
+        self._mode = 'eval'
+
+    # ------------------------------------------------------------------------------------------
+    def _validate_sets(self, dataset_config) -> None:
+        """train_set / val_set normalisation and checks of :85-110 (ValueError on bad config)."""
+        if isinstance(self.train_set, list):
+            self.train_set = tuple(self.train_set)
+        if isinstance(self.val_set, list):
+            self.val_set = tuple(self.val_set)
+        kind = dataset_config.dataset
+        if kind == 'Kitti':
+            if isinstance(self.val_set, int):
+                self.val_set = (self.val_set,)
+            if isinstance(self.train_set, str):
+                if self.train_set != 'all':
+                    raise ValueError('train_set of KITTI only accepts these strings: ["all"]')
+                self.train_set = tuple(s for s in range(11) if s not in self.val_set and s != 3)
+            elif isinstance(self.train_set, int):
+                self.train_set = (self.train_set,)
+            want = int
+        elif kind in ('Cityscapes', 'RobotCar'):
+            if isinstance(self.train_set, str):
+                self.train_set = (self.train_set,)
+            if isinstance(self.val_set, str):
+                self.val_set = (self.val_set,)
+            want = str
+        else:
+            return
+        for name, value in (('train_set', self.train_set), ('val_set', self.val_set)):
+            if not (isinstance(value, tuple) and len(value) > 0 and isinstance(value[0], want)):
+                raise ValueError(f'Passed invalid value for {name}')
+        if self.gpu_ids is not None and len(self.gpu_ids) > 1:
+            raise ValueError('Passed multiple GPU IDs without activating multi-GPU support.')
+
+    def _require_cuda(self) -> None:
+        if self.device.type != 'cuda':
+            raise RuntimeError('clslam_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        L.load()
+
+    # ------------------------------------------------------------------------------------------
+    # modes (:797-827)
+    def _set_train(self) -> None:
+        raise NotImplementedError('training-mode BatchNorm / encoder backward is SURVEY.md 8(f) row 3; '
+                                  'use adapt() (encoders frozen)')
+
+    def _set_eval(self) -> None:
+        for m in self.models.values():
+            m.eval()
+        self._mode = 'eval'
+
+    def _set_adapt(self, freeze_encoder: bool = True) -> None:
+        if not freeze_encoder:
+            raise NotImplementedError('freeze_encoder=False is SURVEY.md 8(f) row 3')
+        for model_name, model in self.models.items():
+            model.eval()
+            for name, param in model.named_parameters():
+                if name.find('bn') != -1 or 'encoder' in model_name:
+                    param.requires_grad = False
+        self._mode = 'adapt'
+
+    # ------------------------------------------------------------------------------------------
+    # engines
+    def _prepared(self, net: str) -> PreparedEncoder:
+        enc = self.models[net]
+        prep = self._prep.get(net)
+        if prep is None or prep.version != enc.version:
+            prep = PreparedEncoder(enc, self.device)
+            self._prep[net] = prep
+            # plans hold raw pointers into the prepared tensors: rebuild them
+            self._engines.clear(); self._enc_runners.clear(); self._graphs.clear(); self._pose_runner = None
+        return prep
+
+    def refresh_encoders(self) -> None:
+        """Call after modifying encoder weights in place (load_state_dict does it automatically)."""
+        for net in ('depth_encoder', 'pose_encoder'):
+            self.models[net].version += 1
+
+    def _engine(self, batch: int) -> AdaptEngine:
+        self._require_cuda()
+        dp, pp = self._prepared('depth_encoder'), self._prepared('pose_encoder')
+        eng = self._engines.get(batch)
+        if eng is None:
+            L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
+            if self.world > 1:
+                b_global, has0 = batch * self.world, self.rank == 0
+            else:
+                b_global, has0 = batch, True
+            eng = AdaptEngine(batch=batch, height=self.height, width=self.width, batch_global=b_global, has_sample0=has0,
+                              depth_prep=dp, pose_prep=pp, flat=self._flat, min_depth=self.min_depth,
+                              max_depth=self.max_depth, disparity_smoothness=self.disparity_smoothness,
+                              velocity_loss_scaling=self.velocity_loss_scaling, device=self.device,
+                              emit_outputs=self.emit_outputs)
+            self._engines[batch] = eng
+        return eng
+
+    def _run_encoder(self, net: str, x: Tensor) -> List[Tensor]:
+        """``models['depth_encoder'](image)`` (slam/slam.py:146): five NCHW-shaped feature maps."""
+        self._require_cuda()
+        prep = self._prepared(net)
+        n, _, h, w = x.shape
+        key = (net, n, h, w)
+        runner = self._enc_runners.get(key)
+        if runner is None:
+            L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
+            runner = EncoderRunner(self.models[net], prep, n, h, w, self.device)
+            self._enc_runners[key] = runner
+        feats = runner(x.to(self.device, dtype=torch.float32))
+        return [f.permute(0, 3, 1, 2).clone() for f in feats]
+
+    # ------------------------------------------------------------------------------------------
+    # input staging (:916-917) and weights
+    def _static_map(self, eng: AdaptEngine) -> Dict[Any, Tensor]:
+        m = {('rgb_aug', -1, 0): eng.rgb_aug[0], ('rgb_aug', 0, 0): eng.rgb_aug[1], ('rgb_aug', 1, 0): eng.rgb_aug[2],
+             ('rgb', 0, 0): eng.target, ('rgb', -1, 0): eng.sources[0], ('rgb', 1, 0): eng.sources[1],
+             ('camera_matrix', 0): eng.k_mat, ('inv_camera_matrix', 0): eng.inv_k,
+             ('relative_distance', 0): eng.rel_dist[0], ('relative_distance', 1): eng.rel_dist[1]}
+        for s in range(1, 4):
+            m[('rgb', 0, s)] = eng.color[s]
+        return m
+
+    def _stage_inputs(self, inputs: Dict[Any, Tensor]) -> AdaptEngine:
+        batch = inputs[('rgb_aug', 0, 0)].shape[0]
+        eng = self._engine(batch)
+        smap = self._static_map(eng)
+        for key in list(inputs.keys()):
+            val = inputs[key]
+            dst = smap.get(key)
+            if dst is not None:
+                if not (val.is_cuda and val.data_ptr() == dst.data_ptr()):
+                    dst.copy_(val.reshape(dst.shape), non_blocking=True)
+                inputs[key] = dst
+            elif self.stage_all_inputs and isinstance(val, Tensor):
+                inputs[key] = val.to(self.device, non_blocking=True)
+        missing = [k for k in smap if k not in inputs and not (k[0] == 'relative_distance' and eng.vel_scale == 0.0)]
+        if missing:
+            raise KeyError(f'batch dict lacks keys the adaptation path reads: {missing}')
+        return eng
+
+    def _set_weights(self, eng: AdaptEngine, loss_sample_weights: Optional[Tensor]) -> None:
+        b_global = eng.b_global
+        if loss_sample_weights is None:
+            w = torch.ones(self.batch_size) / self.batch_size          # :1032 (uses config batch_size)
+        else:
+            w = loss_sample_weights.detach().float().cpu()
+        if w.numel() != b_global:
+            if b_global == 1:
+                w = w.sum().reshape(1)          # (1,) * (batch_size,) broadcast then .sum() in the reference
+            else:
+                raise ValueError(f'{w.numel()} loss weights for a global batch of {b_global}')
+        lo, hi = shard_range(b_global, self.rank, self.world)
+        eng.sample_w_global.copy_(w, non_blocking=True)
+        eng.sample_w.copy_(w[lo:hi], non_blocking=True)
+
+    def _draw_noise(self, eng: AdaptEngine) -> None:
+        """tie-break noise of :1055-1056: one draw per scale from the global torch RNG, in scale order"""
+        for s in range(4):
+            if self.noise_provider is not None:
+                n = self.noise_provider(s, (eng.b_global, 2, self.height, self.width))
+                lo, hi = shard_range(eng.b_global, self.rank, self.world)
+                eng.noise[s].copy_(n[lo:hi], non_blocking=True)
+            else:
+                eng.noise[s].normal_()
+
+    # ------------------------------------------------------------------------------------------
+    def _collect(self, eng: AdaptEngine, check_nan: bool = True) -> Tuple[Dict[Any, Tensor], Dict[str, Tensor]]:
+        b = eng.b
+        outputs: Dict[Any, Tensor] = {}
+        for s in self.scales:
+            outputs[('disp', s)] = eng.disp[s]
+        for p, f in ((0, -1), (1, 1)):
+            outputs[('axis_angle', 0, f)] = eng.axis_angle[p].reshape(b, 1, 3).clone()
+            outputs[('translation', 0, f)] = eng.translation[p].reshape(b, 1, 3).clone()
+            outputs[('cam_T_cam', 0, f)] = eng.cam_t_cam[p].clone()
+        if self.emit_outputs:
+            for s in self.scales:
+                outputs[('depth', s)] = eng.depth[s]
+                for p, f in ((0, -1), (1, 1)):
+                    outputs[('rgb', f, s)] = eng.warped[s][p]
+        vec = eng.losses.clone()
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(vec)
+        losses: Dict[str, Tensor] = {}
+        for s in self.scales:
+            for name in ('reprojection_loss', 'smooth_loss', 'reg_loss', 'depth_loss'):
+                losses[f'{name}/scale_{s}'] = vec[LOSS_SLOTS[name] + s]
+        total = vec[18:19]
+        losses['depth_loss'] = total                     # same tensor as 'loss' 
+        if eng.vel_scale > 0:
+            losses['velocity_loss'] = vec[17]
+        losses['loss'] = total
+        if check_nan:
+            host = vec.cpu()                            # the one sync per call (:1115)
+            if bool(torch.isnan(host[18])):
+                for k, v in losses.items():
+                    print(k, float(v.reshape(-1)[0]))
+                raise RuntimeError('NaN loss')
+        return outputs, losses
+
+    def _process_batch(self, inputs: Dict[Any, Tensor], loss_sample_weights: Optional[Tensor] = None,
+                       use_online: bool = False) -> Tuple[Dict[Any, Tensor], Dict[str, Tensor]]:
+        """Forward + losses of one mini-batch (:906-923).  Values of ``inputs`` are replaced by their
+        device copies, as in the reference."""
+        if use_online:
+            raise NotImplementedError('use_online')
+        eng = self._stage_inputs(inputs)
+        self._set_weights(eng, loss_sample_weights)
+        self._draw_noise(eng)
+        eng.forward()
+        return self._collect(eng)
+
+    def backward(self, inputs_engine: Optional[AdaptEngine] = None) -> None:
+        """Gradients of the last ``_process_batch`` into the flat gradient buffer (= ``loss.backward()``
+        of :312 with the encoders frozen) followed by the data-parallel all-reduce."""
+        eng = inputs_engine or next(iter(self._engines.values()))
+        eng.backward()
+        self._allreduce_grads()
+
+    def _allreduce_grads(self) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flat.grads)            # the single exchange step (NCCL over NVLink)
+
+    def gradients(self) -> Dict[Tuple[str, str], Tensor]:
+        return self._flat.named_gradients()
+
+    def _adam_lr(self) -> float:
+        return float(self.optimizer.param_groups[0]['lr'])
+
+    def _step(self, eng: AdaptEngine) -> None:
+        """one adaptation iteration on staged inputs: fwd, bwd, (all-reduce), Adam"""
+        lr = self._adam_lr()
+        n_run = self._steps_run.get(eng.b, 0)
+        self._steps_run[eng.b] = n_run + 1
+        if not self.use_cuda_graph or n_run == 0:       # first step eager: loads every kernel before capture
+            eng.forward(); eng.backward(); self._allreduce_grads(); eng.adam(lr)
+            return
+        if self.world == 1:
+            key = (eng.b, 'step', lr)
+            g = self._graphs.get(key)
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    eng.forward(); eng.backward(); eng.adam(lr)
+                self._graphs[key] = g
+            g.replay()
+        else:
+            k1, k2 = (eng.b, 'fwdbwd'), (eng.b, 'adam', lr)
+            if k1 not in self._graphs:
+                g1 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    eng.forward(); eng.backward()
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    eng.adam(lr)
+                self._graphs[k1], self._graphs[k2] = g1, g2
+            self._graphs[k1].replay()
+            self._allreduce_grads()
+            self._graphs[k2].replay()
+
+    # ------------------------------------------------------------------------------------------
+    def adapt(self, online_data: Dict[Any, Tensor], training_data: Optional[Dict[Any, Tensor]] = None,
+              online_index: int = 0, steps: int = 1, online_loss_weight: Optional[float] = None):
+        """:291-319.  Returns (outputs, losses) of the LAST iteration (computed before its update)."""
+        if online_loss_weight is None:
+            loss_weights = None
+        else:
+            loss_weights = global_sample_weights(self.batch_size, online_loss_weight, online_index)
+        if training_data is not None:
+            self._set_adapt(freeze_encoder=True)
+            eng = self._stage_inputs(training_data)
+            self._set_weights(eng, loss_weights)
+            for _ in range(steps):
+                self._draw_noise(eng)
+                self._step(eng)
+            return self._collect(eng)
+        self._set_eval()
+        with torch.no_grad():
+            return self._process_batch(online_data, loss_weights)
+
+    def train(self, *args, **kwargs) -> None:
+        raise NotImplementedError('offline pre-training (train(), :219-289) needs encoder backward + training-mode '
+                                  'BatchNorm: SURVEY.md 8(f) row 3.  Use adapt().')
+
+    # ------------------------------------------------------------------------------------------
+    def predict_pose(self, image_0: Tensor, image_1: Tensor, as_numpy: bool = True, use_online: bool = False):
+        """:628-664: pose net forward for a loop-closure pair, invert=False; returns (4x4, eye(6))."""
+        if not self.is_trained:
+            warnings.warn('The model has not been trained yet.', RuntimeWarning)
+        if use_online:
+            raise NotImplementedError('use_online')
+        self._require_cuda()
+        if image_0.dim() == 3:
+            image_0 = image_0.unsqueeze(0)
+        if image_1.dim() == 3:
+            image_1 = image_1.unsqueeze(0)
+        self._set_eval()
+        runner = self._get_pose_runner(image_0.shape[0], image_0.shape[2], image_0.shape[3])
+        transformation = runner(image_0.to(self.device, dtype=torch.float32), image_1.to(self.device, dtype=torch.float32))
+        cov_matrix = torch.eye(6, device=self.device)
+        if as_numpy:
+            return transformation.squeeze().cpu().numpy(), cov_matrix.cpu().numpy()
+        return transformation, cov_matrix
+
+    def _get_pose_runner(self, n: int, h: int, w: int):
+        prep = self._prepared('pose_encoder')
+        r = self._pose_runner
+        if r is None or (r.n, r.h, r.w) != (n, h, w):
+            L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
+            r = _PoseRunner(prep, self._flat, n, h, w, self.device)
+            self._pose_runner = r
+        return r
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoints (:669-749): same files, key names and shapes as the reference
+    def save_model(self) -> None:
+        save_folder = Path(self.log_path) / 'models' / f'weights_{self.epoch:03}'
+        save_folder.mkdir(parents=True, exist_ok=True)
+        for model_name, model in self.models.items():
+            to_save = {k: v.detach().clone().contiguous() for k, v in model.state_dict().items()}
+            torch.save(to_save, save_folder / f'{model_name}.pth')
+        torch.save({'optimizer': self.optimizer.state_dict(), 'scheduler': self.lr_scheduler.state_dict()},
+                   save_folder / 'optimizer.pth')
+        if self.config_file is not None and Path(self.config_file).is_file():
+            shutil.copy(self.config_file, Path(self.log_path) / 'config.yaml')
+        print(f'Saved model to: {save_folder}')
+
+    def load_model(self, load_optimizer: bool = True) -> None:
+        if self.load_weights_folder is None:
+            print('Weights folder required to load the model is not specified.')
+        if not self.load_weights_folder.exists():
+            print(f'Cannot find folder: {self.load_weights_folder}')
+        print(f'Load model from: {self.load_weights_folder}')
+        for model_name, model in self.models.items():
+            path = self.load_weights_folder / f'{model_name}.pth'
+            pretrained = torch.load(path, map_location=self.device)
+            own = model.state_dict()
+            pretrained = {k: v for k, v in pretrained.items() if k in own}      # drops 'height'/'width'
+            if len(pretrained) == 0:
+                raise RuntimeError(f'No fitting weights found in: {path}')
+            own.update(pretrained)
+            model.load_state_dict(own)
+        self.refresh_encoders()
+        self.is_trained = True
+        if load_optimizer:
+            try:
+                optimizer_dict = torch.load(self.load_weights_folder / 'optimizer.pth', map_location=self.device)
+                if 'optimizer' in optimizer_dict:
+                    self.optimizer.load_state_dict(optimizer_dict['optimizer'])
+                    self.lr_scheduler.load_state_dict(optimizer_dict['scheduler'])
+                    self.epoch = self.lr_scheduler.last_epoch
+                    print(f'Restored optimizer and LR scheduler (resume from epoch {self.epoch}).')
+                else:
+                    self.optimizer.load_state_dict(optimizer_dict)
+                    print('Restored optimizer (legacy mode).')
+            except Exception:   # noqa: BLE001  (the reference swallows everything here, :747)
+                print('Cannot find matching optimizer weights, so the optimizer is randomly initialized.')
+
+    def load_online_model(self, load_optimizer: bool = True) -> None:
+        raise NotImplementedError('use_online (SURVEY.md 8(f) row 4)')
+
+
+class _PoseRunner:
+    """pose encoder + decoder + head for ``predict_pose`` (batch n, both 'passes' carry the same pair)."""
+
+    def __init__(self, prep: PreparedEncoder, flat: FlatParams, n: int, h: int, w: int, device):
+        from .engine import build_encoder
+        self.n, self.h, self.w = n, h, w
+        plan = Plan(device)
+        lib = plan.lib
+        self.img0 = plan.alloc(n, 3, h, w)
+        self.img1 = plan.alloc(n, 3, h, w)
+        staged = plan.alloc(2 * n, h, w, prep.cin_pad)
+        for half in (0, 1):
+            plan.simple(f'stage{half}', lib.clslam_stage_images, _p(self.img0), _p(self.img1),
+                        _p(staged[half * n:(half + 1) * n]), n, h, w, prep.cin_pad)
+        f4 = build_encoder(plan, prep, staged, 2 * n, h, w, 'pose_enc')[4]
+        hp, wp = f4.shape[1], f4.shape[2]
+        x = f4
+        for name, co, ci, k, act in (('squeeze', 256, 512, 1, L.ACT_RELU), ('pose_0', 256, 256, 3, L.ACT_RELU),
+                                     ('pose_1', 256, 256, 3, L.ACT_RELU), ('pose_2', 12, 256, 1, L.ACT_NONE)):
+            d = plan.desc(2 * n, hp, wp, ci, co, k, 1, (k - 1) // 2, act=act)
+            y = plan.alloc(2 * n, hp, wp, co)
+            plan.conv_fwd(name, d, x, None, flat.weight_ptr(('pose_decoder', name)), None,
+                          flat.bias_ptr(('pose_decoder', name)), None, y)
+            x = y
+        self.k_eye = torch.eye(4, device=device).repeat(n, 1, 1).contiguous()
+        self.aa = plan.alloc(2, n, 3); self.tr = plan.alloc(2, n, 3)
+        self.cam = plan.alloc(2, n, 4, 4); self.proj = plan.alloc(2, n, 12)
+        plan.simple('pose_head', lib.clslam_pose_head_fwd, _p(x), _p(self.k_eye), n, hp, wp, 0, _p(self.aa), _p(self.tr),
+                    _p(self.cam), _p(self.proj))
+        plan.finalize()
+        self.plan = plan
+
+    def __call__(self, image_0: Tensor, image_1: Tensor) -> Tensor:
+        self.img0.copy_(image_0); self.img1.copy_(image_1)
+        self.plan.run()
+        return self.cam[0].clone()

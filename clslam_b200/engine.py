@@ -1,0 +1,435 @@
+"""Launch plans of the adaptation step: static buffers + the ordered list of C-ABI calls.
+
+An ``AdaptEngine`` is built once per (local batch, H, W).  It owns every activation /
+gradient buffer (torch tensors = device memory plumbing), pre-marshals the ctypes arguments of
+each kernel launch and can therefore be replayed either eagerly or from a CUDA graph.  No
+arithmetic of the hot path happens in PyTorch here.
+
+Data layout in HBM (all fp32):
+  * images, disparities, depth maps, warped images: NCHW as in the reference batch dict;
+  * every network activation: NHWC; weights [Cout][kh][kw][Cin];
+  * the 36 trainable tensors, their gradients and Adam moments: four flat 4,467,296-element
+    buffers (``networks.FlatParams``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from .networks import DEC_CH, ENC_CH, FlatParams, ResnetEncoder
+
+Op = Tuple[str, Callable, tuple]
+
+
+def _p(t) -> Optional[int]:
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return t
+    return t.data_ptr()
+
+
+def conv_out(hi: int, k: int, s: int, p: int) -> int:
+    return (hi + 2 * p - k) // s + 1
+
+
+class PreparedEncoder:
+    """Device-side, kernel-layout copies of a (frozen) encoder: KRSC weights (conv1 input channels
+    zero-padded to 4/8) and BatchNorm(eval) folded to per-channel scale/shift
+    (resnet_encoder.py:118-124; BN eps 1e-5)."""
+
+    def __init__(self, enc: ResnetEncoder, device):
+        self.version = enc.version
+        self.cin_pad = 4 if enc.num_input_images == 1 else 8
+        r = enc.resnet
+        self.t: Dict[str, torch.Tensor] = {}
+
+        def put_conv(name, conv, pad_to=None):
+            w = conv.weight.detach().to(device=device, dtype=torch.float32)
+            if pad_to is not None and w.shape[1] < pad_to:
+                w = torch.cat([w, w.new_zeros(w.shape[0], pad_to - w.shape[1], *w.shape[2:])], 1)
+            self.t[name + '.w'] = w.permute(0, 2, 3, 1).contiguous()
+
+        def put_bn(name, bn):
+            scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+            shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+            self.t[name + '.scale'] = scale.to(device).contiguous()
+            self.t[name + '.shift'] = shift.to(device).contiguous()
+
+        with torch.no_grad():
+            put_conv('conv1', r.conv1, self.cin_pad)
+            put_bn('bn1', r.bn1)
+            for li in range(1, 5):
+                for bi, blk in enumerate(getattr(r, f'layer{li}')):
+                    p = f'layer{li}.{bi}'
+                    put_conv(p + '.conv1', blk.conv1); put_bn(p + '.bn1', blk.bn1)
+                    put_conv(p + '.conv2', blk.conv2); put_bn(p + '.bn2', blk.bn2)
+                    if blk.downsample is not None:
+                        put_conv(p + '.ds', blk.downsample[0]); put_bn(p + '.dsbn', blk.downsample[1])
+
+
+class Plan:
+    """Ordered kernel launches over static buffers."""
+
+    def __init__(self, device):
+        self.device = device
+        self.lib = L.load()
+        self.ops: List[Op] = []
+        self.ws_bytes = 0
+        self.keep: List[object] = []       # ctypes structs / tensors that must outlive the plan
+        self._ws: Optional[torch.Tensor] = None
+
+    def alloc(self, *shape, dtype=torch.float32, zero=False) -> torch.Tensor:
+        t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    def need_ws(self, nbytes: int) -> None:
+        if nbytes < 0:
+            raise RuntimeError('workspace query failed: ' + self.lib.clslam_last_error().decode())
+        self.ws_bytes = max(self.ws_bytes, int(nbytes))
+
+    def add(self, name: str, fn, *args) -> None:
+        self.ops.append((name, fn, args))
+
+    # -- layer helpers -------------------------------------------------------------------------
+    def desc(self, n, hi, wi, ci, co, k, stride, pad, pad_mode=L.PAD_ZERO, in_mode=L.IN_PLAIN, c1=0, h1=0, w1=0,
+             act=L.ACT_NONE) -> L.ConvDesc:
+        d = L.ConvDesc(n, hi, wi, ci, conv_out(hi, k, stride, pad), conv_out(wi, k, stride, pad), co, k, k, stride,
+                       pad, pad_mode, in_mode, c1, h1, w1, act)
+        self.keep.append(d)
+        return d
+
+    def conv_fwd(self, name, d: L.ConvDesc, x, x2, w, scale, shift, res, y) -> None:
+        self.need_ws(self.lib.clslam_conv_fwd_workspace_bytes(ctypes.byref(d)))
+        self.add(name, self._conv_fwd, d, _p(x), _p(x2), _p(w), _p(scale), _p(shift), _p(res), _p(y))
+
+    def _conv_fwd(self, stream, d, x, x2, w, scale, shift, res, y):
+        return self.lib.clslam_conv_fwd(ctypes.byref(d), x, x2, w, scale, shift, res, y, self._ws_ptr, self.ws_bytes, stream)
+
+    def conv_dgrad(self, name, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev) -> None:
+        self.need_ws(self.lib.clslam_conv_dgrad_workspace_bytes(ctypes.byref(d)))
+        self.add(name, self._conv_dgrad, d, _p(dz), _p(w), _p(y_prev), act_prev, _p(disp_dz), _p(disp_w), _p(dz_prev))
+
+    def _conv_dgrad(self, stream, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev):
+        return self.lib.clslam_conv_dgrad(ctypes.byref(d), dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev,
+                                          self._ws_ptr, self.ws_bytes, stream)
+
+    def conv_wgrad(self, name, d, x, x2, dz, dw, db) -> None:
+        self.need_ws(self.lib.clslam_conv_wgrad_workspace_bytes(ctypes.byref(d)))
+        self.add(name, self._conv_wgrad, d, _p(x), _p(x2), _p(dz), _p(dw), _p(db))
+
+    def _conv_wgrad(self, stream, d, x, x2, dz, dw, db):
+        return self.lib.clslam_conv_wgrad(ctypes.byref(d), x, x2, dz, dw, db, self._ws_ptr, self.ws_bytes, stream)
+
+    def simple(self, name, fn, *args) -> None:
+        """fn(*args, stream)"""
+        self.add(name, lambda stream, *a: fn(*a, stream), *args)
+
+    def with_ws(self, name, fn, *args) -> None:
+        """fn(*args, ws, ws_bytes, stream)"""
+        self.add(name, lambda stream, *a: fn(*a, self._ws_ptr, self.ws_bytes, stream), *args)
+
+    # -- execution -----------------------------------------------------------------------------
+    def finalize(self) -> None:
+        self._ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=self.device)
+        self._ws_ptr = self._ws.data_ptr()
+
+    def run(self, first: int = 0, last: Optional[int] = None) -> None:
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for name, fn, args in self.ops[first:last]:
+            rc = fn(stream, *args)
+            if rc != 0:
+                L.check(rc, name)
+
+
+def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: torch.Tensor, n: int, h: int, w: int, tag: str,
+                  ) -> List[torch.Tensor]:
+    """ResNet-18 trunk (networks/resnet_encoder.py:115-125) over an NHWC staged input; returns the
+    five NHWC feature maps."""
+    t = prep.t
+    feats = []
+    d = plan.desc(n, h, w, prep.cin_pad, 64, 7, 2, 3, act=L.ACT_RELU)
+    f0 = plan.alloc(n, d.ho, d.wo, 64)
+    plan.conv_fwd(f'{tag}.conv1', d, x_staged, None, t['conv1.w'], t['bn1.scale'], t['bn1.shift'], None, f0)
+    feats.append(f0)
+    hp, wp = conv_out(d.ho, 3, 2, 1), conv_out(d.wo, 3, 2, 1)
+    x = plan.alloc(n, hp, wp, 64)
+    plan.simple(f'{tag}.maxpool', plan.lib.clslam_maxpool3x3s2, _p(f0), _p(x), n, d.ho, d.wo, 64)
+    hc, wc, cin = hp, wp, 64
+    for li, planes in enumerate((64, 128, 256, 512), start=1):
+        for bi in range(2):
+            stride = 2 if (li > 1 and bi == 0) else 1
+            p = f'layer{li}.{bi}'
+            d1 = plan.desc(n, hc, wc, cin, planes, 3, stride, 1, act=L.ACT_RELU)
+            mid = plan.alloc(n, d1.ho, d1.wo, planes)
+            plan.conv_fwd(f'{tag}.{p}.conv1', d1, x, None, t[p + '.conv1.w'], t[p + '.bn1.scale'], t[p + '.bn1.shift'],
+                          None, mid)
+            if (p + '.ds.w') in t:
+                dd = plan.desc(n, hc, wc, cin, planes, 1, stride, 0, act=L.ACT_NONE)
+                idt = plan.alloc(n, dd.ho, dd.wo, planes)
+                plan.conv_fwd(f'{tag}.{p}.downsample', dd, x, None, t[p + '.ds.w'], t[p + '.dsbn.scale'],
+                              t[p + '.dsbn.shift'], None, idt)
+            else:
+                idt = x
+            d2 = plan.desc(n, d1.ho, d1.wo, planes, planes, 3, 1, 1, act=L.ACT_RELU)
+            out = plan.alloc(n, d2.ho, d2.wo, planes)
+            plan.conv_fwd(f'{tag}.{p}.conv2', d2, mid, None, t[p + '.conv2.w'], t[p + '.bn2.scale'], t[p + '.bn2.shift'],
+                          idt, out)
+            x, hc, wc, cin = out, d2.ho, d2.wo, planes
+        feats.append(x)
+    return feats
+
+
+class EncoderRunner:
+    """Encoder-only forward for callers that use ``models['depth_encoder'](image)`` directly
+    (slam/slam.py:143-147) and for predict_pose (depth_pose_prediction.py:628-664)."""
+
+    def __init__(self, enc: ResnetEncoder, prep: PreparedEncoder, n: int, h: int, w: int, device):
+        self.plan = Plan(device)
+        self.n, self.h, self.w = n, h, w
+        self.two = enc.num_input_images == 2
+        self.img_a = self.plan.alloc(n, 3, h, w)
+        self.img_b = self.plan.alloc(n, 3, h, w) if self.two else None
+        self.staged = self.plan.alloc(n, h, w, prep.cin_pad)
+        self.plan.simple('stage', self.plan.lib.clslam_stage_images, _p(self.img_a), _p(self.img_b), _p(self.staged), n, h,
+                         w, prep.cin_pad)
+        self.feats = build_encoder(self.plan, prep, self.staged, n, h, w, 'enc')
+        self.plan.finalize()
+        self.prep = prep
+
+    def __call__(self, image: torch.Tensor) -> List[torch.Tensor]:
+        if self.two:
+            self.img_a.copy_(image[:, :3]); self.img_b.copy_(image[:, 3:6])
+        else:
+            self.img_a.copy_(image)
+        self.plan.run()
+        return self.feats
+
+
+class AdaptEngine:
+    """fwd + loss + bwd + Adam of one mini-batch shard."""
+
+    def __init__(self, *, batch: int, height: int, width: int, batch_global: int, has_sample0: bool,
+                 depth_prep: PreparedEncoder, pose_prep: PreparedEncoder, flat: FlatParams,
+                 min_depth: Optional[float], max_depth: Optional[float], disparity_smoothness: float,
+                 velocity_loss_scaling: Optional[float], device, emit_outputs: bool = True):
+        if height % 32 or width % 32:
+            raise ValueError('height and width must be multiples of 32 (ResNet-18 / 4-scale pyramid)')
+        self.b, self.h, self.w = batch, height, width
+        self.b_global, self.has_sample0 = batch_global, has_sample0
+        self.device = device
+        self.flat = flat
+        self.depth_prep, self.pose_prep = depth_prep, pose_prep
+        lib = L.load()
+        self.lib = lib
+        b, h, w = batch, height, width
+        plan = Plan(device)
+        self.plan = plan
+        S = 4
+        self.n_scales = S
+
+        # ---- static inputs (only the keys the path reads) ----------------
+        self.rgb_aug = plan.alloc(3, b, 3, h, w)            # frames -1, 0, +1
+        self.target = plan.alloc(b, 3, h, w)                # ('rgb', 0, 0)
+        self.sources = plan.alloc(2, b, 3, h, w)            # ('rgb', -1, 0), ('rgb', 1, 0)
+        self.color = [self.target] + [plan.alloc(b, 3, h >> s, w >> s) for s in range(1, S)]
+        self.k_mat = plan.alloc(b, 4, 4)
+        self.inv_k = plan.alloc(b, 4, 4)
+        self.rel_dist = plan.alloc(2, b, dtype=torch.float64, zero=True)
+        self.sample_w = plan.alloc(b, zero=True)
+        self.sample_w_global = plan.alloc(batch_global, zero=True)
+        self.noise = [plan.alloc(b, 2, h, w, zero=True) for _ in range(S)]
+
+        # ---- depth network -------------------------------------------------------------------
+        self.depth_in = plan.alloc(b, h, w, depth_prep.cin_pad)
+        plan.simple('depth.stage', lib.clslam_stage_images, _p(self.rgb_aug[1]), None, _p(self.depth_in), b, h, w,
+                    depth_prep.cin_pad)
+        feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc')
+        self.depth_feats = feats
+        dd = 'depth_decoder'
+        self.y = {}          # decoder activations (ELU outputs), NHWC
+        self.disp = {}
+        self.dec_desc = {}
+        x = feats[4]
+        for i in range(4, -1, -1):
+            hi_, wi_ = x.shape[1], x.shape[2]
+            d0 = plan.desc(b, hi_, wi_, x.shape[3], DEC_CH[i], 3, 1, 1, pad_mode=L.PAD_REFLECT, act=L.ACT_ELU)
+            y0 = plan.alloc(b, hi_, wi_, DEC_CH[i])
+            key0 = (dd, f'upconv_{i}_0.conv.conv')
+            plan.conv_fwd(f'upconv_{i}_0', d0, x, None, flat.weight_ptr(key0), None, flat.bias_ptr(key0), None, y0)
+            self.y[(i, 0)] = y0; self.dec_desc[(i, 0)] = (d0, x)
+            if i > 0:
+                skip = feats[i - 1]
+                ho_, wo_ = skip.shape[1], skip.shape[2]
+                c2 = skip.shape[3]
+            else:
+                skip = None
+                ho_, wo_ = hi_ * 2, wi_ * 2
+                c2 = 0
+            d1 = plan.desc(b, ho_, wo_, DEC_CH[i] + c2, DEC_CH[i], 3, 1, 1, pad_mode=L.PAD_REFLECT, in_mode=L.IN_UPCAT,
+                           c1=DEC_CH[i], h1=hi_, w1=wi_, act=L.ACT_ELU)
+            y1 = plan.alloc(b, ho_, wo_, DEC_CH[i])
+            key1 = (dd, f'upconv_{i}_1.conv.conv')
+            plan.conv_fwd(f'upconv_{i}_1', d1, y0, skip, flat.weight_ptr(key1), None, flat.bias_ptr(key1), None, y1)
+            self.y[(i, 1)] = y1; self.dec_desc[(i, 1)] = (d1, y0, skip)
+            if i < S:
+                keyd = (dd, f'dispconv_{i}.conv')
+                dsp = plan.alloc(b, 1, ho_, wo_)
+                plan.simple(f'dispconv_{i}', lib.clslam_dispconv_fwd, _p(y1), flat.weight_ptr(keyd), flat.bias_ptr(keyd),
+                            _p(dsp), b, ho_, wo_, DEC_CH[i])
+                self.disp[i] = dsp
+            x = y1
+
+        # ---- pose network (both passes batched: [frame -1 | frame +1]) ------------------------
+        self.pose_in = plan.alloc(2 * b, h, w, pose_prep.cin_pad)
+        # temporal order (depth_pose_prediction.py:951-955): (-1, 0) and (0, +1)
+        plan.simple('pose.stage0', lib.clslam_stage_images, _p(self.rgb_aug[0]), _p(self.rgb_aug[1]), _p(self.pose_in[:b]),
+                    b, h, w, pose_prep.cin_pad)
+        plan.simple('pose.stage1', lib.clslam_stage_images, _p(self.rgb_aug[1]), _p(self.rgb_aug[2]), _p(self.pose_in[b:]),
+                    b, h, w, pose_prep.cin_pad)
+        pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc')
+        pf4 = pfeats[4]
+        hp, wp = pf4.shape[1], pf4.shape[2]
+        self.pose_hw = (hp, wp)
+        pd = 'pose_decoder'
+        self.pose_act = {}
+        self.pose_desc = {}
+        x = pf4
+        for name, co, ci, k, act in (('squeeze', 256, 512, 1, L.ACT_RELU), ('pose_0', 256, 256, 3, L.ACT_RELU),
+                                     ('pose_1', 256, 256, 3, L.ACT_RELU), ('pose_2', 12, 256, 1, L.ACT_NONE)):
+            d = plan.desc(2 * b, hp, wp, ci, co, k, 1, (k - 1) // 2, act=act)
+            yv = plan.alloc(2 * b, hp, wp, co)
+            plan.conv_fwd(name, d, x, None, flat.weight_ptr((pd, name)), None, flat.bias_ptr((pd, name)), None, yv)
+            self.pose_act[name] = yv; self.pose_desc[name] = (d, x)
+            x = yv
+        self.axis_angle = plan.alloc(2, b, 3)
+        self.translation = plan.alloc(2, b, 3)
+        self.cam_t_cam = plan.alloc(2, b, 4, 4)
+        self.proj = plan.alloc(2, b, 12)
+        self.invert_mask = 0b01                                     # pass 0 (frame -1) is inverted (:973)
+        plan.simple('pose_head_fwd', lib.clslam_pose_head_fwd, _p(self.pose_act['pose_2']), _p(self.k_mat), b, hp, wp,
+                    self.invert_mask, _p(self.axis_angle), _p(self.translation), _p(self.cam_t_cam), _p(self.proj))
+
+        # ---- photometric chain + losses -------------------------------------------------------
+        self.n_tiles = lib.clslam_photo_tiles(h, w)
+        self.identity = plan.alloc(b, 2, h, w)
+        self.depth = [plan.alloc(b, 1, h, w) for _ in range(S)] if emit_outputs else [None] * S
+        self.warped = [plan.alloc(2, b, 3, h, w) for _ in range(S)] if emit_outputs else [None] * S
+        self.argmin = [plan.alloc(b, h, w, dtype=torch.uint8) for _ in range(S)]
+        self.loss_partials = plan.alloc(S, b, self.n_tiles)
+        self.ddisp_full = [plan.alloc(b, h, w) for _ in range(S)]
+        self.dproj_partials = plan.alloc(S * self.n_tiles, 2, b, 12)
+        self.losses = plan.alloc(L.N_LOSS_SLOTS, zero=True)
+        self.smooth_grad = plan.alloc(S, 2 * (batch_global + 1) + 1, zero=True)
+        if min_depth is None and max_depth is None:
+            mode = L.DEPTH_INV
+        elif max_depth is None:
+            mode = L.DEPTH_MIN_ONLY
+        elif min_depth is None:
+            raise ValueError('min_depth is None')
+        else:
+            mode = L.DEPTH_MIN_MAX
+        pa = L.PhotoArgs()
+        pa.b, pa.h, pa.w, pa.n_scales = b, h, w, S
+        pa.depth_mode, pa.min_depth, pa.max_depth = mode, float(min_depth or 0.0), float(max_depth or 0.0)
+        pa.target, pa.sources, pa.inv_k, pa.proj = _p(self.target), _p(self.sources), _p(self.inv_k), _p(self.proj)
+        pa.identity, pa.sample_w = _p(self.identity), _p(self.sample_w)
+        for s in range(S):
+            pa.disp[s] = _p(self.disp[s]); pa.noise[s] = _p(self.noise[s])
+            pa.depth[s] = _p(self.depth[s]); pa.warped[s] = _p(self.warped[s])
+            pa.argmin[s] = _p(self.argmin[s]); pa.ddisp_full[s] = _p(self.ddisp_full[s])
+        pa.loss_partials, pa.dproj_partials = _p(self.loss_partials), _p(self.dproj_partials)
+        self.photo_args = pa
+        plan.keep.append(pa)
+        self.vel_scale = float(velocity_loss_scaling) if (velocity_loss_scaling is not None and velocity_loss_scaling > 0) else 0.0
+        la = L.LossArgs()
+        la.b, la.b_global, la.h, la.w, la.n_scales, la.n_tiles = b, batch_global, h, w, S, self.n_tiles
+        la.has_sample0 = 1 if has_sample0 else 0
+        la.disparity_smoothness, la.velocity_scale = float(disparity_smoothness), self.vel_scale
+        la.loss_partials, la.sample_w, la.sample_w_global = _p(self.loss_partials), _p(self.sample_w), _p(self.sample_w_global)
+        for s in range(S):
+            la.disp[s] = _p(self.disp[s]); la.color[s] = _p(self.color[s])
+        la.translation, la.rel_dist = _p(self.translation), _p(self.rel_dist)
+        la.losses, la.smooth_grad = _p(self.losses), _p(self.smooth_grad)
+        self.loss_args = la
+        plan.keep.append(la)
+        self.op_identity = len(plan.ops)
+        plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
+        plan.add('photo_fwd', lambda stream: lib.clslam_photo_fwd(ctypes.byref(pa), stream))
+        plan.add('loss_finalize', lambda stream: lib.clslam_loss_finalize(ctypes.byref(la), stream))
+        self.n_fwd_ops = len(plan.ops)
+
+        # ---- backward ---------------------------------------------------------------------------
+        plan.add('photo_bwd', lambda stream: lib.clslam_photo_bwd(ctypes.byref(pa), stream))
+        self.dz_disp = {}
+        for s in range(S):
+            self.dz_disp[s] = plan.alloc(b, 1, h >> s, w >> s)
+            plan.simple(f'disp_grad_{s}', lib.clslam_disp_grad, _p(self.ddisp_full[s]), _p(self.disp[s]),
+                        _p(self.smooth_grad), batch_global, 1 if has_sample0 else 0, b, h, w, s, _p(self.dz_disp[s]))
+        self.dz = {}
+        for i in range(0, 5):
+            for j in (0, 1):
+                self.dz[(i, j)] = plan.alloc(*self.y[(i, j)].shape)
+        for i in range(0, 5):
+            y1 = self.y[(i, 1)]
+            hi_, wi_ = y1.shape[1], y1.shape[2]
+            if i < S:
+                keyd = (dd, f'dispconv_{i}.conv')
+                plan.need_ws(lib.clslam_dispconv_wgrad_workspace_bytes(b, hi_, wi_, DEC_CH[i]))
+                plan.with_ws(f'dispconv_{i}.wgrad', lib.clslam_dispconv_wgrad, _p(y1), _p(self.dz_disp[i]),
+                             flat.wgrad_ptr(keyd), flat.bgrad_ptr(keyd), b, hi_, wi_, DEC_CH[i])
+            if i == 0:
+                plan.simple('dispconv_0.dgrad', lib.clslam_dispconv_dgrad_act, _p(self.dz_disp[0]),
+                            flat.weight_ptr((dd, 'dispconv_0.conv')), _p(y1), L.ACT_ELU, _p(self.dz[(0, 1)]), b, hi_, wi_,
+                            DEC_CH[0])
+            # upconv_i_1: wgrad + dgrad (to the up-sampled branch only; the skip feeds a frozen encoder)
+            d1, y0, skip = self.dec_desc[(i, 1)]
+            key1 = (dd, f'upconv_{i}_1.conv.conv')
+            plan.conv_wgrad(f'upconv_{i}_1.wgrad', d1, y0, skip, self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
+            plan.conv_dgrad(f'upconv_{i}_1.dgrad', d1, self.dz[(i, 1)], flat.weight_ptr(key1), y0, L.ACT_ELU, None, None,
+                            self.dz[(i, 0)])
+            # upconv_i_0: wgrad; dgrad into upconv_{i+1}_1's output (+ dispconv_{i+1} term)
+            d0, xin = self.dec_desc[(i, 0)]
+            key0 = (dd, f'upconv_{i}_0.conv.conv')
+            plan.conv_wgrad(f'upconv_{i}_0.wgrad', d0, xin, None, self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
+            if i < 4:
+                has_disp = (i + 1) < S
+                plan.conv_dgrad(f'upconv_{i}_0.dgrad', d0, self.dz[(i, 0)], flat.weight_ptr(key0), self.y[(i + 1, 1)],
+                                L.ACT_ELU, self.dz_disp[i + 1] if has_disp else None,
+                                flat.weight_ptr((dd, f'dispconv_{i + 1}.conv')) if has_disp else None,
+                                self.dz[(i + 1, 1)])
+        # pose branch
+        self.dz_pose = {name: plan.alloc(*self.pose_act[name].shape) for name in ('squeeze', 'pose_0', 'pose_1', 'pose_2')}
+        plan.simple('pose_head_bwd', lib.clslam_pose_head_bwd, _p(self.dproj_partials), S * self.n_tiles, _p(self.k_mat),
+                    _p(self.axis_angle), _p(self.translation), _p(self.rel_dist), _p(self.sample_w),
+                    self.vel_scale, b, hp, wp, self.invert_mask, _p(self.dz_pose['pose_2']))
+        prev = {'pose_2': 'pose_1', 'pose_1': 'pose_0', 'pose_0': 'squeeze'}
+        for name in ('pose_2', 'pose_1', 'pose_0', 'squeeze'):
+            d, xin = self.pose_desc[name]
+            plan.conv_wgrad(f'{name}.wgrad', d, xin, None, self.dz_pose[name], flat.wgrad_ptr((pd, name)),
+                            flat.bgrad_ptr((pd, name)))
+            if name in prev:
+                plan.conv_dgrad(f'{name}.dgrad', d, self.dz_pose[name], flat.weight_ptr((pd, name)),
+                                self.pose_act[prev[name]], L.ACT_RELU, None, None, self.dz_pose[prev[name]])
+        self.n_bwd_ops = len(plan.ops)
+        plan.finalize()
+
+        self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+
+    # ---- execution -----------------------------------------------------------------------------
+    def forward(self) -> None:
+        self.plan.run(0, self.n_fwd_ops)
+
+    def backward(self) -> None:
+        self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
+
+    def adam(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
+        f = self.flat
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        L.check(self.lib.clslam_adam_step(f.params.data_ptr(), f.grads.data_ptr(), f.exp_avg.data_ptr(),
+                                          f.exp_avg_sq.data_ptr(), f.numel, lr, beta1, beta2, eps, 0,
+                                          f.step_dev.data_ptr(), stream), 'adam')

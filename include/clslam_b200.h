@@ -1,0 +1,206 @@
+/*
+ * clslam_b200 -- C ABI of the B200-native CL-SLAM online-adaptation hot path.
+ *
+ * The reference (robot-learning-freiburg/CL-SLAM) has no FFI/plugin layer: its boundary for
+ * this path is the Python class depth_pose_prediction.DepthPosePrediction
+ * (depth_pose_prediction/depth_pose_prediction.py:38).  This header is what the drop-in
+ * Python class in clslam_b200/ binds with ctypes; every entry point names the reference
+ * code it replaces (file:line relative to /root/reference).
+ *
+ * Conventions
+ *   - plain C types only: raw DEVICE pointers, ints, floats, a cudaStream_t passed as void*.
+ *   - no allocation, no ownership transfer: the caller (torch) owns every buffer; kernels that
+ *     need scratch take (workspace, workspace_bytes) and a *_workspace_bytes() query exists.
+ *   - stream ordered, no host synchronisation inside, CUDA-graph capturable.
+ *   - return 0 on success, negative on error; clslam_last_error() returns the message of the
+ *     last failing call on this host thread.
+ *   - activations are fp32 NHWC ("pixel-major, channel-fastest"); images / disparities /
+ *     depth maps at the API edge are fp32 NCHW exactly as in the reference's batch dict
+ *     (SURVEY.md App. C).  Convolution weights are fp32 [Cout][kh][kw][Cin] (KRSC), i.e. the
+ *     torch.channels_last storage of the reference's (Cout,Cin,kh,kw) tensors.
+ */
+#ifndef CLSLAM_B200_H
+#define CLSLAM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CLSLAM_ABI_VERSION 1
+
+/* epilogue activations */
+enum { CLSLAM_ACT_NONE = 0, CLSLAM_ACT_RELU = 1, CLSLAM_ACT_ELU = 2, CLSLAM_ACT_SIGMOID = 3 };
+/* border handling of the convolution input */
+enum { CLSLAM_PAD_ZERO = 0, CLSLAM_PAD_REFLECT = 1 };
+/* how the convolution input is assembled */
+enum { CLSLAM_IN_PLAIN = 0,   /* x: (n, hi, wi, ci) */
+       CLSLAM_IN_UPCAT = 1 }; /* cat[nearest_up(x -> hi x wi) (c1 ch @ h1 x w1), x2 (ci-c1 ch @ hi x wi)] */
+/* disp -> depth (depth_pose_prediction/utils.py:120-142) */
+enum { CLSLAM_DEPTH_INV = 0,      /* 1/disp            (min_depth=None, max_depth=None) */
+       CLSLAM_DEPTH_MIN_ONLY = 1, /* min_depth/disp    (max_depth=None; config_adapt.yaml:23-24) */
+       CLSLAM_DEPTH_MIN_MAX = 2 };/* 1/(1/max + (1/min-1/max)*disp) */
+
+/* One convolution layer.  Forward: y = act(scale * conv(x) + shift) (+ residual before act). */
+typedef struct clslam_conv_desc {
+  int n;            /* batch */
+  int hi, wi, ci;   /* (virtual) input height, width, channels (ci = c1 + c2 for UPCAT) */
+  int ho, wo, co;   /* output height, width, channels */
+  int kh, kw, stride, pad;
+  int pad_mode;     /* CLSLAM_PAD_* */
+  int in_mode;      /* CLSLAM_IN_* */
+  int c1, h1, w1;   /* UPCAT: channels / height / width of the low-resolution part */
+  int act;          /* CLSLAM_ACT_* of THIS layer's output */
+} clslam_conv_desc;
+
+const char* clslam_last_error(void);
+int clslam_abi_version(void);
+/* number of kernel launches issued through this library since load (bench.py "gpu_launches") */
+long long clslam_launch_count(void);
+/* bind this library's CUDA runtime to `device` on the calling host thread (one process per GPU) */
+int clslam_set_device(int device);
+
+/* ---- input staging ------------------------------------------------------------------------
+ * (x - 0.45) / 0.225 of networks/resnet_encoder.py:117 fused with NCHW -> NHWC and channel
+ * padding; `img_b` may be NULL (depth net: 3 -> c_pad channels) or a second image that is
+ * concatenated on the channel axis (pose net, depth_pose_prediction.py:951-955). */
+int clslam_stage_images(const float* img_a, const float* img_b, float* out_nhwc, int n, int h, int w,
+                        int c_pad, void* stream);
+
+/* ---- convolution stack --------------------------------------------------------------------
+ * Replaces nn.Conv2d + BatchNorm2d(eval) + ReLU / residual add of torchvision BasicBlock as
+ * driven by networks/resnet_encoder.py:118-124, Conv3x3/ConvBlock (networks/layers.py:9-48),
+ * the nearest-upsample + concat of networks/depth_decoder.py:56-66 (fused into the loader of
+ * upconv_i_1) and PoseDecoder convs (networks/pose_decoder.py:40-47).
+ *   scale may be NULL (=1); shift is the bias or the folded BatchNorm shift; residual may be NULL. */
+long long clslam_conv_fwd_workspace_bytes(const clslam_conv_desc* d);
+int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, const float* w,
+                    const float* scale, const float* shift, const float* residual, float* y,
+                    void* workspace, long long workspace_bytes, void* stream);
+
+/* 3x3/stride-2/pad-1 max pooling, NHWC (networks/resnet_encoder.py:121). */
+int clslam_maxpool3x3s2(const float* x, float* y, int n, int hi, int wi, int c, void* stream);
+
+/* dispconv_s: reflection-padded 3x3 conv to ONE channel + sigmoid (networks/depth_decoder.py:69).
+ * y: (n, 1, h, w). */
+int clslam_dispconv_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int w_,
+                        int ci, void* stream);
+
+/* ---- backward of the decoder convolutions (autograd of losses['loss'].backward(),
+ * depth_pose_prediction.py:312; encoders are frozen, :807-827) --------------------------------
+ * dgrad: gradient wrt the layer input, written as the pre-activation gradient of the layer
+ *   that PRODUCED that input: dz_prev = act'(y_prev) * (dX [+ dispconv contribution]).
+ *   For IN_UPCAT only the first c1 channels (the up-sampled decoder branch) are produced, already
+ *   summed over the nearest-neighbour footprint, at (h1, w1); the skip branch feeds a frozen
+ *   encoder and is not computed.
+ *   disp_dz / disp_w (optional): pre-sigmoid gradient (n,1,hi,wi) and weights [1][3][3][ci] of
+ *   the dispconv that also consumes y_prev; its input gradient is added before act'.
+ * wgrad: dW [co][kh][kw][ci] and db [co] from the layer input (x, x2 as in forward) and dz. */
+long long clslam_conv_dgrad_workspace_bytes(const clslam_conv_desc* d);
+int clslam_conv_dgrad(const clslam_conv_desc* d, const float* dz, const float* w, const float* y_prev,
+                      int act_prev, const float* disp_dz, const float* disp_w, float* dz_prev,
+                      void* workspace, long long workspace_bytes, void* stream);
+long long clslam_conv_wgrad_workspace_bytes(const clslam_conv_desc* d);
+int clslam_conv_wgrad(const clslam_conv_desc* d, const float* x, const float* x2, const float* dz,
+                      float* dw, float* db, void* workspace, long long workspace_bytes, void* stream);
+/* dispconv backward: dW [1][3][3][ci], db [1] (wgrad) and, when the dispconv is the only consumer
+ * of y_prev (scale 0), dz_prev = elu'(y_prev) * dX. */
+long long clslam_dispconv_wgrad_workspace_bytes(int n, int h, int w_, int ci);
+int clslam_dispconv_wgrad(const float* x, const float* dz, float* dw, float* db, int n, int h, int w_, int ci,
+                          void* workspace, long long workspace_bytes, void* stream);
+int clslam_dispconv_dgrad_act(const float* dz, const float* w, const float* y_prev, int act_prev,
+                              float* dz_prev, int n, int h, int w_, int ci, void* stream);
+
+/* ---- pose head ----------------------------------------------------------------------------
+ * mean over (W, H) * 0.01 -> (axis_angle, translation) of frame slot 0 (networks/pose_decoder.py:
+ * 49-54; caller keeps [:,0], depth_pose_prediction.py:965), Rodrigues + translation
+ * (utils.py:34-117; invert for the f=-1 pass), and P = (K @ cam_T_cam)[:3] of
+ * networks/layers.py:94.  pose_out: (2*b, hw, 12) NHWC, pass 0 = frame -1, pass 1 = frame +1.
+ * Outputs (pass-major): axis_angle (2,b,3), translation (2,b,3), cam_t_cam (2,b,16), proj (2,b,12). */
+int clslam_pose_head_fwd(const float* pose_out, const float* k_mat, int b, int h, int w, int invert_mask,
+                         float* axis_angle, float* translation, float* cam_t_cam, float* proj,
+                         void* stream);
+/* Backward of the above plus the velocity term (depth_pose_prediction.py:1125-1146):
+ * dproj_partials (n_partials, 2, b, 12) are the per-block sums written by clslam_photo_bwd.
+ * Writes dz of pose_2's output (2*b, hw, 12). */
+int clslam_pose_head_bwd(const float* dproj_partials, int n_partials, const float* k_mat,
+                         const float* axis_angle, const float* translation, const double* rel_dist,
+                         const float* sample_w, float velocity_scale, int b, int h, int w, int invert_mask,
+                         float* dz_pose_out, void* stream);
+
+/* ---- photometric chain --------------------------------------------------------------------
+ * identity: 0.85*mean_c SSIM + 0.15*mean_c L1 between the UNWARPED sources and the target
+ *   (auto-masking candidates, depth_pose_prediction.py:1049-1053; SSIM networks/layers.py:123-137).
+ *   src: 2 pointers' worth laid out (2, b, 3, h, w); out (b, 2, h, w).
+ * fwd (per call: all `n_scales` scales): bilinear up (align_corners=False, :989-991) -> disp_to_depth
+ *   (utils.py:120-142) -> BackprojectDepth/Project3D (networks/layers.py:74-104) -> grid_sample(bilinear,
+ *   border, align_corners=True) (:1013-1017) -> SSIM+L1 (:1178-1192) -> + noise*1e-5 on the identity
+ *   candidates, min over 4 (:1055-1061) -> per-sample sums.
+ *   disp[s]: (b,1,h>>s,w>>s).  noise[s]: (b,2,h,w) standard normal or NULL.  Optional outputs
+ *   depth[s] (b,1,h,w) and warped[s] (2,b,3,h,w) may be NULL.  argmin[s]: (b,h,w) uint8 stash
+ *   for backward.  loss_partials: (n_scales, b, tiles) block sums (clslam_photo_tiles()).
+ * bwd: gradient wrt disp at full resolution, ddisp_full[s] (b,h,w), and per-block sums of the
+ *   gradient wrt proj, dproj_partials (n_scales*tiles, 2, b, 12). */
+typedef struct clslam_photo_args {
+  int b, h, w, n_scales;
+  int depth_mode; float min_depth, max_depth;
+  const float* target;        /* (b,3,h,w)  inputs['rgb',0,0] */
+  const float* sources;       /* (2,b,3,h,w) inputs['rgb',-1,0], inputs['rgb',1,0] */
+  const float* inv_k;         /* (b,4,4) inputs['inv_camera_matrix',0] */
+  const float* proj;          /* (2,b,12) from clslam_pose_head_fwd */
+  const float* identity;      /* (b,2,h,w) from clslam_photo_identity */
+  const float* sample_w;      /* (b) loss weights w_b */
+  const float* disp[4];
+  const float* noise[4];
+  float* depth[4];
+  float* warped[4];
+  unsigned char* argmin[4];
+  float* loss_partials;
+  float* ddisp_full[4];
+  float* dproj_partials;
+} clslam_photo_args;
+int clslam_photo_tiles(int h, int w);
+int clslam_photo_identity(const float* target, const float* sources, float* identity, int b, int h, int w,
+                          void* stream);
+int clslam_photo_fwd(const clslam_photo_args* a, void* stream);
+int clslam_photo_bwd(const clslam_photo_args* a, void* stream);
+
+/* ---- loss assembly ------------------------------------------------------------------------
+ * depth_pose_prediction.py:1071-1113 incl. the smoothness term AS EXECUTED by the reference
+ * (all b_global terms come from row 0 of batch element 0) and the velocity term.
+ * losses out (24 floats): [0..3] reprojection_loss/scale_s, [4..7] smooth_loss, [8..11] reg_loss,
+ * [12..15] depth_loss/scale_s, [16] depth_loss (== loss, aliased in the reference), [17] velocity_loss,
+ * [18] loss, [19] nan flag.  smooth_grad out (n_scales, 2*(b_global+1)+1): direct d(loss)/d(disp)
+ * at rows 0/1, cols 0..b_global of sample 0 followed by the uniform term from the mean
+ * normalisation.  has_sample0 = 0 on ranks that do not hold global sample 0. */
+typedef struct clslam_loss_args {
+  int b, b_global, h, w, n_scales, n_tiles, has_sample0;
+  float disparity_smoothness, velocity_scale;
+  const float* loss_partials;   /* (n_scales, b, n_tiles) */
+  const float* sample_w;        /* (b) local slice of the global weights */
+  const float* sample_w_global; /* (b_global) */
+  const float* disp[4];         /* (b,1,h>>s,w>>s) */
+  const float* color[4];        /* (b,3,h>>s,w>>s) inputs['rgb',0,s] */
+  const float* translation;     /* (2,b,3) */
+  const double* rel_dist;       /* (2,b): relative_distance 0 and 1 */
+  float* losses;                /* (24) */
+  float* smooth_grad;           /* (n_scales, 2*(b_global+1)+1) */
+} clslam_loss_args;
+int clslam_loss_finalize(const clslam_loss_args* a, void* stream);
+/* d(loss)/d(disp_s): transpose of the bilinear up-sampling applied to ddisp_full[s], plus the
+ * smoothness terms, times sigmoid'; writes dz of dispconv_s (b,1,h>>s,w>>s). */
+int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* smooth_grad, int b_global,
+                     int has_sample0, int b, int h, int w, int scale, float* dz_disp, void* stream);
+
+/* ---- optimiser ----------------------------------------------------------------------------
+ * torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as built at
+ * depth_pose_prediction.py:203 and stepped at :313, over one flat fp32 buffer.  `step` is the
+ * 1-based step number AFTER this update; if step_dev != NULL it is read from (and incremented on)
+ * the device instead, which makes the call CUDA-graph replayable. */
+int clslam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                     double lr, double beta1, double beta2, double eps, int step, int* step_dev,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CLSLAM_B200_H */

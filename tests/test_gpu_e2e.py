@@ -1,0 +1,167 @@
+"""End-to-end parity of the drop-in DepthPosePrediction (CUDA, through the C ABI) against
+(1) fixtures produced by the UNMODIFIED reference (tests/golden, oracle/make_golden.py) and
+(2) the CPU oracle run live on the same seeded inputs.
+
+Tolerance (BASELINE.json north_star): disparity and pose within 1e-4 relative on same-weights
+outputs.  Gradients are compared per tensor (norm + strided samples); post-Adam results against
+the reference's own self-divergence envelope."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
+from oracle import clslam_oracle as orc
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / 'golden'
+REL_TOL = 1e-4
+
+
+def rel(a, b):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def build(name, **kw):
+    rec = np.load(GOLDEN / f'{name}.npz')
+    b, h, w, coherent, max_depth, seed = rec['meta']
+    b, h, w, seed = int(b), int(h), int(w), int(seed)
+    max_depth = None if max_depth < 0 else float(max_depth)
+    pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b, max_depth=max_depth), **kw)
+    params = orc.make_params(0)
+    for n in orc.NET_NAMES:
+        pred.models[n].load_state_dict(params[n])
+    batch = orc.make_batch(b, h, w, seed=seed, coherent=bool(coherent))
+    noise = orc.make_noise(b, h, w, seed=seed)
+    pred.noise_provider = lambda s, shape: noise[s]
+    return rec, pred, params, batch, noise, (b, h, w, max_depth)
+
+
+CASES = ['small_b2', 'small_b3_coherent', 'small_b1_maxdepth', 'full_b1', 'full_b2_coherent']
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_process_batch_matches_reference(name):
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build(name)
+    pred._set_adapt(True)
+    inputs = dict(batch)
+    outputs, losses = pred._process_batch(inputs)
+    torch.cuda.synchronize()
+    assert all(v.is_cuda for v in inputs.values())            # caller's dict now holds device tensors (:916-917)
+    sub = int(rec['subsample'][0])
+    for s in range(4):
+        assert outputs[('disp', s)].shape == (b, 1, h >> s, w >> s)
+        assert rel(outputs[('disp', s)].cpu().numpy(), rec[f'disp_{s}']) < REL_TOL, f'disp {s}'
+        assert rel(outputs[('depth', s)][:, :, ::sub, ::sub].cpu().numpy(), rec[f'depth_{s}_sub']) < REL_TOL
+        for f in (-1, 1):
+            assert rel(outputs[('rgb', f, s)][:, :, ::sub, ::sub].cpu().numpy(), rec[f'rgb_{f}_{s}_sub']) < 5e-4
+    for f in (-1, 1):
+        assert outputs[('axis_angle', 0, f)].shape == (b, 1, 3)
+        assert rel(outputs[('axis_angle', 0, f)].cpu().numpy(), rec[f'axis_angle_{f}']) < REL_TOL
+        assert rel(outputs[('translation', 0, f)].cpu().numpy(), rec[f'translation_{f}']) < REL_TOL
+        assert rel(outputs[('cam_T_cam', 0, f)].cpu().numpy(), rec[f'cam_T_cam_{f}']) < REL_TOL
+    keys = [k[5:] for k in rec.files if k.startswith('loss:')]
+    assert set(keys) == set(losses.keys()) and len(losses) == 19
+    assert losses['depth_loss'] is losses['loss'] and losses['loss'].shape == (1,)
+    for k in keys:
+        np.testing.assert_allclose(losses[k].detach().reshape(-1).cpu().numpy(), rec['loss:' + k], rtol=1e-4, atol=1e-8,
+                                   err_msg=k)
+
+    # gradients of the 36 trainable tensors
+    pred.backward()
+    torch.cuda.synchronize()
+    grads = pred.gradients()
+    assert len(grads) == 36
+    worst = 0.0
+    for (net, key), g in grads.items():
+        gn = float(rec[f'grad_norm:{net}:{key}'][0])
+        got = g.detach().cpu().contiguous()
+        err = abs(float(got.double().norm()) - gn) / (gn + 1e-30)
+        worst = max(worst, err)
+        assert err < 2e-3, (net, key, err)
+        idx = torch.linspace(0, got.numel() - 1, min(64, got.numel())).long()
+        samp = got.reshape(-1)[idx].numpy()
+        scale = gn / np.sqrt(got.numel())
+        assert np.abs(samp - rec[f'grad_sample:{net}:{key}']).max() < 5e-3 * scale * 30 + 1e-9, (net, key)
+
+
+@pytest.mark.parametrize('name', ['small_b2', 'small_b3_coherent'])
+def test_matches_live_oracle_gradients_elementwise(name):
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build(name)
+    adapter = orc.OracleAdapter(params, orc.OracleConfig(h, w, b, max_depth=max_depth))
+    _, ref_losses = adapter.step(batch, noise)
+    ref_grads = adapter.grads()
+    pred._set_adapt(True)
+    _, losses = pred._process_batch(dict(batch))
+    pred.backward()
+    torch.cuda.synchronize()
+    assert abs(float(losses['loss']) - float(ref_losses['loss'])) < 1e-5 * abs(float(ref_losses['loss']))
+    for (net, key), g in pred.gradients().items():
+        ref = ref_grads[(net, key)]
+        got = g.detach().cpu()
+        denom = float(ref.double().norm()) + 1e-30
+        assert float((got.double() - ref.double()).norm()) / denom < 2e-3, (net, key)
+
+
+@pytest.mark.parametrize('name', ['small_b2', 'full_b1'])
+@pytest.mark.parametrize('graph', [False, True])
+def test_adapt_steps(name, graph):
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build(name, use_cuda_graph=graph)
+    out1, losses1 = pred.adapt(dict(batch), dict(batch), steps=1)
+    np.testing.assert_allclose(losses1['loss'].cpu().numpy(), rec['loss:loss'], rtol=1e-4)
+    # after ONE Adam update: |delta| ~ lr; sign must agree wherever the reference gradient is not ~0
+    agree, total = 0, 0
+    for net in ('depth_decoder', 'pose_decoder'):
+        sd = pred.models[net].state_dict()
+        for key, _, _ in orc.net_layouts()[net]:
+            delta = (sd[key].cpu() - params[net][key]).reshape(-1)
+            idx = torch.linspace(0, delta.numel() - 1, min(64, delta.numel())).long()
+            got, ref = delta[idx].numpy(), rec[f'delta1_sample:{net}:{key}']
+            strong = np.abs(ref) > 5e-5
+            agree += int((np.abs(got - ref)[strong] < 2e-5).sum()); total += int(strong.sum())
+            assert np.abs(got).max() <= 1.01e-4 + 1e-7
+    assert agree >= 0.98 * total, (agree, total)
+    out2, losses2 = pred.adapt(dict(batch), dict(batch), steps=1)
+    np.testing.assert_allclose(losses2['loss'].cpu().numpy(), rec['loss2'], rtol=2e-3)
+    # steps=3 in one call (graph replay path when enabled) keeps the loss finite and decreasing-ish
+    out3, losses3 = pred.adapt(dict(batch), dict(batch), steps=3)
+    assert np.isfinite(float(losses3['loss']))
+    sd = pred.optimizer.state_dict()
+    assert len(sd['state']) == 36 and int(float(next(iter(sd['state'].values()))['step'])) == 5
+
+
+def test_predict_pose_and_encoder_callable():
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build('small_b2')
+    pred.is_trained = True
+    tr, cov = pred.predict_pose(batch[('rgb', 0, 0)][0], batch[('rgb', 1, 0)][0], as_numpy=True)
+    assert tr.shape == (4, 4) and np.array_equal(cov, np.eye(6, dtype=cov.dtype))
+    assert rel(tr, rec['predict_pose']) < REL_TOL
+    pred._set_eval()
+    with torch.no_grad():
+        feats = pred.models['depth_encoder'](batch[('rgb', 0, 0)][:1].to(pred.device))       # slam/slam.py:143-147
+    assert [f.shape[1] for f in feats] == [64, 64, 128, 256, 512]
+    assert rel(feats[4].mean(-1).mean(-1).cpu().numpy(), rec['buffer_feature']) < REL_TOL
+
+
+def test_inference_only_adapt_and_checkpoint_roundtrip(tmp_path):
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build('small_b1_maxdepth')
+    outputs, losses = pred.adapt(dict(batch), None)                    # adaptation: false path (:314-317)
+    np.testing.assert_allclose(losses['loss'].cpu().numpy(), rec['loss:loss'], rtol=1e-4)
+    pred.adapt(dict(batch), dict(batch), steps=2)
+    pred.log_path = tmp_path
+    pred.save_model()
+    folder = tmp_path / 'models' / 'weights_000'
+    for n in orc.NET_NAMES:
+        sd = torch.load(folder / f'{n}.pth', map_location='cpu')
+        assert list(sd.keys()) == [k for k, _, _ in orc.net_layouts()[n]]
+        assert all(v.is_contiguous() for v in sd.values())
+    cfg = Config(batch_size=b, max_depth=max_depth, load_weights_folder=folder)
+    pred2 = DepthPosePrediction(DatasetConfig(height=h, width=w), cfg)
+    pred2.load_model(load_optimizer=True)
+    pred2.noise_provider = pred.noise_provider
+    o1, l1 = pred.adapt(dict(batch), dict(batch), steps=1)
+    o2, l2 = pred2.adapt(dict(batch), dict(batch), steps=1)
+    assert float(l1['loss']) == float(l2['loss'])
+    assert torch.equal(pred._flat.params, pred2._flat.params)
