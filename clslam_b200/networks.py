@@ -198,8 +198,12 @@ class FlatParams:
             entries.append(('depth_decoder', path, co, ci, k))
         for path, co, ci, k in pose_decoder_spec():
             entries.append(('pose_decoder', path, co, ci, k))
-        total = sum(co * ci * k * k + co for _, _, co, ci, k in entries)
+        # every tensor starts on a 256-byte boundary (float4 / TMA alignment); the padding elements stay 0
+        def aligned(n):
+            return (n + 63) // 64 * 64
+        total = sum(aligned(co * ci * k * k) + aligned(co) for _, _, co, ci, k in entries)
         self.numel = total
+        self.numel_logical = sum(co * ci * k * k + co for _, _, co, ci, k in entries)
         self.params = torch.zeros(total, device=device)
         self.grads = torch.zeros(total, device=device)
         self.exp_avg = torch.zeros(total, device=device)
@@ -210,7 +214,7 @@ class FlatParams:
         mods = {'depth_decoder': depth_decoder, 'pose_decoder': pose_decoder}
         for net, path, co, ci, k in entries:
             wn = co * ci * k * k
-            info = dict(w_off=off, w_numel=wn, b_off=off + wn, co=co, ci=ci, k=k)
+            info = dict(w_off=off, w_numel=wn, b_off=off + aligned(wn), co=co, ci=ci, k=k)
             self.index[(net, path)] = info
             holder = mods[net].get_submodule(path)
             w_view = self.view_weight(self.params, info)
@@ -223,7 +227,7 @@ class FlatParams:
             holder.bias = nn.Parameter(b_view)
             holder.weight.grad = self.view_weight(self.grads, info)
             holder.bias.grad = self.grads[info['b_off']:info['b_off'] + co]
-            off += wn + co
+            off += aligned(wn) + aligned(co)
 
     @staticmethod
     def view_weight(flat: torch.Tensor, info) -> torch.Tensor:

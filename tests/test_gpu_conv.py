@@ -154,11 +154,12 @@ def test_maxpool_and_stage():
     assert cabi.rel_err(cabi.nchw(y), ref) < 1e-7
     a, b = torch.rand(2, 3, 8, 12), torch.rand(2, 3, 8, 12)
     out = torch.empty(2, 8, 12, 8, device='cuda')
-    L.check(lib.clslam_stage_images(a.cuda().data_ptr(), b.cuda().data_ptr(), out.data_ptr(), 2, 8, 12, 8, cabi.stream()))
+    ac, bc = a.cuda(), b.cuda()
+    L.check(lib.clslam_stage_images(ac.data_ptr(), bc.data_ptr(), out.data_ptr(), 2, 8, 12, 8, cabi.stream()))
     ref8 = torch.cat([(torch.cat([a, b], 1) - 0.45) / 0.225, torch.zeros(2, 2, 8, 12)], 1)
     assert cabi.rel_err(cabi.nchw(out), ref8) < 1e-6
     out4 = torch.empty(2, 8, 12, 4, device='cuda')
-    L.check(lib.clslam_stage_images(a.cuda().data_ptr(), None, out4.data_ptr(), 2, 8, 12, 4, cabi.stream()))
+    L.check(lib.clslam_stage_images(ac.data_ptr(), None, out4.data_ptr(), 2, 8, 12, 4, cabi.stream()))
     ref4 = torch.cat([(a - 0.45) / 0.225, torch.zeros(2, 1, 8, 12)], 1)
     assert cabi.rel_err(cabi.nchw(out4), ref4) < 1e-6
 
