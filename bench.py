@@ -48,6 +48,8 @@ def parse():
     ap.add_argument('--no-op-profile', action='store_true')
     ap.add_argument('--cpu-steps', type=int, default=8)
     ap.add_argument('--op-table', default=None, help='write the per-op timing table (JSON) here')
+    ap.add_argument('--profiler-range', action='store_true',
+                    help='cudaProfilerStart/Stop around the timed `value` loop (ncu --profile-from-start off)')
     return ap.parse_args()
 
 
@@ -243,6 +245,8 @@ def run_ours(args):
     pred._set_weights(eng, None)
     evs = []
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
@@ -253,6 +257,8 @@ def run_ours(args):
         e1.record()
         evs.append((e0, e1))
     barrier()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     wall_value = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(c) for a, c in evs)
     _, losses = pred._collect(eng)                      # NaN check of the whole timed run

@@ -364,12 +364,12 @@ def photometric_error(pred: Tensor, target: Tensor) -> Tensor:
     return 0.85 * ssim_loss_map(pred, target).mean(1, True) + 0.15 * l1
 
 
-def smoothness_reference_quirk(norm_disp: Tensor, img: Tensor) -> Tensor:
+def smoothness_reference_quirk(norm_disp: Tensor, img: Tensor, n_terms: Optional[int] = None) -> Tensor:
     """depth_pose_prediction.py:1148-1176 *as executed* with an all-true mask:
     the first masked_select flattens the edge-weighted gradients to 1-D, after which the
     per-sample loop indexes that flat vector by sample number, so "sample i" receives the
     x- and y-terms at row 0, column i of batch element 0."""
-    b = norm_disp.shape[0]
+    b = norm_disp.shape[0] if n_terms is None else n_terms     # n_terms: global batch when sharded
     gx = (norm_disp[:, :, :, :-1] - norm_disp[:, :, :, 1:]).abs()
     gy = (norm_disp[:, :, :-1, :] - norm_disp[:, :, 1:, :]).abs()
     gx = gx * torch.exp(-(img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, True))
@@ -421,9 +421,14 @@ def predict_poses(params: Dict[str, StateDict], batch: Dict[object, Tensor]) -> 
 
 def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg: OracleConfig,
                   noise: Sequence[Tensor], sample_weights: Optional[Tensor] = None,
+                  smooth_weights: Optional[Tensor] = None, with_smooth: bool = True,
                   ) -> Tuple[Dict[object, Tensor], Dict[str, Tensor]]:
     """depth_pose_prediction.py:906-923 (+ :976-1120).  ``noise[s]`` replaces the
-    ``torch.randn`` draw of scale s (unscaled standard normal, (B,2,H,W))."""
+    ``torch.randn`` draw of scale s (unscaled standard normal, (B,2,H,W)).
+
+    Sharded evaluation (tests of the data-parallel host logic): ``sample_weights`` is the local
+    slice of the global weights; the rank holding global sample 0 passes the GLOBAL weight vector
+    as ``smooth_weights`` (one quirk term per global sample), the others ``with_smooth=False``."""
     h, w = cfg.height, cfg.width
     outputs: Dict[object, Tensor] = {}
     feats = encoder_forward(params['depth_encoder'], batch[('rgb_aug', 0, 0)])
@@ -455,11 +460,13 @@ def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg
 
         disp = outputs[('disp', s)]
         norm_disp = disp / (disp.mean(2, True).mean(3, True) + 1e-7)
-        if cfg.smooth_mode == 'reference':
-            smooth = smoothness_reference_quirk(norm_disp, batch[('rgb', 0, s)])
+        if not with_smooth:
+            smooth = torch.zeros(())
+        elif cfg.smooth_mode == 'reference':
+            sw = sample_weights if smooth_weights is None else smooth_weights
+            smooth = (smoothness_reference_quirk(norm_disp, batch[('rgb', 0, s)], sw.numel()) * sw).sum()
         else:
-            smooth = smoothness_intended(norm_disp, batch[('rgb', 0, s)])
-        smooth = (smooth * sample_weights).sum()
+            smooth = (smoothness_intended(norm_disp, batch[('rgb', 0, s)]) * sample_weights).sum()
         losses[f'smooth_loss/scale_{s}'] = smooth
         reg = cfg.disparity_smoothness / (2 ** s) * smooth
         losses[f'reg_loss/scale_{s}'] = reg
@@ -509,11 +516,12 @@ class OracleAdapter:
         self.optimizer = torch.optim.Adam(self.trainable, cfg.learning_rate)
 
     def step(self, batch: Dict[object, Tensor], noise: Sequence[Tensor],
-             sample_weights: Optional[Tensor] = None):
-        outputs, losses = process_batch(self.params, batch, self.cfg, noise, sample_weights)
+             sample_weights: Optional[Tensor] = None, update: bool = True, **kw):
+        outputs, losses = process_batch(self.params, batch, self.cfg, noise, sample_weights, **kw)
         self.optimizer.zero_grad()
         losses['loss'].backward()
-        self.optimizer.step()
+        if update:
+            self.optimizer.step()
         return outputs, losses
 
     def grads(self) -> Dict[Tuple[str, str], Tensor]:

@@ -1,0 +1,116 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/clslam_b200.h declares,
+the ctypes binding lists exactly those symbols, the drop-in class mirrors the reference's API surface
+and checkpoint key names, and the product path fails loudly without CUDA (no CPU fallback)."""
+import ctypes
+import re
+from pathlib import Path
+
+import pytest
+import torch
+
+from clslam_b200 import Config, DatasetConfig, DepthPosePrediction, _lib
+from clslam_b200.sharding import global_sample_weights, shard_batch, shard_range
+from oracle import clslam_oracle as orc
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_functions():
+    text = (ROOT / 'include' / 'clslam_b200.h').read_text()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(clslam_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 25
+    assert _lib.LIB_PATH.exists(), 'build the library first: python -m clslam_b200.build'
+    lib = ctypes.CDLL(str(_lib.LIB_PATH))
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/clslam_b200.h but not exported'
+    assert sorted(_lib.SIGNATURES) == names, 'ctypes binding and header disagree'
+    assert _lib.load().clslam_abi_version() == 1
+    assert _lib.load().clslam_launch_count() >= 0
+
+
+def test_struct_layouts_match_header_field_order():
+    text = (ROOT / 'include' / 'clslam_b200.h').read_text()
+    body = re.search(r'typedef struct clslam_conv_desc \{(.*?)\} clslam_conv_desc;', text, re.S).group(1)
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = [f.strip() for decl in re.findall(r'int ([^;]+);', body) for f in decl.split(',')]
+    assert fields == [n for n, _ in _lib.ConvDesc._fields_]
+    assert ctypes.sizeof(_lib.ConvDesc) == 4 * len(fields)
+
+
+def test_state_dict_keys_and_shapes_match_reference_layout():
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), Config(batch_size=2), device='cpu')
+    layouts = orc.net_layouts()
+    for net in orc.NET_NAMES:
+        sd = pred.models[net].state_dict()
+        assert list(sd.keys()) == [k for k, _, _ in layouts[net]]
+        for k, shape, _ in layouts[net]:
+            assert tuple(sd[k].shape) == tuple(shape), (net, k)
+    assert sum(p.numel() for p in pred.parameters_to_train) == 27855728
+    assert pred._flat.numel_logical == 4467296
+    # loading reference-format weights keeps the flat (kernel-layout) storage in sync
+    params = orc.make_params(0)
+    for net in orc.NET_NAMES:
+        pred.models[net].load_state_dict(params[net])
+    w = params['pose_decoder']['pose_0.weight']
+    info = pred._flat.index[('pose_decoder', 'pose_0')]
+    flat = pred._flat.params[info['w_off']:info['w_off'] + info['w_numel']]
+    assert torch.equal(flat, w.permute(0, 2, 3, 1).reshape(-1))
+    assert info['w_off'] % 64 == 0 and info['b_off'] % 64 == 0
+    # Adam facade speaks torch.optim.Adam's state_dict format over all 4 nets' params (:183-203)
+    osd = pred.optimizer.state_dict()
+    assert len(osd['param_groups'][0]['params']) == len(pred.parameters_to_train)
+    assert osd['param_groups'][0]['lr'] == 1e-4 and osd['param_groups'][0]['betas'] == (0.9, 0.999)
+
+
+def test_api_surface_and_errors():
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), Config(batch_size=2, train_set='all', val_set=0),
+                               device='cpu')
+    assert pred.train_set == (1, 2, 4, 5, 6, 7, 8, 9, 10) and pred.val_set == (0,)
+    for attr in ('adapt', '_process_batch', 'predict_pose', 'load_model', 'save_model', '_set_eval', '_set_adapt', 'models',
+                 'device', 'min_depth', 'max_depth', 'optimizer', 'lr_scheduler', 'parameters_to_train', 'frame_ids'):
+        assert hasattr(pred, attr), attr
+    assert pred.frame_ids == (0, -1, 1) and set(pred.models) == set(orc.NET_NAMES)
+    with pytest.raises(ValueError):
+        DepthPosePrediction(DatasetConfig(height=64, width=96), Config(train_set='some'), device='cpu')
+    with pytest.raises(ValueError):
+        DepthPosePrediction(DatasetConfig(dataset='Cityscapes', height=64, width=96), Config(train_set=3, val_set='x'),
+                            device='cpu')
+    pred._set_adapt(True)
+    assert not any(p.requires_grad for n, p in pred.models['depth_encoder'].named_parameters())
+    assert all(p.requires_grad for p in pred.models['depth_decoder'].parameters())
+    with pytest.raises(NotImplementedError):
+        pred._set_adapt(freeze_encoder=False)
+
+
+def test_no_cpu_fallback():
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), Config(batch_size=1), device='cpu')
+    batch = orc.make_batch(1, 64, 96)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pred.adapt(dict(batch), dict(batch))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pred.models['depth_encoder'](batch[('rgb', 0, 0)])
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        pred.predict_pose(batch[('rgb', 0, 0)][0], batch[('rgb', 1, 0)][0])
+
+
+def test_product_package_never_imports_the_oracle():
+    for f in (ROOT / 'clslam_b200').rglob('*.py'):
+        src = f.read_text()
+        assert 'oracle' not in re.sub(r'#.*', '', src).replace('"""', ''), f'{f} mentions the oracle'
+
+
+def test_sharding_host_logic():
+    assert shard_range(32, 3, 8) == (12, 16)
+    with pytest.raises(ValueError):
+        shard_range(7, 0, 2)
+    w = global_sample_weights(4, 0.7, 0)
+    assert torch.allclose(w, torch.tensor([0.7, 0.1, 0.1, 0.1]))
+    assert torch.allclose(global_sample_weights(3), torch.full((3,), 1 / 3))
+    batch = orc.make_batch(4, 64, 96)
+    sh = shard_batch(batch, 1, 2)
+    assert sh[('rgb', 0, 0)].shape[0] == 2 and torch.equal(sh['index'], torch.tensor([2, 3]))
