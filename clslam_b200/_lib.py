@@ -52,6 +52,9 @@ SIGNATURES = {
     'clslam_launch_count': (c_longlong, []),
     'clslam_set_device': (c_int, [c_int]),
     'clslam_stage_images': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'clslam_set_conv_mode': (c_int, [c_int]),
+    'clslam_get_conv_mode': (c_int, []),
+    'clslam_debug_tc_stamps': (c_int, [c_void_p]),
     'clslam_conv_fwd_workspace_bytes': (c_longlong, [POINTER(ConvDesc)]),
     'clslam_conv_fwd': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_longlong, c_void_p]),

@@ -3,6 +3,7 @@
 // reference call sites each entry point replaces.
 #include "conv_ops.cuh"
 #include "gemm_core.cuh"
+#include "gemm_tc.cuh"
 
 namespace clslam {
 
@@ -12,6 +13,24 @@ namespace clslam {
 struct AFwd {
   ConvIn c;
   int M, K;
+  // element API used by the tcgen05 stager (gemm_tc.cuh)
+  static constexpr bool kKContig = true;
+  struct Row { int n, ih0, iw0; };
+  using KState = KTap;
+  __device__ Row decode(int m) const {
+    Row r{-1, 0, 0};
+    if (m >= 0 && m < M) {
+      const int hw = c.ho * c.wo;
+      r.n = m / hw;
+      const int rem = m - r.n * hw;
+      const int oh = rem / c.wo;
+      r.ih0 = oh * c.stride - c.pad;
+      r.iw0 = (rem - oh * c.wo) * c.stride - c.pad;
+    }
+    return r;
+  }
+  __device__ KState kdecode(int k) const { return ktap_decode(k, c.ci, c.kw); }
+  __device__ float4 at(const Row& r, const KState& t) const { return r.n >= 0 ? conv_in_gather(c, r.n, r.ih0, r.iw0, t) : f4zero(); }
   template <int R> struct Frag {
     int n[KContigMap<R>::kVec], oh[KContigMap<R>::kVec], ow[KContigMap<R>::kVec];
     float4 r[KContigMap<R>::kVec];
@@ -49,6 +68,12 @@ struct AFwd {
 struct BWeightK {
   const float* w;
   int N, K;
+  static constexpr bool kKContig = true;
+  struct Row { const float* p; };
+  using KState = int;
+  __device__ Row decode(int n) const { return Row{(n >= 0 && n < N) ? w + (size_t)n * K : nullptr}; }
+  __device__ KState kdecode(int k) const { return k; }
+  __device__ float4 at(const Row& r, const KState& k) const { return r.p ? ld4(r.p + k) : f4zero(); }
   template <int R> struct Frag { const float* p[KContigMap<R>::kVec]; float4 r[KContigMap<R>::kVec]; };
   template <int R> __device__ void init(Frag<R>& f, int n0, int tid) const {
     using Map = KContigMap<R>;
@@ -75,6 +100,19 @@ struct BWeightK {
 struct ADgrad {
   DgradIn g;
   int M, K;
+  static constexpr bool kKContig = true;
+  using Row = DgradRow;
+  using KState = KTap;
+  __device__ Row decode(int m) const {
+    if (m < 0 || m >= M) return Row{-1, 0, 0, 0, 0};
+    const int hw = g.hl * g.wl;
+    const int n = m / hw;
+    const int rem = m - n * hw;
+    const int oh = rem / g.wl;
+    return dgrad_row(g, n, oh, rem - oh * g.wl);
+  }
+  __device__ KState kdecode(int k) const { return ktap_decode(k, g.co, g.kw); }
+  __device__ float4 at(const Row& r, const KState& t) const { return r.n >= 0 ? dgrad_in_gather(g, r, t) : f4zero(); }
   template <int R> struct Frag {
     int n[KContigMap<R>::kVec], oh[KContigMap<R>::kVec], ow[KContigMap<R>::kVec];
     float4 r[KContigMap<R>::kVec];
@@ -124,6 +162,15 @@ namespace clslam {
 
 struct BWeightDgradOp {
   BWeightDgrad b;
+  static constexpr bool kKContig = false;
+  using RowState = int;                 // input-channel index, -1 = out of range
+  using KState = const float*;          // row of W for this (tap, co)
+  __device__ RowState rdecode(int n) const { return n < b.N ? n : -1; }
+  __device__ KState kdecode(int k) const {
+    const int tap = k / b.co, o = k - tap * b.co;
+    return b.w + ((size_t)o * b.taps + tap) * b.ci_full;
+  }
+  __device__ float4 at4(const KState& p, const RowState& n) const { return n >= 0 ? ld4(p + n) : f4zero(); }
   template <int R> struct Frag { int n0; float4 r[RContigMap<R>::kVec]; };
   template <int R> __device__ void init(Frag<R>& f, int n0, int) const { f.n0 = n0; }
   template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
@@ -149,6 +196,12 @@ struct BWeightDgradOp {
 struct AWgradDz {
   const float* dz;
   int co, P;
+  static constexpr bool kKContig = false;
+  using RowState = int;
+  using KState = const float*;
+  __device__ RowState rdecode(int m) const { return m < co ? m : -1; }
+  __device__ KState kdecode(int p) const { return dz + (size_t)p * co; }
+  __device__ float4 at4(const KState& p, const RowState& m) const { return m >= 0 ? ld4(p + m) : f4zero(); }
   template <int R> struct Frag { int m0; float4 r[RContigMap<R>::kVec]; };
   template <int R> __device__ void init(Frag<R>& f, int m0, int) const { f.m0 = m0; }
   template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
@@ -169,6 +222,24 @@ struct AWgradDz {
 struct BWgradIn {
   ConvIn c;
   int Kw;   // kh*kw*ci
+  static constexpr bool kKContig = false;
+  using RowState = KTap;                // (r, s, ch) of this weight column; r = -1: out of range
+  struct KState { int n, ih0, iw0; };   // the pixel
+  // column Kw is a virtual all-ones column: its GEMM output is the bias gradient sum_p dz[p][co]
+  __device__ RowState rdecode(int kidx) const {
+    return kidx < Kw ? ktap_decode(kidx, c.ci, c.kw) : (kidx == Kw ? KTap{-2, 0, 0} : KTap{-1, 0, 0});
+  }
+  __device__ KState kdecode(int p) const {
+    const int hw = c.ho * c.wo;
+    const int n = p / hw;
+    const int rem = p - n * hw;
+    const int oh = rem / c.wo;
+    return KState{n, oh * c.stride - c.pad, (rem - oh * c.wo) * c.stride - c.pad};
+  }
+  __device__ float4 at4(const KState& px, const RowState& t) const {
+    if (t.r >= 0) return conv_in_gather(c, px.n, px.ih0, px.iw0, t);
+    return t.r == -2 ? make_float4(1.f, 0.f, 0.f, 0.f) : f4zero();
+  }
   template <int R> struct Frag { int n0; float4 r[RContigMap<R>::kVec]; };
   template <int R> __device__ void init(Frag<R>& f, int n0, int) const { f.n0 = n0; }
   template <int R> __device__ void fetch(Frag<R>& f, int k0, int k_end, int tid) const {
@@ -199,6 +270,24 @@ struct EpiFwd {
   static constexpr bool kBias = false;
   float* y; const float* scale; const float* shift; const float* res;
   int N, act;
+  // tensor-core kernel: per-column parameters are staged in shared memory once per CTA
+  __device__ void tc_prologue(float* sp, int n0, int bn, int n_total, int tid) const {
+    for (int j = tid; j < bn; j += kTcThreads) {
+      const int n = n0 + j;
+      sp[j] = (scale && n < n_total) ? scale[n] : 1.f;
+      sp[bn + j] = (shift && n < n_total) ? shift[n] : 0.f;
+    }
+  }
+  __device__ void tc_store(int m, int n, const float (&v)[4], const float* sp, int nl, int bn) const {
+    const size_t off = (size_t)m * N + n;
+    float4 r4 = f4zero();
+    if (res) r4 = *reinterpret_cast<const float4*>(res + off);
+    const float rr[4] = {r4.x, r4.y, r4.z, r4.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[j] = act_apply(v[j] * sp[nl + j] + sp[bn + nl + j] + rr[j], act);
+    *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+  }
   __device__ void store(int m, int n, const float (&v)[4]) const {
     float o[4];
     const size_t off = (size_t)m * N + n;
@@ -217,6 +306,8 @@ struct EpiFwd {
 
 struct EpiDgrad {
   static constexpr bool kBias = false;
+  __device__ void tc_prologue(float*, int, int, int, int) const {}
+  __device__ void tc_store(int m, int n, const float (&v)[4], const float*, int, int) const { store(m, n, v); }
   float* dzp; const float* y_prev; int act_prev;
   const float* disp_dz; const float* disp_w;
   int N;          // channels of dX
@@ -245,11 +336,26 @@ struct EpiDgrad {
 
 struct EpiWgrad {
   static constexpr bool kBias = true;
+  __device__ void tc_prologue(float*, int, int, int, int) const {}
+  __device__ void tc_store(int m, int n, const float (&v)[4], const float*, int, int) const { store(m, n, v); }
   float* dw; float* db; int N;
   __device__ void store(int m, int n, const float (&v)[4]) const {
     *reinterpret_cast<float4*>(dw + (size_t)m * N + n) = make_float4(v[0], v[1], v[2], v[3]);
   }
   __device__ void store_bias(int m, float v) const { if (db) db[m] = v; }
+};
+
+// tensor-core wgrad: N' = Kw + 4, column Kw carries the bias gradient (see BWgradIn::rdecode)
+struct EpiWgradTc {
+  static constexpr bool kBias = false;
+  __device__ void tc_prologue(float*, int, int, int, int) const {}
+  __device__ void tc_store(int m, int n, const float (&v)[4], const float*, int, int) const { store(m, n, v); }
+  float* dw; float* db; int Kw;
+  __device__ void store(int m, int n, const float (&v)[4]) const {
+    if (n < Kw) *reinterpret_cast<float4*>(dw + (size_t)m * Kw + n) = make_float4(v[0], v[1], v[2], v[3]);
+    else if (n == Kw && db) db[m] = v[0];
+  }
+  __device__ void store_bias(int, float) const {}
 };
 
 // =========================== launch plumbing ================================================
@@ -331,6 +437,93 @@ static int launch_gemm(const TilePlan& p, const AOp& a, const BOp& b, const Epi&
   return rc;
 }
 
+// ---- tensor-core path -----------------------------------------------------------------------
+static int g_conv_mode = 1;      // 0 = exact fp32 CUDA-core path, 1 = tcgen05 3xBF16
+
+struct TcPlan { int bn; int gx, gy, splits, k_chunk; };
+
+static TcPlan plan_tc(int M, int N, int K) {
+  TcPlan p{};
+  p.bn = N >= 128 ? 128 : (N > 32 ? 64 : (N > 16 ? 32 : 16));
+  p.gx = (M + kTcBM - 1) / kTcBM;
+  p.gy = (N + p.bn - 1) / p.bn;
+  const int k_tiles = (K + kTcBK - 1) / kTcBK;
+  const long long tiles = (long long)p.gx * p.gy;
+  int s = 1;
+  const int target = num_sms();
+  if (tiles < target && k_tiles >= 4) {
+    s = (int)((target + tiles - 1) / tiles);
+    const int max_s = k_tiles / 2;              // at least 2 k-blocks (128 k) per split
+    if (s > max_s) s = max_s;
+    if (s > 32) s = 32;
+    if (s < 1) s = 1;
+  }
+  const int per = (k_tiles + s - 1) / s;
+  p.k_chunk = per * kTcBK;
+  p.splits = (k_tiles + per - 1) / per;
+  return p;
+}
+
+template <int BN, class AOp, class BOp, class Epi>
+static int launch_tc_bn(const TcPlan& p, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, float* ws,
+                        cudaStream_t st, const char* what) {
+  auto kern = gemm_tc_kernel<BN, AOp, BOp, Epi>;
+  constexpr int kSmem = TcSmem<BN, AOp, BOp>::kTotal;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(err)); return -3; }
+    attr_set = true;
+  }
+  dim3 grid(p.gx, p.gy, p.splits);
+  kern<<<grid, kTcThreads, kSmem, st>>>(a, b, e, M, N, K, p.k_chunk, ws);
+  return finish_launch(what);
+}
+
+template <class AOp, class BOp, class Epi>
+static int launch_gemm_tc(const TcPlan& p, const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, float* ws,
+                          long long ws_bytes, cudaStream_t st, const char* what) {
+  if (p.splits > 1) {
+    const long long need = ((long long)p.splits * M * N + (Epi::kBias ? (long long)p.splits * M : 0)) * 4;
+    if (ws == nullptr || ws_bytes < need) { set_error("%s: workspace too small (%lld < %lld)", what, ws_bytes, need); return -2; }
+  }
+  int rc;
+  switch (p.bn) {
+    case 128: rc = launch_tc_bn<128>(p, a, b, e, M, N, K, ws, st, what); break;
+    case 64: rc = launch_tc_bn<64>(p, a, b, e, M, N, K, ws, st, what); break;
+    case 32: rc = launch_tc_bn<32>(p, a, b, e, M, N, K, ws, st, what); break;
+    default: rc = launch_tc_bn<16>(p, a, b, e, M, N, K, ws, st, what); break;
+  }
+  if (rc) return rc;
+  if (p.splits > 1) {
+    const long long total4 = (long long)M * N / 4;
+    int blocks = (int)((total4 + 255) / 256);
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    if (blocks < 1) blocks = 1;
+    splitk_reduce_kernel<Epi><<<blocks, 256, 0, st>>>(e, ws, M, N, p.splits);
+    rc = finish_launch(what);
+  }
+  return rc;
+}
+
+// workspace need of either path (the larger, so that the mode can be switched at run time)
+static long long ws_need(int M, int N, int K, bool bias) {
+  const TilePlan p0 = plan_tiles(M, N, K, true);
+  const int n_tc = bias ? N + 4 : N;                       // tensor-core wgrad carries the bias in 4 extra columns
+  const TcPlan p1 = plan_tc(M, n_tc, K);
+  const long long a = p0.splits > 1 ? ((long long)p0.splits * M * N + (bias ? (long long)p0.splits * M : 0)) * 4 : 0;
+  const long long b = p1.splits > 1 ? (long long)p1.splits * M * n_tc * 4 : 0;
+  return a > b ? a : b;
+}
+
+template <class AOp, class BOp, class Epi>
+static int run_gemm(const AOp& a, const BOp& b, const Epi& e, int M, int N, int K, float* ws, long long ws_bytes,
+                    cudaStream_t st, const char* what) {
+  if (g_conv_mode == 1 && K >= 32)
+    return launch_gemm_tc(plan_tc(M, N, K), a, b, e, M, N, K, ws, ws_bytes, st, what);
+  return launch_gemm(plan_tiles(M, N, K, true), a, b, e, M, N, K, ws, ws_bytes, st, what);
+}
+
 static int check_desc(const clslam_conv_desc* d, const char* what) {
   if (!d) { set_error("%s: null descriptor", what); return -1; }
   if (d->ci % 4 != 0 || d->co % 4 != 0) { set_error("%s: channels must be multiples of 4 (ci=%d co=%d)", what, d->ci, d->co); return -1; }
@@ -347,11 +540,21 @@ using namespace clslam;
 
 extern "C" {
 
+int clslam_set_conv_mode(int mode) {
+  if (mode != 0 && mode != 1) { set_error("set_conv_mode: 0 (fp32 CUDA cores) or 1 (tcgen05 3xBF16)"); return -1; }
+  g_conv_mode = mode;
+  return 0;
+}
+int clslam_get_conv_mode(void) { return g_conv_mode; }
+int clslam_debug_tc_stamps(unsigned long long* out16) {
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out16, g_tc_stamps, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -1;
+}
+
 long long clslam_conv_fwd_workspace_bytes(const clslam_conv_desc* d) {
   if (check_desc(d, "conv_fwd_ws")) return -1;
   const int M = d->n * d->ho * d->wo, N = d->co, K = d->kh * d->kw * d->ci;
-  const TilePlan p = plan_tiles(M, N, K, true);
-  return p.splits > 1 ? (long long)p.splits * M * N * 4 : 0;
+  return ws_need(M, N, K, false);
 }
 
 int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const float* scale,
@@ -362,8 +565,7 @@ int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, 
   AFwd a{make_conv_in(*d, x, x2), M, K};
   BWeightK b{w, N, K};
   EpiFwd e{y, scale, shift, residual, N, d->act};
-  const TilePlan p = plan_tiles(M, N, K, true);
-  return launch_gemm(p, a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_fwd");
+  return run_gemm(a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_fwd");
 }
 
 static void dgrad_dims(const clslam_conv_desc* d, int& M, int& N, int& K, DgradIn& g, const float* dz) {
@@ -379,8 +581,7 @@ static void dgrad_dims(const clslam_conv_desc* d, int& M, int& N, int& K, DgradI
 long long clslam_conv_dgrad_workspace_bytes(const clslam_conv_desc* d) {
   if (check_desc(d, "conv_dgrad_ws")) return -1;
   int M, N, K; DgradIn g; dgrad_dims(d, M, N, K, g, nullptr);
-  const TilePlan p = plan_tiles(M, N, K, true);
-  return p.splits > 1 ? (long long)p.splits * M * N * 4 : 0;
+  return ws_need(M, N, K, false);
 }
 
 int clslam_conv_dgrad(const clslam_conv_desc* d, const float* dz, const float* w, const float* y_prev, int act_prev,
@@ -393,15 +594,13 @@ int clslam_conv_dgrad(const clslam_conv_desc* d, const float* dz, const float* w
   ADgrad a{g, M, K};
   BWeightDgradOp b{{w, N, d->ci, d->co, d->kh * d->kw}};
   EpiDgrad e{dz_prev, y_prev, act_prev, disp_dz, disp_w, N, g.hl, g.wl};
-  const TilePlan p = plan_tiles(M, N, K, true);
-  return launch_gemm(p, a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_dgrad");
+  return run_gemm(a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_dgrad");
 }
 
 long long clslam_conv_wgrad_workspace_bytes(const clslam_conv_desc* d) {
   if (check_desc(d, "conv_wgrad_ws")) return -1;
   const int M = d->co, N = d->kh * d->kw * d->ci, K = d->n * d->ho * d->wo;
-  const TilePlan p = plan_tiles(M, N, K, true);
-  return p.splits > 1 ? ((long long)p.splits * M * N + (long long)p.splits * M) * 4 : 0;
+  return ws_need(M, N, K, true);
 }
 
 int clslam_conv_wgrad(const clslam_conv_desc* d, const float* x, const float* x2, const float* dz, float* dw, float* db,
@@ -410,9 +609,13 @@ int clslam_conv_wgrad(const clslam_conv_desc* d, const float* x, const float* x2
   const int M = d->co, N = d->kh * d->kw * d->ci, K = d->n * d->ho * d->wo;
   AWgradDz a{dz, d->co, K};
   BWgradIn b{make_conv_in(*d, x, x2), N};
+  if (g_conv_mode == 1 && K >= 32) {
+    EpiWgradTc e{dw, db, N};
+    return launch_gemm_tc(plan_tc(M, N + 4, K), a, b, e, M, N + 4, K, (float*)workspace, workspace_bytes, as_stream(stream),
+                          "conv_wgrad");
+  }
   EpiWgrad e{dw, db, N};
-  const TilePlan p = plan_tiles(M, N, K, true);
-  return launch_gemm(p, a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_wgrad");
+  return run_gemm(a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_wgrad");
 }
 
 }  // extern "C"

@@ -58,6 +58,36 @@ CLSLAM_HD float4 conv_in_load(const ConvIn& c, int n, int oh, int ow, int k) {
   return conv_in_at(c, n, ih, iw, ch);
 }
 
+// ---- split form of the same gather for the tensor-core stager: k = (r, s, ch) is decoded once per
+// k block per thread (KTap), the pixel once per row (ih0 = oh*stride - pad, iw0 = ow*stride - pad).
+struct KTap { int r, s, ch; };
+CLSLAM_HD KTap ktap_decode(int k, int channels, int kw) {
+  KTap t;
+  const int tap = k / channels;
+  t.ch = k - tap * channels;
+  t.r = tap / kw;
+  t.s = tap - t.r * kw;
+  return t;
+}
+CLSLAM_HD float4 conv_in_gather(const ConvIn& c, int n, int ih0, int iw0, const KTap& t) {
+  int ih = ih0 + t.r, iw = iw0 + t.s;
+  if (c.pad_mode == CLSLAM_PAD_REFLECT) {
+    ih = reflect_idx(ih, c.hi);
+    iw = reflect_idx(iw, c.wi);
+  } else if (ih < 0 || ih >= c.hi || iw < 0 || iw >= c.wi) {
+    return f4zero();
+  }
+  if (c.in_mode == CLSLAM_IN_UPCAT) {
+    if (t.ch < c.c1) {
+      const int sh = (2 * c.h1 == c.hi) ? (ih >> 1) : (int)(((long long)ih * c.h1) / c.hi);
+      const int sw = (2 * c.w1 == c.wi) ? (iw >> 1) : (int)(((long long)iw * c.w1) / c.wi);
+      return ld4(c.x + (((size_t)n * c.h1 + sh) * c.w1 + sw) * c.c1 + t.ch);
+    }
+    return ld4(c.x2 + (((size_t)n * c.hi + ih) * c.wi + iw) * (c.ci - c.c1) + (t.ch - c.c1));
+  }
+  return ld4(c.x + (((size_t)n * c.hi + ih) * c.wi + iw) * c.ci + t.ch);
+}
+
 // ---- dgrad view: A[dX pixel][k], k = (r, s, co), co fastest ------------------------------
 // dX[n,h,w,:] = sum over taps of W^T . dZ gathered at the output positions whose receptive
 // field touches (h,w); with reflection padding the border rows/cols receive extra terms, and
@@ -107,6 +137,31 @@ CLSLAM_HD float4 dgrad_in_load(const DgradIn& g, int n, int oh, int ow, int k) {
       for (int ww = w_lo; ww < w_hi; ++ww) {
         dgrad_sources_1d(ww, s, g.pad, g.w, refl, [&](int sc) {
           f4add(acc, ld4(g.dz + (((size_t)n * g.h + sr) * g.w + sc) * g.co + ch));
+        });
+      }
+    });
+  }
+  return acc;
+}
+
+// split form for the tensor-core stager: footprint decoded once per row, tap once per k block
+struct DgradRow { int n, h_lo, h_hi, w_lo, w_hi; };
+CLSLAM_HD DgradRow dgrad_row(const DgradIn& g, int n, int oh, int ow) {
+  DgradRow r{n, oh, oh + 1, ow, ow + 1};
+  if (g.up) {
+    nearest_footprint(oh, g.hl, g.h, r.h_lo, r.h_hi);
+    nearest_footprint(ow, g.wl, g.w, r.w_lo, r.w_hi);
+  }
+  return r;
+}
+CLSLAM_HD float4 dgrad_in_gather(const DgradIn& g, const DgradRow& row, const KTap& t) {
+  const int refl = g.pad_mode == CLSLAM_PAD_REFLECT;
+  float4 acc = f4zero();
+  for (int hh = row.h_lo; hh < row.h_hi; ++hh) {
+    dgrad_sources_1d(hh, t.r, g.pad, g.h, refl, [&](int sr) {
+      for (int ww = row.w_lo; ww < row.w_hi; ++ww) {
+        dgrad_sources_1d(ww, t.s, g.pad, g.w, refl, [&](int sc) {
+          f4add(acc, ld4(g.dz + (((size_t)row.n * g.h + sr) * g.w + sc) * g.co + t.ch));
         });
       }
     });

@@ -72,6 +72,14 @@ int clslam_stage_images(const float* img_a, const float* img_b, float* out_nhwc,
  * the nearest-upsample + concat of networks/depth_decoder.py:56-66 (fused into the loader of
  * upconv_i_1) and PoseDecoder convs (networks/pose_decoder.py:40-47).
  *   scale may be NULL (=1); shift is the bias or the folded BatchNorm shift; residual may be NULL. */
+/* arithmetic of the three GEMM-shaped entry points below:
+ *   1 (default) = tcgen05 tensor cores, operands split on the fly into bf16 hi+lo, three products per k step
+ *                 (A_lo.B_hi + A_hi.B_lo + A_hi.B_hi), fp32 accumulation in TMEM;
+ *   0           = exact fp32 on the CUDA cores (parity anchor). */
+int clslam_set_conv_mode(int mode);
+int clslam_get_conv_mode(void);
+/* debug aid: clock64 stamps of CTA 0 of the last tensor-core GEMM launch (synchronises the device) */
+int clslam_debug_tc_stamps(unsigned long long* out16);
 long long clslam_conv_fwd_workspace_bytes(const clslam_conv_desc* d);
 int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, const float* w,
                     const float* scale, const float* shift, const float* residual, float* y,

@@ -12,6 +12,19 @@ from tests import cabi
 
 pytestmark = pytest.mark.gpu
 TOL = 2e-5      # fp32 accumulation-order noise relative to the output's max magnitude
+TOL_BY_MODE = {0: 2e-5,     # exact fp32 CUDA-core path
+               1: 6e-5}     # tcgen05, 3 x BF16 split operands (~2^-16 per operand), fp32 accumulation
+
+
+@pytest.fixture(autouse=True, params=[1, 0], ids=['tcgen05', 'fp32'])
+def conv_mode(request):
+    global TOL
+    lib = cabi.lib()
+    L.check(lib.clslam_set_conv_mode(request.param))
+    TOL = TOL_BY_MODE[request.param]
+    yield request.param
+    torch.cuda.synchronize()
+    L.check(lib.clslam_set_conv_mode(1))
 
 
 def rnd(*shape, seed=0, scale=1.0):
