@@ -162,11 +162,13 @@ def profile_ops(eng, pred, reps=5):
     flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=eng.device)
     times = [0.0] * len(plan.ops)
     for _ in range(reps):
-        for i, (name, fn, a) in enumerate(plan.ops[:eng.n_bwd_ops]):
+        for i, (name, fn, a, lane) in enumerate(plan.ops[:eng.n_bwd_ops]):
+            if fn is None:          # lane fork/join markers: the profile pass runs every op serially on one stream
+                continue
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            rc = fn(stream, *a)
+            rc = fn(stream, plan._ws_ptr[0], *a)
             e1.record()
             assert rc == 0, name
             e1.synchronize()
@@ -177,8 +179,10 @@ def profile_ops(eng, pred, reps=5):
         descs[f'upconv_{i}_{j}'] = v[0]
     for k, v in eng.pose_desc.items():
         descs[k] = v[0]
-    for i, (name, fn, a) in enumerate(plan.ops[:eng.n_bwd_ops]):
-        row = {'op': name, 'ms': times[i]}
+    for i, (name, fn, a, lane) in enumerate(plan.ops[:eng.n_bwd_ops]):
+        if fn is None:
+            continue
+        row = {'op': name, 'ms': times[i], 'lane': lane}
         model = op_model(eng, name)
         d = None
         if model is None and a and hasattr(a[0], 'kh'):

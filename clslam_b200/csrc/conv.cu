@@ -455,7 +455,8 @@ static TcPlan plan_tc(int M, int N, int K) {
     s = (int)((target + tiles - 1) / tiles);
     const int max_s = k_tiles / 2;              // at least 2 k-blocks (128 k) per split
     if (s > max_s) s = max_s;
-    if (s > 32) s = 32;
+    const int cap = ((long long)M * N <= 65536) ? 128 : 32;     // small outputs (late-decoder wgrad): partials are cheap
+    if (s > cap) s = cap;
     if (s < 1) s = 1;
   }
   const int per = (k_tiles + s - 1) / s;

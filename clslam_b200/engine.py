@@ -21,7 +21,6 @@ import torch
 from . import _lib as L
 from .networks import DEC_CH, ENC_CH, FlatParams, ResnetEncoder
 
-Op = Tuple[str, Callable, tuple]
 
 
 def _p(t) -> Optional[int]:
@@ -72,15 +71,27 @@ class PreparedEncoder:
 
 
 class Plan:
-    """Ordered kernel launches over static buffers."""
+    """Ordered kernel launches over static buffers, on up to three concurrent lanes.
+
+    Lane 0 runs on the caller's current stream, lanes 1 and 2 on side streams that fork from and
+    join back into lane 0 (``fork`` / ``join`` / ``record`` / ``wait`` markers).  At batch 1 most
+    kernels of the step fill a fraction of the 148 SMs, so the independent branches (depth net /
+    pose net / identity candidates; dgrad chain / wgrads / pose backward) overlap.  Every lane
+    has its own split-K workspace.  The whole thing is CUDA-graph capturable."""
+    N_LANES = 3
 
     def __init__(self, device):
         self.device = device
         self.lib = L.load()
-        self.ops: List[Op] = []
+        self.ops: List[tuple] = []          # (name, fn | None, args, lane)
         self.ws_bytes = 0
         self.keep: List[object] = []       # ctypes structs / tensors that must outlive the plan
-        self._ws: Optional[torch.Tensor] = None
+        self._ws: List[torch.Tensor] = []
+        self._ws_ptr: List[int] = []
+        self.lane = 0
+        self._events: Dict[str, torch.cuda.Event] = {}
+        self._side: List[torch.cuda.Stream] = []
+        self._n_marks = 0
 
     def alloc(self, *shape, dtype=torch.float32, zero=False) -> torch.Tensor:
         t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
@@ -93,7 +104,35 @@ class Plan:
         self.ws_bytes = max(self.ws_bytes, int(nbytes))
 
     def add(self, name: str, fn, *args) -> None:
-        self.ops.append((name, fn, args))
+        """fn(stream, ws_ptr, *args) -> rc"""
+        self.ops.append((name, fn, args, self.lane))
+
+    # -- lanes ---------------------------------------------------------------------------------
+    def set_lane(self, lane: int) -> None:
+        self.lane = lane
+
+    def record(self, event: str) -> None:
+        self.ops.append(('__record__', None, (event,), self.lane))
+
+    def wait(self, event: str) -> None:
+        self.ops.append(('__wait__', None, (event,), self.lane))
+
+    def fork(self, lanes=(1, 2)) -> None:
+        """side lanes start after everything issued on lane 0 so far"""
+        self._n_marks += 1
+        ev = f'__fork{self._n_marks}'
+        self.ops.append(('__record__', None, (ev,), 0))
+        for ln in lanes:
+            self.ops.append(('__wait__', None, (ev,), ln))
+
+    def join(self, lanes=(1, 2)) -> None:
+        """lane 0 continues after everything issued on the side lanes"""
+        self._n_marks += 1
+        for ln in lanes:
+            ev = f'__join{self._n_marks}_{ln}'
+            self.ops.append(('__record__', None, (ev,), ln))
+            self.ops.append(('__wait__', None, (ev,), 0))
+        self.lane = 0
 
     # -- layer helpers -------------------------------------------------------------------------
     def desc(self, n, hi, wi, ci, co, k, stride, pad, pad_mode=L.PAD_ZERO, in_mode=L.IN_PLAIN, c1=0, h1=0, w1=0,
@@ -107,41 +146,57 @@ class Plan:
         self.need_ws(self.lib.clslam_conv_fwd_workspace_bytes(ctypes.byref(d)))
         self.add(name, self._conv_fwd, d, _p(x), _p(x2), _p(w), _p(scale), _p(shift), _p(res), _p(y))
 
-    def _conv_fwd(self, stream, d, x, x2, w, scale, shift, res, y):
-        return self.lib.clslam_conv_fwd(ctypes.byref(d), x, x2, w, scale, shift, res, y, self._ws_ptr, self.ws_bytes, stream)
+    def _conv_fwd(self, stream, ws, d, x, x2, w, scale, shift, res, y):
+        return self.lib.clslam_conv_fwd(ctypes.byref(d), x, x2, w, scale, shift, res, y, ws, self.ws_bytes, stream)
 
     def conv_dgrad(self, name, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev) -> None:
         self.need_ws(self.lib.clslam_conv_dgrad_workspace_bytes(ctypes.byref(d)))
         self.add(name, self._conv_dgrad, d, _p(dz), _p(w), _p(y_prev), act_prev, _p(disp_dz), _p(disp_w), _p(dz_prev))
 
-    def _conv_dgrad(self, stream, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev):
+    def _conv_dgrad(self, stream, ws, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev):
         return self.lib.clslam_conv_dgrad(ctypes.byref(d), dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev,
-                                          self._ws_ptr, self.ws_bytes, stream)
+                                          ws, self.ws_bytes, stream)
 
     def conv_wgrad(self, name, d, x, x2, dz, dw, db) -> None:
         self.need_ws(self.lib.clslam_conv_wgrad_workspace_bytes(ctypes.byref(d)))
         self.add(name, self._conv_wgrad, d, _p(x), _p(x2), _p(dz), _p(dw), _p(db))
 
-    def _conv_wgrad(self, stream, d, x, x2, dz, dw, db):
-        return self.lib.clslam_conv_wgrad(ctypes.byref(d), x, x2, dz, dw, db, self._ws_ptr, self.ws_bytes, stream)
+    def _conv_wgrad(self, stream, ws, d, x, x2, dz, dw, db):
+        return self.lib.clslam_conv_wgrad(ctypes.byref(d), x, x2, dz, dw, db, ws, self.ws_bytes, stream)
 
     def simple(self, name, fn, *args) -> None:
         """fn(*args, stream)"""
-        self.add(name, lambda stream, *a: fn(*a, stream), *args)
+        self.add(name, lambda stream, ws, *a: fn(*a, stream), *args)
 
     def with_ws(self, name, fn, *args) -> None:
         """fn(*args, ws, ws_bytes, stream)"""
-        self.add(name, lambda stream, *a: fn(*a, self._ws_ptr, self.ws_bytes, stream), *args)
+        self.add(name, lambda stream, ws, *a: fn(*a, ws, self.ws_bytes, stream), *args)
 
     # -- execution -----------------------------------------------------------------------------
     def finalize(self) -> None:
-        self._ws = torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=self.device)
-        self._ws_ptr = self._ws.data_ptr()
+        lanes = sorted({op[3] for op in self.ops})
+        n = (max(lanes) + 1) if lanes else 1
+        self._ws = [torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=self.device) for _ in range(n)]
+        self._ws_ptr = [t.data_ptr() for t in self._ws]
+        self._side = [torch.cuda.Stream(device=self.device) for _ in range(n - 1)]
+        for name, fn, args, lane in self.ops:
+            if fn is None and args[0] not in self._events:
+                self._events[args[0]] = torch.cuda.Event()
 
-    def run(self, first: int = 0, last: Optional[int] = None) -> None:
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        for name, fn, args in self.ops[first:last]:
-            rc = fn(stream, *args)
+    def run(self, first: int = 0, last: Optional[int] = None, serial: bool = False) -> None:
+        main = torch.cuda.current_stream(self.device)
+        streams = [main] + ([main] * len(self._side) if serial else self._side)
+        ptrs = [st.cuda_stream for st in streams]
+        for name, fn, args, lane in self.ops[first:last]:
+            if fn is None:
+                if serial:
+                    continue
+                if name == '__record__':
+                    self._events[args[0]].record(streams[lane])
+                else:
+                    streams[lane].wait_event(self._events[args[0]])
+                continue
+            rc = fn(ptrs[lane], self._ws_ptr[lane], *args)
             if rc != 0:
                 L.check(rc, name)
 
@@ -244,7 +299,9 @@ class AdaptEngine:
         self.sample_w_global = plan.alloc(batch_global, zero=True)
         self.noise = [plan.alloc(b, 2, h, w, zero=True) for _ in range(S)]
 
-        # ---- depth network -------------------------------------------------------------------
+        # ---- depth network (lane 0; pose network on lane 1, identity candidates on lane 2) ------
+        plan.fork((1, 2))
+        plan.set_lane(0)
         self.depth_in = plan.alloc(b, h, w, depth_prep.cin_pad)
         plan.simple('depth.stage', lib.clslam_stage_images, _p(self.rgb_aug[1]), None, _p(self.depth_in), b, h, w,
                     depth_prep.cin_pad)
@@ -285,6 +342,7 @@ class AdaptEngine:
             x = y1
 
         # ---- pose network (both passes batched: [frame -1 | frame +1]) ------------------------
+        plan.set_lane(1)
         self.pose_in = plan.alloc(2 * b, h, w, pose_prep.cin_pad)
         # temporal order (depth_pose_prediction.py:951-955): (-1, 0) and (0, +1)
         plan.simple('pose.stage0', lib.clslam_stage_images, _p(self.rgb_aug[0]), _p(self.rgb_aug[1]), _p(self.pose_in[:b]),
@@ -357,19 +415,23 @@ class AdaptEngine:
         la.losses, la.smooth_grad = _p(self.losses), _p(self.smooth_grad)
         self.loss_args = la
         plan.keep.append(la)
-        self.op_identity = len(plan.ops)
+        plan.set_lane(2)
         plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
-        plan.add('photo_fwd', lambda stream: lib.clslam_photo_fwd(ctypes.byref(pa), stream))
-        plan.add('loss_finalize', lambda stream: lib.clslam_loss_finalize(ctypes.byref(la), stream))
+        plan.join((1, 2))
+        plan.add('photo_fwd', lambda stream, ws: lib.clslam_photo_fwd(ctypes.byref(pa), stream))
+        plan.add('loss_finalize', lambda stream, ws: lib.clslam_loss_finalize(ctypes.byref(la), stream))
         self.n_fwd_ops = len(plan.ops)
 
-        # ---- backward ---------------------------------------------------------------------------
-        plan.add('photo_bwd', lambda stream: lib.clslam_photo_bwd(ctypes.byref(pa), stream))
+        # ---- backward: lane 0 = photometric + depth-decoder dgrad chain (critical path),
+        #      lane 1 = pose branch, lane 2 = weight gradients of the depth decoder ----------------
+        plan.add('photo_bwd', lambda stream, ws: lib.clslam_photo_bwd(ctypes.byref(pa), stream))
+        plan.fork((1, 2))
         self.dz_disp = {}
         for s in range(S):
             self.dz_disp[s] = plan.alloc(b, 1, h >> s, w >> s)
             plan.simple(f'disp_grad_{s}', lib.clslam_disp_grad, _p(self.ddisp_full[s]), _p(self.disp[s]),
                         _p(self.smooth_grad), batch_global, 1 if has_sample0 else 0, b, h, w, s, _p(self.dz_disp[s]))
+            plan.record(f'dzd{s}')
         self.dz = {}
         for i in range(0, 5):
             for j in (0, 1):
@@ -380,29 +442,42 @@ class AdaptEngine:
             if i < S:
                 keyd = (dd, f'dispconv_{i}.conv')
                 plan.need_ws(lib.clslam_dispconv_wgrad_workspace_bytes(b, hi_, wi_, DEC_CH[i]))
+                plan.set_lane(2)
+                plan.wait(f'dzd{i}')
                 plan.with_ws(f'dispconv_{i}.wgrad', lib.clslam_dispconv_wgrad, _p(y1), _p(self.dz_disp[i]),
                              flat.wgrad_ptr(keyd), flat.bgrad_ptr(keyd), b, hi_, wi_, DEC_CH[i])
+                plan.set_lane(0)
             if i == 0:
                 plan.simple('dispconv_0.dgrad', lib.clslam_dispconv_dgrad_act, _p(self.dz_disp[0]),
                             flat.weight_ptr((dd, 'dispconv_0.conv')), _p(y1), L.ACT_ELU, _p(self.dz[(0, 1)]), b, hi_, wi_,
                             DEC_CH[0])
+                plan.record('dz01')
             # upconv_i_1: wgrad + dgrad (to the up-sampled branch only; the skip feeds a frozen encoder)
             d1, y0, skip = self.dec_desc[(i, 1)]
             key1 = (dd, f'upconv_{i}_1.conv.conv')
+            plan.set_lane(2)
+            plan.wait(f'dz{i}1')
             plan.conv_wgrad(f'upconv_{i}_1.wgrad', d1, y0, skip, self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
+            plan.set_lane(0)
             plan.conv_dgrad(f'upconv_{i}_1.dgrad', d1, self.dz[(i, 1)], flat.weight_ptr(key1), y0, L.ACT_ELU, None, None,
                             self.dz[(i, 0)])
+            plan.record(f'dz{i}0')
             # upconv_i_0: wgrad; dgrad into upconv_{i+1}_1's output (+ dispconv_{i+1} term)
             d0, xin = self.dec_desc[(i, 0)]
             key0 = (dd, f'upconv_{i}_0.conv.conv')
+            plan.set_lane(2)
+            plan.wait(f'dz{i}0')
             plan.conv_wgrad(f'upconv_{i}_0.wgrad', d0, xin, None, self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
+            plan.set_lane(0)
             if i < 4:
                 has_disp = (i + 1) < S
                 plan.conv_dgrad(f'upconv_{i}_0.dgrad', d0, self.dz[(i, 0)], flat.weight_ptr(key0), self.y[(i + 1, 1)],
                                 L.ACT_ELU, self.dz_disp[i + 1] if has_disp else None,
                                 flat.weight_ptr((dd, f'dispconv_{i + 1}.conv')) if has_disp else None,
                                 self.dz[(i + 1, 1)])
+                plan.record(f'dz{i + 1}1')
         # pose branch
+        plan.set_lane(1)
         self.dz_pose = {name: plan.alloc(*self.pose_act[name].shape) for name in ('squeeze', 'pose_0', 'pose_1', 'pose_2')}
         plan.simple('pose_head_bwd', lib.clslam_pose_head_bwd, _p(self.dproj_partials), S * self.n_tiles, _p(self.k_mat),
                     _p(self.axis_angle), _p(self.translation), _p(self.rel_dist), _p(self.sample_w),
@@ -415,6 +490,7 @@ class AdaptEngine:
             if name in prev:
                 plan.conv_dgrad(f'{name}.dgrad', d, self.dz_pose[name], flat.weight_ptr((pd, name)),
                                 self.pose_act[prev[name]], L.ACT_RELU, None, None, self.dz_pose[prev[name]])
+        plan.join((1, 2))
         self.n_bwd_ops = len(plan.ops)
         plan.finalize()
 
