@@ -90,7 +90,7 @@ pose_head_fwd_kernel(const float* __restrict__ pose_out, const float* __restrict
   }
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(256)
 pose_head_bwd_kernel(const float* __restrict__ dproj_partials, int n_partials, const float* __restrict__ k_mat,
                      const float* __restrict__ axis_angle, const float* __restrict__ translation,
                      const double* __restrict__ rel_dist, const float* __restrict__ sample_w, float velocity_scale,
@@ -99,13 +99,21 @@ pose_head_bwd_kernel(const float* __restrict__ dproj_partials, int n_partials, c
   const int lane = threadIdx.x;
   __shared__ float dP[12];
   __shared__ float dout[12];
+  __shared__ float part[21][12];
+  if (lane < 252) {                       // 21 groups x 12 components, fixed summation order
+    const int comp = lane % 12, grp = lane / 12;
+    float acc = 0.f;
+    for (int p = grp; p < n_partials; p += 21) acc += dproj_partials[(((size_t)p * 2 + pass) * b + bb) * 12 + comp];
+    part[grp][comp] = acc;
+  }
+  __syncthreads();
   if (lane < 12) {
     float acc = 0.f;
-    for (int p = 0; p < n_partials; ++p) acc += dproj_partials[(((size_t)p * 2 + pass) * b + bb) * 12 + lane];
+    for (int g = 0; g < 21; ++g) acc += part[g][lane];
     dP[lane] = acc;
     dout[lane] = 0.f;
   }
-  __syncwarp();
+  __syncthreads();
   if (lane == 0) {
     const size_t o = (size_t)pass * b + bb;
     const float* K = k_mat + (size_t)bb * 16;
@@ -177,15 +185,15 @@ pose_head_bwd_kernel(const float* __restrict__ dproj_partials, int n_partials, c
     const float k_mean = 0.01f / ((float)h * (float)w);
     for (int k = 0; k < 3; ++k) { dout[k] = daa[k] * k_mean; dout[3 + k] = dt[k] * k_mean; }
   }
-  __syncwarp();
+  __syncthreads();
   float* d = dz + (size_t)blockIdx.x * h * w * 12;
-  for (int i = lane; i < h * w * 12; i += 32) d[i] = dout[i % 12];
+  for (int i = lane; i < h * w * 12; i += 256) d[i] = dout[i % 12];
 }
 
 // ---- loss assembly ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 loss_finalize_kernel(clslam_loss_args a) {
-  __shared__ float red[8];
+  __shared__ float red[32];
   __shared__ float s_mean[4];
   __shared__ float s_reproj[4];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -194,7 +202,7 @@ loss_finalize_kernel(clslam_loss_args a) {
   // reprojection terms: sum_b w_b * mean_hw(min-loss)
   for (int s = 0; s < S; ++s) {
     float acc = 0.f;
-    for (int bb = warp; bb < a.b; bb += 8) {
+    for (int bb = warp; bb < a.b; bb += 32) {
       float t = 0.f;
       for (int i = lane; i < a.n_tiles; i += 32) t += a.loss_partials[((size_t)s * a.b + bb) * a.n_tiles + i];
       t = warp_sum(t);
@@ -203,17 +211,18 @@ loss_finalize_kernel(clslam_loss_args a) {
     __syncthreads();
     if (lane == 0) red[warp] = acc;
     __syncthreads();
-    if (tid == 0) { float t = 0.f; for (int i = 0; i < 8; ++i) t += red[i]; s_reproj[s] = t; }
+    if (tid == 0) { float t = 0.f; for (int i = 0; i < 32; ++i) t += red[i]; s_reproj[s] = t; }
     // mean disparity of global sample 0 at this scale
     if (a.has_sample0) {
-      const int n = (a.h >> s) * (a.w >> s);
+      const int n = (a.h >> s) * (a.w >> s);       // multiple of 4 (h, w are multiples of 32)
       float t = 0.f;
-      for (int i = tid; i < n; i += 256) t += a.disp[s][i];
+      const float4* d4 = reinterpret_cast<const float4*>(a.disp[s]);
+      for (int i = tid; i < n / 4; i += 1024) { const float4 q = d4[i]; t += (q.x + q.y) + (q.z + q.w); }
       t = warp_sum(t);
       __syncthreads();
       if (lane == 0) red[warp] = t;
       __syncthreads();
-      if (tid == 0) { float u = 0.f; for (int i = 0; i < 8; ++i) u += red[i]; s_mean[s] = u / (float)n; }
+      if (tid == 0) { float u = 0.f; for (int i = 0; i < 32; ++i) u += red[i]; s_mean[s] = u / (float)n; }
     }
     __syncthreads();
   }
@@ -303,7 +312,7 @@ int clslam_pose_head_fwd(const float* pose_out, const float* k_mat, int b, int h
 int clslam_pose_head_bwd(const float* dproj_partials, int n_partials, const float* k_mat, const float* axis_angle,
                          const float* translation, const double* rel_dist, const float* sample_w, float velocity_scale,
                          int b, int h, int w, int invert_mask, float* dz_pose_out, void* stream) {
-  pose_head_bwd_kernel<<<2 * b, 32, 0, as_stream(stream)>>>(dproj_partials, n_partials, k_mat, axis_angle, translation,
+  pose_head_bwd_kernel<<<2 * b, 256, 0, as_stream(stream)>>>(dproj_partials, n_partials, k_mat, axis_angle, translation,
                                                             rel_dist, sample_w, velocity_scale, b, h, w, invert_mask,
                                                             dz_pose_out);
   return finish_launch("pose_head_bwd");
@@ -314,7 +323,7 @@ int clslam_loss_finalize(const clslam_loss_args* a, void* stream) {
   if (a->has_sample0 && (a->b_global + 1 > (a->w >> (a->n_scales - 1)) || (a->h >> (a->n_scales - 1)) < 2)) {
     set_error("loss_finalize: reference smoothness indexing needs b_global < w / 2^(n_scales-1)"); return -1;
   }
-  loss_finalize_kernel<<<1, 256, 0, as_stream(stream)>>>(*a);
+  loss_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(*a);
   return finish_launch("loss_finalize");
 }
 
