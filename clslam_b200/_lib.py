@@ -58,6 +58,9 @@ SIGNATURES = {
     'clslam_conv_fwd_workspace_bytes': (c_longlong, [POINTER(ConvDesc)]),
     'clslam_conv_fwd': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_longlong, c_void_p]),
+    'clslam_split_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    'clslam_conv_fwd_bf16w': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     'clslam_maxpool3x3s2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_dispconv_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_conv_dgrad_workspace_bytes': (c_longlong, [POINTER(ConvDesc)]),

@@ -4,6 +4,7 @@
 #include "conv_ops.cuh"
 #include "gemm_core.cuh"
 #include "gemm_tc.cuh"
+#include "conv3x3_tc.cuh"
 
 namespace clslam {
 
@@ -477,7 +478,7 @@ static int launch_tc_bn(const TcPlan& p, const AOp& a, const BOp& b, const Epi& 
     attr_set = true;
   }
   dim3 grid(p.gx, p.gy, p.splits);
-  kern<<<grid, kTcThreads, kSmem, st>>>(a, b, e, M, N, K, p.k_chunk, ws);
+  kern<<<grid, kTcBlock, kSmem, st>>>(a, b, e, M, N, K, p.k_chunk, ws);
   return finish_launch(what);
 }
 
@@ -525,6 +526,53 @@ static int run_gemm(const AOp& a, const BOp& b, const Epi& e, int M, int N, int 
   return launch_gemm(plan_tiles(M, N, K, true), a, b, e, M, N, K, ws, ws_bytes, st, what);
 }
 
+// ---- 3x3 patch kernel (conv3x3_tc.cuh) -------------------------------------------------------
+struct P3Plan { int bn, gx, gy, splits; P3Geom g; };
+
+static bool p3_eligible(const clslam_conv_desc* d) {
+  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad != 1 || d->ci % 64 != 0) return false;
+  if (d->hi != d->ho || d->wi != d->wo) return false;
+  if (d->in_mode == CLSLAM_IN_UPCAT && d->c1 % 64 != 0) return false;
+  // the 16 x 8 pixel M tiles must be reasonably full (6 x 20 maps waste 2/3 of every tile: generic kernel instead)
+  const long long tiles = (long long)((d->wo + kP3TW - 1) / kP3TW) * ((d->ho + kP3TH - 1) / kP3TH);
+  return (long long)d->ho * d->wo * 10 >= tiles * kTcBM * 6;
+}
+
+static P3Plan plan_p3(const clslam_conv_desc* d) {
+  P3Plan p{};
+  p.bn = d->co >= 128 ? 128 : (d->co > 32 ? 64 : (d->co > 16 ? 32 : 16));
+  p.g.tiles_x = (d->wo + kP3TW - 1) / kP3TW;
+  p.g.tiles_y = (d->ho + kP3TH - 1) / kP3TH;
+  p.g.n_chunks = d->ci / 64;
+  p.gx = d->n * p.g.tiles_x * p.g.tiles_y;
+  p.gy = (d->co + p.bn - 1) / p.bn;
+  int s = 1;
+  const long long tiles = (long long)p.gx * p.gy;
+  if (tiles < num_sms() && p.g.n_chunks > 1) {
+    s = (int)((num_sms() + tiles - 1) / tiles);
+    if (s > p.g.n_chunks) s = p.g.n_chunks;
+  }
+  p.g.chunks_per_split = (p.g.n_chunks + s - 1) / s;
+  p.splits = (p.g.n_chunks + p.g.chunks_per_split - 1) / p.g.chunks_per_split;
+  return p;
+}
+
+template <int BN>
+static int launch_p3(const P3Plan& p, const ConvIn& c, const uint16_t* w_hi, const uint16_t* w_lo, const EpiFwd& e, int co,
+                     float* ws, cudaStream_t st) {
+  auto kern = conv3x3_tc_kernel<BN, EpiFwd>;
+  constexpr int kSmem = P3Smem<BN>::kTotal;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (err != cudaSuccess) { set_error("conv3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(err)); return -3; }
+    attr_set = true;
+  }
+  dim3 grid(p.gx, p.gy, p.splits);
+  kern<<<grid, kTcBlock, kSmem, st>>>(c, w_hi, w_lo, e, co, p.g, ws);
+  return finish_launch("conv3x3_tc");
+}
+
 static int check_desc(const clslam_conv_desc* d, const char* what) {
   if (!d) { set_error("%s: null descriptor", what); return -1; }
   if (d->ci % 4 != 0 || d->co % 4 != 0) { set_error("%s: channels must be multiples of 4 (ci=%d co=%d)", what, d->ci, d->co); return -1; }
@@ -555,7 +603,55 @@ int clslam_debug_tc_stamps(unsigned long long* out16) {
 long long clslam_conv_fwd_workspace_bytes(const clslam_conv_desc* d) {
   if (check_desc(d, "conv_fwd_ws")) return -1;
   const int M = d->n * d->ho * d->wo, N = d->co, K = d->kh * d->kw * d->ci;
-  return ws_need(M, N, K, false);
+  long long need = ws_need(M, N, K, false);
+  if (p3_eligible(d)) {
+    const P3Plan p = plan_p3(d);
+    const long long n3 = p.splits > 1 ? (long long)p.splits * M * N * 4 : 0;
+    if (n3 > need) need = n3;
+  }
+  return need;
+}
+
+int clslam_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream) {
+  if (n % 4) { set_error("split_bf16: n %% 4 != 0"); return -1; }
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  split_bf16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, (uint16_t*)hi, (uint16_t*)lo, n / 4);
+  return finish_launch("split_bf16");
+}
+
+int clslam_conv_fwd_bf16w(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
+                          const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,
+                          void* workspace, long long workspace_bytes, void* stream) {
+  if (int rc = check_desc(d, "conv_fwd_bf16w")) return rc;
+  if (g_conv_mode != 1 || !w_hi || !w_lo || !p3_eligible(d))
+    return clslam_conv_fwd(d, x, x2, w, scale, shift, residual, y, workspace, workspace_bytes, stream);
+  const int M = d->n * d->ho * d->wo, N = d->co;
+  const P3Plan p = plan_p3(d);
+  if (p.splits > 1 && (workspace == nullptr || workspace_bytes < (long long)p.splits * M * N * 4)) {
+    set_error("conv_fwd_bf16w: workspace too small"); return -2;
+  }
+  EpiFwd e{y, scale, shift, residual, N, d->act};
+  const ConvIn c = make_conv_in(*d, x, x2);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  switch (p.bn) {
+    case 128: rc = launch_p3<128>(p, c, (const uint16_t*)w_hi, (const uint16_t*)w_lo, e, N, (float*)workspace, st); break;
+    case 64: rc = launch_p3<64>(p, c, (const uint16_t*)w_hi, (const uint16_t*)w_lo, e, N, (float*)workspace, st); break;
+    case 32: rc = launch_p3<32>(p, c, (const uint16_t*)w_hi, (const uint16_t*)w_lo, e, N, (float*)workspace, st); break;
+    default: rc = launch_p3<16>(p, c, (const uint16_t*)w_hi, (const uint16_t*)w_lo, e, N, (float*)workspace, st); break;
+  }
+  if (rc) return rc;
+  if (p.splits > 1) {
+    const long long total4 = (long long)M * N / 4;
+    int blocks = (int)((total4 + 255) / 256);
+    if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+    if (blocks < 1) blocks = 1;
+    splitk_reduce_kernel<EpiFwd><<<blocks, 256, 0, st>>>(e, (const float*)workspace, M, N, p.splits);
+    rc = finish_launch("conv_fwd_bf16w");
+  }
+  return rc;
 }
 
 int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const float* scale,

@@ -23,7 +23,8 @@ namespace clslam {
 
 constexpr int kTcBM = 128;      // UMMA M
 constexpr int kTcBK = 64;       // k per stage = one 128-byte swizzle row of bf16
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 256;            // producer (staging / epilogue) threads: warps 0..7
+constexpr int kTcBlock = kTcThreads + 32;  // + warp 8: the MMA issuer
 constexpr int kTcStages = 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,6 +44,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   }
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -199,6 +203,7 @@ struct TcSmem {
   static constexpr int kParamBytes = 2 * BN * 4;          // epilogue per-column parameters (scale, shift)
   static constexpr int kTotal = kTcStages * kStageBytes + kTabABytes + kTabBBytes + kParamBytes + 1024 /*alignment slack*/ +
                                 128 /*barriers + tmem slot*/;
+  static_assert((2 * kTcStages + 1) * 8 + 4 <= 128, "barrier area");
 };
 
 // cycle stamps of CTA (0,0,0), thread 0 (debug aid, read back with clslam_debug_tc_stamps)
@@ -206,7 +211,7 @@ __device__ unsigned long long g_tc_stamps[16];
 #define TC_STAMP(i) do { if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_tc_stamps[i] = clock64(); } while (0)
 
 template <int BN, class AOp, class BOp, class Epi>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcBlock)
 gemm_tc_kernel(AOp aop, BOp bop, Epi epi, int M, int N, int K, int k_chunk, float* __restrict__ ws) {
   using SM = TcSmem<BN, AOp, BOp>;
   using StA = TcStager<kTcBM, AOp>;
@@ -218,10 +223,13 @@ gemm_tc_kernel(AOp aop, BOp bop, Epi epi, int M, int N, int K, int k_chunk, floa
   typename SM::ARow* tab_a = reinterpret_cast<typename SM::ARow*>(after);
   typename SM::BRow* tab_b = reinterpret_cast<typename SM::BRow*>(after + SM::kTabABytes);
   float* eparams = reinterpret_cast<float*>(after + SM::kTabABytes + SM::kTabBBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(after + SM::kTabABytes + SM::kTabBBytes + SM::kParamBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kTcStages);
+  uint64_t* full = reinterpret_cast<uint64_t*>(after + SM::kTabABytes + SM::kTabBBytes + SM::kParamBytes);
+  uint64_t* empty = full + kTcStages;
+  uint64_t* done = empty + kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool producer = warp < kTcThreads / 32;
   const int m0 = blockIdx.x * kTcBM, n0 = blockIdx.y * BN;
   const int k_begin = blockIdx.z * k_chunk;
   const int k_end = min(K, k_begin + k_chunk);
@@ -230,70 +238,84 @@ gemm_tc_kernel(AOp aop, BOp bop, Epi epi, int M, int N, int K, int k_chunk, floa
   TC_STAMP(0);
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < kTcStages; ++s) mbar_init(&bars[s], 1);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], kTcThreads / 32); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (!producer) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    StA::build_table(aop, tab_a, m0, tid);
+    StB::build_table(bop, tab_b, n0, tid);
+    epi.tc_prologue(eparams, n0, BN, N, tid);
   }
-  StA::build_table(aop, tab_a, m0, tid);
-  StB::build_table(bop, tab_b, n0, tid);
-  epi.tc_prologue(eparams, n0, BN, N, tid);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
   constexpr uint32_t idesc = umma_idesc_bf16(BN);
-  StA sa;
-  StB sb;
-  sa.init(tab_a, tid);
-  sb.init(tab_b, tid);
-  if (n_kb > 0) { sa.fetch(aop, k_begin, k_end, tid); sb.fetch(bop, k_begin, k_end, tid); }
   TC_STAMP(1);
 
-  for (int kb = 0; kb < n_kb; ++kb) {
-    const int s = kb % kTcStages;
-    uint8_t* a_hi = tiles + s * SM::kStageBytes;
-    uint8_t* a_lo = a_hi + SM::kABytes;
-    uint8_t* b_hi = a_lo + SM::kABytes;
-    uint8_t* b_lo = b_hi + SM::kBBytes;
-    if (kb >= kTcStages) mbar_wait(&bars[s], (uint32_t)((kb / kTcStages - 1) & 1));   // MMAs that read this stage are done
-    sa.commit(a_hi, a_lo, tid);
-    sb.commit(b_hi, b_lo, tid);
-    if (kb == 0) TC_STAMP(2);
-    fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    __syncthreads();
-    if (kb + 1 < n_kb) {                  // loads of the next k block fly while the MMAs run
-      sa.fetch(aop, k_begin + (kb + 1) * kTcBK, k_end, tid);
-      sb.fetch(bop, k_begin + (kb + 1) * kTcBK, k_end, tid);
-    }
-    if (tid == 0) {
-      tc_fence_after();
-      const uint64_t dah = umma_desc_k_sw128(smem_u32(a_hi)), dal = umma_desc_k_sw128(smem_u32(a_lo));
-      const uint64_t dbh = umma_desc_k_sw128(smem_u32(b_hi)), dbl = umma_desc_k_sw128(smem_u32(b_lo));
-#pragma unroll
-      for (int j = 0; j < kTcBK / 16; ++j) {
-        const uint64_t adv = (uint64_t)((j * 32) >> 4);       // 16 bf16 = 32 bytes inside the swizzle row
-        umma_bf16(tmem_d, dal + adv, dbh + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
-        umma_bf16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
-        umma_bf16(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+  if (producer) {
+    // ===== producers: gather + split + swizzled store, one k block ahead of the tensor core =====
+    StA sa;
+    StB sb;
+    sa.init(tab_a, tid);
+    sb.init(tab_b, tid);
+    if (n_kb > 0) { sa.fetch(aop, k_begin, k_end, tid); sb.fetch(bop, k_begin, k_end, tid); }
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % kTcStages;
+      uint8_t* a_hi = tiles + s * SM::kStageBytes;
+      uint8_t* a_lo = a_hi + SM::kABytes;
+      uint8_t* b_hi = a_lo + SM::kABytes;
+      uint8_t* b_lo = b_hi + SM::kBBytes;
+      if (kb >= kTcStages) mbar_wait(&empty[s], (uint32_t)((kb / kTcStages - 1) & 1));   // MMAs that read this stage are done
+      sa.commit(a_hi, a_lo, tid);
+      sb.commit(b_hi, b_lo, tid);
+      fence_proxy_async_smem();             // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+      if (kb == 0) TC_STAMP(2);
+      if (kb + 1 < n_kb) {                  // loads of the next k block fly while the MMAs run
+        sa.fetch(aop, k_begin + (kb + 1) * kTcBK, k_end, tid);
+        sb.fetch(bop, k_begin + (kb + 1) * kTcBK, k_end, tid);
       }
-      umma_commit(&bars[s]);
     }
-    if (kb == 0) TC_STAMP(3);
+    TC_STAMP(4);
+    if (n_kb > 0) mbar_wait(done, 0);
+  } else {
+    // ===== warp 8: MMA issuer =====
+    for (int kb = 0; kb < n_kb; ++kb) {
+      const int s = kb % kTcStages;
+      mbar_wait(&full[s], (uint32_t)((kb / kTcStages) & 1));
+      tc_fence_after();
+      if (lane == 0) {
+        uint8_t* a_hi = tiles + s * SM::kStageBytes;
+        uint8_t* a_lo = a_hi + SM::kABytes;
+        uint8_t* b_hi = a_lo + SM::kABytes;
+        uint8_t* b_lo = b_hi + SM::kBBytes;
+        const uint64_t dah = umma_desc_k_sw128(smem_u32(a_hi)), dal = umma_desc_k_sw128(smem_u32(a_lo));
+        const uint64_t dbh = umma_desc_k_sw128(smem_u32(b_hi)), dbl = umma_desc_k_sw128(smem_u32(b_lo));
+#pragma unroll
+        for (int j = 0; j < kTcBK / 16; ++j) {
+          const uint64_t adv = (uint64_t)((j * 32) >> 4);       // 16 bf16 = 32 bytes inside the swizzle row
+          umma_bf16(tmem_d, dal + adv, dbh + adv, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+          umma_bf16(tmem_d, dah + adv, dbl + adv, idesc, 1u);
+          umma_bf16(tmem_d, dah + adv, dbh + adv, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+        if (kb == n_kb - 1) umma_commit(done);
+      }
+      __syncwarp();
+    }
   }
-  TC_STAMP(4);
-  // ---- epilogue -------------------------------------------------------------------------------
-  if (n_kb > 0) {
-    const int last = n_kb - 1;
-    mbar_wait(&bars[last % kTcStages], (uint32_t)((last / kTcStages) & 1));
-  }
+  // ---- epilogue (producer warps) ----------------------------------------------------------------
   tc_fence_after();
   TC_STAMP(5);
   constexpr int kColsPerWarp = (BN >= 64) ? BN / 2 : BN;          // 8 warps: 4 lane quarters x 2 column halves
-  const int quarter = warp & 3, half = warp >> 2;
-  const bool active = (BN >= 64) || half == 0;
+  const int quarter = warp & 3, half = (warp >> 2) & 1;
+  const bool active = producer && ((BN >= 64) || half == 0);
   if (active) {
     const int m = m0 + quarter * 32 + lane;
     const int col0 = (BN >= 64) ? half * kColsPerWarp : 0;
@@ -329,7 +351,7 @@ gemm_tc_kernel(AOp aop, BOp bop, Epi epi, int M, int N, int K, int k_chunk, floa
   TC_STAMP(6);
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (!producer) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(kTmemCols) : "memory");
   }
 }

@@ -560,7 +560,7 @@ class _PoseRunner:
             d = plan.desc(2 * n, hp, wp, ci, co, k, 1, (k - 1) // 2, act=act)
             y = plan.alloc(2 * n, hp, wp, co)
             plan.conv_fwd(name, d, x, None, flat.weight_ptr(('pose_decoder', name)), None,
-                          flat.bias_ptr(('pose_decoder', name)), None, y)
+                          flat.bias_ptr(('pose_decoder', name)), None, y)      # fp32 weights (no bf16 planes needed here)
             x = y
         self.k_eye = torch.eye(4, device=device).repeat(n, 1, 1).contiguous()
         self.aa = plan.alloc(2, n, 3); self.tr = plan.alloc(2, n, 3)

@@ -50,7 +50,11 @@ class PreparedEncoder:
             w = conv.weight.detach().to(device=device, dtype=torch.float32)
             if pad_to is not None and w.shape[1] < pad_to:
                 w = torch.cat([w, w.new_zeros(w.shape[0], pad_to - w.shape[1], *w.shape[2:])], 1)
-            self.t[name + '.w'] = w.permute(0, 2, 3, 1).contiguous()
+            wk = w.permute(0, 2, 3, 1).contiguous()
+            self.t[name + '.w'] = wk
+            hi = wk.to(torch.bfloat16)                                   # same round-to-nearest split as the kernels
+            self.t[name + '.w_hi'] = hi
+            self.t[name + '.w_lo'] = (wk - hi.float()).to(torch.bfloat16)
 
         def put_bn(name, bn):
             scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
@@ -142,12 +146,13 @@ class Plan:
         self.keep.append(d)
         return d
 
-    def conv_fwd(self, name, d: L.ConvDesc, x, x2, w, scale, shift, res, y) -> None:
+    def conv_fwd(self, name, d: L.ConvDesc, x, x2, w, scale, shift, res, y, w_hi=None, w_lo=None) -> None:
         self.need_ws(self.lib.clslam_conv_fwd_workspace_bytes(ctypes.byref(d)))
-        self.add(name, self._conv_fwd, d, _p(x), _p(x2), _p(w), _p(scale), _p(shift), _p(res), _p(y))
+        self.add(name, self._conv_fwd, d, _p(x), _p(x2), _p(w), _p(w_hi), _p(w_lo), _p(scale), _p(shift), _p(res), _p(y))
 
-    def _conv_fwd(self, stream, ws, d, x, x2, w, scale, shift, res, y):
-        return self.lib.clslam_conv_fwd(ctypes.byref(d), x, x2, w, scale, shift, res, y, ws, self.ws_bytes, stream)
+    def _conv_fwd(self, stream, ws, d, x, x2, w, w_hi, w_lo, scale, shift, res, y):
+        return self.lib.clslam_conv_fwd_bf16w(ctypes.byref(d), x, x2, w, w_hi, w_lo, scale, shift, res, y, ws, self.ws_bytes,
+                                              stream)
 
     def conv_dgrad(self, name, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev) -> None:
         self.need_ws(self.lib.clslam_conv_dgrad_workspace_bytes(ctypes.byref(d)))
@@ -209,7 +214,8 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: torch.Tensor, n: 
     feats = []
     d = plan.desc(n, h, w, prep.cin_pad, 64, 7, 2, 3, act=L.ACT_RELU)
     f0 = plan.alloc(n, d.ho, d.wo, 64)
-    plan.conv_fwd(f'{tag}.conv1', d, x_staged, None, t['conv1.w'], t['bn1.scale'], t['bn1.shift'], None, f0)
+    plan.conv_fwd(f'{tag}.conv1', d, x_staged, None, t['conv1.w'], t['bn1.scale'], t['bn1.shift'], None, f0,
+                  t['conv1.w_hi'], t['conv1.w_lo'])
     feats.append(f0)
     hp, wp = conv_out(d.ho, 3, 2, 1), conv_out(d.wo, 3, 2, 1)
     x = plan.alloc(n, hp, wp, 64)
@@ -222,18 +228,18 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: torch.Tensor, n: 
             d1 = plan.desc(n, hc, wc, cin, planes, 3, stride, 1, act=L.ACT_RELU)
             mid = plan.alloc(n, d1.ho, d1.wo, planes)
             plan.conv_fwd(f'{tag}.{p}.conv1', d1, x, None, t[p + '.conv1.w'], t[p + '.bn1.scale'], t[p + '.bn1.shift'],
-                          None, mid)
+                          None, mid, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'])
             if (p + '.ds.w') in t:
                 dd = plan.desc(n, hc, wc, cin, planes, 1, stride, 0, act=L.ACT_NONE)
                 idt = plan.alloc(n, dd.ho, dd.wo, planes)
                 plan.conv_fwd(f'{tag}.{p}.downsample', dd, x, None, t[p + '.ds.w'], t[p + '.dsbn.scale'],
-                              t[p + '.dsbn.shift'], None, idt)
+                              t[p + '.dsbn.shift'], None, idt, t[p + '.ds.w_hi'], t[p + '.ds.w_lo'])
             else:
                 idt = x
             d2 = plan.desc(n, d1.ho, d1.wo, planes, planes, 3, 1, 1, act=L.ACT_RELU)
             out = plan.alloc(n, d2.ho, d2.wo, planes)
             plan.conv_fwd(f'{tag}.{p}.conv2', d2, mid, None, t[p + '.conv2.w'], t[p + '.bn2.scale'], t[p + '.bn2.shift'],
-                          idt, out)
+                          idt, out, t[p + '.conv2.w_hi'], t[p + '.conv2.w_lo'])
             x, hc, wc, cin = out, d2.ho, d2.wo, planes
         feats.append(x)
     return feats
@@ -301,6 +307,9 @@ class AdaptEngine:
 
         # ---- depth network (lane 0; pose network on lane 1, identity candidates on lane 2) ------
         plan.fork((1, 2))
+        plan.set_lane(2)      # bf16 hi/lo planes of the trainable weights (they change every Adam step)
+        plan.simple('split_weights', lib.clslam_split_bf16, _p(flat.params), _p(flat.params_hi), _p(flat.params_lo), flat.numel)
+        plan.record('wsplit')
         plan.set_lane(0)
         self.depth_in = plan.alloc(b, h, w, depth_prep.cin_pad)
         plan.simple('depth.stage', lib.clslam_stage_images, _p(self.rgb_aug[1]), None, _p(self.depth_in), b, h, w,
@@ -312,12 +321,14 @@ class AdaptEngine:
         self.disp = {}
         self.dec_desc = {}
         x = feats[4]
+        plan.wait('wsplit')
         for i in range(4, -1, -1):
             hi_, wi_ = x.shape[1], x.shape[2]
             d0 = plan.desc(b, hi_, wi_, x.shape[3], DEC_CH[i], 3, 1, 1, pad_mode=L.PAD_REFLECT, act=L.ACT_ELU)
             y0 = plan.alloc(b, hi_, wi_, DEC_CH[i])
             key0 = (dd, f'upconv_{i}_0.conv.conv')
-            plan.conv_fwd(f'upconv_{i}_0', d0, x, None, flat.weight_ptr(key0), None, flat.bias_ptr(key0), None, y0)
+            plan.conv_fwd(f'upconv_{i}_0', d0, x, None, flat.weight_ptr(key0), None, flat.bias_ptr(key0), None, y0,
+                          flat.weight_hi_ptr(key0), flat.weight_lo_ptr(key0))
             self.y[(i, 0)] = y0; self.dec_desc[(i, 0)] = (d0, x)
             if i > 0:
                 skip = feats[i - 1]
@@ -331,7 +342,8 @@ class AdaptEngine:
                            c1=DEC_CH[i], h1=hi_, w1=wi_, act=L.ACT_ELU)
             y1 = plan.alloc(b, ho_, wo_, DEC_CH[i])
             key1 = (dd, f'upconv_{i}_1.conv.conv')
-            plan.conv_fwd(f'upconv_{i}_1', d1, y0, skip, flat.weight_ptr(key1), None, flat.bias_ptr(key1), None, y1)
+            plan.conv_fwd(f'upconv_{i}_1', d1, y0, skip, flat.weight_ptr(key1), None, flat.bias_ptr(key1), None, y1,
+                          flat.weight_hi_ptr(key1), flat.weight_lo_ptr(key1))
             self.y[(i, 1)] = y1; self.dec_desc[(i, 1)] = (d1, y0, skip)
             if i < S:
                 keyd = (dd, f'dispconv_{i}.conv')
@@ -357,11 +369,13 @@ class AdaptEngine:
         self.pose_act = {}
         self.pose_desc = {}
         x = pf4
+        plan.wait('wsplit')
         for name, co, ci, k, act in (('squeeze', 256, 512, 1, L.ACT_RELU), ('pose_0', 256, 256, 3, L.ACT_RELU),
                                      ('pose_1', 256, 256, 3, L.ACT_RELU), ('pose_2', 12, 256, 1, L.ACT_NONE)):
             d = plan.desc(2 * b, hp, wp, ci, co, k, 1, (k - 1) // 2, act=act)
             yv = plan.alloc(2 * b, hp, wp, co)
-            plan.conv_fwd(name, d, x, None, flat.weight_ptr((pd, name)), None, flat.bias_ptr((pd, name)), None, yv)
+            plan.conv_fwd(name, d, x, None, flat.weight_ptr((pd, name)), None, flat.bias_ptr((pd, name)), None, yv,
+                          flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)))
             self.pose_act[name] = yv; self.pose_desc[name] = (d, x)
             x = yv
         self.axis_angle = plan.alloc(2, b, 3)

@@ -209,6 +209,9 @@ class FlatParams:
         self.exp_avg = torch.zeros(total, device=device)
         self.exp_avg_sq = torch.zeros(total, device=device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)   # Adam updates done so far
+        # bf16 hi / lo planes of `params` (refreshed on the device at the start of every forward pass)
+        self.params_hi = torch.zeros(total, dtype=torch.bfloat16, device=device)
+        self.params_lo = torch.zeros(total, dtype=torch.bfloat16, device=device)
         self.index = {}   # (net, path) -> dict(w_off, w_numel, b_off, co, ci, k)
         off = 0
         mods = {'depth_decoder': depth_decoder, 'pose_decoder': pose_decoder}
@@ -237,6 +240,12 @@ class FlatParams:
 
     def weight_ptr(self, key) -> int:
         return self.params.data_ptr() + 4 * self.index[key]['w_off']
+
+    def weight_hi_ptr(self, key) -> int:
+        return self.params_hi.data_ptr() + 2 * self.index[key]['w_off']
+
+    def weight_lo_ptr(self, key) -> int:
+        return self.params_lo.data_ptr() + 2 * self.index[key]['w_off']
 
     def bias_ptr(self, key) -> int:
         return self.params.data_ptr() + 4 * self.index[key]['b_off']

@@ -85,6 +85,15 @@ int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, 
                     const float* scale, const float* shift, const float* residual, float* y,
                     void* workspace, long long workspace_bytes, void* stream);
 
+/* Same layer as clslam_conv_fwd with the weights additionally given as pre-split bf16 planes
+ * (w = w_hi + w_lo up to ~2^-17, [Cout][kh][kw][Cin] each, produced by clslam_split_bf16): 3x3/stride-1
+ * layers with Cin % 64 == 0 then run the patch-staged tcgen05 kernel, everything else falls back to
+ * clslam_conv_fwd with the fp32 weights `w`. */
+int clslam_split_bf16(const float* src, void* hi, void* lo, long long n, void* stream);
+int clslam_conv_fwd_bf16w(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
+                          const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,
+                          void* workspace, long long workspace_bytes, void* stream);
+
 /* 3x3/stride-2/pad-1 max pooling, NHWC (networks/resnet_encoder.py:121). */
 int clslam_maxpool3x3s2(const float* x, float* y, int n, int hi, int wi, int c, void* stream);
 

@@ -108,3 +108,21 @@ def conv_pre_ref(x, x2, w, stride, pad, pad_mode, upcat, out_hw=None):
 def rel_err(got, ref):
     got, ref = got.double().cpu(), ref.double().cpu()
     return float((got - ref).abs().max() / (ref.abs().max() + 1e-30))
+
+
+def split_bf16(t):
+    """fp32 cuda tensor -> (hi, lo) bf16 planes via the library's split kernel"""
+    flat = t.contiguous().view(-1)
+    hi = torch.empty(flat.numel(), dtype=torch.bfloat16, device='cuda')
+    lo = torch.empty(flat.numel(), dtype=torch.bfloat16, device='cuda')
+    L.check(lib().clslam_split_bf16(flat.data_ptr(), hi.data_ptr(), lo.data_ptr(), flat.numel(), stream()), 'split_bf16')
+    return hi, lo
+
+
+def conv_fwd_bf16w(d, x, x2, w, scale, shift, res):
+    y = torch.empty(d.n, d.ho, d.wo, d.co, device='cuda')
+    hi, lo = split_bf16(w)
+    ws, wp, wb = _ws(lib().clslam_conv_fwd_workspace_bytes(ctypes.byref(d)))
+    L.check(lib().clslam_conv_fwd_bf16w(ctypes.byref(d), P(x), P(x2), P(w), P(hi), P(lo), P(scale), P(shift), P(res), P(y), wp, wb,
+                                        stream()), 'conv_fwd_bf16w')
+    return y

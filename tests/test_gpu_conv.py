@@ -231,3 +231,49 @@ def test_adam_matches_torch_optim():
         d_got = (p.cpu() - p0).double()
         assert float((d_ref - d_got).abs().max()) < 1e-6      # ~1 ulp of the O(1) parameters; |delta| ~ 1e-4
     assert int(step_dev.item()) == 3
+
+
+P3_CASES = [
+    # n, h, w, c1, c2, co, pad_mode, act, use_scale, use_res   (c2 > 0 or c1 != ci -> UPCAT: x at (h/2, w/2))
+    (1, 48, 160, 64, 0, 64, L.PAD_ZERO, L.ACT_RELU, True, True),       # encoder layer1 conv2 (+ residual)
+    (2, 6, 20, 512, 0, 512, L.PAD_ZERO, L.ACT_RELU, True, False),      # layer4: ragged tile (6 rows, 20 cols), split over chunks
+    (1, 6, 20, 512, 0, 256, L.PAD_REFLECT, L.ACT_ELU, False, False),   # upconv_4_0
+    (3, 2, 3, 512, 0, 256, L.PAD_REFLECT, L.ACT_ELU, False, False),    # 2x3 map (64x96 fixtures)
+    (1, 24, 40, 64, 0, 32, L.PAD_REFLECT, L.ACT_ELU, False, False),    # upconv_1_0-like (co=32)
+    (1, 17, 23, 128, 0, 16, L.PAD_ZERO, L.ACT_NONE, False, False),     # odd sizes, co=16
+    (2, 12, 20, 256, 256, 256, L.PAD_REFLECT, L.ACT_ELU, False, False),  # upconv_4_1 (UPCAT)
+    (1, 24, 40, 64, 64, 64, L.PAD_REFLECT, L.ACT_ELU, False, False),     # upconv_2_1 (UPCAT)
+    (1, 4, 6, 256, 256, 256, L.PAD_REFLECT, L.ACT_ELU, False, False),    # UPCAT on a 4x6 map
+]
+
+
+@pytest.mark.parametrize('case', P3_CASES)
+def test_conv3x3_patch_kernel(case, conv_mode):
+    """3x3/s1 forward through clslam_conv_fwd_bf16w (patch-staged tcgen05 kernel in mode 1, fp32 fallback in mode 0)"""
+    n, h, w_, c1, c2, co, pad_mode, act, use_scale, use_res = case
+    upcat = c2 > 0
+    ci = c1 + c2
+    if upcat:
+        d = cabi.make_desc(n, h, w_, ci, co, 3, 1, 1, pad_mode, L.IN_UPCAT, c1, h // 2, w_ // 2, act=act)
+        x1 = rnd(n, c1, h // 2, w_ // 2, seed=1)
+        x2 = rnd(n, c2, h, w_, seed=2)
+    else:
+        d = cabi.make_desc(n, h, w_, ci, co, 3, 1, 1, pad_mode, act=act)
+        x1 = rnd(n, ci, h, w_, seed=1)
+        x2 = None
+    w = rnd(co, ci, 3, 3, seed=3, scale=(ci * 9) ** -0.5)
+    scale = (1 + 0.2 * rnd(co, seed=4)) if use_scale else None
+    shift = 0.1 * rnd(co, seed=5)
+    res = rnd(n, co, h, w_, seed=6) if use_res else None
+    ref = cabi.conv_pre_ref(x1, x2, w, 1, 1, pad_mode, upcat, (h, w_))
+    if scale is not None:
+        ref = ref * scale.view(1, -1, 1, 1)
+    ref = ref + shift.view(1, -1, 1, 1)
+    if res is not None:
+        ref = ref + res
+    ref = cabi.act_ref(ref, act)
+    cu = lambda t: None if t is None else t.float().cuda()
+    y = cabi.conv_fwd_bf16w(d, cabi.nhwc(x1).float().cuda(), None if x2 is None else cabi.nhwc(x2).float().cuda(),
+                            cabi.krsc(w).float().cuda(), cu(scale), cu(shift), None if res is None else cabi.nhwc(res).float().cuda())
+    torch.cuda.synchronize()
+    assert cabi.rel_err(cabi.nchw(y), ref) < TOL
