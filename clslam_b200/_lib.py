@@ -27,7 +27,7 @@ class PhotoArgs(Structure):
     _fields_ = [
         ('b', c_int), ('h', c_int), ('w', c_int), ('n_scales', c_int),
         ('depth_mode', c_int), ('min_depth', c_float), ('max_depth', c_float),
-        ('target', c_void_p), ('sources', c_void_p), ('inv_k', c_void_p), ('proj', c_void_p),
+        ('target', c_void_p), ('sources', c_void_p), ('sources_rgba', c_void_p), ('inv_k', c_void_p), ('proj', c_void_p),
         ('identity', c_void_p), ('sample_w', c_void_p),
         ('disp', c_void_p * 4), ('noise', c_void_p * 4), ('depth', c_void_p * 4), ('warped', c_void_p * 4),
         ('argmin', c_void_p * 4), ('loss_partials', c_void_p), ('ddisp_full', c_void_p * 4),
@@ -79,6 +79,7 @@ SIGNATURES = {
     'clslam_pose_head_bwd': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
                                      c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'clslam_photo_tiles': (c_int, [c_int, c_int]),
+    'clslam_pack_rgba': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'clslam_photo_identity': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'clslam_photo_fwd': (c_int, [POINTER(PhotoArgs), c_void_p]),
     'clslam_photo_bwd': (c_int, [POINTER(PhotoArgs), c_void_p]),

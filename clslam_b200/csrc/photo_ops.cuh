@@ -69,12 +69,15 @@ CLSLAM_HD void warp_geometry(const float* inv_k /*4x4*/, const float* P /*3x4*/,
 #pragma unroll
   for (int r = 0; r < 3; ++r) p[r] = P[r * 4 + 0] * g.X[0] + P[r * 4 + 1] * g.X[1] + P[r * 4 + 2] * g.X[2] + P[r * 4 + 3];
   g.z = p[2] + 1e-7f;
-  g.px = p[0] / g.z;
-  g.py = p[1] / g.z;
-  const float gx = (g.px / (float)(w - 1) - 0.5f) * 2.f;
-  const float gy = (g.py / (float)(h - 1) - 0.5f) * 2.f;
-  float ix = ((gx + 1.f) / 2.f) * (float)(w - 1);
-  float iy = ((gy + 1.f) / 2.f) * (float)(h - 1);
+  // one reciprocal instead of two divisions, and multiplications by 1/(W-1), 1/(H-1): <= 1 ulp from the
+  // reference's division sequence (layers.py:98-103), far below the sampling-coordinate sensitivity
+  const float rz = 1.f / g.z;
+  g.px = p[0] * rz;
+  g.py = p[1] * rz;
+  const float gx = (g.px * (1.f / (float)(w - 1)) - 0.5f) * 2.f;
+  const float gy = (g.py * (1.f / (float)(h - 1)) - 0.5f) * 2.f;
+  float ix = ((gx + 1.f) * 0.5f) * (float)(w - 1);
+  float iy = ((gy + 1.f) * 0.5f) * (float)(h - 1);
   // clip_coordinates_set_grad: gradient is zeroed where the coordinate is clipped
   g.mx = 1.f; g.my = 1.f;
   if (!(ix > 0.f)) { ix = 0.f; g.mx = 0.f; } else if (ix >= (float)(w - 1)) { ix = (float)(w - 1); g.mx = 0.f; }
@@ -117,21 +120,47 @@ CLSLAM_HD void sample_plane_grad(const float* plane, int w, const Taps& t, float
   diy = -nw * t.tx0 - ne * t.tx1 + sw * t.tx0 + se * t.tx1;
 }
 
+// ---- the same sampling on RGBA-packed sources ((h, w, 4) floats): one 16-byte load per tap ----------
+CLSLAM_HD void sample_rgba(const float* img, int w, const Taps& t, float (&out)[3]) {
+  const float* r0 = img + (t.y0 * w + t.x0) * 4;
+  const float4 nw = ld4(r0);
+  out[0] = nw.x * t.nw; out[1] = nw.y * t.nw; out[2] = nw.z * t.nw;
+  if (t.x1ok) { const float4 v = ld4(r0 + 4); out[0] += v.x * t.ne; out[1] += v.y * t.ne; out[2] += v.z * t.ne; }
+  if (t.y1ok) {
+    const float4 v = ld4(r0 + w * 4);
+    out[0] += v.x * t.sw; out[1] += v.y * t.sw; out[2] += v.z * t.sw;
+    if (t.x1ok) { const float4 u = ld4(r0 + w * 4 + 4); out[0] += u.x * t.se; out[1] += u.y * t.se; out[2] += u.z * t.se; }
+  }
+}
+// sum_c g[c] * d(sample_c)/d(ix), .../d(iy) (before the clip mask)
+CLSLAM_HD void sample_rgba_grad(const float* img, int w, const Taps& t, const float (&g)[3], float& gix, float& giy) {
+  const float* r0 = img + (t.y0 * w + t.x0) * 4;
+  const float4 nw = ld4(r0);
+  const float4 ne = t.x1ok ? ld4(r0 + 4) : f4zero();
+  const float4 sw = t.y1ok ? ld4(r0 + w * 4) : f4zero();
+  const float4 se = (t.x1ok && t.y1ok) ? ld4(r0 + w * 4 + 4) : f4zero();
+  const float dnw = g[0] * nw.x + g[1] * nw.y + g[2] * nw.z, dne = g[0] * ne.x + g[1] * ne.y + g[2] * ne.z;
+  const float dsw = g[0] * sw.x + g[1] * sw.y + g[2] * sw.z, dse = g[0] * se.x + g[1] * se.y + g[2] * se.z;
+  gix = -dnw * t.ty0 + dne * t.ty0 - dsw * t.ty1 + dse * t.ty1;
+  giy = -dnw * t.tx0 - dne * t.tx1 + dsw * t.tx0 + dse * t.tx1;
+}
+
 // ---- SSIM of one channel from 3x3 window sums (networks/layers.py:123-137) -----------------
 struct SsimStats { float mu_x, mu_y, a1, a2, b1, b2, n, d, val; };
 CLSLAM_HD SsimStats ssim_stats(float sx, float sy, float sxx, float syy, float sxy) {
   SsimStats s;
-  s.mu_x = sx / 9.f; s.mu_y = sy / 9.f;
-  const float sig_x = sxx / 9.f - s.mu_x * s.mu_x;
-  const float sig_y = syy / 9.f - s.mu_y * s.mu_y;
-  const float sig_xy = sxy / 9.f - s.mu_x * s.mu_y;
+  constexpr float k9 = 1.f / 9.f;      // AvgPool2d(3, 1) divides the window sum by 9
+  s.mu_x = sx * k9; s.mu_y = sy * k9;
+  const float sig_x = sxx * k9 - s.mu_x * s.mu_x;
+  const float sig_y = syy * k9 - s.mu_y * s.mu_y;
+  const float sig_xy = sxy * k9 - s.mu_x * s.mu_y;
   s.a1 = 2.f * s.mu_x * s.mu_y + kSsimC1;
   s.a2 = 2.f * sig_xy + kSsimC2;
   s.b1 = s.mu_x * s.mu_x + s.mu_y * s.mu_y + kSsimC1;
   s.b2 = sig_x + sig_y + kSsimC2;
   s.n = s.a1 * s.a2;
   s.d = s.b1 * s.b2;
-  s.val = (1.f - s.n / s.d) / 2.f;
+  s.val = (1.f - s.n / s.d) * 0.5f;
   return s;
 }
 CLSLAM_HD float clamp01(float v) { return v < 0.f ? 0.f : (v > 1.f ? 1.f : v); }

@@ -52,6 +52,17 @@ __device__ __forceinline__ float reproj_error(const float* xs /*[3][..][LW]*/, c
   return 0.85f * (ssim_sum / 3.f) + 0.15f * (l1_sum / 3.f);
 }
 
+// ---- (n, 3, h, w) planar -> (n, h, w, 4) packed: the warp gathers one float4 per bilinear tap ----------
+__global__ void __launch_bounds__(256)
+pack_rgba_kernel(const float* __restrict__ planar, float* __restrict__ packed, int n, int hw) {
+  const size_t total = (size_t)n * hw;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t img = i / hw, px = i - img * hw;
+    const float* p = planar + img * 3 * hw + px;
+    *reinterpret_cast<float4*>(packed + i * 4) = make_float4(ld1(p), ld1(p + hw), ld1(p + 2 * (size_t)hw), 0.f);
+  }
+}
+
 // ---- identity (auto-mask) candidates -------------------------------------------------------
 __global__ void __launch_bounds__(kPhotoThreads)
 photo_identity_kernel(const float* __restrict__ target, const float* __restrict__ sources, float* __restrict__ identity,
@@ -86,76 +97,144 @@ photo_identity_kernel(const float* __restrict__ target, const float* __restrict_
 }
 
 // ---- forward --------------------------------------------------------------------------------
+// One CTA = one 32x16 tile of one sample, looping over the scales: the target tile and its SSIM
+// window statistics are loaded / computed once and reused by every scale and both source frames.
 __global__ void __launch_bounds__(kPhotoThreads)
 photo_fwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
   __shared__ float tg[3 * kFN];
   __shared__ float wx[2 * 3 * kFN];
   __shared__ float red[8];
   __shared__ float geo[16 + 24];           // inv_K (4x4), proj (2 x 3x4)
-  const int s = blockIdx.y / a.b, bb = blockIdx.y % a.b;
-  const int h = a.h, w = a.w, hs = h >> s, ws = w >> s;
+  __shared__ int up_i0[kFH + kFW], up_i1[kFH + kFW];     // bilinear up-sampling taps of the halo rows / columns
+  __shared__ float up_l1[kFH + kFW];
+  const int bb = blockIdx.y;
+  const int h = a.h, w = a.w;
   const int tile = blockIdx.x;
   const int tx0 = (tile % tiles_x) * kPhotoTW, ty0 = (tile / tiles_x) * kPhotoTH;
   const size_t hw = (size_t)h * w;
-  if (threadIdx.x < 16) geo[threadIdx.x] = a.inv_k[bb * 16 + threadIdx.x];
-  else if (threadIdx.x < 40) {
-    const int i = threadIdx.x - 16, f = i / 12;
-    geo[threadIdx.x] = a.proj[((size_t)f * a.b + bb) * 12 + (i - f * 12)];
+  const int tid = threadIdx.x;
+  if (tid < 16) geo[tid] = a.inv_k[bb * 16 + tid];
+  else if (tid < 40) {
+    const int i = tid - 16, f = i / 12;
+    geo[tid] = a.proj[((size_t)f * a.b + bb) * 12 + (i - f * 12)];
   }
-  __syncthreads();
-  const float* disp_b = a.disp[s] + (size_t)bb * hs * ws;
-  float* depth_out = a.depth[s];
-  float* warped_out = a.warped[s];
-  for (int i = threadIdx.x; i < kFN; i += kPhotoThreads) {
+  for (int i = tid; i < kFN; i += kPhotoThreads) {
     const int ly = i / kFW, lx = i - ly * kFW;
-    const int py = ty0 + ly - 1, px = tx0 + lx - 1;
-    const int y = pad_coord(py, h), x = pad_coord(px, w);
-    const size_t off = (size_t)y * w + x;
+    const size_t off = (size_t)pad_coord(ty0 + ly - 1, h) * w + pad_coord(tx0 + lx - 1, w);
 #pragma unroll
     for (int c = 0; c < 3; ++c) tg[c * kFN + i] = ld1(a.target + ((size_t)bb * 3 + c) * hw + off);
-    const float d = disp_upsample(disp_b, hs, ws, h, w, y, x);
-    const float depth = depth_from_disp(d, a.depth_mode, a.min_depth, a.max_depth);
-    const bool interior = (py == y) && (px == x) && ly >= 1 && ly <= kPhotoTH && lx >= 1 && lx <= kPhotoTW;
-    if (interior && depth_out) depth_out[(size_t)bb * hw + off] = depth;
-#pragma unroll
-    for (int f = 0; f < 2; ++f) {
-      WarpGeom g;
-      warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
-      const Taps t = make_taps(g.ix, g.iy, h, w);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float v = sample_plane(a.sources + (((size_t)f * a.b + bb) * 3 + c) * hw, w, t);
-        wx[(f * 3 + c) * kFN + i] = v;
-        if (interior && warped_out) warped_out[(((size_t)f * a.b + bb) * 3 + c) * hw + off] = v;
-      }
-    }
   }
   __syncthreads();
-  float local = 0.f;
+  // this thread's two output pixels: (lx, 2*jy) and (lx, 2*jy + 1); target window sums are scale independent
+  const int lx = tid % kPhotoTW, jy = tid / kPhotoTW;
+  float sy[2][3], syy[2][3];
 #pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int lx = threadIdx.x % kPhotoTW, ly = (threadIdx.x / kPhotoTW) * 2 + j;
-    const int x = tx0 + lx, y = ty0 + ly;
-    if (x < w && y < h) {
+  for (int c = 0; c < 3; ++c) {
+    float rs[4], rss[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float* p = tg + c * kFN + (2 * jy + r) * kFW + lx;
+      rs[r] = p[0] + p[1] + p[2];
+      rss[r] = p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
+    }
+    sy[0][c] = rs[0] + rs[1] + rs[2]; syy[0][c] = rss[0] + rss[1] + rss[2];
+    sy[1][c] = rs[1] + rs[2] + rs[3]; syy[1][c] = rss[1] + rss[2] + rss[3];
+  }
+  float local[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int s = 0; s < a.n_scales; ++s) {
+    const int hs = h >> s, ws = w >> s;
+    const float* disp_b = a.disp[s] + (size_t)bb * hs * ws;
+    float* depth_out = a.depth[s];
+    float* warped_out = a.warped[s];
+    if (tid < kFH + kFW) {
+      const bool is_row = tid < kFH;
+      const int coord = is_row ? pad_coord(ty0 + tid - 1, h) : pad_coord(tx0 + (tid - kFH) - 1, w);
+      const UpCoef cf = is_row ? up_coef(coord, hs, h) : up_coef(coord, ws, w);
+      up_i0[tid] = cf.i0; up_i1[tid] = cf.i1; up_l1[tid] = cf.l1;
+    }
+    __syncthreads();          // also: every read of wx by the previous scale is done
+    for (int i = tid; i < kFN; i += kPhotoThreads) {
+      const int ly = i / kFW, lxx = i - ly * kFW;
+      const int py = ty0 + ly - 1, px = tx0 + lxx - 1;
+      const int y = pad_coord(py, h), x = pad_coord(px, w);
       const size_t off = (size_t)y * w + x;
-      float best = ld1(a.identity + ((size_t)bb * 2 + 0) * hw + off);
-      float c1 = ld1(a.identity + ((size_t)bb * 2 + 1) * hw + off);
-      if (a.noise[s]) {
-        best += ld1(a.noise[s] + ((size_t)bb * 2 + 0) * hw + off) * 0.00001f;
-        c1 += ld1(a.noise[s] + ((size_t)bb * 2 + 1) * hw + off) * 0.00001f;
+      const float ly1 = up_l1[ly], lx1 = up_l1[kFH + lxx];
+      const float* r0 = disp_b + (size_t)up_i0[ly] * ws;
+      const float* r1 = disp_b + (size_t)up_i1[ly] * ws;
+      const int c0 = up_i0[kFH + lxx], c1 = up_i1[kFH + lxx];
+      const float d = (1.f - ly1) * ((1.f - lx1) * ld1(r0 + c0) + lx1 * ld1(r0 + c1)) +
+                      ly1 * ((1.f - lx1) * ld1(r1 + c0) + lx1 * ld1(r1 + c1));
+      const float depth = depth_from_disp(d, a.depth_mode, a.min_depth, a.max_depth);
+      const bool interior = (py == y) && (px == x) && ly >= 1 && ly <= kPhotoTH && lxx >= 1 && lxx <= kPhotoTW;
+      if (interior && depth_out) depth_out[(size_t)bb * hw + off] = depth;
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        WarpGeom g;
+        warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
+        const Taps t = make_taps(g.ix, g.iy, h, w);
+        float v3[3];
+        sample_rgba(a.sources_rgba + ((size_t)f * a.b + bb) * hw * 4, w, t, v3);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          wx[(f * 3 + c) * kFN + i] = v3[c];
+          if (interior && warped_out) warped_out[(((size_t)f * a.b + bb) * 3 + c) * hw + off] = v3[c];
+        }
       }
-      int arg = 0;
-      if (c1 < best) { best = c1; arg = 1; }
-      const float r0 = reproj_error<kFW>(wx, tg, kFN, ly + 1, lx + 1);
-      if (r0 < best) { best = r0; arg = 2; }
-      const float r1 = reproj_error<kFW>(wx + 3 * kFN, tg, kFN, ly + 1, lx + 1);
-      if (r1 < best) { best = r1; arg = 3; }
-      a.argmin[s][(size_t)bb * hw + off] = (unsigned char)arg;
-      local += best;
+    }
+    __syncthreads();
+    // SSIM + L1 of both warped frames for the two pixels of this thread (shared row sums)
+    float rep[2][2];          // [frame][pixel]
+#pragma unroll
+    for (int f = 0; f < 2; ++f) {
+      float ssim_sum[2] = {0.f, 0.f}, l1_sum[2] = {0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float* xp = wx + (f * 3 + c) * kFN + (2 * jy) * kFW + lx;
+        const float* yp = tg + c * kFN + (2 * jy) * kFW + lx;
+        float rx[4], rxx[4], rxy[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const float x0 = xp[r * kFW], x1 = xp[r * kFW + 1], x2 = xp[r * kFW + 2];
+          const float y0 = yp[r * kFW], y1 = yp[r * kFW + 1], y2 = yp[r * kFW + 2];
+          rx[r] = x0 + x1 + x2;
+          rxx[r] = x0 * x0 + x1 * x1 + x2 * x2;
+          rxy[r] = x0 * y0 + x1 * y1 + x2 * y2;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const SsimStats st = ssim_stats(rx[j] + rx[j + 1] + rx[j + 2], sy[j][c], rxx[j] + rxx[j + 1] + rxx[j + 2], syy[j][c],
+                                          rxy[j] + rxy[j + 1] + rxy[j + 2]);
+          ssim_sum[j] += clamp01(st.val);
+          l1_sum[j] += fabsf(yp[(j + 1) * kFW + 1] - xp[(j + 1) * kFW + 1]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) rep[f][j] = 0.85f * (ssim_sum[j] * (1.f / 3.f)) + 0.15f * (l1_sum[j] * (1.f / 3.f));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int x = tx0 + lx, y = ty0 + 2 * jy + j;
+      if (x < w && y < h) {
+        const size_t off = (size_t)y * w + x;
+        float best = ld1(a.identity + ((size_t)bb * 2 + 0) * hw + off);
+        float c1v = ld1(a.identity + ((size_t)bb * 2 + 1) * hw + off);
+        if (a.noise[s]) {
+          best += ld1(a.noise[s] + ((size_t)bb * 2 + 0) * hw + off) * 0.00001f;
+          c1v += ld1(a.noise[s] + ((size_t)bb * 2 + 1) * hw + off) * 0.00001f;
+        }
+        int arg = 0;
+        if (c1v < best) { best = c1v; arg = 1; }
+        if (rep[0][j] < best) { best = rep[0][j]; arg = 2; }
+        if (rep[1][j] < best) { best = rep[1][j]; arg = 3; }
+        a.argmin[s][(size_t)bb * hw + off] = (unsigned char)arg;
+        local[s] += best;
+      }
     }
   }
-  const float total = block_sum(local, red);
-  if (threadIdx.x == 0) a.loss_partials[((size_t)s * a.b + bb) * tiles + tile] = total;
+  for (int s = 0; s < a.n_scales; ++s) {
+    const float total = block_sum(local[s], red);
+    if (tid == 0) a.loss_partials[((size_t)s * a.b + bb) * tiles + tile] = total;
+  }
 }
 
 // ---- backward -------------------------------------------------------------------------------
@@ -193,7 +272,7 @@ photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
   float ddepth[2] = {0.f, 0.f};
   float dval[2] = {0.f, 0.f}, depthv[2] = {0.f, 0.f};
   for (int f = 0; f < 2; ++f) {
-    const float* src = a.sources + ((size_t)f * a.b + bb) * 3 * hw;
+    const float* src = a.sources_rgba + ((size_t)f * a.b + bb) * hw * 4;
     // phase 1: warped source on tile + 2
     for (int i = threadIdx.x; i < kBN; i += kPhotoThreads) {
       const int ly = i / kBW, lx = i - ly * kBW;
@@ -203,8 +282,10 @@ photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
       WarpGeom g;
       warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
       const Taps t = make_taps(g.ix, g.iy, h, w);
+      float v3[3];
+      sample_rgba(src, w, t, v3);
 #pragma unroll
-      for (int c = 0; c < 3; ++c) wx[c * kBN + i] = sample_plane(src + (size_t)c * hw, w, t);
+      for (int c = 0; c < 3; ++c) wx[c * kBN + i] = v3[c];
     }
     __syncthreads();
     // phase 2: SSIM gradient coefficients at window centres p on tile + 1 (in-image, selected by argmin)
@@ -259,6 +340,7 @@ photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
       const Taps t = make_taps(g.ix, g.iy, h, w);
       const bool sel = amin[(size_t)y * w + x] == 2 + f;
       float gix = 0.f, giy = 0.f;
+      float gx3[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const float xq = wx[c * kBN + (ly + 2) * kBW + lx + 2];
@@ -281,16 +363,15 @@ photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
           const float diff = yq - xq;                     // |target - pred|: d/dpred = -sgn(target - pred)
           gxc -= g0 * (0.15f / 3.f) * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
         }
-        float dix, diy;
-        sample_plane_grad(src + (size_t)c * hw, w, t, dix, diy);
-        gix += gxc * dix;
-        giy += gxc * diy;
+        gx3[c] = gxc;
       }
+      sample_rgba_grad(src, w, t, gx3, gix, giy);
       const float dpx = gix * g.mx, dpy = giy * g.my;   // (W-1)/2 * 2/(W-1) cancel
+      const float rz = 1.f / g.z;
       float dp[3];
-      dp[0] = dpx / g.z;
-      dp[1] = dpy / g.z;
-      dp[2] = -(dpx * g.px + dpy * g.py) / g.z;
+      dp[0] = dpx * rz;
+      dp[1] = dpy * rz;
+      dp[2] = -(dpx * g.px + dpy * g.py) * rz;
       const float* P = geo + 16 + f * 12;
       float dd = 0.f;
 #pragma unroll
@@ -383,6 +464,14 @@ using namespace clslam;
 
 extern "C" {
 
+int clslam_pack_rgba(const float* planar, float* packed, int n_images, int h, int w, void* stream) {
+  const size_t total = (size_t)n_images * h * w;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pack_rgba_kernel<<<blocks, 256, 0, as_stream(stream)>>>(planar, packed, n_images, h * w);
+  return finish_launch("pack_rgba");
+}
+
 int clslam_photo_tiles(int h, int w) { return ((w + kPhotoTW - 1) / kPhotoTW) * ((h + kPhotoTH - 1) / kPhotoTH); }
 
 int clslam_photo_identity(const float* target, const float* sources, float* identity, int b, int h, int w, void* stream) {
@@ -395,6 +484,7 @@ int clslam_photo_identity(const float* target, const float* sources, float* iden
 
 static int check_photo(const clslam_photo_args* a, const char* what) {
   if (!a) { set_error("%s: null args", what); return -1; }
+  if (!a->sources_rgba) { set_error("%s: sources_rgba is null (clslam_pack_rgba)", what); return -1; }
   if (a->n_scales < 1 || a->n_scales > 4 || a->b < 1 || a->h < 2 || a->w < 2) { set_error("%s: bad dims", what); return -1; }
   if ((a->h % (1 << (a->n_scales - 1))) || (a->w % (1 << (a->n_scales - 1)))) { set_error("%s: h, w must be divisible by 2^(n_scales-1)", what); return -1; }
   if ((long long)a->b * a->n_scales > 65535) { set_error("%s: b * n_scales > 65535", what); return -1; }
@@ -404,7 +494,7 @@ static int check_photo(const clslam_photo_args* a, const char* what) {
 int clslam_photo_fwd(const clslam_photo_args* a, void* stream) {
   if (int rc = check_photo(a, "photo_fwd")) return rc;
   const int tiles_x = (a->w + kPhotoTW - 1) / kPhotoTW, tiles = clslam_photo_tiles(a->h, a->w);
-  dim3 grid(tiles, a->b * a->n_scales);
+  dim3 grid(tiles, a->b);
   photo_fwd_kernel<<<grid, kPhotoThreads, 0, as_stream(stream)>>>(*a, tiles_x, tiles);
   return finish_launch("photo_fwd");
 }

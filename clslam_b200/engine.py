@@ -297,6 +297,7 @@ class AdaptEngine:
         self.rgb_aug = plan.alloc(3, b, 3, h, w)            # frames -1, 0, +1
         self.target = plan.alloc(b, 3, h, w)                # ('rgb', 0, 0)
         self.sources = plan.alloc(2, b, 3, h, w)            # ('rgb', -1, 0), ('rgb', 1, 0)
+        self.sources_rgba = plan.alloc(2, b, h, w, 4)       # packed copy sampled by the warp kernels
         self.color = [self.target] + [plan.alloc(b, 3, h >> s, w >> s) for s in range(1, S)]
         self.k_mat = plan.alloc(b, 4, 4)
         self.inv_k = plan.alloc(b, 4, 4)
@@ -409,6 +410,7 @@ class AdaptEngine:
         pa.b, pa.h, pa.w, pa.n_scales = b, h, w, S
         pa.depth_mode, pa.min_depth, pa.max_depth = mode, float(min_depth or 0.0), float(max_depth or 0.0)
         pa.target, pa.sources, pa.inv_k, pa.proj = _p(self.target), _p(self.sources), _p(self.inv_k), _p(self.proj)
+        pa.sources_rgba = _p(self.sources_rgba)
         pa.identity, pa.sample_w = _p(self.identity), _p(self.sample_w)
         for s in range(S):
             pa.disp[s] = _p(self.disp[s]); pa.noise[s] = _p(self.noise[s])
@@ -430,6 +432,7 @@ class AdaptEngine:
         self.loss_args = la
         plan.keep.append(la)
         plan.set_lane(2)
+        plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
         plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
         plan.join((1, 2))
         plan.add('photo_fwd', lambda stream, ws: lib.clslam_photo_fwd(ctypes.byref(pa), stream))

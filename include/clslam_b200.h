@@ -162,6 +162,7 @@ typedef struct clslam_photo_args {
   int depth_mode; float min_depth, max_depth;
   const float* target;        /* (b,3,h,w)  inputs['rgb',0,0] */
   const float* sources;       /* (2,b,3,h,w) inputs['rgb',-1,0], inputs['rgb',1,0] */
+  const float* sources_rgba;  /* (2,b,h,w,4) the same images packed by clslam_pack_rgba (sampled by fwd / bwd) */
   const float* inv_k;         /* (b,4,4) inputs['inv_camera_matrix',0] */
   const float* proj;          /* (2,b,12) from clslam_pose_head_fwd */
   const float* identity;      /* (b,2,h,w) from clslam_photo_identity */
@@ -176,6 +177,8 @@ typedef struct clslam_photo_args {
   float* dproj_partials;
 } clslam_photo_args;
 int clslam_photo_tiles(int h, int w);
+/* (n,3,h,w) planar -> (n,h,w,4) packed (4th component 0): one 16-byte load per bilinear tap in the warp */
+int clslam_pack_rgba(const float* planar, float* packed, int n_images, int h, int w, void* stream);
 int clslam_photo_identity(const float* target, const float* sources, float* identity, int b, int h, int w,
                           void* stream);
 int clslam_photo_fwd(const clslam_photo_args* a, void* stream);
