@@ -12,7 +12,7 @@ from pathlib import Path
 LIB_PATH = Path(__file__).resolve().parent / 'libclslam_b200.so'
 
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3
-PAD_ZERO, PAD_REFLECT = 0, 1
+PAD_ZERO, PAD_REFLECT, PAD_FULL = 0, 1, 2
 IN_PLAIN, IN_UPCAT = 0, 1
 DEPTH_INV, DEPTH_MIN_ONLY, DEPTH_MIN_MAX = 0, 1, 2
 N_LOSS_SLOTS = 24
@@ -21,6 +21,19 @@ N_LOSS_SLOTS = 24
 class ConvDesc(Structure):
     _fields_ = [(n, c_int) for n in ('n', 'hi', 'wi', 'ci', 'ho', 'wo', 'co', 'kh', 'kw', 'stride', 'pad',
                                      'pad_mode', 'in_mode', 'c1', 'h1', 'w1', 'act')]
+
+
+class Planes(Structure):
+    """clslam_planes: bf16 hi/lo activation planes [2][n][h+2][w+2][c_total]"""
+    _fields_ = [('base', c_void_p), ('plane_stride', c_longlong), ('n', c_int), ('h', c_int), ('w', c_int),
+                ('c_total', c_int), ('c_off', c_int), ('c', c_int)]
+
+
+class ConvTma(Structure):
+    """clslam_conv_tma"""
+    _fields_ = [('inp', Planes), ('pad_mode', c_int), ('cout', c_int), ('w_hi', c_void_p), ('w_lo', c_void_p),
+                ('scale', c_void_p), ('shift', c_void_p), ('act', c_int), ('residual', POINTER(Planes)), ('y', c_void_p),
+                ('out', POINTER(Planes)), ('out_up', c_int), ('out_halo', c_int)]
 
 
 class PhotoArgs(Structure):
@@ -61,6 +74,11 @@ SIGNATURES = {
     'clslam_split_bf16': (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     'clslam_conv_fwd_bf16w': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    'clslam_conv3x3_tma': (c_int, [POINTER(ConvTma), c_void_p]),
+    'clslam_conv_fwd_emit': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, POINTER(Planes), c_int, c_int, c_void_p, c_longlong, c_void_p]),
+    'clslam_maxpool3x3s2_emit': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(Planes), c_int, c_void_p]),
+    'clslam_planes_from_f32': (c_int, [c_void_p, POINTER(Planes), c_int, c_int, c_void_p]),
     'clslam_maxpool3x3s2': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_dispconv_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_conv_dgrad_workspace_bytes': (c_longlong, [POINTER(ConvDesc)]),

@@ -5,6 +5,7 @@
 #include "gemm_core.cuh"
 #include "gemm_tc.cuh"
 #include "conv3x3_tc.cuh"
+#include "planes.cuh"
 
 namespace clslam {
 
@@ -271,6 +272,14 @@ struct EpiFwd {
   static constexpr bool kBias = false;
   float* y; const float* scale; const float* shift; const float* res;
   int N, act;
+  PlaneView po;       // optional second output: bf16 hi/lo planes (base == nullptr: none)
+  int ho, wo;         // output spatial dims (row m -> (image, oh, ow)) when po is set
+  __device__ void emit(int m, int n, const float (&o)[4]) const {
+    const int hw = ho * wo;
+    const int img = m / hw, rem = m - img * hw;
+    const int oh = rem / wo;
+    planes_emit<4>(po, img, oh, rem - oh * wo, n, o);
+  }
   // tensor-core kernel: per-column parameters are staged in shared memory once per CTA
   __device__ void tc_prologue(float* sp, int n0, int bn, int n_total, int tid) const {
     for (int j = tid; j < bn; j += kTcThreads) {
@@ -287,7 +296,8 @@ struct EpiFwd {
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) o[j] = act_apply(v[j] * sp[nl + j] + sp[bn + nl + j] + rr[j], act);
-    *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (y) *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (po.base) emit(m, n, o);
   }
   __device__ void store(int m, int n, const float (&v)[4]) const {
     float o[4];
@@ -300,7 +310,8 @@ struct EpiFwd {
       if (res) t += res[off + j];
       o[j] = act_apply(t, act);
     }
-    *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (y) *reinterpret_cast<float4*>(y + off) = make_float4(o[0], o[1], o[2], o[3]);
+    if (po.base) emit(m, n, o);
   }
   __device__ void store_bias(int, float) const {}
 };
@@ -621,18 +632,44 @@ int clslam_split_bf16(const float* src, void* hi, void* lo, long long n, void* s
   return finish_launch("split_bf16");
 }
 
-int clslam_conv_fwd_bf16w(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
-                          const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,
-                          void* workspace, long long workspace_bytes, void* stream) {
-  if (int rc = check_desc(d, "conv_fwd_bf16w")) return rc;
+static int make_po(const clslam_conv_desc* d, const clslam_planes* out, int up, int halo, PlaneView& po, const char* what) {
+  po = PlaneView{};
+  if (!out) return 0;
+  if (!out->base || (up != 1 && up != 2) || out->h != d->ho * up || out->w != d->wo * up || out->c != d->co || out->n != d->n ||
+      out->c_total % 8 || out->c_off % 4 || out->c_off + out->c > out->c_total) {
+    set_error("%s: plane output does not match the layer (%d x %d x %d, up %d)", what, d->ho, d->wo, d->co, up);
+    return -1;
+  }
+  po = make_plane_view(out, up, halo);
+  return 0;
+}
+
+static int conv_fwd_generic(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const float* scale,
+                            const float* shift, const float* residual, float* y, const PlaneView& po, void* workspace,
+                            long long workspace_bytes, void* stream) {
+  const int M = d->n * d->ho * d->wo, N = d->co, K = d->kh * d->kw * d->ci;
+  AFwd a{make_conv_in(*d, x, x2), M, K};
+  BWeightK b{w, N, K};
+  EpiFwd e{y, scale, shift, residual, N, d->act, po, d->ho, d->wo};
+  return run_gemm(a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_fwd");
+}
+
+int clslam_conv_fwd_emit(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
+                         const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,
+                         const clslam_planes* out, int out_up, int out_halo, void* workspace, long long workspace_bytes,
+                         void* stream) {
+  if (int rc = check_desc(d, "conv_fwd")) return rc;
+  PlaneView po;
+  if (int rc = make_po(d, out, out_up, out_halo, po, "conv_fwd")) return rc;
+  if (!y && !po.base) { set_error("conv_fwd: no output"); return -1; }
   if (g_conv_mode != 1 || !w_hi || !w_lo || !p3_eligible(d))
-    return clslam_conv_fwd(d, x, x2, w, scale, shift, residual, y, workspace, workspace_bytes, stream);
+    return conv_fwd_generic(d, x, x2, w, scale, shift, residual, y, po, workspace, workspace_bytes, stream);
   const int M = d->n * d->ho * d->wo, N = d->co;
   const P3Plan p = plan_p3(d);
   if (p.splits > 1 && (workspace == nullptr || workspace_bytes < (long long)p.splits * M * N * 4)) {
     set_error("conv_fwd_bf16w: workspace too small"); return -2;
   }
-  EpiFwd e{y, scale, shift, residual, N, d->act};
+  EpiFwd e{y, scale, shift, residual, N, d->act, po, d->ho, d->wo};
   const ConvIn c = make_conv_in(*d, x, x2);
   cudaStream_t st = as_stream(stream);
   int rc;
@@ -654,15 +691,17 @@ int clslam_conv_fwd_bf16w(const clslam_conv_desc* d, const float* x, const float
   return rc;
 }
 
+int clslam_conv_fwd_bf16w(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
+                          const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,
+                          void* workspace, long long workspace_bytes, void* stream) {
+  return clslam_conv_fwd_emit(d, x, x2, w, w_hi, w_lo, scale, shift, residual, y, nullptr, 1, 0, workspace, workspace_bytes, stream);
+}
+
 int clslam_conv_fwd(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const float* scale,
                     const float* shift, const float* residual, float* y, void* workspace, long long workspace_bytes,
                     void* stream) {
   if (int rc = check_desc(d, "conv_fwd")) return rc;
-  const int M = d->n * d->ho * d->wo, N = d->co, K = d->kh * d->kw * d->ci;
-  AFwd a{make_conv_in(*d, x, x2), M, K};
-  BWeightK b{w, N, K};
-  EpiFwd e{y, scale, shift, residual, N, d->act};
-  return run_gemm(a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_fwd");
+  return conv_fwd_generic(d, x, x2, w, scale, shift, residual, y, PlaneView{}, workspace, workspace_bytes, stream);
 }
 
 static void dgrad_dims(const clslam_conv_desc* d, int& M, int& N, int& K, DgradIn& g, const float* dz) {

@@ -1,0 +1,461 @@
+// TMA-fed, persistent, warp-specialised tcgen05 kernel for 3x3 / stride-1 convolutions over bf16
+// hi/lo activation planes (include/clslam_b200.h: clslam_conv3x3_tma).
+//
+//   warp 0    : TMA producer   (one elected lane issues cp.async.bulk.tensor loads)
+//   warp 1    : MMA issuer     (one elected lane issues tcgen05.mma / tcgen05.commit)
+//   warps 2-17: epilogue       (tcgen05.ld -> scale/shift/residual/activation -> fp32 and/or planes)
+//
+// M tile = 16 output rows x 8 output columns of one image (TMEM lane l <-> pixel (l / 8, l % 8)): an
+// 8-pixel row segment is one 8-row core-matrix group of the K-major swizzled UMMA layout, so the input
+// patch loaded for column shift s (box: KC channels x 8 px x 18 rows, both planes in one TMA
+// instruction) serves the three taps (r, s), r = 0..2, by moving the descriptor start by r groups.
+// Per (channel chunk, s) one A stage; per (chunk, s, r) one B stage (weights [BN][KC], hi + lo).
+// Per k16 step three MMAs: A_lo.B_hi + A_hi.B_lo + A_hi.B_hi (fp32 accumulate in TMEM, two accumulator
+// stages so the epilogue of tile i overlaps the main loop of tile i + 1).
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include "planes.cuh"
+
+namespace clslam {
+
+constexpr int kTmaTH = 16, kTmaTW = 8;     // output tile
+constexpr int kTmaPH = kTmaTH + 2;         // rows of an A patch
+constexpr int kTmaEpiWarps = 16;          // 4 TMEM lane quarters x 4 column slots (8 accumulator columns per tcgen05.ld)
+constexpr int kTmaThreads = 64 + 32 * kTmaEpiWarps;
+
+// ELU on the epilogue's hot path: exp through ex2.approx, Taylor series next to 0 where exp(x) - 1 cancels
+// (relative error < 3e-6 of the result; the reference's expm1f costs ~3x the instructions)
+__device__ __forceinline__ float elu_fast(float v) {
+  const float e = __expf(v) - 1.f;
+  const float t = v * (1.f + v * (0.5f + v * (0.16666667f + v * (0.041666668f + v * 0.0083333338f))));
+  const float neg = v > -0.0625f ? t : e;
+  return v > 0.f ? v : neg;
+}
+__device__ __forceinline__ float act_fast(float v, int act) {
+  if (act == CLSLAM_ACT_ELU) return elu_fast(v);
+  return act_apply(v, act);
+}
+
+template <int KC, int BN>
+struct TmaConvCfg {
+  static constexpr int kRowBytes = KC * 2;
+  static constexpr int kAPlane = kTmaPH * kTmaTW * kRowBytes;
+  static constexpr int kAStage = 2 * kAPlane;
+  static constexpr int kBPlane = BN * kRowBytes;
+  static constexpr int kBStage = 2 * kBPlane;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  // upper 32 bits of every K-major swizzled descriptor of this configuration (SBO = 8 rows, version 1, layout type)
+  static constexpr uint32_t kDescHi = (uint32_t)((8 * kRowBytes) >> 4) | (1u << 14) |
+                                      ((kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u)) << 29);
+  static_assert(kAStage % 1024 == 0 && kBStage % 1024 == 0, "stage alignment");
+};
+constexpr int kTmaMaxStages = 8;
+constexpr int kTmaBarBytes = 512;          // 4 x 8 ring barriers + 2 x 2 accumulator barriers + resident-B barrier + TMEM slot
+constexpr int kTmaSmemMax = 232448;
+constexpr int kTmaResidentMax = 112 * 1024;
+
+struct TmaConvArgs {
+  int n_img, ho, wo, cout, cin;
+  int tiles_x, tiles_y, n_blocks, chunks;
+  int org;                       // input coordinate of tap (0, 0) relative to the output pixel, in tensor-map coordinates
+  int na, nbr;                   // A ring depth; B ring depth, or 0: the whole weight tensor stays resident in shared memory
+  int act;
+  const float* scale;
+  const float* shift;
+  PlaneView res;                 // base == nullptr: none
+  float* y;
+  PlaneView out;                 // base == nullptr: none
+};
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
+
+template <int KC, int BN>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TmaConvArgs g) {
+  using C = TmaConvCfg<KC, BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* a_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* b_tiles = a_tiles + g.na * C::kAStage;
+  const int b_slots = g.nbr > 0 ? g.nbr : g.chunks * 9;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(b_tiles + (size_t)b_slots * C::kBStage);
+  uint64_t* a_empty = a_full + kTmaMaxStages;
+  uint64_t* b_full = a_empty + kTmaMaxStages;
+  uint64_t* b_empty = b_full + kTmaMaxStages;
+  uint64_t* t_full = b_empty + kTmaMaxStages;
+  uint64_t* t_empty = t_full + 2;
+  uint64_t* b_res = t_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kTmaMaxStages; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kTmaEpiWarps); }
+    mbar_init(b_res, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 2) tmem_alloc(tmem_slot, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = g.tiles_x * g.tiles_y;
+  const int total = g.n_img * tiles_per_img * g.n_blocks;
+  const int n_cs = g.chunks * 3;
+
+  if (warp == 0) {
+    // ===================== TMA producer (one thread) =====================
+    if (lane == 0) {
+      if (g.nbr == 0) {       // resident weights: every (chunk, s, r) tile once, slot = (chunk * 3 + s) * 3 + r
+        mbar_arrive_expect_tx(b_res, (uint32_t)(b_slots * C::kBStage));
+        for (int slot = 0; slot < b_slots; ++slot) {
+          const int r = slot % 3, cs = slot / 3, sft = cs % 3, chunk = cs / 3;
+          tma_load_3d(b_tiles + (size_t)slot * C::kBStage, &map_b, b_res, (r * 3 + sft) * g.cin + chunk * KC, 0, 0);
+        }
+      }
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int nb = t % g.n_blocks, mt = t / g.n_blocks;
+        const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+        const int oh0 = (rem / g.tiles_x) * kTmaTH + g.org, ow0 = (rem % g.tiles_x) * kTmaTW + g.org;
+        const int n0 = nb * BN;
+        for (int chunk = 0; chunk < g.chunks; ++chunk) {
+          for (int sft = 0; sft < 3; ++sft) {
+            mbar_wait(&a_empty[sa], (uint32_t)(pa ^ 1));
+            mbar_arrive_expect_tx(&a_full[sa], C::kAStage);
+            tma_load_5d(a_tiles + sa * C::kAStage, &map_a, &a_full[sa], chunk * KC, ow0 + sft, oh0, img, 0);
+            if (++sa == g.na) { sa = 0; pa ^= 1; }
+            if (g.nbr > 0) {
+              for (int r = 0; r < 3; ++r) {
+                mbar_wait(&b_empty[sb], (uint32_t)(pb ^ 1));
+                mbar_arrive_expect_tx(&b_full[sb], C::kBStage);
+                tma_load_3d(b_tiles + sb * C::kBStage, &map_b, &b_full[sb], (r * 3 + sft) * g.cin + chunk * KC, n0, 0);
+                if (++sb == g.nbr) { sb = 0; pb ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN);
+      constexpr uint32_t kLbo = 1u << 16;
+      const uint32_t a_ring = ((smem_u32(a_tiles) >> 4) & 0x3FFF) | kLbo;       // low descriptor words: start address >> 4
+      const uint32_t b_ring = ((smem_u32(b_tiles) >> 4) & 0x3FFF) | kLbo;
+      const bool resident = g.nbr == 0;
+      if (resident) { mbar_wait(b_res, 0); tc_fence_after(); }
+      int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(&t_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));      // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        uint32_t accumulate = 0;
+        for (int cs = 0; cs < n_cs; ++cs) {
+          mbar_wait(&a_full[sa], (uint32_t)pa);
+          tc_fence_after();
+          const uint32_t a_st = a_ring + (uint32_t)(sa * (C::kAStage >> 4));
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            uint32_t b_st;
+            if (resident) {
+              b_st = b_ring + (uint32_t)((cs * 3 + r) * (C::kBStage >> 4));
+            } else {
+              mbar_wait(&b_full[sb], (uint32_t)pb);
+              tc_fence_after();
+              b_st = b_ring + (uint32_t)(sb * (C::kBStage >> 4));
+            }
+            const uint32_t a_hi = a_st + (uint32_t)((r * kTmaTW * C::kRowBytes) >> 4);
+#pragma unroll
+            for (int j = 0; j < KC / 16; ++j) {
+              const uint32_t o = (uint32_t)(j * 2);                    // 16 bf16 = 32 bytes along k inside the swizzled row
+              const uint64_t dah = make_desc(C::kDescHi, a_hi + o), dal = make_desc(C::kDescHi, a_hi + o + (C::kAPlane >> 4));
+              const uint64_t dbh = make_desc(C::kDescHi, b_st + o), dbl = make_desc(C::kDescHi, b_st + o + (C::kBPlane >> 4));
+              umma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+              umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+              umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+              accumulate = 1u;
+            }
+            if (!resident) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == g.nbr) { sb = 0; pb ^= 1; }
+            }
+          }
+          umma_commit(&a_empty[sa]);
+          if (++sa == g.na) { sa = 0; pa ^= 1; }
+        }
+        umma_commit(&t_full[as]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                      // TMEM lane quarter this warp may access
+    const int slot = (warp - 2) >> 2;            // column slot: groups slot, slot + 4, ... of 8 accumulator columns
+    const int l = q * 32 + lane;
+    int it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      const int nb = t % g.n_blocks, mt = t / g.n_blocks;
+      const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
+      const int oh = (rem / g.tiles_x) * kTmaTH + (l >> 3), ow = (rem % g.tiles_x) * kTmaTW + (l & 7);
+      const bool ok = oh < g.ho && ow < g.wo;
+      // output addressing of this pixel, once per tile
+      const size_t y_off = (((size_t)img * g.ho + oh) * g.wo + ow) * g.cout;
+      int rows[3] = {-1, -1, -1}, cols[3] = {-1, -1, -1};
+      if (g.out.base && ok) {
+        plane_coords(oh, g.out.h_lo, g.out.up, g.out.halo, rows);
+        plane_coords(ow, g.out.w_lo, g.out.up, g.out.halo, cols);
+      }
+      const size_t res_off = g.res.base ? (((size_t)img * g.res.hp + oh + 1) * g.res.wp + ow + 1) * g.res.c_total : 0;
+      mbar_wait(&t_full[as], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = slot * 8; c < BN; c += 32) {
+        uint32_t r[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+        const int n = nb * BN + c;
+        if (!ok || n >= g.cout) continue;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+        if (g.scale) {
+          const float4 s0 = ld4(g.scale + n), s1 = ld4(g.scale + n + 4);
+          v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+        }
+        if (g.shift) {
+          const float4 s0 = ld4(g.shift + n), s1 = ld4(g.shift + n + 4);
+          v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+        }
+        if (g.res.base) {
+          const __nv_bfloat16* rp = g.res.base + res_off + n;
+          const uint4 h = *reinterpret_cast<const uint4*>(rp);
+          const uint4 lo4 = *reinterpret_cast<const uint4*>(rp + g.res.plane);
+          const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = join_bf16x2(hh[j], ll[j]);
+            v[2 * j] += f.x; v[2 * j + 1] += f.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = act_fast(v[j], g.act);
+        if (g.y) {
+          float* p = g.y + y_off + n;
+          *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        if (g.out.base) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+          const uint4 hv = make_uint4(hi[0], hi[1], hi[2], hi[3]), lv = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+              if (rows[a] >= 0 && cols[b] >= 0) {
+                __nv_bfloat16* p = g.out.base + (((size_t)img * g.out.hp + rows[a]) * g.out.wp + cols[b]) * g.out.c_total + n;
+                *reinterpret_cast<uint4*>(p) = hv;
+                *reinterpret_cast<uint4*>(p + g.out.plane) = lv;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[as]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ---- fp32 NHWC -> planes -------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+planes_from_f32_kernel(const float* __restrict__ x, PlaneView out, int n, int h, int w, int c) {
+  const int c4 = c / 4;
+  const size_t total = (size_t)n * h * w * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c4) * 4;
+    size_t p = i / c4;
+    const int ow = (int)(p % w); p /= w;
+    const int oh = (int)(p % h);
+    const int img = (int)(p / h);
+    const float4 v4 = ld4(x + i * 4);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    planes_emit<4>(out, img, oh, ow, cc, v);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+
+static int get_encoder() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    set_error("cuTensorMapEncodeTiled is not available (%s)", cudaGetErrorString(e));
+    return -3;
+  }
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  return 0;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+static int encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+                  int row_bytes, const char* what) {
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  const CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, ones,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed: %d", what, (int)r); return -4; }
+  return 0;
+}
+
+static int g_tma_sms = 0;
+static int tma_num_sms() {
+  if (g_tma_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_tma_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_tma_sms <= 0)
+      g_tma_sms = 148;
+  }
+  return g_tma_sms;
+}
+
+template <int KC, int BN>
+static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConvArgs g, cudaStream_t st) {
+  using C = TmaConvCfg<KC, BN>;
+  auto kern = conv3x3_tma_kernel<KC, BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemMax);
+    if (e != cudaSuccess) { set_error("conv3x3_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -3; }
+    attr_set = true;
+  }
+  // shared-memory plan: weights resident when the whole tensor fits next to >= 3 A stages, else a B ring
+  const int budget = kTmaSmemMax - 1024 - kTmaBarBytes;
+  const long long w_bytes = (long long)g.chunks * 9 * C::kBStage;
+  long long b_bytes;
+  if (g.n_blocks == 1 && w_bytes <= kTmaResidentMax && budget - w_bytes >= 3LL * C::kAStage) {
+    g.nbr = 0; b_bytes = w_bytes;
+  } else {
+    g.nbr = (KC == 64 && BN == 128) ? 3 : 6; b_bytes = (long long)g.nbr * C::kBStage;
+  }
+  long long na = (budget - b_bytes) / C::kAStage;
+  g.na = (int)(na > kTmaMaxStages ? kTmaMaxStages : na);
+  if (g.na < 2) { set_error("conv3x3_tma: shared memory plan failed"); return -3; }
+  const int smem = (int)(g.na * C::kAStage + b_bytes + 1024 + kTmaBarBytes);
+  const long long total = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks;
+  const int grid = (int)(total < tma_num_sms() ? total : tma_num_sms());
+  kern<<<grid, kTmaThreads, smem, st>>>(ma, mb, g);
+  return finish_launch("conv3x3_tma");
+}
+
+static int check_planes(const clslam_planes* p, const char* what) {
+  if (!p || !p->base) { set_error("%s: null planes", what); return -1; }
+  if (p->c_total % 8 || p->c_off % 8 || p->c % 8 || p->c_off + p->c > p->c_total || p->n < 1 || p->h < 2 || p->w < 2 ||
+      (reinterpret_cast<uintptr_t>(p->base) & 15) || (p->plane_stride % 8)) {
+    set_error("%s: bad planes (c_total=%d c_off=%d c=%d n=%d h=%d w=%d)", what, p->c_total, p->c_off, p->c, p->n, p->h, p->w);
+    return -1;
+  }
+  return 0;
+}
+
+}  // namespace clslam
+
+using namespace clslam;
+
+extern "C" {
+
+int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
+  if (!p) { set_error("conv3x3_tma: null"); return -1; }
+  if (int rc = check_planes(&p->in, "conv3x3_tma.in")) return rc;
+  const clslam_planes& in = p->in;
+  const int cin = in.c, cout = p->cout;
+  if (cin % 16 || cout % 16 || !p->w_hi || !p->w_lo) { set_error("conv3x3_tma: cin %% 16, cout %% 16, weights"); return -1; }
+  if (p->pad_mode < 0 || p->pad_mode > 2) { set_error("conv3x3_tma: pad_mode"); return -1; }
+  if (int rc = get_encoder()) return rc;
+  const int kc = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16);
+  const int bn = cout >= 128 ? 128 : (cout >= 64 ? 64 : (cout >= 32 ? 32 : 16));
+  if (cout % bn) { set_error("conv3x3_tma: cout %d is not a multiple of the N block %d", cout, bn); return -1; }
+  const int full = p->pad_mode == CLSLAM_PAD_FULL;
+  const int ho = in.h + (full ? 2 : 0), wo = in.w + (full ? 2 : 0);
+
+  TmaConvArgs g{};
+  g.n_img = in.n; g.ho = ho; g.wo = wo; g.cout = cout; g.cin = cin;
+  g.tiles_x = (wo + kTmaTW - 1) / kTmaTW; g.tiles_y = (ho + kTmaTH - 1) / kTmaTH;
+  g.n_blocks = cout / bn; g.chunks = cin / kc;
+  g.act = p->act; g.scale = p->scale; g.shift = p->shift; g.y = p->y;
+  if (p->residual) {
+    if (int rc = check_planes(p->residual, "conv3x3_tma.residual")) return rc;
+    if (p->residual->h != ho || p->residual->w != wo || p->residual->c != cout || p->residual->n != in.n) { set_error("conv3x3_tma: residual dims"); return -1; }
+    g.res = make_plane_view(p->residual, 1, 0);
+  }
+  if (p->out) {
+    if (int rc = check_planes(p->out, "conv3x3_tma.out")) return rc;
+    const int up = p->out_up;
+    if ((up != 1 && up != 2) || p->out->h != ho * up || p->out->w != wo * up || p->out->c != cout || p->out->n != in.n) {
+      set_error("conv3x3_tma: out dims (%d x %d x %d, up %d) vs (%d x %d x %d)", p->out->h, p->out->w, p->out->c, up, ho, wo, cout);
+      return -1;
+    }
+    g.out = make_plane_view(p->out, up, p->out_halo);
+  }
+
+  // A: 5-D map (channel, x, y, image, plane) over the padded view (reflect: the stored halo is the padding) or the
+  // interior view (zero / full: TMA zero-fills outside)
+  const int hp = in.h + 2, wp = in.w + 2;
+  const bool padded_view = p->pad_mode == CLSLAM_PAD_REFLECT;
+  __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(in.base) + in.c_off + (padded_view ? 0 : ((size_t)wp + 1) * in.c_total);
+  g.org = padded_view ? 0 : (full ? -2 : -1);
+  const cuuint64_t adims[5] = {(cuuint64_t)cin, (cuuint64_t)(padded_view ? wp : in.w), (cuuint64_t)(padded_view ? hp : in.h),
+                               (cuuint64_t)in.n, 2};
+  const cuuint64_t astr[4] = {(cuuint64_t)in.c_total * 2, (cuuint64_t)wp * in.c_total * 2, (cuuint64_t)hp * wp * in.c_total * 2,
+                              (cuuint64_t)in.plane_stride * 2};
+  const cuuint32_t abox[5] = {(cuuint32_t)kc, kTmaTW, kTmaPH, 1, 2};
+  CUtensorMap ma, mb;
+  if (int rc = encode(&ma, abase, 5, adims, astr, abox, kc * 2, "A")) return rc;
+  // B: 3-D map (k, cout, plane); the lo plane must follow the hi plane in memory (one [2][...] allocation)
+  const long long wdiff = reinterpret_cast<const char*>(p->w_lo) - reinterpret_cast<const char*>(p->w_hi);
+  if (wdiff <= 0 || (wdiff & 15)) { set_error("conv3x3_tma: w_lo must follow w_hi (16-byte aligned distance)"); return -1; }
+  const cuuint64_t bdims[3] = {(cuuint64_t)9 * cin, (cuuint64_t)cout, 2};
+  const cuuint64_t bstr[2] = {(cuuint64_t)9 * cin * 2, (cuuint64_t)wdiff};
+  const cuuint32_t bbox[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 2};
+  if (int rc = encode(&mb, const_cast<void*>(p->w_hi), 3, bdims, bstr, bbox, kc * 2, "B")) return rc;
+
+  cudaStream_t st = as_stream(stream);
+#define CLSLAM_TMA_CASE(KC_, BN_) if (kc == KC_ && bn == BN_) return launch_tma_conv<KC_, BN_>(ma, mb, g, st);
+  CLSLAM_TMA_CASE(64, 128) CLSLAM_TMA_CASE(64, 64) CLSLAM_TMA_CASE(64, 32) CLSLAM_TMA_CASE(64, 16)
+  CLSLAM_TMA_CASE(32, 128) CLSLAM_TMA_CASE(32, 64) CLSLAM_TMA_CASE(32, 32) CLSLAM_TMA_CASE(32, 16)
+  CLSLAM_TMA_CASE(16, 64) CLSLAM_TMA_CASE(16, 32) CLSLAM_TMA_CASE(16, 16)
+#undef CLSLAM_TMA_CASE
+  set_error("conv3x3_tma: no kernel for channel chunk %d / N block %d", kc, bn);
+  return -1;
+}
+
+int clslam_planes_from_f32(const float* x, const clslam_planes* out, int out_up, int out_halo, void* stream) {
+  if (int rc = check_planes(out, "planes_from_f32")) return rc;
+  if (out_up != 1 && out_up != 2) { set_error("planes_from_f32: up"); return -1; }
+  const PlaneView v = make_plane_view(out, out_up, out_halo);
+  const size_t total = (size_t)out->n * v.h_lo * v.w_lo * (out->c / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  planes_from_f32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, v, out->n, v.h_lo, v.w_lo, out->c);
+  return finish_launch("planes_from_f32");
+}
+
+}  // extern "C"

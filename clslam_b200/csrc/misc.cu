@@ -1,6 +1,7 @@
 // Memory-bound helpers of the conv stack: image staging, max-pool, the one-channel dispconv
 // (forward / wgrad / dgrad) and the flat Adam update.
 #include "conv_ops.cuh"
+#include "planes.cuh"
 
 namespace clslam {
 
@@ -30,7 +31,7 @@ stage_images_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 
 // ---- 3x3 / s2 / p1 max pool, NHWC ----------------------------------------------------------
 __global__ void __launch_bounds__(256)
-maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int hi, int wi, int c, int ho, int wo) {
+maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int hi, int wi, int c, int ho, int wo, PlaneView po) {
   const int c4 = c / 4;
   const size_t total = (size_t)n * ho * wo * c4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -50,7 +51,11 @@ maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int hi
         m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
       }
     }
-    *reinterpret_cast<float4*>(y + i * 4) = m;
+    if (y) *reinterpret_cast<float4*>(y + i * 4) = m;
+    if (po.base) {
+      const float v[4] = {m.x, m.y, m.z, m.w};
+      planes_emit<4>(po, b, oh, ow, cc, v);
+    }
   }
 }
 
@@ -238,11 +243,24 @@ int clslam_stage_images(const float* img_a, const float* img_b, float* out_nhwc,
   return finish_launch("stage_images");
 }
 
-int clslam_maxpool3x3s2(const float* x, float* y, int n, int hi, int wi, int c, void* stream) {
+int clslam_maxpool3x3s2_emit(const float* x, float* y, int n, int hi, int wi, int c, const clslam_planes* out, int out_halo,
+                             void* stream) {
   if (c % 4) { set_error("maxpool: c %% 4 != 0"); return -1; }
   const int ho = (hi + 2 - 3) / 2 + 1, wo = (wi + 2 - 3) / 2 + 1;
-  maxpool_kernel<<<grid_for((size_t)n * ho * wo * (c / 4)), 256, 0, as_stream(stream)>>>(x, y, n, hi, wi, c, ho, wo);
+  PlaneView po{};
+  if (out) {
+    if (!out->base || out->n != n || out->h != ho || out->w != wo || out->c != c || out->c_total % 8 || out->c_off % 4) {
+      set_error("maxpool: plane output does not match (%d x %d x %d)", ho, wo, c); return -1;
+    }
+    po = make_plane_view(out, 1, out_halo);
+  }
+  if (!y && !po.base) { set_error("maxpool: no output"); return -1; }
+  maxpool_kernel<<<grid_for((size_t)n * ho * wo * (c / 4)), 256, 0, as_stream(stream)>>>(x, y, n, hi, wi, c, ho, wo, po);
   return finish_launch("maxpool");
+}
+
+int clslam_maxpool3x3s2(const float* x, float* y, int n, int hi, int wi, int c, void* stream) {
+  return clslam_maxpool3x3s2_emit(x, y, n, hi, wi, c, nullptr, 0, stream);
 }
 
 int clslam_dispconv_fwd(const float* x, const float* w, const float* bias, float* y, int n, int h, int w_, int ci,

@@ -94,6 +94,58 @@ int clslam_conv_fwd_bf16w(const clslam_conv_desc* d, const float* x, const float
                           const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,
                           void* workspace, long long workspace_bytes, void* stream);
 
+/* ---- bf16 hi/lo activation planes + TMA-fed tcgen05 3x3 convolution -------------------------
+ * A "planes" tensor stores an activation x as two bf16 tensors hi = bf16(x), lo = bf16(x - hi)
+ * (x = hi + lo up to ~2^-17): exactly the operands of the 3xBF16 tensor-core products, written
+ * once by the producing kernel's epilogue, so that consumers feed them to tcgen05.mma with
+ * plain TMA loads (no CUDA-core staging).  Layout: [2 planes][n][h + 2][w + 2][c_total] (channels
+ * fastest) with a one-pixel halo ring: reflection-padded consumers (networks/layers.py:36,
+ * nn.ReflectionPad2d(1)) read the stored halo, zero-padded consumers (torchvision BasicBlock,
+ * pose decoder) address the interior and let TMA zero-fill outside.  A channel slice
+ * [c_off, c_off + c) of a wider buffer realises torch.cat (networks/depth_decoder.py:66)
+ * without a copy; writing with up = 2 realises F.interpolate(nearest) (:61-64). */
+typedef struct clslam_planes {
+  void* base;              /* bf16 element (hi plane, image 0, padded row 0, padded col 0, channel 0) */
+  long long plane_stride;  /* elements between the hi and the lo plane */
+  int n, h, w;             /* images, logical height and width (stored (h + 2) x (w + 2)) */
+  int c_total;             /* channels per stored pixel */
+  int c_off, c;            /* channel slice this operand refers to */
+} clslam_planes;
+
+enum { CLSLAM_PAD_FULL = 2 };  /* dgrad: "full" correlation, output grid (h + 2) x (w + 2), zero outside */
+
+/* y = act(scale * conv3x3_s1(in) + shift (+ residual)), implicit GEMM on tcgen05 (M = 16 x 8 output
+ * pixels, N = cout block, K = 9 * cin in (tap, channel chunk) steps), operands by TMA, fp32
+ * accumulators double-buffered in TMEM, persistent CTAs.  Outputs (each optional): fp32 NHWC `y`
+ * (n, ho, wo, cout) and/or planes `out` (logical dims (ho * out_up, wo * out_up); out_halo = 1 also
+ * writes the reflection halo).  Needs in.c % 16 == 0 and cout % 16 == 0. */
+typedef struct clslam_conv_tma {
+  clslam_planes in;
+  int pad_mode;            /* CLSLAM_PAD_ZERO | CLSLAM_PAD_REFLECT | CLSLAM_PAD_FULL */
+  int cout;
+  const void* w_hi;        /* bf16 [cout][3][3][in.c] */
+  const void* w_lo;
+  const float* scale;      /* [cout] or NULL */
+  const float* shift;      /* [cout] or NULL */
+  int act;                 /* CLSLAM_ACT_* */
+  const clslam_planes* residual;  /* optional, logical dims of the output */
+  float* y;                /* optional */
+  const clslam_planes* out;       /* optional */
+  int out_up;              /* 1 or 2 (nearest up-sampling on write) */
+  int out_halo;            /* write the reflection halo of `out` */
+} clslam_conv_tma;
+int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
+
+/* clslam_conv_fwd_bf16w / clslam_maxpool3x3s2 that additionally emit their result as planes */
+int clslam_conv_fwd_emit(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
+                         const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,
+                         const clslam_planes* out, int out_up, int out_halo,
+                         void* workspace, long long workspace_bytes, void* stream);
+int clslam_maxpool3x3s2_emit(const float* x, float* y, int n, int hi, int wi, int c, const clslam_planes* out,
+                             int out_halo, void* stream);
+/* fp32 NHWC (n, h, w, c) -> planes (test / staging helper) */
+int clslam_planes_from_f32(const float* x, const clslam_planes* out, int out_up, int out_halo, void* stream);
+
 /* 3x3/stride-2/pad-1 max pooling, NHWC (networks/resnet_encoder.py:121). */
 int clslam_maxpool3x3s2(const float* x, float* y, int n, int hi, int wi, int c, void* stream);
 

@@ -113,8 +113,8 @@ def rel_err(got, ref):
 def split_bf16(t):
     """fp32 cuda tensor -> (hi, lo) bf16 planes via the library's split kernel"""
     flat = t.contiguous().view(-1)
-    hi = torch.empty(flat.numel(), dtype=torch.bfloat16, device='cuda')
-    lo = torch.empty(flat.numel(), dtype=torch.bfloat16, device='cuda')
+    both = torch.empty(2, (flat.numel() + 63) // 64 * 64, dtype=torch.bfloat16, device='cuda')   # lo follows hi (one TMA map)
+    hi, lo = both[0, :flat.numel()], both[1, :flat.numel()]
     L.check(lib().clslam_split_bf16(flat.data_ptr(), hi.data_ptr(), lo.data_ptr(), flat.numel(), stream()), 'split_bf16')
     return hi, lo
 

@@ -1,0 +1,185 @@
+"""Parity of the TMA-fed tcgen05 3x3 convolution over bf16 hi/lo planes (clslam_conv3x3_tma) and of the
+plane-emitting epilogues against fp64 torch references."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from clslam_b200 import _lib as L
+from tests import cabi
+
+pytestmark = pytest.mark.gpu
+TOL = 6e-5        # 3 x BF16 split operands (~2^-16 per operand), fp32 accumulation
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.rand(*shape, generator=g, dtype=torch.float64) * 2 - 1) * scale
+
+
+class PlaneBuf:
+    """[2][n][h+2][w+2][c_total] bf16 on the GPU + its clslam_planes descriptor(s)"""
+
+    def __init__(self, n, h, w, c_total, fill=None):
+        self.n, self.h, self.w, self.c_total = n, h, w, c_total
+        self.t = torch.zeros(2, n, h + 2, w + 2, c_total, dtype=torch.bfloat16, device='cuda')
+        if fill is not None:
+            self.t.fill_(fill)
+
+    def desc(self, c_off=0, c=None):
+        c = self.c_total - c_off if c is None else c
+        return L.Planes(self.t.data_ptr(), self.t[0].numel(), self.n, self.h, self.w, self.c_total, c_off, c)
+
+    def set_padded(self, xp_nchw, c_off=0):
+        """store an already padded (n, c, h+2, w+2) fp64/fp32 tensor as hi/lo planes"""
+        x = xp_nchw.float().permute(0, 2, 3, 1).contiguous().cuda()
+        hi = x.to(torch.bfloat16)
+        lo = (x - hi.float()).to(torch.bfloat16)
+        c = x.shape[-1]
+        self.t[0, ..., c_off:c_off + c] = hi
+        self.t[1, ..., c_off:c_off + c] = lo
+
+    def value(self, c_off=0, c=None):
+        """(n, c, h+2, w+2) fp64 value hi + lo of the padded buffer"""
+        c = self.c_total - c_off if c is None else c
+        v = self.t[0, ..., c_off:c_off + c].double() + self.t[1, ..., c_off:c_off + c].double()
+        return v.permute(0, 3, 1, 2).cpu()
+
+
+def run_tma(inp, pad_mode, w, scale=None, shift=None, act=L.ACT_NONE, res=None, want_y=True, out=None, out_up=1, out_halo=0):
+    co = w.shape[0]
+    hi, lo = cabi.split_bf16(cabi.krsc(w).float().cuda())
+    full = pad_mode == L.PAD_FULL
+    ho, wo = inp.h + (2 if full else 0), inp.w + (2 if full else 0)
+    y = torch.full((inp.n, ho, wo, co), float('nan'), device='cuda') if want_y else None
+    a = L.ConvTma()
+    a.inp = inp
+    a.pad_mode, a.cout = pad_mode, co
+    a.w_hi, a.w_lo = hi.data_ptr(), lo.data_ptr()
+    keep = [hi, lo]
+    if scale is not None:
+        sc = scale.float().cuda(); keep.append(sc); a.scale = sc.data_ptr()
+    if shift is not None:
+        sh = shift.float().cuda(); keep.append(sh); a.shift = sh.data_ptr()
+    a.act = act
+    if res is not None:
+        a.residual = ctypes.pointer(res)
+    if y is not None:
+        a.y = y.data_ptr()
+    if out is not None:
+        a.out = ctypes.pointer(out)
+    a.out_up, a.out_halo = out_up, out_halo
+    L.check(cabi.lib().clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma')
+    torch.cuda.synchronize()
+    return y
+
+
+TMA_CASES = [
+    # n, h, w, ci, co, pad_mode, act, use_scale, use_res
+    (1, 16, 8, 64, 64, L.PAD_ZERO, L.ACT_NONE, False, False),          # one tile, one chunk
+    (2, 24, 40, 64, 64, L.PAD_ZERO, L.ACT_RELU, True, True),           # BasicBlock conv2 + residual, ragged tiles
+    (1, 12, 20, 128, 128, L.PAD_ZERO, L.ACT_RELU, True, False),        # BN = 128, two chunks
+    (1, 6, 20, 512, 256, L.PAD_REFLECT, L.ACT_ELU, False, False),      # upconv_4_0: 8 chunks, 2 N blocks
+    (2, 12, 24, 256, 128, L.PAD_REFLECT, L.ACT_ELU, False, False),     # upconv_3_x
+    (1, 48, 64, 64, 32, L.PAD_REFLECT, L.ACT_ELU, False, False),       # upconv_1_0 (BN = 32)
+    (1, 48, 64, 96, 32, L.PAD_REFLECT, L.ACT_ELU, False, False),       # upconv_1_1 (KC = 32, 3 chunks)
+    (1, 48, 64, 32, 16, L.PAD_REFLECT, L.ACT_ELU, False, False),       # upconv_0_0 (KC = 32, BN = 16)
+    (2, 33, 47, 16, 16, L.PAD_REFLECT, L.ACT_SIGMOID, False, False),   # upconv_0_1-like (KC = 16), ragged
+    (3, 40, 200, 64, 64, L.PAD_ZERO, L.ACT_RELU, True, False),         # > 148 tiles: persistent loop, both TMEM stages
+    (1, 20, 28, 32, 64, L.PAD_FULL, L.ACT_NONE, False, False),         # dgrad-style full correlation
+]
+
+
+@pytest.mark.parametrize('case', TMA_CASES)
+def test_conv3x3_tma(case):
+    n, h, w, ci, co, pad_mode, act, use_scale, use_res = case
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    scale = (1 + 0.2 * rnd(co, seed=3)) if use_scale else None
+    shift = 0.1 * rnd(co, seed=4)
+    buf = PlaneBuf(n, h, w, ci, fill=7.0)        # a poisoned halo must not leak into zero-padded results
+    if pad_mode == L.PAD_REFLECT:
+        buf.set_padded(F.pad(x, (1, 1, 1, 1), mode='reflect'))
+    else:
+        xp = torch.full((n, ci, h + 2, w + 2), 7.0, dtype=torch.float64)
+        xp[:, :, 1:-1, 1:-1] = x
+        buf.set_padded(xp)
+    xq = buf.value()[:, :, 1:-1, 1:-1]           # the value the kernel actually sees (hi + lo)
+    if pad_mode == L.PAD_REFLECT:
+        ref = F.conv2d(F.pad(xq, (1, 1, 1, 1), mode='reflect'), wt)
+    elif pad_mode == L.PAD_FULL:
+        ref = F.conv2d(xq, wt, padding=2)
+    else:
+        ref = F.conv2d(xq, wt, padding=1)
+    if scale is not None:
+        ref = ref * scale.view(1, -1, 1, 1)
+    ref = ref + shift.view(1, -1, 1, 1)
+    res_desc = None
+    if use_res:
+        r = rnd(n, co, h, w, seed=5)
+        rbuf = PlaneBuf(n, h, w, co)
+        rbuf.set_padded(F.pad(r, (1, 1, 1, 1)))
+        ref = ref + rbuf.value()[:, :, 1:-1, 1:-1]
+        res_desc = rbuf.desc()
+    ref = cabi.act_ref(ref, act)
+    y = run_tma(buf.desc(), pad_mode, wt, scale, shift, act, res_desc)
+    assert cabi.rel_err(cabi.nchw(y), ref) < TOL
+
+
+@pytest.mark.parametrize('up,halo', [(1, 1), (2, 1), (1, 0)])
+def test_conv3x3_tma_plane_output(up, halo):
+    """planes written by the epilogue: channel slice of a wider buffer, reflection halo, nearest 2x up-sampling"""
+    n, h, w, ci, co = 2, 18, 26, 64, 32
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    buf = PlaneBuf(n, h, w, ci)
+    buf.set_padded(F.pad(x, (1, 1, 1, 1), mode='reflect'))
+    xq = buf.value()[:, :, 1:-1, 1:-1]
+    ref = F.elu(F.conv2d(F.pad(xq, (1, 1, 1, 1), mode='reflect'), wt))
+    out = PlaneBuf(n, h * up, w * up, co + 16, fill=3.0)
+    y = run_tma(buf.desc(), L.PAD_REFLECT, wt, act=L.ACT_ELU, out=out.desc(16, co), out_up=up, out_halo=halo)
+    assert cabi.rel_err(cabi.nchw(y), ref) < TOL
+    got = out.value(16, co)
+    exp = F.interpolate(ref, scale_factor=up, mode='nearest') if up == 2 else ref
+    if halo:
+        exp_p = F.pad(exp, (1, 1, 1, 1), mode='reflect')
+        assert cabi.rel_err(got, exp_p) < 2e-5          # + the bf16 hi/lo storage error (~2^-17)
+    else:
+        assert cabi.rel_err(got[:, :, 1:-1, 1:-1], exp) < 2e-5
+        assert float((out.t[:, :, 0].float() - 3.0).abs().max()) == 0.0   # halo untouched
+    assert float((out.t[..., :16].float() - 3.0).abs().max()) == 0.0   # other channels untouched
+
+
+def test_conv_fwd_emit_and_maxpool_emit():
+    """the gather kernels and the max pool write the same planes as clslam_planes_from_f32"""
+    lib = cabi.lib()
+    n, hi, wi, ci, co = 2, 24, 40, 64, 128
+    d = cabi.make_desc(n, hi, wi, ci, co, 3, 2, 1, L.PAD_ZERO, act=L.ACT_RELU)
+    x = rnd(n, ci, hi, wi, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    shift = 0.1 * rnd(co, seed=4)
+    xg, wg, sg = cabi.nhwc(x).float().cuda(), cabi.krsc(wt).float().cuda(), shift.float().cuda()
+    y = torch.empty(n, d.ho, d.wo, co, device='cuda')
+    out = PlaneBuf(n, d.ho, d.wo, co)
+    od = out.desc()
+    ws, wp, wb = cabi._ws(lib.clslam_conv_fwd_workspace_bytes(ctypes.byref(d)))
+    L.check(lib.clslam_conv_fwd_emit(ctypes.byref(d), xg.data_ptr(), None, wg.data_ptr(), None, None, None, sg.data_ptr(), None,
+                                     y.data_ptr(), ctypes.byref(od), 1, 1, wp, wb, cabi.stream()), 'conv_fwd_emit')
+    ref = PlaneBuf(n, d.ho, d.wo, co)
+    rd = ref.desc()
+    L.check(lib.clslam_planes_from_f32(y.data_ptr(), ctypes.byref(rd), 1, 1, cabi.stream()), 'planes_from_f32')
+    torch.cuda.synchronize()
+    assert torch.equal(out.t, ref.t)
+    exp = F.pad(cabi.nchw(y).double().cpu(), (1, 1, 1, 1), mode='reflect')
+    assert cabi.rel_err(ref.value(), exp) < 2e-5
+    # max pool
+    ho, wo = (hi + 2 - 3) // 2 + 1, (wi + 2 - 3) // 2 + 1
+    yp = torch.empty(n, ho, wo, ci, device='cuda')
+    outp = PlaneBuf(n, ho, wo, ci)
+    opd = outp.desc()
+    L.check(lib.clslam_maxpool3x3s2_emit(xg.data_ptr(), yp.data_ptr(), n, hi, wi, ci, ctypes.byref(opd), 0, cabi.stream()), 'maxpool')
+    torch.cuda.synchronize()
+    expp = F.max_pool2d(x, 3, 2, 1)
+    assert cabi.rel_err(cabi.nchw(yp), expp) < 1e-6
+    assert cabi.rel_err(outp.value()[:, :, 1:-1, 1:-1], expp) < 2e-5
