@@ -187,6 +187,10 @@ def profile_ops(eng, pred, reps=5):
         d = None
         if model is None and a and hasattr(a[0], 'kh'):
             d = a[0]
+        if model is None and a and hasattr(a[0], 'inp'):          # clslam_conv_tma: 3x3 over planes
+            t = a[0]
+            full = 2 if t.pad_mode == 2 else 0
+            row.update(bound='tensor', amount=2.0 * t.inp.n * (t.inp.h + full) * (t.inp.w + full) * t.cout * t.inp.c * 9, unit='FLOP')
         if model is not None:
             row.update(bound=model[0], amount=model[1], unit='B')
         elif d is not None:

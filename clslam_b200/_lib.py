@@ -75,6 +75,7 @@ SIGNATURES = {
     'clslam_conv_fwd_bf16w': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     'clslam_conv3x3_tma': (c_int, [POINTER(ConvTma), c_void_p]),
+    'clslam_debug_tma_flags': (c_int, [c_int]),
     'clslam_conv_fwd_emit': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, POINTER(Planes), c_int, c_int, c_void_p, c_longlong, c_void_p]),
     'clslam_maxpool3x3s2_emit': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(Planes), c_int, c_void_p]),

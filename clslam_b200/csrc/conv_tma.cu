@@ -59,6 +59,7 @@ struct TmaConvArgs {
   int n_img, ho, wo, cout, cin;
   int tiles_x, tiles_y, n_blocks, chunks;
   int org;                       // input coordinate of tap (0, 0) relative to the output pixel, in tensor-map coordinates
+  int debug;                     // timing experiments only (results are wrong when != 0): 1 no MMA, 2 no epilogue body, 4 no B ring, 8 no A loads
   int na, nbr;                   // A ring depth; B ring depth, or 0: the whole weight tensor stays resident in shared memory
   int act;
   const float* scale;
@@ -125,11 +126,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int n0 = nb * BN;
         for (int chunk = 0; chunk < g.chunks; ++chunk) {
           for (int sft = 0; sft < 3; ++sft) {
-            mbar_wait(&a_empty[sa], (uint32_t)(pa ^ 1));
-            mbar_arrive_expect_tx(&a_full[sa], C::kAStage);
-            tma_load_5d(a_tiles + sa * C::kAStage, &map_a, &a_full[sa], chunk * KC, ow0 + sft, oh0, img, 0);
-            if (++sa == g.na) { sa = 0; pa ^= 1; }
-            if (g.nbr > 0) {
+            if (!(g.debug & 8)) {
+              mbar_wait(&a_empty[sa], (uint32_t)(pa ^ 1));
+              mbar_arrive_expect_tx(&a_full[sa], C::kAStage);
+              tma_load_5d(a_tiles + sa * C::kAStage, &map_a, &a_full[sa], chunk * KC, ow0 + sft, oh0, img, 0);
+              if (++sa == g.na) { sa = 0; pa ^= 1; }
+            }
+            if (g.nbr > 0 && !(g.debug & 4)) {
               for (int r = 0; r < 3; ++r) {
                 mbar_wait(&b_empty[sb], (uint32_t)(pb ^ 1));
                 mbar_arrive_expect_tx(&b_full[sb], C::kBStage);
@@ -158,14 +161,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t accumulate = 0;
         for (int cs = 0; cs < n_cs; ++cs) {
-          mbar_wait(&a_full[sa], (uint32_t)pa);
-          tc_fence_after();
+          if (!(g.debug & 8)) { mbar_wait(&a_full[sa], (uint32_t)pa); tc_fence_after(); }
           const uint32_t a_st = a_ring + (uint32_t)(sa * (C::kAStage >> 4));
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
             uint32_t b_st;
-            if (resident) {
-              b_st = b_ring + (uint32_t)((cs * 3 + r) * (C::kBStage >> 4));
+            if (resident || (g.debug & 4)) {
+              b_st = b_ring + (uint32_t)(resident ? (cs * 3 + r) * (C::kBStage >> 4) : 0);
             } else {
               mbar_wait(&b_full[sb], (uint32_t)pb);
               tc_fence_after();
@@ -177,18 +179,22 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               const uint32_t o = (uint32_t)(j * 2);                    // 16 bf16 = 32 bytes along k inside the swizzled row
               const uint64_t dah = make_desc(C::kDescHi, a_hi + o), dal = make_desc(C::kDescHi, a_hi + o + (C::kAPlane >> 4));
               const uint64_t dbh = make_desc(C::kDescHi, b_st + o), dbl = make_desc(C::kDescHi, b_st + o + (C::kBPlane >> 4));
-              umma_bf16(tmem_d, dal, dbh, idesc, accumulate);
-              umma_bf16(tmem_d, dah, dbl, idesc, 1u);
-              umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+              if (!(g.debug & 1)) {
+                umma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+                umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+              }
               accumulate = 1u;
             }
-            if (!resident) {
+            if (!resident && !(g.debug & 4)) {
               umma_commit(&b_empty[sb]);
               if (++sb == g.nbr) { sb = 0; pb ^= 1; }
             }
           }
-          umma_commit(&a_empty[sa]);
-          if (++sa == g.na) { sa = 0; pa ^= 1; }
+          if (!(g.debug & 8)) {
+            umma_commit(&a_empty[sa]);
+            if (++sa == g.na) { sa = 0; pa ^= 1; }
+          }
         }
         umma_commit(&t_full[as]);
       }
@@ -213,14 +219,15 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         plane_coords(ow, g.out.w_lo, g.out.up, g.out.halo, cols);
       }
       const size_t res_off = g.res.base ? (((size_t)img * g.res.hp + oh + 1) * g.res.wp + ow + 1) * g.res.c_total : 0;
-      mbar_wait(&t_full[as], (uint32_t)((it >> 1) & 1));
+      if (lane == 0) mbar_wait(&t_full[as], (uint32_t)((it >> 1) & 1));      // one poller per warp
+      __syncwarp();
       tc_fence_after();
 #pragma unroll 1
       for (int c = slot * 8; c < BN; c += 32) {
         uint32_t r[8];
         tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
         const int n = nb * BN + c;
-        if (!ok || n >= g.cout) continue;
+        if (!ok || n >= g.cout || (g.debug & 2)) continue;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
@@ -325,6 +332,7 @@ static int encode(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, 
   return 0;
 }
 
+static int g_tma_debug = 0;
 static int g_tma_sms = 0;
 static int tma_num_sms() {
   if (g_tma_sms == 0) {
@@ -399,6 +407,7 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   g.n_img = in.n; g.ho = ho; g.wo = wo; g.cout = cout; g.cin = cin;
   g.tiles_x = (wo + kTmaTW - 1) / kTmaTW; g.tiles_y = (ho + kTmaTH - 1) / kTmaTH;
   g.n_blocks = cout / bn; g.chunks = cin / kc;
+  g.debug = g_tma_debug;
   g.act = p->act; g.scale = p->scale; g.shift = p->shift; g.y = p->y;
   if (p->residual) {
     if (int rc = check_planes(p->residual, "conv3x3_tma.residual")) return rc;
@@ -445,6 +454,8 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   set_error("conv3x3_tma: no kernel for channel chunk %d / N block %d", kc, bn);
   return -1;
 }
+
+int clslam_debug_tma_flags(int flags) { g_tma_debug = flags; return 0; }
 
 int clslam_planes_from_f32(const float* x, const clslam_planes* out, int out_up, int out_halo, void* stream) {
   if (int rc = check_planes(out, "planes_from_f32")) return rc;

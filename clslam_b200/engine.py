@@ -35,6 +35,34 @@ def conv_out(hi: int, k: int, s: int, p: int) -> int:
     return (hi + 2 * p - k) // s + 1
 
 
+TMA_MIN_TILES = 24        # below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: gather kernels
+
+
+def tma_ok(n: int, h: int, w: int, ci: int, co: int) -> bool:
+    """3x3 / stride-1 layer eligible for clslam_conv3x3_tma (planes in, planes / fp32 out)"""
+    if L.load().clslam_get_conv_mode() != 1 or ci % 16 or co % 16:
+        return False
+    bn = 128 if co >= 128 else (64 if co >= 64 else (32 if co >= 32 else 16))
+    if co % bn:
+        return False
+    return n * ((h + 15) // 16) * ((w + 7) // 8) >= TMA_MIN_TILES
+
+
+class PlaneBuf:
+    """bf16 hi/lo activation planes [2][n][h+2][w+2][c_total] (include/clslam_b200.h: clslam_planes)"""
+
+    def __init__(self, plan: 'Plan', n: int, h: int, w: int, c_total: int):
+        self.n, self.h, self.w, self.c_total = n, h, w, c_total
+        self.t = plan.alloc(2, n, h + 2, w + 2, c_total, dtype=torch.bfloat16, zero=True)
+        self.plan = plan
+
+    def view(self, c_off: int = 0, c: Optional[int] = None) -> L.Planes:
+        c = self.c_total - c_off if c is None else c
+        v = L.Planes(self.t.data_ptr(), self.t[0].numel(), self.n, self.h, self.w, self.c_total, c_off, c)
+        self.plan.keep.append(v)
+        return v
+
+
 class PreparedEncoder:
     """Device-side, kernel-layout copies of a (frozen) encoder: KRSC weights (conv1 input channels
     zero-padded to 4/8) and BatchNorm(eval) folded to per-channel scale/shift
@@ -52,9 +80,12 @@ class PreparedEncoder:
                 w = torch.cat([w, w.new_zeros(w.shape[0], pad_to - w.shape[1], *w.shape[2:])], 1)
             wk = w.permute(0, 2, 3, 1).contiguous()
             self.t[name + '.w'] = wk
-            hi = wk.to(torch.bfloat16)                                   # same round-to-nearest split as the kernels
-            self.t[name + '.w_hi'] = hi
-            self.t[name + '.w_lo'] = (wk - hi.float()).to(torch.bfloat16)
+            hl = torch.empty(2, *wk.shape, dtype=torch.bfloat16, device=device)   # lo follows hi: one TMA map covers both
+            hl[0] = wk.to(torch.bfloat16)                                 # same round-to-nearest split as the kernels
+            hl[1] = (wk - hl[0].float()).to(torch.bfloat16)
+            self.t[name + '.w_hl'] = hl
+            self.t[name + '.w_hi'] = hl[0]
+            self.t[name + '.w_lo'] = hl[1]
 
         def put_bn(name, bn):
             scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
@@ -146,13 +177,35 @@ class Plan:
         self.keep.append(d)
         return d
 
-    def conv_fwd(self, name, d: L.ConvDesc, x, x2, w, scale, shift, res, y, w_hi=None, w_lo=None) -> None:
+    def conv_fwd(self, name, d: L.ConvDesc, x, x2, w, scale, shift, res, y, w_hi=None, w_lo=None,
+                 out: Optional[L.Planes] = None, out_up: int = 1, out_halo: int = 0) -> None:
+        """gather kernels (any geometry, fp32 NHWC input); optional second output as planes"""
         self.need_ws(self.lib.clslam_conv_fwd_workspace_bytes(ctypes.byref(d)))
-        self.add(name, self._conv_fwd, d, _p(x), _p(x2), _p(w), _p(w_hi), _p(w_lo), _p(scale), _p(shift), _p(res), _p(y))
+        self.add(name, self._conv_fwd, d, _p(x), _p(x2), _p(w), _p(w_hi), _p(w_lo), _p(scale), _p(shift), _p(res), _p(y),
+                 out, out_up, out_halo)
 
-    def _conv_fwd(self, stream, ws, d, x, x2, w, w_hi, w_lo, scale, shift, res, y):
-        return self.lib.clslam_conv_fwd_bf16w(ctypes.byref(d), x, x2, w, w_hi, w_lo, scale, shift, res, y, ws, self.ws_bytes,
-                                              stream)
+    def _conv_fwd(self, stream, ws, d, x, x2, w, w_hi, w_lo, scale, shift, res, y, out, out_up, out_halo):
+        return self.lib.clslam_conv_fwd_emit(ctypes.byref(d), x, x2, w, w_hi, w_lo, scale, shift, res, y,
+                                             ctypes.byref(out) if out is not None else None, out_up, out_halo,
+                                             ws, self.ws_bytes, stream)
+
+    def conv_tma(self, name, inp: L.Planes, pad_mode: int, cout: int, w_hi, w_lo, scale, shift, act: int,
+                 res: Optional[L.Planes] = None, y=None, out: Optional[L.Planes] = None, out_up: int = 1,
+                 out_halo: int = 0) -> None:
+        """TMA-fed tcgen05 3x3 / stride-1 convolution over planes (clslam_conv3x3_tma)"""
+        a = L.ConvTma()
+        a.inp = inp
+        a.pad_mode, a.cout = pad_mode, cout
+        a.w_hi, a.w_lo = _p(w_hi), _p(w_lo)
+        a.scale, a.shift, a.act = _p(scale), _p(shift), act
+        if res is not None:
+            a.residual = ctypes.pointer(res)
+        a.y = _p(y)
+        if out is not None:
+            a.out = ctypes.pointer(out)
+        a.out_up, a.out_halo = out_up, out_halo
+        self.keep.append(a)
+        self.ops.append((name, lambda stream, ws, arg: self.lib.clslam_conv3x3_tma(ctypes.byref(arg), stream), (a,), self.lane))
 
     def conv_dgrad(self, name, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev) -> None:
         self.need_ws(self.lib.clslam_conv_dgrad_workspace_bytes(ctypes.byref(d)))
@@ -207,41 +260,72 @@ class Plan:
 
 
 def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: torch.Tensor, n: int, h: int, w: int, tag: str,
+                  skips: Optional[Dict[int, L.Planes]] = None, feat4_planes: Optional[L.Planes] = None,
                   ) -> List[torch.Tensor]:
     """ResNet-18 trunk (networks/resnet_encoder.py:115-125) over an NHWC staged input; returns the
-    five NHWC feature maps."""
+    five fp32 NHWC feature maps.  3x3 / stride-1 convolutions run the TMA kernel on bf16 hi/lo planes
+    (intermediate activations then exist only as planes); conv1, the stride-2 convolutions and the 1x1
+    down-sampling run the gather kernels.  ``skips[i]`` / ``feat4_planes``: where feature i is additionally
+    written as planes (reflection halo) for the depth decoder."""
     t = prep.t
+    skips = skips or {}
     feats = []
     d = plan.desc(n, h, w, prep.cin_pad, 64, 7, 2, 3, act=L.ACT_RELU)
     f0 = plan.alloc(n, d.ho, d.wo, 64)
     plan.conv_fwd(f'{tag}.conv1', d, x_staged, None, t['conv1.w'], t['bn1.scale'], t['bn1.shift'], None, f0,
-                  t['conv1.w_hi'], t['conv1.w_lo'])
+                  t['conv1.w_hi'], t['conv1.w_lo'], out=skips.get(0), out_halo=1)
     feats.append(f0)
     hp, wp = conv_out(d.ho, 3, 2, 1), conv_out(d.wo, 3, 2, 1)
-    x = plan.alloc(n, hp, wp, 64)
-    plan.simple(f'{tag}.maxpool', plan.lib.clslam_maxpool3x3s2, _p(f0), _p(x), n, d.ho, d.wo, 64)
     hc, wc, cin = hp, wp, 64
+    use = tma_ok(n, hc, wc, 64, 64)
+    x_f32 = plan.alloc(n, hp, wp, 64) if not use else None
+    x_pl = PlaneBuf(plan, n, hp, wp, 64).view() if use else None
+    plan.add(f'{tag}.maxpool', lambda stream, ws, a, b, c: plan.lib.clslam_maxpool3x3s2_emit(
+        a, b, n, d.ho, d.wo, 64, ctypes.byref(c) if c is not None else None, 0, stream), _p(f0), _p(x_f32), x_pl)
     for li, planes in enumerate((64, 128, 256, 512), start=1):
         for bi in range(2):
             stride = 2 if (li > 1 and bi == 0) else 1
             p = f'layer{li}.{bi}'
             d1 = plan.desc(n, hc, wc, cin, planes, 3, stride, 1, act=L.ACT_RELU)
-            mid = plan.alloc(n, d1.ho, d1.wo, planes)
-            plan.conv_fwd(f'{tag}.{p}.conv1', d1, x, None, t[p + '.conv1.w'], t[p + '.bn1.scale'], t[p + '.bn1.shift'],
-                          None, mid, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'])
+            ho, wo = d1.ho, d1.wo
+            use2 = tma_ok(n, ho, wo, planes, planes)                    # conv2 (and, for bi == 1 / layer1, conv1)
+            use1 = stride == 1 and use2 and x_pl is not None
+            last = bi == 1                                              # this block's output is encoder feature li
+            # ---- conv1 -> mid
+            mid_pl = PlaneBuf(plan, n, ho, wo, planes).view() if use2 else None
+            mid_f32 = plan.alloc(n, ho, wo, planes) if not use2 else None
+            if use1:
+                plan.conv_tma(f'{tag}.{p}.conv1', x_pl, L.PAD_ZERO, planes, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'],
+                              t[p + '.bn1.scale'], t[p + '.bn1.shift'], L.ACT_RELU, y=mid_f32, out=mid_pl)
+            else:
+                plan.conv_fwd(f'{tag}.{p}.conv1', d1, x_f32, None, t[p + '.conv1.w'], t[p + '.bn1.scale'], t[p + '.bn1.shift'],
+                              None, mid_f32, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'], out=mid_pl)
+            # ---- identity branch
             if (p + '.ds.w') in t:
                 dd = plan.desc(n, hc, wc, cin, planes, 1, stride, 0, act=L.ACT_NONE)
-                idt = plan.alloc(n, dd.ho, dd.wo, planes)
-                plan.conv_fwd(f'{tag}.{p}.downsample', dd, x, None, t[p + '.ds.w'], t[p + '.dsbn.scale'],
-                              t[p + '.dsbn.shift'], None, idt, t[p + '.ds.w_hi'], t[p + '.ds.w_lo'])
+                idt_pl = PlaneBuf(plan, n, ho, wo, planes).view() if use2 else None
+                idt_f32 = plan.alloc(n, ho, wo, planes) if not use2 else None
+                plan.conv_fwd(f'{tag}.{p}.downsample', dd, x_f32, None, t[p + '.ds.w'], t[p + '.dsbn.scale'],
+                              t[p + '.dsbn.shift'], None, idt_f32, t[p + '.ds.w_hi'], t[p + '.ds.w_lo'], out=idt_pl)
             else:
-                idt = x
-            d2 = plan.desc(n, d1.ho, d1.wo, planes, planes, 3, 1, 1, act=L.ACT_RELU)
-            out = plan.alloc(n, d2.ho, d2.wo, planes)
-            plan.conv_fwd(f'{tag}.{p}.conv2', d2, mid, None, t[p + '.conv2.w'], t[p + '.bn2.scale'], t[p + '.bn2.shift'],
-                          idt, out, t[p + '.conv2.w_hi'], t[p + '.conv2.w_lo'])
-            x, hc, wc, cin = out, d2.ho, d2.wo, planes
-        feats.append(x)
+                idt_pl, idt_f32 = x_pl, x_f32
+            # ---- conv2 (+ identity, ReLU) -> block output.  Block 0 feeds block 1 of the same layer (planes when that
+            # runs the TMA kernel); block 1 is encoder feature li: always fp32 (stride-2 / 1x1 consumers, the callers,
+            # weight gradients) plus, for the depth net, planes in the decoder's concat buffer (reflection halo)
+            skip_pl = (skips.get(li) if li < 4 else feat4_planes) if last else None
+            out_pl = PlaneBuf(plan, n, ho, wo, planes).view() if (use2 and not last) else skip_pl
+            out_f32 = plan.alloc(n, ho, wo, planes) if (last or not use2) else None
+            if use2:
+                plan.conv_tma(f'{tag}.{p}.conv2', mid_pl, L.PAD_ZERO, planes, t[p + '.conv2.w_hi'], t[p + '.conv2.w_lo'],
+                              t[p + '.bn2.scale'], t[p + '.bn2.shift'], L.ACT_RELU, res=idt_pl, y=out_f32, out=out_pl,
+                              out_halo=1 if last else 0)
+            else:
+                d2 = plan.desc(n, ho, wo, planes, planes, 3, 1, 1, act=L.ACT_RELU)
+                plan.conv_fwd(f'{tag}.{p}.conv2', d2, mid_f32, None, t[p + '.conv2.w'], t[p + '.bn2.scale'], t[p + '.bn2.shift'],
+                              idt_f32, out_f32, t[p + '.conv2.w_hi'], t[p + '.conv2.w_lo'], out=out_pl, out_halo=1 if last else 0)
+            x_f32, x_pl = out_f32, (None if last else out_pl)
+            hc, wc, cin = ho, wo, planes
+        feats.append(x_f32)
     return feats
 
 
@@ -315,21 +399,40 @@ class AdaptEngine:
         self.depth_in = plan.alloc(b, h, w, depth_prep.cin_pad)
         plan.simple('depth.stage', lib.clslam_stage_images, _p(self.rgb_aug[1]), None, _p(self.depth_in), b, h, w,
                     depth_prep.cin_pad)
-        feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc')
+        # decoder geometry first: which layers run the TMA kernel decides where the encoder writes its skip features
+        # (planes inside the decoder's concat buffers: torch.cat of depth_decoder.py:66 without a copy)
+        fh = [h >> (k + 1) for k in range(5)]
+        fw = [w >> (k + 1) for k in range(5)]
+        u0, u1, cat, y1_pl = {}, {}, {}, {}
+        for i in range(4, -1, -1):
+            hi_, wi_ = (fh[4], fw[4]) if i == 4 else (fh[i], fw[i])          # input of upconv_i_0: feats[4] or y1 of stage i + 1
+            cin0 = ENC_CH[4] if i == 4 else DEC_CH[i + 1]
+            c2 = ENC_CH[i - 1] if i > 0 else 0
+            u0[i] = tma_ok(b, hi_, wi_, cin0, DEC_CH[i])
+            u1[i] = tma_ok(b, 2 * hi_, 2 * wi_, DEC_CH[i] + c2, DEC_CH[i])
+            cat[i] = PlaneBuf(plan, b, 2 * hi_, 2 * wi_, DEC_CH[i] + c2) if u1[i] else None
+        skips = {i - 1: cat[i].view(DEC_CH[i], ENC_CH[i - 1]) for i in range(1, 5) if cat[i] is not None}
+        feat4_pl = PlaneBuf(plan, b, fh[4], fw[4], ENC_CH[4]).view() if u0[4] else None
+        feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc', skips=skips, feat4_planes=feat4_pl)
         self.depth_feats = feats
         dd = 'depth_decoder'
-        self.y = {}          # decoder activations (ELU outputs), NHWC
+        self.y = {}          # decoder activations (ELU outputs), NHWC fp32 (dispconv, backward)
         self.disp = {}
         self.dec_desc = {}
-        x = feats[4]
+        x, x_pl = feats[4], feat4_pl
         plan.wait('wsplit')
         for i in range(4, -1, -1):
             hi_, wi_ = x.shape[1], x.shape[2]
             d0 = plan.desc(b, hi_, wi_, x.shape[3], DEC_CH[i], 3, 1, 1, pad_mode=L.PAD_REFLECT, act=L.ACT_ELU)
             y0 = plan.alloc(b, hi_, wi_, DEC_CH[i])
             key0 = (dd, f'upconv_{i}_0.conv.conv')
-            plan.conv_fwd(f'upconv_{i}_0', d0, x, None, flat.weight_ptr(key0), None, flat.bias_ptr(key0), None, y0,
-                          flat.weight_hi_ptr(key0), flat.weight_lo_ptr(key0))
+            y0_up = cat[i].view(0, DEC_CH[i]) if cat[i] is not None else None     # nearest 2x on write (depth_decoder.py:61-64)
+            if u0[i]:
+                plan.conv_tma(f'upconv_{i}_0', x_pl, L.PAD_REFLECT, DEC_CH[i], flat.weight_hi_ptr(key0), flat.weight_lo_ptr(key0),
+                              None, flat.bias_ptr(key0), L.ACT_ELU, y=y0, out=y0_up, out_up=2, out_halo=1)
+            else:
+                plan.conv_fwd(f'upconv_{i}_0', d0, x, None, flat.weight_ptr(key0), None, flat.bias_ptr(key0), None, y0,
+                              flat.weight_hi_ptr(key0), flat.weight_lo_ptr(key0), out=y0_up, out_up=2, out_halo=1)
             self.y[(i, 0)] = y0; self.dec_desc[(i, 0)] = (d0, x)
             if i > 0:
                 skip = feats[i - 1]
@@ -343,8 +446,13 @@ class AdaptEngine:
                            c1=DEC_CH[i], h1=hi_, w1=wi_, act=L.ACT_ELU)
             y1 = plan.alloc(b, ho_, wo_, DEC_CH[i])
             key1 = (dd, f'upconv_{i}_1.conv.conv')
-            plan.conv_fwd(f'upconv_{i}_1', d1, y0, skip, flat.weight_ptr(key1), None, flat.bias_ptr(key1), None, y1,
-                          flat.weight_hi_ptr(key1), flat.weight_lo_ptr(key1))
+            y1_pl[i] = PlaneBuf(plan, b, ho_, wo_, DEC_CH[i]).view() if (i > 0 and u0[i - 1]) else None
+            if u1[i]:
+                plan.conv_tma(f'upconv_{i}_1', cat[i].view(), L.PAD_REFLECT, DEC_CH[i], flat.weight_hi_ptr(key1),
+                              flat.weight_lo_ptr(key1), None, flat.bias_ptr(key1), L.ACT_ELU, y=y1, out=y1_pl[i], out_halo=1)
+            else:
+                plan.conv_fwd(f'upconv_{i}_1', d1, y0, skip, flat.weight_ptr(key1), None, flat.bias_ptr(key1), None, y1,
+                              flat.weight_hi_ptr(key1), flat.weight_lo_ptr(key1), out=y1_pl[i], out_halo=1)
             self.y[(i, 1)] = y1; self.dec_desc[(i, 1)] = (d1, y0, skip)
             if i < S:
                 keyd = (dd, f'dispconv_{i}.conv')
@@ -352,7 +460,7 @@ class AdaptEngine:
                 plan.simple(f'dispconv_{i}', lib.clslam_dispconv_fwd, _p(y1), flat.weight_ptr(keyd), flat.bias_ptr(keyd),
                             _p(dsp), b, ho_, wo_, DEC_CH[i])
                 self.disp[i] = dsp
-            x = y1
+            x, x_pl = y1, y1_pl[i]
 
         # ---- pose network (both passes batched: [frame -1 | frame +1]) ------------------------
         plan.set_lane(1)
@@ -371,14 +479,21 @@ class AdaptEngine:
         self.pose_desc = {}
         x = pf4
         plan.wait('wsplit')
+        up = tma_ok(2 * b, hp, wp, 256, 256)          # pose_0 / pose_1 on the TMA kernel (planes chained squeeze -> pose_0 -> pose_1)
+        x_pl = None
         for name, co, ci, k, act in (('squeeze', 256, 512, 1, L.ACT_RELU), ('pose_0', 256, 256, 3, L.ACT_RELU),
                                      ('pose_1', 256, 256, 3, L.ACT_RELU), ('pose_2', 12, 256, 1, L.ACT_NONE)):
             d = plan.desc(2 * b, hp, wp, ci, co, k, 1, (k - 1) // 2, act=act)
             yv = plan.alloc(2 * b, hp, wp, co)
-            plan.conv_fwd(name, d, x, None, flat.weight_ptr((pd, name)), None, flat.bias_ptr((pd, name)), None, yv,
-                          flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)))
+            out_pl = PlaneBuf(plan, 2 * b, hp, wp, co).view() if (up and name in ('squeeze', 'pose_0')) else None
+            if up and k == 3:
+                plan.conv_tma(name, x_pl, L.PAD_ZERO, co, flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)), None,
+                              flat.bias_ptr((pd, name)), act, y=yv, out=out_pl)
+            else:
+                plan.conv_fwd(name, d, x, None, flat.weight_ptr((pd, name)), None, flat.bias_ptr((pd, name)), None, yv,
+                              flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)), out=out_pl)
             self.pose_act[name] = yv; self.pose_desc[name] = (d, x)
-            x = yv
+            x, x_pl = yv, out_pl
         self.axis_angle = plan.alloc(2, b, 3)
         self.translation = plan.alloc(2, b, 3)
         self.cam_t_cam = plan.alloc(2, b, 4, 4)

@@ -210,8 +210,10 @@ class FlatParams:
         self.exp_avg_sq = torch.zeros(total, device=device)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=device)   # Adam updates done so far
         # bf16 hi / lo planes of `params` (refreshed on the device at the start of every forward pass)
-        self.params_hi = torch.zeros(total, dtype=torch.bfloat16, device=device)
-        self.params_lo = torch.zeros(total, dtype=torch.bfloat16, device=device)
+        # (one [2][total] allocation: the lo plane follows the hi plane, so a single TMA map covers both)
+        self.params_hl = torch.zeros(2, total, dtype=torch.bfloat16, device=device)
+        self.params_hi = self.params_hl[0]
+        self.params_lo = self.params_hl[1]
         self.index = {}   # (net, path) -> dict(w_off, w_numel, b_off, co, ci, k)
         off = 0
         mods = {'depth_decoder': depth_decoder, 'pose_decoder': pose_decoder}

@@ -135,6 +135,8 @@ typedef struct clslam_conv_tma {
   int out_halo;            /* write the reflection halo of `out` */
 } clslam_conv_tma;
 int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
+/* timing experiments only (results are wrong when != 0): 1 no MMA, 2 no epilogue body, 4 no weight ring, 8 no A loads */
+int clslam_debug_tma_flags(int flags);
 
 /* clslam_conv_fwd_bf16w / clslam_maxpool3x3s2 that additionally emit their result as planes */
 int clslam_conv_fwd_emit(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,

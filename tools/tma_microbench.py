@@ -71,6 +71,10 @@ def bench(n, h, w, ci, co, pad_mode):
     r = {'shape': f'n{n} {h}x{w} {ci}->{co} pad{pad_mode}', 'old_us': timed(run_old), 'tma_planes_us': timed(run_tma_planes),
          'tma_f32_us': timed(run_tma_f32)}
     r['old_warm_us'] = warm(run_old); r['tma_planes_warm_us'] = warm(run_tma_planes)
+    for fl in (1, 2, 3, 4, 8, 12, 15):
+        lib.clslam_debug_tma_flags(fl)
+        r[f'dbg{fl}_warm_us'] = warm(run_tma_planes)
+    lib.clslam_debug_tma_flags(0)
     r['tma_tflops'] = flops / (r['tma_planes_us'] * 1e-6) / 1e12
     r['tma_gbs'] = byts / (r['tma_planes_us'] * 1e-6) / 1e9
     r['old_tflops'] = flops / (r['old_us'] * 1e-6) / 1e12
