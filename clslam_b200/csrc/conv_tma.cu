@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include "conv_ops.cuh"
 #include "planes.cuh"
 
 namespace clslam {
@@ -65,6 +66,8 @@ struct TmaConvArgs {
   const float* scale;
   const float* shift;
   PlaneView res;                 // base == nullptr: none
+  const float* gate;             // optional fp32 NHWC (n, ho, wo, cout): result *= act'(gate) (dgrad through the previous activation)
+  int gate_act;
   float* y;
   PlaneView out;                 // base == nullptr: none
 };
@@ -252,6 +255,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = act_fast(v[j], g.act);
+        if (g.gate) {
+          const float4 g0 = ld4(g.gate + y_off + n), g1 = ld4(g.gate + y_off + n + 4);
+          v[0] *= act_grad_from_output(g0.x, g.gate_act); v[1] *= act_grad_from_output(g0.y, g.gate_act);
+          v[2] *= act_grad_from_output(g0.z, g.gate_act); v[3] *= act_grad_from_output(g0.w, g.gate_act);
+          v[4] *= act_grad_from_output(g1.x, g.gate_act); v[5] *= act_grad_from_output(g1.y, g.gate_act);
+          v[6] *= act_grad_from_output(g1.z, g.gate_act); v[7] *= act_grad_from_output(g1.w, g.gate_act);
+        }
         if (g.y) {
           float* p = g.y + y_off + n;
           *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -299,6 +309,74 @@ planes_from_f32_kernel(const float* __restrict__ x, PlaneView out, int n, int h,
     const float4 v4 = ld4(x + i * 4);
     const float v[4] = {v4.x, v4.y, v4.z, v4.w};
     planes_emit<4>(out, img, oh, ow, cc, v);
+  }
+}
+
+// ---- dgrad helpers ---------------------------------------------------------------------------------
+// Wt[ci'][2 - r][2 - s][co] = W[co][r][s][ci'] for ci' < n_ci, on both bf16 planes (a pure permutation): the weights
+// of the convolution that computes dX from dZ (taps flipped, channels transposed)
+struct WtFlipItem { long long src, dst; int co, ci, n_ci, pad; };
+
+__global__ void __launch_bounds__(256)
+wt_flip_kernel(const WtFlipItem* __restrict__ items, const uint16_t* __restrict__ w_hi, long long w_plane,
+               uint16_t* __restrict__ wt_hi, long long wt_plane) {
+  const WtFlipItem it = items[blockIdx.y];
+  const long long total = (long long)it.n_ci * 9 * it.co;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % it.co);
+    const int tap = (int)((i / it.co) % 9);
+    const int c = (int)(i / ((long long)it.co * 9));
+    const long long src = it.src + ((long long)o * 9 + (8 - tap)) * it.ci + c;
+    wt_hi[it.dst + i] = w_hi[src];
+    wt_hi[wt_plane + it.dst + i] = w_hi[w_plane + src];
+  }
+}
+
+// dX from the "full" correlation dxp (n, H + 2, W + 2, c) of a reflection-padded layer: every interior pixel also
+// receives the halo cells that mirror onto it; up = 2 additionally sums the 2 x 2 nearest-neighbour footprint (the
+// layer read an up-sampled tensor).  Then + the dispconv input gradient, * act'(y_prev); written as fp32 and/or planes.
+__global__ void __launch_bounds__(256)
+dgrad_fold_kernel(const float* __restrict__ dxp, int n, int H, int W, int c, int up, const float* __restrict__ y_prev,
+                  int act_prev, const float* __restrict__ disp_dz, const float* __restrict__ disp_w,
+                  float* __restrict__ dz_prev, PlaneView po) {
+  const int ho = H / up, wo = W / up, c4 = c / 4;
+  const size_t total = (size_t)n * ho * wo * c4;
+  const int Wp = W + 2;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c4) * 4;
+    size_t p = i / c4;
+    const int ow = (int)(p % wo); p /= wo;
+    const int oh = (int)(p % ho);
+    const int img = (int)(p / ho);
+    float4 acc = f4zero();
+    for (int a = 0; a < up; ++a) {
+      const int hh = oh * up + a;                       // interior row of the layer input
+      int rows[3] = {hh + 1, hh == 1 ? 0 : -1, hh == H - 2 ? H + 1 : -1};
+      for (int b = 0; b < up; ++b) {
+        const int ww = ow * up + b;
+        int cols[3] = {ww + 1, ww == 1 ? 0 : -1, ww == W - 2 ? W + 1 : -1};
+#pragma unroll
+        for (int ra = 0; ra < 3; ++ra) {
+          if (rows[ra] < 0) continue;
+#pragma unroll
+          for (int cb = 0; cb < 3; ++cb) {
+            if (cols[cb] < 0) continue;
+            f4add(acc, ld4(dxp + (((size_t)img * (H + 2) + rows[ra]) * Wp + cols[cb]) * c + cc));
+          }
+        }
+      }
+    }
+    if (disp_dz) f4add(acc, dispconv_dgrad_at(disp_dz, disp_w, img, oh, ow, ho, wo, c, cc));
+    if (y_prev) {
+      const float4 yv = ld4(y_prev + i * 4);
+      acc.x *= act_grad_from_output(yv.x, act_prev); acc.y *= act_grad_from_output(yv.y, act_prev);
+      acc.z *= act_grad_from_output(yv.z, act_prev); acc.w *= act_grad_from_output(yv.w, act_prev);
+    }
+    if (dz_prev) *reinterpret_cast<float4*>(dz_prev + i * 4) = acc;
+    if (po.base) {
+      const float v[4] = {acc.x, acc.y, acc.z, acc.w};
+      planes_emit<4>(po, img, oh, ow, cc, v);
+    }
   }
 }
 
@@ -408,6 +486,7 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   g.tiles_x = (wo + kTmaTW - 1) / kTmaTW; g.tiles_y = (ho + kTmaTH - 1) / kTmaTH;
   g.n_blocks = cout / bn; g.chunks = cin / kc;
   g.debug = g_tma_debug;
+  g.gate = p->gate; g.gate_act = p->gate_act;
   g.act = p->act; g.scale = p->scale; g.shift = p->shift; g.y = p->y;
   if (p->residual) {
     if (int rc = check_planes(p->residual, "conv3x3_tma.residual")) return rc;
@@ -453,6 +532,39 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
 #undef CLSLAM_TMA_CASE
   set_error("conv3x3_tma: no kernel for channel chunk %d / N block %d", kc, bn);
   return -1;
+}
+
+int clslam_wt_flip(const void* items_dev, int n_items, int max_elems, const void* w_hi, long long w_plane_stride, void* wt_hi,
+                   long long wt_plane_stride, void* stream) {
+  if (n_items < 1 || !items_dev || !w_hi || !wt_hi) { set_error("wt_flip: bad arguments"); return -1; }
+  int bx = (max_elems + 255) / 256;
+  if (bx > 64) bx = 64;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n_items);
+  wt_flip_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const WtFlipItem*>(items_dev),
+                                                      reinterpret_cast<const uint16_t*>(w_hi), w_plane_stride,
+                                                      reinterpret_cast<uint16_t*>(wt_hi), wt_plane_stride);
+  return finish_launch("wt_flip");
+}
+
+int clslam_dgrad_fold(const float* dxp, int n, int h, int w, int c, int up, const float* y_prev, int act_prev,
+                      const float* disp_dz, const float* disp_w, float* dz_prev, const clslam_planes* dz_prev_planes,
+                      void* stream) {
+  if ((up != 1 && up != 2) || c % 4 || h % up || w % up || h < 3 || w < 3) { set_error("dgrad_fold: bad dims"); return -1; }
+  if (disp_dz && up != 1) { set_error("dgrad_fold: dispconv term needs up == 1"); return -1; }
+  PlaneView po{};
+  if (dz_prev_planes) {
+    if (!dz_prev_planes->base || dz_prev_planes->n != n || dz_prev_planes->h != h / up || dz_prev_planes->w != w / up ||
+        dz_prev_planes->c != c || dz_prev_planes->c_total % 8 || dz_prev_planes->c_off % 4) { set_error("dgrad_fold: planes mismatch"); return -1; }
+    po = make_plane_view(dz_prev_planes, 1, 0);
+  }
+  if (!dz_prev && !po.base) { set_error("dgrad_fold: no output"); return -1; }
+  const size_t total = (size_t)n * (h / up) * (w / up) * (c / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  dgrad_fold_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dxp, n, h, w, c, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, po);
+  return finish_launch("dgrad_fold");
 }
 
 int clslam_debug_tma_flags(int flags) { g_tma_debug = flags; return 0; }

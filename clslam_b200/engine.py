@@ -191,7 +191,7 @@ class Plan:
 
     def conv_tma(self, name, inp: L.Planes, pad_mode: int, cout: int, w_hi, w_lo, scale, shift, act: int,
                  res: Optional[L.Planes] = None, y=None, out: Optional[L.Planes] = None, out_up: int = 1,
-                 out_halo: int = 0) -> None:
+                 out_halo: int = 0, gate=None, gate_act: int = L.ACT_NONE) -> None:
         """TMA-fed tcgen05 3x3 / stride-1 convolution over planes (clslam_conv3x3_tma)"""
         a = L.ConvTma()
         a.inp = inp
@@ -201,6 +201,7 @@ class Plan:
         if res is not None:
             a.residual = ctypes.pointer(res)
         a.y = _p(y)
+        a.gate, a.gate_act = _p(gate), gate_act
         if out is not None:
             a.out = ctypes.pointer(out)
         a.out_up, a.out_halo = out_up, out_halo
@@ -221,6 +222,14 @@ class Plan:
 
     def _conv_wgrad(self, stream, ws, d, x, x2, dz, dw, db):
         return self.lib.clslam_conv_wgrad(ctypes.byref(d), x, x2, dz, dw, db, ws, self.ws_bytes, stream)
+
+    def planes_from_f32(self, name, x, out: L.Planes) -> None:
+        self.add(name, lambda stream, ws, xp, o: self.lib.clslam_planes_from_f32(xp, ctypes.byref(o), 1, 0, stream), _p(x), out)
+
+    def dgrad_fold(self, name, dxp, n, h, w, c, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, dz_prev_pl) -> None:
+        self.add(name, lambda stream, ws, *a: self.lib.clslam_dgrad_fold(*a[:11], ctypes.byref(a[11]) if a[11] is not None else None,
+                                                                         stream),
+                 _p(dxp), n, h, w, c, up, _p(y_prev), act_prev, _p(disp_dz), _p(disp_w), _p(dz_prev), dz_prev_pl)
 
     def simple(self, name, fn, *args) -> None:
         """fn(*args, stream)"""
@@ -394,6 +403,10 @@ class AdaptEngine:
         plan.fork((1, 2))
         plan.set_lane(2)      # bf16 hi/lo planes of the trainable weights (they change every Adam step)
         plan.simple('split_weights', lib.clslam_split_bf16, _p(flat.params), _p(flat.params_hi), _p(flat.params_lo), flat.numel)
+        # flipped / transposed weight planes for the TMA dgrad launches (filled in below, see _wt_flip_items)
+        self._wt_items: List[tuple] = []          # (key, n_ci)
+        self._wt_op_index = len(plan.ops)
+        plan.add('wt_flip', lambda stream, ws: self._run_wt_flip(stream))
         plan.record('wsplit')
         plan.set_lane(0)
         self.depth_in = plan.alloc(b, h, w, depth_prep.cin_pad)
@@ -568,6 +581,18 @@ class AdaptEngine:
         for i in range(0, 5):
             for j in (0, 1):
                 self.dz[(i, j)] = plan.alloc(*self.y[(i, j)].shape)
+        # dgrad on the TMA kernel where the (padded) output grid has enough tiles; dz is then also kept as planes
+        ud1 = {i: tma_ok(b, self.y[(i, 1)].shape[1] + 2, self.y[(i, 1)].shape[2] + 2, DEC_CH[i], DEC_CH[i]) for i in range(5)}
+        ud0 = {i: tma_ok(b, self.y[(i, 0)].shape[1] + 2, self.y[(i, 0)].shape[2] + 2, DEC_CH[i], DEC_CH[i + 1]) for i in range(4)}
+        dz_pl = {}
+        for i in range(5):
+            if ud1[i]:
+                dz_pl[(i, 1)] = PlaneBuf(plan, b, self.y[(i, 1)].shape[1], self.y[(i, 1)].shape[2], DEC_CH[i]).view()
+            if i < 4 and ud0[i]:
+                dz_pl[(i, 0)] = PlaneBuf(plan, b, self.y[(i, 0)].shape[1], self.y[(i, 0)].shape[2], DEC_CH[i]).view()
+        scratch_elems = max([b * (self.y[(i, 1)].shape[1] + 2) * (self.y[(i, 1)].shape[2] + 2) * DEC_CH[i] for i in range(5) if ud1[i]] +
+                            [b * (self.y[(i, 0)].shape[1] + 2) * (self.y[(i, 0)].shape[2] + 2) * DEC_CH[i + 1] for i in range(4) if ud0[i]] + [4])
+        dxp = plan.alloc(scratch_elems)
         for i in range(0, 5):
             y1 = self.y[(i, 1)]
             hi_, wi_ = y1.shape[1], y1.shape[2]
@@ -583,6 +608,8 @@ class AdaptEngine:
                 plan.simple('dispconv_0.dgrad', lib.clslam_dispconv_dgrad_act, _p(self.dz_disp[0]),
                             flat.weight_ptr((dd, 'dispconv_0.conv')), _p(y1), L.ACT_ELU, _p(self.dz[(0, 1)]), b, hi_, wi_,
                             DEC_CH[0])
+                if ud1[0]:
+                    plan.planes_from_f32('dz01.planes', self.dz[(0, 1)], dz_pl[(0, 1)])
                 plan.record('dz01')
             # upconv_i_1: wgrad + dgrad (to the up-sampled branch only; the skip feeds a frozen encoder)
             d1, y0, skip = self.dec_desc[(i, 1)]
@@ -591,8 +618,17 @@ class AdaptEngine:
             plan.wait(f'dz{i}1')
             plan.conv_wgrad(f'upconv_{i}_1.wgrad', d1, y0, skip, self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
             plan.set_lane(0)
-            plan.conv_dgrad(f'upconv_{i}_1.dgrad', d1, self.dz[(i, 1)], flat.weight_ptr(key1), y0, L.ACT_ELU, None, None,
-                            self.dz[(i, 0)])
+            nxt = dz_pl.get((i, 0)) if i < 4 else None
+            if ud1[i]:
+                wt_hi, wt_lo = self._wt_slot(key1, DEC_CH[i])
+                plan.conv_tma(f'upconv_{i}_1.dgrad', dz_pl[(i, 1)], L.PAD_FULL, DEC_CH[i], wt_hi, wt_lo, None, None, L.ACT_NONE, y=dxp)
+                plan.dgrad_fold(f'upconv_{i}_1.dgrad.fold', dxp, b, hi_, wi_, DEC_CH[i], 2, y0, L.ACT_ELU, None, None,
+                                self.dz[(i, 0)], nxt)
+            else:
+                plan.conv_dgrad(f'upconv_{i}_1.dgrad', d1, self.dz[(i, 1)], flat.weight_ptr(key1), y0, L.ACT_ELU, None, None,
+                                self.dz[(i, 0)])
+                if nxt is not None:
+                    plan.planes_from_f32(f'dz{i}0.planes', self.dz[(i, 0)], nxt)
             plan.record(f'dz{i}0')
             # upconv_i_0: wgrad; dgrad into upconv_{i+1}_1's output (+ dispconv_{i+1} term)
             d0, xin = self.dec_desc[(i, 0)]
@@ -603,10 +639,21 @@ class AdaptEngine:
             plan.set_lane(0)
             if i < 4:
                 has_disp = (i + 1) < S
-                plan.conv_dgrad(f'upconv_{i}_0.dgrad', d0, self.dz[(i, 0)], flat.weight_ptr(key0), self.y[(i + 1, 1)],
-                                L.ACT_ELU, self.dz_disp[i + 1] if has_disp else None,
-                                flat.weight_ptr((dd, f'dispconv_{i + 1}.conv')) if has_disp else None,
-                                self.dz[(i + 1, 1)])
+                disp_dz = self.dz_disp[i + 1] if has_disp else None
+                disp_w = flat.weight_ptr((dd, f'dispconv_{i + 1}.conv')) if has_disp else None
+                nxt = dz_pl.get((i + 1, 1))
+                if ud0[i]:
+                    hl, wl = self.y[(i, 0)].shape[1], self.y[(i, 0)].shape[2]
+                    wt_hi, wt_lo = self._wt_slot(key0, DEC_CH[i + 1])
+                    plan.conv_tma(f'upconv_{i}_0.dgrad', dz_pl[(i, 0)], L.PAD_FULL, DEC_CH[i + 1], wt_hi, wt_lo, None, None,
+                                  L.ACT_NONE, y=dxp)
+                    plan.dgrad_fold(f'upconv_{i}_0.dgrad.fold', dxp, b, hl, wl, DEC_CH[i + 1], 1, self.y[(i + 1, 1)], L.ACT_ELU,
+                                    disp_dz, disp_w, self.dz[(i + 1, 1)], nxt)
+                else:
+                    plan.conv_dgrad(f'upconv_{i}_0.dgrad', d0, self.dz[(i, 0)], flat.weight_ptr(key0), self.y[(i + 1, 1)],
+                                    L.ACT_ELU, disp_dz, disp_w, self.dz[(i + 1, 1)])
+                    if nxt is not None:
+                        plan.planes_from_f32(f'dz{i + 1}1.planes', self.dz[(i + 1, 1)], nxt)
                 plan.record(f'dz{i + 1}1')
         # pose branch
         plan.set_lane(1)
@@ -615,18 +662,63 @@ class AdaptEngine:
                     _p(self.axis_angle), _p(self.translation), _p(self.rel_dist), _p(self.sample_w),
                     self.vel_scale, b, hp, wp, self.invert_mask, _p(self.dz_pose['pose_2']))
         prev = {'pose_2': 'pose_1', 'pose_1': 'pose_0', 'pose_0': 'squeeze'}
+        upd = tma_ok(2 * b, hp, wp, 256, 256)         # pose_1 / pose_0 dgrad (zero padding: one launch, act' fused as a gate)
+        dzp_pl = {name: PlaneBuf(plan, 2 * b, hp, wp, 256).view() for name in ('pose_1', 'pose_0')} if upd else {}
         for name in ('pose_2', 'pose_1', 'pose_0', 'squeeze'):
             d, xin = self.pose_desc[name]
             plan.conv_wgrad(f'{name}.wgrad', d, xin, None, self.dz_pose[name], flat.wgrad_ptr((pd, name)),
                             flat.bgrad_ptr((pd, name)))
             if name in prev:
-                plan.conv_dgrad(f'{name}.dgrad', d, self.dz_pose[name], flat.weight_ptr((pd, name)),
-                                self.pose_act[prev[name]], L.ACT_RELU, None, None, self.dz_pose[prev[name]])
+                if upd and name in ('pose_1', 'pose_0'):
+                    wt_hi, wt_lo = self._wt_slot((pd, name), 256)
+                    plan.conv_tma(f'{name}.dgrad', dzp_pl[name], L.PAD_ZERO, 256, wt_hi, wt_lo, None, None, L.ACT_NONE,
+                                  y=self.dz_pose[prev[name]], out=dzp_pl.get(prev[name]), gate=self.pose_act[prev[name]],
+                                  gate_act=L.ACT_RELU)
+                else:
+                    plan.conv_dgrad(f'{name}.dgrad', d, self.dz_pose[name], flat.weight_ptr((pd, name)),
+                                    self.pose_act[prev[name]], L.ACT_RELU, None, None, self.dz_pose[prev[name]])
+                    if prev[name] in dzp_pl:
+                        plan.planes_from_f32(f'dz_{prev[name]}.planes', self.dz_pose[prev[name]], dzp_pl[prev[name]])
         plan.join((1, 2))
         self.n_bwd_ops = len(plan.ops)
+        self._finish_wt_flip()
         plan.finalize()
 
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
+
+    # ---- flipped weights of the TMA dgrad launches ------------------------------------------------
+    _WT_CAP = 4 * 1024 * 1024          # elements per plane reserved up front (the decoder has 3.1 M 3x3 weights)
+
+    def _wt_slot(self, key, n_ci: int):
+        """reserve Wt[n_ci][9][co] for layer `key`; returns (hi, lo) device addresses"""
+        if not hasattr(self, '_wt_buf'):
+            self._wt_buf = self.plan.alloc(2, self._WT_CAP, dtype=torch.bfloat16, zero=True)
+            self._wt_used = 0
+        info = self.flat.index[key]
+        n = n_ci * 9 * info['co']
+        off = self._wt_used
+        self._wt_used += (n + 63) // 64 * 64
+        if self._wt_used > self._WT_CAP:
+            raise RuntimeError('flipped-weight buffer too small')
+        self._wt_items.append((info['w_off'], off, info['co'], info['ci'], n_ci))
+        base = self._wt_buf.data_ptr()
+        return base + 2 * off, base + 2 * (self._WT_CAP + off)
+
+    def _finish_wt_flip(self) -> None:
+        import struct
+        if not self._wt_items:
+            self._wt_table = None
+            return
+        raw = b''.join(struct.pack('qqiiii', src, dst, co, ci, n_ci, 0) for src, dst, co, ci, n_ci in self._wt_items)
+        self._wt_table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+        self._wt_max = max(n_ci * 9 * co for _, _, co, _, n_ci in self._wt_items)
+
+    def _run_wt_flip(self, stream) -> int:
+        if self._wt_table is None:
+            return 0
+        f = self.flat
+        return self.lib.clslam_wt_flip(self._wt_table.data_ptr(), len(self._wt_items), self._wt_max, f.params_hi.data_ptr(),
+                                       f.params_hl[0].numel(), self._wt_buf.data_ptr(), self._WT_CAP, stream)
 
     # ---- execution -----------------------------------------------------------------------------
     def forward(self) -> None:

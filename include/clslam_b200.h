@@ -129,12 +129,27 @@ typedef struct clslam_conv_tma {
   const float* shift;      /* [cout] or NULL */
   int act;                 /* CLSLAM_ACT_* */
   const clslam_planes* residual;  /* optional, logical dims of the output */
+  const float* gate;       /* optional fp32 NHWC (n, ho, wo, cout): result *= act'(gate), dgrad through the activation */
+  int gate_act;            /* CLSLAM_ACT_* whose derivative (expressed through its output) is applied */
   float* y;                /* optional */
   const clslam_planes* out;       /* optional */
   int out_up;              /* 1 or 2 (nearest up-sampling on write) */
   int out_halo;            /* write the reflection halo of `out` */
 } clslam_conv_tma;
 int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
+/* dgrad of the 3x3 decoder convolutions on the same kernel (autograd of depth_pose_prediction.py:312):
+ *   clslam_wt_flip: Wt[ci'][2-r][2-s][co] = W[co][r][s][ci'] (ci' < n_ci) for a batch of layers described by a DEVICE
+ *     array of items {long long src, dst (element offsets into the planes); int co, ci, n_ci, pad}; planes are bf16 with
+ *     the lo plane `*_plane_stride` elements after the hi plane.
+ *   dX of a zero-padded layer = clslam_conv3x3_tma(dz planes, PAD_ZERO, Wt, gate = y_prev): one launch.
+ *   dX of a reflection-padded layer = clslam_conv3x3_tma(dz planes, PAD_FULL, Wt) -> fp32 (n, h+2, w+2, c), then
+ *   clslam_dgrad_fold: adds the halo cells onto the pixels they mirror, sums the 2x2 footprint when the layer read
+ *     an up-sampled tensor (up = 2), adds the dispconv input gradient, multiplies by act'(y_prev). */
+int clslam_wt_flip(const void* items_dev, int n_items, int max_elems, const void* w_hi, long long w_plane_stride, void* wt_hi,
+                   long long wt_plane_stride, void* stream);
+int clslam_dgrad_fold(const float* dxp, int n, int h, int w, int c, int up, const float* y_prev, int act_prev,
+                      const float* disp_dz, const float* disp_w, float* dz_prev, const clslam_planes* dz_prev_planes,
+                      void* stream);
 /* timing experiments only (results are wrong when != 0): 1 no MMA, 2 no epilogue body, 4 no weight ring, 8 no A loads */
 int clslam_debug_tma_flags(int flags);
 

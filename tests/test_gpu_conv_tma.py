@@ -183,3 +183,85 @@ def test_conv_fwd_emit_and_maxpool_emit():
     expp = F.max_pool2d(x, 3, 2, 1)
     assert cabi.rel_err(cabi.nchw(yp), expp) < 1e-6
     assert cabi.rel_err(outp.value()[:, :, 1:-1, 1:-1], expp) < 2e-5
+
+
+# ---- dgrad on the TMA kernel (flipped weights + fold) against the gather dgrad (itself checked against fp64) ----
+def _wt_flip(w_krsc, n_ci):
+    """(co,3,3,ci) fp32 cuda -> (hi, lo) planes of Wt[n_ci][9][co] through clslam_wt_flip"""
+    co, _, _, ci = w_krsc.shape
+    hi, lo = cabi.split_bf16(w_krsc)
+    total = n_ci * 9 * co
+    wt = torch.zeros(2, (total + 63) // 64 * 64, dtype=torch.bfloat16, device='cuda')
+    import struct
+    item = torch.frombuffer(bytearray(struct.pack('qqiiii', 0, 0, co, ci, n_ci, 0)), dtype=torch.uint8).cuda()
+    L.check(cabi.lib().clslam_wt_flip(item.data_ptr(), 1, total, hi.data_ptr(), lo.data_ptr() - hi.data_ptr() >> 1,
+                                      wt.data_ptr(), wt[0].numel(), cabi.stream()), 'wt_flip')
+    torch.cuda.synchronize()
+    ref = w_krsc[..., :n_ci].permute(3, 1, 2, 0).flip(1, 2).contiguous().view(-1)     # [ci'][2-r][2-s][co]
+    got = wt[0, :total].float() + wt[1, :total].float()
+    assert float((got - ref).abs().max()) < 1e-4 * float(ref.abs().max())
+    return wt[0], wt[1], (hi, lo, wt, item)
+
+
+def _planes_of(x_nhwc):
+    n, h, w, c = x_nhwc.shape
+    buf = PlaneBuf(n, h, w, c)
+    d = buf.desc()
+    L.check(cabi.lib().clslam_planes_from_f32(x_nhwc.data_ptr(), ctypes.byref(d), 1, 0, cabi.stream()), 'planes_from_f32')
+    return buf, d
+
+
+@pytest.mark.parametrize('upcat', [False, True])
+def test_dgrad_tma_reflect(upcat):
+    lib = cabi.lib()
+    if upcat:
+        n, h1, w1, c1, c2, co = 1, 12, 20, 32, 64, 32
+        h, w, ci = 2 * h1, 2 * w1, c1 + c2
+        d = cabi.make_desc(n, h, w, ci, co, 3, 1, 1, L.PAD_REFLECT, L.IN_UPCAT, c1, h1, w1, act=L.ACT_ELU)
+        n_ci, ho, wo = c1, h1, w1
+    else:
+        n, h, w, ci, co = 2, 20, 28, 64, 32
+        d = cabi.make_desc(n, h, w, ci, co, 3, 1, 1, L.PAD_REFLECT, act=L.ACT_ELU)
+        n_ci, ho, wo = ci, h, w
+    dz = rnd(n, h, w, co, seed=1).float().cuda()
+    wk = (rnd(co, 3, 3, ci, seed=2) * (ci * 9) ** -0.5).float().cuda()
+    y_prev = rnd(n, ho, wo, n_ci, seed=3).float().cuda()
+    disp_dz = None if upcat else rnd(n, 1, h, w, seed=4).float().cuda()
+    disp_w = None if upcat else (0.1 * rnd(1, 3, 3, ci, seed=5)).float().cuda()
+    ref = cabi.conv_dgrad(d, dz, wk, y_prev, L.ACT_ELU, disp_dz, disp_w)
+    # TMA path
+    wt_hi, wt_lo, keep = _wt_flip(wk, n_ci)
+    buf, pd = _planes_of(dz)
+    dxp = torch.full((n, h + 2, w + 2, n_ci), float('nan'), device='cuda')
+    a = L.ConvTma()
+    a.inp = pd; a.pad_mode = L.PAD_FULL; a.cout = n_ci; a.w_hi = wt_hi.data_ptr(); a.w_lo = wt_lo.data_ptr()
+    a.act = L.ACT_NONE; a.y = dxp.data_ptr(); a.out_up = 1
+    L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma(full)')
+    got = torch.empty(n, ho, wo, n_ci, device='cuda')
+    outp = PlaneBuf(n, ho, wo, n_ci)
+    od = outp.desc()
+    L.check(lib.clslam_dgrad_fold(dxp.data_ptr(), n, h, w, n_ci, 2 if upcat else 1, y_prev.data_ptr(), L.ACT_ELU,
+                                  cabi.P(disp_dz), cabi.P(disp_w), got.data_ptr(), ctypes.byref(od), cabi.stream()), 'dgrad_fold')
+    torch.cuda.synchronize()
+    assert cabi.rel_err(got, ref) < 1e-4
+    assert cabi.rel_err(outp.value()[:, :, 1:-1, 1:-1], cabi.nchw(got)) < 2e-5
+    assert float(outp.t[:, :, 0].float().abs().max()) == 0.0          # gradient planes keep a zero halo
+
+
+def test_dgrad_tma_zero_pad_gate():
+    lib = cabi.lib()
+    n, h, w, ci, co = 4, 6, 20, 256, 256
+    d = cabi.make_desc(n, h, w, ci, co, 3, 1, 1, L.PAD_ZERO, act=L.ACT_RELU)
+    dz = rnd(n, h, w, co, seed=1).float().cuda()
+    wk = (rnd(co, 3, 3, ci, seed=2) * (ci * 9) ** -0.5).float().cuda()
+    y_prev = rnd(n, h, w, ci, seed=3).float().cuda()
+    ref = cabi.conv_dgrad(d, dz, wk, y_prev, L.ACT_RELU, None, None)
+    wt_hi, wt_lo, keep = _wt_flip(wk, ci)
+    buf, pd = _planes_of(dz)
+    got = torch.full((n, h, w, ci), float('nan'), device='cuda')
+    a = L.ConvTma()
+    a.inp = pd; a.pad_mode = L.PAD_ZERO; a.cout = ci; a.w_hi = wt_hi.data_ptr(); a.w_lo = wt_lo.data_ptr()
+    a.act = L.ACT_NONE; a.gate = y_prev.data_ptr(); a.gate_act = L.ACT_RELU; a.y = got.data_ptr(); a.out_up = 1
+    L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma(gate)')
+    torch.cuda.synchronize()
+    assert cabi.rel_err(got, ref) < 1e-4
