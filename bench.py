@@ -187,6 +187,8 @@ def profile_ops(eng, pred, reps=5):
         d = None
         if model is None and a and hasattr(a[0], 'kh'):
             d = a[0]
+        if model is None and len(a) >= 2 and hasattr(a[0], 'c_total') and hasattr(a[1], 'c_total'):    # clslam_wgrad3x3_tma(x planes, dz planes)
+            row.update(bound='tensor', amount=2.0 * a[0].n * a[0].h * a[0].w * a[0].c * a[1].c * 9, unit='FLOP')
         if model is None and a and hasattr(a[0], 'inp'):          # clslam_conv_tma: 3x3 over planes
             t = a[0]
             full = 2 if t.pad_mode == 2 else 0

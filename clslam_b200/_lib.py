@@ -76,6 +76,9 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     'clslam_conv3x3_tma': (c_int, [POINTER(ConvTma), c_void_p]),
     'clslam_debug_tma_flags': (c_int, [c_int]),
+    'clslam_wgrad3x3_tma_workspace_bytes': (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
+    'clslam_wgrad3x3_tma': (c_int, [POINTER(Planes), c_int, POINTER(Planes), c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
+                                    c_void_p]),
     'clslam_wt_flip': (c_int, [c_void_p, c_int, c_int, c_void_p, c_longlong, c_void_p, c_longlong, c_void_p]),
     'clslam_dgrad_fold': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                   POINTER(Planes), c_void_p]),

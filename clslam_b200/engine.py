@@ -223,6 +223,13 @@ class Plan:
     def _conv_wgrad(self, stream, ws, d, x, x2, dz, dw, db):
         return self.lib.clslam_conv_wgrad(ctypes.byref(d), x, x2, dz, dw, db, ws, self.ws_bytes, stream)
 
+    def conv_wgrad_tma(self, name, n, h, w, x_pl: L.Planes, pad_mode: int, dz_pl: L.Planes, dz, dw, db) -> None:
+        """tcgen05 wgrad with TMA-fed MN-major operands (clslam_wgrad3x3_tma)"""
+        self.need_ws(self.lib.clslam_wgrad3x3_tma_workspace_bytes(n, h, w, x_pl.c, dz_pl.c))
+        self.add(name, lambda stream, ws, xp, dp, *a: self.lib.clslam_wgrad3x3_tma(ctypes.byref(xp), pad_mode, ctypes.byref(dp), *a, ws,
+                                                                                   self.ws_bytes, stream),
+                 x_pl, dz_pl, _p(dz), _p(dw), _p(db))
+
     def planes_from_f32(self, name, x, out: L.Planes) -> None:
         self.add(name, lambda stream, ws, xp, o: self.lib.clslam_planes_from_f32(xp, ctypes.byref(o), 1, 0, stream), _p(x), out)
 
@@ -432,6 +439,7 @@ class AdaptEngine:
         self.y = {}          # decoder activations (ELU outputs), NHWC fp32 (dispconv, backward)
         self.disp = {}
         self.dec_desc = {}
+        self.dec_in_pl = {}   # input planes of the decoder convolutions (TMA forward + wgrad)
         x, x_pl = feats[4], feat4_pl
         plan.wait('wsplit')
         for i in range(4, -1, -1):
@@ -447,6 +455,8 @@ class AdaptEngine:
                 plan.conv_fwd(f'upconv_{i}_0', d0, x, None, flat.weight_ptr(key0), None, flat.bias_ptr(key0), None, y0,
                               flat.weight_hi_ptr(key0), flat.weight_lo_ptr(key0), out=y0_up, out_up=2, out_halo=1)
             self.y[(i, 0)] = y0; self.dec_desc[(i, 0)] = (d0, x)
+            self.dec_in_pl[(i, 0)] = x_pl if u0[i] else None
+            self.dec_in_pl[(i, 1)] = cat[i].view() if cat[i] is not None else None
             if i > 0:
                 skip = feats[i - 1]
                 ho_, wo_ = skip.shape[1], skip.shape[2]
@@ -492,6 +502,7 @@ class AdaptEngine:
         self.pose_desc = {}
         x = pf4
         plan.wait('wsplit')
+        self.pose_in_pl = {}
         up = tma_ok(2 * b, hp, wp, 256, 256)          # pose_0 / pose_1 on the TMA kernel (planes chained squeeze -> pose_0 -> pose_1)
         x_pl = None
         for name, co, ci, k, act in (('squeeze', 256, 512, 1, L.ACT_RELU), ('pose_0', 256, 256, 3, L.ACT_RELU),
@@ -506,6 +517,7 @@ class AdaptEngine:
                 plan.conv_fwd(name, d, x, None, flat.weight_ptr((pd, name)), None, flat.bias_ptr((pd, name)), None, yv,
                               flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)), out=out_pl)
             self.pose_act[name] = yv; self.pose_desc[name] = (d, x)
+            self.pose_in_pl[name] = x_pl
             x, x_pl = yv, out_pl
         self.axis_angle = plan.alloc(2, b, 3)
         self.translation = plan.alloc(2, b, 3)
@@ -584,11 +596,13 @@ class AdaptEngine:
         # dgrad on the TMA kernel where the (padded) output grid has enough tiles; dz is then also kept as planes
         ud1 = {i: tma_ok(b, self.y[(i, 1)].shape[1] + 2, self.y[(i, 1)].shape[2] + 2, DEC_CH[i], DEC_CH[i]) for i in range(5)}
         ud0 = {i: tma_ok(b, self.y[(i, 0)].shape[1] + 2, self.y[(i, 0)].shape[2] + 2, DEC_CH[i], DEC_CH[i + 1]) for i in range(4)}
+        ud0[4] = False
+        wg = {k: v is not None for k, v in self.dec_in_pl.items()}       # wgrad on tcgen05 needs the layer input as planes
         dz_pl = {}
         for i in range(5):
-            if ud1[i]:
+            if ud1[i] or wg[(i, 1)]:
                 dz_pl[(i, 1)] = PlaneBuf(plan, b, self.y[(i, 1)].shape[1], self.y[(i, 1)].shape[2], DEC_CH[i]).view()
-            if i < 4 and ud0[i]:
+            if ud0[i] or wg[(i, 0)]:
                 dz_pl[(i, 0)] = PlaneBuf(plan, b, self.y[(i, 0)].shape[1], self.y[(i, 0)].shape[2], DEC_CH[i]).view()
         scratch_elems = max([b * (self.y[(i, 1)].shape[1] + 2) * (self.y[(i, 1)].shape[2] + 2) * DEC_CH[i] for i in range(5) if ud1[i]] +
                             [b * (self.y[(i, 0)].shape[1] + 2) * (self.y[(i, 0)].shape[2] + 2) * DEC_CH[i + 1] for i in range(4) if ud0[i]] + [4])
@@ -608,7 +622,7 @@ class AdaptEngine:
                 plan.simple('dispconv_0.dgrad', lib.clslam_dispconv_dgrad_act, _p(self.dz_disp[0]),
                             flat.weight_ptr((dd, 'dispconv_0.conv')), _p(y1), L.ACT_ELU, _p(self.dz[(0, 1)]), b, hi_, wi_,
                             DEC_CH[0])
-                if ud1[0]:
+                if (0, 1) in dz_pl:
                     plan.planes_from_f32('dz01.planes', self.dz[(0, 1)], dz_pl[(0, 1)])
                 plan.record('dz01')
             # upconv_i_1: wgrad + dgrad (to the up-sampled branch only; the skip feeds a frozen encoder)
@@ -616,9 +630,13 @@ class AdaptEngine:
             key1 = (dd, f'upconv_{i}_1.conv.conv')
             plan.set_lane(2)
             plan.wait(f'dz{i}1')
-            plan.conv_wgrad(f'upconv_{i}_1.wgrad', d1, y0, skip, self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
+            if wg[(i, 1)]:
+                plan.conv_wgrad_tma(f'upconv_{i}_1.wgrad', b, hi_, wi_, self.dec_in_pl[(i, 1)], L.PAD_REFLECT, dz_pl[(i, 1)],
+                                    self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
+            else:
+                plan.conv_wgrad(f'upconv_{i}_1.wgrad', d1, y0, skip, self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
             plan.set_lane(0)
-            nxt = dz_pl.get((i, 0)) if i < 4 else None
+            nxt = dz_pl.get((i, 0))
             if ud1[i]:
                 wt_hi, wt_lo = self._wt_slot(key1, DEC_CH[i])
                 plan.conv_tma(f'upconv_{i}_1.dgrad', dz_pl[(i, 1)], L.PAD_FULL, DEC_CH[i], wt_hi, wt_lo, None, None, L.ACT_NONE, y=dxp)
@@ -635,7 +653,11 @@ class AdaptEngine:
             key0 = (dd, f'upconv_{i}_0.conv.conv')
             plan.set_lane(2)
             plan.wait(f'dz{i}0')
-            plan.conv_wgrad(f'upconv_{i}_0.wgrad', d0, xin, None, self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
+            if wg[(i, 0)]:
+                plan.conv_wgrad_tma(f'upconv_{i}_0.wgrad', b, self.y[(i, 0)].shape[1], self.y[(i, 0)].shape[2], self.dec_in_pl[(i, 0)],
+                                    L.PAD_REFLECT, dz_pl[(i, 0)], self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
+            else:
+                plan.conv_wgrad(f'upconv_{i}_0.wgrad', d0, xin, None, self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
             plan.set_lane(0)
             if i < 4:
                 has_disp = (i + 1) < S
@@ -666,8 +688,12 @@ class AdaptEngine:
         dzp_pl = {name: PlaneBuf(plan, 2 * b, hp, wp, 256).view() for name in ('pose_1', 'pose_0')} if upd else {}
         for name in ('pose_2', 'pose_1', 'pose_0', 'squeeze'):
             d, xin = self.pose_desc[name]
-            plan.conv_wgrad(f'{name}.wgrad', d, xin, None, self.dz_pose[name], flat.wgrad_ptr((pd, name)),
-                            flat.bgrad_ptr((pd, name)))
+            if name in dzp_pl and self.pose_in_pl.get(name) is not None:
+                plan.conv_wgrad_tma(f'{name}.wgrad', 2 * b, hp, wp, self.pose_in_pl[name], L.PAD_ZERO, dzp_pl[name], self.dz_pose[name],
+                                    flat.wgrad_ptr((pd, name)), flat.bgrad_ptr((pd, name)))
+            else:
+                plan.conv_wgrad(f'{name}.wgrad', d, xin, None, self.dz_pose[name], flat.wgrad_ptr((pd, name)),
+                                flat.bgrad_ptr((pd, name)))
             if name in prev:
                 if upd and name in ('pose_1', 'pose_0'):
                     wt_hi, wt_lo = self._wt_slot((pd, name), 256)

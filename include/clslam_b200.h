@@ -150,6 +150,13 @@ int clslam_wt_flip(const void* items_dev, int n_items, int max_elems, const void
 int clslam_dgrad_fold(const float* dxp, int n, int h, int w, int c, int up, const float* y_prev, int act_prev,
                       const float* disp_dz, const float* disp_w, float* dz_prev, const clslam_planes* dz_prev_planes,
                       void* stream);
+/* wgrad of a 3x3 / stride-1 layer on tcgen05 with TMA-fed MN-major operands (no transposition): dW [co][3][3][ci] and
+ * db [co] (may be NULL; reduced from the fp32 copy dz_f32 (n, h, w, co)) from the layer input planes `x` (pad_mode ZERO: interior view, REFLECT: stored halo) and the
+ * output-gradient planes `dz` (zero halo), both (n, h, w).  Needs x->c % 16 == 0 and dz->c in {16, 32, 64, 128 * k}
+ * (dz->c == 16 only when x->c % 32 != 0 ... see wg_plan).  Deterministic: per-CTA partials + fixed-order reduction. */
+long long clslam_wgrad3x3_tma_workspace_bytes(int n, int h, int w, int ci, int co);
+int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_planes* dz, const float* dz_f32, float* dw, float* db,
+                        void* workspace, long long workspace_bytes, void* stream);
 /* timing experiments only (results are wrong when != 0): 1 no MMA, 2 no epilogue body, 4 no weight ring, 8 no A loads */
 int clslam_debug_tma_flags(int flags);
 

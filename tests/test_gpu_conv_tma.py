@@ -265,3 +265,41 @@ def test_dgrad_tma_zero_pad_gate():
     L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma(gate)')
     torch.cuda.synchronize()
     assert cabi.rel_err(got, ref) < 1e-4
+
+
+# ---- wgrad on tcgen05 with MN-major operands against the gather wgrad (itself checked against fp64) ----
+WGRAD_CASES = [
+    # n, h, w, ci, co, pad_mode
+    (2, 20, 28, 64, 32, L.PAD_REFLECT),      # ragged tiles, 2 ci chunks
+    (1, 24, 40, 96, 32, L.PAD_REFLECT),      # upconv_1_1 (concat buffer: 3 chunks)
+    (1, 33, 47, 16, 16, L.PAD_REFLECT),      # upconv_0_1 (CC = 16)
+    (1, 48, 64, 32, 16, L.PAD_REFLECT),      # upconv_0_0
+    (1, 24, 32, 128, 64, L.PAD_REFLECT),     # upconv_2_x (CO = 64)
+    (2, 12, 24, 256, 128, L.PAD_REFLECT),    # upconv_3_x (CO = 128: two dz atoms)
+    (4, 6, 20, 256, 256, L.PAD_ZERO),        # pose_0 / pose_1 (two co blocks)
+    (8, 24, 40, 64, 32, L.PAD_REFLECT),      # several tiles per CTA (ring reuse, accumulation across tiles)
+    (3, 64, 96, 16, 16, L.PAD_REFLECT),
+]
+
+
+@pytest.mark.parametrize('case', WGRAD_CASES)
+def test_wgrad3x3_tma(case):
+    lib = cabi.lib()
+    n, h, w, ci, co, pad_mode = case
+    d = cabi.make_desc(n, h, w, ci, co, 3, 1, 1, pad_mode)
+    x = rnd(n, h, w, ci, seed=1).float().cuda()
+    dz = rnd(n, h, w, co, seed=2).float().cuda()
+    dw_ref, db_ref = cabi.conv_wgrad(d, x, None, dz)
+    xb = PlaneBuf(n, h, w, ci + 16, fill=5.0)            # slice of a wider buffer; poisoned halo for the zero-pad case
+    xd = xb.desc(16, ci)
+    L.check(lib.clslam_planes_from_f32(x.data_ptr(), ctypes.byref(xd), 1, 1 if pad_mode == L.PAD_REFLECT else 0, cabi.stream()))
+    dzb, dzd = _planes_of(dz)
+    q = lib.clslam_wgrad3x3_tma_workspace_bytes(n, h, w, ci, co)
+    ws, wp, wb = cabi._ws(q)
+    dw = torch.full((co, 3, 3, ci), float('nan'), device='cuda')
+    db = torch.full((co,), float('nan'), device='cuda')
+    L.check(lib.clslam_wgrad3x3_tma(ctypes.byref(xd), pad_mode, ctypes.byref(dzd), dz.data_ptr(), dw.data_ptr(), db.data_ptr(), wp, wb,
+                                    cabi.stream()), 'wgrad3x3_tma')
+    torch.cuda.synchronize()
+    assert cabi.rel_err(db, db_ref) < 1e-4
+    assert cabi.rel_err(dw, dw_ref) < 1e-4
