@@ -35,7 +35,10 @@ def conv_out(hi: int, k: int, s: int, p: int) -> int:
     return (hi + 2 * p - k) // s + 1
 
 
-TMA_MIN_TILES = 24        # below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: gather kernels
+import os
+
+# below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: gather kernels (split-K) instead
+TMA_MIN_TILES = int(os.environ.get('CLSLAM_TMA_MIN_TILES', '24'))
 
 
 def tma_ok(n: int, h: int, w: int, ci: int, co: int) -> bool:
