@@ -33,7 +33,7 @@ class ConvTma(Structure):
     """clslam_conv_tma"""
     _fields_ = [('inp', Planes), ('pad_mode', c_int), ('cout', c_int), ('w_hi', c_void_p), ('w_lo', c_void_p),
                 ('scale', c_void_p), ('shift', c_void_p), ('act', c_int), ('residual', POINTER(Planes)), ('gate', c_void_p), ('gate_act', c_int), ('y', c_void_p),
-                ('out', POINTER(Planes)), ('out_up', c_int), ('out_halo', c_int)]
+                ('out', POINTER(Planes)), ('out_up', c_int), ('out_halo', c_int), ('taps', c_int)]
 
 
 class PhotoArgs(Structure):
@@ -76,6 +76,7 @@ SIGNATURES = {
                                       c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     'clslam_conv3x3_tma': (c_int, [POINTER(ConvTma), c_void_p]),
     'clslam_debug_tma_flags': (c_int, [c_int]),
+    'clslam_stage_images_s2d': (c_int, [c_void_p, c_void_p, POINTER(Planes), c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_wgrad3x3_tma_workspace_bytes': (c_longlong, [c_int, c_int, c_int, c_int, c_int]),
     'clslam_wgrad3x3_tma': (c_int, [POINTER(Planes), c_int, POINTER(Planes), c_void_p, c_void_p, c_void_p, c_void_p, c_longlong,
                                     c_void_p]),

@@ -21,7 +21,6 @@
 namespace clslam {
 
 constexpr int kTmaTH = 16, kTmaTW = 8;     // output tile
-constexpr int kTmaPH = kTmaTH + 2;         // rows of an A patch
 constexpr int kTmaEpiWarps = 16;          // 4 TMEM lane quarters x 4 column slots (8 accumulator columns per tcgen05.ld)
 constexpr int kTmaThreads = 64 + 32 * kTmaEpiWarps;
 
@@ -38,10 +37,11 @@ __device__ __forceinline__ float act_fast(float v, int act) {
   return act_apply(v, act);
 }
 
-template <int KC, int BN>
+template <int KC, int BN, int T = 3>      // T x T taps (3: the 3x3 layers; 4: conv1 in its space-to-depth form)
 struct TmaConvCfg {
   static constexpr int kRowBytes = KC * 2;
-  static constexpr int kAPlane = kTmaPH * kTmaTW * kRowBytes;
+  static constexpr int kPH = kTmaTH + T - 1;                  // rows of an A patch
+  static constexpr int kAPlane = kPH * kTmaTW * kRowBytes;
   static constexpr int kAStage = 2 * kAPlane;
   static constexpr int kBPlane = BN * kRowBytes;
   static constexpr int kBStage = 2 * kBPlane;
@@ -49,12 +49,12 @@ struct TmaConvCfg {
   // upper 32 bits of every K-major swizzled descriptor of this configuration (SBO = 8 rows, version 1, layout type)
   static constexpr uint32_t kDescHi = (uint32_t)((8 * kRowBytes) >> 4) | (1u << 14) |
                                       ((kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u)) << 29);
-  static_assert(kAStage % 1024 == 0 && kBStage % 1024 == 0, "stage alignment");
+  static_assert(kAStage % (8 * kRowBytes) == 0 && kBStage % (8 * kRowBytes) == 0, "stage alignment (swizzle atom)");
 };
 constexpr int kTmaMaxStages = 8;
 constexpr int kTmaBarBytes = 512;          // 4 x 8 ring barriers + 2 x 2 accumulator barriers + resident-B barrier + TMEM slot
 constexpr int kTmaSmemMax = 232448;
-constexpr int kTmaResidentMax = 112 * 1024;
+constexpr int kTmaResidentMax = 128 * 1024;
 
 struct TmaConvArgs {
   int n_img, ho, wo, cout, cin;
@@ -74,14 +74,14 @@ struct TmaConvArgs {
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
-template <int KC, int BN>
+template <int KC, int BN, int T>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TmaConvArgs g) {
-  using C = TmaConvCfg<KC, BN>;
+  using C = TmaConvCfg<KC, BN, T>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* a_tiles = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* b_tiles = a_tiles + g.na * C::kAStage;
-  const int b_slots = g.nbr > 0 ? g.nbr : g.chunks * 9;
+  const int b_slots = g.nbr > 0 ? g.nbr : g.chunks * T * T;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(b_tiles + (size_t)b_slots * C::kBStage);
   uint64_t* a_empty = a_full + kTmaMaxStages;
   uint64_t* b_full = a_empty + kTmaMaxStages;
@@ -109,16 +109,16 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   const int tiles_per_img = g.tiles_x * g.tiles_y;
   const int total = g.n_img * tiles_per_img * g.n_blocks;
-  const int n_cs = g.chunks * 3;
+  const int n_cs = g.chunks * T;
 
   if (warp == 0) {
     // ===================== TMA producer (one thread) =====================
     if (lane == 0) {
-      if (g.nbr == 0) {       // resident weights: every (chunk, s, r) tile once, slot = (chunk * 3 + s) * 3 + r
+      if (g.nbr == 0) {       // resident weights: every (chunk, s, r) tile once, slot = (chunk * T + s) * T + r
         mbar_arrive_expect_tx(b_res, (uint32_t)(b_slots * C::kBStage));
         for (int slot = 0; slot < b_slots; ++slot) {
-          const int r = slot % 3, cs = slot / 3, sft = cs % 3, chunk = cs / 3;
-          tma_load_3d(b_tiles + (size_t)slot * C::kBStage, &map_b, b_res, (r * 3 + sft) * g.cin + chunk * KC, 0, 0);
+          const int r = slot % T, cs = slot / T, sft = cs % T, chunk = cs / T;
+          tma_load_3d(b_tiles + (size_t)slot * C::kBStage, &map_b, b_res, (r * T + sft) * g.cin + chunk * KC, 0, 0);
         }
       }
       int sa = 0, pa = 0, sb = 0, pb = 0;
@@ -128,7 +128,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int oh0 = (rem / g.tiles_x) * kTmaTH + g.org, ow0 = (rem % g.tiles_x) * kTmaTW + g.org;
         const int n0 = nb * BN;
         for (int chunk = 0; chunk < g.chunks; ++chunk) {
-          for (int sft = 0; sft < 3; ++sft) {
+          for (int sft = 0; sft < T; ++sft) {
             if (!(g.debug & 8)) {
               mbar_wait(&a_empty[sa], (uint32_t)(pa ^ 1));
               mbar_arrive_expect_tx(&a_full[sa], C::kAStage);
@@ -136,10 +136,10 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               if (++sa == g.na) { sa = 0; pa ^= 1; }
             }
             if (g.nbr > 0 && !(g.debug & 4)) {
-              for (int r = 0; r < 3; ++r) {
+              for (int r = 0; r < T; ++r) {
                 mbar_wait(&b_empty[sb], (uint32_t)(pb ^ 1));
                 mbar_arrive_expect_tx(&b_full[sb], C::kBStage);
-                tma_load_3d(b_tiles + sb * C::kBStage, &map_b, &b_full[sb], (r * 3 + sft) * g.cin + chunk * KC, n0, 0);
+                tma_load_3d(b_tiles + sb * C::kBStage, &map_b, &b_full[sb], (r * T + sft) * g.cin + chunk * KC, n0, 0);
                 if (++sb == g.nbr) { sb = 0; pb ^= 1; }
               }
             }
@@ -167,10 +167,10 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (!(g.debug & 8)) { mbar_wait(&a_full[sa], (uint32_t)pa); tc_fence_after(); }
           const uint32_t a_st = a_ring + (uint32_t)(sa * (C::kAStage >> 4));
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
+          for (int r = 0; r < T; ++r) {
             uint32_t b_st;
             if (resident || (g.debug & 4)) {
-              b_st = b_ring + (uint32_t)(resident ? (cs * 3 + r) * (C::kBStage >> 4) : 0);
+              b_st = b_ring + (uint32_t)(resident ? (cs * T + r) * (C::kBStage >> 4) : 0);
             } else {
               mbar_wait(&b_full[sb], (uint32_t)pb);
               tc_fence_after();
@@ -312,6 +312,40 @@ planes_from_f32_kernel(const float* __restrict__ x, PlaneView out, int n, int h,
   }
 }
 
+// ---- conv1 in space-to-depth form --------------------------------------------------------------------
+// (x - 0.45) / 0.225 (networks/resnet_encoder.py:117) of one or two NCHW images, 2x2 space-to-depth, channel padding
+// 3 -> 4 per image, written as planes: channel (p * 2 + q) * cp + c of S2D pixel (y, x) = image pixel (2y + p, 2x + q).
+// A 7x7 / stride-2 / pad-3 convolution of the image is the 4x4 (rows o-2 .. o+1) stride-1 convolution of this tensor.
+__global__ void __launch_bounds__(256)
+stage_s2d_kernel(const float* __restrict__ a, const float* __restrict__ b, PlaneView out, int n, int h, int w, int img0) {
+  const int h2 = h / 2, w2 = w / 2, cp = b ? 8 : 4;
+  const size_t total = (size_t)n * h2 * w2 * 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int pq = (int)(i & 3);
+    size_t t = i >> 2;
+    const int x2 = (int)(t % w2); t /= w2;
+    const int y2 = (int)(t % h2);
+    const int img = (int)(t / h2);
+    const size_t hw = (size_t)h * w;
+    const size_t px = (size_t)(2 * y2 + (pq >> 1)) * w + 2 * x2 + (pq & 1);
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = 0.f;
+    const float* pa = a + (size_t)img * 3 * hw + px;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = (ld1(pa + c * hw) - 0.45f) / 0.225f;
+    if (b) {
+      const float* pb = b + (size_t)img * 3 * hw + px;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[3 + c] = (ld1(pb + c * hw) - 0.45f) / 0.225f;
+      planes_emit<8>(out, img0 + img, y2, x2, pq * cp, v);
+    } else {
+      const float v4[4] = {v[0], v[1], v[2], v[3]};
+      planes_emit<4>(out, img0 + img, y2, x2, pq * cp, v4);
+    }
+  }
+}
+
 // ---- dgrad helpers ---------------------------------------------------------------------------------
 // Wt[ci'][2 - r][2 - s][co] = W[co][r][s][ci'] for ci' < n_ci, on both bf16 planes (a pure permutation): the weights
 // of the convolution that computes dX from dZ (taps flipped, channels transposed)
@@ -422,10 +456,10 @@ static int tma_num_sms() {
   return g_tma_sms;
 }
 
-template <int KC, int BN>
+template <int KC, int BN, int T>
 static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConvArgs g, cudaStream_t st) {
-  using C = TmaConvCfg<KC, BN>;
-  auto kern = conv3x3_tma_kernel<KC, BN>;
+  using C = TmaConvCfg<KC, BN, T>;
+  auto kern = conv3x3_tma_kernel<KC, BN, T>;
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemMax);
@@ -434,7 +468,7 @@ static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConv
   }
   // shared-memory plan: weights resident when the whole tensor fits next to >= 3 A stages, else a B ring
   const int budget = kTmaSmemMax - 1024 - kTmaBarBytes;
-  const long long w_bytes = (long long)g.chunks * 9 * C::kBStage;
+  const long long w_bytes = (long long)g.chunks * T * T * C::kBStage;
   long long b_bytes;
   if (g.n_blocks == 1 && w_bytes <= kTmaResidentMax && budget - w_bytes >= 3LL * C::kAStage) {
     g.nbr = 0; b_bytes = w_bytes;
@@ -474,6 +508,9 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   const int cin = in.c, cout = p->cout;
   if (cin % 16 || cout % 16 || !p->w_hi || !p->w_lo) { set_error("conv3x3_tma: cin %% 16, cout %% 16, weights"); return -1; }
   if (p->pad_mode < 0 || p->pad_mode > 2) { set_error("conv3x3_tma: pad_mode"); return -1; }
+  const int taps = p->taps == 4 ? 4 : 3;
+  if (p->taps != 0 && p->taps != 3 && p->taps != 4) { set_error("conv3x3_tma: taps must be 3 or 4"); return -1; }
+  if (taps == 4 && p->pad_mode != CLSLAM_PAD_ZERO) { set_error("conv3x3_tma: the 4x4 form is zero padded"); return -1; }
   if (int rc = get_encoder()) return rc;
   const int kc = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16);
   const int bn = cout >= 128 ? 128 : (cout >= 64 ? 64 : (cout >= 32 ? 32 : 16));
@@ -508,30 +545,51 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   const int hp = in.h + 2, wp = in.w + 2;
   const bool padded_view = p->pad_mode == CLSLAM_PAD_REFLECT;
   __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(in.base) + in.c_off + (padded_view ? 0 : ((size_t)wp + 1) * in.c_total);
-  g.org = padded_view ? 0 : (full ? -2 : -1);
+  g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : -1);      // 4x4: input rows o - 2 .. o + 1
   const cuuint64_t adims[5] = {(cuuint64_t)cin, (cuuint64_t)(padded_view ? wp : in.w), (cuuint64_t)(padded_view ? hp : in.h),
                                (cuuint64_t)in.n, 2};
   const cuuint64_t astr[4] = {(cuuint64_t)in.c_total * 2, (cuuint64_t)wp * in.c_total * 2, (cuuint64_t)hp * wp * in.c_total * 2,
                               (cuuint64_t)in.plane_stride * 2};
-  const cuuint32_t abox[5] = {(cuuint32_t)kc, kTmaTW, kTmaPH, 1, 2};
+  const cuuint32_t abox[5] = {(cuuint32_t)kc, kTmaTW, (cuuint32_t)(kTmaTH + taps - 1), 1, 2};
   CUtensorMap ma, mb;
   if (int rc = encode(&ma, abase, 5, adims, astr, abox, kc * 2, "A")) return rc;
   // B: 3-D map (k, cout, plane); the lo plane must follow the hi plane in memory (one [2][...] allocation)
   const long long wdiff = reinterpret_cast<const char*>(p->w_lo) - reinterpret_cast<const char*>(p->w_hi);
   if (wdiff <= 0 || (wdiff & 15)) { set_error("conv3x3_tma: w_lo must follow w_hi (16-byte aligned distance)"); return -1; }
-  const cuuint64_t bdims[3] = {(cuuint64_t)9 * cin, (cuuint64_t)cout, 2};
-  const cuuint64_t bstr[2] = {(cuuint64_t)9 * cin * 2, (cuuint64_t)wdiff};
+  const cuuint64_t bdims[3] = {(cuuint64_t)taps * taps * cin, (cuuint64_t)cout, 2};
+  const cuuint64_t bstr[2] = {(cuuint64_t)taps * taps * cin * 2, (cuuint64_t)wdiff};
   const cuuint32_t bbox[3] = {(cuuint32_t)kc, (cuuint32_t)bn, 2};
   if (int rc = encode(&mb, const_cast<void*>(p->w_hi), 3, bdims, bstr, bbox, kc * 2, "B")) return rc;
 
   cudaStream_t st = as_stream(stream);
-#define CLSLAM_TMA_CASE(KC_, BN_) if (kc == KC_ && bn == BN_) return launch_tma_conv<KC_, BN_>(ma, mb, g, st);
+  if (taps == 4) {
+    if (kc == 16 && bn == 64) return launch_tma_conv<16, 64, 4>(ma, mb, g, st);
+    if (kc == 32 && bn == 64) return launch_tma_conv<32, 64, 4>(ma, mb, g, st);
+    set_error("conv3x3_tma: the 4x4 form is built for 16 / 32 input channels and 64 output channels");
+    return -1;
+  }
+#define CLSLAM_TMA_CASE(KC_, BN_) if (kc == KC_ && bn == BN_) return launch_tma_conv<KC_, BN_, 3>(ma, mb, g, st);
   CLSLAM_TMA_CASE(64, 128) CLSLAM_TMA_CASE(64, 64) CLSLAM_TMA_CASE(64, 32) CLSLAM_TMA_CASE(64, 16)
   CLSLAM_TMA_CASE(32, 128) CLSLAM_TMA_CASE(32, 64) CLSLAM_TMA_CASE(32, 32) CLSLAM_TMA_CASE(32, 16)
   CLSLAM_TMA_CASE(16, 64) CLSLAM_TMA_CASE(16, 32) CLSLAM_TMA_CASE(16, 16)
 #undef CLSLAM_TMA_CASE
   set_error("conv3x3_tma: no kernel for channel chunk %d / N block %d", kc, bn);
   return -1;
+}
+
+int clslam_stage_images_s2d(const float* img_a, const float* img_b, const clslam_planes* out, int image_offset, int n, int h, int w,
+                            void* stream) {
+  if (int rc = check_planes(out, "stage_images_s2d")) return rc;
+  const int cs = img_b ? 32 : 16;
+  if (h % 2 || w % 2 || out->h != h / 2 || out->w != w / 2 || out->c != cs || image_offset < 0 || image_offset + n > out->n) {
+    set_error("stage_images_s2d: output planes must be (>= %d, %d, %d, %d)", image_offset + n, h / 2, w / 2, cs); return -1;
+  }
+  const PlaneView v = make_plane_view(out, 1, 0);
+  const size_t total = (size_t)n * (h / 2) * (w / 2) * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  stage_s2d_kernel<<<blocks, 256, 0, as_stream(stream)>>>(img_a, img_b, v, n, h, w, image_offset);
+  return finish_launch("stage_images_s2d");
 }
 
 int clslam_wt_flip(const void* items_dev, int n_items, int max_elems, const void* w_hi, long long w_plane_stride, void* wt_hi,

@@ -548,11 +548,9 @@ class _PoseRunner:
         lib = plan.lib
         self.img0 = plan.alloc(n, 3, h, w)
         self.img1 = plan.alloc(n, 3, h, w)
-        staged = plan.alloc(2 * n, h, w, prep.cin_pad)
-        for half in (0, 1):
-            plan.simple(f'stage{half}', lib.clslam_stage_images, _p(self.img0), _p(self.img1),
-                        _p(staged[half * n:(half + 1) * n]), n, h, w, prep.cin_pad)
-        f4 = build_encoder(plan, prep, staged, 2 * n, h, w, 'pose_enc')[4]
+        from .engine import stage_for_encoder
+        staged, s2d = stage_for_encoder(plan, prep, 'stage', [(self.img0, self.img1, 0, n), (self.img0, self.img1, n, n)], 2 * n, h, w)
+        f4 = build_encoder(plan, prep, staged, 2 * n, h, w, 'pose_enc', x_s2d=s2d)[4]
         hp, wp = f4.shape[1], f4.shape[2]
         x = f4
         for name, co, ci, k, act in (('squeeze', 256, 512, 1, L.ACT_RELU), ('pose_0', 256, 256, 3, L.ACT_RELU),

@@ -96,7 +96,21 @@ class PreparedEncoder:
             self.t[name + '.scale'] = scale.to(device).contiguous()
             self.t[name + '.shift'] = shift.to(device).contiguous()
 
+        def put_conv1_s2d(conv):
+            """conv1 (7x7 / s2 / p3) as a 4x4 convolution over the 2x2 space-to-depth input:
+            W'[co][r][s][(p, q, c)] = W[co][c][2r + p - 1][2s + q - 1] (zero outside the 7x7 window)"""
+            w = conv.weight.detach().to(device=device, dtype=torch.float32)
+            co, ci = w.shape[0], w.shape[1]
+            wp = w.new_zeros(co, self.cin_pad, 8, 8)
+            wp[:, :ci, 1:, 1:] = w
+            wk = wp.view(co, self.cin_pad, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(co, 4, 4, 4 * self.cin_pad)
+            hl = torch.empty(2, *wk.shape, dtype=torch.bfloat16, device=device)
+            hl[0] = wk.to(torch.bfloat16)
+            hl[1] = (wk - hl[0].float()).to(torch.bfloat16)
+            self.t['conv1.s2d_hl'] = hl
+
         with torch.no_grad():
+            put_conv1_s2d(r.conv1)
             put_conv('conv1', r.conv1, self.cin_pad)
             put_bn('bn1', r.bn1)
             for li in range(1, 5):
@@ -194,7 +208,7 @@ class Plan:
 
     def conv_tma(self, name, inp: L.Planes, pad_mode: int, cout: int, w_hi, w_lo, scale, shift, act: int,
                  res: Optional[L.Planes] = None, y=None, out: Optional[L.Planes] = None, out_up: int = 1,
-                 out_halo: int = 0, gate=None, gate_act: int = L.ACT_NONE) -> None:
+                 out_halo: int = 0, gate=None, gate_act: int = L.ACT_NONE, taps: int = 3) -> None:
         """TMA-fed tcgen05 3x3 / stride-1 convolution over planes (clslam_conv3x3_tma)"""
         a = L.ConvTma()
         a.inp = inp
@@ -207,7 +221,7 @@ class Plan:
         a.gate, a.gate_act = _p(gate), gate_act
         if out is not None:
             a.out = ctypes.pointer(out)
-        a.out_up, a.out_halo = out_up, out_halo
+        a.out_up, a.out_halo, a.taps = out_up, out_halo, taps
         self.keep.append(a)
         self.ops.append((name, lambda stream, ws, arg: self.lib.clslam_conv3x3_tma(ctypes.byref(arg), stream), (a,), self.lane))
 
@@ -278,9 +292,13 @@ class Plan:
                 L.check(rc, name)
 
 
-def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: torch.Tensor, n: int, h: int, w: int, tag: str,
+def conv1_s2d_ok(n: int, h: int, w: int, cin_pad: int) -> bool:
+    return h % 2 == 0 and w % 2 == 0 and tma_ok(n, h // 2, w // 2, 4 * cin_pad, 64)
+
+
+def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Tensor], n: int, h: int, w: int, tag: str,
                   skips: Optional[Dict[int, L.Planes]] = None, feat4_planes: Optional[L.Planes] = None,
-                  ) -> List[torch.Tensor]:
+                  x_s2d: Optional[L.Planes] = None) -> List[torch.Tensor]:
     """ResNet-18 trunk (networks/resnet_encoder.py:115-125) over an NHWC staged input; returns the
     five fp32 NHWC feature maps.  3x3 / stride-1 convolutions run the TMA kernel on bf16 hi/lo planes
     (intermediate activations then exist only as planes); conv1, the stride-2 convolutions and the 1x1
@@ -291,8 +309,13 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: torch.Tensor, n: 
     feats = []
     d = plan.desc(n, h, w, prep.cin_pad, 64, 7, 2, 3, act=L.ACT_RELU)
     f0 = plan.alloc(n, d.ho, d.wo, 64)
-    plan.conv_fwd(f'{tag}.conv1', d, x_staged, None, t['conv1.w'], t['bn1.scale'], t['bn1.shift'], None, f0,
-                  t['conv1.w_hi'], t['conv1.w_lo'], out=skips.get(0), out_halo=1)
+    if x_s2d is not None:       # conv1 on the TMA kernel: 4x4 taps over the space-to-depth planes
+        hl = t['conv1.s2d_hl']
+        plan.conv_tma(f'{tag}.conv1', x_s2d, L.PAD_ZERO, 64, hl[0], hl[1], t['bn1.scale'], t['bn1.shift'], L.ACT_RELU, y=f0,
+                      out=skips.get(0), out_halo=1, taps=4)
+    else:
+        plan.conv_fwd(f'{tag}.conv1', d, x_staged, None, t['conv1.w'], t['bn1.scale'], t['bn1.shift'], None, f0,
+                      t['conv1.w_hi'], t['conv1.w_lo'], out=skips.get(0), out_halo=1)
     feats.append(f0)
     hp, wp = conv_out(d.ho, 3, 2, 1), conv_out(d.wo, 3, 2, 1)
     hc, wc, cin = hp, wp, 64
@@ -348,6 +371,22 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: torch.Tensor, n: 
     return feats
 
 
+def stage_for_encoder(plan: Plan, prep: PreparedEncoder, name: str, pairs, n: int, h: int, w: int):
+    """input staging of an encoder over `n` images given as [(img_a, img_b | None, first image, count)]:
+    returns (x_staged fp32 NHWC | None, x_s2d planes | None) -- the latter when conv1 runs on the TMA kernel"""
+    lib = plan.lib
+    if conv1_s2d_ok(n, h, w, prep.cin_pad):
+        buf = PlaneBuf(plan, n, h // 2, w // 2, 4 * prep.cin_pad).view()
+        for k, (a, b2, first, cnt) in enumerate(pairs):
+            plan.add(f'{name}{k}', lambda stream, ws, pa, pb, o, f, c: lib.clslam_stage_images_s2d(pa, pb, ctypes.byref(o), f, c, h, w, stream),
+                     _p(a), _p(b2), buf, first, cnt)
+        return None, buf
+    staged = plan.alloc(n, h, w, prep.cin_pad)
+    for k, (a, b2, first, cnt) in enumerate(pairs):
+        plan.simple(f'{name}{k}', lib.clslam_stage_images, _p(a), _p(b2), _p(staged[first:first + cnt]), cnt, h, w, prep.cin_pad)
+    return staged, None
+
+
 class EncoderRunner:
     """Encoder-only forward for callers that use ``models['depth_encoder'](image)`` directly
     (slam/slam.py:143-147) and for predict_pose (depth_pose_prediction.py:628-664)."""
@@ -358,10 +397,8 @@ class EncoderRunner:
         self.two = enc.num_input_images == 2
         self.img_a = self.plan.alloc(n, 3, h, w)
         self.img_b = self.plan.alloc(n, 3, h, w) if self.two else None
-        self.staged = self.plan.alloc(n, h, w, prep.cin_pad)
-        self.plan.simple('stage', self.plan.lib.clslam_stage_images, _p(self.img_a), _p(self.img_b), _p(self.staged), n, h,
-                         w, prep.cin_pad)
-        self.feats = build_encoder(self.plan, prep, self.staged, n, h, w, 'enc')
+        self.staged, s2d = stage_for_encoder(self.plan, prep, 'stage', [(self.img_a, self.img_b, 0, n)], n, h, w)
+        self.feats = build_encoder(self.plan, prep, self.staged, n, h, w, 'enc', x_s2d=s2d)
         self.plan.finalize()
         self.prep = prep
 
@@ -419,9 +456,7 @@ class AdaptEngine:
         plan.add('wt_flip', lambda stream, ws: self._run_wt_flip(stream))
         plan.record('wsplit')
         plan.set_lane(0)
-        self.depth_in = plan.alloc(b, h, w, depth_prep.cin_pad)
-        plan.simple('depth.stage', lib.clslam_stage_images, _p(self.rgb_aug[1]), None, _p(self.depth_in), b, h, w,
-                    depth_prep.cin_pad)
+        self.depth_in, depth_s2d = stage_for_encoder(plan, depth_prep, 'depth.stage', [(self.rgb_aug[1], None, 0, b)], b, h, w)
         # decoder geometry first: which layers run the TMA kernel decides where the encoder writes its skip features
         # (planes inside the decoder's concat buffers: torch.cat of depth_decoder.py:66 without a copy)
         fh = [h >> (k + 1) for k in range(5)]
@@ -436,7 +471,8 @@ class AdaptEngine:
             cat[i] = PlaneBuf(plan, b, 2 * hi_, 2 * wi_, DEC_CH[i] + c2) if u1[i] else None
         skips = {i - 1: cat[i].view(DEC_CH[i], ENC_CH[i - 1]) for i in range(1, 5) if cat[i] is not None}
         feat4_pl = PlaneBuf(plan, b, fh[4], fw[4], ENC_CH[4]).view() if u0[4] else None
-        feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc', skips=skips, feat4_planes=feat4_pl)
+        feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc', skips=skips, feat4_planes=feat4_pl,
+                              x_s2d=depth_s2d)
         self.depth_feats = feats
         dd = 'depth_decoder'
         self.y = {}          # decoder activations (ELU outputs), NHWC fp32 (dispconv, backward)
@@ -490,13 +526,10 @@ class AdaptEngine:
 
         # ---- pose network (both passes batched: [frame -1 | frame +1]) ------------------------
         plan.set_lane(1)
-        self.pose_in = plan.alloc(2 * b, h, w, pose_prep.cin_pad)
         # temporal order (depth_pose_prediction.py:951-955): (-1, 0) and (0, +1)
-        plan.simple('pose.stage0', lib.clslam_stage_images, _p(self.rgb_aug[0]), _p(self.rgb_aug[1]), _p(self.pose_in[:b]),
-                    b, h, w, pose_prep.cin_pad)
-        plan.simple('pose.stage1', lib.clslam_stage_images, _p(self.rgb_aug[1]), _p(self.rgb_aug[2]), _p(self.pose_in[b:]),
-                    b, h, w, pose_prep.cin_pad)
-        pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc')
+        self.pose_in, pose_s2d = stage_for_encoder(plan, pose_prep, 'pose.stage', [(self.rgb_aug[0], self.rgb_aug[1], 0, b),
+                                                                                  (self.rgb_aug[1], self.rgb_aug[2], b, b)], 2 * b, h, w)
+        pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc', x_s2d=pose_s2d)
         pf4 = pfeats[4]
         hp, wp = pf4.shape[1], pf4.shape[2]
         self.pose_hw = (hp, wp)

@@ -135,6 +135,8 @@ typedef struct clslam_conv_tma {
   const clslam_planes* out;       /* optional */
   int out_up;              /* 1 or 2 (nearest up-sampling on write) */
   int out_halo;            /* write the reflection halo of `out` */
+  int taps;                /* 0 / 3: 3x3.  4: 4x4 kernel over input rows / cols o-2 .. o+1, zero padded, weights [cout][4][4][in.c]
+                              (the space-to-depth form of the encoders' 7x7 / stride-2 conv1, clslam_stage_images_s2d) */
 } clslam_conv_tma;
 int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
 /* dgrad of the 3x3 decoder convolutions on the same kernel (autograd of depth_pose_prediction.py:312):
@@ -160,6 +162,12 @@ int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_plane
 /* timing experiments only (results are wrong when != 0): 1 no MMA, 2 no epilogue body, 4 no weight ring, 8 no A loads */
 int clslam_debug_tma_flags(int flags);
 
+/* Input staging for conv1 on the TMA kernel: (x - 0.45) / 0.225 (networks/resnet_encoder.py:117), channel concat of
+ * img_b (pose net) and 2x2 space-to-depth, written as planes (n, h/2, w/2, 16 | 32): channel (p*2 + q) * cp + c of
+ * S2D pixel (y, x) is image pixel (2y + p, 2x + q), cp = 4 (one image) or 8 (two).  Images go to planes image
+ * `image_offset` .. + n. */
+int clslam_stage_images_s2d(const float* img_a, const float* img_b, const clslam_planes* out, int image_offset, int n, int h, int w,
+                            void* stream);
 /* clslam_conv_fwd_bf16w / clslam_maxpool3x3s2 that additionally emit their result as planes */
 int clslam_conv_fwd_emit(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
                          const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,

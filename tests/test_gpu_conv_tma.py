@@ -303,3 +303,37 @@ def test_wgrad3x3_tma(case):
     torch.cuda.synchronize()
     assert cabi.rel_err(db, db_ref) < 1e-4
     assert cabi.rel_err(dw, dw_ref) < 1e-4
+
+
+@pytest.mark.parametrize('two', [False, True])
+def test_conv1_space_to_depth(two):
+    """encoder conv1 (7x7 / stride 2 / pad 3 on the normalised image) as the 4x4 TMA convolution of the S2D planes"""
+    lib = cabi.lib()
+    n, h, w = 2, 64, 96
+    ci = 6 if two else 3
+    cp = 8 if two else 4
+    img_a = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(1))
+    img_b = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(2)) if two else None
+    wt = rnd(64, ci, 7, 7, seed=3, scale=(ci * 49) ** -0.5)
+    scale, shift = 1 + 0.2 * rnd(64, seed=4), 0.1 * rnd(64, seed=5)
+    x = torch.cat([img_a] + ([img_b] if two else []), 1).double()
+    ref = F.relu(F.conv2d((x - 0.45) / 0.225, wt, None, 2, 3) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    # S2D planes
+    buf = PlaneBuf(n, h // 2, w // 2, 4 * cp)
+    bd = buf.desc()
+    a_g = img_a.cuda()
+    b_g = img_b.cuda() if two else None
+    L.check(lib.clslam_stage_images_s2d(a_g.data_ptr(), cabi.P(b_g), ctypes.byref(bd), 0, n, h, w, cabi.stream()), 'stage_s2d')
+    # weights W'[co][r][s][(p, q, c)] = W[co][c][2r + p - 1][2s + q - 1]
+    wp = torch.zeros(64, cp, 8, 8, dtype=torch.float64)
+    wp[:, :ci, 1:, 1:] = wt
+    wk = wp.view(64, cp, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(64, 4, 4, 4 * cp)
+    hi, lo = cabi.split_bf16(wk.float().cuda())
+    y = torch.full((n, h // 2, w // 2, 64), float('nan'), device='cuda')
+    sc, sh = scale.float().cuda(), shift.float().cuda()
+    a = L.ConvTma()
+    a.inp = bd; a.pad_mode = L.PAD_ZERO; a.cout = 64; a.w_hi = hi.data_ptr(); a.w_lo = lo.data_ptr()
+    a.scale = sc.data_ptr(); a.shift = sh.data_ptr(); a.act = L.ACT_RELU; a.y = y.data_ptr(); a.out_up = 1; a.taps = 4
+    L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv1 s2d')
+    torch.cuda.synchronize()
+    assert cabi.rel_err(cabi.nchw(y), ref) < TOL
