@@ -45,14 +45,15 @@ struct TmaConvCfg {
   static constexpr int kAStage = 2 * kAPlane;
   static constexpr int kBPlane = BN * kRowBytes;
   static constexpr int kBStage = 2 * kBPlane;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;
+  static constexpr int kAcc = BN <= 64 ? 4 : 2;               // accumulator stages in TMEM (thin layers: the hand-off latency dominates)
+  static constexpr int kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
   // upper 32 bits of every K-major swizzled descriptor of this configuration (SBO = 8 rows, version 1, layout type)
   static constexpr uint32_t kDescHi = (uint32_t)((8 * kRowBytes) >> 4) | (1u << 14) |
                                       ((kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u)) << 29);
   static_assert(kAStage % (8 * kRowBytes) == 0 && kBStage % (8 * kRowBytes) == 0, "stage alignment (swizzle atom)");
 };
 constexpr int kTmaMaxStages = 8;
-constexpr int kTmaBarBytes = 512;          // 4 x 8 ring barriers + 2 x 2 accumulator barriers + resident-B barrier + TMEM slot
+constexpr int kTmaBarBytes = 512;          // 4 x 8 ring barriers + 2 x 4 accumulator barriers + resident-B barrier + TMEM slot
 constexpr int kTmaSmemMax = 232448;
 constexpr int kTmaResidentMax = 128 * 1024;
 
@@ -87,8 +88,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* b_full = a_empty + kTmaMaxStages;
   uint64_t* b_empty = b_full + kTmaMaxStages;
   uint64_t* t_full = b_empty + kTmaMaxStages;
-  uint64_t* t_empty = t_full + 2;
-  uint64_t* b_res = t_empty + 2;
+  uint64_t* t_empty = t_full + 4;
+  uint64_t* b_res = t_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -96,7 +97,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int i = 0; i < kTmaMaxStages; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kTmaEpiWarps); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kTmaEpiWarps); }
     mbar_init(b_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -158,8 +159,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       if (resident) { mbar_wait(b_res, 0); tc_fence_after(); }
       int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int as = it & 1;
-        mbar_wait(&t_empty[as], (uint32_t)(((it >> 1) & 1) ^ 1));      // the epilogue has drained this accumulator
+        const int as = it % C::kAcc;
+        mbar_wait(&t_empty[as], (uint32_t)(((it / C::kAcc) & 1) ^ 1));      // the epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t accumulate = 0;
@@ -209,7 +210,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int l = q * 32 + lane;
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int as = it & 1;
+      const int as = it % C::kAcc;
       const int nb = t % g.n_blocks, mt = t / g.n_blocks;
       const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
       const int oh = (rem / g.tiles_x) * kTmaTH + (l >> 3), ow = (rem % g.tiles_x) * kTmaTW + (l & 7);
@@ -222,7 +223,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         plane_coords(ow, g.out.w_lo, g.out.up, g.out.halo, cols);
       }
       const size_t res_off = g.res.base ? (((size_t)img * g.res.hp + oh + 1) * g.res.wp + ow + 1) * g.res.c_total : 0;
-      if (lane == 0) mbar_wait(&t_full[as], (uint32_t)((it >> 1) & 1));      // one poller per warp
+      if (lane == 0) mbar_wait(&t_full[as], (uint32_t)((it / C::kAcc) & 1));      // one poller per warp
       __syncwarp();
       tc_fence_after();
 #pragma unroll 1

@@ -412,19 +412,15 @@ photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
 }
 
 // ---- transpose of the bilinear up-sampling + smoothness terms + sigmoid' -------------------
-// scale 0 is the identity; for s >= 1 one warp gathers the (3f x 3f) window of a low-res pixel
+// scale 0 is the identity; for s >= 1 (f = 2^s) one thread owns one low-res pixel and walks the 2f x 2f full-res
+// window whose bilinear taps (align_corners = False) touch it: rows f*r - f/2 .. f*r + 3f/2 - 1 (clipped)
 __global__ void __launch_bounds__(256)
 disp_grad_kernel(const float* __restrict__ ddisp_full, const float* __restrict__ disp, const float* __restrict__ smooth_grad,
                  int b_global, int has_sample0, int b, int h, int w, int scale, float* __restrict__ dz) {
   const int hs = h >> scale, ws = w >> scale;
   const int f = 1 << scale;
   const size_t total = (size_t)b * hs * ws;
-  const int lane = threadIdx.x & 31;
-  const size_t gthread = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t gstride = (size_t)gridDim.x * blockDim.x;
-  const size_t first = scale == 0 ? gthread : (gthread >> 5);
-  const size_t step = scale == 0 ? gstride : (gstride >> 5);
-  for (size_t i = first; i < total; i += step) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int j = (int)(i % ws);
     const int r = (int)((i / ws) % hs);
     const int bb = (int)(i / ((size_t)ws * hs));
@@ -433,20 +429,20 @@ disp_grad_kernel(const float* __restrict__ ddisp_full, const float* __restrict__
     if (scale == 0) {
       g = src[(size_t)r * w + j];
     } else {
-      const int y_lo = max(0, f * (r - 1)), y_hi = min(h, f * (r + 2));
-      const int x_lo = max(0, f * (j - 1)), x_hi = min(w, f * (j + 2));
-      const int ww = x_hi - x_lo, n_win = (y_hi - y_lo) * ww;
-      for (int e = lane; e < n_win; e += 32) {
-        const int y = y_lo + e / ww, x = x_lo + e % ww;
+      const int y_lo = max(0, f * r - f / 2), y_hi = min(h, f * r + 3 * f / 2);
+      const int x_lo = max(0, f * j - f / 2), x_hi = min(w, f * j + 3 * f / 2);
+      for (int y = y_lo; y < y_hi; ++y) {
         const UpCoef cy = up_coef(y, hs, h);
         const float wy = (cy.i0 == r ? cy.l0 : 0.f) + (cy.i1 == r ? cy.l1 : 0.f);
-        const UpCoef cx = up_coef(x, ws, w);
-        const float wxv = (cx.i0 == j ? cx.l0 : 0.f) + (cx.i1 == j ? cx.l1 : 0.f);
-        const float wgt = wy * wxv;
-        if (wgt != 0.f) g += wgt * src[(size_t)y * w + x];
+        if (wy == 0.f) continue;
+        float row = 0.f;
+        for (int x = x_lo; x < x_hi; ++x) {
+          const UpCoef cx = up_coef(x, ws, w);
+          const float wxv = (cx.i0 == j ? cx.l0 : 0.f) + (cx.i1 == j ? cx.l1 : 0.f);
+          row += wxv * ld1(src + (size_t)y * w + x);
+        }
+        g += wy * row;
       }
-      g = warp_sum(g);
-      if (lane != 0) continue;
     }
     if (has_sample0 && bb == 0 && smooth_grad) {
       const float* sg = smooth_grad + (size_t)scale * (2 * (b_global + 1) + 1);
@@ -509,7 +505,7 @@ int clslam_photo_bwd(const clslam_photo_args* a, void* stream) {
 
 int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* smooth_grad, int b_global, int has_sample0,
                      int b, int h, int w, int scale, float* dz_disp, void* stream) {
-  const size_t total = (size_t)b * (h >> scale) * (w >> scale) * (scale == 0 ? 1 : 32);     // one warp per pixel for s >= 1
+  const size_t total = (size_t)b * (h >> scale) * (w >> scale);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   disp_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ddisp_full, disp, smooth_grad, b_global, has_sample0, b, h, w, scale,

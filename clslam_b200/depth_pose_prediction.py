@@ -411,7 +411,7 @@ class DepthPosePrediction:
         n_run = self._steps_run.get(eng.b, 0)
         self._steps_run[eng.b] = n_run + 1
         if not self.use_cuda_graph or n_run == 0:       # first step eager: loads every kernel before capture
-            eng.forward(); eng.backward(); self._allreduce_grads(); eng.adam(lr)
+            eng.forward_backward(); self._allreduce_grads(); eng.adam(lr)
             return
         if self.world == 1:
             key = (eng.b, 'step', lr)
@@ -419,7 +419,7 @@ class DepthPosePrediction:
             if g is None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
-                    eng.forward(); eng.backward(); eng.adam(lr)
+                    eng.forward_backward(); eng.adam(lr)
                 self._graphs[key] = g
             g.replay()
         else:
@@ -427,7 +427,7 @@ class DepthPosePrediction:
             if k1 not in self._graphs:
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
-                    eng.forward(); eng.backward()
+                    eng.forward_backward()
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2):
                     eng.adam(lr)

@@ -455,6 +455,10 @@ class AdaptEngine:
         self._wt_op_index = len(plan.ops)
         plan.add('wt_flip', lambda stream, ws: self._run_wt_flip(stream))
         plan.record('wsplit')
+        # identity (auto-mask) candidates and the packed sources only depend on the inputs
+        self.identity = plan.alloc(b, 2, h, w)
+        plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
+        plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
         plan.set_lane(0)
         self.depth_in, depth_s2d = stage_for_encoder(plan, depth_prep, 'depth.stage', [(self.rgb_aug[1], None, 0, b)], b, h, w)
         # decoder geometry first: which layers run the TMA kernel decides where the encoder writes its skip features
@@ -519,8 +523,13 @@ class AdaptEngine:
             if i < S:
                 keyd = (dd, f'dispconv_{i}.conv')
                 dsp = plan.alloc(b, 1, ho_, wo_)
+                if i > 0:                    # only the photometric chain reads disp_i: lane 2, parallel to the next decoder stage
+                    plan.record(f'y1_{i}')
+                    plan.set_lane(2)
+                    plan.wait(f'y1_{i}')
                 plan.simple(f'dispconv_{i}', lib.clslam_dispconv_fwd, _p(y1), flat.weight_ptr(keyd), flat.bias_ptr(keyd),
                             _p(dsp), b, ho_, wo_, DEC_CH[i])
+                plan.set_lane(0)
                 self.disp[i] = dsp
             x, x_pl = y1, y1_pl[i]
 
@@ -565,7 +574,6 @@ class AdaptEngine:
 
         # ---- photometric chain + losses -------------------------------------------------------
         self.n_tiles = lib.clslam_photo_tiles(h, w)
-        self.identity = plan.alloc(b, 2, h, w)
         self.depth = [plan.alloc(b, 1, h, w) for _ in range(S)] if emit_outputs else [None] * S
         self.warped = [plan.alloc(2, b, 3, h, w) for _ in range(S)] if emit_outputs else [None] * S
         self.argmin = [plan.alloc(b, h, w, dtype=torch.uint8) for _ in range(S)]
@@ -607,12 +615,17 @@ class AdaptEngine:
         la.losses, la.smooth_grad = _p(self.losses), _p(self.smooth_grad)
         self.loss_args = la
         plan.keep.append(la)
-        plan.set_lane(2)
-        plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
-        plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
         plan.join((1, 2))
         plan.add('photo_fwd', lambda stream, ws: lib.clslam_photo_fwd(ctypes.byref(pa), stream))
+        # the loss assembly is off the critical path (photo_bwd does not need it): lane 2, next to photo_bwd
+        plan.record('pfwd')
+        plan.set_lane(2)
+        plan.wait('pfwd')
         plan.add('loss_finalize', lambda stream, ws: lib.clslam_loss_finalize(ctypes.byref(la), stream))
+        plan.record('lossfin')
+        plan.set_lane(0)
+        self.n_fwd_core = len(plan.ops)
+        plan.join((2,))                      # forward-only callers (eval) need the losses: executed by forward() only
         self.n_fwd_ops = len(plan.ops)
 
         # ---- backward: lane 0 = photometric + depth-decoder dgrad chain (critical path),
@@ -620,11 +633,14 @@ class AdaptEngine:
         plan.add('photo_bwd', lambda stream, ws: lib.clslam_photo_bwd(ctypes.byref(pa), stream))
         plan.fork((1, 2))
         self.dz_disp = {}
+        plan.wait('lossfin')                 # smooth_grad (lane 0 and, through the fork above, lanes 1 / 2 follow loss_finalize)
         for s in range(S):
             self.dz_disp[s] = plan.alloc(b, 1, h >> s, w >> s)
+            plan.set_lane(0 if s == 0 else 2)        # scale 0 heads the dgrad chain; the others are needed later
             plan.simple(f'disp_grad_{s}', lib.clslam_disp_grad, _p(self.ddisp_full[s]), _p(self.disp[s]),
                         _p(self.smooth_grad), batch_global, 1 if has_sample0 else 0, b, h, w, s, _p(self.dz_disp[s]))
             plan.record(f'dzd{s}')
+        plan.set_lane(0)
         self.dz = {}
         for i in range(0, 5):
             for j in (0, 1):
@@ -697,6 +713,8 @@ class AdaptEngine:
             plan.set_lane(0)
             if i < 4:
                 has_disp = (i + 1) < S
+                if has_disp:
+                    plan.wait(f'dzd{i + 1}')
                 disp_dz = self.dz_disp[i + 1] if has_disp else None
                 disp_w = flat.weight_ptr((dd, f'dispconv_{i + 1}.conv')) if has_disp else None
                 nxt = dz_pl.get((i + 1, 1))
@@ -787,6 +805,11 @@ class AdaptEngine:
         self.plan.run(0, self.n_fwd_ops)
 
     def backward(self) -> None:
+        self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
+
+    def forward_backward(self) -> None:
+        """one pass without the forward-only join (the loss assembly overlaps the photometric backward)"""
+        self.plan.run(0, self.n_fwd_core)
         self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
 
     def adam(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
