@@ -2,6 +2,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -15,6 +16,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CLSLAM_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;      // measured: no gain inside the CUDA graph (profiles/), off by default
+  }
+  return v == 1;
 }
 
 int finish_launch(const char* what) {

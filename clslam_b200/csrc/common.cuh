@@ -14,6 +14,27 @@ int finish_launch(const char* what);   // cudaGetLastError -> error string, coun
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch: every kernel is launched with the programmatic-stream-serialization attribute and
+// starts with griddepcontrol.wait (all memory of the preceding kernel is visible after it) + launch_dependents, so the
+// launch latency and the prologue (barrier init, TMEM allocation, tensor-map prefetch) of kernel i + 1 overlap the
+// tail of kernel i.  CLSLAM_PDL=1 in the environment turns the attribute on (default: plain stream order; inside the step graph it measured neutral).
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface through finish_launch (cudaGetLastError)
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 CLSLAM_HD float4 ld4(const float* p) {
 #ifdef __CUDA_ARCH__
   return __ldg(reinterpret_cast<const float4*>(p));

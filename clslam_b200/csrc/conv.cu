@@ -429,12 +429,12 @@ static int launch_gemm(const TilePlan& p, const AOp& a, const BOp& b, const Epi&
   }
   dim3 grid(p.gx, p.gy, p.splits), block(kGemmThreads);
   switch (p.cfg) {
-    case 0: gemm_tile_kernel<128, 64, 8, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
-    case 1: gemm_tile_kernel<64, 64, 4, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
-    case 2: gemm_tile_kernel<128, 32, 4, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
-    case 3: gemm_tile_kernel<256, 16, 4, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
-    case 4: gemm_tile_kernel<32, 64, 2, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
-    default: gemm_tile_kernel<16, 64, 1, AOp, BOp, Epi><<<grid, block, 0, st>>>(a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 0: launch_k(gemm_tile_kernel<128, 64, 8, AOp, BOp, Epi>, dim3(grid), dim3(block), 0, st, a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 1: launch_k(gemm_tile_kernel<64, 64, 4, AOp, BOp, Epi>, dim3(grid), dim3(block), 0, st, a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 2: launch_k(gemm_tile_kernel<128, 32, 4, AOp, BOp, Epi>, dim3(grid), dim3(block), 0, st, a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 3: launch_k(gemm_tile_kernel<256, 16, 4, AOp, BOp, Epi>, dim3(grid), dim3(block), 0, st, a, b, e, M, N, K, p.k_chunk, ws); break;
+    case 4: launch_k(gemm_tile_kernel<32, 64, 2, AOp, BOp, Epi>, dim3(grid), dim3(block), 0, st, a, b, e, M, N, K, p.k_chunk, ws); break;
+    default: launch_k(gemm_tile_kernel<16, 64, 1, AOp, BOp, Epi>, dim3(grid), dim3(block), 0, st, a, b, e, M, N, K, p.k_chunk, ws); break;
   }
   int rc = finish_launch(what);
   if (rc) return rc;
@@ -443,7 +443,7 @@ static int launch_gemm(const TilePlan& p, const AOp& a, const BOp& b, const Epi&
     int blocks = (int)((total4 + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     if (blocks < 1) blocks = 1;
-    splitk_reduce_kernel<Epi><<<blocks, 256, 0, st>>>(e, ws, M, N, p.splits);
+    launch_k(splitk_reduce_kernel<Epi>, dim3(blocks), dim3(256), 0, st, e, ws, M, N, p.splits);
     rc = finish_launch(what);
   }
   return rc;
@@ -489,7 +489,7 @@ static int launch_tc_bn(const TcPlan& p, const AOp& a, const BOp& b, const Epi& 
     attr_set = true;
   }
   dim3 grid(p.gx, p.gy, p.splits);
-  kern<<<grid, kTcBlock, kSmem, st>>>(a, b, e, M, N, K, p.k_chunk, ws);
+  launch_k(kern, dim3(grid), dim3(kTcBlock), kSmem, st, a, b, e, M, N, K, p.k_chunk, ws);
   return finish_launch(what);
 }
 
@@ -513,7 +513,7 @@ static int launch_gemm_tc(const TcPlan& p, const AOp& a, const BOp& b, const Epi
     int blocks = (int)((total4 + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     if (blocks < 1) blocks = 1;
-    splitk_reduce_kernel<Epi><<<blocks, 256, 0, st>>>(e, ws, M, N, p.splits);
+    launch_k(splitk_reduce_kernel<Epi>, dim3(blocks), dim3(256), 0, st, e, ws, M, N, p.splits);
     rc = finish_launch(what);
   }
   return rc;
@@ -580,7 +580,7 @@ static int launch_p3(const P3Plan& p, const ConvIn& c, const uint16_t* w_hi, con
     attr_set = true;
   }
   dim3 grid(p.gx, p.gy, p.splits);
-  kern<<<grid, kTcBlock, kSmem, st>>>(c, w_hi, w_lo, e, co, p.g, ws);
+  launch_k(kern, dim3(grid), dim3(kTcBlock), kSmem, st, c, w_hi, w_lo, e, co, p.g, ws);
   return finish_launch("conv3x3_tc");
 }
 
@@ -628,7 +628,7 @@ int clslam_split_bf16(const float* src, void* hi, void* lo, long long n, void* s
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (blocks < 1) blocks = 1;
-  split_bf16_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(src, (uint16_t*)hi, (uint16_t*)lo, n / 4);
+  launch_k(split_bf16_kernel, dim3((int)blocks), dim3(256), 0, as_stream(stream), src, (uint16_t*)hi, (uint16_t*)lo, n / 4);
   return finish_launch("split_bf16");
 }
 
@@ -685,7 +685,7 @@ int clslam_conv_fwd_emit(const clslam_conv_desc* d, const float* x, const float*
     int blocks = (int)((total4 + 255) / 256);
     if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
     if (blocks < 1) blocks = 1;
-    splitk_reduce_kernel<EpiFwd><<<blocks, 256, 0, st>>>(e, (const float*)workspace, M, N, p.splits);
+    launch_k(splitk_reduce_kernel<EpiFwd>, dim3(blocks), dim3(256), 0, st, e, (const float*)workspace, M, N, p.splits);
     rc = finish_launch("conv_fwd_bf16w");
   }
   return rc;

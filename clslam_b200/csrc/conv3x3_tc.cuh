@@ -83,6 +83,8 @@ template <int BN, class Epi>
 __global__ void __launch_bounds__(kTcBlock)
 conv3x3_tc_kernel(ConvIn c, const uint16_t* __restrict__ w_hi, const uint16_t* __restrict__ w_lo, Epi epi, int co, P3Geom g,
                   float* __restrict__ ws) {
+  pdl_wait();
+  pdl_trigger();
   using SM = P3Smem<BN>;
   constexpr int kTmemCols = BN < 32 ? 32 : BN;
   constexpr int kBVec = (BN * 8 * 2 + kTcThreads - 1) / kTcThreads;      // 16-byte copies per thread and k block (hi + lo)
@@ -276,6 +278,8 @@ conv3x3_tc_kernel(ConvIn c, const uint16_t* __restrict__ w_hi, const uint16_t* _
 // fp32 -> bf16 hi / lo planes (weights are split once per update instead of once per tile)
 __global__ void __launch_bounds__(256)
 split_bf16_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, long long n4) {
+  pdl_wait();
+  pdl_trigger();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const float4 v = ld4(src + i * 4);
     const __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);

@@ -107,6 +107,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();            // everything above overlapped the previous kernel; its results are visible from here on
+  pdl_trigger();
 
   const int tiles_per_img = g.tiles_x * g.tiles_y;
   const int total = g.n_img * tiles_per_img * g.n_blocks;
@@ -299,6 +301,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // ---- fp32 NHWC -> planes -------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 planes_from_f32_kernel(const float* __restrict__ x, PlaneView out, int n, int h, int w, int c) {
+  pdl_wait();
+  pdl_trigger();
   const int c4 = c / 4;
   const size_t total = (size_t)n * h * w * c4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -319,6 +323,8 @@ planes_from_f32_kernel(const float* __restrict__ x, PlaneView out, int n, int h,
 // A 7x7 / stride-2 / pad-3 convolution of the image is the 4x4 (rows o-2 .. o+1) stride-1 convolution of this tensor.
 __global__ void __launch_bounds__(256)
 stage_s2d_kernel(const float* __restrict__ a, const float* __restrict__ b, PlaneView out, int n, int h, int w, int img0) {
+  pdl_wait();
+  pdl_trigger();
   const int h2 = h / 2, w2 = w / 2, cp = b ? 8 : 4;
   const size_t total = (size_t)n * h2 * w2 * 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -355,6 +361,8 @@ struct WtFlipItem { long long src, dst; int co, ci, n_ci, pad; };
 __global__ void __launch_bounds__(256)
 wt_flip_kernel(const WtFlipItem* __restrict__ items, const uint16_t* __restrict__ w_hi, long long w_plane,
                uint16_t* __restrict__ wt_hi, long long wt_plane) {
+  pdl_wait();
+  pdl_trigger();
   const WtFlipItem it = items[blockIdx.y];
   const long long total = (long long)it.n_ci * 9 * it.co;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -374,6 +382,8 @@ __global__ void __launch_bounds__(256)
 dgrad_fold_kernel(const float* __restrict__ dxp, int n, int H, int W, int c, int up, const float* __restrict__ y_prev,
                   int act_prev, const float* __restrict__ disp_dz, const float* __restrict__ disp_w,
                   float* __restrict__ dz_prev, PlaneView po) {
+  pdl_wait();
+  pdl_trigger();
   const int ho = H / up, wo = W / up, c4 = c / 4;
   const size_t total = (size_t)n * ho * wo * c4;
   const int Wp = W + 2;
@@ -482,7 +492,7 @@ static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConv
   const int smem = (int)(g.na * C::kAStage + b_bytes + 1024 + kTmaBarBytes);
   const long long total = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks;
   const int grid = (int)(total < tma_num_sms() ? total : tma_num_sms());
-  kern<<<grid, kTmaThreads, smem, st>>>(ma, mb, g);
+  launch_k(kern, dim3(grid), dim3(kTmaThreads), smem, st, ma, mb, g);
   return finish_launch("conv3x3_tma");
 }
 
@@ -589,7 +599,7 @@ int clslam_stage_images_s2d(const float* img_a, const float* img_b, const clslam
   const size_t total = (size_t)n * (h / 2) * (w / 2) * 4;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  stage_s2d_kernel<<<blocks, 256, 0, as_stream(stream)>>>(img_a, img_b, v, n, h, w, image_offset);
+  launch_k(stage_s2d_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), img_a, img_b, v, n, h, w, image_offset);
   return finish_launch("stage_images_s2d");
 }
 
@@ -600,7 +610,7 @@ int clslam_wt_flip(const void* items_dev, int n_items, int max_elems, const void
   if (bx > 64) bx = 64;
   if (bx < 1) bx = 1;
   dim3 grid(bx, n_items);
-  wt_flip_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const WtFlipItem*>(items_dev),
+  launch_k(wt_flip_kernel, dim3(grid), dim3(256), 0, as_stream(stream), reinterpret_cast<const WtFlipItem*>(items_dev),
                                                       reinterpret_cast<const uint16_t*>(w_hi), w_plane_stride,
                                                       reinterpret_cast<uint16_t*>(wt_hi), wt_plane_stride);
   return finish_launch("wt_flip");
@@ -622,7 +632,7 @@ int clslam_dgrad_fold(const float* dxp, int n, int h, int w, int c, int up, cons
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  dgrad_fold_kernel<<<blocks, 256, 0, as_stream(stream)>>>(dxp, n, h, w, c, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, po);
+  launch_k(dgrad_fold_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), dxp, n, h, w, c, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, po);
   return finish_launch("dgrad_fold");
 }
 
@@ -636,7 +646,7 @@ int clslam_planes_from_f32(const float* x, const clslam_planes* out, int out_up,
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  planes_from_f32_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, v, out->n, v.h_lo, v.w_lo, out->c);
+  launch_k(planes_from_f32_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), x, v, out->n, v.h_lo, v.w_lo, out->c);
   return finish_launch("planes_from_f32");
 }
 

@@ -65,6 +65,8 @@ struct RContigMap {
 template <int BM, int BN, int TM, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(kGemmThreads)
 gemm_tile_kernel(AOp aop, BOp bop, Epi epi, int M, int N, int K, int k_chunk, float* __restrict__ ws) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int TN = 4;
   constexpr int TX = BN / TN;
   static_assert((BM / TM) * TX == kGemmThreads, "tile / thread mismatch");
@@ -175,6 +177,8 @@ gemm_tile_kernel(AOp aop, BOp bop, Epi epi, int M, int N, int K, int k_chunk, fl
 template <class Epi>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(Epi epi, const float* __restrict__ ws, int M, int N, int splits) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total4 = (size_t)M * N / 4;
   const size_t stride = (size_t)M * N;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {

@@ -160,6 +160,8 @@ __device__ unsigned long long g_tc_stamps[16];
 template <int BN, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(kTcBlock)
 gemm_tc_kernel(AOp aop, BOp bop, Epi epi, int M, int N, int K, int k_chunk, float* __restrict__ ws) {
+  pdl_wait();
+  pdl_trigger();
   using SM = TcSmem<BN, AOp, BOp>;
   using StA = TcStager<kTcBM, AOp>;
   using StB = TcStager<BN, BOp>;

@@ -9,6 +9,8 @@ namespace clslam {
 __global__ void __launch_bounds__(256)
 stage_images_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int n, int hw,
                     int c_pad) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total = (size_t)n * hw;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t img = i / hw, px = i - img * hw;
@@ -32,6 +34,8 @@ stage_images_kernel(const float* __restrict__ a, const float* __restrict__ b, fl
 // ---- 3x3 / s2 / p1 max pool, NHWC ----------------------------------------------------------
 __global__ void __launch_bounds__(256)
 maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int hi, int wi, int c, int ho, int wo, PlaneView po) {
+  pdl_wait();
+  pdl_trigger();
   const int c4 = c / 4;
   const size_t total = (size_t)n * ho * wo * c4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -65,6 +69,8 @@ template <int G>
 __global__ void __launch_bounds__(256)
 dispconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                     float* __restrict__ y, int n, int h, int wd) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int CI = G * 4;
   constexpr int PPW = 32 / G;
   const int lane = threadIdx.x & 31, sub = lane % G, grp = lane / G;
@@ -106,6 +112,8 @@ template <int G>
 __global__ void __launch_bounds__(256)
 dispconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz, float* __restrict__ ws, int n, int h,
                       int wd) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int CI = G * 4;
   constexpr int PPW = 32 / G;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane % G, grp = lane / G;
@@ -169,10 +177,18 @@ dispconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
 __global__ void __launch_bounds__(256)
 dispconv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, float* __restrict__ db, int blocks,
                              int ci) {
+  pdl_wait();
+  pdl_trigger();
   const int len = 9 * ci + 1;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < len; i += gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += ws[(size_t)b * len + i];
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;       // fixed order, four independent chains
+    int b = 0;
+    for (; b + 4 <= blocks; b += 4) {
+      a0 += ws[(size_t)b * len + i]; a1 += ws[(size_t)(b + 1) * len + i];
+      a2 += ws[(size_t)(b + 2) * len + i]; a3 += ws[(size_t)(b + 3) * len + i];
+    }
+    for (; b < blocks; ++b) a0 += ws[(size_t)b * len + i];
+    const float s = (a0 + a1) + (a2 + a3);
     if (i < 9 * ci) dw[i] = s; else if (db) db[0] = s;
   }
 }
@@ -181,6 +197,8 @@ dispconv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ d
 __global__ void __launch_bounds__(256)
 dispconv_dgrad_act_kernel(const float* __restrict__ dz, const float* __restrict__ w, const float* __restrict__ y_prev,
                           int act_prev, float* __restrict__ dz_prev, int n, int h, int wd, int ci) {
+  pdl_wait();
+  pdl_trigger();
   const int c4 = ci / 4;
   const size_t total = (size_t)n * h * wd * c4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -204,6 +222,8 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             long long n, double lr, double beta1, double beta2, double eps_d, int step_host,
             const int* __restrict__ step_dev) {
+  pdl_wait();
+  pdl_trigger();
   // step_dev holds the number of updates done BEFORE this one (adam_tick_kernel bumps it after)
   const int step = step_dev ? (*step_dev + 1) : step_host;
   const double bc1 = 1.0 - pow(beta1, (double)step);
@@ -221,7 +241,9 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     m[i] = mi; v[i] = vi;
   }
 }
-__global__ void adam_tick_kernel(int* step_dev) { *step_dev += 1; }
+__global__ void adam_tick_kernel(int* step_dev) {
+  pdl_wait();
+  pdl_trigger(); *step_dev += 1; }
 
 static int grid_for(size_t work, int per_block = 256, int cap = 148 * 8) {
   size_t b = (work + per_block - 1) / per_block;
@@ -239,7 +261,7 @@ extern "C" {
 int clslam_stage_images(const float* img_a, const float* img_b, float* out_nhwc, int n, int h, int w, int c_pad,
                         void* stream) {
   if (!(c_pad == 4 || c_pad == 8) || (img_b && c_pad != 8)) { set_error("stage_images: c_pad must be 4 (one image) or 8 (two)"); return -1; }
-  stage_images_kernel<<<grid_for((size_t)n * h * w), 256, 0, as_stream(stream)>>>(img_a, img_b, out_nhwc, n, h * w, c_pad);
+  launch_k(stage_images_kernel, dim3(grid_for((size_t)n * h * w)), dim3(256), 0, as_stream(stream), img_a, img_b, out_nhwc, n, h * w, c_pad);
   return finish_launch("stage_images");
 }
 
@@ -255,7 +277,7 @@ int clslam_maxpool3x3s2_emit(const float* x, float* y, int n, int hi, int wi, in
     po = make_plane_view(out, 1, out_halo);
   }
   if (!y && !po.base) { set_error("maxpool: no output"); return -1; }
-  maxpool_kernel<<<grid_for((size_t)n * ho * wo * (c / 4)), 256, 0, as_stream(stream)>>>(x, y, n, hi, wi, c, ho, wo, po);
+  launch_k(maxpool_kernel, dim3(grid_for((size_t)n * ho * wo * (c / 4))), dim3(256), 0, as_stream(stream), x, y, n, hi, wi, c, ho, wo, po);
   return finish_launch("maxpool");
 }
 
@@ -268,10 +290,10 @@ int clslam_dispconv_fwd(const float* x, const float* w, const float* bias, float
   const size_t px = (size_t)n * h * w_;
   cudaStream_t st = as_stream(stream);
   switch (ci) {
-    case 16: dispconv_fwd_kernel<4><<<grid_for(px, 64), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
-    case 32: dispconv_fwd_kernel<8><<<grid_for(px, 32), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
-    case 64: dispconv_fwd_kernel<16><<<grid_for(px, 16), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
-    case 128: dispconv_fwd_kernel<32><<<grid_for(px, 8), 256, 0, st>>>(x, w, bias, y, n, h, w_); break;
+    case 16: launch_k(dispconv_fwd_kernel<4>, dim3(grid_for(px, 64)), dim3(256), 0, st, x, w, bias, y, n, h, w_); break;
+    case 32: launch_k(dispconv_fwd_kernel<8>, dim3(grid_for(px, 32)), dim3(256), 0, st, x, w, bias, y, n, h, w_); break;
+    case 64: launch_k(dispconv_fwd_kernel<16>, dim3(grid_for(px, 16)), dim3(256), 0, st, x, w, bias, y, n, h, w_); break;
+    case 128: launch_k(dispconv_fwd_kernel<32>, dim3(grid_for(px, 8)), dim3(256), 0, st, x, w, bias, y, n, h, w_); break;
     default: set_error("dispconv_fwd: ci must be 16/32/64/128 (got %d)", ci); return -1;
   }
   return finish_launch("dispconv_fwd");
@@ -297,21 +319,21 @@ int clslam_dispconv_wgrad(const float* x, const float* dz, float* dw, float* db,
   float* ws = (float*)workspace;
   cudaStream_t st = as_stream(stream);
   switch (ci) {
-    case 16: dispconv_wgrad_kernel<4><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
-    case 32: dispconv_wgrad_kernel<8><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
-    case 64: dispconv_wgrad_kernel<16><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
-    case 128: dispconv_wgrad_kernel<32><<<blocks, 256, 0, st>>>(x, dz, ws, n, h, w_); break;
+    case 16: launch_k(dispconv_wgrad_kernel<4>, dim3(blocks), dim3(256), 0, st, x, dz, ws, n, h, w_); break;
+    case 32: launch_k(dispconv_wgrad_kernel<8>, dim3(blocks), dim3(256), 0, st, x, dz, ws, n, h, w_); break;
+    case 64: launch_k(dispconv_wgrad_kernel<16>, dim3(blocks), dim3(256), 0, st, x, dz, ws, n, h, w_); break;
+    case 128: launch_k(dispconv_wgrad_kernel<32>, dim3(blocks), dim3(256), 0, st, x, dz, ws, n, h, w_); break;
     default: set_error("dispconv_wgrad: ci must be 16/32/64/128 (got %d)", ci); return -1;
   }
   if (int rc = finish_launch("dispconv_wgrad")) return rc;
-  dispconv_wgrad_reduce_kernel<<<grid_for(9 * ci + 1), 256, 0, st>>>(ws, dw, db, blocks, ci);
+  launch_k(dispconv_wgrad_reduce_kernel, dim3(grid_for(9 * ci + 1)), dim3(256), 0, st, ws, dw, db, blocks, ci);
   return finish_launch("dispconv_wgrad_reduce");
 }
 
 int clslam_dispconv_dgrad_act(const float* dz, const float* w, const float* y_prev, int act_prev, float* dz_prev, int n,
                               int h, int w_, int ci, void* stream) {
   if (ci % 4) { set_error("dispconv_dgrad: ci %% 4 != 0"); return -1; }
-  dispconv_dgrad_act_kernel<<<grid_for((size_t)n * h * w_ * (ci / 4)), 256, 0, as_stream(stream)>>>(dz, w, y_prev, act_prev,
+  launch_k(dispconv_dgrad_act_kernel, dim3(grid_for((size_t)n * h * w_ * (ci / 4))), dim3(256), 0, as_stream(stream), dz, w, y_prev, act_prev,
                                                                                                  dz_prev, n, h, w_, ci);
   return finish_launch("dispconv_dgrad_act");
 }
@@ -319,11 +341,11 @@ int clslam_dispconv_dgrad_act(const float* dz, const float* w, const float* y_pr
 int clslam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr,
                      double beta1, double beta2, double eps, int step, int* step_dev, void* stream) {
   cudaStream_t st = as_stream(stream);
-  adam_kernel<<<grid_for((size_t)n, 256 * 4), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step,
+  launch_k(adam_kernel, dim3(grid_for((size_t)n, 256 * 4)), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step,
                                                            step_dev);
   if (int rc = finish_launch("adam")) return rc;
   if (step_dev) {
-    adam_tick_kernel<<<1, 1, 0, st>>>(step_dev);
+    launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, st, step_dev);
     return finish_launch("adam_tick");
   }
   return 0;

@@ -55,6 +55,8 @@ __device__ __forceinline__ float reproj_error(const float* xs /*[3][..][LW]*/, c
 // ---- (n, 3, h, w) planar -> (n, h, w, 4) packed: the warp gathers one float4 per bilinear tap ----------
 __global__ void __launch_bounds__(256)
 pack_rgba_kernel(const float* __restrict__ planar, float* __restrict__ packed, int n, int hw) {
+  pdl_wait();
+  pdl_trigger();
   const size_t total = (size_t)n * hw;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t img = i / hw, px = i - img * hw;
@@ -67,6 +69,8 @@ pack_rgba_kernel(const float* __restrict__ planar, float* __restrict__ packed, i
 __global__ void __launch_bounds__(kPhotoThreads)
 photo_identity_kernel(const float* __restrict__ target, const float* __restrict__ sources, float* __restrict__ identity,
                       int b, int h, int w, int tiles_x) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tg[3 * kFN];
   __shared__ float sr[3 * kFN];
   const int bb = blockIdx.y;
@@ -101,6 +105,8 @@ photo_identity_kernel(const float* __restrict__ target, const float* __restrict_
 // window statistics are loaded / computed once and reused by every scale and both source frames.
 __global__ void __launch_bounds__(kPhotoThreads)
 photo_fwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float tg[3 * kFN];
   __shared__ float wx[2 * 3 * kFN];
   __shared__ float red[8];
@@ -240,6 +246,8 @@ photo_fwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
 // ---- backward -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPhotoThreads)
 photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int kCW = kFW, kCN = kFN;      // coefficient maps cover tile + 1
   __shared__ float tg[3 * kBN];
   __shared__ float wx[3 * kBN];
@@ -417,6 +425,8 @@ photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
 __global__ void __launch_bounds__(256)
 disp_grad_kernel(const float* __restrict__ ddisp_full, const float* __restrict__ disp, const float* __restrict__ smooth_grad,
                  int b_global, int has_sample0, int b, int h, int w, int scale, float* __restrict__ dz) {
+  pdl_wait();
+  pdl_trigger();
   const int hs = h >> scale, ws = w >> scale;
   const int f = 1 << scale;
   const size_t total = (size_t)b * hs * ws;
@@ -464,7 +474,7 @@ int clslam_pack_rgba(const float* planar, float* packed, int n_images, int h, in
   const size_t total = (size_t)n_images * h * w;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  pack_rgba_kernel<<<blocks, 256, 0, as_stream(stream)>>>(planar, packed, n_images, h * w);
+  launch_k(pack_rgba_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), planar, packed, n_images, h * w);
   return finish_launch("pack_rgba");
 }
 
@@ -474,7 +484,7 @@ int clslam_photo_identity(const float* target, const float* sources, float* iden
   if (h < 2 || w < 2) { set_error("photo_identity: image too small"); return -1; }
   const int tiles_x = (w + kPhotoTW - 1) / kPhotoTW;
   dim3 grid(clslam_photo_tiles(h, w), b);
-  photo_identity_kernel<<<grid, kPhotoThreads, 0, as_stream(stream)>>>(target, sources, identity, b, h, w, tiles_x);
+  launch_k(photo_identity_kernel, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), target, sources, identity, b, h, w, tiles_x);
   return finish_launch("photo_identity");
 }
 
@@ -491,7 +501,7 @@ int clslam_photo_fwd(const clslam_photo_args* a, void* stream) {
   if (int rc = check_photo(a, "photo_fwd")) return rc;
   const int tiles_x = (a->w + kPhotoTW - 1) / kPhotoTW, tiles = clslam_photo_tiles(a->h, a->w);
   dim3 grid(tiles, a->b);
-  photo_fwd_kernel<<<grid, kPhotoThreads, 0, as_stream(stream)>>>(*a, tiles_x, tiles);
+  launch_k(photo_fwd_kernel, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), *a, tiles_x, tiles);
   return finish_launch("photo_fwd");
 }
 
@@ -499,7 +509,7 @@ int clslam_photo_bwd(const clslam_photo_args* a, void* stream) {
   if (int rc = check_photo(a, "photo_bwd")) return rc;
   const int tiles_x = (a->w + kPhotoTW - 1) / kPhotoTW, tiles = clslam_photo_tiles(a->h, a->w);
   dim3 grid(tiles, a->b * a->n_scales);
-  photo_bwd_kernel<<<grid, kPhotoThreads, 0, as_stream(stream)>>>(*a, tiles_x, tiles);
+  launch_k(photo_bwd_kernel, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), *a, tiles_x, tiles);
   return finish_launch("photo_bwd");
 }
 
@@ -508,7 +518,7 @@ int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* sm
   const size_t total = (size_t)b * (h >> scale) * (w >> scale);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  disp_grad_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ddisp_full, disp, smooth_grad, b_global, has_sample0, b, h, w, scale,
+  launch_k(disp_grad_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ddisp_full, disp, smooth_grad, b_global, has_sample0, b, h, w, scale,
                                                          dz_disp);
   return finish_launch("disp_grad");
 }

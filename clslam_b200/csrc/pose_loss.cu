@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(32)
 pose_head_fwd_kernel(const float* __restrict__ pose_out, const float* __restrict__ k_mat, int b, int h, int w,
                      int invert_mask, float* __restrict__ axis_angle, float* __restrict__ translation,
                      float* __restrict__ cam_t_cam, float* __restrict__ proj) {
+  pdl_wait();
+  pdl_trigger();
   const int pass = blockIdx.x / b, bb = blockIdx.x % b;
   __shared__ float out6[6];
   const int lane = threadIdx.x;
@@ -95,6 +97,8 @@ pose_head_bwd_kernel(const float* __restrict__ dproj_partials, int n_partials, c
                      const float* __restrict__ axis_angle, const float* __restrict__ translation,
                      const double* __restrict__ rel_dist, const float* __restrict__ sample_w, float velocity_scale,
                      int b, int h, int w, int invert_mask, float* __restrict__ dz) {
+  pdl_wait();
+  pdl_trigger();
   const int pass = blockIdx.x / b, bb = blockIdx.x % b;
   const int lane = threadIdx.x;
   __shared__ float dP[12];
@@ -193,6 +197,8 @@ pose_head_bwd_kernel(const float* __restrict__ dproj_partials, int n_partials, c
 // ---- loss assembly ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024)
 loss_finalize_kernel(clslam_loss_args a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float red[32];
   __shared__ float s_mean[4];
   __shared__ float s_reproj[4];
@@ -304,7 +310,7 @@ extern "C" {
 
 int clslam_pose_head_fwd(const float* pose_out, const float* k_mat, int b, int h, int w, int invert_mask, float* axis_angle,
                          float* translation, float* cam_t_cam, float* proj, void* stream) {
-  pose_head_fwd_kernel<<<2 * b, 32, 0, as_stream(stream)>>>(pose_out, k_mat, b, h, w, invert_mask, axis_angle, translation,
+  launch_k(pose_head_fwd_kernel, dim3(2 * b), dim3(32), 0, as_stream(stream), pose_out, k_mat, b, h, w, invert_mask, axis_angle, translation,
                                                             cam_t_cam, proj);
   return finish_launch("pose_head_fwd");
 }
@@ -312,7 +318,7 @@ int clslam_pose_head_fwd(const float* pose_out, const float* k_mat, int b, int h
 int clslam_pose_head_bwd(const float* dproj_partials, int n_partials, const float* k_mat, const float* axis_angle,
                          const float* translation, const double* rel_dist, const float* sample_w, float velocity_scale,
                          int b, int h, int w, int invert_mask, float* dz_pose_out, void* stream) {
-  pose_head_bwd_kernel<<<2 * b, 256, 0, as_stream(stream)>>>(dproj_partials, n_partials, k_mat, axis_angle, translation,
+  launch_k(pose_head_bwd_kernel, dim3(2 * b), dim3(256), 0, as_stream(stream), dproj_partials, n_partials, k_mat, axis_angle, translation,
                                                             rel_dist, sample_w, velocity_scale, b, h, w, invert_mask,
                                                             dz_pose_out);
   return finish_launch("pose_head_bwd");
@@ -323,7 +329,7 @@ int clslam_loss_finalize(const clslam_loss_args* a, void* stream) {
   if (a->has_sample0 && (a->b_global + 1 > (a->w >> (a->n_scales - 1)) || (a->h >> (a->n_scales - 1)) < 2)) {
     set_error("loss_finalize: reference smoothness indexing needs b_global < w / 2^(n_scales-1)"); return -1;
   }
-  loss_finalize_kernel<<<1, 1024, 0, as_stream(stream)>>>(*a);
+  launch_k(loss_finalize_kernel, dim3(1), dim3(1024), 0, as_stream(stream), *a);
   return finish_launch("loss_finalize");
 }
 

@@ -94,6 +94,8 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();            // the prologue above overlapped the previous kernel; its results are visible from here on
+  pdl_trigger();
 
   // work item of this CTA: (co block, ci chunk, split of the pixel tiles)
   const int pair = blockIdx.x / g.splits, split = blockIdx.x - pair * g.splits;
@@ -182,6 +184,8 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 // dW[co][r][s][ci] = sum over splits of ws[(cb, chunk, split)][r * CC + ci % CC][s * CO + co % CO]
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co, int ci, int cc, int cob, int ci_chunks, int splits) {
+  pdl_wait();
+  pdl_trigger();
   const int cols = 3 * cob;
   const size_t cta_stride = (size_t)(3 * cc) * cols;
   const int total = co * 9 * ci;
@@ -190,9 +194,15 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
     const int r = tap / 3, s = tap - r * 3;
     const int pair = (o / cob) * ci_chunks + c / cc;
     const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
-    float acc = 0.f;
-    for (int k = 0; k < splits; ++k) acc += p[(size_t)k * cta_stride];
-    dw[i] = acc;
+    // fixed summation order (deterministic), four independent chains so the loads overlap
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= splits; k += 4) {
+      a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride];
+      a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
+    }
+    for (; k < splits; ++k) a0 += p[(size_t)k * cta_stride];
+    dw[i] = (a0 + a1) + (a2 + a3);
   }
 }
 
@@ -200,6 +210,8 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
 constexpr int kBiasBlocks = 148;
 __global__ void __launch_bounds__(256)
 bias_grad_partial_kernel(const float* __restrict__ dz, long long pixels, int c, float* __restrict__ part) {
+  pdl_wait();
+  pdl_trigger();
   // thread = (pixel lane, channel quad); c / 4 quads (<= 64), 256 / quads pixel lanes
   __shared__ float4 red[256];
   const int quads = c / 4, lanes = 256 / quads;
@@ -219,11 +231,18 @@ bias_grad_partial_kernel(const float* __restrict__ dz, long long pixels, int c, 
 }
 __global__ void __launch_bounds__(256)
 bias_grad_final_kernel(const float* __restrict__ part, int blocks, int c, float* __restrict__ db) {
+  pdl_wait();
+  pdl_trigger();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= c) return;
-  float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += part[(size_t)b * c + i];
-  db[i] = s;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int b = 0;
+  for (; b + 4 <= blocks; b += 4) {
+    a0 += part[(size_t)b * c + i]; a1 += part[(size_t)(b + 1) * c + i];
+    a2 += part[(size_t)(b + 2) * c + i]; a3 += part[(size_t)(b + 3) * c + i];
+  }
+  for (; b < blocks; ++b) a0 += part[(size_t)b * c + i];
+  db[i] = (a0 + a1) + (a2 + a3);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -309,7 +328,7 @@ static int wg_launch(const CUtensorMap& mx, const CUtensorMap& mdz, const WgArgs
     if (e != cudaSuccess) { set_error("wgrad3x3_tma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -3; }
     attr_set = true;
   }
-  kern<<<p.grid, kWgThreads, p.smem, st>>>(mx, mdz, g);
+  launch_k(kern, dim3(p.grid), dim3(kWgThreads), p.smem, st, mx, mdz, g);
   return finish_launch("wgrad3x3_tma");
 }
 
@@ -357,15 +376,15 @@ int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_plane
   const int total = dz->c * 9 * x->c;
   int blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(g.ws, dw, dz->c, x->c, p.cc, p.cob, p.ci_chunks, p.splits);
+  launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, g.ws, dw, dz->c, x->c, p.cc, p.cob, p.ci_chunks, p.splits);
   rc = finish_launch("wgrad_reduce");
   if (rc || !db) return rc;
   // bias gradient from the fp32 dz (workspace reused after the reduction above: stream order)
   if (!dz_f32 || dz->c > 256) { set_error("wgrad3x3_tma: db needs dz_f32 and co <= 256"); return -1; }
   const long long pixels = (long long)dz->n * dz->h * dz->w;
-  bias_grad_partial_kernel<<<kBiasBlocks, 256, 0, st>>>(dz_f32, pixels, dz->c, g.ws);
+  launch_k(bias_grad_partial_kernel, dim3(kBiasBlocks), dim3(256), 0, st, dz_f32, pixels, dz->c, g.ws);
   if ((rc = finish_launch("bias_grad"))) return rc;
-  bias_grad_final_kernel<<<(dz->c + 255) / 256, 256, 0, st>>>(g.ws, kBiasBlocks, dz->c, db);
+  launch_k(bias_grad_final_kernel, dim3((dz->c + 255) / 256), dim3(256), 0, st, g.ws, kBiasBlocks, dz->c, db);
   return finish_launch("bias_grad_final");
 }
 
