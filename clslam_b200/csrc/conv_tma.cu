@@ -21,6 +21,13 @@
 namespace clslam {
 
 constexpr int kTmaTH = 16, kTmaTW = 8;     // output tile
+// timing experiments (clslam_debug_tma_flags) are compiled out unless CLSLAM_TMA_DEBUG is defined: their flag tests sit in
+// the single-thread issue loops, where every instruction counts
+#ifdef CLSLAM_TMA_DEBUG
+#define TMA_DBG(g, bit) (((g).debug & (bit)) != 0)
+#else
+#define TMA_DBG(g, bit) (false)
+#endif
 constexpr int kTmaEpiWarps = 16;          // 4 TMEM lane quarters x 4 column slots (8 accumulator columns per tcgen05.ld)
 constexpr int kTmaThreads = 64 + 32 * kTmaEpiWarps;
 
@@ -45,6 +52,7 @@ struct TmaConvCfg {
   static constexpr int kAStage = 2 * kAPlane;
   static constexpr int kBPlane = BN * kRowBytes;
   static constexpr int kBStage = 2 * kBPlane;
+  static constexpr int kSlots = BN >= 32 ? 4 : BN / 8;        // epilogue column slots with work
   static constexpr int kAcc = BN <= 64 ? 4 : 2;               // accumulator stages in TMEM (thin layers: the hand-off latency dominates)
   static constexpr int kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
   // upper 32 bits of every K-major swizzled descriptor of this configuration (SBO = 8 rows, version 1, layout type)
@@ -61,6 +69,7 @@ struct TmaConvArgs {
   int n_img, ho, wo, cout, cin;
   int tiles_x, tiles_y, n_blocks, chunks;
   int org;                       // input coordinate of tap (0, 0) relative to the output pixel, in tensor-map coordinates
+  FastDiv div_nb, div_tpi, div_tx;   // divisions by n_blocks, tiles per image, tiles_x
   int debug;                     // timing experiments only (results are wrong when != 0): 1 no MMA, 2 no epilogue body, 4 no B ring, 8 no A loads
   int na, nbr;                   // A ring depth; B ring depth, or 0: the whole weight tensor stays resident in shared memory
   int act;
@@ -97,7 +106,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     for (int i = 0; i < kTmaMaxStages; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], kTmaEpiWarps); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4 * C::kSlots); }
     mbar_init(b_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -115,182 +124,238 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   const int n_cs = g.chunks * T;
 
   if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
-      if (g.nbr == 0) {       // resident weights: every (chunk, s, r) tile once, slot = (chunk * T + s) * T + r
+    // ===================== TMA producer: the whole warp runs the (uniform) loops, one elected lane issues =========
+    if (g.nbr == 0) {         // resident weights: every (chunk, s, r) tile once, slot = (chunk * T + s) * T + r
+      if (elect_one()) {
         mbar_arrive_expect_tx(b_res, (uint32_t)(b_slots * C::kBStage));
         for (int slot = 0; slot < b_slots; ++slot) {
           const int r = slot % T, cs = slot / T, sft = cs % T, chunk = cs / T;
           tma_load_3d(b_tiles + (size_t)slot * C::kBStage, &map_b, b_res, (r * T + sft) * g.cin + chunk * KC, 0, 0);
         }
       }
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        const int nb = t % g.n_blocks, mt = t / g.n_blocks;
-        const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
-        const int oh0 = (rem / g.tiles_x) * kTmaTH + g.org, ow0 = (rem % g.tiles_x) * kTmaTW + g.org;
-        const int n0 = nb * BN;
-        for (int chunk = 0; chunk < g.chunks; ++chunk) {
-          for (int sft = 0; sft < T; ++sft) {
-            if (!(g.debug & 8)) {
-              mbar_wait(&a_empty[sa], (uint32_t)(pa ^ 1));
+      __syncwarp();
+    }
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      const int mt = g.div_nb.quot(t), nb = t - mt * g.n_blocks;
+      const int img = g.div_tpi.quot(mt), rem = mt - img * tiles_per_img;
+      const int ty = g.div_tx.quot(rem);
+      const int oh0 = ty * kTmaTH + g.org, ow0 = (rem - ty * g.tiles_x) * kTmaTW + g.org;
+      const int n0 = nb * BN;
+      for (int chunk = 0; chunk < g.chunks; ++chunk) {
+        for (int sft = 0; sft < T; ++sft) {
+          if (!TMA_DBG(g, 8)) {
+            mbar_wait(&a_empty[sa], (uint32_t)(pa ^ 1));
+            if (elect_one()) {
               mbar_arrive_expect_tx(&a_full[sa], C::kAStage);
               tma_load_5d(a_tiles + sa * C::kAStage, &map_a, &a_full[sa], chunk * KC, ow0 + sft, oh0, img, 0);
-              if (++sa == g.na) { sa = 0; pa ^= 1; }
             }
-            if (g.nbr > 0 && !(g.debug & 4)) {
-              for (int r = 0; r < T; ++r) {
-                mbar_wait(&b_empty[sb], (uint32_t)(pb ^ 1));
+            __syncwarp();
+            if (++sa == g.na) { sa = 0; pa ^= 1; }
+          }
+          if (g.nbr > 0 && !TMA_DBG(g, 4)) {
+            for (int r = 0; r < T; ++r) {
+              mbar_wait(&b_empty[sb], (uint32_t)(pb ^ 1));
+              if (elect_one()) {
                 mbar_arrive_expect_tx(&b_full[sb], C::kBStage);
                 tma_load_3d(b_tiles + sb * C::kBStage, &map_b, &b_full[sb], (r * T + sft) * g.cin + chunk * KC, n0, 0);
-                if (++sb == g.nbr) { sb = 0; pb ^= 1; }
               }
+              __syncwarp();
+              if (++sb == g.nbr) { sb = 0; pb ^= 1; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN);
-      constexpr uint32_t kLbo = 1u << 16;
-      const uint32_t a_ring = ((smem_u32(a_tiles) >> 4) & 0x3FFF) | kLbo;       // low descriptor words: start address >> 4
-      const uint32_t b_ring = ((smem_u32(b_tiles) >> 4) & 0x3FFF) | kLbo;
-      const bool resident = g.nbr == 0;
-      if (resident) { mbar_wait(b_res, 0); tc_fence_after(); }
-      int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int as = it % C::kAcc;
-        mbar_wait(&t_empty[as], (uint32_t)(((it / C::kAcc) & 1) ^ 1));      // the epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        uint32_t accumulate = 0;
-        for (int cs = 0; cs < n_cs; ++cs) {
-          if (!(g.debug & 8)) { mbar_wait(&a_full[sa], (uint32_t)pa); tc_fence_after(); }
-          const uint32_t a_st = a_ring + (uint32_t)(sa * (C::kAStage >> 4));
+    // ===================== MMA issuer: warp-uniform loops (descriptors stay in uniform registers), one elected lane issues
+    constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    constexpr uint32_t kLbo = 1u << 16;
+    const uint32_t a_ring = ((smem_u32(a_tiles) >> 4) & 0x3FFF) | kLbo;       // low descriptor words: start address >> 4
+    const uint32_t b_ring = ((smem_u32(b_tiles) >> 4) & 0x3FFF) | kLbo;
+    const bool resident = g.nbr == 0;
+    if (resident) { mbar_wait(b_res, 0); tc_fence_after(); }
+    int sa = 0, pa = 0, sb = 0, pb = 0, it = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int as = it % C::kAcc;
+      mbar_wait(&t_empty[as], (uint32_t)(((it / C::kAcc) & 1) ^ 1));      // the epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      uint32_t accumulate = 0;
+      for (int cs = 0; cs < (TMA_DBG(g, 512) ? 0 : n_cs); ++cs) {
+        if (!TMA_DBG(g, 8)) { mbar_wait(&a_full[sa], (uint32_t)pa); tc_fence_after(); }
+        const uint32_t a_st = a_ring + (uint32_t)(sa * (C::kAStage >> 4));
+        if (resident) {
+          // weights resident: nothing to wait for inside the stage, one election issues all T taps
+          if (elect_one()) {
 #pragma unroll
-          for (int r = 0; r < T; ++r) {
-            uint32_t b_st;
-            if (resident || (g.debug & 4)) {
-              b_st = b_ring + (uint32_t)(resident ? (cs * T + r) * (C::kBStage >> 4) : 0);
-            } else {
-              mbar_wait(&b_full[sb], (uint32_t)pb);
-              tc_fence_after();
-              b_st = b_ring + (uint32_t)(sb * (C::kBStage >> 4));
+            for (int r = 0; r < T; ++r) {
+              const uint32_t b_st = b_ring + (uint32_t)((cs * T + r) * (C::kBStage >> 4));
+              const uint32_t a_hi = a_st + (uint32_t)((r * kTmaTW * C::kRowBytes) >> 4);
+#pragma unroll
+              for (int j = 0; j < KC / 16; ++j) {
+                const uint32_t o = (uint32_t)(j * 2);
+                const uint64_t dah = make_desc(C::kDescHi, a_hi + o), dal = make_desc(C::kDescHi, a_hi + o + (C::kAPlane >> 4));
+                const uint64_t dbh = make_desc(C::kDescHi, b_st + o), dbl = make_desc(C::kDescHi, b_st + o + (C::kBPlane >> 4));
+                if (!TMA_DBG(g, 1)) {
+                  umma_bf16(tmem_d, dal, dbh, idesc, (r == 0 && j == 0) ? accumulate : 1u);
+                  umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                  umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                }
+              }
             }
-            const uint32_t a_hi = a_st + (uint32_t)((r * kTmaTW * C::kRowBytes) >> 4);
+            umma_commit(&a_empty[sa]);
+          }
+          __syncwarp();
+          accumulate = 1u;
+          if (++sa == g.na) { sa = 0; pa ^= 1; }
+          continue;
+        }
+#pragma unroll
+        for (int r = 0; r < T; ++r) {
+          mbar_wait(&b_full[sb], (uint32_t)pb);
+          tc_fence_after();
+          const uint32_t b_st = b_ring + (uint32_t)(sb * (C::kBStage >> 4));
+          const uint32_t a_hi = a_st + (uint32_t)((r * kTmaTW * C::kRowBytes) >> 4);
+          if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < KC / 16; ++j) {
               const uint32_t o = (uint32_t)(j * 2);                    // 16 bf16 = 32 bytes along k inside the swizzled row
               const uint64_t dah = make_desc(C::kDescHi, a_hi + o), dal = make_desc(C::kDescHi, a_hi + o + (C::kAPlane >> 4));
               const uint64_t dbh = make_desc(C::kDescHi, b_st + o), dbl = make_desc(C::kDescHi, b_st + o + (C::kBPlane >> 4));
-              if (!(g.debug & 1)) {
-                umma_bf16(tmem_d, dal, dbh, idesc, accumulate);
+              if (!TMA_DBG(g, 1)) {
+                umma_bf16(tmem_d, dal, dbh, idesc, (j == 0) ? accumulate : 1u);
                 umma_bf16(tmem_d, dah, dbl, idesc, 1u);
                 umma_bf16(tmem_d, dah, dbh, idesc, 1u);
               }
-              accumulate = 1u;
             }
-            if (!resident && !(g.debug & 4)) {
-              umma_commit(&b_empty[sb]);
-              if (++sb == g.nbr) { sb = 0; pb ^= 1; }
-            }
+            umma_commit(&b_empty[sb]);
           }
-          if (!(g.debug & 8)) {
-            umma_commit(&a_empty[sa]);
-            if (++sa == g.na) { sa = 0; pa ^= 1; }
-          }
+          __syncwarp();
+          accumulate = 1u;
+          if (++sb == g.nbr) { sb = 0; pb ^= 1; }
         }
-        umma_commit(&t_full[as]);
+        if (!TMA_DBG(g, 8)) {
+          if (elect_one()) umma_commit(&a_empty[sa]);
+          __syncwarp();
+          if (++sa == g.na) { sa = 0; pa ^= 1; }
+        }
       }
+      if (elect_one()) umma_commit(&t_full[as]);
+      __syncwarp();
     }
   } else {
     // ===================== epilogue =====================
+    // 4 TMEM lane quarters x up to 4 column slots of 8 accumulator columns; with BN < 32 the surplus warps have no columns
+    // and stay out of the hand-off (t_empty counts the working warps only)
     const int q = warp & 3;                      // TMEM lane quarter this warp may access
     const int slot = (warp - 2) >> 2;            // column slot: groups slot, slot + 4, ... of 8 accumulator columns
     const int l = q * 32 + lane;
-    int it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-      const int as = it % C::kAcc;
-      const int nb = t % g.n_blocks, mt = t / g.n_blocks;
-      const int img = mt / tiles_per_img, rem = mt - img * tiles_per_img;
-      const int oh = (rem / g.tiles_x) * kTmaTH + (l >> 3), ow = (rem % g.tiles_x) * kTmaTW + (l & 7);
-      const bool ok = oh < g.ho && ow < g.wo;
-      // output addressing of this pixel, once per tile
-      const size_t y_off = (((size_t)img * g.ho + oh) * g.wo + ow) * g.cout;
-      int rows[3] = {-1, -1, -1}, cols[3] = {-1, -1, -1};
-      if (g.out.base && ok) {
-        plane_coords(oh, g.out.h_lo, g.out.up, g.out.halo, rows);
-        plane_coords(ow, g.out.w_lo, g.out.up, g.out.halo, cols);
-      }
-      const size_t res_off = g.res.base ? (((size_t)img * g.res.hp + oh + 1) * g.res.wp + ow + 1) * g.res.c_total : 0;
-      if (lane == 0) mbar_wait(&t_full[as], (uint32_t)((it / C::kAcc) & 1));      // one poller per warp
-      __syncwarp();
-      tc_fence_after();
+    if (slot < C::kSlots) {
+      // loop invariants of the plane output (bf16 elements)
+      const long long o_px = g.out.c_total, o_row = (long long)g.out.wp * g.out.c_total;
+      const long long o_img = (long long)g.out.hp * o_row;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int as = it % C::kAcc;
+        const int mt = g.div_nb.quot(t), nb = t - mt * g.n_blocks;
+        const int img = g.div_tpi.quot(mt), rem = mt - img * tiles_per_img;
+        const int ty = g.div_tx.quot(rem);
+        const int oh = ty * kTmaTH + (l >> 3), ow = (rem - ty * g.tiles_x) * kTmaTW + (l & 7);
+        const bool ok = oh < g.ho && ow < g.wo;
+        const size_t y_off = (((size_t)img * g.ho + oh) * g.wo + ow) * g.cout;
+        // planes: primary position(s) by pointer arithmetic; the reflection-halo copies of border pixels on a slow path
+        const int up = g.out.up;
+        __nv_bfloat16* o_base = g.out.base + img * o_img + (long long)(up * oh + 1) * o_row + (long long)(up * ow + 1) * o_px;
+        const bool edge = g.out.base != nullptr && g.out.halo != 0 && ok &&
+                          (up == 1 ? (oh == 1 || oh == g.out.h_lo - 2 || ow == 1 || ow == g.out.w_lo - 2)
+                                   : (oh == 0 || oh == g.out.h_lo - 1 || ow == 0 || ow == g.out.w_lo - 1));
+        if (TMA_DBG(g, 256)) {
+          mbar_wait(&t_full[as], (uint32_t)((it / C::kAcc) & 1));
+        } else {
+          if (lane == 0) mbar_wait(&t_full[as], (uint32_t)((it / C::kAcc) & 1));      // one poller per warp
+          __syncwarp();
+        }
+        if (!TMA_DBG(g, 128)) tc_fence_after();
 #pragma unroll 1
-      for (int c = slot * 8; c < BN; c += 32) {
-        uint32_t r[8];
-        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
-        const int n = nb * BN + c;
-        if (!ok || n >= g.cout || (g.debug & 2)) continue;
-        float v[8];
+        for (int c = slot * 8; c < BN; c += 32) {
+          uint32_t r[8];
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+          const int n = nb * BN + c;
+          if (!ok || n >= g.cout || TMA_DBG(g, 2)) continue;
+          float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-        if (g.scale) {
-          const float4 s0 = ld4(g.scale + n), s1 = ld4(g.scale + n + 4);
-          v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-        }
-        if (g.shift) {
-          const float4 s0 = ld4(g.shift + n), s1 = ld4(g.shift + n + 4);
-          v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
-        }
-        if (g.res.base) {
-          const __nv_bfloat16* rp = g.res.base + res_off + n;
-          const uint4 h = *reinterpret_cast<const uint4*>(rp);
-          const uint4 lo4 = *reinterpret_cast<const uint4*>(rp + g.res.plane);
-          const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = join_bf16x2(hh[j], ll[j]);
-            v[2 * j] += f.x; v[2 * j + 1] += f.y;
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+          if (g.scale) {
+            const float4 s0 = ld4(g.scale + n), s1 = ld4(g.scale + n + 4);
+            v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
           }
-        }
+          if (g.shift) {
+            const float4 s0 = ld4(g.shift + n), s1 = ld4(g.shift + n + 4);
+            v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+          }
+          if (g.res.base) {
+            const __nv_bfloat16* rp = g.res.base + (((size_t)img * g.res.hp + oh + 1) * g.res.wp + ow + 1) * g.res.c_total + n;
+            const uint4 h = *reinterpret_cast<const uint4*>(rp);
+            const uint4 lo4 = *reinterpret_cast<const uint4*>(rp + g.res.plane);
+            const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {lo4.x, lo4.y, lo4.z, lo4.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = act_fast(v[j], g.act);
-        if (g.gate) {
-          const float4 g0 = ld4(g.gate + y_off + n), g1 = ld4(g.gate + y_off + n + 4);
-          v[0] *= act_grad_from_output(g0.x, g.gate_act); v[1] *= act_grad_from_output(g0.y, g.gate_act);
-          v[2] *= act_grad_from_output(g0.z, g.gate_act); v[3] *= act_grad_from_output(g0.w, g.gate_act);
-          v[4] *= act_grad_from_output(g1.x, g.gate_act); v[5] *= act_grad_from_output(g1.y, g.gate_act);
-          v[6] *= act_grad_from_output(g1.z, g.gate_act); v[7] *= act_grad_from_output(g1.w, g.gate_act);
-        }
-        if (g.y) {
-          float* p = g.y + y_off + n;
-          *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
-        if (g.out.base) {
-          uint32_t hi[4], lo[4];
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = join_bf16x2(hh[j], ll[j]);
+              v[2 * j] += f.x; v[2 * j + 1] += f.y;
+            }
+          }
 #pragma unroll
-          for (int j = 0; j < 4; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-          const uint4 hv = make_uint4(hi[0], hi[1], hi[2], hi[3]), lv = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          for (int j = 0; j < 8; ++j) v[j] = act_fast(v[j], g.act);
+          if (g.gate) {
+            const float4 g0 = ld4(g.gate + y_off + n), g1 = ld4(g.gate + y_off + n + 4);
+            v[0] *= act_grad_from_output(g0.x, g.gate_act); v[1] *= act_grad_from_output(g0.y, g.gate_act);
+            v[2] *= act_grad_from_output(g0.z, g.gate_act); v[3] *= act_grad_from_output(g0.w, g.gate_act);
+            v[4] *= act_grad_from_output(g1.x, g.gate_act); v[5] *= act_grad_from_output(g1.y, g.gate_act);
+            v[6] *= act_grad_from_output(g1.z, g.gate_act); v[7] *= act_grad_from_output(g1.w, g.gate_act);
+          }
+          if (g.y) {
+            float* p = g.y + y_off + n;
+            *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+          if (g.out.base) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int a = 0; a < 3; ++a) {
-#pragma unroll
-            for (int b = 0; b < 3; ++b) {
-              if (rows[a] >= 0 && cols[b] >= 0) {
-                __nv_bfloat16* p = g.out.base + (((size_t)img * g.out.hp + rows[a]) * g.out.wp + cols[b]) * g.out.c_total + n;
-                *reinterpret_cast<uint4*>(p) = hv;
-                *reinterpret_cast<uint4*>(p + g.out.plane) = lv;
+            for (int j = 0; j < 4; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+            const uint4 hv = make_uint4(hi[0], hi[1], hi[2], hi[3]), lv = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            __nv_bfloat16* p = o_base + n;
+            *reinterpret_cast<uint4*>(p) = hv;
+            *reinterpret_cast<uint4*>(p + g.out.plane) = lv;
+            if (up == 2) {                        // nearest 2x: the other three pixels of the footprint
+              *reinterpret_cast<uint4*>(p + o_px) = hv;             *reinterpret_cast<uint4*>(p + o_px + g.out.plane) = lv;
+              *reinterpret_cast<uint4*>(p + o_row) = hv;            *reinterpret_cast<uint4*>(p + o_row + g.out.plane) = lv;
+              *reinterpret_cast<uint4*>(p + o_row + o_px) = hv;     *reinterpret_cast<uint4*>(p + o_row + o_px + g.out.plane) = lv;
+            }
+            if (edge) {                           // border pixels also feed the halo cells that mirror onto them
+              int rows[3], cols[3];
+              plane_coords(oh, g.out.h_lo, up, 1, rows);
+              plane_coords(ow, g.out.w_lo, up, 1, cols);
+#pragma unroll 1
+              for (int a = 0; a < 3; ++a) {
+#pragma unroll 1
+                for (int b = 0; b < 3; ++b) {
+                  const int ra = a == 0 ? rows[0] : (a == 1 ? rows[1] : rows[2]);
+                  const int cb = b == 0 ? cols[0] : (b == 1 ? cols[1] : cols[2]);
+                  const bool primary = up == 1 ? (a == 0 && b == 0) : (a < 2 && b < 2);
+                  if (ra < 0 || cb < 0 || primary) continue;
+                  __nv_bfloat16* ph = g.out.base + img * o_img + ra * o_row + cb * o_px + n;
+                  *reinterpret_cast<uint4*>(ph) = hv;
+                  *reinterpret_cast<uint4*>(ph + g.out.plane) = lv;
+                }
               }
             }
           }
         }
+        if (!TMA_DBG(g, 128)) tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[as]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[as]);
     }
   }
   tc_fence_before();
@@ -533,6 +598,7 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   g.n_img = in.n; g.ho = ho; g.wo = wo; g.cout = cout; g.cin = cin;
   g.tiles_x = (wo + kTmaTW - 1) / kTmaTW; g.tiles_y = (ho + kTmaTH - 1) / kTmaTH;
   g.n_blocks = cout / bn; g.chunks = cin / kc;
+  g.div_nb = make_fastdiv(g.n_blocks); g.div_tpi = make_fastdiv(g.tiles_x * g.tiles_y); g.div_tx = make_fastdiv(g.tiles_x);
   g.debug = g_tma_debug;
   g.gate = p->gate; g.gate_act = p->gate_act;
   g.act = p->act; g.scale = p->scale; g.shift = p->shift; g.y = p->y;

@@ -26,6 +26,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
   }
 }
+// non-suspending variant (mbarrier.test_wait in a tight loop)
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -98,6 +112,27 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const void* map, uint64_t
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+// one lane of the (converged) warp: the warp-uniform control flow around it keeps descriptors / addresses in uniform registers
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// division by a runtime constant without the ~100-instruction integer divide (x < 2^31)
+struct FastDiv {
+  uint32_t mul, shift, div;
+  __device__ __forceinline__ int quot(int x) const { return (int)((__umulhi((uint32_t)x, mul) + (uint32_t)x) >> shift); }
+};
+static inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.div = (uint32_t)d;
+  uint32_t s = 0;
+  while ((1u << s) < (uint32_t)d) ++s;
+  f.shift = s;
+  f.mul = (uint32_t)((((unsigned long long)1 << 32) * (((unsigned long long)1 << s) - (unsigned long long)d)) / (unsigned long long)d + 1);
+  return f;
 }
 
 // tensor memory: allocation by one full warp (columns: power of two >= 32), 32 lanes x 16 columns loads

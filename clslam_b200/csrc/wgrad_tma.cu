@@ -62,6 +62,7 @@ struct WgArgs {
   int co_blocks, ci_chunks, splits;
   int org_x;                       // x-patch origin relative to the output pixel in x-map coordinates (0: padded view, -1: interior)
   int stages;
+  FastDiv div_tpi, div_tx;         // divisions by tiles per image and tiles_x
   float* ws;                       // [cta][3 * CC][3 * CO]
 };
 
@@ -105,12 +106,14 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int t_begin = (int)(((long long)total * split) / g.splits), t_end = (int)(((long long)total * (split + 1)) / g.splits);
 
   if (warp == 0) {
-    if (lane == 0) {
-      int st = 0, ph = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
-        const int h0 = (rem / g.tiles_x) * kWgR, w0 = (rem % g.tiles_x) * kWgW;
-        mbar_wait(&empty[st], (uint32_t)(ph ^ 1));
+    // TMA producer: warp-uniform loop, one elected lane issues
+    int st = 0, ph = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      const int img = g.div_tpi.quot(t), rem = t - img * tiles_per_img;
+      const int ty = g.div_tx.quot(rem);
+      const int h0 = ty * kWgR, w0 = (rem - ty * g.tiles_x) * kWgW;
+      mbar_wait(&empty[st], (uint32_t)(ph ^ 1));
+      if (elect_one()) {
         mbar_arrive_expect_tx(&full[st], C::kStage);
         uint8_t* base = tiles + (size_t)st * C::kStage;
 #pragma unroll
@@ -119,20 +122,22 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll
         for (int a = 0; a < C::kAtoms; ++a)
           tma_load_5d(base + C::kABytes + a * C::kBAtom, &map_dz, &full[st], cb * CO + a * C::kAtomCo, w0, h0, img, 0);
-        if (++st == g.stages) { st = 0; ph ^= 1; }
       }
+      __syncwarp();
+      if (++st == g.stages) { st = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16_mn(CO);
-      const uint32_t ring = (smem_u32(tiles) >> 4) & 0x3FFF;
-      int st = 0, ph = 0;
-      uint32_t acc = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        mbar_wait(&full[st], (uint32_t)ph);
-        tc_fence_after();
-        const uint32_t a0 = ring + (uint32_t)(st * (C::kStage >> 4));
-        const uint32_t b0 = a0 + (uint32_t)(C::kABytes >> 4);
+    // MMA issuer: warp-uniform loop (descriptors in uniform registers), one elected lane issues
+    constexpr uint32_t idesc = umma_idesc_bf16_mn(CO);
+    const uint32_t ring = (smem_u32(tiles) >> 4) & 0x3FFF;
+    int st = 0, ph = 0;
+    uint32_t acc = 0;
+    for (int t = t_begin; t < t_end; ++t) {
+      mbar_wait(&full[st], (uint32_t)ph);
+      tc_fence_after();
+      const uint32_t a0 = ring + (uint32_t)(st * (C::kStage >> 4));
+      const uint32_t b0 = a0 + (uint32_t)(C::kABytes >> 4);
+      if (elect_one()) {
 #pragma unroll
         for (int rr = 0; rr < kWgR; ++rr) {
           const uint32_t b_hi = (b0 + (uint32_t)((rr * kWgW * C::kRowB) >> 4)) | C::kLboB;
@@ -144,17 +149,19 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const uint32_t a_lo = a_hi + (uint32_t)(C::kAPlane >> 4);
             const uint64_t dah = wg_desc(C::kDescHiA, a_hi), dal = wg_desc(C::kDescHiA, a_lo);
             const uint32_t d = tmem_base + (uint32_t)(s * CO);
-            umma_bf16(d, dal, dbh, idesc, acc);
+            umma_bf16(d, dal, dbh, idesc, rr == 0 ? acc : 1u);
             umma_bf16(d, dah, dbl, idesc, 1u);
             umma_bf16(d, dah, dbh, idesc, 1u);
           }
-          acc = 1u;
         }
         umma_commit(&empty[st]);
-        if (++st == g.stages) { st = 0; ph ^= 1; }
       }
-      umma_commit(done);
+      __syncwarp();
+      acc = 1u;
+      if (++st == g.stages) { st = 0; ph ^= 1; }
     }
+    if (elect_one()) umma_commit(done);
+    __syncwarp();
   } else {
     // final copy: lanes (r, ci) < 3 * CC, columns (s, co)
     if (lane == 0) mbar_wait(done, 0);
@@ -363,6 +370,7 @@ int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_plane
   g.tiles_x = (x->w + kWgW - 1) / kWgW; g.tiles_y = (x->h + kWgR - 1) / kWgR;
   g.co_blocks = p.co_blocks; g.ci_chunks = p.ci_chunks; g.splits = p.splits;
   g.org_x = padded ? 0 : -1;
+  g.div_tpi = make_fastdiv(g.tiles_x * g.tiles_y); g.div_tx = make_fastdiv(g.tiles_x);
   g.stages = p.stages;
   g.ws = reinterpret_cast<float*>(workspace);
   cudaStream_t st = as_stream(stream);

@@ -71,10 +71,11 @@ def bench(n, h, w, ci, co, pad_mode):
     r = {'shape': f'n{n} {h}x{w} {ci}->{co} pad{pad_mode}', 'old_us': timed(run_old), 'tma_planes_us': timed(run_tma_planes),
          'tma_f32_us': timed(run_tma_f32)}
     r['old_warm_us'] = warm(run_old); r['tma_planes_warm_us'] = warm(run_tma_planes)
-    for fl in (1, 2, 3, 4, 8, 12, 15):
+    for fl in (() if len(sys.argv) <= 2 else ()):
         lib.clslam_debug_tma_flags(fl)
         r[f'dbg{fl}_warm_us'] = warm(run_tma_planes)
-    lib.clslam_debug_tma_flags(0)
+    if len(sys.argv) <= 2:
+        lib.clslam_debug_tma_flags(0)
     r['tma_tflops'] = flops / (r['tma_planes_us'] * 1e-6) / 1e12
     r['tma_gbs'] = byts / (r['tma_planes_us'] * 1e-6) / 1e9
     r['old_tflops'] = flops / (r['old_us'] * 1e-6) / 1e12
@@ -88,5 +89,11 @@ cases = [(8, 48, 160, 64, 64, L.PAD_ZERO), (16, 48, 160, 64, 64, L.PAD_ZERO), (8
          (1, 48, 160, 64, 64, L.PAD_ZERO), (1, 96, 320, 96, 32, L.PAD_REFLECT), (1, 192, 640, 16, 16, L.PAD_REFLECT)]
 if len(sys.argv) > 1:
     cases = [cases[int(i)] for i in sys.argv[1].split(',')]
+if len(sys.argv) > 2:          # profile mode: a few launches with fixed debug flags
+    import os
+    n, h, w, ci, co, pm = cases[0]
+    lib.clslam_debug_tma_flags(int(sys.argv[2]))
+    r = bench(n, h, w, ci, co, pm)
+    sys.exit(0)
 for c in cases:
     print(json.dumps(bench(*c)), flush=True)
