@@ -39,16 +39,17 @@ import os
 
 # below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: gather kernels (split-K) instead
 TMA_MIN_TILES = int(os.environ.get('CLSLAM_TMA_MIN_TILES', '24'))
+TMA_MIN_TILES_BWD = int(os.environ.get('CLSLAM_TMA_MIN_TILES_BWD', '24'))     # dgrad: the gather dgrad is slower, so the bar is lower
 
 
-def tma_ok(n: int, h: int, w: int, ci: int, co: int) -> bool:
+def tma_ok(n: int, h: int, w: int, ci: int, co: int, min_tiles: Optional[int] = None) -> bool:
     """3x3 / stride-1 layer eligible for clslam_conv3x3_tma (planes in, planes / fp32 out)"""
     if L.load().clslam_get_conv_mode() != 1 or ci % 16 or co % 16:
         return False
     bn = 128 if co >= 128 else (64 if co >= 64 else (32 if co >= 32 else 16))
     if co % bn:
         return False
-    return n * ((h + 15) // 16) * ((w + 7) // 8) >= TMA_MIN_TILES
+    return n * ((h + 15) // 16) * ((w + 7) // 8) >= (TMA_MIN_TILES if min_tiles is None else min_tiles)
 
 
 class PlaneBuf:
@@ -646,8 +647,10 @@ class AdaptEngine:
             for j in (0, 1):
                 self.dz[(i, j)] = plan.alloc(*self.y[(i, j)].shape)
         # dgrad on the TMA kernel where the (padded) output grid has enough tiles; dz is then also kept as planes
-        ud1 = {i: tma_ok(b, self.y[(i, 1)].shape[1] + 2, self.y[(i, 1)].shape[2] + 2, DEC_CH[i], DEC_CH[i]) for i in range(5)}
-        ud0 = {i: tma_ok(b, self.y[(i, 0)].shape[1] + 2, self.y[(i, 0)].shape[2] + 2, DEC_CH[i], DEC_CH[i + 1]) for i in range(4)}
+        ud1 = {i: tma_ok(b, self.y[(i, 1)].shape[1] + 2, self.y[(i, 1)].shape[2] + 2, DEC_CH[i], DEC_CH[i], TMA_MIN_TILES_BWD)
+               for i in range(5)}
+        ud0 = {i: tma_ok(b, self.y[(i, 0)].shape[1] + 2, self.y[(i, 0)].shape[2] + 2, DEC_CH[i], DEC_CH[i + 1], TMA_MIN_TILES_BWD)
+               for i in range(4)}
         ud0[4] = False
         wg = {k: v is not None for k, v in self.dec_in_pl.items()}       # wgrad on tcgen05 needs the layer input as planes
         dz_pl = {}
@@ -738,7 +741,7 @@ class AdaptEngine:
                     _p(self.axis_angle), _p(self.translation), _p(self.rel_dist), _p(self.sample_w),
                     self.vel_scale, b, hp, wp, self.invert_mask, _p(self.dz_pose['pose_2']))
         prev = {'pose_2': 'pose_1', 'pose_1': 'pose_0', 'pose_0': 'squeeze'}
-        upd = tma_ok(2 * b, hp, wp, 256, 256)         # pose_1 / pose_0 dgrad (zero padding: one launch, act' fused as a gate)
+        upd = tma_ok(2 * b, hp, wp, 256, 256, TMA_MIN_TILES_BWD)         # pose_1 / pose_0 dgrad (zero padding: one launch, act' fused as a gate)
         dzp_pl = {name: PlaneBuf(plan, 2 * b, hp, wp, 256).view() for name in ('pose_1', 'pose_0')} if upd else {}
         for name in ('pose_2', 'pose_1', 'pose_0', 'squeeze'):
             d, xin = self.pose_desc[name]
