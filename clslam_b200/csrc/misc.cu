@@ -63,6 +63,23 @@ maxpool_kernel(const float* __restrict__ x, float* __restrict__ y, int n, int hi
   }
 }
 
+// work index -> pixel, walking 8 x 16 pixel tiles instead of image rows: the 3x3 taps of the pixels a block touches in
+// one sweep then share their rows through L1 instead of re-reading them from L2 (falls back to row order for odd sizes)
+__device__ __forceinline__ void tile_order(size_t p, int h, int wd, int& b, int& hh, int& ww) {
+  const int hw = h * wd;
+  b = (int)(p / (size_t)hw);
+  const int r = (int)(p - (size_t)b * hw);
+  if ((h & 7) == 0 && (wd & 15) == 0) {
+    const int tile = r >> 7, off = r & 127, tiles_x = wd >> 4;
+    const int ty = tile / tiles_x;
+    hh = ty * 8 + (off >> 4);
+    ww = (tile - ty * tiles_x) * 16 + (off & 15);
+  } else {
+    hh = r / wd;
+    ww = r - hh * wd;
+  }
+}
+
 // ---- dispconv forward: reflect 3x3 -> 1 channel, + bias, sigmoid ---------------------------
 // G = ci/4 lanes cooperate on one pixel (each owns 4 channels), 32/G pixels per warp.
 template <int G>
@@ -84,10 +101,9 @@ dispconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
   for (size_t base = warp_id * PPW; base < total; base += n_warps * PPW) {
     const size_t p = base + grp;
     float acc = 0.f;
+    int b = 0, hh = 0, ww = 0;
     if (p < total) {
-      const int ww = (int)(p % wd);
-      const int hh = (int)((p / wd) % h);
-      const int b = (int)(p / ((size_t)wd * h));
+      tile_order(p, h, wd, b, hh, ww);
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int ih = reflect_idx(hh + r - 1, h);
@@ -102,7 +118,7 @@ dispconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (sub == 0 && p < total) y[p] = act_apply(acc + bv, CLSLAM_ACT_SIGMOID);
+    if (sub == 0 && p < total) y[((size_t)b * h + hh) * wd + ww] = act_apply(acc + bv, CLSLAM_ACT_SIGMOID);
   }
 }
 
@@ -127,10 +143,9 @@ dispconv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dz,
   for (size_t base = warp_id * PPW; base < total; base += n_warps * PPW) {
     const size_t p = base + grp;
     if (p >= total) continue;
-    const float g = ld1(dz + p);
-    const int ww = (int)(p % wd);
-    const int hh = (int)((p / wd) % h);
-    const int b = (int)(p / ((size_t)wd * h));
+    int b, hh, ww;
+    tile_order(p, h, wd, b, hh, ww);
+    const float g = ld1(dz + ((size_t)b * h + hh) * wd + ww);
     if (sub == 0) bsum += g;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {

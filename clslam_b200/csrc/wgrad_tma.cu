@@ -189,14 +189,28 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 }
 
 // dW[co][r][s][ci] = sum over splits of ws[(cb, chunk, split)][r * CC + ci % CC][s * CO + co % CO]
+// ... and db[o] = sum over the bias_grad_partial blocks (threads past the dW range)
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co, int ci, int cc, int cob, int ci_chunks, int splits) {
+wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co, int ci, int cc, int cob, int ci_chunks, int splits,
+                    const float* __restrict__ bias_part, int bias_blocks, float* __restrict__ db) {
   pdl_wait();
   pdl_trigger();
   const int cols = 3 * cob;
   const size_t cta_stride = (size_t)(3 * cc) * cols;
   const int total = co * 9 * ci;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + (db ? co : 0); i += gridDim.x * blockDim.x) {
+    if (i >= total) {
+      const int o = i - total;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int b = 0;
+      for (; b + 4 <= bias_blocks; b += 4) {
+        a0 += bias_part[(size_t)b * co + o]; a1 += bias_part[(size_t)(b + 1) * co + o];
+        a2 += bias_part[(size_t)(b + 2) * co + o]; a3 += bias_part[(size_t)(b + 3) * co + o];
+      }
+      for (; b < bias_blocks; ++b) a0 += bias_part[(size_t)b * co + o];
+      db[o] = (a0 + a1) + (a2 + a3);
+      continue;
+    }
     const int c = i % ci, tap = (i / ci) % 9, o = i / (9 * ci);
     const int r = tap / 3, s = tap - r * 3;
     const int pair = (o / cob) * ci_chunks + c / cc;
@@ -236,22 +250,6 @@ bias_grad_partial_kernel(const float* __restrict__ dz, long long pixels, int c, 
     *reinterpret_cast<float4*>(part + (size_t)blockIdx.x * c + threadIdx.x * 4) = s;
   }
 }
-__global__ void __launch_bounds__(256)
-bias_grad_final_kernel(const float* __restrict__ part, int blocks, int c, float* __restrict__ db) {
-  pdl_wait();
-  pdl_trigger();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int b = 0;
-  for (; b + 4 <= blocks; b += 4) {
-    a0 += part[(size_t)b * c + i]; a1 += part[(size_t)(b + 1) * c + i];
-    a2 += part[(size_t)(b + 2) * c + i]; a3 += part[(size_t)(b + 3) * c + i];
-  }
-  for (; b < blocks; ++b) a0 += part[(size_t)b * c + i];
-  db[i] = (a0 + a1) + (a2 + a3);
-}
-
 // ---- host side ---------------------------------------------------------------------------------
 static PFN_cuTensorMapEncodeTiled g_wg_encode = nullptr;
 static int wg_get_encoder() {
@@ -280,7 +278,7 @@ static int wg_encode(CUtensorMap* m, const clslam_planes& p, bool padded_view, i
   return 0;
 }
 
-struct WgPlan { int cc, cob, co_blocks, ci_chunks, splits, grid, stages, smem; long long ws_bytes; };
+struct WgPlan { int cc, cob, co_blocks, ci_chunks, splits, grid, stages, smem; long long ws_bytes, partial_bytes; };
 
 static int wg_sms() {
   static int sms = 0;
@@ -320,9 +318,8 @@ static int wg_plan(int n, int h, int w, int ci, int co, WgPlan& p) {
   else if (p.cob == 32) wg_fill<32, 32>(p);
   else if (p.cob == 64) wg_fill<32, 64>(p);
   else wg_fill<32, 128>(p);
-  p.ws_bytes = (long long)p.grid * (3 * p.cc) * (3 * p.cob) * 4;
-  const long long bias_bytes = (long long)kBiasBlocks * co * 4;
-  if (p.ws_bytes < bias_bytes) p.ws_bytes = bias_bytes;
+  p.partial_bytes = ((long long)p.grid * (3 * p.cc) * (3 * p.cob) * 4 + 255) / 256 * 256;
+  p.ws_bytes = p.partial_bytes + (long long)kBiasBlocks * co * 4;        // + the bias_grad partial sums
   return p.stages >= 2 ? 0 : -1;
 }
 
@@ -381,19 +378,20 @@ int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_plane
   else if (p.cob == 64) rc = wg_launch<32, 64>(mx, mdz, g, p, st);
   else rc = wg_launch<32, 128>(mx, mdz, g, p, st);
   if (rc) return rc;
-  const int total = dz->c * 9 * x->c;
+  float* bias_part = nullptr;
+  if (db) {       // bias gradient from the fp32 dz: per-block channel sums, folded into the reduction kernel below
+    if (!dz_f32 || dz->c > 256) { set_error("wgrad3x3_tma: db needs dz_f32 and co <= 256"); return -1; }
+    bias_part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + p.partial_bytes);
+    const long long pixels = (long long)dz->n * dz->h * dz->w;
+    launch_k(bias_grad_partial_kernel, dim3(kBiasBlocks), dim3(256), 0, st, dz_f32, pixels, dz->c, bias_part);
+    if ((rc = finish_launch("bias_grad"))) return rc;
+  }
+  const int total = dz->c * 9 * x->c + (db ? dz->c : 0);
   int blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, g.ws, dw, dz->c, x->c, p.cc, p.cob, p.ci_chunks, p.splits);
-  rc = finish_launch("wgrad_reduce");
-  if (rc || !db) return rc;
-  // bias gradient from the fp32 dz (workspace reused after the reduction above: stream order)
-  if (!dz_f32 || dz->c > 256) { set_error("wgrad3x3_tma: db needs dz_f32 and co <= 256"); return -1; }
-  const long long pixels = (long long)dz->n * dz->h * dz->w;
-  launch_k(bias_grad_partial_kernel, dim3(kBiasBlocks), dim3(256), 0, st, dz_f32, pixels, dz->c, g.ws);
-  if ((rc = finish_launch("bias_grad"))) return rc;
-  launch_k(bias_grad_final_kernel, dim3((dz->c + 255) / 256), dim3(256), 0, st, g.ws, kBiasBlocks, dz->c, db);
-  return finish_launch("bias_grad_final");
+  launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, g.ws, dw, dz->c, x->c, p.cc, p.cob, p.ci_chunks, p.splits,
+           (const float*)bias_part, (int)kBiasBlocks, db);
+  return finish_launch("wgrad_reduce");
 }
 
 }  // extern "C"
