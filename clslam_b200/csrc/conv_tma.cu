@@ -54,7 +54,13 @@ struct TmaConvCfg {
   static constexpr int kBStage = 2 * kBPlane;
   static constexpr int kSlots = BN >= 32 ? 4 : BN / 8;        // epilogue column slots with work
   static constexpr int kAcc = BN <= 64 ? 4 : 2;               // accumulator stages in TMEM (thin layers: the hand-off latency dominates)
-  static constexpr int kTmemCols = kAcc * BN < 32 ? 32 : kAcc * BN;
+  // N-concatenation: with BN <= 64 one MMA multiplies A_hi by [B_hi; B_lo] (the lo plane follows the hi plane in the
+  // weight tile, N = 2 BN) into two column blocks that the epilogue adds, a second MMA adds A_lo.B_hi: two instructions
+  // per k step instead of three (an SS-mode MMA with M = 128 costs ~64 cycles for any N <= 128: it is bound by the A read)
+  static constexpr bool kNcat = BN <= 64;
+  static constexpr int kAccCols = kNcat ? 2 * BN : BN;        // TMEM columns of one accumulator stage
+  static constexpr int kTmemCols = kAcc * kAccCols < 32 ? 32 : kAcc * kAccCols;
+  static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM columns");
   // upper 32 bits of every K-major swizzled descriptor of this configuration (SBO = 8 rows, version 1, layout type)
   static constexpr uint32_t kDescHi = (uint32_t)((8 * kRowBytes) >> 4) | (1u << 14) |
                                       ((kRowBytes == 128 ? 2u : (kRowBytes == 64 ? 4u : 6u)) << 29);
@@ -170,6 +176,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   } else if (warp == 1) {
     // ===================== MMA issuer: warp-uniform loops (descriptors stay in uniform registers), one elected lane issues
     constexpr uint32_t idesc = umma_idesc_bf16(BN);
+    constexpr uint32_t idesc2 = umma_idesc_bf16(2 * BN);      // N-concatenated weight tile
     constexpr uint32_t kLbo = 1u << 16;
     const uint32_t a_ring = ((smem_u32(a_tiles) >> 4) & 0x3FFF) | kLbo;       // low descriptor words: start address >> 4
     const uint32_t b_ring = ((smem_u32(b_tiles) >> 4) & 0x3FFF) | kLbo;
@@ -180,7 +187,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int as = it % C::kAcc;
       mbar_wait(&t_empty[as], (uint32_t)(((it / C::kAcc) & 1) ^ 1));      // the epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * C::kAccCols);
       uint32_t accumulate = 0;
       for (int cs = 0; cs < (TMA_DBG(g, 512) ? 0 : n_cs); ++cs) {
         if (!TMA_DBG(g, 8)) { mbar_wait(&a_full[sa], (uint32_t)pa); tc_fence_after(); }
@@ -198,9 +205,14 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const uint64_t dah = make_desc(C::kDescHi, a_hi + o), dal = make_desc(C::kDescHi, a_hi + o + (C::kAPlane >> 4));
                 const uint64_t dbh = make_desc(C::kDescHi, b_st + o), dbl = make_desc(C::kDescHi, b_st + o + (C::kBPlane >> 4));
                 if (!TMA_DBG(g, 1)) {
-                  umma_bf16(tmem_d, dal, dbh, idesc, (r == 0 && j == 0) ? accumulate : 1u);
-                  umma_bf16(tmem_d, dah, dbl, idesc, 1u);
-                  umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                  if constexpr (C::kNcat) {
+                    umma_bf16(tmem_d, dah, dbh, idesc2, (r == 0 && j == 0) ? accumulate : 1u);     // A_hi.[B_hi; B_lo]
+                    umma_bf16(tmem_d, dal, dbh, idesc, 1u);                                         // + A_lo.B_hi
+                  } else {
+                    umma_bf16(tmem_d, dal, dbh, idesc, (r == 0 && j == 0) ? accumulate : 1u);
+                    umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                    umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                  }
                 }
               }
             }
@@ -224,9 +236,14 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               const uint64_t dah = make_desc(C::kDescHi, a_hi + o), dal = make_desc(C::kDescHi, a_hi + o + (C::kAPlane >> 4));
               const uint64_t dbh = make_desc(C::kDescHi, b_st + o), dbl = make_desc(C::kDescHi, b_st + o + (C::kBPlane >> 4));
               if (!TMA_DBG(g, 1)) {
-                umma_bf16(tmem_d, dal, dbh, idesc, (j == 0) ? accumulate : 1u);
-                umma_bf16(tmem_d, dah, dbl, idesc, 1u);
-                umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                if constexpr (C::kNcat) {
+                  umma_bf16(tmem_d, dah, dbh, idesc2, (j == 0) ? accumulate : 1u);
+                  umma_bf16(tmem_d, dal, dbh, idesc, 1u);
+                } else {
+                  umma_bf16(tmem_d, dal, dbh, idesc, (j == 0) ? accumulate : 1u);
+                  umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                  umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                }
               }
             }
             umma_commit(&b_empty[sb]);
@@ -280,7 +297,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll 1
         for (int c = slot * 8; c < BN; c += 32) {
           uint32_t r[8];
-          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c), r);
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + c), r);
+          if constexpr (C::kNcat) {               // + the A_hi.B_lo block
+            uint32_t r2[8];
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + BN + c), r2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
           const int n = nb * BN + c;
           if (!ok || n >= g.cout || TMA_DBG(g, 2)) continue;
           float v[8];
