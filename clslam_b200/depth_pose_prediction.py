@@ -174,6 +174,8 @@ class DepthPosePrediction:
         self._pose_runner = None
         self._graphs: Dict[Tuple, Any] = {}
         self._steps_run: Dict[int, int] = {}
+        self._aux_dev: Dict[Any, Tensor] = {}
+        self._weights_key: Dict[int, Any] = {}
         self.noise_provider: Optional[Callable[[int, Tuple[int, ...]], Tensor]] = None
         self.stage_all_inputs = True          # move every dict value to the device like :916-917
         self._mode = 'eval'
@@ -246,6 +248,7 @@ class DepthPosePrediction:
             self._prep[net] = prep
             # plans hold raw pointers into the prepared tensors: rebuild them
             self._engines.clear(); self._enc_runners.clear(); self._graphs.clear(); self._pose_runner = None
+            self._weights_key.clear()
         return prep
 
     def refresh_encoders(self) -> None:
@@ -308,7 +311,13 @@ class DepthPosePrediction:
                     dst.copy_(val.reshape(dst.shape), non_blocking=True)
                 inputs[key] = dst
             elif self.stage_all_inputs and isinstance(val, Tensor):
-                inputs[key] = val.to(self.device, non_blocking=True)
+                # keys the path does not read are still moved like :916-917, into cached device buffers (no allocation per call)
+                buf = self._aux_dev.get(key)
+                if buf is None or buf.shape != val.shape or buf.dtype != val.dtype:
+                    buf = torch.empty(val.shape, dtype=val.dtype, device=self.device)
+                    self._aux_dev[key] = buf
+                buf.copy_(val, non_blocking=True)
+                inputs[key] = buf
         missing = [k for k in smap if k not in inputs and not (k[0] == 'relative_distance' and eng.vel_scale == 0.0)]
         if missing:
             raise KeyError(f'batch dict lacks keys the adaptation path reads: {missing}')
@@ -316,6 +325,11 @@ class DepthPosePrediction:
 
     def _set_weights(self, eng: AdaptEngine, loss_sample_weights: Optional[Tensor]) -> None:
         b_global = eng.b_global
+        # the weights rarely change between calls: upload only when they do (a pageable H2D copy stalls the host)
+        key = None if loss_sample_weights is None else tuple(float(v) for v in loss_sample_weights.detach().flatten().tolist())
+        if self._weights_key.get(eng.b, 'unset') == (key, self.batch_size):
+            return
+        self._weights_key[eng.b] = (key, self.batch_size)
         if loss_sample_weights is None:
             w = torch.ones(self.batch_size) / self.batch_size          # :1032 (uses config batch_size)
         else:
