@@ -175,6 +175,8 @@ class DepthPosePrediction:
         self._graphs: Dict[Tuple, Any] = {}
         self._steps_run: Dict[int, int] = {}
         self._aux_dev: Dict[Any, Tensor] = {}
+        self._deferred: List[Tuple[Tensor, Tensor]] = []
+        self._copy_stream = None
         self._weights_key: Dict[int, Any] = {}
         self.noise_provider: Optional[Callable[[int, Tuple[int, ...]], Tensor]] = None
         self.stage_all_inputs = True          # move every dict value to the device like :916-917
@@ -299,10 +301,16 @@ class DepthPosePrediction:
             m[('rgb', 0, s)] = eng.color[s]
         return m
 
-    def _stage_inputs(self, inputs: Dict[Any, Tensor]) -> AdaptEngine:
+    def _stage_inputs(self, inputs: Dict[Any, Tensor], defer_unused: bool = False) -> AdaptEngine:
+        """copies the dict to the device in place (:916-917).  With ``defer_unused`` the values the path does not read are
+        only queued (``_flush_deferred`` moves them on a side stream after the step has been launched)."""
         batch = inputs[('rgb_aug', 0, 0)].shape[0]
         eng = self._engine(batch)
         smap = self._static_map(eng)
+        self._deferred = []
+        if defer_unused:
+            self._stage_event = torch.cuda.Event()
+            self._stage_event.record(torch.cuda.current_stream(self.device))
         for key in list(inputs.keys()):
             val = inputs[key]
             dst = smap.get(key)
@@ -316,12 +324,29 @@ class DepthPosePrediction:
                 if buf is None or buf.shape != val.shape or buf.dtype != val.dtype:
                     buf = torch.empty(val.shape, dtype=val.dtype, device=self.device)
                     self._aux_dev[key] = buf
-                buf.copy_(val, non_blocking=True)
+                if defer_unused:
+                    self._deferred.append((buf, val))
+                else:
+                    buf.copy_(val, non_blocking=True)
                 inputs[key] = buf
         missing = [k for k in smap if k not in inputs and not (k[0] == 'relative_distance' and eng.vel_scale == 0.0)]
         if missing:
             raise KeyError(f'batch dict lacks keys the adaptation path reads: {missing}')
         return eng
+
+    def _flush_deferred(self) -> None:
+        """H2D of the unused dict values on a side stream, overlapping the step; the caller's stream waits for them"""
+        if not self._deferred:
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self._copy_stream.wait_event(self._stage_event)     # readers of the cached buffers queued before this call are done
+        with torch.cuda.stream(self._copy_stream):
+            for buf, val in self._deferred:
+                buf.copy_(val, non_blocking=True)
+        cur.wait_stream(self._copy_stream)
+        self._deferred = []
 
     def _set_weights(self, eng: AdaptEngine, loss_sample_weights: Optional[Tensor]) -> None:
         b_global = eng.b_global
@@ -460,11 +485,12 @@ class DepthPosePrediction:
             loss_weights = global_sample_weights(self.batch_size, online_loss_weight, online_index)
         if training_data is not None:
             self._set_adapt(freeze_encoder=True)
-            eng = self._stage_inputs(training_data)
+            eng = self._stage_inputs(training_data, defer_unused=True)
             self._set_weights(eng, loss_weights)
             for _ in range(steps):
                 self._draw_noise(eng)
                 self._step(eng)
+            self._flush_deferred()          # unused dict values move while the step runs
             return self._collect(eng)
         self._set_eval()
         with torch.no_grad():
