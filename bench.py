@@ -208,7 +208,9 @@ def profile_ops(eng, pred, reps=5):
         if model is None and a and hasattr(a[0], 'inp'):          # clslam_conv_tma: 3x3 over planes
             t = a[0]
             full = 2 if t.pad_mode == 2 else 0
-            k_alg = t.inp.c * 9 if t.taps != 4 else 49 * (3 if t.inp.c == 16 else 6)       # conv1 (space-to-depth form): 7 x 7 x C
+            k_alg = t.inp.c * 9 if t.taps not in (2, 4) else 49 * (3 if t.inp.c == 16 else 6)       # conv1 (space-to-depth form): 7 x 7 x C
+            if t.taps == 2:
+                k_alg = 9 * t.inp.c // 4                                                        # 3x3 / stride 2 in space-to-depth form
             row.update(bound='tensor', amount=2.0 * t.inp.n * (t.inp.h + full) * (t.inp.w + full) * t.cout * k_alg, unit='FLOP')
         if model is not None:
             row.update(bound=model[0], amount=model[1], unit='B')

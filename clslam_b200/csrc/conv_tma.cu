@@ -441,6 +441,27 @@ stage_s2d_kernel(const float* __restrict__ a, const float* __restrict__ b, Plane
   }
 }
 
+// fp32 NHWC (n, h, w, c) -> 2x2 space-to-depth planes (n, h/2, w/2, 4c): channel (p*2 + q) * c + k of S2D pixel (y, x) is
+// channel k of pixel (2y + p, 2x + q).  A 3x3 / stride-2 / pad-1 convolution of the tensor is the 2x2 (rows o-1 .. o)
+// stride-1 convolution of this one with W'[co][r][s][(p, q, k)] = W[co][2r + p - 1][2s + q - 1][k] (zero for index -1).
+__global__ void __launch_bounds__(256)
+s2d_planes_kernel(const float* __restrict__ x, PlaneView out, int n, int h, int w, int c) {
+  pdl_wait();
+  pdl_trigger();
+  const int c4 = c / 4;
+  const size_t total = (size_t)n * h * w * c4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cc = (int)(i % c4) * 4;
+    size_t p = i / c4;
+    const int xw = (int)(p % w); p /= w;
+    const int yh = (int)(p % h);
+    const int img = (int)(p / h);
+    const float4 v4 = ld4(x + i * 4);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    planes_emit<4>(out, img, yh >> 1, xw >> 1, ((yh & 1) * 2 + (xw & 1)) * c + cc, v);
+  }
+}
+
 // ---- dgrad helpers ---------------------------------------------------------------------------------
 // Wt[ci'][2 - r][2 - s][co] = W[co][r][s][ci'] for ci' < n_ci, on both bf16 planes (a pure permutation): the weights
 // of the convolution that computes dX from dZ (taps flipped, channels transposed)
@@ -607,9 +628,9 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   const int cin = in.c, cout = p->cout;
   if (cin % 16 || cout % 16 || !p->w_hi || !p->w_lo) { set_error("conv3x3_tma: cin %% 16, cout %% 16, weights"); return -1; }
   if (p->pad_mode < 0 || p->pad_mode > 2) { set_error("conv3x3_tma: pad_mode"); return -1; }
-  const int taps = p->taps == 4 ? 4 : 3;
-  if (p->taps != 0 && p->taps != 3 && p->taps != 4) { set_error("conv3x3_tma: taps must be 3 or 4"); return -1; }
-  if (taps == 4 && p->pad_mode != CLSLAM_PAD_ZERO) { set_error("conv3x3_tma: the 4x4 form is zero padded"); return -1; }
+  const int taps = p->taps == 0 ? 3 : p->taps;
+  if (taps != 2 && taps != 3 && taps != 4) { set_error("conv3x3_tma: taps must be 2, 3 or 4"); return -1; }
+  if (taps != 3 && p->pad_mode != CLSLAM_PAD_ZERO) { set_error("conv3x3_tma: the 2x2 / 4x4 (space-to-depth) forms are zero padded"); return -1; }
   if (int rc = get_encoder()) return rc;
   const int kc = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16);
   const int bn = cout >= 128 ? 128 : (cout >= 64 ? 64 : (cout >= 32 ? 32 : 16));
@@ -645,7 +666,7 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   const int hp = in.h + 2, wp = in.w + 2;
   const bool padded_view = p->pad_mode == CLSLAM_PAD_REFLECT;
   __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(in.base) + in.c_off + (padded_view ? 0 : ((size_t)wp + 1) * in.c_total);
-  g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : -1);      // 4x4: input rows o - 2 .. o + 1
+  g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : -1);      // 4x4: input rows o - 2 .. o + 1; 2x2: o - 1 .. o
   const cuuint64_t adims[5] = {(cuuint64_t)cin, (cuuint64_t)(padded_view ? wp : in.w), (cuuint64_t)(padded_view ? hp : in.h),
                                (cuuint64_t)in.n, 2};
   const cuuint64_t astr[4] = {(cuuint64_t)in.c_total * 2, (cuuint64_t)wp * in.c_total * 2, (cuuint64_t)hp * wp * in.c_total * 2,
@@ -666,6 +687,11 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
     if (kc == 16 && bn == 64) return launch_tma_conv<16, 64, 4>(ma, mb, g, st);
     if (kc == 32 && bn == 64) return launch_tma_conv<32, 64, 4>(ma, mb, g, st);
     set_error("conv3x3_tma: the 4x4 form is built for 16 / 32 input channels and 64 output channels");
+    return -1;
+  }
+  if (taps == 2) {
+    if (kc == 64 && bn == 128) return launch_tma_conv<64, 128, 2>(ma, mb, g, st);
+    set_error("conv3x3_tma: the 2x2 form is built for input channels %% 64 == 0 and output channels %% 128 == 0");
     return -1;
   }
 #define CLSLAM_TMA_CASE(KC_, BN_) if (kc == KC_ && bn == BN_) return launch_tma_conv<KC_, BN_, 3>(ma, mb, g, st);
@@ -690,6 +716,19 @@ int clslam_stage_images_s2d(const float* img_a, const float* img_b, const clslam
   if (blocks > 148 * 16) blocks = 148 * 16;
   launch_k(stage_s2d_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), img_a, img_b, v, n, h, w, image_offset);
   return finish_launch("stage_images_s2d");
+}
+
+int clslam_planes_s2d_from_f32(const float* x, const clslam_planes* out, int n, int h, int w, int c, void* stream) {
+  if (int rc = check_planes(out, "planes_s2d_from_f32")) return rc;
+  if (h % 2 || w % 2 || c % 4 || out->n != n || out->h != h / 2 || out->w != w / 2 || out->c != 4 * c) {
+    set_error("planes_s2d_from_f32: output planes must be (%d, %d, %d, %d)", n, h / 2, w / 2, 4 * c); return -1;
+  }
+  const PlaneView v = make_plane_view(out, 1, 0);
+  const size_t total = (size_t)n * h * w * (c / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  launch_k(s2d_planes_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), x, v, n, h, w, c);
+  return finish_launch("planes_s2d_from_f32");
 }
 
 int clslam_wt_flip(const void* items_dev, int n_items, int max_elems, const void* w_hi, long long w_plane_stride, void* wt_hi,

@@ -110,7 +110,22 @@ class PreparedEncoder:
             hl[1] = (wk - hl[0].float()).to(torch.bfloat16)
             self.t['conv1.s2d_hl'] = hl
 
+        def put_conv_s2(name, conv):
+            """3x3 / s2 / p1 conv as a 2x2 convolution over the 2x2 space-to-depth input:
+            W'[co][r][s][(p, q, k)] = W[co][k][2r + p - 1][2s + q - 1] (zero for index -1)"""
+            w = conv.weight.detach().to(device=device, dtype=torch.float32)
+            co, ci = w.shape[0], w.shape[1]
+            wp = w.new_zeros(co, ci, 4, 4)
+            wp[:, :, 1:, 1:] = w
+            wk = wp.view(co, ci, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(co, 2, 2, 4 * ci)
+            hl = torch.empty(2, *wk.shape, dtype=torch.bfloat16, device=device)
+            hl[0] = wk.to(torch.bfloat16)
+            hl[1] = (wk - hl[0].float()).to(torch.bfloat16)
+            self.t[name + '.s2d_hl'] = hl
+
         with torch.no_grad():
+            for li in (2, 3, 4):
+                put_conv_s2(f'layer{li}.0.conv1', getattr(r, f'layer{li}')[0].conv1)
             put_conv1_s2d(r.conv1)
             put_conv('conv1', r.conv1, self.cin_pad)
             put_bn('bn1', r.bn1)
@@ -337,9 +352,17 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Te
             # ---- conv1 -> mid
             mid_pl = PlaneBuf(plan, n, ho, wo, planes).view() if use2 else None
             mid_f32 = plan.alloc(n, ho, wo, planes) if not use2 else None
+            use_s2 = stride == 2 and use2 and planes % 128 == 0 and cin % 16 == 0 and hc % 2 == 0 and wc % 2 == 0
             if use1:
                 plan.conv_tma(f'{tag}.{p}.conv1', x_pl, L.PAD_ZERO, planes, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'],
                               t[p + '.bn1.scale'], t[p + '.bn1.shift'], L.ACT_RELU, y=mid_f32, out=mid_pl)
+            elif use_s2:            # stride-2 conv on the TMA kernel: 2x2 taps over the space-to-depth planes of the input feature
+                s2d = PlaneBuf(plan, n, hc // 2, wc // 2, 4 * cin).view()
+                plan.add(f'{tag}.{p}.s2d', lambda stream, ws, xp, o, hh, ww, cc: plan.lib.clslam_planes_s2d_from_f32(
+                    xp, ctypes.byref(o), n, hh, ww, cc, stream), _p(x_f32), s2d, hc, wc, cin)
+                hl = t[p + '.conv1.s2d_hl']
+                plan.conv_tma(f'{tag}.{p}.conv1', s2d, L.PAD_ZERO, planes, hl[0], hl[1], t[p + '.bn1.scale'], t[p + '.bn1.shift'],
+                              L.ACT_RELU, y=mid_f32, out=mid_pl, taps=2)
             else:
                 plan.conv_fwd(f'{tag}.{p}.conv1', d1, x_f32, None, t[p + '.conv1.w'], t[p + '.bn1.scale'], t[p + '.bn1.shift'],
                               None, mid_f32, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'], out=mid_pl)

@@ -135,7 +135,8 @@ typedef struct clslam_conv_tma {
   const clslam_planes* out;       /* optional */
   int out_up;              /* 1 or 2 (nearest up-sampling on write) */
   int out_halo;            /* write the reflection halo of `out` */
-  int taps;                /* 0 / 3: 3x3.  4: 4x4 kernel over input rows / cols o-2 .. o+1, zero padded, weights [cout][4][4][in.c]
+  int taps;                /* 0 / 3: 3x3.  2: 2x2 kernel over input rows / cols o-1 .. o (space-to-depth form of a 3x3 / stride-2 conv).
+                              4: 4x4 kernel over input rows / cols o-2 .. o+1, zero padded, weights [cout][4][4][in.c]
                               (the space-to-depth form of the encoders' 7x7 / stride-2 conv1, clslam_stage_images_s2d) */
 } clslam_conv_tma;
 int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
@@ -168,6 +169,10 @@ int clslam_debug_tma_flags(int flags);
  * `image_offset` .. + n. */
 int clslam_stage_images_s2d(const float* img_a, const float* img_b, const clslam_planes* out, int image_offset, int n, int h, int w,
                             void* stream);
+/* fp32 NHWC (n, h, w, c) -> 2x2 space-to-depth planes (n, h/2, w/2, 4c), zero halo: the input of a 3x3 / stride-2 / pad-1
+ * convolution (torchvision BasicBlock conv1 of layer2-4) run as clslam_conv3x3_tma(taps = 2) with
+ * W'[co][r][s][(p, q, k)] = W[co][2r + p - 1][2s + q - 1][k]. */
+int clslam_planes_s2d_from_f32(const float* x, const clslam_planes* out, int n, int h, int w, int c, void* stream);
 /* clslam_conv_fwd_bf16w / clslam_maxpool3x3s2 that additionally emit their result as planes */
 int clslam_conv_fwd_emit(const clslam_conv_desc* d, const float* x, const float* x2, const float* w, const void* w_hi,
                          const void* w_lo, const float* scale, const float* shift, const float* residual, float* y,

@@ -337,3 +337,29 @@ def test_conv1_space_to_depth(two):
     L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv1 s2d')
     torch.cuda.synchronize()
     assert cabi.rel_err(cabi.nchw(y), ref) < TOL
+
+
+def test_stride2_conv_space_to_depth():
+    """BasicBlock conv1 of layer2-4 (3x3 / stride 2 / pad 1) as the 2x2 TMA convolution of the S2D planes"""
+    lib = cabi.lib()
+    n, h, w, ci, co = 2, 24, 40, 64, 128
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    scale, shift = 1 + 0.2 * rnd(co, seed=3), 0.1 * rnd(co, seed=4)
+    ref = F.relu(F.conv2d(x, wt, None, 2, 1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1))
+    xg = cabi.nhwc(x).float().cuda()
+    buf = PlaneBuf(n, h // 2, w // 2, 4 * ci)
+    bd = buf.desc()
+    L.check(lib.clslam_planes_s2d_from_f32(xg.data_ptr(), ctypes.byref(bd), n, h, w, ci, cabi.stream()), 's2d')
+    wp = torch.zeros(co, ci, 4, 4, dtype=torch.float64)
+    wp[:, :, 1:, 1:] = wt
+    wk = wp.view(co, ci, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(co, 2, 2, 4 * ci)
+    hi, lo = cabi.split_bf16(wk.float().cuda())
+    y = torch.full((n, h // 2, w // 2, co), float('nan'), device='cuda')
+    sc, sh = scale.float().cuda(), shift.float().cuda()
+    a = L.ConvTma()
+    a.inp = bd; a.pad_mode = L.PAD_ZERO; a.cout = co; a.w_hi = hi.data_ptr(); a.w_lo = lo.data_ptr()
+    a.scale = sc.data_ptr(); a.shift = sh.data_ptr(); a.act = L.ACT_RELU; a.y = y.data_ptr(); a.out_up = 1; a.taps = 2
+    L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv s2 s2d')
+    torch.cuda.synchronize()
+    assert cabi.rel_err(cabi.nchw(y), ref) < TOL
