@@ -44,16 +44,21 @@ struct WgCfg {
   static constexpr int kBBytes = kAtoms * kBAtom;
   static constexpr int kStage = kABytes + kBBytes;
   static constexpr int kTail = 8 * kWgW * kRowA;              // the junk row blocks of the last stage stay inside the allocation
-  static constexpr int kCols = 3 * CO;                        // one accumulator per horizontal tap
-  static constexpr int kTmemCols = kCols <= 32 ? 32 : (kCols <= 64 ? 64 : (kCols <= 128 ? 128 : (kCols <= 256 ? 256 : 512)));
+  static constexpr int kCols = 3 * CO;                        // workspace columns: one block per horizontal tap
+  // N-concatenation (CO <= 64: one channel atom per plane): x_hi . [dz_hi | dz_lo] in one MMA (the lo plane follows the hi
+  // plane, leading-dimension offset = one plane) + x_lo . dz_hi: two instructions per 16 pixels and tap instead of three
+  static constexpr bool kNcat = CO <= 64;
+  static constexpr int kAccCols = kNcat ? 2 * CO : CO;        // TMEM columns per horizontal tap
+  static constexpr int kTmemNeed = 3 * kAccCols;
+  static constexpr int kTmemCols = kTmemNeed <= 32 ? 32 : (kTmemNeed <= 64 ? 64 : (kTmemNeed <= 128 ? 128 : (kTmemNeed <= 256 ? 256 : 512)));
   static constexpr uint32_t layout_of(int row_bytes) { return row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u); }
   // upper descriptor words: SBO (stride between 8-pixel groups) | version 1 | swizzle mode
   static constexpr uint32_t kDescHiA = (uint32_t)((8 * kRowA) >> 4) | (1u << 14) | (layout_of(kRowA) << 29);
   static constexpr uint32_t kDescHiB = (uint32_t)((8 * kRowB) >> 4) | (1u << 14) | (layout_of(kRowB) << 29);
   static constexpr uint32_t kLboA = (uint32_t)((kWgW * kRowA) >> 4) << 16;       // next row block = next patch row
-  static constexpr uint32_t kLboB = (uint32_t)(kBAtom >> 4) << 16;               // next 64-channel atom of dz
+  static constexpr uint32_t kLboB = (uint32_t)((kNcat ? kBPlane : kBAtom) >> 4) << 16;   // next N block: the lo plane (N-concat) or the next 64-channel atom
   static_assert(kStage % 1024 == 0, "stage alignment");
-  static_assert(kCols <= 512, "TMEM");
+  static_assert(kTmemNeed <= 512, "TMEM");
 };
 
 struct WgArgs {
@@ -129,6 +134,7 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   } else if (warp == 1) {
     // MMA issuer: warp-uniform loop (descriptors in uniform registers), one elected lane issues
     constexpr uint32_t idesc = umma_idesc_bf16_mn(CO);
+    constexpr uint32_t idesc2 = umma_idesc_bf16_mn(2 * CO);
     const uint32_t ring = (smem_u32(tiles) >> 4) & 0x3FFF;
     int st = 0, ph = 0;
     uint32_t acc = 0;
@@ -148,10 +154,15 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             const uint32_t a_hi = (a0 + (uint32_t)((s * C::kAShift + rr * kWgW * C::kRowA) >> 4)) | C::kLboA;
             const uint32_t a_lo = a_hi + (uint32_t)(C::kAPlane >> 4);
             const uint64_t dah = wg_desc(C::kDescHiA, a_hi), dal = wg_desc(C::kDescHiA, a_lo);
-            const uint32_t d = tmem_base + (uint32_t)(s * CO);
-            umma_bf16(d, dal, dbh, idesc, rr == 0 ? acc : 1u);
-            umma_bf16(d, dah, dbl, idesc, 1u);
-            umma_bf16(d, dah, dbh, idesc, 1u);
+            const uint32_t d = tmem_base + (uint32_t)(s * C::kAccCols);
+            if constexpr (C::kNcat) {
+              umma_bf16(d, dah, dbh, idesc2, rr == 0 ? acc : 1u);       // x_hi . [dz_hi | dz_lo]
+              umma_bf16(d, dal, dbh, idesc, 1u);                        // + x_lo . dz_hi
+            } else {
+              umma_bf16(d, dal, dbh, idesc, rr == 0 ? acc : 1u);
+              umma_bf16(d, dah, dbl, idesc, 1u);
+              umma_bf16(d, dah, dbh, idesc, 1u);
+            }
           }
         }
         umma_commit(&empty[st]);
@@ -173,7 +184,16 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 #pragma unroll 1
     for (int c = 0; c < C::kCols; c += 8) {
       uint32_t r[8];
-      tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      if constexpr (C::kNcat) {             // tap block s = c / CO: its two column halves (x_hi.dz_hi + x_lo.dz_hi, x_hi.dz_lo) are added here
+        const int sblk = c / CO, cc = c - sblk * CO;
+        uint32_t r2[8];
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sblk * C::kAccCols + cc), r);
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sblk * C::kAccCols + CO + cc), r2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+      } else {
+        tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+      }
       if (l < 3 * CC && t_end > t_begin) {
         *reinterpret_cast<float4*>(dst + c) = make_float4(__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3]));
         *reinterpret_cast<float4*>(dst + c + 4) = make_float4(__uint_as_float(r[4]), __uint_as_float(r[5]), __uint_as_float(r[6]), __uint_as_float(r[7]));
@@ -211,7 +231,8 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
       db[o] = (a0 + a1) + (a2 + a3);
       continue;
     }
-    const int c = i % ci, tap = (i / ci) % 9, o = i / (9 * ci);
+    // work order (tap, ci, co) with co fastest: neighbouring threads read neighbouring workspace columns
+    const int o = i % co, c = (i / co) % ci, tap = i / (co * ci);
     const int r = tap / 3, s = tap - r * 3;
     const int pair = (o / cob) * ci_chunks + c / cc;
     const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
@@ -223,7 +244,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
       a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
     }
     for (; k < splits; ++k) a0 += p[(size_t)k * cta_stride];
-    dw[i] = (a0 + a1) + (a2 + a3);
+    dw[((size_t)o * 9 + tap) * ci + c] = (a0 + a1) + (a2 + a3);
   }
 }
 
