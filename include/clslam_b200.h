@@ -155,12 +155,13 @@ int clslam_dgrad_fold(const float* dxp, int n, int h, int w, int c, int up, cons
                       void* stream);
 /* wgrad of a 3x3 / stride-1 layer on tcgen05 with TMA-fed MN-major operands (no transposition): dW [co][3][3][ci] and
  * db [co] (may be NULL; reduced from the fp32 copy dz_f32 (n, h, w, co)) from the layer input planes `x` (pad_mode ZERO: interior view, REFLECT: stored halo) and the
- * output-gradient planes `dz` (zero halo), both (n, h, w).  Needs x->c % 16 == 0 and dz->c in {16, 32, 64, 128 * k}
- * (dz->c == 16 only when x->c % 32 != 0 ... see wg_plan).  Deterministic: per-CTA partials + fixed-order reduction. */
+ * output-gradient planes `dz` (zero halo), both (n, h, w).  Needs x->c % 32 == 0 and dz->c in {16, 32, 64, 128 * k}, or
+ * x->c == dz->c == 16 (the last decoder layer).  Deterministic: per-CTA partial sums + fixed-order reduction. */
 long long clslam_wgrad3x3_tma_workspace_bytes(int n, int h, int w, int ci, int co);
 int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_planes* dz, const float* dz_f32, float* dw, float* db,
                         void* workspace, long long workspace_bytes, void* stream);
-/* timing experiments only (results are wrong when != 0): 1 no MMA, 2 no epilogue body, 4 no weight ring, 8 no A loads */
+/* timing experiments only (results are wrong when != 0; the tests are compiled out unless the library is built with
+ * -DCLSLAM_TMA_DEBUG): 1 no MMA, 2 no epilogue body, 4 no weight ring, 8 no A loads */
 int clslam_debug_tma_flags(int flags);
 
 /* Input staging for conv1 on the TMA kernel: (x - 0.45) / 0.225 (networks/resnet_encoder.py:117), channel concat of
