@@ -239,20 +239,44 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
             const int* __restrict__ step_dev) {
   pdl_wait();
   pdl_trigger();
-  // step_dev holds the number of updates done BEFORE this one (adam_tick_kernel bumps it after)
-  const int step = step_dev ? (*step_dev + 1) : step_host;
-  const double bc1 = 1.0 - pow(beta1, (double)step);
-  const double bc2 = 1.0 - pow(beta2, (double)step);
-  const float neg_step_size = (float)(-(lr / bc1));
-  const float bc2_sqrt = (float)sqrt(bc2);
+  // step_dev holds the number of updates done BEFORE this one (adam_tick_kernel bumps it after).
+  // The bias corrections need double-precision pow: one thread per block computes them, the rest read shared memory.
+  __shared__ float s_neg_step_size, s_bc2_sqrt;
+  if (threadIdx.x == 0) {
+    const int step = step_dev ? (*step_dev + 1) : step_host;
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    s_neg_step_size = (float)(-(lr / bc1));
+    s_bc2_sqrt = (float)sqrt(bc2);
+  }
+  __syncthreads();
+  const float neg_step_size = s_neg_step_size, bc2_sqrt = s_bc2_sqrt;
   const float w1 = (float)(1.0 - beta1), b2 = (float)beta2, w2 = (float)(1.0 - beta2), eps = (float)eps_d;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+  const long long n4 = n >> 2;                           // the flat buffers are padded to multiples of 64 elements
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = ld4(g + i * 4);
+    float4 m4 = *reinterpret_cast<const float4*>(m + i * 4), v4 = *reinterpret_cast<const float4*>(v + i * 4);
+    float4 p4 = *reinterpret_cast<const float4*>(p + i * 4);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float mm[4] = {m4.x, m4.y, m4.z, m4.w}, vv[4] = {v4.x, v4.y, v4.z, v4.w}, pp[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mm[j] = mm[j] + w1 * (gg[j] - mm[j]);              // exp_avg.lerp_(grad, 1 - beta1)
+      vv[j] = vv[j] * b2 + w2 * gg[j] * gg[j];           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+      const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
+      pp[j] = pp[j] + neg_step_size * mm[j] / denom;     // param.addcdiv_(exp_avg, denom, value=-step_size)
+    }
+    *reinterpret_cast<float4*>(p + i * 4) = make_float4(pp[0], pp[1], pp[2], pp[3]);
+    *reinterpret_cast<float4*>(m + i * 4) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(v + i * 4) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  }
+  for (long long i = (n4 << 2) + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i];
     float mi = m[i], vi = v[i];
-    mi = mi + w1 * (gi - mi);                            // exp_avg.lerp_(grad, 1 - beta1)
-    vi = vi * b2 + w2 * gi * gi;                         // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    mi = mi + w1 * (gi - mi);
+    vi = vi * b2 + w2 * gi * gi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] = p[i] + neg_step_size * mi / denom;            // param.addcdiv_(exp_avg, denom, value=-step_size)
+    p[i] = p[i] + neg_step_size * mi / denom;
     m[i] = mi; v[i] = vi;
   }
 }
