@@ -52,6 +52,25 @@ def tma_ok(n: int, h: int, w: int, ci: int, co: int, min_tiles: Optional[int] = 
     return n * ((h + 15) // 16) * ((w + 7) // 8) >= (TMA_MIN_TILES if min_tiles is None else min_tiles)
 
 
+def s2d_weights_7x7s2(w: torch.Tensor, cin_pad: int) -> torch.Tensor:
+    """conv1 (7x7 / stride 2 / pad 3, (co, ci, 7, 7)) as a 4x4 stride-1 convolution over the 2x2 space-to-depth input
+    (input rows o-2 .. o+1): W'[co][r][s][(p, q, c)] = W[co][c][2r + p - 1][2s + q - 1], zero outside the 7x7 window and
+    for the padding channels c >= ci.  Returns (co, 4, 4, 4 * cin_pad), channels (p * 2 + q) * cin_pad + c."""
+    co, ci = w.shape[0], w.shape[1]
+    wp = w.new_zeros(co, cin_pad, 8, 8)
+    wp[:, :ci, 1:, 1:] = w
+    return wp.view(co, cin_pad, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(co, 4, 4, 4 * cin_pad)
+
+
+def s2d_weights_3x3s2(w: torch.Tensor) -> torch.Tensor:
+    """3x3 / stride 2 / pad 1 conv ((co, ci, 3, 3)) as a 2x2 stride-1 convolution over the 2x2 space-to-depth input (input
+    rows o-1 .. o): W'[co][r][s][(p, q, k)] = W[co][k][2r + p - 1][2s + q - 1] (zero for index -1).  Returns (co, 2, 2, 4 * ci)."""
+    co, ci = w.shape[0], w.shape[1]
+    wp = w.new_zeros(co, ci, 4, 4)
+    wp[:, :, 1:, 1:] = w
+    return wp.view(co, ci, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(co, 2, 2, 4 * ci)
+
+
 class PlaneBuf:
     """bf16 hi/lo activation planes [2][n][h+2][w+2][c_total] (include/clslam_b200.h: clslam_planes)"""
 
@@ -98,26 +117,14 @@ class PreparedEncoder:
             self.t[name + '.shift'] = shift.to(device).contiguous()
 
         def put_conv1_s2d(conv):
-            """conv1 (7x7 / s2 / p3) as a 4x4 convolution over the 2x2 space-to-depth input:
-            W'[co][r][s][(p, q, c)] = W[co][c][2r + p - 1][2s + q - 1] (zero outside the 7x7 window)"""
-            w = conv.weight.detach().to(device=device, dtype=torch.float32)
-            co, ci = w.shape[0], w.shape[1]
-            wp = w.new_zeros(co, self.cin_pad, 8, 8)
-            wp[:, :ci, 1:, 1:] = w
-            wk = wp.view(co, self.cin_pad, 4, 2, 4, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(co, 4, 4, 4 * self.cin_pad)
+            wk = s2d_weights_7x7s2(conv.weight.detach().to(device=device, dtype=torch.float32), self.cin_pad)
             hl = torch.empty(2, *wk.shape, dtype=torch.bfloat16, device=device)
             hl[0] = wk.to(torch.bfloat16)
             hl[1] = (wk - hl[0].float()).to(torch.bfloat16)
             self.t['conv1.s2d_hl'] = hl
 
         def put_conv_s2(name, conv):
-            """3x3 / s2 / p1 conv as a 2x2 convolution over the 2x2 space-to-depth input:
-            W'[co][r][s][(p, q, k)] = W[co][k][2r + p - 1][2s + q - 1] (zero for index -1)"""
-            w = conv.weight.detach().to(device=device, dtype=torch.float32)
-            co, ci = w.shape[0], w.shape[1]
-            wp = w.new_zeros(co, ci, 4, 4)
-            wp[:, :, 1:, 1:] = w
-            wk = wp.view(co, ci, 2, 2, 2, 2).permute(0, 2, 4, 3, 5, 1).contiguous().view(co, 2, 2, 4 * ci)
+            wk = s2d_weights_3x3s2(conv.weight.detach().to(device=device, dtype=torch.float32))
             hl = torch.empty(2, *wk.shape, dtype=torch.bfloat16, device=device)
             hl[0] = wk.to(torch.bfloat16)
             hl[1] = (wk - hl[0].float()).to(torch.bfloat16)
