@@ -292,6 +292,8 @@ class Plan:
         n = (max(lanes) + 1) if lanes else 1
         self._ws = [torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=self.device) for _ in range(n)]
         self._ws_ptr = [t.data_ptr() for t in self._ws]
+        if torch.device(self.device).type != 'cuda':
+            return          # a plan built on the CPU can be inspected (tests of the wiring) but not run
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(n - 1)]
         for name, fn, args, lane in self.ops:
             if fn is None and args[0] not in self._events:

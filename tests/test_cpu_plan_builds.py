@@ -1,0 +1,63 @@
+"""The launch plan of the adaptation step (clslam_b200.engine.AdaptEngine) is host logic: it can be BUILT without a GPU
+(buffers on the CPU, workspace queries are pure host functions of the C-ABI library) and inspected, although not run.
+Guards the wiring: which layers go to the TMA kernels, lane / event structure, workspace sizes."""
+import pytest
+import torch
+
+from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
+from clslam_b200.engine import AdaptEngine, PreparedEncoder
+
+
+def build(b, h, w):
+    dev = torch.device('cpu')
+    pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b), device=dev)
+    dp = PreparedEncoder(pred.models['depth_encoder'], dev)
+    pp = PreparedEncoder(pred.models['pose_encoder'], dev)
+    return AdaptEngine(batch=b, height=h, width=w, batch_global=b, has_sample0=True, depth_prep=dp, pose_prep=pp, flat=pred._flat,
+                       min_depth=0.1, max_depth=None, disparity_smoothness=1e-3, velocity_loss_scaling=0.05, device=dev)
+
+
+def kinds(eng):
+    out = {}
+    for name, fn, a, lane in eng.plan.ops:
+        if fn is None:
+            continue
+        if a and hasattr(a[0], 'inp'):
+            k = 'conv_tma'
+        elif len(a) >= 2 and hasattr(a[0], 'c_total') and hasattr(a[1], 'c_total'):
+            k = 'wgrad_tma'
+        elif a and hasattr(a[0], 'kh'):
+            k = 'gather'
+        else:
+            k = 'other'
+        out[k] = out.get(k, 0) + 1
+    return out
+
+
+@pytest.mark.parametrize('b,h,w', [(1, 192, 640), (8, 192, 640), (2, 64, 96)])
+def test_plan_builds_and_is_consistent(b, h, w):
+    eng = build(b, h, w)
+    ops = eng.plan.ops
+    names = [o[0] for o in ops if o[1] is not None]
+    assert len(names) == len(set(names)), 'duplicate op names'
+    # every event that is waited for is recorded earlier in program order
+    seen = set()
+    for name, fn, a, lane in ops:
+        if fn is None and name == '__record__':
+            seen.add(a[0])
+        if fn is None and name == '__wait__':
+            assert a[0] in seen, f'wait on {a[0]} before it is recorded'
+    assert 0 < eng.n_fwd_core <= eng.n_fwd_ops < eng.n_bwd_ops == len(ops)
+    for must in ('photo_fwd', 'photo_bwd', 'loss_finalize', 'pose_head_fwd', 'pose_head_bwd', 'split_weights', 'wt_flip'):
+        assert must in names
+    # 36 trainable tensors = (weight, bias) of 10 upconv + 4 dispconv + 4 pose-decoder convolutions: one wgrad op each
+    assert sum(n.endswith('.wgrad') for n in names) == 18
+    k = kinds(eng)
+    if (b, h, w) == (8, 192, 640):
+        # batch 8: every 3x3 / 7x7 / stride-2 convolution runs the TMA kernels; 1x1 convolutions stay on the gather kernel
+        # (conv1 + 16 3x3 convs) per encoder, 10 decoder + 2 pose-decoder convs, 9 + 2 dgrads
+        assert k['conv_tma'] == 2 * 17 + 10 + 2 + 9 + 2
+        assert k['wgrad_tma'] == 12
+        assert k['gather'] <= 2 * 3 + 2 + 3 + 2 + 3               # downsample 1x1, squeeze / pose_2 (+ wgrad / dgrad)
+    if (b, h, w) == (2, 64, 96):
+        assert k.get('conv_tma', 0) == 0 or k['gather'] > 0       # tiny maps: mostly gather kernels
