@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
+
 #include "conv_ops.cuh"
 #include "planes.cuh"
 
@@ -86,11 +88,18 @@ struct TmaConvArgs {
   int gate_act;
   float* y;
   PlaneView out;                 // base == nullptr: none
+  // split-K form (SK instantiations only; appended so that the offsets above are those of the plain kernel): work item
+  // t = (tile, N block) * ksplit + z handles the (channel chunk, column shift) steps [z * cs_per, (z + 1) * cs_per) and
+  // stores its raw fp32 accumulators to part[z][pixel][cout]; tma_splitk_epilogue_kernel adds them in a fixed order
+  int ksplit, cs_per;
+  FastDiv div_ks;
+  float* part;
+  long long part_stride;         // elements between two z slices = n_img * ho * wo * cout
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
-template <int KC, int BN, int T>
+template <int KC, int BN, int T, bool SK = false>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TmaConvArgs g) {
   using C = TmaConvCfg<KC, BN, T>;
@@ -126,7 +135,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   pdl_trigger();
 
   const int tiles_per_img = g.tiles_x * g.tiles_y;
-  const int total = g.n_img * tiles_per_img * g.n_blocks;
+  const int total = g.n_img * tiles_per_img * g.n_blocks * (SK ? g.ksplit : 1);
   const int n_cs = g.chunks * T;
 
   if (warp == 0) {
@@ -143,13 +152,22 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     int sa = 0, pa = 0, sb = 0, pb = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      const int mt = g.div_nb.quot(t), nb = t - mt * g.n_blocks;
+      int tq = t, cs0 = 0, cs1 = n_cs;
+      if constexpr (SK) {
+        tq = g.div_ks.quot(t);
+        cs0 = (t - tq * g.ksplit) * g.cs_per;
+        cs1 = min(n_cs, cs0 + g.cs_per);
+      }
+      const int mt = g.div_nb.quot(tq), nb = tq - mt * g.n_blocks;
       const int img = g.div_tpi.quot(mt), rem = mt - img * tiles_per_img;
       const int ty = g.div_tx.quot(rem);
       const int oh0 = ty * kTmaTH + g.org, ow0 = (rem - ty * g.tiles_x) * kTmaTW + g.org;
       const int n0 = nb * BN;
-      for (int chunk = 0; chunk < g.chunks; ++chunk) {
+      for (int chunk = SK ? cs0 / T : 0; chunk < (SK ? (cs1 + T - 1) / T : g.chunks); ++chunk) {
         for (int sft = 0; sft < T; ++sft) {
+          if constexpr (SK) {
+            if (chunk * T + sft < cs0 || chunk * T + sft >= cs1) continue;
+          }
           if (!TMA_DBG(g, 8)) {
             mbar_wait(&a_empty[sa], (uint32_t)(pa ^ 1));
             if (elect_one()) {
@@ -189,7 +207,12 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * C::kAccCols);
       uint32_t accumulate = 0;
-      for (int cs = 0; cs < (TMA_DBG(g, 512) ? 0 : n_cs); ++cs) {
+      int cs_first = 0, cs_last = n_cs;
+      if constexpr (SK) {
+        cs_first = (t - g.div_ks.quot(t) * g.ksplit) * g.cs_per;
+        cs_last = min(n_cs, cs_first + g.cs_per);
+      }
+      for (int cs = cs_first; cs < (TMA_DBG(g, 512) ? 0 : cs_last); ++cs) {
         if (!TMA_DBG(g, 8)) { mbar_wait(&a_full[sa], (uint32_t)pa); tc_fence_after(); }
         const uint32_t a_st = a_ring + (uint32_t)(sa * (C::kAStage >> 4));
         if (resident) {
@@ -275,7 +298,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int as = it % C::kAcc;
-        const int mt = g.div_nb.quot(t), nb = t - mt * g.n_blocks;
+        int tq = t;
+        float* part = nullptr;
+        if constexpr (SK) {
+          tq = g.div_ks.quot(t);
+          part = g.part + (long long)(t - tq * g.ksplit) * g.part_stride;
+        }
+        const int mt = g.div_nb.quot(tq), nb = tq - mt * g.n_blocks;
         const int img = g.div_tpi.quot(mt), rem = mt - img * tiles_per_img;
         const int ty = g.div_tx.quot(rem);
         const int oh = ty * kTmaTH + (l >> 3), ow = (rem - ty * g.tiles_x) * kTmaTW + (l & 7);
@@ -309,6 +338,12 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           float v[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+          if constexpr (SK) {                     // raw partial sums; the epilogue proper runs in tma_splitk_epilogue_kernel
+            float* p = part + y_off + n;
+            *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            continue;
+          }
           if (g.scale) {
             const float4 s0 = ld4(g.scale + n), s1 = ld4(g.scale + n + 4);
             v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
@@ -384,6 +419,78 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ---- split-K epilogue --------------------------------------------------------------------------------
+// y = epilogue(sum_z part[z]) for the split-K form of conv3x3_tma_kernel: the z slices are added in a fixed order
+// (deterministic), then the same scale / shift / residual / activation / gate sequence as the fused epilogue above;
+// fp32 NHWC and / or planes (reflection halo, nearest 2x on write).  One thread = 8 channels of one output pixel.
+struct TmaSplitkEpiArgs {
+  int n_img, ho, wo, cout, ksplit;
+  long long part_stride;
+  const float* part;
+  int act;
+  const float* scale;
+  const float* shift;
+  PlaneView res;
+  const float* gate;
+  int gate_act;
+  float* y;
+  PlaneView out;
+};
+
+__global__ void __launch_bounds__(256)
+tma_splitk_epilogue_kernel(const TmaSplitkEpiArgs g) {
+  pdl_wait();
+  pdl_trigger();
+  const int c8 = g.cout / 8;
+  const size_t total = (size_t)g.n_img * g.ho * g.wo * c8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int n = (int)(i % c8) * 8;
+    size_t px = i / c8;
+    const int ow = (int)(px % g.wo); px /= g.wo;
+    const int oh = (int)(px % g.ho);
+    const int img = (int)(px / g.ho);
+    const size_t off = i * 8;                       // = ((img * ho + oh) * wo + ow) * cout + n
+    float v[8];
+    {
+      const float4 a = ld4(g.part + off), b = ld4(g.part + off + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    for (int z = 1; z < g.ksplit; ++z) {
+      const float* pz = g.part + (size_t)z * g.part_stride + off;
+      const float4 a = ld4(pz), b = ld4(pz + 4);
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    if (g.scale) {
+      const float4 s0 = ld4(g.scale + n), s1 = ld4(g.scale + n + 4);
+      v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+    }
+    if (g.shift) {
+      const float4 s0 = ld4(g.shift + n), s1 = ld4(g.shift + n + 4);
+      v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+    }
+    if (g.res.base) {
+      float r[8];
+      planes_load8(g.res, img, oh + 1, ow + 1, n, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = act_fast(v[j], g.act);
+    if (g.gate) {
+      const float4 g0 = ld4(g.gate + off), g1 = ld4(g.gate + off + 4);
+      v[0] *= act_grad_from_output(g0.x, g.gate_act); v[1] *= act_grad_from_output(g0.y, g.gate_act);
+      v[2] *= act_grad_from_output(g0.z, g.gate_act); v[3] *= act_grad_from_output(g0.w, g.gate_act);
+      v[4] *= act_grad_from_output(g1.x, g.gate_act); v[5] *= act_grad_from_output(g1.y, g.gate_act);
+      v[6] *= act_grad_from_output(g1.z, g.gate_act); v[7] *= act_grad_from_output(g1.w, g.gate_act);
+    }
+    if (g.y) {
+      *reinterpret_cast<float4*>(g.y + off) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(g.y + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    if (g.out.base) planes_emit<8>(g.out, img, oh, ow, n, v);
+  }
 }
 
 // ---- fp32 NHWC -> planes -------------------------------------------------------------------------
@@ -576,10 +683,10 @@ static int tma_num_sms() {
   return g_tma_sms;
 }
 
-template <int KC, int BN, int T>
+template <int KC, int BN, int T, bool SK = false>
 static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConvArgs g, cudaStream_t st) {
   using C = TmaConvCfg<KC, BN, T>;
-  auto kern = conv3x3_tma_kernel<KC, BN, T>;
+  auto kern = conv3x3_tma_kernel<KC, BN, T, SK>;
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemMax);
@@ -590,7 +697,7 @@ static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConv
   const int budget = kTmaSmemMax - 1024 - kTmaBarBytes;
   const long long w_bytes = (long long)g.chunks * T * T * C::kBStage;
   long long b_bytes;
-  if (g.n_blocks == 1 && w_bytes <= kTmaResidentMax && budget - w_bytes >= 3LL * C::kAStage) {
+  if (!SK && g.n_blocks == 1 && w_bytes <= kTmaResidentMax && budget - w_bytes >= 3LL * C::kAStage) {
     g.nbr = 0; b_bytes = w_bytes;
   } else {
     g.nbr = (KC == 64 && BN == 128) ? 3 : 6; b_bytes = (long long)g.nbr * C::kBStage;
@@ -599,10 +706,39 @@ static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConv
   g.na = (int)(na > kTmaMaxStages ? kTmaMaxStages : na);
   if (g.na < 2) { set_error("conv3x3_tma: shared memory plan failed"); return -3; }
   const int smem = (int)(g.na * C::kAStage + b_bytes + 1024 + kTmaBarBytes);
-  const long long total = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks;
+  const long long total = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks * (SK ? g.ksplit : 1);
   const int grid = (int)(total < tma_num_sms() ? total : tma_num_sms());
   launch_k(kern, dim3(grid), dim3(kTmaThreads), smem, st, ma, mb, g);
-  return finish_launch("conv3x3_tma");
+  return finish_launch(SK ? "conv3x3_tma (split-K)" : "conv3x3_tma");
+}
+
+// ---- split-K plan ------------------------------------------------------------------------------------
+// Layers whose output grid has fewer (tile, N block) work items than half the SMs (everything <= 24 x 80 at batch 1)
+// cannot fill the persistent kernel; their K = 9 * cin is long (cin 128..512), so the (channel chunk, column shift)
+// steps are spread over ksplit work items per tile.  Built for the shapes those layers have: 64-channel chunks,
+// N block 64 / 128, 3x3 and the 2x2 space-to-depth form.  CLSLAM_TMA_SPLITK_ITEMS overrides the item threshold.
+static int tma_splitk_items() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("CLSLAM_TMA_SPLITK_ITEMS");
+    v = e ? atoi(e) : tma_num_sms() / 2;
+    if (v < 0) v = 0;
+  }
+  return v;
+}
+struct TmaSplit { int ksplit, cs_per; };
+static TmaSplit tma_split_plan(long long items, int n_cs, int kc, int bn, int taps) {
+  TmaSplit sp{1, n_cs};
+  const bool built = kc == 64 && ((taps == 3 && (bn == 64 || bn == 128)) || (taps == 2 && bn == 128));
+  if (!built || items < 1 || items > tma_splitk_items() || n_cs < 2) return sp;
+  long long want = tma_num_sms() / items;            // one wave of work items
+  if (want > n_cs) want = n_cs;
+  if (want < 2) return sp;
+  sp.cs_per = (int)((n_cs + want - 1) / want);
+  sp.ksplit = (n_cs + sp.cs_per - 1) / sp.cs_per;     // every z slice has at least one step
+  // not worth it when the slices are badly balanced (3 steps as 2 + 1: the 48 x 160 / 64-channel layers at batch 1)
+  if (sp.ksplit < 2 || 5 * n_cs < 4 * sp.ksplit * sp.cs_per) { sp.ksplit = 1; sp.cs_per = n_cs; }
+  return sp;
 }
 
 static int check_planes(const clslam_planes* p, const char* what) {
@@ -619,9 +755,44 @@ static int check_planes(const clslam_planes* p, const char* what) {
 
 using namespace clslam;
 
+// geometry shared by the launch and the workspace query
+struct TmaGeom { int taps, kc, bn, ho, wo, tiles_x, tiles_y, n_blocks, chunks; long long items; };
+static int tma_geometry(const clslam_conv_tma* p, TmaGeom& q) {
+  if (!p) { set_error("conv3x3_tma: null"); return -1; }
+  const int cin = p->in.c, cout = p->cout;
+  if (cin < 16 || cin % 16 || cout < 16 || cout % 16) { set_error("conv3x3_tma: cin %% 16, cout %% 16"); return -1; }
+  q.taps = p->taps == 0 ? 3 : p->taps;
+  q.kc = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16);
+  q.bn = cout >= 128 ? 128 : (cout >= 64 ? 64 : (cout >= 32 ? 32 : 16));
+  const int full = p->pad_mode == CLSLAM_PAD_FULL;
+  q.ho = p->in.h + (full ? 2 : 0); q.wo = p->in.w + (full ? 2 : 0);
+  q.tiles_x = (q.wo + kTmaTW - 1) / kTmaTW; q.tiles_y = (q.ho + kTmaTH - 1) / kTmaTH;
+  q.n_blocks = cout / q.bn; q.chunks = cin / q.kc;
+  q.items = (long long)p->in.n * q.tiles_x * q.tiles_y * q.n_blocks;
+  return 0;
+}
+
+static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream);
+
 extern "C" {
 
-int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
+int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) { return conv3x3_tma_impl(p, nullptr, 0, stream); }
+
+long long clslam_conv3x3_tma_workspace_bytes(const clslam_conv_tma* p) {
+  TmaGeom q{};
+  if (tma_geometry(p, q)) return -1;
+  const TmaSplit sp = tma_split_plan(q.items, q.chunks * q.taps, q.kc, q.bn, q.taps);
+  if (sp.ksplit < 2) return 0;
+  return (long long)sp.ksplit * p->in.n * q.ho * q.wo * p->cout * 4;
+}
+
+int clslam_conv3x3_tma_ws(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream) {
+  return conv3x3_tma_impl(p, workspace, workspace_bytes, stream);
+}
+
+}  // extern "C"
+
+static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream) {
   if (!p) { set_error("conv3x3_tma: null"); return -1; }
   if (int rc = check_planes(&p->in, "conv3x3_tma.in")) return rc;
   const clslam_planes& in = p->in;
@@ -683,6 +854,37 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   if (int rc = encode(&mb, const_cast<void*>(p->w_hi), 3, bdims, bstr, bbox, kc * 2, "B")) return rc;
 
   cudaStream_t st = as_stream(stream);
+  if (workspace) {
+    const long long items = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks;
+    const TmaSplit sp = tma_split_plan(items, g.chunks * taps, kc, bn, taps);
+    if (sp.ksplit >= 2) {
+      const long long slice = (long long)in.n * ho * wo * cout;
+      if (workspace_bytes < sp.ksplit * slice * 4) {
+        set_error("conv3x3_tma: workspace too small (%lld < %lld)", workspace_bytes, sp.ksplit * slice * 4); return -2;
+      }
+      TmaConvArgs k = g;                    // the main kernel only stores raw partial sums
+      k.scale = nullptr; k.shift = nullptr; k.res = PlaneView{}; k.gate = nullptr; k.y = nullptr; k.out = PlaneView{};
+      k.act = CLSLAM_ACT_NONE;
+      k.ksplit = sp.ksplit; k.cs_per = sp.cs_per; k.div_ks = make_fastdiv(sp.ksplit);
+      k.part = reinterpret_cast<float*>(workspace); k.part_stride = slice;
+      int rc;
+      if (taps == 2) rc = launch_tma_conv<64, 128, 2, true>(ma, mb, k, st);
+      else if (bn == 128) rc = launch_tma_conv<64, 128, 3, true>(ma, mb, k, st);
+      else rc = launch_tma_conv<64, 64, 3, true>(ma, mb, k, st);
+      if (rc) return rc;
+      TmaSplitkEpiArgs e{};
+      e.n_img = in.n; e.ho = ho; e.wo = wo; e.cout = cout; e.ksplit = sp.ksplit;
+      e.part_stride = slice; e.part = k.part;
+      e.act = g.act; e.scale = g.scale; e.shift = g.shift; e.res = g.res; e.gate = g.gate; e.gate_act = g.gate_act;
+      e.y = g.y; e.out = g.out;
+      const long long threads = slice / 8;
+      int blocks = (int)((threads + 255) / 256);
+      if (blocks > 148 * 8) blocks = 148 * 8;
+      if (blocks < 1) blocks = 1;
+      launch_k(tma_splitk_epilogue_kernel, dim3(blocks), dim3(256), 0, st, e);
+      return finish_launch("conv3x3_tma (split-K epilogue)");
+    }
+  }
   if (taps == 4) {
     if (kc == 16 && bn == 64) return launch_tma_conv<16, 64, 4>(ma, mb, g, st);
     if (kc == 32 && bn == 64) return launch_tma_conv<32, 64, 4>(ma, mb, g, st);
@@ -702,6 +904,8 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) {
   set_error("conv3x3_tma: no kernel for channel chunk %d / N block %d", kc, bn);
   return -1;
 }
+
+extern "C" {
 
 int clslam_stage_images_s2d(const float* img_a, const float* img_b, const clslam_planes* out, int image_offset, int n, int h, int w,
                             void* stream) {

@@ -40,6 +40,16 @@ import os
 # below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: gather kernels (split-K) instead
 TMA_MIN_TILES = int(os.environ.get('CLSLAM_TMA_MIN_TILES', '24'))
 TMA_MIN_TILES_BWD = int(os.environ.get('CLSLAM_TMA_MIN_TILES_BWD', '24'))     # dgrad: the gather dgrad is slower, so the bar is lower
+# EXPERIMENTAL (off by default; written after this round's GPU budget was spent, not yet run on hardware): small-map layers
+# with 64-multiple channels also take the TMA kernel, in its split-K form (clslam_conv3x3_tma_ws)
+TMA_SPLITK = os.environ.get('CLSLAM_TMA_SPLITK', '0') == '1'
+# with TMA_SPLITK: also move the weight gradients of those layers to clslam_wgrad3x3_tma (default: they stay on the gather kernel)
+TMA_SPLITK_WGRAD = os.environ.get('CLSLAM_TMA_SPLITK_WGRAD', '0') == '1'
+
+
+def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
+    """enough 16 x 8 output tiles for the persistent kernel without split-K"""
+    return n * ((h + 15) // 16) * ((w + 7) // 8) >= (TMA_MIN_TILES if min_tiles is None else min_tiles)
 
 
 def tma_ok(n: int, h: int, w: int, ci: int, co: int, min_tiles: Optional[int] = None) -> bool:
@@ -49,7 +59,9 @@ def tma_ok(n: int, h: int, w: int, ci: int, co: int, min_tiles: Optional[int] = 
     bn = 128 if co >= 128 else (64 if co >= 64 else (32 if co >= 32 else 16))
     if co % bn:
         return False
-    return n * ((h + 15) // 16) * ((w + 7) // 8) >= (TMA_MIN_TILES if min_tiles is None else min_tiles)
+    if TMA_SPLITK and ci % 64 == 0 and co % 64 == 0:
+        return True
+    return tma_big(n, h, w, min_tiles)
 
 
 def s2d_weights_7x7s2(w: torch.Tensor, cin_pad: int) -> torch.Tensor:
@@ -246,6 +258,11 @@ class Plan:
             a.out = ctypes.pointer(out)
         a.out_up, a.out_halo, a.taps = out_up, out_halo, taps
         self.keep.append(a)
+        if TMA_SPLITK:      # small layers split K over the SMs (workspace: raw partial sums); large ones run the plain kernel
+            self.need_ws(self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a)))
+            self.ops.append((name, lambda stream, ws, arg: self.lib.clslam_conv3x3_tma_ws(ctypes.byref(arg), ws, self.ws_bytes, stream),
+                             (a,), self.lane))
+            return
         self.ops.append((name, lambda stream, ws, arg: self.lib.clslam_conv3x3_tma(ctypes.byref(arg), stream), (a,), self.lane))
 
     def conv_dgrad(self, name, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev) -> None:
@@ -684,7 +701,13 @@ class AdaptEngine:
         ud0 = {i: tma_ok(b, self.y[(i, 0)].shape[1] + 2, self.y[(i, 0)].shape[2] + 2, DEC_CH[i], DEC_CH[i + 1], TMA_MIN_TILES_BWD)
                for i in range(4)}
         ud0[4] = False
-        wg = {k: v is not None for k, v in self.dec_in_pl.items()}       # wgrad on tcgen05 needs the layer input as planes
+        # wgrad on tcgen05 needs the layer input as planes; the layers that only run the TMA kernel in its split-K form keep
+        # the gather wgrad unless CLSLAM_TMA_SPLITK_WGRAD=1
+        def wg_ok(key):
+            if self.dec_in_pl[key] is None:
+                return False
+            return (not TMA_SPLITK) or TMA_SPLITK_WGRAD or tma_big(b, self.y[key].shape[1], self.y[key].shape[2])
+        wg = {k: wg_ok(k) for k in self.dec_in_pl}
         dz_pl = {}
         for i in range(5):
             if ud1[i] or wg[(i, 1)]:
@@ -777,7 +800,8 @@ class AdaptEngine:
         dzp_pl = {name: PlaneBuf(plan, 2 * b, hp, wp, 256).view() for name in ('pose_1', 'pose_0')} if upd else {}
         for name in ('pose_2', 'pose_1', 'pose_0', 'squeeze'):
             d, xin = self.pose_desc[name]
-            if name in dzp_pl and self.pose_in_pl.get(name) is not None:
+            if name in dzp_pl and self.pose_in_pl.get(name) is not None and (
+                    (not TMA_SPLITK) or TMA_SPLITK_WGRAD or tma_big(2 * b, hp, wp, TMA_MIN_TILES_BWD)):
                 plan.conv_wgrad_tma(f'{name}.wgrad', 2 * b, hp, wp, self.pose_in_pl[name], L.PAD_ZERO, dzp_pl[name], self.dz_pose[name],
                                     flat.wgrad_ptr((pd, name)), flat.bgrad_ptr((pd, name)))
             else:

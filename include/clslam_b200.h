@@ -140,6 +140,15 @@ typedef struct clslam_conv_tma {
                               (the space-to-depth form of the encoders' 7x7 / stride-2 conv1, clslam_stage_images_s2d) */
 } clslam_conv_tma;
 int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
+/* Split-K form for the layers whose output grid is too small to fill the persistent kernel (the <= 24 x 80 maps of
+ * ResNet layer2-4, upconv_4_x .. upconv_2_0 and the pose decoder at batch 1): when the layer has fewer (16 x 8 tile,
+ * N block) work items than half the SMs, the (64-channel chunk, column shift) steps of K = 9 * cin are spread over
+ * ksplit work items per tile, each storing raw fp32 partial sums to `workspace` [ksplit][n][ho][wo][cout]; a second
+ * kernel adds them in a fixed order (deterministic) and applies the same epilogue.  Same arguments, same results up to
+ * fp32 summation order; layers that are large enough (or whose shape the split kernel is not built for: it needs
+ * in.c % 64 == 0, cout % 64 == 0, taps 3 or 2) run exactly clslam_conv3x3_tma and need no workspace (query returns 0). */
+long long clslam_conv3x3_tma_workspace_bytes(const clslam_conv_tma* p);
+int clslam_conv3x3_tma_ws(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream);
 /* dgrad of the 3x3 decoder convolutions on the same kernel (autograd of depth_pose_prediction.py:312):
  *   clslam_wt_flip: Wt[ci'][2-r][2-s][co] = W[co][r][s][ci'] (ci' < n_ci) for a batch of layers described by a DEVICE
  *     array of items {long long src, dst (element offsets into the planes); int co, ci, n_ci, pad}; planes are bf16 with

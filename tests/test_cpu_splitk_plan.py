@@ -1,0 +1,107 @@
+"""Host logic of the (experimental) split-K form of the TMA convolution: the work split that
+clslam_conv3x3_tma_workspace_bytes reports (a pure host function of the C-ABI library) and the launch plan the engine
+builds with CLSLAM_TMA_SPLITK=1.  Runs without a GPU; the kernels themselves are covered by
+tests/test_gpu_zz_conv_tma_splitk.py (opt-in)."""
+import ctypes
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+from clslam_b200 import _lib as L
+
+ROOT = Path(__file__).resolve().parent.parent
+SMS = 148
+
+
+def expected_split(n, h, w, ci, co, pad_mode=L.PAD_ZERO, taps=3):
+    """mirror of tma_split_plan (csrc/conv_tma.cu): (ksplit, steps per slice)"""
+    kc = 64 if ci % 64 == 0 else (32 if ci % 32 == 0 else 16)
+    bn = 128 if co >= 128 else (64 if co >= 64 else (32 if co >= 32 else 16))
+    full = 2 if pad_mode == L.PAD_FULL else 0
+    ho, wo = h + full, w + full
+    items = n * ((ho + 15) // 16) * ((wo + 7) // 8) * (co // bn)
+    n_cs = (ci // kc) * taps
+    built = kc == 64 and ((taps == 3 and bn in (64, 128)) or (taps == 2 and bn == 128))
+    if not built or items > SMS // 2 or n_cs < 2:
+        return 1, n_cs, ho, wo
+    want = min(SMS // items, n_cs)
+    if want < 2:
+        return 1, n_cs, ho, wo
+    per = -(-n_cs // want)
+    ks = -(-n_cs // per)
+    if ks < 2 or 5 * n_cs < 4 * ks * per:          # badly balanced slices: not worth it
+        return 1, n_cs, ho, wo
+    return ks, per, ho, wo
+
+
+def query(n, h, w, ci, co, pad_mode=L.PAD_ZERO, taps=3):
+    a = L.ConvTma()
+    a.inp = L.Planes(0, 0, n, h, w, ci, 0, ci)
+    a.pad_mode, a.cout, a.taps = pad_mode, co, taps
+    return L.load().clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+
+
+LAYERS = [
+    # the small-map layers of the batch-1 step at 192 x 640 ...
+    (1, 24, 80, 128, 128, L.PAD_ZERO, 3), (1, 12, 40, 256, 256, L.PAD_ZERO, 3), (1, 6, 20, 512, 512, L.PAD_ZERO, 3),
+    (2, 24, 80, 128, 128, L.PAD_ZERO, 3), (2, 12, 40, 256, 256, L.PAD_ZERO, 3), (2, 6, 20, 512, 512, L.PAD_ZERO, 3),
+    (1, 12, 40, 512, 256, L.PAD_ZERO, 2), (1, 6, 20, 1024, 512, L.PAD_ZERO, 2),          # layer3.0 / layer4.0 conv1, space-to-depth
+    (1, 6, 20, 512, 256, L.PAD_REFLECT, 3), (1, 12, 40, 512, 256, L.PAD_REFLECT, 3), (1, 12, 40, 256, 128, L.PAD_REFLECT, 3),
+    (1, 24, 80, 256, 128, L.PAD_REFLECT, 3), (1, 24, 80, 128, 64, L.PAD_REFLECT, 3),
+    (1, 12, 40, 256, 512, L.PAD_FULL, 3), (1, 24, 80, 128, 256, L.PAD_FULL, 3), (2, 6, 20, 256, 256, L.PAD_ZERO, 3),
+    # ... and layers that must NOT split: large grids, thin channels, conv1's 4x4 form
+    (1, 48, 160, 64, 64, L.PAD_ZERO, 3), (8, 24, 80, 128, 128, L.PAD_ZERO, 3), (1, 96, 320, 32, 16, L.PAD_REFLECT, 3),
+    (1, 24, 80, 96, 32, L.PAD_REFLECT, 3), (1, 96, 320, 16, 64, L.PAD_ZERO, 4),
+]
+
+
+@pytest.mark.parametrize('layer', LAYERS)
+def test_workspace_query_follows_the_split_rule(layer):
+    n, h, w, ci, co, pad_mode, taps = layer
+    ks, per, ho, wo = expected_split(n, h, w, ci, co, pad_mode, taps)
+    want = 0 if ks == 1 else ks * n * ho * wo * co * 4
+    assert query(n, h, w, ci, co, pad_mode, taps) == want
+    if ks > 1:
+        n_cs = (ci // 64) * taps
+        assert (ks - 1) * per < n_cs <= ks * per          # every slice has at least one (chunk, shift) step
+        items = n * ((ho + 15) // 16) * ((wo + 7) // 8) * (co // (128 if co >= 128 else 64))
+        assert items * ks <= SMS                           # one wave of work items
+
+
+def test_small_layers_do_split_and_large_do_not():
+    assert query(1, 6, 20, 512, 512) == 12 * 1 * 6 * 20 * 512 * 4          # 12 items -> 12 slices of 2 steps
+    assert query(1, 48, 160, 64, 64) == 0
+    assert query(1, 6, 20, 48, 64) == 0                                    # channel chunk 16: not built
+    assert query(1, 6, 20, 512, 500) == -1                                 # cout % 16
+
+
+def test_plan_with_splitk_flag():
+    """the engine's plan with CLSLAM_TMA_SPLITK=1 (read at import -> subprocess): every 3x3 / stride-2 layer of the batch-1 step
+    on the TMA kernel as at batch 8, wgrads of the small layers still on the gather kernel, workspace covers the partial sums"""
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+from tests.test_cpu_plan_builds import build, kinds
+eng = build(1, 192, 640)
+k = kinds(eng)
+ops = eng.plan.ops
+seen = set()
+for name, fn, a, lane in ops:
+    if fn is None and name == "__record__":
+        seen.add(a[0])
+    if fn is None and name == "__wait__":
+        assert a[0] in seen, name
+names = [o[0] for o in ops if o[1] is not None]
+assert len(names) == len(set(names))
+assert k["conv_tma"] == 2 * 17 + 10 + 2 + 9 + 2, k
+assert k["wgrad_tma"] == 5, k
+assert eng.plan.ws_bytes >= 12 * 6 * 20 * 512 * 4
+print("ok", k, eng.plan.ws_bytes)
+'''
+    env = dict(os.environ, CLSLAM_TMA_SPLITK='1')
+    r = subprocess.run([sys.executable, '-c', code], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith('ok')
