@@ -64,6 +64,7 @@ def workload_config(args, world):
         'tie_break_noise': 'torch.randn per scale (reference RNG semantics)',
         'conv_arithmetic': 'tcgen05 bf16 hi/lo split (3 products per fp32 product), fp32 accumulation in TMEM',
         'l2': 'flushed between timed steps (256 MiB memset, outside the per-step events)',
+        **({'small_maps': 'split-K TMA kernel (CLSLAM_TMA_SPLITK=1, experimental)'} if os.environ.get('CLSLAM_TMA_SPLITK') == '1' else {}),
     }
 
 

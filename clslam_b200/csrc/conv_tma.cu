@@ -594,12 +594,13 @@ wt_flip_kernel(const WtFlipItem* __restrict__ items, const uint16_t* __restrict_
 // dX from the "full" correlation dxp (n, H + 2, W + 2, c) of a reflection-padded layer: every interior pixel also
 // receives the halo cells that mirror onto it; up = 2 additionally sums the 2 x 2 nearest-neighbour footprint (the
 // layer read an up-sampled tensor).  Then + the dispconv input gradient, * act'(y_prev); written as fp32 and/or planes.
-__global__ void __launch_bounds__(256)
-dgrad_fold_kernel(const float* __restrict__ dxp, int n, int H, int W, int c, int up, const float* __restrict__ y_prev,
-                  int act_prev, const float* __restrict__ disp_dz, const float* __restrict__ disp_w,
-                  float* __restrict__ dz_prev, PlaneView po) {
-  pdl_wait();
-  pdl_trigger();
+// SK: dxp is the split-K workspace of the preceding conv3x3_tma_kernel<.., true> ([ksplit][n][H + 2][W + 2][c] raw partial
+// sums, slices `part_stride` elements apart): the fold also adds the slices (fixed order), replacing the split-K epilogue
+template <bool SK>
+__device__ __forceinline__ void dgrad_fold_body(const float* __restrict__ dxp, int n, int H, int W, int c, int up,
+                                                const float* __restrict__ y_prev, int act_prev, const float* __restrict__ disp_dz,
+                                                const float* __restrict__ disp_w, float* __restrict__ dz_prev, PlaneView po,
+                                                int ksplit, long long part_stride) {
   const int ho = H / up, wo = W / up, c4 = c / 4;
   const size_t total = (size_t)n * ho * wo * c4;
   const int Wp = W + 2;
@@ -622,7 +623,12 @@ dgrad_fold_kernel(const float* __restrict__ dxp, int n, int H, int W, int c, int
 #pragma unroll
           for (int cb = 0; cb < 3; ++cb) {
             if (cols[cb] < 0) continue;
-            f4add(acc, ld4(dxp + (((size_t)img * (H + 2) + rows[ra]) * Wp + cols[cb]) * c + cc));
+            const size_t cell = (((size_t)img * (H + 2) + rows[ra]) * Wp + cols[cb]) * c + cc;
+            if constexpr (SK) {
+              for (int z = 0; z < ksplit; ++z) f4add(acc, ld4(dxp + (size_t)z * part_stride + cell));
+            } else {
+              f4add(acc, ld4(dxp + cell));
+            }
           }
         }
       }
@@ -639,6 +645,24 @@ dgrad_fold_kernel(const float* __restrict__ dxp, int n, int H, int W, int c, int
       planes_emit<4>(po, img, oh, ow, cc, v);
     }
   }
+}
+
+__global__ void __launch_bounds__(256)
+dgrad_fold_kernel(const float* __restrict__ dxp, int n, int H, int W, int c, int up, const float* __restrict__ y_prev,
+                  int act_prev, const float* __restrict__ disp_dz, const float* __restrict__ disp_w,
+                  float* __restrict__ dz_prev, PlaneView po) {
+  pdl_wait();
+  pdl_trigger();
+  dgrad_fold_body<false>(dxp, n, H, W, c, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, po, 1, 0);
+}
+
+__global__ void __launch_bounds__(256)
+dgrad_fold_splitk_kernel(const float* __restrict__ part, int ksplit, long long part_stride, int n, int H, int W, int c, int up,
+                         const float* __restrict__ y_prev, int act_prev, const float* __restrict__ disp_dz,
+                         const float* __restrict__ disp_w, float* __restrict__ dz_prev, PlaneView po) {
+  pdl_wait();
+  pdl_trigger();
+  dgrad_fold_body<true>(part, n, H, W, c, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, po, ksplit, part_stride);
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -772,7 +796,16 @@ static int tma_geometry(const clslam_conv_tma* p, TmaGeom& q) {
   return 0;
 }
 
-static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream);
+// arguments of the fold that follows a PAD_FULL dgrad launch (clslam_dgrad_fold)
+struct FoldArgs {
+  int up;
+  const float* y_prev; int act_prev;
+  const float* disp_dz; const float* disp_w;
+  float* dz_prev; const clslam_planes* dz_prev_planes;
+};
+static int launch_fold(const float* dxp, int ksplit, long long part_stride, int n, int h, int w, int c, const FoldArgs& f, cudaStream_t st);
+static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream,
+                            const FoldArgs* fold = nullptr, bool* folded = nullptr);
 
 extern "C" {
 
@@ -792,7 +825,8 @@ int clslam_conv3x3_tma_ws(const clslam_conv_tma* p, void* workspace, long long w
 
 }  // extern "C"
 
-static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream) {
+static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream, const FoldArgs* fold,
+                            bool* folded) {
   if (!p) { set_error("conv3x3_tma: null"); return -1; }
   if (int rc = check_planes(&p->in, "conv3x3_tma.in")) return rc;
   const clslam_planes& in = p->in;
@@ -872,6 +906,10 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
       else if (bn == 128) rc = launch_tma_conv<64, 128, 3, true>(ma, mb, k, st);
       else rc = launch_tma_conv<64, 64, 3, true>(ma, mb, k, st);
       if (rc) return rc;
+      if (fold) {        // dgrad of a reflection-padded layer: the fold adds the slices itself
+        if (folded) *folded = true;
+        return launch_fold(k.part, sp.ksplit, slice, in.n, in.h, in.w, cout, *fold, st);
+      }
       TmaSplitkEpiArgs e{};
       e.n_img = in.n; e.ho = ho; e.wo = wo; e.cout = cout; e.ksplit = sp.ksplit;
       e.part_stride = slice; e.part = k.part;
@@ -903,6 +941,32 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
 #undef CLSLAM_TMA_CASE
   set_error("conv3x3_tma: no kernel for channel chunk %d / N block %d", kc, bn);
   return -1;
+}
+
+static int launch_fold(const float* dxp, int ksplit, long long part_stride, int n, int h, int w, int c, const FoldArgs& f, cudaStream_t st) {
+  const int up = f.up;
+  if ((up != 1 && up != 2) || c % 4 || h % up || w % up || h < 3 || w < 3) { set_error("dgrad_fold: bad dims"); return -1; }
+  if (f.disp_dz && up != 1) { set_error("dgrad_fold: dispconv term needs up == 1"); return -1; }
+  PlaneView po{};
+  if (f.dz_prev_planes) {
+    const clslam_planes* q = f.dz_prev_planes;
+    if (!q->base || q->n != n || q->h != h / up || q->w != w / up || q->c != c || q->c_total % 8 || q->c_off % 4) {
+      set_error("dgrad_fold: planes mismatch"); return -1;
+    }
+    po = make_plane_view(q, 1, 0);
+  }
+  if (!f.dz_prev && !po.base) { set_error("dgrad_fold: no output"); return -1; }
+  const size_t total = (size_t)n * (h / up) * (w / up) * (c / 4);
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  if (ksplit > 1) {
+    launch_k(dgrad_fold_splitk_kernel, dim3(blocks), dim3(256), 0, st, dxp, ksplit, part_stride, n, h, w, c, up, f.y_prev, f.act_prev,
+             f.disp_dz, f.disp_w, f.dz_prev, po);
+    return finish_launch("dgrad_fold (split-K)");
+  }
+  launch_k(dgrad_fold_kernel, dim3(blocks), dim3(256), 0, st, dxp, n, h, w, c, up, f.y_prev, f.act_prev, f.disp_dz, f.disp_w, f.dz_prev, po);
+  return finish_launch("dgrad_fold");
 }
 
 extern "C" {
@@ -951,21 +1015,22 @@ int clslam_wt_flip(const void* items_dev, int n_items, int max_elems, const void
 int clslam_dgrad_fold(const float* dxp, int n, int h, int w, int c, int up, const float* y_prev, int act_prev,
                       const float* disp_dz, const float* disp_w, float* dz_prev, const clslam_planes* dz_prev_planes,
                       void* stream) {
-  if ((up != 1 && up != 2) || c % 4 || h % up || w % up || h < 3 || w < 3) { set_error("dgrad_fold: bad dims"); return -1; }
-  if (disp_dz && up != 1) { set_error("dgrad_fold: dispconv term needs up == 1"); return -1; }
-  PlaneView po{};
-  if (dz_prev_planes) {
-    if (!dz_prev_planes->base || dz_prev_planes->n != n || dz_prev_planes->h != h / up || dz_prev_planes->w != w / up ||
-        dz_prev_planes->c != c || dz_prev_planes->c_total % 8 || dz_prev_planes->c_off % 4) { set_error("dgrad_fold: planes mismatch"); return -1; }
-    po = make_plane_view(dz_prev_planes, 1, 0);
+  const FoldArgs f{up, y_prev, act_prev, disp_dz, disp_w, dz_prev, dz_prev_planes};
+  return launch_fold(dxp, 1, 0, n, h, w, c, f, as_stream(stream));
+}
+
+int clslam_dgrad3x3_tma_ws(const clslam_conv_tma* p, int up, const float* y_prev, int act_prev, const float* disp_dz,
+                           const float* disp_w, float* dz_prev, const clslam_planes* dz_prev_planes, void* workspace,
+                           long long workspace_bytes, void* stream) {
+  if (!p || p->pad_mode != CLSLAM_PAD_FULL || !p->y || p->out || p->residual || p->gate || p->scale || p->shift ||
+      p->act != CLSLAM_ACT_NONE) {
+    set_error("dgrad3x3_tma: needs a plain PAD_FULL launch with the fp32 scratch output y"); return -1;
   }
-  if (!dz_prev && !po.base) { set_error("dgrad_fold: no output"); return -1; }
-  const size_t total = (size_t)n * (h / up) * (w / up) * (c / 4);
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (blocks < 1) blocks = 1;
-  launch_k(dgrad_fold_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), dxp, n, h, w, c, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, po);
-  return finish_launch("dgrad_fold");
+  const FoldArgs f{up, y_prev, act_prev, disp_dz, disp_w, dz_prev, dz_prev_planes};
+  bool folded = false;
+  if (int rc = conv3x3_tma_impl(p, workspace, workspace_bytes, stream, &f, &folded)) return rc;
+  if (folded) return 0;          // split-K: the fold read the partial sums directly
+  return launch_fold(p->y, 1, 0, p->in.n, p->in.h, p->in.w, p->cout, f, as_stream(stream));
 }
 
 int clslam_debug_tma_flags(int flags) { g_tma_debug = flags; return 0; }

@@ -265,6 +265,26 @@ class Plan:
             return
         self.ops.append((name, lambda stream, ws, arg: self.lib.clslam_conv3x3_tma(ctypes.byref(arg), stream), (a,), self.lane))
 
+    def dgrad_tma(self, name, dz_pl: L.Planes, cin_prev: int, wt_hi, wt_lo, dxp, n, h, w, up, y_prev, act_prev, disp_dz, disp_w,
+                  dz_prev, dz_prev_pl) -> None:
+        """dX of a reflection-padded 3x3 layer: full correlation of the dz planes with the flipped weights + fold
+        (clslam_conv3x3_tma(PAD_FULL) + clslam_dgrad_fold; with TMA_SPLITK one call, clslam_dgrad3x3_tma_ws, whose fold reads
+        the split-K partial sums directly)"""
+        if not TMA_SPLITK:
+            self.conv_tma(f'{name}', dz_pl, L.PAD_FULL, cin_prev, wt_hi, wt_lo, None, None, L.ACT_NONE, y=dxp)
+            self.dgrad_fold(f'{name}.fold', dxp, n, h, w, cin_prev, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, dz_prev_pl)
+            return
+        a = L.ConvTma()
+        a.inp = dz_pl
+        a.pad_mode, a.cout = L.PAD_FULL, cin_prev
+        a.w_hi, a.w_lo = _p(wt_hi), _p(wt_lo)
+        a.act, a.y, a.out_up, a.taps = L.ACT_NONE, _p(dxp), 1, 3
+        self.keep.append(a)
+        self.need_ws(self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a)))
+        self.add(name, lambda stream, ws, arg, *r: self.lib.clslam_dgrad3x3_tma_ws(
+            ctypes.byref(arg), *r[:6], ctypes.byref(r[6]) if r[6] is not None else None, ws, self.ws_bytes, stream),
+            a, up, _p(y_prev), act_prev, _p(disp_dz), _p(disp_w), _p(dz_prev), dz_prev_pl)
+
     def conv_dgrad(self, name, d, dz, w, y_prev, act_prev, disp_dz, disp_w, dz_prev) -> None:
         self.need_ws(self.lib.clslam_conv_dgrad_workspace_bytes(ctypes.byref(d)))
         self.add(name, self._conv_dgrad, d, _p(dz), _p(w), _p(y_prev), act_prev, _p(disp_dz), _p(disp_w), _p(dz_prev))
@@ -749,9 +769,8 @@ class AdaptEngine:
             nxt = dz_pl.get((i, 0))
             if ud1[i]:
                 wt_hi, wt_lo = self._wt_slot(key1, DEC_CH[i])
-                plan.conv_tma(f'upconv_{i}_1.dgrad', dz_pl[(i, 1)], L.PAD_FULL, DEC_CH[i], wt_hi, wt_lo, None, None, L.ACT_NONE, y=dxp)
-                plan.dgrad_fold(f'upconv_{i}_1.dgrad.fold', dxp, b, hi_, wi_, DEC_CH[i], 2, y0, L.ACT_ELU, None, None,
-                                self.dz[(i, 0)], nxt)
+                plan.dgrad_tma(f'upconv_{i}_1.dgrad', dz_pl[(i, 1)], DEC_CH[i], wt_hi, wt_lo, dxp, b, hi_, wi_, 2, y0, L.ACT_ELU,
+                               None, None, self.dz[(i, 0)], nxt)
             else:
                 plan.conv_dgrad(f'upconv_{i}_1.dgrad', d1, self.dz[(i, 1)], flat.weight_ptr(key1), y0, L.ACT_ELU, None, None,
                                 self.dz[(i, 0)])
@@ -779,10 +798,8 @@ class AdaptEngine:
                 if ud0[i]:
                     hl, wl = self.y[(i, 0)].shape[1], self.y[(i, 0)].shape[2]
                     wt_hi, wt_lo = self._wt_slot(key0, DEC_CH[i + 1])
-                    plan.conv_tma(f'upconv_{i}_0.dgrad', dz_pl[(i, 0)], L.PAD_FULL, DEC_CH[i + 1], wt_hi, wt_lo, None, None,
-                                  L.ACT_NONE, y=dxp)
-                    plan.dgrad_fold(f'upconv_{i}_0.dgrad.fold', dxp, b, hl, wl, DEC_CH[i + 1], 1, self.y[(i + 1, 1)], L.ACT_ELU,
-                                    disp_dz, disp_w, self.dz[(i + 1, 1)], nxt)
+                    plan.dgrad_tma(f'upconv_{i}_0.dgrad', dz_pl[(i, 0)], DEC_CH[i + 1], wt_hi, wt_lo, dxp, b, hl, wl, 1,
+                                   self.y[(i + 1, 1)], L.ACT_ELU, disp_dz, disp_w, self.dz[(i + 1, 1)], nxt)
                 else:
                     plan.conv_dgrad(f'upconv_{i}_0.dgrad', d0, self.dz[(i, 0)], flat.weight_ptr(key0), self.y[(i + 1, 1)],
                                     L.ACT_ELU, disp_dz, disp_w, self.dz[(i + 1, 1)])

@@ -149,6 +149,13 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
  * in.c % 64 == 0, cout % 64 == 0, taps 3 or 2) run exactly clslam_conv3x3_tma and need no workspace (query returns 0). */
 long long clslam_conv3x3_tma_workspace_bytes(const clslam_conv_tma* p);
 int clslam_conv3x3_tma_ws(const clslam_conv_tma* p, void* workspace, long long workspace_bytes, void* stream);
+/* dX of a reflection-padded layer in one call: clslam_conv3x3_tma_ws(p) with p->pad_mode = CLSLAM_PAD_FULL and the fp32
+ * scratch p->y (n, h + 2, w + 2, cout), followed by clslam_dgrad_fold(p->y, p->in.n, p->in.h, p->in.w, p->cout, up, ...).
+ * When the launch is split over K the fold reads the partial sums of the workspace directly (it adds the slices and the
+ * mirrored halo cells in one pass: no separate split-K epilogue, p->y untouched).  Workspace: clslam_conv3x3_tma_workspace_bytes(p). */
+int clslam_dgrad3x3_tma_ws(const clslam_conv_tma* p, int up, const float* y_prev, int act_prev, const float* disp_dz,
+                           const float* disp_w, float* dz_prev, const clslam_planes* dz_prev_planes, void* workspace,
+                           long long workspace_bytes, void* stream);
 /* dgrad of the 3x3 decoder convolutions on the same kernel (autograd of depth_pose_prediction.py:312):
  *   clslam_wt_flip: Wt[ci'][2-r][2-s][co] = W[co][r][s][ci'] (ci' < n_ci) for a batch of layers described by a DEVICE
  *     array of items {long long src, dst (element offsets into the planes); int co, ci, n_ci, pad}; planes are bf16 with

@@ -98,6 +98,8 @@ names = [o[0] for o in ops if o[1] is not None]
 assert len(names) == len(set(names))
 assert k["conv_tma"] == 2 * 17 + 10 + 2 + 9 + 2, k
 assert k["wgrad_tma"] == 5, k
+assert not any(n.endswith(".fold") for n in names)          # the reflection-padded dgrads fold inside clslam_dgrad3x3_tma_ws
+assert sum(n.endswith(".dgrad") for n in names) == 1 + 9 + 3
 assert eng.plan.ws_bytes >= 12 * 6 * 20 * 512 * 4
 print("ok", k, eng.plan.ws_bytes)
 '''

@@ -175,3 +175,57 @@ def test_large_layers_do_not_split():
     buf.set_padded(F.pad(x, (1, 1, 1, 1)))
     y0, y1, _, _ = run_both(buf.desc(), L.PAD_ZERO, cabi.krsc(wt), expect_split=False)
     assert torch.equal(y0, y1)
+
+
+@pytest.mark.parametrize('upcat', [False, True])
+def test_dgrad_splitk_fold_matches_two_step(upcat):
+    """clslam_dgrad3x3_tma_ws (split-K partial sums folded directly) against clslam_conv3x3_tma(PAD_FULL) + clslam_dgrad_fold
+    and against the gather dgrad (itself checked against fp64 in test_gpu_conv.py)"""
+    from tests.test_gpu_conv_tma import _planes_of, _wt_flip
+    lib = cabi.lib()
+    if upcat:        # upconv_3_1: reads cat[up2(y0), skip]; dX for the up-sampled branch only
+        n, h1, w1, c1, c2, co = 1, 12, 40, 128, 128, 128
+        h, w, ci = 2 * h1, 2 * w1, c1 + c2
+        d = cabi.make_desc(n, h, w, ci, co, 3, 1, 1, L.PAD_REFLECT, L.IN_UPCAT, c1, h1, w1, act=L.ACT_ELU)
+        n_ci, ho, wo = c1, h1, w1
+    else:            # upconv_3_0 with the dispconv_3 term
+        n, h, w, ci, co = 1, 12, 40, 256, 128
+        d = cabi.make_desc(n, h, w, ci, co, 3, 1, 1, L.PAD_REFLECT, act=L.ACT_ELU)
+        n_ci, ho, wo = ci, h, w
+    dz = rnd(n, h, w, co, seed=1).float().cuda()
+    wk = (rnd(co, 3, 3, ci, seed=2) * (ci * 9) ** -0.5).float().cuda()
+    y_prev = rnd(n, ho, wo, n_ci, seed=3).float().cuda()
+    disp_dz = None if upcat else rnd(n, 1, h, w, seed=4).float().cuda()
+    disp_w = None if upcat else (0.1 * rnd(1, 3, 3, ci, seed=5)).float().cuda()
+    ref = cabi.conv_dgrad(d, dz, wk, y_prev, L.ACT_ELU, disp_dz, disp_w)
+    wt_hi, wt_lo, keep = _wt_flip(wk, n_ci)
+    buf, pd = _planes_of(dz)
+    up = 2 if upcat else 1
+    res = []
+    for fused in (False, True):
+        dxp = torch.full((n, h + 2, w + 2, n_ci), float('nan'), device='cuda')
+        a = L.ConvTma()
+        a.inp = pd; a.pad_mode = L.PAD_FULL; a.cout = n_ci; a.w_hi = wt_hi.data_ptr(); a.w_lo = wt_lo.data_ptr()
+        a.act = L.ACT_NONE; a.y = dxp.data_ptr(); a.out_up = 1
+        got = torch.full((n, ho, wo, n_ci), float('nan'), device='cuda')
+        outp = PlaneBuf(n, ho, wo, n_ci)
+        od = outp.desc()
+        if fused:
+            nbytes = lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+            assert nbytes > 0, 'this layer is expected to split'
+            ws = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device='cuda')
+            L.check(lib.clslam_dgrad3x3_tma_ws(ctypes.byref(a), up, y_prev.data_ptr(), L.ACT_ELU, cabi.P(disp_dz), cabi.P(disp_w),
+                                               got.data_ptr(), ctypes.byref(od), ws.data_ptr(), nbytes, cabi.stream()), 'dgrad3x3_tma_ws')
+            torch.cuda.synchronize()
+            assert torch.isnan(dxp).all()          # the scratch is not touched on the split path
+        else:
+            L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma(full)')
+            L.check(lib.clslam_dgrad_fold(dxp.data_ptr(), n, h, w, n_ci, up, y_prev.data_ptr(), L.ACT_ELU, cabi.P(disp_dz),
+                                          cabi.P(disp_w), got.data_ptr(), ctypes.byref(od), cabi.stream()), 'dgrad_fold')
+            torch.cuda.synchronize()
+        res.append((got, outp))
+    (g0, o0), (g1, o1) = res
+    assert cabi.rel_err(g1, ref) < 1e-4
+    assert cabi.rel_err(g1, g0) < 2e-6
+    assert cabi.rel_err(o1.value(), o0.value()) < 2e-5
+    assert float(o1.t[:, :, 0].float().abs().max()) == 0.0          # gradient planes keep a zero halo
