@@ -26,7 +26,7 @@ def _sources():
 
 
 def _newest_header_mtime() -> float:
-    hdrs = list(CSRC.glob('*.cuh')) + list((ROOT / 'include').glob('*.h'))
+    hdrs = list(CSRC.glob('*.cuh')) + list(CSRC.glob('*.inc')) + list((ROOT / 'include').glob('*.h'))
     return max(h.stat().st_mtime for h in hdrs)
 
 

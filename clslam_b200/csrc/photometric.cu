@@ -2,6 +2,8 @@
 // border-clipped bilinear warp -> SSIM + L1 -> auto-mask min, and its hand-derived backward.
 // HBM-bound: each CTA owns a 32x16 pixel tile, stages the warped images of the tile + halo in
 // shared memory once and evaluates all 3x3 stencils from there.  See include/clslam_b200.h.
+#include <cstdlib>
+
 #include "photo_ops.cuh"
 
 namespace clslam {
@@ -103,10 +105,7 @@ photo_identity_kernel(const float* __restrict__ target, const float* __restrict_
 // ---- forward --------------------------------------------------------------------------------
 // One CTA = one 32x16 tile of one sample, looping over the scales: the target tile and its SSIM
 // window statistics are loaded / computed once and reused by every scale and both source frames.
-__global__ void __launch_bounds__(kPhotoThreads)
-photo_fwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
-  pdl_wait();
-  pdl_trigger();
+__device__ __forceinline__ void photo_fwd_body(const clslam_photo_args& a, int tiles_x, int tiles) {
   __shared__ float tg[3 * kFN];
   __shared__ float wx[2 * 3 * kFN];
   __shared__ float red[8];
@@ -243,181 +242,56 @@ photo_fwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
   }
 }
 
-// ---- backward -------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPhotoThreads)
-photo_bwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
+photo_fwd_kernel(clslam_photo_args a, int tiles_x, int tiles) {
   pdl_wait();
   pdl_trigger();
-  constexpr int kCW = kFW, kCN = kFN;      // coefficient maps cover tile + 1
-  __shared__ float tg[3 * kBN];
-  __shared__ float wx[3 * kBN];
-  __shared__ float coef[9 * kCN];          // [c][alpha,beta,gamma][pos]
-  __shared__ float red[8 * 12];
-  __shared__ float geo[16 + 24];
-  const int s = blockIdx.y / a.b, bb = blockIdx.y % a.b;
-  const int h = a.h, w = a.w, hs = h >> s, ws = w >> s;
-  const int tile = blockIdx.x;
-  const int tx0 = (tile % tiles_x) * kPhotoTW, ty0 = (tile / tiles_x) * kPhotoTH;
-  const size_t hw = (size_t)h * w;
-  if (threadIdx.x < 16) geo[threadIdx.x] = a.inv_k[bb * 16 + threadIdx.x];
-  else if (threadIdx.x < 40) {
-    const int i = threadIdx.x - 16, f = i / 12;
-    geo[threadIdx.x] = a.proj[((size_t)f * a.b + bb) * 12 + (i - f * 12)];
-  }
-  const float* disp_b = a.disp[s] + (size_t)bb * hs * ws;
-  const unsigned char* amin = a.argmin[s] + (size_t)bb * hw;
-  // d(loss)/d(min-reprojection value at a pixel): w_b / (n_scales * H * W)
-  const float g0 = ld1(a.sample_w + bb) / ((float)a.n_scales * (float)h * (float)w);
-
-  for (int i = threadIdx.x; i < kBN; i += kPhotoThreads) {
-    const int ly = i / kBW, lx = i - ly * kBW;
-    const size_t off = (size_t)pad_coord(ty0 + ly - 2, h) * w + pad_coord(tx0 + lx - 2, w);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) tg[c * kBN + i] = ld1(a.target + ((size_t)bb * 3 + c) * hw + off);
-  }
-  __syncthreads();
-
-  float ddepth[2] = {0.f, 0.f};
-  float dval[2] = {0.f, 0.f}, depthv[2] = {0.f, 0.f};
-  for (int f = 0; f < 2; ++f) {
-    const float* src = a.sources_rgba + ((size_t)f * a.b + bb) * hw * 4;
-    // phase 1: warped source on tile + 2
-    for (int i = threadIdx.x; i < kBN; i += kPhotoThreads) {
-      const int ly = i / kBW, lx = i - ly * kBW;
-      const int y = pad_coord(ty0 + ly - 2, h), x = pad_coord(tx0 + lx - 2, w);
-      const float d = disp_upsample(disp_b, hs, ws, h, w, y, x);
-      const float depth = depth_from_disp(d, a.depth_mode, a.min_depth, a.max_depth);
-      WarpGeom g;
-      warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
-      const Taps t = make_taps(g.ix, g.iy, h, w);
-      float v3[3];
-      sample_rgba(src, w, t, v3);
-#pragma unroll
-      for (int c = 0; c < 3; ++c) wx[c * kBN + i] = v3[c];
-    }
-    __syncthreads();
-    // phase 2: SSIM gradient coefficients at window centres p on tile + 1 (in-image, selected by argmin)
-    for (int i = threadIdx.x; i < kCN; i += kPhotoThreads) {
-      const int ly = i / kCW, lx = i - ly * kCW;
-      const int py = ty0 + ly - 1, px = tx0 + lx - 1;
-      const bool on = py >= 0 && py < h && px >= 0 && px < w && amin[(size_t)py * w + px] == 2 + f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float al = 0.f, be = 0.f, ga = 0.f;
-        if (on) {
-          const float* xp = wx + c * kBN;
-          const float* yp = tg + c * kBN;
-          float sx = 0.f, sy = 0.f, sxx = 0.f, syy = 0.f, sxy = 0.f;
-#pragma unroll
-          for (int dy = 0; dy <= 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx <= 2; ++dx) {
-              const float xv = xp[(ly + dy) * kBW + lx + dx], yv = yp[(ly + dy) * kBW + lx + dx];
-              sx += xv; sy += yv; sxx += xv * xv; syy += yv * yv; sxy += xv * yv;
-            }
-          const SsimStats st = ssim_stats(sx, sy, sxx, syy, sxy);
-          if (st.val >= 0.f && st.val <= 1.f) {          // clamp backward passes inside [0, 1]
-            const float gm = g0 * (0.85f / 3.f);
-            const float inv9d = 1.f / (9.f * st.d);
-            const float nd = st.n / st.d;
-            al = -gm * inv9d * (st.mu_y * (st.a2 - st.a1) - nd * st.mu_x * (st.b2 - st.b1));
-            be = gm * inv9d * nd * st.b1;
-            ga = -gm * inv9d * st.a1;
-          }
-        }
-        coef[(c * 3 + 0) * kCN + i] = al;
-        coef[(c * 3 + 1) * kCN + i] = be;
-        coef[(c * 3 + 2) * kCN + i] = ga;
-      }
-    }
-    __syncthreads();
-    // phase 3: gradient wrt the warped pixel -> sampling coordinates -> depth and projection
-    float dP[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) dP[k] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int lx = threadIdx.x % kPhotoTW, ly = (threadIdx.x / kPhotoTW) * 2 + j;
-      const int x = tx0 + lx, y = ty0 + ly;
-      if (x >= w || y >= h) continue;
-      const float d = disp_upsample(disp_b, hs, ws, h, w, y, x);
-      const float depth = depth_from_disp(d, a.depth_mode, a.min_depth, a.max_depth);
-      dval[j] = d; depthv[j] = depth;
-      WarpGeom g;
-      warp_geometry(geo, geo + 16 + f * 12, depth, x, y, h, w, g);
-      const Taps t = make_taps(g.ix, g.iy, h, w);
-      const bool sel = amin[(size_t)y * w + x] == 2 + f;
-      float gix = 0.f, giy = 0.f;
-      float gx3[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float xq = wx[c * kBN + (ly + 2) * kBW + lx + 2];
-        const float yq = tg[c * kBN + (ly + 2) * kBW + lx + 2];
-        float al = 0.f, be = 0.f, ga = 0.f;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy) {
-          const float wy = refl_box_weight(y, y + dy, h);
-#pragma unroll
-          for (int dx = -1; dx <= 1; ++dx) {
-            const float wgt = wy * refl_box_weight(x, x + dx, w);
-            const int ci = (ly + 1 + dy) * kCW + lx + 1 + dx;
-            al += wgt * coef[(c * 3 + 0) * kCN + ci];
-            be += wgt * coef[(c * 3 + 1) * kCN + ci];
-            ga += wgt * coef[(c * 3 + 2) * kCN + ci];
-          }
-        }
-        float gxc = al + be * xq + ga * yq;
-        if (sel) {
-          const float diff = yq - xq;                     // |target - pred|: d/dpred = -sgn(target - pred)
-          gxc -= g0 * (0.15f / 3.f) * (diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f));
-        }
-        gx3[c] = gxc;
-      }
-      sample_rgba_grad(src, w, t, gx3, gix, giy);
-      const float dpx = gix * g.mx, dpy = giy * g.my;   // (W-1)/2 * 2/(W-1) cancel
-      const float rz = 1.f / g.z;
-      float dp[3];
-      dp[0] = dpx * rz;
-      dp[1] = dpy * rz;
-      dp[2] = -(dpx * g.px + dpy * g.py) * rz;
-      const float* P = geo + 16 + f * 12;
-      float dd = 0.f;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) dd += (P[0 * 4 + c] * dp[0] + P[1 * 4 + c] * dp[1] + P[2 * 4 + c] * dp[2]) * g.ray[c];
-      ddepth[j] += dd;
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        dP[r * 4 + 0] += dp[r] * g.X[0];
-        dP[r * 4 + 1] += dp[r] * g.X[1];
-        dP[r * 4 + 2] += dp[r] * g.X[2];
-        dP[r * 4 + 3] += dp[r];
-      }
-    }
-    // block-reduce the 12 projection gradients of this frame
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const float v = warp_sum(dP[k]);
-      if (lane == 0) red[warp * 12 + k] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < 12) {
-      float sum = 0.f;
-#pragma unroll
-      for (int wv = 0; wv < 8; ++wv) sum += red[wv * 12 + threadIdx.x];
-      a.dproj_partials[((((size_t)s * tiles + tile) * 2 + f) * a.b + bb) * 12 + threadIdx.x] = sum;
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const int lx = threadIdx.x % kPhotoTW, ly = (threadIdx.x / kPhotoTW) * 2 + j;
-    const int x = tx0 + lx, y = ty0 + ly;
-    if (x < w && y < h)
-      a.ddisp_full[s][(size_t)bb * hw + (size_t)y * w + x] =
-          ddepth[j] * depth_grad(dval[j], depthv[j], a.depth_mode, a.min_depth, a.max_depth);
-  }
+  photo_fwd_body(a, tiles_x, tiles);
 }
+// EXPERIMENTAL variant (CLSLAM_PHOTO_OCC3=1): the same body capped at 85 registers, three CTAs per SM.  The warp phase is
+// bound by the latency of its dependent gathers (ncu: long-scoreboard stalls, 25 % of the warp slots occupied)
+__global__ void __launch_bounds__(kPhotoThreads, 3)
+photo_fwd_occ3_kernel(clslam_photo_args a, int tiles_x, int tiles) {
+  pdl_wait();
+  pdl_trigger();
+  photo_fwd_body(a, tiles_x, tiles);
+}
+
+// ---- backward -------------------------------------------------------------------------------
+// The kernel body lives in photo_bwd_body.inc and is compiled once per variant.  The default kernel is the first one;
+// the others are EXPERIMENTAL (CLSLAM_PHOTO_BWD_REUSE=1: phase 1 reads the forward pass's warped images;
+// CLSLAM_PHOTO_OCC3=1: 85-register cap, three CTAs per SM)
+#define PHOTO_BWD_NAME photo_bwd_kernel
+#define PHOTO_BWD_BOUNDS __launch_bounds__(kPhotoThreads)
+#define PHOTO_BWD_REUSE 0
+#include "photo_bwd_body.inc"
+#undef PHOTO_BWD_NAME
+#undef PHOTO_BWD_BOUNDS
+#undef PHOTO_BWD_REUSE
+
+#define PHOTO_BWD_NAME photo_bwd_reuse_kernel
+#define PHOTO_BWD_BOUNDS __launch_bounds__(kPhotoThreads)
+#define PHOTO_BWD_REUSE 1
+#include "photo_bwd_body.inc"
+#undef PHOTO_BWD_NAME
+#undef PHOTO_BWD_BOUNDS
+#undef PHOTO_BWD_REUSE
+
+#define PHOTO_BWD_NAME photo_bwd_occ3_kernel
+#define PHOTO_BWD_BOUNDS __launch_bounds__(kPhotoThreads, 3)
+#define PHOTO_BWD_REUSE 0
+#include "photo_bwd_body.inc"
+#undef PHOTO_BWD_NAME
+#undef PHOTO_BWD_BOUNDS
+#undef PHOTO_BWD_REUSE
+
+#define PHOTO_BWD_NAME photo_bwd_reuse_occ3_kernel
+#define PHOTO_BWD_BOUNDS __launch_bounds__(kPhotoThreads, 3)
+#define PHOTO_BWD_REUSE 1
+#include "photo_bwd_body.inc"
+#undef PHOTO_BWD_NAME
+#undef PHOTO_BWD_BOUNDS
+#undef PHOTO_BWD_REUSE
 
 // ---- transpose of the bilinear up-sampling + smoothness terms + sigmoid' -------------------
 // scale 0 is the identity; for s >= 1 (f = 2^s) one thread owns one low-res pixel and walks the 2f x 2f full-res
@@ -497,11 +371,20 @@ static int check_photo(const clslam_photo_args* a, const char* what) {
   return 0;
 }
 
+// experimental kernel variants, off unless the environment asks for them (read once)
+static bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+static bool photo_occ3() { static const bool v = env_flag("CLSLAM_PHOTO_OCC3"); return v; }
+static bool photo_bwd_reuse() { static const bool v = env_flag("CLSLAM_PHOTO_BWD_REUSE"); return v; }
+
 int clslam_photo_fwd(const clslam_photo_args* a, void* stream) {
   if (int rc = check_photo(a, "photo_fwd")) return rc;
   const int tiles_x = (a->w + kPhotoTW - 1) / kPhotoTW, tiles = clslam_photo_tiles(a->h, a->w);
   dim3 grid(tiles, a->b);
-  launch_k(photo_fwd_kernel, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), *a, tiles_x, tiles);
+  launch_k(photo_occ3() ? photo_fwd_occ3_kernel : photo_fwd_kernel, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), *a,
+           tiles_x, tiles);
   return finish_launch("photo_fwd");
 }
 
@@ -509,7 +392,11 @@ int clslam_photo_bwd(const clslam_photo_args* a, void* stream) {
   if (int rc = check_photo(a, "photo_bwd")) return rc;
   const int tiles_x = (a->w + kPhotoTW - 1) / kPhotoTW, tiles = clslam_photo_tiles(a->h, a->w);
   dim3 grid(tiles, a->b * a->n_scales);
-  launch_k(photo_bwd_kernel, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), *a, tiles_x, tiles);
+  bool reuse = photo_bwd_reuse();          // needs the forward pass's warped images of every scale
+  for (int s = 0; s < a->n_scales; ++s) reuse = reuse && a->warped[s] != nullptr;
+  auto kern = reuse ? (photo_occ3() ? photo_bwd_reuse_occ3_kernel : photo_bwd_reuse_kernel)
+                    : (photo_occ3() ? photo_bwd_occ3_kernel : photo_bwd_kernel);
+  launch_k(kern, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), *a, tiles_x, tiles);
   return finish_launch("photo_bwd");
 }
 
