@@ -1,0 +1,62 @@
+#!/usr/bin/env bash
+# One gpurun call that answers every open A/B question left by round 1 (the experimental paths below were written after
+# that round's GPU budget was spent and have not run on hardware yet):
+#
+#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/ab_round2.sh'
+#
+# 1. parity of the split-K TMA convolution / fused split-K dgrad (opt-in tests) and of the whole step with the small
+#    layers routed through it; 2. parity of the photometric variants; 3. bench lines (device-resident value only:
+#    no CPU baseline, no per-op profile) for each switch at batch 1 and batch 8.
+# Results: gpurun_out/ab/*.log, gpurun_out/ab/bench_<tag>_b<B>.json, gpurun_out/ab/summary.txt
+set -u
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/ab
+mkdir -p "$OUT"
+PY=python
+
+run_tests() {           # tag, env assignments..., -- pytest args
+  local tag=$1; shift
+  local envs=()
+  while [ "$1" != "--" ]; do envs+=("$1"); shift; done
+  shift
+  env "${envs[@]}" timeout 600 $PY -m pytest "$@" -m gpu -q -x > "$OUT/test_$tag.log" 2>&1
+  echo "test $tag rc=$? $(tail -1 "$OUT/test_$tag.log")" | tee -a "$OUT/summary.txt"
+}
+
+run_bench() {           # tag, batch, env assignments...
+  local tag=$1 b=$2; shift 2
+  env "$@" timeout 300 $PY bench.py --batch-per-gpu "$b" --steps 30 --warmup 5 --no-cpu-baseline --no-op-profile \
+      > "$OUT/bench_${tag}_b${b}.json" 2> "$OUT/bench_${tag}_b${b}.err"
+  $PY - "$OUT/bench_${tag}_b${b}.json" "$tag" "$b" <<'PYEOF' | tee -a "$OUT/summary.txt"
+import json, sys
+try:
+    d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    print(f"bench {sys.argv[2]:28s} b{sys.argv[3]}: {d['ms_per_step']:.3f} ms/step  {d['value']:.1f} triplets/s  e2e {d['e2e']['value']:.1f}  "
+          f"launches/step {d['launches_per_step']}  loss {d['loss']:.6f}")
+except Exception as e:
+    print(f"bench {sys.argv[2]} b{sys.argv[3]}: FAILED ({e})")
+PYEOF
+}
+
+: > "$OUT/summary.txt"
+# ---- 1. split-K ------------------------------------------------------------------------------------------
+run_tests splitk_ops CLSLAM_EXPERIMENTAL=1 -- tests/test_gpu_zz_conv_tma_splitk.py
+run_tests splitk_e2e CLSLAM_TMA_SPLITK=1 -- tests/test_gpu_e2e.py
+run_tests splitk_wgrad_e2e CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WGRAD=1 -- tests/test_gpu_e2e.py
+# ---- 2. photometric variants -----------------------------------------------------------------------------
+run_tests photo_reuse CLSLAM_PHOTO_BWD_REUSE=1 -- tests/test_gpu_photometric.py tests/test_gpu_e2e.py
+run_tests photo_occ3 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py tests/test_gpu_e2e.py
+run_tests photo_reuse_occ3 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py
+# ---- 3. bench lines ----------------------------------------------------------------------------------------
+for b in 1 8; do
+  run_bench base "$b" CLSLAM_AB=base
+  run_bench splitk "$b" CLSLAM_TMA_SPLITK=1
+  run_bench splitk_wgrad "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WGRAD=1
+  run_bench splitk_items37 "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_ITEMS=37
+  run_bench photo_reuse "$b" CLSLAM_PHOTO_BWD_REUSE=1
+  run_bench photo_occ3 "$b" CLSLAM_PHOTO_OCC3=1
+  run_bench photo_reuse_occ3 "$b" CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1
+  run_bench all "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1
+done
+echo "---- summary ----"
+cat "$OUT/summary.txt"
