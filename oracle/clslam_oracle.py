@@ -205,6 +205,49 @@ def make_batch(batch: int, height: int, width: int, seed: int = 0, coherent: boo
     return out
 
 
+def cityscapes_like_intrinsics(height: int, width: int, scale: int) -> Tuple[np.ndarray, np.ndarray]:
+    """A second camera for mixed replay batches: typical Cityscapes calibration (fx 2262.5, fy 2265.3, u0 1097.0,
+    v0 513.1 on 2048 x 1024; the reference reads it per recording, datasets/cityscapes.py:186-215) normalised by the
+    image size and scaled like datasets/utils.py:104-110."""
+    k = np.array([[2262.5 / 2048, 0, 1097.0 / 2048, 0], [0, 2265.3 / 1024, 513.1 / 1024, 0], [0, 0, 1, 0], [0, 0, 0, 1]],
+                 dtype=np.float32)
+    k[0, :] *= width // (2 ** scale)
+    k[1, :] *= height // (2 ** scale)
+    return k, np.linalg.pinv(k)
+
+
+def make_replay_batch(batch: int, height: int, width: int, seed: int = 0) -> Dict[object, Tensor]:
+    """A batch as ``Slam.step`` assembles it (slam/slam.py:158-164, slam/replay_buffer.py:164-177): the online sample
+    followed by replay samples that come from ANOTHER dataset, i.e. per-sample intrinsics (even samples KITTI, odd
+    samples Cityscapes-like), and colour-augmented network inputs (``rgb_aug`` != ``rgb``: per-sample brightness /
+    contrast, the photometric loss still compares the un-augmented ``rgb``, datasets/utils.py:236-259)."""
+    out = make_batch(batch, height, width, seed=seed, coherent=True)
+    g = torch.Generator().manual_seed(15485863 * seed + 29)
+    gain = 0.8 + 0.4 * torch.rand(batch, 1, 1, 1, generator=g)
+    bias = 0.1 * (torch.rand(batch, 1, 1, 1, generator=g) - 0.5)
+    gain[0], bias[0] = 1.0, 0.0                      # the online sample is not augmented
+    for f in (-1, 0, 1):
+        for s in range(4):
+            out[('rgb_aug', f, s)] = (out[('rgb', f, s)] * gain + bias).clamp(0.0, 1.0).contiguous()
+    for s in range(4):
+        for b in range(1, batch, 2):
+            k, ik = cityscapes_like_intrinsics(height, width, s)
+            out[('camera_matrix', s)][b] = torch.from_numpy(k)
+            out[('inv_camera_matrix', s)][b] = torch.from_numpy(ik)
+    return out
+
+
+def adapt_loss_weights(batch_size: int, online_loss_weight: Optional[float], online_index: int = 0) -> Optional[Tensor]:
+    """per-sample loss weights of ``adapt(online_loss_weight=...)`` (depth_pose_prediction.py:297-305)"""
+    if online_loss_weight is None:
+        return None
+    if batch_size == 1:
+        return torch.ones(1)
+    w = torch.full((batch_size,), (1 - online_loss_weight) / (batch_size - 1))
+    w[online_index] = online_loss_weight
+    return w
+
+
 def make_noise(batch: int, height: int, width: int, seed: int = 0, n_scales: int = 4) -> List[Tensor]:
     """Stand-in for the ``torch.randn`` tie-break draws (depth_pose_prediction.py:1055-1056):
     one (B,2,H,W) standard-normal tensor per scale, in scale order."""

@@ -39,6 +39,12 @@ CASES = {
     'full_b1': (1, 192, 640, False, None, 4),
     'full_b2_coherent': (2, 192, 640, True, None, 5),
 }
+# replay-like batches (oracle.make_replay_batch: per-sample intrinsics, rgb_aug != rgb) run through
+# adapt(online_loss_weight=...), i.e. non-uniform per-sample loss weights (:297-305): name -> online_loss_weight
+REPLAY_CASES = {
+    'small_b4_replay': (4, 64, 96, True, None, 6),
+}
+ONLINE_LOSS_WEIGHT = {'small_b4_replay': 0.4}
 
 
 class _Stub(types.ModuleType):
@@ -112,9 +118,14 @@ def run_case(name, spec, out_dir: Path):
     b, h, w, coherent, max_depth, seed = spec
     torch.manual_seed(0)
     pred, params = build_reference(b, h, w, max_depth)
-    batch = orc.make_batch(b, h, w, seed=seed, coherent=coherent)
+    replay = name in REPLAY_CASES
+    olw = ONLINE_LOSS_WEIGHT.get(name)
+    batch = orc.make_replay_batch(b, h, w, seed=seed) if replay else orc.make_batch(b, h, w, seed=seed, coherent=coherent)
     noise = orc.make_noise(b, h, w, seed=seed)
     rec = {}
+    if replay:
+        rec['replay_variant'] = np.array([1.0])
+        rec['online_loss_weight'] = np.array([olw])
     rec['meta'] = np.array([b, h, w, int(coherent), -1.0 if max_depth is None else max_depth, seed],
                            dtype=np.float64)
     rec['input_checksum'] = np.array(
@@ -124,8 +135,9 @@ def run_case(name, spec, out_dir: Path):
 
     # ---- iteration 1: same-weights outputs, losses, gradients (adapt mode, encoders frozen)
     pred._set_adapt(freeze_encoder=True)
+    weights = orc.adapt_loss_weights(b, olw)          # what adapt() builds from online_loss_weight (:297-305)
     with injected_noise(noise):
-        outputs, losses = pred._process_batch(dict(batch))
+        outputs, losses = pred._process_batch(dict(batch), weights)
     pred.optimizer.zero_grad()
     losses['loss'].backward()
     for s in range(4):
@@ -164,7 +176,7 @@ def run_case(name, spec, out_dir: Path):
             delta = sd[key] - params[net][key]
             rec[f'delta1_sample:{net}:{key}'] = sample_flat(delta)
     with injected_noise(noise):
-        out2, losses2 = pred.adapt(dict(batch), dict(batch), steps=1)
+        out2, losses2 = pred.adapt(dict(batch), dict(batch), steps=1, online_loss_weight=olw)
     rec['loss2'] = losses2['loss'].detach().reshape(-1).numpy()
     rec['disp2_0_sub'] = out2[('disp', 0)].detach()[:, :, ::4, ::4].numpy()
     for f in (-1, 1):
@@ -193,7 +205,7 @@ def run_case(name, spec, out_dir: Path):
 def main():
     out_dir = ROOT / 'tests' / 'golden'
     only = sys.argv[1:]
-    for name, spec in CASES.items():
+    for name, spec in {**CASES, **REPLAY_CASES}.items():
         if only and name not in only:
             continue
         run_case(name, spec, out_dir)

@@ -114,3 +114,17 @@ def test_sharding_host_logic():
     batch = orc.make_batch(4, 64, 96)
     sh = shard_batch(batch, 1, 2)
     assert sh[('rgb', 0, 0)].shape[0] == 2 and torch.equal(sh['index'], torch.tensor([2, 3]))
+
+
+def test_adapt_loss_weights_follow_the_reference_formula():
+    """adapt(online_loss_weight=...) (depth_pose_prediction.py:297-305): the product's host helper against the oracle's
+    restatement (which the replay-like golden fixture pins to the reference)"""
+    import torch
+    from clslam_b200.sharding import global_sample_weights
+    from oracle import clslam_oracle as orc
+    for b in (1, 2, 4, 8):
+        for olw in (0.25, 0.4, 1.0):
+            for idx in (0, b - 1):
+                assert torch.allclose(global_sample_weights(b, olw, idx), orc.adapt_loss_weights(b, olw, idx))
+    assert torch.allclose(global_sample_weights(4), torch.full((4,), 0.25))
+    assert orc.adapt_loss_weights(4, None) is None

@@ -11,6 +11,7 @@ from oracle import clslam_oracle as orc
 GOLDEN = Path(__file__).resolve().parent / 'golden'
 SMALL = ['small_b2', 'small_b3_coherent', 'small_b1_maxdepth']
 FULL = ['full_b1', 'full_b2_coherent']
+REPLAY = ['small_b4_replay']      # per-sample intrinsics, rgb_aug != rgb, adapt(online_loss_weight=0.4)
 
 
 def load_case(name):
@@ -19,7 +20,8 @@ def load_case(name):
     b, h, w, seed = int(b), int(h), int(w), int(seed)
     cfg = orc.OracleConfig(h, w, b, max_depth=None if max_depth < 0 else float(max_depth))
     params = orc.make_params(0)
-    batch = orc.make_batch(b, h, w, seed=seed, coherent=bool(coherent))
+    replay = 'replay_variant' in rec.files
+    batch = orc.make_replay_batch(b, h, w, seed=seed) if replay else orc.make_batch(b, h, w, seed=seed, coherent=bool(coherent))
     noise = orc.make_noise(b, h, w, seed=seed)
     chk = np.array(
         [float(sum(v.double().sum() for k, v in batch.items() if isinstance(k, tuple))),
@@ -30,16 +32,23 @@ def load_case(name):
     return rec, cfg, params, batch, noise
 
 
+def case_weights(rec, b):
+    """per-sample loss weights the case was recorded with (None: the default ones / batch_size)"""
+    if 'online_loss_weight' not in rec.files:
+        return None
+    return orc.adapt_loss_weights(b, float(rec['online_loss_weight'][0]))
+
+
 def rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-@pytest.mark.parametrize('name', SMALL + FULL)
+@pytest.mark.parametrize('name', SMALL + FULL + REPLAY)
 def test_oracle_matches_reference_outputs(name):
     rec, cfg, params, batch, noise = load_case(name)
     adapter = orc.OracleAdapter(params, cfg)
-    outputs, losses = adapter.step(batch, noise)
+    outputs, losses = adapter.step(batch, noise, case_weights(rec, cfg.batch_size))
     sub = int(rec['subsample'][0])
     # tolerance: same torch kernels in a different call order -> fp32 rounding only
     for s in range(4):
@@ -68,17 +77,18 @@ def test_oracle_matches_reference_outputs(name):
         assert np.abs(got - rec[f'grad_sample:{net}:{key}']).max() <= 2e-4 * gn / np.sqrt(g.numel()) * 30 + 1e-10, (net, key)
 
 
-@pytest.mark.parametrize('name', SMALL)
+@pytest.mark.parametrize('name', SMALL + REPLAY)
 def test_oracle_second_step_within_reference_envelope(name):
     """After one Adam update results are ill-conditioned: loss to 1e-3."""
     rec, cfg, params, batch, noise = load_case(name)
     adapter = orc.OracleAdapter(params, cfg)
-    adapter.step(batch, noise)
-    _, losses2 = adapter.step(batch, noise)
+    wts = case_weights(rec, cfg.batch_size)
+    adapter.step(batch, noise, wts)
+    _, losses2 = adapter.step(batch, noise, wts)
     np.testing.assert_allclose(losses2['loss'].detach().numpy(), rec['loss2'], rtol=1e-3)
 
 
-@pytest.mark.parametrize('name', SMALL)
+@pytest.mark.parametrize('name', SMALL + REPLAY)
 def test_oracle_predict_pose_and_buffer_feature(name):
     rec, cfg, params, batch, noise = load_case(name)
     tr = orc.predict_pose(params, batch[('rgb', 0, 0)][:1], batch[('rgb', 1, 0)][:1]).numpy()
@@ -98,3 +108,18 @@ def test_smoothness_quirk_is_row0_of_sample0():
         gx = abs(nd[0, 0, 0, i] - nd[0, 0, 0, i + 1]) * torch.exp(-(img[0, :, 0, i] - img[0, :, 0, i + 1]).abs().mean())
         gy = abs(nd[0, 0, 0, i] - nd[0, 0, 1, i]) * torch.exp(-(img[0, :, 0, i] - img[0, :, 1, i]).abs().mean())
         assert abs(float(got[i]) - float(gx + gy)) < 1e-6
+
+
+def test_replay_case_really_differs_from_the_plain_one():
+    """the replay-like fixture exercises what the plain ones do not: two cameras, augmented inputs, unequal weights"""
+    rec, cfg, params, batch, noise = load_case('small_b4_replay')
+    k = batch[('camera_matrix', 0)]
+    assert not torch.equal(k[0], k[1]) and torch.equal(k[0], k[2])
+    assert float((batch[('rgb_aug', 0, 0)][1:] - batch[('rgb', 0, 0)][1:]).abs().max()) > 0.01
+    assert torch.equal(batch[('rgb_aug', 0, 0)][0], batch[('rgb', 0, 0)][0])
+    w = case_weights(rec, cfg.batch_size)
+    assert abs(float(w.sum()) - 1.0) < 1e-6 and float(w[0]) == pytest.approx(0.4)
+    # with uniform weights the loss is different: the fixture pins the weighted sum
+    adapter = orc.OracleAdapter(params, cfg)
+    _, uniform = adapter.step(batch, noise, None, update=False)
+    assert abs(float(uniform['loss']) - float(rec['loss:loss'][0])) > 1e-4 * float(rec['loss:loss'][0])
