@@ -80,6 +80,7 @@ SIGNATURES = {
     'clslam_dgrad3x3_tma_ws': (c_int, [POINTER(ConvTma), c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, POINTER(Planes),
                                        c_void_p, c_longlong, c_void_p]),
     'clslam_debug_tma_flags': (c_int, [c_int]),
+    'clslam_debug_tma_stamps': (c_int, [c_void_p]),
     'clslam_planes_s2d_from_f32': (c_int, [c_void_p, POINTER(Planes), c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_stage_images_s2d': (c_int, [c_void_p, c_void_p, POINTER(Planes), c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_wgrad3x3_tma_workspace_bytes': (c_longlong, [c_int, c_int, c_int, c_int, c_int]),

@@ -27,8 +27,12 @@ constexpr int kTmaTH = 16, kTmaTW = 8;     // output tile
 // the single-thread issue loops, where every instruction counts
 #ifdef CLSLAM_TMA_DEBUG
 #define TMA_DBG(g, bit) (((g).debug & (bit)) != 0)
+// clock64 stamps of CTA 0's first work item (read back with clslam_debug_tma_stamps; tools/tma_stamps.py names them)
+__device__ unsigned long long g_tma_stamps[32];
+#define TMA_STAMP(i, cond) do { if (blockIdx.x == 0 && (cond)) g_tma_stamps[i] = clock64(); } while (0)
 #else
 #define TMA_DBG(g, bit) (false)
+#define TMA_STAMP(i, cond) do { } while (0)
 #endif
 constexpr int kTmaEpiWarps = 16;          // 4 TMEM lane quarters x 4 column slots (8 accumulator columns per tcgen05.ld)
 constexpr int kTmaThreads = 64 + 32 * kTmaEpiWarps;
@@ -117,6 +121,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TMA_STAMP(0, threadIdx.x == 0);
   if (threadIdx.x == 0) {
     for (int i = 0; i < kTmaMaxStages; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
@@ -131,8 +136,10 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  TMA_STAMP(1, threadIdx.x == 0);
   pdl_wait();            // everything above overlapped the previous kernel; its results are visible from here on
   pdl_trigger();
+  TMA_STAMP(2, threadIdx.x == 0);
 
   const int tiles_per_img = g.tiles_x * g.tiles_y;
   const int total = g.n_img * tiles_per_img * g.n_blocks * (SK ? g.ksplit : 1);
@@ -175,6 +182,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               tma_load_5d(a_tiles + sa * C::kAStage, &map_a, &a_full[sa], chunk * KC, ow0 + sft, oh0, img, 0);
             }
             __syncwarp();
+            TMA_STAMP(3, lane == 0 && t == (int)blockIdx.x && chunk * T + sft == cs0);
+            TMA_STAMP(4, lane == 0 && t == (int)blockIdx.x);
             if (++sa == g.na) { sa = 0; pa ^= 1; }
           }
           if (g.nbr > 0 && !TMA_DBG(g, 4)) {
@@ -214,6 +223,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       for (int cs = cs_first; cs < (TMA_DBG(g, 512) ? 0 : cs_last); ++cs) {
         if (!TMA_DBG(g, 8)) { mbar_wait(&a_full[sa], (uint32_t)pa); tc_fence_after(); }
+        TMA_STAMP(5, lane == 0 && it == 0 && cs == cs_first);
         const uint32_t a_st = a_ring + (uint32_t)(sa * (C::kAStage >> 4));
         if (resident) {
           // weights resident: nothing to wait for inside the stage, one election issues all T taps
@@ -250,6 +260,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int r = 0; r < T; ++r) {
           mbar_wait(&b_full[sb], (uint32_t)pb);
           tc_fence_after();
+          TMA_STAMP(6, lane == 0 && it == 0 && cs == cs_first && r == 0);
           const uint32_t b_st = b_ring + (uint32_t)(sb * (C::kBStage >> 4));
           const uint32_t a_hi = a_st + (uint32_t)((r * kTmaTW * C::kRowBytes) >> 4);
           if (elect_one()) {
@@ -283,6 +294,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       }
       if (elect_one()) umma_commit(&t_full[as]);
       __syncwarp();
+      TMA_STAMP(7, lane == 0 && it == 0);
     }
   } else {
     // ===================== epilogue =====================
@@ -323,10 +335,12 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           __syncwarp();
         }
         if (!TMA_DBG(g, 128)) tc_fence_after();
+        TMA_STAMP(8, warp == 2 && lane == 0 && it == 0);
 #pragma unroll 1
         for (int c = slot * 8; c < BN; c += 32) {
           uint32_t r[8];
           tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + c), r);
+          TMA_STAMP(9, warp == 2 && lane == 0 && it == 0 && c == slot * 8);
           if constexpr (C::kNcat) {               // + the A_hi.B_lo block
             uint32_t r2[8];
             tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + BN + c), r2);
@@ -412,13 +426,17 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         if (!TMA_DBG(g, 128)) tc_fence_before();
         __syncwarp();
+        TMA_STAMP(10, warp == 2 && lane == 0 && it == 0);
         if (lane == 0) mbar_arrive(&t_empty[as]);
       }
     }
   }
+  TMA_STAMP(11, threadIdx.x == 0);
   tc_fence_before();
   __syncthreads();
+  TMA_STAMP(12, threadIdx.x == 0);
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+  TMA_STAMP(13, warp == 2 && lane == 0);
 }
 
 // ---- split-K epilogue --------------------------------------------------------------------------------
@@ -1034,6 +1052,17 @@ int clslam_dgrad3x3_tma_ws(const clslam_conv_tma* p, int up, const float* y_prev
 }
 
 int clslam_debug_tma_flags(int flags) { g_tma_debug = flags; return 0; }
+
+int clslam_debug_tma_stamps(unsigned long long* out32) {
+#ifdef CLSLAM_TMA_DEBUG
+  cudaDeviceSynchronize();
+  return cudaMemcpyFromSymbol(out32, g_tma_stamps, sizeof(unsigned long long) * 32) == cudaSuccess ? 0 : -1;
+#else
+  for (int i = 0; i < 32; ++i) out32[i] = 0;
+  set_error("clslam_debug_tma_stamps: the library was built without -DCLSLAM_TMA_DEBUG");
+  return -1;
+#endif
+}
 
 int clslam_planes_from_f32(const float* x, const clslam_planes* out, int out_up, int out_halo, void* stream) {
   if (int rc = check_planes(out, "planes_from_f32")) return rc;

@@ -179,6 +179,9 @@ int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_plane
 /* timing experiments only (results are wrong when != 0; the tests are compiled out unless the library is built with
  * -DCLSLAM_TMA_DEBUG): 1 no MMA, 2 no epilogue body, 4 no weight ring, 8 no A loads */
 int clslam_debug_tma_flags(int flags);
+/* debug builds only (-DCLSLAM_TMA_DEBUG, tools/tma_stamps.py): clock64 stamps of CTA 0's first work item in the last
+ * clslam_conv3x3_tma launch (synchronises the device); returns -1 in a normal build */
+int clslam_debug_tma_stamps(unsigned long long* out32);
 
 /* Input staging for conv1 on the TMA kernel: (x - 0.45) / 0.225 (networks/resnet_encoder.py:117), channel concat of
  * img_b (pose net) and 2x2 space-to-depth, written as planes (n, h/2, w/2, 16 | 32): channel (p*2 + q) * cp + c of
