@@ -45,6 +45,10 @@ TMA_MIN_TILES_BWD = int(os.environ.get('CLSLAM_TMA_MIN_TILES_BWD', '24'))     # 
 TMA_SPLITK = os.environ.get('CLSLAM_TMA_SPLITK', '0') == '1'
 # with TMA_SPLITK: also move the weight gradients of those layers to clslam_wgrad3x3_tma (default: they stay on the gather kernel)
 TMA_SPLITK_WGRAD = os.environ.get('CLSLAM_TMA_SPLITK_WGRAD', '0') == '1'
+# EXPERIMENTAL (off by default): the dispconv weight gradients run on lane 1 (ahead of the short pose branch) instead of lane 2,
+# whose wgrad chain is the longest lane of the batch-1 backward pass (profiles/r01_bench_b1.json: 0.51 ms of per-op time
+# against 0.39 ms on lane 0 and 0.19 ms on lane 1)
+DISP_WGRAD_LANE = 1 if os.environ.get('CLSLAM_DISP_WGRAD_LANE1', '0') == '1' else 2
 
 
 def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
@@ -743,7 +747,7 @@ class AdaptEngine:
             if i < S:
                 keyd = (dd, f'dispconv_{i}.conv')
                 plan.need_ws(lib.clslam_dispconv_wgrad_workspace_bytes(b, hi_, wi_, DEC_CH[i]))
-                plan.set_lane(2)
+                plan.set_lane(DISP_WGRAD_LANE)
                 plan.wait(f'dzd{i}')
                 plan.with_ws(f'dispconv_{i}.wgrad', lib.clslam_dispconv_wgrad, _p(y1), _p(self.dz_disp[i]),
                              flat.wgrad_ptr(keyd), flat.bgrad_ptr(keyd), b, hi_, wi_, DEC_CH[i])

@@ -47,6 +47,7 @@ run_tests splitk_wgrad_e2e CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WGRAD=1 -- test
 run_tests photo_reuse CLSLAM_PHOTO_BWD_REUSE=1 -- tests/test_gpu_photometric.py tests/test_gpu_e2e.py
 run_tests photo_occ3 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py tests/test_gpu_e2e.py
 run_tests photo_reuse_occ3 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py
+run_tests disp_wgrad_lane1 CLSLAM_DISP_WGRAD_LANE1=1 -- tests/test_gpu_e2e.py
 # ---- 3. bench lines ----------------------------------------------------------------------------------------
 for b in 1 8; do
   run_bench base "$b" CLSLAM_AB=base
@@ -56,7 +57,11 @@ for b in 1 8; do
   run_bench photo_reuse "$b" CLSLAM_PHOTO_BWD_REUSE=1
   run_bench photo_occ3 "$b" CLSLAM_PHOTO_OCC3=1
   run_bench photo_reuse_occ3 "$b" CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1
-  run_bench all "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1
+  run_bench disp_wgrad_lane1 "$b" CLSLAM_DISP_WGRAD_LANE1=1
+  run_bench all "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 CLSLAM_DISP_WGRAD_LANE1=1
 done
+# ---- 4. where a TMA conv launch spends its time (debug build with clock stamps) ---------------------------------
+timeout 600 $PY tools/tma_stamps.py > "$OUT/tma_stamps.log" 2>&1
+echo "tma_stamps rc=$?" | tee -a "$OUT/summary.txt"
 echo "---- summary ----"
 cat "$OUT/summary.txt"
