@@ -14,9 +14,8 @@ from __future__ import annotations
 import shutil
 import warnings
 from pathlib import Path
-from typing import Any, Callable, Dict, List, Optional, Sequence, Tuple, Union
+from typing import Any, Callable, Dict, List, Optional, Tuple
 
-import numpy as np
 import torch
 from torch import Tensor, nn, optim
 

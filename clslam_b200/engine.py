@@ -14,13 +14,13 @@ Data layout in HBM (all fp32):
 from __future__ import annotations
 
 import ctypes
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+import os
+from typing import Dict, List, Optional
 
 import torch
 
 from . import _lib as L
 from .networks import DEC_CH, ENC_CH, FlatParams, ResnetEncoder
-
 
 
 def _p(t) -> Optional[int]:
@@ -34,8 +34,6 @@ def _p(t) -> Optional[int]:
 def conv_out(hi: int, k: int, s: int, p: int) -> int:
     return (hi + 2 * p - k) // s + 1
 
-
-import os
 
 # below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: gather kernels (split-K) instead
 TMA_MIN_TILES = int(os.environ.get('CLSLAM_TMA_MIN_TILES', '24'))

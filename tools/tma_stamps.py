@@ -54,7 +54,6 @@ def main():
     from tests import cabi
     lib = cabi.lib()
     st = cabi.stream()
-    clock_mhz = torch.cuda.clock_rate() if hasattr(torch.cuda, 'clock_rate') else 1965
     shapes = [  # n, h, w, ci, co, pad_mode, what
         (1, 48, 160, 64, 64, L.PAD_ZERO, 'layer1 conv (60 tiles)'),
         (2, 24, 80, 128, 128, L.PAD_ZERO, 'pose layer2 conv (40 tiles)'),
