@@ -768,11 +768,31 @@ static int tma_splitk_items() {
   }
   return v;
 }
+// CLSLAM_TMA_SPLITK_WAVES=1 additionally splits launches with SMs / 2 < items < SMs (layer3 / layer4 at batch 8: 80 / 96
+// items) when that shortens the schedule: cost = waves x steps per item (+ 2 steps for the extra epilogue launch),
+// e.g. 80 items x 12 steps: 1 wave x 12 -> 3 slices: 2 waves x 4
+static bool tma_splitk_waves() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("CLSLAM_TMA_SPLITK_WAVES"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
 struct TmaSplit { int ksplit, cs_per; };
 static TmaSplit tma_split_plan(long long items, int n_cs, int kc, int bn, int taps) {
   TmaSplit sp{1, n_cs};
   const bool built = kc == 64 && ((taps == 3 && (bn == 64 || bn == 128)) || (taps == 2 && bn == 128));
-  if (!built || items < 1 || items > tma_splitk_items() || n_cs < 2) return sp;
+  if (!built || items < 1 || n_cs < 2) return sp;
+  const int sms = tma_num_sms();
+  if (items > tma_splitk_items()) {
+    if (!tma_splitk_waves() || items >= sms) return sp;
+    long long best = n_cs;
+    for (int ks = 2; ks <= 4 && ks <= n_cs; ++ks) {
+      const int per = (n_cs + ks - 1) / ks, ks2 = (n_cs + per - 1) / per;
+      if (ks2 < 2 || 5 * n_cs < 4 * ks2 * per) continue;
+      const long long waves = (items * ks2 + sms - 1) / sms, cost = waves * per + 2;
+      if (cost < best) { best = cost; sp.ksplit = ks2; sp.cs_per = per; }
+    }
+    return sp;
+  }
   long long want = tma_num_sms() / items;            // one wave of work items
   if (want > n_cs) want = n_cs;
   if (want < 2) return sp;

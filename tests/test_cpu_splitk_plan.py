@@ -107,3 +107,24 @@ print("ok", k, eng.plan.ws_bytes)
     r = subprocess.run([sys.executable, '-c', code], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith('ok')
+
+
+def test_wave_rule_is_opt_in_and_shortens_the_schedule():
+    """CLSLAM_TMA_SPLITK_WAVES=1 (read once by the library -> subprocess): launches with SMs/2 < items < SMs split when
+    waves x steps per item (+ 2 for the extra epilogue launch) gets smaller"""
+    assert query(8, 12, 40, 256, 256) == 0                 # 80 items: not split by default
+    code = r'''
+import ctypes, sys
+sys.path.insert(0, "tests")
+from clslam_b200 import _lib as L
+from tests.test_cpu_splitk_plan import query
+n, h, w, ci, co = 8, 12, 40, 256, 256                      # layer3 at batch 8: 80 items x 12 steps -> 3 slices of 4 (2 waves)
+assert query(n, h, w, ci, co) == 3 * n * h * w * co * 4, query(n, h, w, ci, co)
+assert query(8, 6, 20, 512, 512) == 3 * 8 * 6 * 20 * 512 * 4    # layer4: 96 items x 24 steps -> 3 slices of 8 (2 waves)
+assert query(8, 48, 160, 64, 64) == 0                      # 480 items: more than one wave anyway
+assert query(1, 6, 20, 512, 512) == 12 * 6 * 20 * 512 * 4  # the small-map rule is unchanged
+print("ok")
+'''
+    env = dict(os.environ, CLSLAM_TMA_SPLITK_WAVES='1')
+    r = subprocess.run([sys.executable, '-c', code], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr

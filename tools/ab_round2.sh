@@ -54,6 +54,7 @@ for b in 1 8; do
   run_bench splitk "$b" CLSLAM_TMA_SPLITK=1
   run_bench splitk_wgrad "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WGRAD=1
   run_bench splitk_items37 "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_ITEMS=37
+  run_bench splitk_waves "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WAVES=1
   run_bench photo_reuse "$b" CLSLAM_PHOTO_BWD_REUSE=1
   run_bench photo_occ3 "$b" CLSLAM_PHOTO_OCC3=1
   run_bench photo_reuse_occ3 "$b" CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1
