@@ -872,8 +872,8 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
   if (cin % 16 || cout % 16 || !p->w_hi || !p->w_lo) { set_error("conv3x3_tma: cin %% 16, cout %% 16, weights"); return -1; }
   if (p->pad_mode < 0 || p->pad_mode > 2) { set_error("conv3x3_tma: pad_mode"); return -1; }
   const int taps = p->taps == 0 ? 3 : p->taps;
-  if (taps != 2 && taps != 3 && taps != 4) { set_error("conv3x3_tma: taps must be 2, 3 or 4"); return -1; }
-  if (taps != 3 && p->pad_mode != CLSLAM_PAD_ZERO) { set_error("conv3x3_tma: the 2x2 / 4x4 (space-to-depth) forms are zero padded"); return -1; }
+  if (taps != 1 && taps != 2 && taps != 3 && taps != 4) { set_error("conv3x3_tma: taps must be 1, 2, 3 or 4"); return -1; }
+  if (taps != 3 && p->pad_mode != CLSLAM_PAD_ZERO) { set_error("conv3x3_tma: the 1x1 / 2x2 / 4x4 forms are zero padded"); return -1; }
   if (int rc = get_encoder()) return rc;
   const int kc = cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16);
   const int bn = cout >= 128 ? 128 : (cout >= 64 ? 64 : (cout >= 32 ? 32 : 16));
@@ -909,7 +909,7 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
   const int hp = in.h + 2, wp = in.w + 2;
   const bool padded_view = p->pad_mode == CLSLAM_PAD_REFLECT;
   __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(in.base) + in.c_off + (padded_view ? 0 : ((size_t)wp + 1) * in.c_total);
-  g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : -1);      // 4x4: input rows o - 2 .. o + 1; 2x2: o - 1 .. o
+  g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : (taps == 1 ? 0 : -1));      // 4x4: input rows o - 2 .. o + 1; 2x2: o - 1 .. o; 1x1: o
   const cuuint64_t adims[5] = {(cuuint64_t)cin, (cuuint64_t)(padded_view ? wp : in.w), (cuuint64_t)(padded_view ? hp : in.h),
                                (cuuint64_t)in.n, 2};
   const cuuint64_t astr[4] = {(cuuint64_t)in.c_total * 2, (cuuint64_t)wp * in.c_total * 2, (cuuint64_t)hp * wp * in.c_total * 2,
@@ -965,6 +965,12 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
     if (kc == 16 && bn == 64) return launch_tma_conv<16, 64, 4>(ma, mb, g, st);
     if (kc == 32 && bn == 64) return launch_tma_conv<32, 64, 4>(ma, mb, g, st);
     set_error("conv3x3_tma: the 4x4 form is built for 16 / 32 input channels and 64 output channels");
+    return -1;
+  }
+  if (taps == 1) {        // EXPERIMENTAL (not yet run on hardware): 1x1 convolution, e.g. the stride-2 down-sampling branch of a
+                          // BasicBlock read from the (p, q) = (0, 0) channel block of the space-to-depth planes
+    if (kc == 64 && bn == 128) return launch_tma_conv<64, 128, 1>(ma, mb, g, st);
+    set_error("conv3x3_tma: the 1x1 form is built for input channels %% 64 == 0 and output channels %% 128 == 0");
     return -1;
   }
   if (taps == 2) {

@@ -47,6 +47,9 @@ TMA_SPLITK_WGRAD = os.environ.get('CLSLAM_TMA_SPLITK_WGRAD', '0') == '1'
 # whose wgrad chain is the longest lane of the batch-1 backward pass (profiles/r01_bench_b1.json: 0.51 ms of per-op time
 # against 0.39 ms on lane 0 and 0.19 ms on lane 1)
 DISP_WGRAD_LANE = 1 if os.environ.get('CLSLAM_DISP_WGRAD_LANE1', '0') == '1' else 2
+# EXPERIMENTAL (off by default): the 1x1 / stride-2 down-sampling convolutions of layer2-4 run the TMA kernel (taps = 1) on the
+# (0, 0) channel block of the space-to-depth planes their block's conv1 already reads, instead of the gather kernel
+TMA_DS = os.environ.get('CLSLAM_TMA_DS', '0') == '1'
 
 
 def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
@@ -405,7 +408,8 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Te
                 plan.conv_tma(f'{tag}.{p}.conv1', x_pl, L.PAD_ZERO, planes, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'],
                               t[p + '.bn1.scale'], t[p + '.bn1.shift'], L.ACT_RELU, y=mid_f32, out=mid_pl)
             elif use_s2:            # stride-2 conv on the TMA kernel: 2x2 taps over the space-to-depth planes of the input feature
-                s2d = PlaneBuf(plan, n, hc // 2, wc // 2, 4 * cin).view()
+                s2d_buf = PlaneBuf(plan, n, hc // 2, wc // 2, 4 * cin)
+                s2d = s2d_buf.view()
                 plan.add(f'{tag}.{p}.s2d', lambda stream, ws, xp, o, hh, ww, cc: plan.lib.clslam_planes_s2d_from_f32(
                     xp, ctypes.byref(o), n, hh, ww, cc, stream), _p(x_f32), s2d, hc, wc, cin)
                 hl = t[p + '.conv1.s2d_hl']
@@ -419,8 +423,13 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Te
                 dd = plan.desc(n, hc, wc, cin, planes, 1, stride, 0, act=L.ACT_NONE)
                 idt_pl = PlaneBuf(plan, n, ho, wo, planes).view() if use2 else None
                 idt_f32 = plan.alloc(n, ho, wo, planes) if not use2 else None
-                plan.conv_fwd(f'{tag}.{p}.downsample', dd, x_f32, None, t[p + '.ds.w'], t[p + '.dsbn.scale'],
-                              t[p + '.dsbn.shift'], None, idt_f32, t[p + '.ds.w_hi'], t[p + '.ds.w_lo'], out=idt_pl)
+                if TMA_DS and use_s2 and cin % 64 == 0:
+                    hl = t[p + '.ds.w_hl']          # [2][planes][1][1][cin]
+                    plan.conv_tma(f'{tag}.{p}.downsample', s2d_buf.view(0, cin), L.PAD_ZERO, planes, hl[0], hl[1],
+                                  t[p + '.dsbn.scale'], t[p + '.dsbn.shift'], L.ACT_NONE, y=idt_f32, out=idt_pl, taps=1)
+                else:
+                    plan.conv_fwd(f'{tag}.{p}.downsample', dd, x_f32, None, t[p + '.ds.w'], t[p + '.dsbn.scale'],
+                                  t[p + '.dsbn.shift'], None, idt_f32, t[p + '.ds.w_hi'], t[p + '.ds.w_lo'], out=idt_pl)
             else:
                 idt_pl, idt_f32 = x_pl, x_f32
             # ---- conv2 (+ identity, ReLU) -> block output.  Block 0 feeds block 1 of the same layer (planes when that

@@ -135,7 +135,9 @@ typedef struct clslam_conv_tma {
   const clslam_planes* out;       /* optional */
   int out_up;              /* 1 or 2 (nearest up-sampling on write) */
   int out_halo;            /* write the reflection halo of `out` */
-  int taps;                /* 0 / 3: 3x3.  2: 2x2 kernel over input rows / cols o-1 .. o (space-to-depth form of a 3x3 / stride-2 conv).
+  int taps;                /* 0 / 3: 3x3.  1 (experimental): 1x1 kernel, weights [cout][in.c] (with `in` = the first c channels of
+                              space-to-depth planes: a 1x1 / stride-2 convolution, torchvision BasicBlock.downsample).
+                              2: 2x2 kernel over input rows / cols o-1 .. o (space-to-depth form of a 3x3 / stride-2 conv).
                               4: 4x4 kernel over input rows / cols o-2 .. o+1, zero padded, weights [cout][4][4][in.c]
                               (the space-to-depth form of the encoders' 7x7 / stride-2 conv1, clslam_stage_images_s2d) */
 } clslam_conv_tma;

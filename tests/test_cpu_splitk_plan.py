@@ -128,3 +128,24 @@ print("ok")
     env = dict(os.environ, CLSLAM_TMA_SPLITK_WAVES='1')
     r = subprocess.run([sys.executable, '-c', code], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_plan_with_tma_downsample_flag():
+    """CLSLAM_TMA_DS=1 (+ split-K so that layer2-4 run the space-to-depth conv1): the six 1x1 / stride-2 convolutions become
+    taps = 1 launches over the first cin channels of the planes their block's conv1 reads"""
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+from tests.test_cpu_plan_builds import build
+eng = build(1, 192, 640)
+ds = [(n, a[0]) for n, f, a, l in eng.plan.ops if f is not None and "downsample" in n]
+assert len(ds) == 6
+names = [n for n, f, a, l in eng.plan.ops if f is not None]
+for n, a in ds:
+    assert hasattr(a, "inp") and a.taps == 1 and a.inp.c_off == 0 and a.inp.c * 4 == a.inp.c_total and a.cout == 2 * a.inp.c
+    assert names.index(n.replace("downsample", "s2d")) < names.index(n)          # reads what the s2d op wrote
+print("ok")
+'''
+    env = dict(os.environ, CLSLAM_TMA_SPLITK='1', CLSLAM_TMA_DS='1')
+    r = subprocess.run([sys.executable, '-c', code], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr

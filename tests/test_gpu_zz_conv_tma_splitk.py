@@ -229,3 +229,28 @@ def test_dgrad_splitk_fold_matches_two_step(upcat):
     assert cabi.rel_err(g1, g0) < 2e-6
     assert cabi.rel_err(o1.value(), o0.value()) < 2e-5
     assert float(o1.t[:, :, 0].float().abs().max()) == 0.0          # gradient planes keep a zero halo
+
+
+def test_1x1_stride2_downsample_on_the_tma_kernel():
+    """taps = 1 (CLSLAM_TMA_DS=1 in the engine): BasicBlock.downsample (1x1 / stride 2, BN folded to scale / shift) read from the
+    (p, q) = (0, 0) channel block of the space-to-depth planes"""
+    lib = cabi.lib()
+    n, h, w, ci, co = 2, 24, 80, 64, 128
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 1, 1, seed=2, scale=ci ** -0.5)
+    scale, shift = 1 + 0.2 * rnd(co, seed=3), 0.1 * rnd(co, seed=4)
+    xg = cabi.nhwc(x).float().cuda()
+    s2d = PlaneBuf(n, h // 2, w // 2, 4 * ci)
+    sd = s2d.desc()
+    L.check(lib.clslam_planes_s2d_from_f32(xg.data_ptr(), ctypes.byref(sd), n, h, w, ci, cabi.stream()), 's2d')
+    torch.cuda.synchronize()
+    keep = []
+    y = torch.full((n, h // 2, w // 2, co), float('nan'), device='cuda')
+    out = PlaneBuf(n, h // 2, w // 2, co)
+    od = out.desc()
+    a = _args(s2d.desc(0, ci), L.PAD_ZERO, cabi.krsc(wt), scale, shift, L.ACT_NONE, None, y, od, 1, 0, None, L.ACT_NONE, 1, keep)
+    L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma(taps=1)')
+    torch.cuda.synchronize()
+    ref = F.conv2d(x.float().double(), wt, stride=2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
+    assert cabi.rel_err(cabi.nchw(y), ref) < TOL
+    assert cabi.rel_err(out.value()[:, :, 1:-1, 1:-1], ref) < 2e-5 + TOL
