@@ -619,7 +619,9 @@ class AdaptEngine:
         # temporal order (depth_pose_prediction.py:951-955): (-1, 0) and (0, +1)
         self.pose_in, pose_s2d = stage_for_encoder(plan, pose_prep, 'pose.stage', [(self.rgb_aug[0], self.rgb_aug[1], 0, b),
                                                                                   (self.rgb_aug[1], self.rgb_aug[2], b, b)], 2 * b, h, w)
-        pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc', x_s2d=pose_s2d)
+        # with TMA_DS the last pose feature is also written as planes: the 1x1 `squeeze` then runs the TMA kernel (taps = 1)
+        pf4_pl = PlaneBuf(plan, 2 * b, h >> 5, w >> 5, ENC_CH[4]).view() if (TMA_DS and tma_ok(2 * b, h >> 5, w >> 5, 512, 256)) else None
+        pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc', x_s2d=pose_s2d, feat4_planes=pf4_pl)
         pf4 = pfeats[4]
         hp, wp = pf4.shape[1], pf4.shape[2]
         self.pose_hw = (hp, wp)
@@ -639,6 +641,9 @@ class AdaptEngine:
             if up and k == 3:
                 plan.conv_tma(name, x_pl, L.PAD_ZERO, co, flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)), None,
                               flat.bias_ptr((pd, name)), act, y=yv, out=out_pl)
+            elif name == 'squeeze' and pf4_pl is not None:
+                plan.conv_tma(name, pf4_pl, L.PAD_ZERO, co, flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)), None,
+                              flat.bias_ptr((pd, name)), act, y=yv, out=out_pl, taps=1)
             else:
                 plan.conv_fwd(name, d, x, None, flat.weight_ptr((pd, name)), None, flat.bias_ptr((pd, name)), None, yv,
                               flat.weight_hi_ptr((pd, name)), flat.weight_lo_ptr((pd, name)), out=out_pl)
