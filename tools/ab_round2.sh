@@ -66,5 +66,8 @@ done
 # ---- 4. where a TMA conv launch spends its time (debug build with clock stamps) ---------------------------------
 timeout 600 $PY tools/tma_stamps.py > "$OUT/tma_stamps.log" 2>&1
 echo "tma_stamps rc=$?" | tee -a "$OUT/summary.txt"
+# ---- 5. per-layer numbers: gather vs plain TMA vs split-K -----------------------------------------------------
+timeout 600 $PY tools/splitk_microbench.py > "$OUT/splitk_microbench.jsonl" 2> "$OUT/splitk_microbench.err"
+echo "splitk_microbench rc=$?" | tee -a "$OUT/summary.txt"
 echo "---- summary ----"
 cat "$OUT/summary.txt"
