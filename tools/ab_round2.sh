@@ -2,7 +2,7 @@
 # One gpurun call that answers every open A/B question left by round 1 (the experimental paths below were written after
 # that round's GPU budget was spent and have not run on hardware yet):
 #
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/ab_round2.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/ab_round2.sh'      # ~13 min of box time
 #
 # 1. parity of the split-K TMA convolution / fused split-K dgrad (opt-in tests) and of the whole step with the small
 #    layers routed through it; 2. parity of the photometric variants; 3. bench lines (device-resident value only:
