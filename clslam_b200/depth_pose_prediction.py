@@ -180,6 +180,7 @@ class DepthPosePrediction:
         self.noise_provider: Optional[Callable[[int, Tuple[int, ...]], Tensor]] = None
         self.stage_all_inputs = True          # move every dict value to the device like :916-917
         self._mode = 'eval'
+        self._adapt_flags_set = False
 
     # ------------------------------------------------------------------------------------------
     def _validate_sets(self, dataset_config) -> None:
@@ -224,19 +225,32 @@ class DepthPosePrediction:
         raise NotImplementedError('training-mode BatchNorm / encoder backward is SURVEY.md 8(f) row 3; '
                                   'use adapt() (encoders frozen)')
 
+    # Both mode switches are called once per frame by Slam.step / adapt (slam/slam.py:143, :291-319).  Walking the four module
+    # trees costs 0.4-0.6 ms of host time per call, in front of the step's H2D copies and launches, and is idempotent: the
+    # modules only hold the parameters here (the CUDA path always evaluates BatchNorm with running statistics and never
+    # differentiates the encoders), so the walk is skipped when nothing changed since the last one.
+    def _all_eval(self) -> bool:
+        return not any(m.training for m in self.models.values())
+
     def _set_eval(self) -> None:
-        for m in self.models.values():
-            m.eval()
+        if not self._all_eval():
+            for m in self.models.values():
+                m.eval()
         self._mode = 'eval'
 
     def _set_adapt(self, freeze_encoder: bool = True) -> None:
         if not freeze_encoder:
             raise NotImplementedError('freeze_encoder=False is SURVEY.md 8(f) row 3')
-        for model_name, model in self.models.items():
-            model.eval()
-            for name, param in model.named_parameters():
-                if name.find('bn') != -1 or 'encoder' in model_name:
-                    param.requires_grad = False
+        if not self._all_eval():
+            for m in self.models.values():
+                m.eval()
+        if not self._adapt_flags_set:
+            # requires_grad=False for BatchNorm and encoder parameters (:813-822); the reference never re-enables them
+            for model_name, model in self.models.items():
+                for name, param in model.named_parameters():
+                    if name.find('bn') != -1 or 'encoder' in model_name:
+                        param.requires_grad = False
+            self._adapt_flags_set = True
         self._mode = 'adapt'
 
     # ------------------------------------------------------------------------------------------
@@ -369,13 +383,16 @@ class DepthPosePrediction:
 
     def _draw_noise(self, eng: AdaptEngine) -> None:
         """tie-break noise of :1055-1056: one draw per scale from the global torch RNG, in scale order"""
+        if self.noise_provider is None:
+            # one RNG launch over the scale-major buffer instead of four (same distribution, same number of values; the
+            # reference draws on its own device generator, so the streams never matched bitwise -- parity runs inject the
+            # noise through ``noise_provider``)
+            eng.noise_all.normal_()
+            return
         for s in range(4):
-            if self.noise_provider is not None:
-                n = self.noise_provider(s, (eng.b_global, 2, self.height, self.width))
-                lo, hi = shard_range(eng.b_global, self.rank, self.world)
-                eng.noise[s].copy_(n[lo:hi], non_blocking=True)
-            else:
-                eng.noise[s].normal_()
+            n = self.noise_provider(s, (eng.b_global, 2, self.height, self.width))
+            lo, hi = shard_range(eng.b_global, self.rank, self.world)
+            eng.noise[s].copy_(n[lo:hi], non_blocking=True)
 
     # ------------------------------------------------------------------------------------------
     def _collect(self, eng: AdaptEngine, check_nan: bool = True) -> Tuple[Dict[Any, Tensor], Dict[str, Tensor]]:

@@ -525,7 +525,8 @@ class AdaptEngine:
         self.rel_dist = plan.alloc(2, b, dtype=torch.float64, zero=True)
         self.sample_w = plan.alloc(b, zero=True)
         self.sample_w_global = plan.alloc(batch_global, zero=True)
-        self.noise = [plan.alloc(b, 2, h, w, zero=True) for _ in range(S)]
+        self.noise_all = plan.alloc(S, b, 2, h, w, zero=True)          # one buffer: the four per-scale draws are one RNG launch
+        self.noise = [self.noise_all[s] for s in range(S)]
 
         # ---- depth network (lane 0; pose network on lane 1, identity candidates on lane 2) ------
         plan.fork((1, 2))

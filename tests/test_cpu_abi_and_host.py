@@ -128,3 +128,30 @@ def test_adapt_loss_weights_follow_the_reference_formula():
                 assert torch.allclose(global_sample_weights(b, olw, idx), orc.adapt_loss_weights(b, olw, idx))
     assert torch.allclose(global_sample_weights(4), torch.full((4,), 0.25))
     assert orc.adapt_loss_weights(4, None) is None
+
+
+def test_mode_switches_are_idempotent_and_cheap():
+    """_set_adapt / _set_eval (:797-827) run once per frame in front of the step: the module walk happens only when something
+    changed, the observable state is the reference's (all modules in eval mode, BatchNorm and encoder parameters frozen)"""
+    import time
+    import torch
+    from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), Config(batch_size=1), device=torch.device('cpu'))
+    for net in pred.models.values():
+        net.train()
+    pred._set_adapt(True)
+    assert all(not m.training for net in pred.models.values() for m in net.modules())
+    for name in ('depth_encoder', 'pose_encoder'):
+        assert not any(p.requires_grad for p in pred.models[name].parameters())
+    for name in ('depth_decoder', 'pose_decoder'):
+        assert all(p.requires_grad for p in pred.models[name].parameters())
+    t0 = time.perf_counter()
+    for _ in range(100):
+        pred._set_eval(); pred._set_adapt(True)
+    assert (time.perf_counter() - t0) / 100 < 1e-4          # was ~1 ms per pair when every call walked the module trees
+    pred.models['depth_decoder'].train()                    # a caller that flips a network back is still honoured
+    pred._set_adapt(True)
+    assert all(not m.training for m in pred.models['depth_decoder'].modules())
+    pred.models['pose_encoder'].train()
+    pred._set_eval()
+    assert all(not m.training for m in pred.models['pose_encoder'].modules())
