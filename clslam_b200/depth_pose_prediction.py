@@ -329,7 +329,7 @@ class DepthPosePrediction:
             dst = smap.get(key)
             if dst is not None:
                 if not (val.is_cuda and val.data_ptr() == dst.data_ptr()):
-                    dst.copy_(val.reshape(dst.shape), non_blocking=True)
+                    dst.copy_(val if val.shape == dst.shape else val.reshape(dst.shape), non_blocking=True)
                 inputs[key] = dst
             elif self.stage_all_inputs and isinstance(val, Tensor):
                 # keys the path does not read are still moved like :916-917, into cached device buffers (no allocation per call)
