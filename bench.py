@@ -228,7 +228,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from clslam_b200 import Config, DatasetConfig, DepthPosePrediction, _lib
-    from oracle import clslam_oracle as orc        # input generators + the timed CPU baseline only
+    from clslam_b200 import synthetic              # seeded workload (images, intrinsics, weights): data generation only
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -245,10 +245,10 @@ def run_ours(args):
 
     pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b_global),
                                data_parallel=world > 1, use_cuda_graph=not args.no_graph)
-    params = orc.make_params(0)
-    for n in orc.NET_NAMES:
+    params = synthetic.make_params(0)
+    for n in synthetic.NET_NAMES:
         pred.models[n].load_state_dict(params[n])
-    full = orc.make_batch(b_global, h, w, seed=1, coherent=True)
+    full = synthetic.make_batch(b_global, h, w, seed=1, coherent=True)
     host = {k: v[rank * b:(rank + 1) * b].contiguous().pin_memory() for k, v in full.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
     lib = _lib.load()
@@ -384,6 +384,7 @@ def run_ours(args):
             if args.op_table:
                 Path(args.op_table).write_text(json.dumps(rows, indent=1))
         if world == 1 and not args.no_cpu_baseline:
+            from oracle import clslam_oracle as orc        # the timed CPU baseline: the only use of the oracle in this arm
             cores = os.cpu_count() or 1
             res = orc.time_adapt_steps(b_global, h, w, steps=args.cpu_steps, warmup=1, threads=cores)
             line['cpu_baseline'] = {
