@@ -99,11 +99,18 @@ struct TmaConvArgs {
   FastDiv div_ks;
   float* part;
   long long part_stride;         // elements between two z slices = n_img * ho * wo * cout
+  // tall form (TALL instantiations only): the input is addressed as ONE image of tall_n * tall_hp rows -- the images of the
+  // planes buffer stacked with their halo rows, which are valid padding (reflection halo, or zeros for a zero-padded layer
+  // whose producer left the halo untouched).  A 16-row tile then covers 16 / tall_hp images instead of wasting 16 - h rows:
+  // 6 x 20 maps (tall_hp = 8) need half the tiles.  n_img = 1, ho stays the height of one image, output row v of the
+  // stack is row v % tall_hp of image v / tall_hp (valid when < ho)
+  int tall_hp, tall_n;
+  FastDiv div_hp;
 };
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
-template <int KC, int BN, int T, bool SK = false>
+template <int KC, int BN, int T, bool SK = false, bool TALL = false>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TmaConvArgs g) {
   using C = TmaConvCfg<KC, BN, T>;
@@ -317,10 +324,13 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           part = g.part + (long long)(t - tq * g.ksplit) * g.part_stride;
         }
         const int mt = g.div_nb.quot(tq), nb = tq - mt * g.n_blocks;
-        const int img = g.div_tpi.quot(mt), rem = mt - img * tiles_per_img;
+        const int img0 = g.div_tpi.quot(mt), rem = mt - img0 * tiles_per_img;
         const int ty = g.div_tx.quot(rem);
-        const int oh = ty * kTmaTH + (l >> 3), ow = (rem - ty * g.tiles_x) * kTmaTW + (l & 7);
-        const bool ok = oh < g.ho && ow < g.wo;
+        const int oh0 = ty * kTmaTH + (l >> 3), ow = (rem - ty * g.tiles_x) * kTmaTW + (l & 7);
+        // TALL: the tile walks the images stacked with their halo rows (see TmaConvArgs::tall_hp); row -> (image, row)
+        const int img = TALL ? g.div_hp.quot(oh0) : img0;
+        const int oh = TALL ? oh0 - img * g.tall_hp : oh0;
+        const bool ok = oh < g.ho && ow < g.wo && (!TALL || img < g.tall_n);
         const size_t y_off = (((size_t)img * g.ho + oh) * g.wo + ow) * g.cout;
         // planes: primary position(s) by pointer arithmetic; the reflection-halo copies of border pixels on a slow path
         const int up = g.out.up;
@@ -725,10 +735,10 @@ static int tma_num_sms() {
   return g_tma_sms;
 }
 
-template <int KC, int BN, int T, bool SK = false>
+template <int KC, int BN, int T, bool SK = false, bool TALL = false>
 static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConvArgs g, cudaStream_t st) {
   using C = TmaConvCfg<KC, BN, T>;
-  auto kern = conv3x3_tma_kernel<KC, BN, T, SK>;
+  auto kern = conv3x3_tma_kernel<KC, BN, T, SK, TALL>;
   static bool attr_set = false;
   if (!attr_set) {
     const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaSmemMax);
@@ -818,6 +828,17 @@ static int check_planes(const clslam_planes* p, const char* what) {
 using namespace clslam;
 
 // geometry shared by the launch and the workspace query
+// Tall form (TmaConvArgs::tall_hp): > 0 = number of 16-row tiles when the images are walked as one stack, 0 = not applicable
+// (the caller did not vouch for the halo, other kernel shapes, a single image) or no fewer tiles than one image at a time
+static int tma_tall_tiles_y(const clslam_conv_tma* p, int taps, int kc, int bn) {
+  if (!(p->flags & CLSLAM_TMA_IN_HALO_VALID) || taps != 3 || p->pad_mode == CLSLAM_PAD_FULL || p->in.n < 2) return 0;
+  if (kc != 64 || bn != 128) return 0;                      // instantiated for the layers that have small maps
+  const long long rows = (long long)p->in.n * (p->in.h + 2) - 2;         // output rows of the stack
+  const long long tall = (rows + kTmaTH - 1) / kTmaTH;
+  const long long plain = (long long)p->in.n * ((p->in.h + kTmaTH - 1) / kTmaTH);
+  return tall < plain ? (int)tall : 0;
+}
+
 struct TmaGeom { int taps, kc, bn, ho, wo, tiles_x, tiles_y, n_blocks, chunks; long long items; };
 static int tma_geometry(const clslam_conv_tma* p, TmaGeom& q) {
   if (!p) { set_error("conv3x3_tma: null"); return -1; }
@@ -831,6 +852,7 @@ static int tma_geometry(const clslam_conv_tma* p, TmaGeom& q) {
   q.tiles_x = (q.wo + kTmaTW - 1) / kTmaTW; q.tiles_y = (q.ho + kTmaTH - 1) / kTmaTH;
   q.n_blocks = cout / q.bn; q.chunks = cin / q.kc;
   q.items = (long long)p->in.n * q.tiles_x * q.tiles_y * q.n_blocks;
+  if (const int ty = tma_tall_tiles_y(p, q.taps, q.kc, q.bn)) { q.tiles_y = ty; q.items = (long long)q.tiles_x * ty * q.n_blocks; }
   return 0;
 }
 
@@ -907,11 +929,20 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
   // A: 5-D map (channel, x, y, image, plane) over the padded view (reflect: the stored halo is the padding) or the
   // interior view (zero / full: TMA zero-fills outside)
   const int hp = in.h + 2, wp = in.w + 2;
-  const bool padded_view = p->pad_mode == CLSLAM_PAD_REFLECT;
+  // tall form: the n images are one stack of n * hp rows whose halo rows / columns are the padding (EXPERIMENTAL, opt-in
+  // through p->flags; not yet run on hardware)
+  const int tall_ty = tma_tall_tiles_y(p, taps, kc, bn);
+  const bool tall = tall_ty > 0;
+  if (tall) {
+    g.n_img = 1; g.tiles_y = tall_ty;
+    g.div_tpi = make_fastdiv(g.tiles_x * g.tiles_y);
+    g.tall_hp = hp; g.tall_n = in.n; g.div_hp = make_fastdiv(hp);
+  }
+  const bool padded_view = p->pad_mode == CLSLAM_PAD_REFLECT || tall;
   __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(in.base) + in.c_off + (padded_view ? 0 : ((size_t)wp + 1) * in.c_total);
   g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : (taps == 1 ? 0 : -1));      // 4x4: input rows o - 2 .. o + 1; 2x2: o - 1 .. o; 1x1: o
-  const cuuint64_t adims[5] = {(cuuint64_t)cin, (cuuint64_t)(padded_view ? wp : in.w), (cuuint64_t)(padded_view ? hp : in.h),
-                               (cuuint64_t)in.n, 2};
+  const cuuint64_t adims[5] = {(cuuint64_t)cin, (cuuint64_t)(padded_view ? wp : in.w),
+                               (cuuint64_t)(tall ? (long long)in.n * hp : (padded_view ? hp : in.h)), (cuuint64_t)(tall ? 1 : in.n), 2};
   const cuuint64_t astr[4] = {(cuuint64_t)in.c_total * 2, (cuuint64_t)wp * in.c_total * 2, (cuuint64_t)hp * wp * in.c_total * 2,
                               (cuuint64_t)in.plane_stride * 2};
   const cuuint32_t abox[5] = {(cuuint32_t)kc, kTmaTW, (cuuint32_t)(kTmaTH + taps - 1), 1, 2};
@@ -941,6 +972,7 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
       k.part = reinterpret_cast<float*>(workspace); k.part_stride = slice;
       int rc;
       if (taps == 2) rc = launch_tma_conv<64, 128, 2, true>(ma, mb, k, st);
+      else if (tall) rc = launch_tma_conv<64, 128, 3, true, true>(ma, mb, k, st);
       else if (bn == 128) rc = launch_tma_conv<64, 128, 3, true>(ma, mb, k, st);
       else rc = launch_tma_conv<64, 64, 3, true>(ma, mb, k, st);
       if (rc) return rc;
@@ -978,6 +1010,7 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
     set_error("conv3x3_tma: the 2x2 form is built for input channels %% 64 == 0 and output channels %% 128 == 0");
     return -1;
   }
+  if (tall) return launch_tma_conv<64, 128, 3, false, true>(ma, mb, g, st);
 #define CLSLAM_TMA_CASE(KC_, BN_) if (kc == KC_ && bn == BN_) return launch_tma_conv<KC_, BN_, 3>(ma, mb, g, st);
   CLSLAM_TMA_CASE(64, 128) CLSLAM_TMA_CASE(64, 64) CLSLAM_TMA_CASE(64, 32) CLSLAM_TMA_CASE(64, 16)
   CLSLAM_TMA_CASE(32, 128) CLSLAM_TMA_CASE(32, 64) CLSLAM_TMA_CASE(32, 32) CLSLAM_TMA_CASE(32, 16)

@@ -50,6 +50,11 @@ DISP_WGRAD_LANE = 1 if os.environ.get('CLSLAM_DISP_WGRAD_LANE1', '0') == '1' els
 # EXPERIMENTAL (off by default): the 1x1 / stride-2 down-sampling convolutions of layer2-4 run the TMA kernel (taps = 1) on the
 # (0, 0) channel block of the space-to-depth planes their block's conv1 already reads, instead of the gather kernel
 TMA_DS = os.environ.get('CLSLAM_TMA_DS', '0') == '1'
+# EXPERIMENTAL (off by default): 3x3 launches over several small images walk them as one stack of n * (h + 2) rows (the halo
+# rows between two images are the padding), so a 16-row tile is not wasted on a 6-row map: clslam_conv_tma.flags.  Every
+# planes buffer this engine feeds to a zero-padded launch has an all-zero halo (allocated zeroed, producers write with
+# out_halo = 0); reflection-padded launches read the reflection halo anyway.
+TMA_TALL = os.environ.get('CLSLAM_TMA_TALL', '0') == '1'
 
 
 def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
@@ -262,6 +267,8 @@ class Plan:
         if out is not None:
             a.out = ctypes.pointer(out)
         a.out_up, a.out_halo, a.taps = out_up, out_halo, taps
+        if TMA_TALL and taps == 3 and pad_mode != L.PAD_FULL:
+            a.flags = L.TMA_IN_HALO_VALID
         self.keep.append(a)
         if TMA_SPLITK:      # small layers split K over the SMs (workspace: raw partial sums); large ones run the plain kernel
             self.need_ws(self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a)))

@@ -140,7 +140,13 @@ typedef struct clslam_conv_tma {
                               2: 2x2 kernel over input rows / cols o-1 .. o (space-to-depth form of a 3x3 / stride-2 conv).
                               4: 4x4 kernel over input rows / cols o-2 .. o+1, zero padded, weights [cout][4][4][in.c]
                               (the space-to-depth form of the encoders' 7x7 / stride-2 conv1, clslam_stage_images_s2d) */
+  int flags;               /* CLSLAM_TMA_* bits, 0 = none */
 } clslam_conv_tma;
+/* flags bit (experimental): the stored halo ring of `in` is valid padding for this layer -- the reflection halo for
+ * CLSLAM_PAD_REFLECT (always required), all zeros for CLSLAM_PAD_ZERO (true when the producer wrote the planes with
+ * out_halo = 0 into a zero-initialised buffer).  The kernel may then walk the n images as ONE stack of n * (h + 2) rows, so
+ * that a 16-row tile covers several small images (6 x 20 maps: half the tiles) instead of padding each image to 16 rows. */
+#define CLSLAM_TMA_IN_HALO_VALID 1
 int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
 /* Split-K form for the layers whose output grid is too small to fill the persistent kernel (the <= 24 x 80 maps of
  * ResNet layer2-4, upconv_4_x .. upconv_2_0 and the pose decoder at batch 1): when the layer has fewer (16 x 8 tile,

@@ -149,3 +149,25 @@ print("ok")
     env = dict(os.environ, CLSLAM_TMA_SPLITK='1', CLSLAM_TMA_DS='1')
     r = subprocess.run([sys.executable, '-c', code], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_tall_form_geometry():
+    """clslam_conv_tma.flags = CLSLAM_TMA_IN_HALO_VALID: several small images are walked as one stack of n * (h + 2) rows.  The
+    workspace query shows the item count the split plan sees: 8 images of 6 x 20 give 4 tile rows instead of 8"""
+    def q(n, h, w, ci, co, flags, pad_mode=L.PAD_ZERO):
+        a = L.ConvTma()
+        a.inp = L.Planes(0, 0, n, h, w, ci, 0, ci)
+        a.pad_mode, a.cout, a.taps, a.flags = pad_mode, co, 3, flags
+        return L.load().clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+    slice_b = lambda n, h, w, co: n * h * w * co * 4
+    # depth layer4 at batch 8: plain 8 x 3 tiles x 4 N blocks = 96 items (no split by default); tall: 4 x 3 x 4 = 48 -> 3 slices of 8
+    assert q(8, 6, 20, 512, 512, 0) == 0
+    assert q(8, 6, 20, 512, 512, L.TMA_IN_HALO_VALID) == 3 * slice_b(8, 6, 20, 512)
+    # pose layer4 at batch 1 (two images): 2 x 3 x 4 = 24 items -> 6 slices; tall: 1 x 3 x 4 = 12 items -> 12 slices
+    assert q(2, 6, 20, 512, 512, 0) == 6 * slice_b(2, 6, 20, 512)
+    assert q(2, 6, 20, 512, 512, L.TMA_IN_HALO_VALID) == 12 * slice_b(2, 6, 20, 512)
+    # no gain when the height is a multiple of the tile (48 rows = 3 tiles, the stack needs 25 for 8 images), one image, or
+    # the full-correlation form
+    assert q(8, 48, 160, 64, 128, L.TMA_IN_HALO_VALID) == q(8, 48, 160, 64, 128, 0)
+    assert q(1, 6, 20, 512, 512, L.TMA_IN_HALO_VALID) == q(1, 6, 20, 512, 512, 0)
+    assert q(2, 6, 20, 256, 512, L.TMA_IN_HALO_VALID, L.PAD_FULL) == q(2, 6, 20, 256, 512, 0, L.PAD_FULL)

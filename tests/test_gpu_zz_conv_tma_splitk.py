@@ -254,3 +254,57 @@ def test_1x1_stride2_downsample_on_the_tma_kernel():
     ref = F.conv2d(x.float().double(), wt, stride=2) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1)
     assert cabi.rel_err(cabi.nchw(y), ref) < TOL
     assert cabi.rel_err(out.value()[:, :, 1:-1, 1:-1], ref) < 2e-5 + TOL
+
+
+TALL_CASES = [
+    # n, h, w, ci, co, pad_mode, use_res, out_up     (kc = 64, N block 128: the instantiated tall kernel)
+    (8, 6, 20, 512, 512, L.PAD_ZERO, True, 1),        # depth layer4 conv2 at batch 8: 4 tile rows instead of 8
+    (2, 6, 20, 256, 256, L.PAD_ZERO, False, 1),       # pose_0 at batch 1: both images in one tile
+    (5, 6, 20, 512, 256, L.PAD_REFLECT, False, 2),    # upconv_4_0: reflection halo, nearest 2x + halo on write, odd image count
+    (8, 24, 80, 128, 128, L.PAD_ZERO, True, 1),       # layer2: 26-row images straddle tile boundaries (13 tile rows instead of 16)
+    (8, 12, 40, 256, 128, L.PAD_REFLECT, False, 1),   # upconv_3_0: 7 tile rows instead of 8
+]
+
+
+@pytest.mark.parametrize('split', [False, True])
+@pytest.mark.parametrize('case', TALL_CASES)
+def test_tall_form_is_bit_identical_to_the_plain_kernel(case, split):
+    """flags = CLSLAM_TMA_IN_HALO_VALID (CLSLAM_TMA_TALL=1 in the engine): same MMAs per output pixel in the same order, so
+    the results must not differ by a single bit; with the workspace the tall launch is additionally split over K"""
+    lib = cabi.lib()
+    n, h, w, ci, co, pad_mode, use_res, up = case
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    shift = 0.1 * rnd(co, seed=4)
+    buf = PlaneBuf(n, h, w, ci)
+    buf.set_padded(F.pad(x, (1, 1, 1, 1), mode='reflect' if pad_mode == L.PAD_REFLECT else 'constant'))
+    res_desc = None
+    if use_res:
+        rbuf = PlaneBuf(n, h, w, co)
+        rbuf.set_padded(F.pad(rnd(n, co, h, w, seed=5), (1, 1, 1, 1)))
+        res_desc = rbuf.desc()
+    outs = []
+    for flags in (0, L.TMA_IN_HALO_VALID):
+        keep = []
+        y = torch.full((n, h, w, co), float('nan'), device='cuda')
+        ob = PlaneBuf(n, h * up, w * up, co, fill=3.0)
+        od = ob.desc()
+        a = _args(buf.desc(), pad_mode, cabi.krsc(wt), None, shift, L.ACT_RELU, res_desc, y, od, up, 1, None, L.ACT_NONE, 3, keep)
+        a.flags = flags
+        if split:
+            nbytes = lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+            ws = torch.full((max(nbytes, 16),), 0xFF, dtype=torch.uint8, device='cuda')
+            L.check(lib.clslam_conv3x3_tma_ws(ctypes.byref(a), ws.data_ptr(), nbytes, cabi.stream()), 'conv3x3_tma_ws')
+        else:
+            L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma')
+        torch.cuda.synchronize()
+        outs.append((y, ob))
+    (y0, o0), (y1, o1) = outs
+    assert not torch.isnan(y1).any()
+    if split:        # the two launches may be split differently: same products, other summation order
+        assert cabi.rel_err(y1, y0) < 2e-6 and cabi.rel_err(o1.value(), o0.value()) < 2e-5
+    else:
+        assert torch.equal(y1, y0) and torch.equal(o1.t, o0.t)
+    xq = buf.value()
+    ref = F.relu(F.conv2d(xq, wt) + shift.view(1, -1, 1, 1) + (rbuf.value()[:, :, 1:-1, 1:-1] if use_res else 0))
+    assert cabi.rel_err(cabi.nchw(y1), ref) < TOL

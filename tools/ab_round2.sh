@@ -49,6 +49,8 @@ run_tests photo_occ3 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py tests/
 run_tests photo_reuse_occ3 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py
 run_tests disp_wgrad_lane1 CLSLAM_DISP_WGRAD_LANE1=1 -- tests/test_gpu_e2e.py
 run_tests tma_ds CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_DS=1 -- tests/test_gpu_e2e.py
+run_tests tma_tall CLSLAM_TMA_TALL=1 -- tests/test_gpu_e2e.py
+run_tests tma_tall_splitk CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1 -- tests/test_gpu_e2e.py
 # ---- 3. bench lines ----------------------------------------------------------------------------------------
 for b in 1 8; do
   run_bench base "$b" CLSLAM_AB=base
@@ -61,7 +63,10 @@ for b in 1 8; do
   run_bench photo_reuse_occ3 "$b" CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1
   run_bench disp_wgrad_lane1 "$b" CLSLAM_DISP_WGRAD_LANE1=1
   run_bench splitk_ds "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_DS=1
-  run_bench all "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_DS=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 CLSLAM_DISP_WGRAD_LANE1=1
+  run_bench tall "$b" CLSLAM_TMA_TALL=1
+  run_bench tall_splitk "$b" CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1
+  run_bench tall_splitk_waves "$b" CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WAVES=1
+  run_bench all "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_TALL=1 CLSLAM_TMA_DS=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 CLSLAM_DISP_WGRAD_LANE1=1
 done
 # ---- 4. where a TMA conv launch spends its time (debug build with clock stamps) ---------------------------------
 timeout 600 $PY tools/tma_stamps.py > "$OUT/tma_stamps.log" 2>&1
