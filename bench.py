@@ -304,6 +304,19 @@ def run_ours(args):
     barrier()
     e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
     clocks = sampler.stop() if sampler else None
+    # ---- per-frame latency of adapt(steps=5): one H2D staging, five iterations (informational) ----------------
+    frame5_ms = None
+    if world == 1:
+        try:
+            barrier()
+            t5 = time.perf_counter()
+            for _ in range(5):
+                _, l5 = pred.adapt(dict(host), dict(host), steps=5)
+                _ = float(l5['loss'])
+            barrier()
+            frame5_ms = (time.perf_counter() - t5) * 1e3 / 5
+        except Exception as exc:          # never lose the bench line over the extra number
+            print(f'adapt(steps=5) timing failed: {exc}', file=sys.stderr)
 
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -325,6 +338,8 @@ def run_ours(args):
             'cuda_graph': not args.no_graph,
             'loss': float(losses['loss']),
         }
+        if frame5_ms is not None:
+            line['adapt_steps5_ms_per_frame'] = frame5_ms
         peaks = {}
         pk = ROOT / 'MEASURED_PEAKS.json'
         if pk.exists():
