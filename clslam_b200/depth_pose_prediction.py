@@ -20,7 +20,7 @@ import torch
 from torch import Tensor, nn, optim
 
 from . import _lib as L
-from .engine import AdaptEngine, EncoderRunner, Plan, PreparedEncoder, _p
+from .engine import H2D_OVERLAP, AdaptEngine, EncoderRunner, Plan, PreparedEncoder, _p
 from .networks import DepthDecoder, FlatParams, PoseDecoder, ResnetEncoder
 from .sharding import global_sample_weights, shard_range
 
@@ -76,6 +76,11 @@ class FlatAdam:
 
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.flat.grads.zero_()
+
+
+# inputs that only the photometric chain / the losses read (H2D_OVERLAP: they travel on the copy stream while the networks run)
+LATE_INPUT_KEYS = frozenset([('rgb', 0, 0), ('rgb', -1, 0), ('rgb', 1, 0), ('rgb', 0, 1), ('rgb', 0, 2), ('rgb', 0, 3),
+                             ('relative_distance', 0), ('relative_distance', 1)])
 
 
 class DepthPosePrediction:
@@ -181,6 +186,7 @@ class DepthPosePrediction:
         self.stage_all_inputs = True          # move every dict value to the device like :916-917
         self._mode = 'eval'
         self._adapt_flags_set = False
+        self._late_event = None
 
     # ------------------------------------------------------------------------------------------
     def _validate_sets(self, dataset_config) -> None:
@@ -324,12 +330,18 @@ class DepthPosePrediction:
         if defer_unused:
             self._stage_event = torch.cuda.Event()
             self._stage_event.record(torch.cuda.current_stream(self.device))
+        overlap = H2D_OVERLAP and defer_unused and self.world == 1
+        late: List[Tuple[Tensor, Tensor]] = []
         for key in list(inputs.keys()):
             val = inputs[key]
             dst = smap.get(key)
             if dst is not None:
                 if not (val.is_cuda and val.data_ptr() == dst.data_ptr()):
-                    dst.copy_(val if val.shape == dst.shape else val.reshape(dst.shape), non_blocking=True)
+                    src = val if val.shape == dst.shape else val.reshape(dst.shape)
+                    if overlap and key in LATE_INPUT_KEYS:
+                        late.append((dst, src))
+                    else:
+                        dst.copy_(src, non_blocking=True)
                 inputs[key] = dst
             elif self.stage_all_inputs and isinstance(val, Tensor):
                 # keys the path does not read are still moved like :916-917, into cached device buffers (no allocation per call)
@@ -345,6 +357,18 @@ class DepthPosePrediction:
         missing = [k for k in smap if k not in inputs and not (k[0] == 'relative_distance' and eng.vel_scale == 0.0)]
         if missing:
             raise KeyError(f'batch dict lacks keys the adaptation path reads: {missing}')
+        self._late_event = None
+        if overlap and late:
+            # the photometric inputs follow the network inputs on the copy stream; the second graph of the step waits for them
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cur = torch.cuda.current_stream(self.device)
+            self._copy_stream.wait_stream(cur)        # earlier readers of these buffers (the previous step) and the copies above
+            with torch.cuda.stream(self._copy_stream):
+                for dst, src in late:
+                    dst.copy_(src, non_blocking=True)
+            self._late_event = torch.cuda.Event()
+            self._late_event.record(self._copy_stream)
         return eng
 
     def _flush_deferred(self) -> None:
@@ -465,8 +489,29 @@ class DepthPosePrediction:
         lr = self._adam_lr()
         n_run = self._steps_run.get(eng.b, 0)
         self._steps_run[eng.b] = n_run + 1
+        late_event = getattr(self, '_late_event', None)
         if not self.use_cuda_graph or n_run == 0:       # first step eager: loads every kernel before capture
+            if late_event is not None:
+                torch.cuda.current_stream(self.device).wait_event(late_event)
             eng.forward_backward(); self._allreduce_grads(); eng.adam(lr)
+            return
+        if self.world == 1 and H2D_OVERLAP:
+            # two graphs: the networks (need rgb_aug / intrinsics only) run while the photometric inputs are still in flight
+            ka, kb = (eng.b, 'nets'), (eng.b, 'rest', lr)
+            if ka not in self._graphs:
+                ga = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ga):
+                    eng.networks_forward()
+                self._graphs[ka] = ga
+            if kb not in self._graphs:
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb):
+                    eng.photometric_and_backward(); eng.adam(lr)
+                self._graphs[kb] = gb
+            self._graphs[ka].replay()
+            if late_event is not None:
+                torch.cuda.current_stream(self.device).wait_event(late_event)
+            self._graphs[kb].replay()
             return
         if self.world == 1:
             key = (eng.b, 'step', lr)

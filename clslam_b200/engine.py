@@ -55,6 +55,11 @@ TMA_DS = os.environ.get('CLSLAM_TMA_DS', '0') == '1'
 # planes buffer this engine feeds to a zero-padded launch has an all-zero halo (allocated zeroed, producers write with
 # out_halo = 0); reflection-padded launches read the reflection halo anyway.
 TMA_TALL = os.environ.get('CLSLAM_TMA_TALL', '0') == '1'
+# EXPERIMENTAL (off by default): the step is two graphs.  The first holds everything that only reads the network inputs (rgb_aug,
+# intrinsics); the photometric inputs (rgb target / sources, colour pyramid, distances: half of the H2D bytes) travel on a
+# copy stream meanwhile and the second graph waits for them.  The identity candidates then run at the head of the second
+# graph instead of on lane 2 next to the encoders.
+H2D_OVERLAP = os.environ.get('CLSLAM_H2D_OVERLAP', '0') == '1'
 
 
 def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
@@ -546,8 +551,9 @@ class AdaptEngine:
         plan.record('wsplit')
         # identity (auto-mask) candidates and the packed sources only depend on the inputs
         self.identity = plan.alloc(b, 2, h, w)
-        plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
-        plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
+        if not H2D_OVERLAP:
+            plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
+            plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
         plan.set_lane(0)
         self.depth_in, depth_s2d = stage_for_encoder(plan, depth_prep, 'depth.stage', [(self.rgb_aug[1], None, 0, b)], b, h, w)
         # decoder geometry first: which layers run the TMA kernel decides where the encoder writes its skip features
@@ -710,6 +716,10 @@ class AdaptEngine:
         self.loss_args = la
         plan.keep.append(la)
         plan.join((1, 2))
+        self.n_net_ops = len(plan.ops)       # ops [0, n_net_ops) read rgb_aug / intrinsics only: the first graph of H2D_OVERLAP
+        if H2D_OVERLAP:
+            plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
+            plan.simple('photo_identity', lib.clslam_photo_identity, _p(self.target), _p(self.sources), _p(self.identity), b, h, w)
         plan.add('photo_fwd', lambda stream, ws: lib.clslam_photo_fwd(ctypes.byref(pa), stream))
         # the loss assembly is off the critical path (photo_bwd does not need it): lane 2, next to photo_bwd
         plan.record('pfwd')
@@ -910,6 +920,15 @@ class AdaptEngine:
     def forward_backward(self) -> None:
         """one pass without the forward-only join (the loss assembly overlaps the photometric backward)"""
         self.plan.run(0, self.n_fwd_core)
+        self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
+
+    def networks_forward(self) -> None:
+        """first part of forward_backward: both networks (reads rgb_aug and the intrinsics only)"""
+        self.plan.run(0, self.n_net_ops)
+
+    def photometric_and_backward(self) -> None:
+        """second part of forward_backward: photometric chain, losses, backward pass"""
+        self.plan.run(self.n_net_ops, self.n_fwd_core)
         self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
 
     def adam(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:

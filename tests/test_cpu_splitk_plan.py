@@ -171,3 +171,41 @@ def test_tall_form_geometry():
     assert q(8, 48, 160, 64, 128, L.TMA_IN_HALO_VALID) == q(8, 48, 160, 64, 128, 0)
     assert q(1, 6, 20, 512, 512, L.TMA_IN_HALO_VALID) == q(1, 6, 20, 512, 512, 0)
     assert q(2, 6, 20, 256, 512, L.TMA_IN_HALO_VALID, L.PAD_FULL) == q(2, 6, 20, 256, 512, 0, L.PAD_FULL)
+
+
+def test_h2d_overlap_plan_splits_into_two_self_contained_graphs():
+    """CLSLAM_H2D_OVERLAP=1: ops [0, n_net_ops) (both networks) never touch the photometric inputs and every event waited for
+    inside one part is recorded earlier in the same part (each part is captured as its own CUDA graph)"""
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+from tests.test_cpu_plan_builds import build
+for cfg in [(1, 192, 640), (8, 192, 640), (2, 64, 96)]:
+    eng = build(*cfg)
+    ops = eng.plan.ops
+    parts = [list(range(0, eng.n_net_ops)), list(range(eng.n_net_ops, eng.n_fwd_core)) + list(range(eng.n_fwd_ops, eng.n_bwd_ops))]
+    for idxs in parts:
+        seen = set()
+        for i in idxs:
+            name, fn, a, lane = ops[i]
+            if fn is None and name == "__record__":
+                seen.add(a[0])
+            elif fn is None:
+                assert a[0] in seen, (cfg, a[0])
+    na = [ops[i][0] for i in parts[0] if ops[i][1] is not None]
+    nb = [ops[i][0] for i in parts[1] if ops[i][1] is not None]
+    assert not any(n.startswith("photo") or n in ("pack_rgba", "loss_finalize") for n in na)
+    assert nb[:3] == ["pack_rgba", "photo_identity", "photo_fwd"]
+    assert sorted(na + nb) == sorted(o[0] for i, o in enumerate(ops) if o[1] is not None)
+print("ok")
+'''
+    env = dict(os.environ, CLSLAM_H2D_OVERLAP='1')
+    r = subprocess.run([sys.executable, '-c', code], cwd=str(ROOT), env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_late_input_keys_are_exactly_what_the_networks_do_not_read():
+    from clslam_b200.depth_pose_prediction import LATE_INPUT_KEYS
+    early = {('rgb_aug', f, 0) for f in (-1, 0, 1)} | {('camera_matrix', 0), ('inv_camera_matrix', 0)}
+    assert not (early & LATE_INPUT_KEYS)
+    assert {('rgb', f, 0) for f in (-1, 0, 1)} <= LATE_INPUT_KEYS and ('rgb', 0, 3) in LATE_INPUT_KEYS

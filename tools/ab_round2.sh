@@ -49,6 +49,7 @@ run_tests photo_occ3 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py tests/
 run_tests photo_reuse_occ3 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 -- tests/test_gpu_photometric.py
 run_tests disp_wgrad_lane1 CLSLAM_DISP_WGRAD_LANE1=1 -- tests/test_gpu_e2e.py
 run_tests tma_ds CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_DS=1 -- tests/test_gpu_e2e.py
+run_tests h2d_overlap CLSLAM_H2D_OVERLAP=1 -- tests/test_gpu_e2e.py
 run_tests tma_tall CLSLAM_TMA_TALL=1 -- tests/test_gpu_e2e.py
 run_tests tma_tall_splitk CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1 -- tests/test_gpu_e2e.py
 # ---- 3. bench lines ----------------------------------------------------------------------------------------
@@ -63,6 +64,7 @@ for b in 1 8; do
   run_bench photo_reuse_occ3 "$b" CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1
   run_bench disp_wgrad_lane1 "$b" CLSLAM_DISP_WGRAD_LANE1=1
   run_bench splitk_ds "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_DS=1
+  run_bench h2d_overlap "$b" CLSLAM_H2D_OVERLAP=1
   run_bench tall "$b" CLSLAM_TMA_TALL=1
   run_bench tall_splitk "$b" CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1
   run_bench tall_splitk_waves "$b" CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WAVES=1
