@@ -2,7 +2,7 @@
 # One gpurun call that answers every open A/B question left by round 1 (the experimental paths below were written after
 # that round's GPU budget was spent and have not run on hardware yet):
 #
-#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/ab_round2.sh'      # ~13 min of box time
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/ab_round2.sh'      # ~20 min of box time
 #
 # 1. parity of the split-K TMA convolution / fused split-K dgrad (opt-in tests) and of the whole step with the small
 #    layers routed through it; 2. parity of the photometric variants; 3. bench lines (device-resident value only:
@@ -68,7 +68,7 @@ for b in 1 8; do
   run_bench tall "$b" CLSLAM_TMA_TALL=1
   run_bench tall_splitk "$b" CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1
   run_bench tall_splitk_waves "$b" CLSLAM_TMA_TALL=1 CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_SPLITK_WAVES=1
-  run_bench all "$b" CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_TALL=1 CLSLAM_TMA_DS=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 CLSLAM_DISP_WGRAD_LANE1=1
+  run_bench all "$b" CLSLAM_H2D_OVERLAP=1 CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_TALL=1 CLSLAM_TMA_DS=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 CLSLAM_DISP_WGRAD_LANE1=1
 done
 # ---- 4. where a TMA conv launch spends its time (debug build with clock stamps) ---------------------------------
 timeout 600 $PY tools/tma_stamps.py > "$OUT/tma_stamps.log" 2>&1
