@@ -19,14 +19,25 @@ run_tests() {           # tag, env assignments..., -- pytest args
   local envs=()
   while [ "$1" != "--" ]; do envs+=("$1"); shift; done
   shift
-  env "${envs[@]}" timeout 600 $PY -m pytest "$@" -m gpu -q -x > "$OUT/test_$tag.log" 2>&1
-  echo "test $tag rc=$? $(tail -1 "$OUT/test_$tag.log")" | tee -a "$OUT/summary.txt"
+  env "${envs[@]}" timeout 240 $PY -m pytest "$@" -m gpu -q -x > "$OUT/test_$tag.log" 2>&1
+  local rc=$?
+  echo "test $tag rc=$rc $(tail -1 "$OUT/test_$tag.log")" | tee -a "$OUT/summary.txt"
+  stop_if_hung "$rc" "test $tag"
+}
+
+stop_if_hung() {        # a timeout means a kernel hung: do not burn the GPU budget (or a strike) on the remaining steps
+  if [ "$1" -eq 124 ] || [ "$1" -eq 137 ]; then
+    echo "ABORT: $2 timed out; remaining steps skipped" | tee -a "$OUT/summary.txt"
+    cat "$OUT/summary.txt"
+    exit 3
+  fi
 }
 
 run_bench() {           # tag, batch, env assignments...
   local tag=$1 b=$2; shift 2
-  env "$@" timeout 300 $PY bench.py --batch-per-gpu "$b" --steps 30 --warmup 5 --no-cpu-baseline --no-op-profile \
+  env "$@" timeout 180 $PY bench.py --batch-per-gpu "$b" --steps 30 --warmup 5 --no-cpu-baseline --no-op-profile \
       > "$OUT/bench_${tag}_b${b}.json" 2> "$OUT/bench_${tag}_b${b}.err"
+  local rc=$?
   $PY - "$OUT/bench_${tag}_b${b}.json" "$tag" "$b" <<'PYEOF' | tee -a "$OUT/summary.txt"
 import json, sys
 try:
@@ -36,6 +47,7 @@ try:
 except Exception as e:
     print(f"bench {sys.argv[2]} b{sys.argv[3]}: FAILED ({e})")
 PYEOF
+  stop_if_hung "$rc" "bench $tag b$b"
 }
 
 : > "$OUT/summary.txt"
@@ -71,10 +83,10 @@ for b in 1 8; do
   run_bench all "$b" CLSLAM_H2D_OVERLAP=1 CLSLAM_TMA_SPLITK=1 CLSLAM_TMA_TALL=1 CLSLAM_TMA_DS=1 CLSLAM_PHOTO_BWD_REUSE=1 CLSLAM_PHOTO_OCC3=1 CLSLAM_DISP_WGRAD_LANE1=1
 done
 # ---- 4. where a TMA conv launch spends its time (debug build with clock stamps) ---------------------------------
-timeout 600 $PY tools/tma_stamps.py > "$OUT/tma_stamps.log" 2>&1
+timeout 300 $PY tools/tma_stamps.py > "$OUT/tma_stamps.log" 2>&1
 echo "tma_stamps rc=$?" | tee -a "$OUT/summary.txt"
 # ---- 5. per-layer numbers: gather vs plain TMA vs split-K -----------------------------------------------------
-timeout 600 $PY tools/splitk_microbench.py > "$OUT/splitk_microbench.jsonl" 2> "$OUT/splitk_microbench.err"
+timeout 300 $PY tools/splitk_microbench.py > "$OUT/splitk_microbench.jsonl" 2> "$OUT/splitk_microbench.err"
 echo "splitk_microbench rc=$?" | tee -a "$OUT/summary.txt"
 echo "---- summary ----"
 cat "$OUT/summary.txt"
