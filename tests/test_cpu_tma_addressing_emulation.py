@@ -14,8 +14,8 @@ TH, TW, KC = 16, 8, 64
 PAD_ZERO, PAD_REFLECT, PAD_FULL = 0, 1, 2
 
 
-def emulate(planes, n, h, w, c_total, c_off, cin, wk, pad_mode, tall):
-    """planes: (n, h + 2, w + 2, c_total) values (hi + lo); wk: (cout, 3, 3, cin).  Returns y (n, ho, wo, cout)."""
+def emulate(planes, n, h, w, c_total, c_off, cin, wk, pad_mode, tall, taps=3):
+    """planes: (n, h + 2, w + 2, c_total) values (hi + lo); wk: (cout, taps, taps, cin).  Returns y (n, ho, wo, cout)."""
     cout = wk.shape[0]
     hp, wp = h + 2, w + 2
     full = pad_mode == PAD_FULL
@@ -27,7 +27,7 @@ def emulate(planes, n, h, w, c_total, c_off, cin, wk, pad_mode, tall):
         tiles_y, n_img = -(-(n * hp - 2) // TH), 1
     padded_view = pad_mode == PAD_REFLECT or tall
     base = c_off + (0 if padded_view else (wp + 1) * c_total)
-    org = 0 if padded_view else (-2 if full else -1)
+    org = 0 if padded_view else (-2 if full else (0 if taps == 1 else -1))
     dim_x = wp if padded_view else w
     dim_y = n * hp if tall else (hp if padded_view else h)
     dim_n = 1 if tall else n
@@ -35,8 +35,8 @@ def emulate(planes, n, h, w, c_total, c_off, cin, wk, pad_mode, tall):
 
     def box(c0, x0, y0, img):
         """cp.async.bulk.tensor box (KC channels, 8 px, 18 rows) at tensor-map coordinates; zero outside the map"""
-        out = np.zeros((TH + 2, TW, KC))
-        for yy in range(TH + 2):
+        out = np.zeros((TH + taps - 1, TW, KC))
+        for yy in range(TH + taps - 1):
             for xx in range(TW):
                 x, y = x0 + xx, y0 + yy
                 if 0 <= x < dim_x and 0 <= y < dim_y and 0 <= img < dim_n:
@@ -51,9 +51,9 @@ def emulate(planes, n, h, w, c_total, c_off, cin, wk, pad_mode, tall):
                 oh0, ow0 = ty * TH + org, tx * TW + org
                 acc = np.zeros((TH * TW, cout))
                 for chunk in range(cin // KC):
-                    for sft in range(3):
+                    for sft in range(taps):
                         patch = box(chunk * KC, ow0 + sft, oh0, img0)
-                        for r in range(3):      # descriptor start moved by r row groups of 8 pixels
+                        for r in range(taps):   # descriptor start moved by r row groups of 8 pixels
                             a = patch[r:r + TH].reshape(TH * TW, KC)
                             acc += a @ wk[:, r, sft, chunk * KC:(chunk + 1) * KC].T
                 for lane in range(TH * TW):
@@ -123,3 +123,19 @@ def test_tall_form_needs_the_zero_halo_it_is_promised():
     bad = emulate(make_planes(x, PAD_ZERO, 64, 0, True), n, h, w, 64, 0, cin, wk, PAD_ZERO, True)
     good = emulate(make_planes(x, PAD_ZERO, 64, 0, False), n, h, w, 64, 0, cin, wk, PAD_ZERO, True)
     assert np.abs(good - ref).max() < 1e-9 and np.abs(bad - ref).max() > 1.0
+
+
+def test_downsample_as_one_tap_over_the_space_to_depth_planes():
+    """CLSLAM_TMA_DS: BasicBlock.downsample (1x1 / stride 2) = a one-tap launch over the first cin channels of the
+    space-to-depth planes (channel (p * 2 + q) * c + k of pixel (y, x) is channel k of pixel (2y + p, 2x + q))"""
+    n, h, w, cin, cout = 2, 12, 20, 64, 16
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(n, cin, h, w, generator=g, dtype=torch.float64) - 0.5
+    wt = (torch.rand(cout, cin, 1, 1, generator=g, dtype=torch.float64) - 0.5) / 8
+    s2d = x.view(n, cin, h // 2, 2, w // 2, 2).permute(0, 2, 4, 3, 5, 1).reshape(n, h // 2, w // 2, 4 * cin)      # (p, q, k) channels
+    buf = np.full((n, h // 2 + 2, w // 2 + 2, 4 * cin), 7.0)          # poisoned halo: the interior view never reads it
+    buf[:, 1:-1, 1:-1] = s2d.numpy()
+    wk = wt.permute(0, 2, 3, 1).contiguous().numpy()
+    y = emulate(buf, n, h // 2, w // 2, 4 * cin, 0, cin, wk, PAD_ZERO, False, taps=1)
+    ref = F.conv2d(x, wt, stride=2).permute(0, 2, 3, 1).numpy()
+    np.testing.assert_allclose(y, ref, rtol=0, atol=1e-12)
