@@ -43,6 +43,7 @@ CASES = {
 # adapt(online_loss_weight=...), i.e. non-uniform per-sample loss weights (:297-305): name -> online_loss_weight
 REPLAY_CASES = {
     'small_b4_replay': (4, 64, 96, True, None, 6),
+    'small_b8_replay': (8, 64, 96, True, None, 7),       # BASELINE configs[2]: 1 current + 7 replay triplets, default weights
 }
 ONLINE_LOSS_WEIGHT = {'small_b4_replay': 0.4}
 
@@ -125,7 +126,8 @@ def run_case(name, spec, out_dir: Path):
     rec = {}
     if replay:
         rec['replay_variant'] = np.array([1.0])
-        rec['online_loss_weight'] = np.array([olw])
+        if olw is not None:
+            rec['online_loss_weight'] = np.array([olw])
     rec['meta'] = np.array([b, h, w, int(coherent), -1.0 if max_depth is None else max_depth, seed],
                            dtype=np.float64)
     rec['input_checksum'] = np.array(

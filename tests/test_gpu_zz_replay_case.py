@@ -19,7 +19,7 @@ from oracle import clslam_oracle as orc        # the checker + the seeded input 
 pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='new fixture, not yet run on hardware')]
 GOLDEN = Path(__file__).resolve().parent / 'golden'
 REL_TOL = 1e-4          # north_star: disparity and pose within 1e-4 relative of the reference
-NAME = 'small_b4_replay'
+NAMES = ['small_b4_replay', 'small_b8_replay']      # the second: BASELINE configs[2] (1 current + 7 replay), default weights
 
 
 def rel(a, b):
@@ -27,8 +27,8 @@ def rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
 
 
-def build(**kw):
-    rec = np.load(GOLDEN / f'{NAME}.npz')
+def build(name, **kw):
+    rec = np.load(GOLDEN / f'{name}.npz')
     b, h, w, _, max_depth, seed = rec['meta']
     b, h, w, seed = int(b), int(h), int(w), int(seed)
     pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b), **kw)
@@ -38,12 +38,13 @@ def build(**kw):
     batch = orc.make_replay_batch(b, h, w, seed=seed)
     noise = orc.make_noise(b, h, w, seed=seed)
     pred.noise_provider = lambda s, shape: noise[s]
-    olw = float(rec['online_loss_weight'][0])
+    olw = float(rec['online_loss_weight'][0]) if 'online_loss_weight' in rec.files else None
     return rec, pred, params, batch, noise, olw, (b, h, w)
 
 
-def test_replay_batch_outputs_losses_gradients():
-    rec, pred, params, batch, noise, olw, (b, h, w) = build()
+@pytest.mark.parametrize('name', NAMES)
+def test_replay_batch_outputs_losses_gradients(name):
+    rec, pred, params, batch, noise, olw, (b, h, w) = build(name)
     pred._set_adapt(True)
     outputs, losses = pred._process_batch(dict(batch), orc.adapt_loss_weights(b, olw))
     torch.cuda.synchronize()
@@ -70,9 +71,10 @@ def test_replay_batch_outputs_losses_gradients():
         assert abs(float(got.double().norm()) - gn) / (gn + 1e-30) < 2e-3, (net, key)
 
 
+@pytest.mark.parametrize('name', NAMES)
 @pytest.mark.parametrize('graph', [False, True])
-def test_replay_batch_adapt_with_online_loss_weight(graph):
-    rec, pred, params, batch, noise, olw, (b, h, w) = build(use_cuda_graph=graph)
+def test_replay_batch_adapt_with_online_loss_weight(name, graph):
+    rec, pred, params, batch, noise, olw, (b, h, w) = build(name, use_cuda_graph=graph)
     _, losses1 = pred.adapt(dict(batch), dict(batch), steps=1, online_loss_weight=olw)
     np.testing.assert_allclose(losses1['loss'].cpu().numpy(), rec['loss:loss'], rtol=1e-4)
     _, losses2 = pred.adapt(dict(batch), dict(batch), steps=1, online_loss_weight=olw)

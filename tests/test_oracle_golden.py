@@ -11,7 +11,8 @@ from oracle import clslam_oracle as orc
 GOLDEN = Path(__file__).resolve().parent / 'golden'
 SMALL = ['small_b2', 'small_b3_coherent', 'small_b1_maxdepth']
 FULL = ['full_b1', 'full_b2_coherent']
-REPLAY = ['small_b4_replay']      # per-sample intrinsics, rgb_aug != rgb, adapt(online_loss_weight=0.4)
+REPLAY = ['small_b4_replay',      # per-sample intrinsics, rgb_aug != rgb, adapt(online_loss_weight=0.4)
+          'small_b8_replay']      # BASELINE configs[2]: 1 current + 7 replay triplets, default weights
 
 
 def load_case(name):
