@@ -562,6 +562,89 @@ class DepthPosePrediction:
                                   'BatchNorm: SURVEY.md 8(f) row 3.  Use adapt().')
 
     # ------------------------------------------------------------------------------------------
+    # inference entry points of the reference that Slam does not call (:530-626).  They reuse the adaptation engine's forward
+    # pass; added after round 1's last GPU run (API completeness, not yet exercised on hardware).
+    def predict(self, batch) -> Dict[Any, Tensor]:
+        """:530-536: eval-mode forward of one batch dict, returns the outputs"""
+        if not self.is_trained:
+            warnings.warn('The model has not been trained yet.', RuntimeWarning)
+        self._set_eval()
+        with torch.no_grad():
+            outputs, _ = self._process_batch(batch)
+        return outputs
+
+    def _depth_of(self, image: Tensor) -> Tensor:
+        """depth of `image` (n, 3, H, W) from the depth network alone.  The engine evaluates whole triplets, so the image
+        stands in for all three frames with a generic camera; only ('depth', 0) = disp_to_depth(disp_0) is kept, which
+        does not depend on the other frames or the intrinsics."""
+        from . import synthetic
+        if image.dim() == 3:
+            image = image.unsqueeze(0)
+        n = image.shape[0]
+        img = image.to(dtype=torch.float32)
+        batch: Dict[Any, Tensor] = {}
+        for f in (-1, 0, 1):
+            batch[('rgb', f, 0)] = img
+            batch[('rgb_aug', f, 0)] = img
+        for sc in range(1, 4):
+            batch[('rgb', 0, sc)] = torch.nn.functional.avg_pool2d(img, 2 ** sc)
+        k, ik = synthetic.kitti_intrinsics(self.height, self.width, 0)
+        batch[('camera_matrix', 0)] = torch.from_numpy(k).unsqueeze(0).repeat(n, 1, 1)
+        batch[('inv_camera_matrix', 0)] = torch.from_numpy(ik).unsqueeze(0).repeat(n, 1, 1)
+        for f in (0, 1):
+            batch[('relative_distance', f)] = torch.zeros(n, dtype=torch.float64)
+        self._set_eval()
+        with torch.no_grad():
+            outputs, _ = self._process_batch(batch, torch.ones(n) / n)
+        if ('depth', 0) in outputs:
+            return outputs[('depth', 0)].clone()
+        disp = outputs[('disp', 0)]                       # emit_outputs=False: depth_pose_prediction/utils.py:120-142
+        if self.max_depth is None:
+            return (self.min_depth if self.min_depth is not None else 1.0) / disp
+        return 1.0 / (1.0 / self.max_depth + (1.0 / self.min_depth - 1.0 / self.max_depth) * disp)
+
+    def predict_from_image(self, image, as_numpy: bool = True):
+        """:538-554: one image in, predicted depth out"""
+        if not self.is_trained:
+            warnings.warn('The model has not been trained yet.', RuntimeWarning)
+        depth = self._depth_of(image)
+        if as_numpy:
+            depth = depth.squeeze().cpu().detach().numpy()
+        return depth
+
+    def predict_from_images(self, image_0: Tensor, image_1: Tensor, as_numpy: bool = True, return_loss: bool = False,
+                            camera_matrix: Optional[Tensor] = None, inv_camera_matrix: Optional[Tensor] = None,
+                            relative_distance: Optional[Tensor] = None):
+        """:556-626: two images in, depth of both and the relative pose (image_0 -> image_1, not inverted) out"""
+        if return_loss:
+            raise NotImplementedError('predict_from_images(return_loss=True): the two-frame, single-scale loss of :603-624 is '
+                                      'outside the adaptation hot path (SURVEY.md 8)')
+        if not self.is_trained:
+            warnings.warn('The model has not been trained yet.', RuntimeWarning)
+        depth_0, depth_1 = self._depth_of(image_0), self._depth_of(image_1)
+        was_trained, self.is_trained = self.is_trained, True          # the warning above was issued once
+        try:
+            transformation, _ = self.predict_pose(image_0, image_1, as_numpy=False)
+        finally:
+            self.is_trained = was_trained
+        if as_numpy:
+            depth_0 = depth_0.squeeze().cpu().detach().numpy()
+            depth_1 = depth_1.squeeze().cpu().detach().numpy()
+            transformation = transformation.squeeze().cpu().detach().numpy()
+        return depth_0, depth_1, transformation
+
+    def validate(self) -> float:
+        raise NotImplementedError('validate() (:321-342) iterates the validation DataLoader: datasets are outside SURVEY.md 8')
+
+    def compute_depth_error(self, median_scaling: bool = True, print_results: bool = True) -> Dict[str, float]:
+        raise NotImplementedError('compute_depth_error() (:344-468) needs the dataset loaders: outside SURVEY.md 8')
+
+    def compute_pose_error(self, print_results: bool = True) -> Dict[str, float]:
+        raise NotImplementedError('compute_pose_error() (:470-528) needs the dataset loaders: outside SURVEY.md 8')
+
+    def save_prediction(self, inputs: Dict[Any, Tensor], outputs: Dict[Any, Tensor]) -> None:
+        raise NotImplementedError('save_prediction() (:1197 ff.) is plotting (matplotlib): outside SURVEY.md 8')
+
     def predict_pose(self, image_0: Tensor, image_1: Tensor, as_numpy: bool = True, use_online: bool = False):
         """:628-664: pose net forward for a loop-closure pair, invert=False; returns (4x4, eye(6))."""
         if not self.is_trained:

@@ -1,0 +1,109 @@
+"""API surface of the drop-in class against the UNMODIFIED reference class, checked live: method
+signatures Slam and main_pretrain call, the attributes they read, the configuration errors of :85-120 and the normalised
+train / val sets.  Needs the reference checkout (/root/reference, present in the build container; skipped elsewhere)."""
+import dataclasses
+import inspect
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+REFERENCE = Path('/root/reference')
+pytestmark = pytest.mark.skipif(not (REFERENCE / 'depth_pose_prediction').is_dir(), reason='reference checkout not present')
+
+
+@pytest.fixture(scope='module')
+def ref():
+    before = list(sys.path)
+    sys.path.insert(0, str(ROOT / 'oracle'))
+    try:
+        import make_golden as mg
+        Dataset, Cfg, RefPred = mg.import_reference()
+    finally:
+        sys.path[:] = before
+    return Dataset, Cfg, RefPred
+
+
+def _ref_cfg(Dataset, Cfg, **over):
+    ds = Dataset(dataset=over.pop('dataset', 'Kitti'), config_file=Path('x'), dataset_path=None, scales=(0, 1, 2, 3), height=64, width=96,
+                 frame_ids=(0, -1, 1))
+    kw = dict(config_file=Path('x'), train_set=(0,), val_set=(9,), resnet_depth=18, resnet_pose=18, resnet_pretrained=False,
+              scales=(0, 1, 2, 3), learning_rate=1e-4, scheduler_step_size=15, batch_size=2, num_workers=0, num_epochs=1, min_depth=0.1,
+              max_depth=None, disparity_smoothness=1e-3, velocity_loss_scaling=0.05, mask_dynamic=False, log_path=Path('/tmp/clslam_api'),
+              save_frequency=-1, save_val_depth=False, save_val_depth_batches=0, multiple_gpus=False, gpu_ids=None,
+              load_weights_folder=None, use_wandb=False)
+    kw.update(over)
+    return ds, Cfg(**kw)
+
+
+METHODS = ['adapt', 'predict_pose', 'load_model', 'save_model', '_set_eval', '_set_adapt', '_process_batch', 'predict',
+           'predict_from_image', 'predict_from_images', 'validate', 'compute_depth_error', 'compute_pose_error', 'save_prediction',
+           'load_online_model', 'train']
+
+
+def test_public_method_signatures_match(ref):
+    from clslam_b200 import DepthPosePrediction
+    _, _, RefPred = ref
+    for name in METHODS:
+        assert hasattr(DepthPosePrediction, name), name
+        want = inspect.signature(getattr(RefPred, name))
+        got = inspect.signature(getattr(DepthPosePrediction, name))
+        w = [(p.name, p.default) for p in want.parameters.values() if p.kind not in (p.VAR_POSITIONAL, p.VAR_KEYWORD)]
+        g = [(p.name, p.default) for p in got.parameters.values() if p.kind not in (p.VAR_POSITIONAL, p.VAR_KEYWORD)]
+        if name == 'train':          # not built: accepts anything, raises NotImplementedError
+            continue
+        assert g[:len(w)] == w, f'{name}: reference {w} vs {g}'
+    ctor_w = list(inspect.signature(RefPred.__init__).parameters)[:4]
+    ctor_g = list(inspect.signature(DepthPosePrediction.__init__).parameters)[:4]
+    assert ctor_g == ctor_w == ['self', 'dataset_config', 'config', 'use_online']
+
+
+def test_reference_config_objects_are_accepted_and_normalised_alike(ref):
+    """the reference's own dataclass instances construct the drop-in; train / val sets are normalised as in :85-110"""
+    from clslam_b200 import DepthPosePrediction
+    Dataset, Cfg, RefPred = ref
+    for over in (dict(train_set=0, val_set=9), dict(train_set='all', val_set=(9, 10)), dict(train_set=[0, 1], val_set=[9]),
+                 dict(dataset='Cityscapes', train_set='frankfurt', val_set='munster')):
+        ds, cfg = _ref_cfg(Dataset, Cfg, **dict(over))
+        r = RefPred(ds, dataclasses.replace(cfg))
+        o = DepthPosePrediction(ds, dataclasses.replace(cfg), device=torch.device('cpu'))
+        assert o.train_set == r.train_set and o.val_set == r.val_set, over
+        assert (o.min_depth, o.max_depth, o.batch_size, o.height, o.width) == (r.min_depth, r.max_depth, r.batch_size, r.height, r.width)
+        assert list(o.models.keys()) == list(r.models.keys())
+        assert tuple(o.frame_ids) == tuple(r.frame_ids) == (0, -1, 1)
+
+
+@pytest.mark.parametrize('over', [dict(train_set='some'), dict(train_set=(1.5,)), dict(val_set=('a',)),
+                                  dict(dataset='Cityscapes', train_set=(0,), val_set=('munster',)),
+                                  dict(gpu_ids=(0, 1))])
+def test_bad_configurations_raise_valueerror_in_both(ref, over):
+    from clslam_b200 import DepthPosePrediction
+    Dataset, Cfg, RefPred = ref
+    ds, cfg = _ref_cfg(Dataset, Cfg, **dict(over))
+    with pytest.raises(ValueError):
+        RefPred(ds, dataclasses.replace(cfg))
+    with pytest.raises(ValueError):
+        DepthPosePrediction(ds, dataclasses.replace(cfg), device=torch.device('cpu'))
+
+
+def test_every_public_method_of_the_reference_exists(ref):
+    """public = no leading underscore; the ones outside the hot path raise NotImplementedError with the reason"""
+    from clslam_b200 import DepthPosePrediction
+    _, _, RefPred = ref
+    public = [n for n, f in inspect.getmembers(RefPred, inspect.isfunction) if not n.startswith('_')]
+    missing = [n for n in public if not hasattr(DepthPosePrediction, n)]
+    assert not missing, missing
+    pred = DepthPosePrediction(*_our_cfg(), device=torch.device('cpu'))
+    for name, args in (('validate', ()), ('compute_depth_error', ()), ('compute_pose_error', ()), ('save_prediction', ({}, {})),
+                       ('train', ()), ('load_online_model', ())):
+        with pytest.raises(NotImplementedError):
+            getattr(pred, name)(*args)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):          # the compute entry points need the GPU
+        pred.predict_from_image(torch.zeros(1, 3, 64, 96))
+
+
+def _our_cfg():
+    from clslam_b200 import Config, DatasetConfig
+    return DatasetConfig(height=64, width=96), Config(batch_size=1)
