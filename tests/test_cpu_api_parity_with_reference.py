@@ -107,3 +107,33 @@ def test_every_public_method_of_the_reference_exists(ref):
 def _our_cfg():
     from clslam_b200 import Config, DatasetConfig
     return DatasetConfig(height=64, width=96), Config(batch_size=1)
+
+
+def test_output_and_loss_schema_matches_the_reference(ref, monkeypatch):
+    """keys, shapes and dtypes of what _process_batch returns: the reference runs on the CPU; the drop-in's
+    result dictionaries are assembled from an engine whose buffers were allocated on the CPU (no kernel runs)"""
+    import clslam_b200.depth_pose_prediction as dpp
+    from clslam_b200 import DepthPosePrediction
+    from oracle import clslam_oracle as orc
+    Dataset, Cfg, RefPred = ref
+    b, h, w = 2, 64, 96
+    ds, cfg = _ref_cfg(Dataset, Cfg)
+    r = RefPred(ds, dataclasses.replace(cfg))
+    r._set_adapt(freeze_encoder=True)
+    ref_out, ref_losses = r._process_batch(dict(orc.make_batch(b, h, w, seed=1, coherent=True)))
+
+    o = DepthPosePrediction(ds, dataclasses.replace(cfg), device=torch.device('cpu'))
+    monkeypatch.setattr(o, '_require_cuda', lambda: None)
+    monkeypatch.setattr(dpp.L, 'check', lambda rc, what='': None)          # clslam_set_device has no device to bind here
+    eng = o._engine(b)
+    out, losses = o._collect(eng, check_nan=False)
+
+    assert set(out.keys()) == set(ref_out.keys()), set(out.keys()) ^ set(ref_out.keys())
+    for k, v in ref_out.items():
+        assert tuple(out[k].shape) == tuple(v.shape), (k, out[k].shape, v.shape)
+        assert out[k].dtype == v.dtype, k
+    assert set(losses.keys()) == set(ref_losses.keys()) and len(losses) == 19
+    for k, v in ref_losses.items():
+        assert losses[k].numel() == v.numel() == 1 and losses[k].dtype == v.dtype, k
+    assert tuple(losses['loss'].shape) == tuple(ref_losses['loss'].shape) == (1,)
+    assert (losses['depth_loss'] is losses['loss']) and (ref_losses['depth_loss'] is ref_losses['loss'])      # SURVEY.md A.8
