@@ -137,3 +137,25 @@ def test_output_and_loss_schema_matches_the_reference(ref, monkeypatch):
         assert losses[k].numel() == v.numel() == 1 and losses[k].dtype == v.dtype, k
     assert tuple(losses['loss'].shape) == tuple(ref_losses['loss'].shape) == (1,)
     assert (losses['depth_loss'] is losses['loss']) and (ref_losses['depth_loss'] is ref_losses['loss'])
+
+
+def test_everything_slam_touches_on_the_predictor_exists():
+    """every attribute / method the reference's callers reach through their predictor object (slam/slam.py `self.predictor.*`,
+    main_pretrain.py) exists on the drop-in instance"""
+    import ast
+    from clslam_b200 import DepthPosePrediction
+    used = set()
+    for rel in ('slam/slam.py', 'main_pretrain.py', 'main_adapt.py'):
+        path = REFERENCE / rel
+        if not path.is_file():
+            continue
+        tree = ast.parse(path.read_text())
+        for node in ast.walk(tree):
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Attribute) and node.value.attr == 'predictor':
+                used.add(node.attr)                                       # self.predictor.<attr>
+            if isinstance(node, ast.Attribute) and isinstance(node.value, ast.Name) and node.value.id in ('predictor', 'depth_pose_predictor'):
+                used.add(node.attr)
+    assert {'adapt', 'load_model', 'predict_pose', 'device', 'models'} <= used, used       # the scan found the known call sites
+    pred = DepthPosePrediction(*_our_cfg(), device=torch.device('cpu'))
+    missing = sorted(a for a in used if not hasattr(pred, a))
+    assert not missing, missing
