@@ -26,11 +26,16 @@ def _flat_grads(adapter):
     return torch.cat([g.reshape(-1) for g in adapter.grads().values()])
 
 
-def _worker(rank, world, port, out):
+def _make_full(replay):
+    """plain coherent batch, or a replay-like one (per-sample intrinsics, colour-augmented network inputs)"""
+    return orc.make_replay_batch(B, H, W, seed=7) if replay else orc.make_batch(B, H, W, seed=7, coherent=True)
+
+
+def _worker(rank, world, port, out, replay):
     torch.set_num_threads(2)
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
     params = orc.make_params(0)
-    full = orc.make_batch(B, H, W, seed=7, coherent=True)
+    full = _make_full(replay)
     noise = orc.make_noise(B, H, W, seed=7)
     w_global = global_sample_weights(B, online_loss_weight=0.4, online_index=0)
     lo, hi = shard_range(B, rank, world)
@@ -46,12 +51,13 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharding_matches_single_process(tmp_path):
+@pytest.mark.parametrize('replay', [False, True])
+def test_two_rank_sharding_matches_single_process(tmp_path, replay):
     out = tmp_path / 'dp.pt'
-    mp.spawn(_worker, args=(2, _free_port(), str(out)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(out), replay), nprocs=2, join=True)
     got = torch.load(out)
     params = orc.make_params(0)
-    full = orc.make_batch(B, H, W, seed=7, coherent=True)
+    full = _make_full(replay)
     noise = orc.make_noise(B, H, W, seed=7)
     w_global = global_sample_weights(B, online_loss_weight=0.4, online_index=0)
     adapter = orc.OracleAdapter(params, orc.OracleConfig(H, W, B))
