@@ -45,7 +45,20 @@ REPLAY_CASES = {
     'small_b4_replay': (4, 64, 96, True, None, 6),
     'small_b8_replay': (8, 64, 96, True, None, 7),       # BASELINE configs[2]: 1 current + 7 replay triplets, default weights
 }
+# the configurations BASELINE.json's roofline targets are defined on, at their own size (configs[2] / configs[4]): these
+# batches select the launch plan the bench numbers are taken with (every layer on the TMA kernels).  Maps are stored
+# sub-sampled (strided) to keep the fixtures small; per-map float64 means of the FULL maps are stored next to them
+BIG_REPLAY_CASES = {
+    'full_b8_replay': (8, 192, 640, True, None, 8),         # configs[2]: 1 current + 7 replay triplets at 192x640
+    'hires_b8_replay': (8, 384, 1280, True, None, 9),       # configs[4]: 1 + 7 at 384x1280
+    'hires_b1': (1, 384, 1280, True, None, 10),             # 384x1280 at batch 1 (plain batch: one camera)
+}
+REPLAY_CASES.update({k: v for k, v in BIG_REPLAY_CASES.items() if k.endswith('_replay')})
+CASES.update({k: v for k, v in BIG_REPLAY_CASES.items() if not k.endswith('_replay')})
 ONLINE_LOSS_WEIGHT = {'small_b4_replay': 0.4}
+# stride of the stored ('disp', s) maps / of the stored depth and warped maps
+DISP_SUB = {'full_b8_replay': (4, 2, 1, 1), 'hires_b8_replay': (8, 4, 2, 1), 'hires_b1': (4, 2, 1, 1)}
+MAP_SUB = {'full_b8_replay': 8, 'hires_b8_replay': 16, 'hires_b1': 8}
 
 
 class _Stub(types.ModuleType):
@@ -142,9 +155,17 @@ def run_case(name, spec, out_dir: Path):
         outputs, losses = pred._process_batch(dict(batch), weights)
     pred.optimizer.zero_grad()
     losses['loss'].backward()
+    dsub = DISP_SUB.get(name, (1, 1, 1, 1))
     for s in range(4):
-        rec[f'disp_{s}'] = outputs[('disp', s)].detach().numpy()
-    sub = 1 if h * w <= 64 * 96 else 4
+        rec[f'disp_{s}'] = outputs[('disp', s)].detach()[:, :, ::dsub[s], ::dsub[s]].numpy()
+    if name in DISP_SUB:
+        rec['disp_subsample'] = np.array(dsub)
+        for s in range(4):       # float64 means over the full maps, per sample (the strided samples miss most pixels)
+            rec[f'disp_mean_{s}'] = outputs[('disp', s)].detach().double().mean(dim=(1, 2, 3)).numpy()
+            rec[f'depth_mean_{s}'] = outputs[('depth', s)].detach().double().mean(dim=(1, 2, 3)).numpy()
+            for f in (-1, 1):
+                rec[f'rgb_mean_{f}_{s}'] = outputs[('rgb', f, s)].detach().double().mean(dim=(1, 2, 3)).numpy()
+    sub = MAP_SUB.get(name, 1 if h * w <= 64 * 96 else 4)
     for s in range(4):
         rec[f'depth_{s}_sub'] = outputs[('depth', s)].detach()[:, :, ::sub, ::sub].numpy()
         for f in (-1, 1):
@@ -180,7 +201,9 @@ def run_case(name, spec, out_dir: Path):
     with injected_noise(noise):
         out2, losses2 = pred.adapt(dict(batch), dict(batch), steps=1, online_loss_weight=olw)
     rec['loss2'] = losses2['loss'].detach().reshape(-1).numpy()
-    rec['disp2_0_sub'] = out2[('disp', 0)].detach()[:, :, ::4, ::4].numpy()
+    sub2 = 4 if name not in MAP_SUB else MAP_SUB[name]
+    rec['disp2_0_sub'] = out2[('disp', 0)].detach()[:, :, ::sub2, ::sub2].numpy()
+    rec['disp2_subsample'] = np.array([sub2])
     for f in (-1, 1):
         rec[f'translation2_{f}'] = out2[('translation', 0, f)].detach().numpy()
         rec[f'axis_angle2_{f}'] = out2[('axis_angle', 0, f)].detach().numpy()

@@ -13,6 +13,8 @@ import torch
 
 from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
 from oracle import clslam_oracle as orc
+from tests.golden_util import output_errors
+from tests.test_gpu_zz_replay_case import record_achieved
 
 pytestmark = pytest.mark.gpu
 GOLDEN = Path(__file__).resolve().parent / 'golden'
@@ -50,18 +52,15 @@ def test_process_batch_matches_reference(name):
     outputs, losses = pred._process_batch(inputs)
     torch.cuda.synchronize()
     assert all(v.is_cuda for v in inputs.values())            # caller's dict now holds device tensors (:916-917)
-    sub = int(rec['subsample'][0])
     for s in range(4):
         assert outputs[('disp', s)].shape == (b, 1, h >> s, w >> s)
-        assert rel(outputs[('disp', s)].cpu().numpy(), rec[f'disp_{s}']) < REL_TOL, f'disp {s}'
-        assert rel(outputs[('depth', s)][:, :, ::sub, ::sub].cpu().numpy(), rec[f'depth_{s}_sub']) < REL_TOL
-        for f in (-1, 1):
-            assert rel(outputs[('rgb', f, s)][:, :, ::sub, ::sub].cpu().numpy(), rec[f'rgb_{f}_{s}_sub']) < 5e-4
     for f in (-1, 1):
         assert outputs[('axis_angle', 0, f)].shape == (b, 1, 3)
-        assert rel(outputs[('axis_angle', 0, f)].cpu().numpy(), rec[f'axis_angle_{f}']) < REL_TOL
-        assert rel(outputs[('translation', 0, f)].cpu().numpy(), rec[f'translation_{f}']) < REL_TOL
-        assert rel(outputs[('cam_T_cam', 0, f)].cpu().numpy(), rec[f'cam_T_cam_{f}']) < REL_TOL
+    err = output_errors(rec, outputs)
+    record_achieved(name, err)
+    assert max(err['disp']) < REL_TOL and max(err['depth']) < REL_TOL, err
+    assert max(err['axis_angle'], err['translation'], err['cam_T_cam']) < REL_TOL, err
+    assert max(err['rgb']) < 5e-4, err        # warped images: see DESIGN.md section 2 (coordinate sensitivity of the bilinear sample)
     keys = [k[5:] for k in rec.files if k.startswith('loss:')]
     assert set(keys) == set(losses.keys()) and len(losses) == 19
     assert losses['depth_loss'] is losses['loss'] and losses['loss'].shape == (1,)

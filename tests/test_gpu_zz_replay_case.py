@@ -3,8 +3,9 @@
 per-sample intrinsics (slam/replay_buffer.py:164-177), colour-augmented network inputs (rgb_aug != rgb) and the
 non-uniform per-sample loss weights of adapt(online_loss_weight=...) (depth_pose_prediction.py:297-305).
 
-Added after round 1's GPU budget was spent: the fixture and the oracle side are checked on the CPU
-(tests/test_oracle_golden.py); this file is the GPU side and runs last in the suite."""
+The fixtures and the oracle side are checked on the CPU (tests/test_oracle_golden.py); this file is the GPU side.  It also
+holds the BASELINE configs[2] / configs[4] batches at their own sizes (192x640 and 384x1280, batch 8)."""
+import json
 from pathlib import Path
 
 import numpy as np
@@ -13,18 +14,27 @@ import torch
 
 from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
 from oracle import clslam_oracle as orc        # the checker + the seeded input generators
+from tests.golden_util import GOLDEN, output_errors
 
-# not strict: the fixture was added after the round's last GPU run -- a pass shows up as XPASS, a failure must not hide the
-# results of the files that ran before it (drop the marker once it has passed on hardware)
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason='new fixture, not yet run on hardware')]
-GOLDEN = Path(__file__).resolve().parent / 'golden'
+pytestmark = pytest.mark.gpu
 REL_TOL = 1e-4          # north_star: disparity and pose within 1e-4 relative of the reference
-NAMES = ['small_b4_replay', 'small_b8_replay']      # the second: BASELINE configs[2] (1 current + 7 replay), default weights
+# small_b8_replay: BASELINE configs[2] (1 current + 7 replay) at the small test size; full_b8_replay: the same at 192x640 (the
+# launch plan the configs[2] bench numbers are taken with); hires_b8_replay / hires_b1: configs[4] (384x1280) at batch 8 and 1
+NAMES = ['small_b4_replay', 'small_b8_replay', 'full_b8_replay', 'hires_b8_replay', 'hires_b1']
 
 
-def rel(a, b):
-    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
-    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+WARP_TOL = 1e-3
+
+
+def record_achieved(name, err):
+    """achieved errors, for DESIGN.md section 2 (gpurun_out/ travels back from the GPU box)"""
+    try:
+        out = Path(__file__).resolve().parent.parent / 'gpurun_out'
+        out.mkdir(exist_ok=True)
+        with open(out / 'parity_achieved.jsonl', 'a') as fh:
+            fh.write(json.dumps({'case': name, **{k: (max(v) if isinstance(v, list) else v) for k, v in err.items()}}) + '\n')
+    except OSError:
+        pass
 
 
 def build(name, **kw):
@@ -35,7 +45,8 @@ def build(name, **kw):
     params = orc.make_params(0)
     for n in orc.NET_NAMES:
         pred.models[n].load_state_dict(params[n])
-    batch = orc.make_replay_batch(b, h, w, seed=seed)
+    replay = 'replay_variant' in rec.files
+    batch = orc.make_replay_batch(b, h, w, seed=seed) if replay else orc.make_batch(b, h, w, seed=seed, coherent=True)
     noise = orc.make_noise(b, h, w, seed=seed)
     pred.noise_provider = lambda s, shape: noise[s]
     olw = float(rec['online_loss_weight'][0]) if 'online_loss_weight' in rec.files else None
@@ -48,16 +59,14 @@ def test_replay_batch_outputs_losses_gradients(name):
     pred._set_adapt(True)
     outputs, losses = pred._process_batch(dict(batch), orc.adapt_loss_weights(b, olw))
     torch.cuda.synchronize()
-    sub = int(rec['subsample'][0])
-    for s in range(4):
-        assert rel(outputs[('disp', s)].cpu().numpy(), rec[f'disp_{s}']) < REL_TOL, f'disp {s}'
-        assert rel(outputs[('depth', s)][:, :, ::sub, ::sub].cpu().numpy(), rec[f'depth_{s}_sub']) < REL_TOL
-        for f in (-1, 1):      # per-sample K / inv_K enter here
-            assert rel(outputs[('rgb', f, s)][:, :, ::sub, ::sub].cpu().numpy(), rec[f'rgb_{f}_{s}_sub']) < 1e-3
-    for f in (-1, 1):
-        assert rel(outputs[('axis_angle', 0, f)].cpu().numpy(), rec[f'axis_angle_{f}']) < REL_TOL
-        assert rel(outputs[('translation', 0, f)].cpu().numpy(), rec[f'translation_{f}']) < REL_TOL
-        assert rel(outputs[('cam_T_cam', 0, f)].cpu().numpy(), rec[f'cam_T_cam_{f}']) < REL_TOL
+    err = output_errors(rec, outputs)
+    record_achieved(name, err)
+    assert max(err['disp']) < REL_TOL and max(err['depth']) < REL_TOL, err
+    assert max(err['axis_angle'], err['translation'], err['cam_T_cam']) < REL_TOL, err
+    assert err['means'] < REL_TOL, err
+    # warped images: per-sample K / inv_K enter here; a sampling coordinate off by 1e-4 relative (= 0.06 px at x = 600)
+    # moves a bilinear sample of white-noise-like replay images by up to that fraction of the local contrast
+    assert max(err['rgb']) < WARP_TOL, err
     keys = [k[5:] for k in rec.files if k.startswith('loss:')]
     assert set(keys) == set(losses.keys())
     for k in keys:
