@@ -11,8 +11,15 @@ N times that.  ``value`` is measured with the inputs resident in HBM (CUDA event
 flushed between steps, max over ranks); ``e2e`` goes through the public
 ``DepthPosePrediction.adapt()`` call with pinned HOST inputs and the loss read back every step.
 
-The CPU oracle (oracle/) is used here only as the timed CPU baseline (``cpu_baseline`` leg and
-``--impl reference``), never on the measured GPU path.
+Roofline time base: the per-kernel durations are read INSIDE the replayed step graph (an instrumented
+copy of the step graph with external event-record nodes around every launch, warm, L2 flushed between
+replays) -- where the product runs, not from launches timed alone.  The N=1 line also carries
+``roofline_cfg3`` (BASELINE configs[2]: batch 8 at 192x640) and ``roofline_cfg5`` (configs[4]: batch 8
+at 384x1280), the configurations the north-star roofline targets are defined on.
+
+The CPU oracle (oracle/) is used here only as the timed baseline (``cpu_baseline`` / ``torch_eager_gpu``
+legs and ``--impl reference``) and, for N>1, as the checker behind ``dp_parity`` -- never on the
+measured GPU path.
 """
 from __future__ import annotations
 
@@ -46,26 +53,34 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-op-profile', action='store_true')
+    ap.add_argument('--no-extra-configs', action='store_true', help='skip roofline_cfg3 / roofline_cfg5 (N=1 line)')
+    ap.add_argument('--no-dp-parity', action='store_true', help='skip the oracle check of the sharded step (N>1 line)')
     ap.add_argument('--cpu-steps', type=int, default=8)
-    ap.add_argument('--op-table', default=None, help='write the per-op timing table (JSON) here')
+    ap.add_argument('--op-table', default=None, help='write the per-op in-graph timing table (JSON) here')
     ap.add_argument('--profiler-range', action='store_true',
                     help='cudaProfilerStart/Stop around the timed `value` loop (ncu --profile-from-start off)')
     return ap.parse_args()
 
 
-def workload_config(args, world):
-    b = args.batch_per_gpu
-    return {
-        'workload': f'online adapt step (fwd+loss+bwd+Adam), batch={b} triplet(s) per GPU, '
-                    f'{args.height}x{args.width}, {world}xB200',
-        'batch_per_gpu': b, 'global_batch': b * world, 'height': args.height, 'width': args.width,
+def workload_config(b, h, w, world, impl='ours'):
+    cfg = {
+        'workload': f'online adapt step (fwd+loss+bwd+Adam), batch={b} triplet(s) per GPU, {h}x{w}, '
+                    + (f'{world}xB200' if impl == 'ours' else 'host CPU cores'),
+        'batch_per_gpu': b, 'global_batch': b * world, 'height': h, 'width': w,
         'parallelism': f'dp{world}' if world > 1 else 'single',
-        'encoders': 'frozen (adapt)', 'outputs': 'API-complete (depth + warped images emitted)',
-        'tie_break_noise': 'torch.randn per scale (reference RNG semantics)',
-        'conv_arithmetic': 'tcgen05 bf16 hi/lo split (3 products per fp32 product), fp32 accumulation in TMEM',
-        'l2': 'flushed between timed steps (256 MiB memset, outside the per-step events)',
-        **({'small_maps': 'split-K TMA kernel (CLSLAM_TMA_SPLITK=1, experimental)'} if os.environ.get('CLSLAM_TMA_SPLITK') == '1' else {}),
+        'encoders': 'frozen (adapt)',
     }
+    if impl == 'ours':
+        cfg.update({
+            'outputs': 'API-complete (depth + warped images emitted)',
+            'tie_break_noise': 'torch.randn per scale (reference RNG semantics)',
+            'conv_arithmetic': 'tcgen05 bf16 hi/lo split (3 products per fp32 product), fp32 accumulation in TMEM',
+            'l2': 'flushed between timed steps (256 MiB memset, outside the per-step events)',
+        })
+    else:
+        cfg.update({'arithmetic': 'torch CPU fp32 (MKL-DNN), autograd backward, torch.optim.Adam',
+                    'note': 'same workload as the GPU arm; each step is one full adapt iteration of the global batch'})
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------------
@@ -88,7 +103,7 @@ def run_reference(args):
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': world, 'steps': steps, 'warmup': warm,
         'ms_per_step': res['median_s'] * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
+        'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.batch_per_gpu, args.height, args.width, world, 'reference'),
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': int(res['threads']), 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -139,21 +154,46 @@ class ClockSampler:
         return out
 
 
-def conv_flops(d) -> float:
-    return 2.0 * d.n * d.ho * d.wo * d.co * d.ci * d.kh * d.kw
-
-
-def op_model(eng, name):
-    """(bound, algorithmic amount, unit) for a plan op; DESIGN.md section 'kernels' states the formulas."""
+# ------------------------------------------------------------------------------------------------
+# Algorithmic work per plan op (DESIGN.md section 4 states the formulas).  Convolutions: FLOPs = 2 * MACs of the layer as the
+# reference executes it.  Memory-bound kernels: compulsory bytes = the distinct tensors the launch must read + write.
+def op_model(eng, name, a):
+    """(bound, algorithmic amount) for a plan op, or None"""
     b, h, w = eng.b, eng.h, eng.w
     n_px = h * w
-    if name == 'photo_fwd':          # sum_s (72 + 4/4^s) * N bytes per triplet (SURVEY.md 8d, API-complete + noise tensor)
-        return 'hbm', b * sum(72 + 4 / 4 ** s for s in range(4)) * n_px, 'B'
-    if name == 'photo_bwd':          # read disp_s, target, 2 sources, 1-byte argmin; write d(disp_full)
-        return 'hbm', b * sum(41 + 4 / 4 ** s for s in range(4)) * n_px, 'B'
+    if name == 'photo_fwd':
+        # ONE launch covers the four scales and reads target / sources once: disp pyramid 5.31 N + target 12 N + 2 sources 24 N +
+        # tie-break noise 4 x 8 N in; depth 4 x 4 N + warped 4 x 24 N out = 185.3 N bytes per triplet (API-complete, parity noise)
+        return 'hbm', b * (sum(4 / 4 ** s for s in range(4)) + 12 + 24 + 32 + 16 + 96) * n_px
+    if name == 'photo_bwd':
+        # one launch: disp pyramid 5.31 N + target 12 N + sources 24 N + 1-byte argmin x 4 in; d(disp_full) 4 x 4 N out = 61.3 N
+        return 'hbm', b * (sum(4 / 4 ** s for s in range(4)) + 12 + 24 + 4 + 16) * n_px
     if name == 'photo_identity':     # target + 2 sources in, 2 maps out
-        return 'hbm', b * (36 + 8) * n_px, 'B'
+        return 'hbm', b * (36 + 8) * n_px
+    if name == 'pack_rgba':          # 2 sources in (12 N each), packed RGBA out (16 N each)
+        return 'hbm', b * 2 * (12 + 16) * n_px
+    if name.startswith('dispconv_') and name.endswith('.wgrad'):     # x (C ch) + dz in
+        n, hh, ww, c = a[-4:]
+        return 'hbm', 4.0 * n * hh * ww * (c + 1)
+    if name == 'dispconv_0.dgrad':                                   # dz + y_prev in, dz_prev out
+        n, hh, ww, c = a[-4:]
+        return 'hbm', 4.0 * n * hh * ww * (1 + 2 * c)
+    if name.startswith('dispconv_'):                                  # forward: x in, disp out
+        n, hh, ww, c = a[-4:]
+        return 'hbm', 4.0 * n * hh * ww * (c + 1)
+    if name.startswith('disp_grad_'):                                 # d(disp_full) in, disp in, dz out
+        s = int(name.rsplit('_', 1)[1])
+        return 'hbm', 4.0 * b * (n_px + 2 * n_px / 4 ** s)
+    if name.endswith('.fold'):                                        # (H+2)(W+2) c partial grid + y_prev in, dz fp32 + planes out
+        _, n, hh, ww, c, up = a[:6]
+        return 'hbm', 4.0 * n * c * ((hh + 2) * (ww + 2) + 3 * (hh // up) * (ww // up))
+    if name.endswith('.planes') or name.endswith('.s2d'):             # fp32 in, bf16 hi/lo planes out (same bytes)
+        return None
     return None
+
+
+def conv_flops(d) -> float:
+    return 2.0 * d.n * d.ho * d.wo * d.co * d.ci * d.kh * d.kw
 
 
 def kernel_of(name, a):
@@ -164,70 +204,268 @@ def kernel_of(name, a):
         return 'wgrad3x3_tma_kernel'
     if a and hasattr(a[0], 'kh'):
         return 'gemm_tc_kernel (gather)'
-    for key in ('photo_fwd', 'photo_bwd', 'photo_identity', 'dgrad.fold', 'dispconv', 'disp_grad', 'loss_finalize', 'pose_head',
-                'maxpool', 'stage', 'planes', 'split_weights', 'wt_flip', 'pack_rgba'):
+    for key in ('photo_fwd', 'photo_bwd', 'photo_identity', 'pack_rgba', 'loss_finalize', 'pose_head', 'maxpool', 'stage', 'split_weights',
+                'wt_flip', 'disp_grad'):
         if key in name:
             return key + '_kernel'
+    if name.endswith('.fold'):
+        return 'dgrad_fold_kernel'
+    if name.endswith('.planes') or name.endswith('.s2d'):
+        return 'planes_from_f32_kernel'
+    if name.startswith('dispconv_'):
+        return 'dispconv_wgrad_kernel' if name.endswith('.wgrad') else ('dispconv_dgrad_act_kernel' if name.endswith('.dgrad')
+                                                                         else 'dispconv_fwd_kernel')
     return name
 
 
-def profile_ops(eng, pred, reps=5):
-    """per-op CUDA-event timing of one eager step (for the roofline block)"""
-    import torch
-    plan = eng.plan
-    stream = torch.cuda.current_stream().cuda_stream
-    flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=eng.device)
-    times = [0.0] * len(plan.ops)
-    for _ in range(reps):
-        for i, (name, fn, a, lane) in enumerate(plan.ops[:eng.n_bwd_ops]):
-            if fn is None:          # lane fork/join markers: the profile pass runs every op serially on one stream
-                continue
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            rc = fn(stream, plan._ws_ptr[0], *a)
-            e1.record()
-            assert rc == 0, name
-            e1.synchronize()
-            times[i] += e0.elapsed_time(e1) / reps
+def describe_ops(eng):
+    """static description of every real plan op: index, name, lane, kernel family, roofline model"""
     rows = []
-    descs = {}
-    for (i, j), v in eng.dec_desc.items():
-        descs[f'upconv_{i}_{j}'] = v[0]
-    for k, v in eng.pose_desc.items():
-        descs[k] = v[0]
-    for i, (name, fn, a, lane) in enumerate(plan.ops[:eng.n_bwd_ops]):
-        if fn is None:
+    for i, (name, fn, a, lane) in enumerate(eng.plan.ops[:eng.n_bwd_ops]):
+        if fn is None or (eng.n_fwd_core <= i < eng.n_fwd_ops):          # markers; the forward-only join is not part of the step
             continue
-        row = {'op': name, 'ms': times[i], 'lane': lane, 'kernel': kernel_of(name, a)}
-        model = op_model(eng, name)
-        d = None
-        if model is None and a and hasattr(a[0], 'kh'):
-            d = a[0]
-        if model is None and len(a) >= 2 and hasattr(a[0], 'c_total') and hasattr(a[1], 'c_total'):    # clslam_wgrad3x3_tma(x planes, dz planes)
-            row.update(bound='tensor', amount=2.0 * a[0].n * a[0].h * a[0].w * a[0].c * a[1].c * 9, unit='FLOP')
-        if model is None and a and hasattr(a[0], 'inp'):          # clslam_conv_tma: 3x3 over planes
+        row = {'i': i, 'op': name, 'lane': lane, 'kernel': kernel_of(name, a)}
+        model = op_model(eng, name, a)
+        if model is not None:
+            row.update(bound=model[0], amount=model[1])
+        elif len(a) >= 2 and hasattr(a[0], 'c_total') and hasattr(a[1], 'c_total'):    # clslam_wgrad3x3_tma(x planes, dz planes)
+            row.update(bound='tensor', amount=2.0 * a[0].n * a[0].h * a[0].w * a[0].c * a[1].c * 9)
+        elif a and hasattr(a[0], 'inp'):          # clslam_conv_tma over planes (3x3, or the space-to-depth forms)
             t = a[0]
             full = 2 if t.pad_mode == 2 else 0
-            k_alg = t.inp.c * 9 if t.taps not in (2, 4) else 49 * (3 if t.inp.c == 16 else 6)       # conv1 (space-to-depth form): 7 x 7 x C
-            if t.taps == 2:
-                k_alg = 9 * t.inp.c // 4                                                        # 3x3 / stride 2 in space-to-depth form
-            row.update(bound='tensor', amount=2.0 * t.inp.n * (t.inp.h + full) * (t.inp.w + full) * t.cout * k_alg, unit='FLOP')
-        if model is not None:
-            row.update(bound=model[0], amount=model[1], unit='B')
-        elif d is not None:
+            taps = t.taps or 3
+            if taps == 4:
+                k_alg = 49 * (3 if t.inp.c == 16 else 6)          # conv1 (space-to-depth form): 7 x 7 x C
+            elif taps == 2:
+                k_alg = 9 * t.inp.c // 4                          # 3x3 / stride 2 in space-to-depth form
+            elif taps == 1:
+                k_alg = t.inp.c                                   # 1x1
+            else:
+                k_alg = t.inp.c * 9
+            row.update(bound='tensor', amount=2.0 * t.inp.n * (t.inp.h + full) * (t.inp.w + full) * t.cout * k_alg)
+        elif a and hasattr(a[0], 'kh'):
+            d = a[0]
             fl = conv_flops(d)
             if name.endswith('.dgrad') and d.in_mode == 1:      # only the c1 up-sampled channels at (h1, w1)
                 fl = 2.0 * d.n * d.h1 * d.w1 * d.c1 * d.co * 9
-            row.update(bound='tensor', amount=fl, unit='FLOP')
+            row.update(bound='tensor', amount=fl)
         rows.append(row)
     return rows
+
+
+def profile_in_graph(pred, eng, reps, flush):
+    """Per-op durations INSIDE the replayed step graph: an instrumented copy of the step graph (the same launches on the same
+    lanes, plus an external event-record node before and after each) is replayed `reps` times, warm, L2 flushed between
+    replays.  Returns (rows with 'ms', step time of the instrumented graph in ms, Adam ms)."""
+    import ctypes
+
+    import torch
+    lib = eng.lib
+    plan = eng.plan
+    plan.make_timers()
+    lr = pred._adam_lr()
+    t_adam = (lib.clslam_event_create(), lib.clslam_event_create())
+    stream = torch.cuda.current_stream()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        eng.forward_backward(timed=True)
+        cur = torch.cuda.current_stream().cuda_stream
+        lib.clslam_event_record(t_adam[0], cur)
+        eng.adam(lr)
+        lib.clslam_event_record(t_adam[1], cur)
+    rows = describe_ops(eng)
+    acc = [0.0] * len(plan.ops)
+    adam_ms, step_ms = 0.0, 0.0
+    ms = ctypes.c_float(0.0)
+    for _ in range(reps):
+        flush.zero_()
+        pred._draw_noise(eng)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        g.replay()
+        e1.record(stream)
+        e1.synchronize()
+        step_ms += e0.elapsed_time(e1) / reps
+        t = plan.read_timers(0, eng.n_bwd_ops)
+        for r in rows:
+            acc[r['i']] += t[r['i']] / reps
+        lib.clslam_event_elapsed_ms(t_adam[0], t_adam[1], ctypes.byref(ms))
+        adam_ms += float(ms.value) / reps
+    for r in rows:
+        r['ms'] = acc[r['i']]
+    n_adam = eng.flat.numel
+    rows.append({'i': -1, 'op': 'adam', 'lane': 0, 'kernel': 'adam_kernel', 'bound': 'hbm', 'amount': 28.0 * n_adam, 'ms': adam_ms})
+    del g
+    return rows, step_ms
+
+
+def summarize_profile(rows, step_ms, hbm_peak, tensor_peak, traffic_db, tag):
+    """kernel families (in-graph time, share of the step, achieved vs roofline) from the per-op rows"""
+    fams = {}
+    for r in rows:
+        f = fams.setdefault(r['kernel'], {'kernel': r['kernel'], 'ms': 0.0, 'launches': 0, 'amount': 0.0, 'bound': None, 'modelled_ms': 0.0})
+        f['ms'] += r['ms']; f['launches'] += 1
+        if 'amount' in r:
+            f['amount'] += r['amount']; f['bound'] = r['bound']; f['modelled_ms'] += r['ms']
+    lanes = {}
+    for r in rows:
+        lanes[r['lane']] = lanes.get(r['lane'], 0.0) + r['ms']
+    total = sum(f['ms'] for f in fams.values())
+    out = []
+    for f in sorted(fams.values(), key=lambda f: -f['ms']):
+        f['share_of_kernel_time'] = f['ms'] / total if total > 0 else 0.0
+        if f['bound'] is not None and f['modelled_ms'] > 0:
+            if f['bound'] == 'hbm':
+                f['achieved'] = f['amount'] / (f['modelled_ms'] * 1e-3) / 1e9; f['peak'] = hbm_peak; f['unit'] = 'GB/s'
+            else:
+                f['achieved'] = f['amount'] / (f['modelled_ms'] * 1e-3) / 1e12; f['peak'] = tensor_peak; f['unit'] = 'TFLOP/s'
+            f['frac'] = f['achieved'] / f['peak']
+            f['avg_launch_ms'] = f['ms'] / f['launches']
+            f['traffic'] = traffic_db.get(f"{f['kernel']}@{tag}")
+        out.append({k: (round(v, 6) if isinstance(v, float) else v) for k, v in f.items() if k not in ('amount', 'modelled_ms')})
+    return out, {str(k): round(v, 6) for k, v in sorted(lanes.items())}, total
+
+
+def roofline_block(fams, lanes, kernel_ms_total, step_ms_instr, step_ms_clean, peak_src):
+    """the `roofline` object of the JSON line: the family with the largest in-graph time that has a roofline model"""
+    top = next((f for f in fams if 'frac' in f), None)
+    if top is None:
+        return None
+    note = ('achieved = algorithmic FLOPs of all launches of this kernel in one step / their summed in-graph duration; the kernel executes 3x '
+            'these FLOPs on tcgen05 (bf16 hi/lo split products A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation in TMEM); peak = measured '
+            'dense bf16') if top['bound'] == 'tensor' else 'fused memory-bound kernel; achieved = algorithmic (compulsory) bytes / in-graph duration'
+    return {
+        'kernel': top['kernel'], 'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'], 'unit': top['unit'],
+        'frac': top['frac'], 'traffic': top.get('traffic'), 'share_of_kernel_time': top['share_of_kernel_time'],
+        'launches_per_step': top['launches'], 'avg_launch_ms': top['avg_launch_ms'], 'peak_source': peak_src,
+        'time_base': 'per-launch durations read inside the replayed step graph (external event-record nodes around every launch; warm, '
+                     'L2 flushed between replays)',
+        'lane_kernel_ms': lanes, 'kernel_ms_all_lanes': round(kernel_ms_total, 6),
+        'step_ms_instrumented_graph': round(step_ms_instr, 6), 'step_ms_clean_graph': round(step_ms_clean, 6),
+        'note': note,
+        'traffic_note': 'dram read+write bytes per launch (sum over the launches of this kernel in one step / launches), ncu --set full '
+                        '(profiles/r02_traffic.json); null when not captured for this configuration'}
+
+
+# ------------------------------------------------------------------------------------------------
+def load_peaks():
+    peaks = {}
+    pk = ROOT / 'MEASURED_PEAKS.json'
+    if pk.exists():
+        peaks = json.loads(pk.read_text())
+    hbm = float(peaks.get('hbm_gbs', 6650.0))
+    tensor = float(peaks.get('bf16_tflops', 1590.0))
+    src = 'measured (MEASURED_PEAKS.json: hbm_gbs, bf16_tflops burst)' if peaks else 'fallback (B200_PROFILING.md)'
+    return hbm, tensor, src
+
+
+def load_traffic():
+    tp = ROOT / 'profiles' / 'r02_traffic.json'
+    return json.loads(tp.read_text()) if tp.exists() else {}
+
+
+def build_predictor(b_global, h, w, world, use_graph):
+    from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
+    from clslam_b200 import synthetic              # seeded workload (images, intrinsics, weights): data generation only
+    pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b_global), data_parallel=world > 1,
+                               use_cuda_graph=use_graph)
+    params = synthetic.make_params(0)
+    for n in synthetic.NET_NAMES:
+        pred.models[n].load_state_dict(params[n])
+    return pred
+
+
+def measure_single(b, h, w, steps, warmup, flush, hbm_peak, tensor_peak, traffic_db, op_profile=True):
+    """one single-GPU configuration: device-resident step time + in-graph kernel table (the extra-config legs of the N=1 line)"""
+    import torch
+    from clslam_b200 import synthetic
+    pred = build_predictor(b, h, w, 1, True)
+    host = {k: v.contiguous().pin_memory() for k, v in synthetic.make_batch(b, h, w, seed=1, coherent=True).items()}
+    for _ in range(max(3, warmup)):
+        pred.adapt(dict(host), dict(host), steps=1)
+    eng = pred._engines[b]
+    staged = dict(host)
+    pred._stage_inputs(staged)
+    pred._set_weights(eng, None)
+    for _ in range(2):          # the resident-input form of the step (one graph) is captured here, outside the timed loop
+        pred._draw_noise(eng); pred._step(eng)
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pred._draw_noise(eng)
+        pred._step(eng)
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(c) for a, c in evs) / steps
+    # end to end through adapt() with pinned host inputs
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    n_e2e = max(3, steps // 2)
+    for _ in range(n_e2e):
+        _, losses = pred.adapt(dict(host), dict(host), steps=1)
+        _ = float(losses['loss'])
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / n_e2e
+    out = {'workload': f'adapt step, batch={b}, {h}x{w}, 1xB200', 'ms_per_step': ms, 'value': b / (ms * 1e-3), 'unit': UNIT,
+           'steps': steps, 'e2e_value': b / (e2e_ms * 1e-3), 'loss': float(losses['loss'])}
+    if op_profile:
+        rows, step_instr = profile_in_graph(pred, eng, 5, flush)
+        fams, lanes, total = summarize_profile(rows, step_instr, hbm_peak, tensor_peak, traffic_db, f'b{b}@{h}x{w}')
+        out['kernel_families'] = fams[:8]
+        out['lane_kernel_ms'] = lanes
+        out['step_ms_instrumented_graph'] = round(step_instr, 6)
+        for f in fams:          # the two north-star targets, by name
+            if f['kernel'] == 'conv3x3_tma_kernel':
+                out['conv_tensor'] = {k: f[k] for k in ('achieved', 'peak', 'unit', 'frac', 'traffic', 'launches', 'ms') if k in f}
+            if f['kernel'] == 'photo_fwd_kernel':
+                out['warp_ssim_hbm'] = {k: f[k] for k in ('achieved', 'peak', 'unit', 'frac', 'traffic', 'launches', 'ms') if k in f}
+            if f['kernel'] == 'photo_bwd_kernel':
+                out['warp_ssim_bwd_hbm'] = {k: f[k] for k in ('achieved', 'peak', 'unit', 'frac', 'traffic', 'launches', 'ms') if k in f}
+    del pred
+    torch.cuda.empty_cache()
+    return out
+
+
+def dp_parity_check(pred, full, rank, world, b, h, w):
+    """N>1: one un-timed sharded forward + backward with seeded tie-break noise against the CPU oracle evaluated ONCE on the global
+    batch by rank 0 (the checker).  Returns {loss_rel_err, worst_grad_rel_l2} on rank 0."""
+    import torch
+    from clslam_b200 import synthetic
+    b_global = b * world
+    noise = synthetic.make_noise(b_global, h, w, seed=1)
+    pred.noise_provider = lambda s, shape: noise[s]
+    local = {k: v[rank * b:(rank + 1) * b].contiguous() for k, v in full.items()}
+    pred._set_adapt(True)
+    _, losses = pred._process_batch(dict(local))
+    pred.backward()
+    torch.cuda.synchronize()
+    pred.noise_provider = None
+    out = None
+    if rank == 0:
+        from oracle import clslam_oracle as orc          # the checker
+        adapter = orc.OracleAdapter(synthetic.make_params(0), orc.OracleConfig(h, w, b_global))
+        _, ref_losses = adapter.step(full, noise, update=False)
+        ref_grads = adapter.grads()
+        worst = 0.0
+        for key, g in pred.gradients().items():
+            ref = ref_grads[key].double()
+            worst = max(worst, float((g.detach().cpu().double() - ref).norm() / (ref.norm() + 1e-30)))
+        lr = float(ref_losses['loss'])
+        out = {'loss_rel_err': abs(float(losses['loss']) - lr) / abs(lr), 'worst_grad_rel_l2': worst,
+               'checker': f'CPU oracle on the global batch of {b_global} (rank 0, outside the timed regions), seeded tie-break noise'}
+    return out
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from clslam_b200 import Config, DatasetConfig, DepthPosePrediction, _lib
+    from clslam_b200 import _lib
     from clslam_b200 import synthetic              # seeded workload (images, intrinsics, weights): data generation only
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -243,11 +481,7 @@ def run_ours(args):
     b, h, w = args.batch_per_gpu, args.height, args.width
     b_global = b * world
 
-    pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b_global),
-                               data_parallel=world > 1, use_cuda_graph=not args.no_graph)
-    params = synthetic.make_params(0)
-    for n in synthetic.NET_NAMES:
-        pred.models[n].load_state_dict(params[n])
+    pred = build_predictor(b_global, h, w, world, not args.no_graph)
     full = synthetic.make_batch(b_global, h, w, seed=1, coherent=True)
     host = {k: v[rank * b:(rank + 1) * b].contiguous().pin_memory() for k, v in full.items()}
     h2d_bytes = sum(v.numel() * v.element_size() for v in host.values())
@@ -257,6 +491,10 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    dp_parity = None
+    if world > 1 and not args.no_dp_parity:
+        dp_parity = dp_parity_check(pred, full, rank, world, b, h, w)      # gradients only: the weights are untouched
 
     # ---- warm-up (first step eager, then graph capture + replays) --------------------------------
     n_before = lib.clslam_launch_count()
@@ -273,11 +511,12 @@ def run_ours(args):
     staged = dict(host)
     pred._stage_inputs(staged)
     pred._set_weights(eng, None)
+    for _ in range(2):          # the resident-input form of the step (one graph) is captured here, outside the timed loop
+        pred._draw_noise(eng); pred._step(eng)
     evs = []
     barrier()
     if args.profiler_range:
         torch.cuda.profiler.start()
-    t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -289,7 +528,6 @@ def run_ours(args):
     barrier()
     if args.profiler_range:
         torch.cuda.profiler.stop()
-    wall_value = time.perf_counter() - t_wall0
     dev_ms = sum(a.elapsed_time(c) for a, c in evs)
     _, losses = pred._collect(eng)                      # NaN check of the whole timed run
     # ---- e2e: public API, pinned host inputs, loss read back every step ---------------------------
@@ -318,6 +556,15 @@ def run_ours(args):
         except Exception as exc:          # never lose the bench line over the extra number
             print(f'adapt(steps=5) timing failed: {exc}', file=sys.stderr)
 
+    replicas_identical = None
+    if world > 1:
+        # after all those steps every replica must hold bit-identical weights (replicated Adam on all-reduced gradients)
+        ref = pred._flat.params.clone()
+        dist.broadcast(ref, 0)
+        same = torch.tensor([1 if torch.equal(ref, pred._flat.params) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        replicas_identical = bool(int(same.item()))
+
     t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -329,7 +576,7 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(3, args.warmup),
             'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args, world),
+            'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(b, h, w, world),
             'clocks': clocks,
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d_bytes), 'd2h_bytes_per_step': 4 * _lib.N_LOSS_SLOTS,
                     'ms_per_step': e2e_ms / args.steps},
@@ -340,72 +587,52 @@ def run_ours(args):
         }
         if frame5_ms is not None:
             line['adapt_steps5_ms_per_frame'] = frame5_ms
-        peaks = {}
-        pk = ROOT / 'MEASURED_PEAKS.json'
-        if pk.exists():
-            peaks = json.loads(pk.read_text())
-        hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
-        tensor_peak = float(peaks.get('bf16_tflops', 1590.0))
-        peak_src = 'measured (MEASURED_PEAKS.json)' if peaks else 'fallback (B200_PROFILING.md)'
-        if world == 1 and not args.no_op_profile:
-            rows = profile_ops(eng, pred)
-            for r in rows:
-                if 'amount' in r and r['ms'] > 0:
-                    if r['bound'] == 'hbm':
-                        r['achieved'] = r['amount'] / (r['ms'] * 1e-3) / 1e9; r['peak'] = hbm_peak; r['runit'] = 'GB/s'
-                    else:
-                        r['achieved'] = r['amount'] / (r['ms'] * 1e-3) / 1e12; r['peak'] = tensor_peak; r['runit'] = 'TFLOP/s'
-                    r['frac'] = r['achieved'] / r['peak']
+        if dp_parity is not None:
+            dp_parity['replicas_identical'] = replicas_identical
+            line['dp_parity'] = dp_parity
+        elif replicas_identical is not None:
+            line['dp_parity'] = {'replicas_identical': replicas_identical}
+        hbm_peak, tensor_peak, peak_src = load_peaks()
+        traffic_db = load_traffic()
+        if world == 1 and not args.no_op_profile and not args.no_graph:
+            rows, step_instr = profile_in_graph(pred, eng, 10, flush)
+            fams, lanes, total = summarize_profile(rows, step_instr, hbm_peak, tensor_peak, traffic_db, f'b{b}@{h}x{w}')
+            rb = roofline_block(fams, lanes, total, step_instr, dev_ms / args.steps, peak_src)
+            if rb is not None:
+                line['roofline'] = rb
+            line['kernel_families'] = fams[:12]
             rows.sort(key=lambda r: -r['ms'])
-            total_ms = sum(r['ms'] for r in rows)
-            # the roofline block is quoted for the dominant KERNEL: ops are grouped by the kernel that runs them
-            fams = {}
-            for r in rows:
-                f = fams.setdefault(r['kernel'], {'kernel': r['kernel'], 'ms': 0.0, 'launches': 0, 'amount': 0.0, 'bound': None})
-                f['ms'] += r['ms']; f['launches'] += 1
-                if 'amount' in r:
-                    f['amount'] += r['amount']; f['bound'] = r['bound']
-            fam_rows = sorted(fams.values(), key=lambda f: -f['ms'])
-            traffic_db = {}
-            tp = ROOT / 'profiles' / 'r01_traffic.json'
-            if tp.exists():
-                traffic_db = json.loads(tp.read_text())
-            for f in fam_rows:
-                f['share_of_step'] = f['ms'] / total_ms
-                if f['bound'] is not None and f['ms'] > 0:
-                    if f['bound'] == 'hbm':
-                        f['achieved'] = f['amount'] / (f['ms'] * 1e-3) / 1e9; f['peak'] = hbm_peak; f['unit'] = 'GB/s'
-                    else:
-                        f['achieved'] = f['amount'] / (f['ms'] * 1e-3) / 1e12; f['peak'] = tensor_peak; f['unit'] = 'TFLOP/s'
-                    f['frac'] = f['achieved'] / f['peak']
-            top = next((f for f in fam_rows if 'frac' in f), None)
-            if top is not None:
-                tr = traffic_db.get(f"{top['kernel']}@b{b}")
-                line['roofline'] = {
-                    'kernel': top['kernel'], 'bound': top['bound'], 'achieved': top['achieved'], 'peak': top['peak'], 'unit': top['unit'],
-                    'frac': top['frac'], 'traffic': tr, 'share_of_step': top['share_of_step'], 'launches_per_step': top['launches'],
-                    'avg_launch_ms': top['ms'] / top['launches'], 'peak_source': peak_src,
-                    'note': ('achieved = algorithmic FLOPs of all launches of this kernel in one step / their summed CUDA-event time '
-                             '(each launch timed alone after an L2 flush); the kernel executes 3x these FLOPs on tcgen05 '
-                             '(bf16 hi/lo split products A_lo.B_hi + A_hi.B_lo + A_hi.B_hi, fp32 accumulation in TMEM); '
-                             'peak = measured dense bf16') if top['bound'] == 'tensor' else
-                            'fused memory-bound kernel; achieved = algorithmic bytes / CUDA-event time',
-                    'traffic_note': 'dram read+write bytes per launch, ncu --set full (profiles/), null when not captured for this batch'}
-            line['kernel_families'] = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in f.items() if k != 'amount'}
-                                       for f in fam_rows[:10]]
-            line['kernels'] = [{k: (round(v, 6) if isinstance(v, float) else v) for k, v in r.items() if k in
-                                ('op', 'kernel', 'ms', 'bound', 'achieved', 'frac', 'runit')} for r in rows[:12]]
-            line['op_profile_total_ms'] = total_ms
+            line['kernels'] = [{'op': r['op'], 'kernel': r['kernel'], 'lane': r['lane'], 'ms': round(r['ms'], 6)} for r in rows[:12]]
             if args.op_table:
-                Path(args.op_table).write_text(json.dumps(rows, indent=1))
+                Path(args.op_table).write_text(json.dumps([{k: v for k, v in r.items()} for r in rows], indent=1))
+        if world == 1 and not args.no_extra_configs and not args.no_graph and (b, h, w) == (1, 192, 640):
+            # the configurations the north-star roofline targets are defined on (not the bench line's own workload)
+            del pred, eng
+            torch.cuda.empty_cache()
+            for key, (bb, hh, ww) in (('roofline_cfg3', (8, 192, 640)), ('roofline_cfg5', (8, 384, 1280))):
+                try:
+                    line[key] = measure_single(bb, hh, ww, max(5, args.steps // 3), 3, flush, hbm_peak, tensor_peak, traffic_db)
+                except Exception as exc:          # never lose the bench line over the extra keys
+                    line[key] = {'error': str(exc)}
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import clslam_oracle as orc        # the timed CPU baseline: the only use of the oracle in this arm
+            from oracle import clslam_oracle as orc        # the timed baselines: the only use of the oracle in this arm
             cores = os.cpu_count() or 1
             res = orc.time_adapt_steps(b_global, h, w, steps=args.cpu_steps, warmup=1, threads=cores)
             line['cpu_baseline'] = {
                 'value': b_global / res['median_s'], 'unit': UNIT, 'cores': int(res['threads']), 'kind': 'port',
                 'sample': f'{args.cpu_steps} timed + 1 warm-up adapt steps of the same B={b_global} {h}x{w} workload '
                           f'(oracle port of the reference, torch CPU fp32), median {res["median_s"]:.3f} s/step'}
+            # "the existing Blackwell path to beat" (SURVEY 2.1 / 8(d)): the same stock-PyTorch graph on this GPU (cuDNN / ATen eager)
+            try:
+                eager = {}
+                for tag, tf32 in (('fp32', False), ('tf32', True)):
+                    r = orc.time_adapt_steps(b_global, h, w, steps=10, warmup=3, device='cuda', allow_tf32=tf32)
+                    eager[tag] = b_global / r['median_s']
+                eager.update(unit=UNIT, sample='10 timed + 3 warm-up adapt steps, oracle port on cuda:0 (stock PyTorch eager, cuDNN / ATen), '
+                                               'median; fp32 = allow_tf32 False (the parity-grade setting), tf32 = torch default')
+                line['torch_eager_gpu'] = eager
+            except Exception as exc:
+                line['torch_eager_gpu'] = {'error': str(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -65,6 +65,11 @@ SIGNATURES = {
     'clslam_abi_version': (c_int, []),
     'clslam_launch_count': (c_longlong, []),
     'clslam_set_device': (c_int, [c_int]),
+    'clslam_event_create': (c_void_p, []),
+    'clslam_event_destroy': (c_int, [c_void_p]),
+    'clslam_event_record': (c_int, [c_void_p, c_void_p]),
+    'clslam_event_elapsed_ms': (c_int, [c_void_p, c_void_p, POINTER(c_float)]),
+    'clslam_disp_to_depth': (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_float, c_float, c_void_p]),
     'clslam_stage_images': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'clslam_set_conv_mode': (c_int, [c_int]),
     'clslam_get_conv_mode': (c_int, []),

@@ -338,6 +338,14 @@ disp_grad_kernel(const float* __restrict__ ddisp_full, const float* __restrict__
   }
 }
 
+__global__ void __launch_bounds__(256)
+disp_to_depth_kernel(const float* __restrict__ disp, float* __restrict__ depth, long long n, int mode, float min_depth, float max_depth) {
+  pdl_wait();
+  pdl_trigger();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    depth[i] = depth_from_disp(ld1(disp + i), mode, min_depth, max_depth);
+}
+
 }  // namespace clslam
 
 using namespace clslam;
@@ -371,10 +379,10 @@ static int check_photo(const clslam_photo_args* a, const char* what) {
   return 0;
 }
 
-// experimental kernel variants, off unless the environment asks for them (read once)
+// kernel variants (A/B-tested on hardware in round 2, both on by default; NAME=0 in the environment selects the round-1 kernels)
 static bool env_flag(const char* name) {
   const char* e = getenv(name);
-  return e && e[0] == '1';
+  return !e || e[0] != '0';
 }
 static bool photo_occ3() { static const bool v = env_flag("CLSLAM_PHOTO_OCC3"); return v; }
 static bool photo_bwd_reuse() { static const bool v = env_flag("CLSLAM_PHOTO_BWD_REUSE"); return v; }
@@ -398,6 +406,14 @@ int clslam_photo_bwd(const clslam_photo_args* a, void* stream) {
                     : (photo_occ3() ? photo_bwd_occ3_kernel : photo_bwd_kernel);
   launch_k(kern, dim3(grid), dim3(kPhotoThreads), 0, as_stream(stream), *a, tiles_x, tiles);
   return finish_launch("photo_bwd");
+}
+
+int clslam_disp_to_depth(const float* disp, float* depth, long long n, int depth_mode, float min_depth, float max_depth, void* stream) {
+  if (!disp || !depth || n < 1) { set_error("disp_to_depth: bad arguments"); return -1; }
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  launch_k(disp_to_depth_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), disp, depth, n, depth_mode, min_depth, max_depth);
+  return finish_launch("disp_to_depth");
 }
 
 int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* smooth_grad, int b_global, int has_sample0,

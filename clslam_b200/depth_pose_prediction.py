@@ -20,7 +20,7 @@ import torch
 from torch import Tensor, nn, optim
 
 from . import _lib as L
-from .engine import H2D_OVERLAP, AdaptEngine, EncoderRunner, Plan, PreparedEncoder, _p
+from .engine import H2D_OVERLAP, AdaptEngine, DepthRunner, EncoderRunner, Plan, PreparedEncoder, _p
 from .networks import DepthDecoder, FlatParams, PoseDecoder, ResnetEncoder
 from .sharding import global_sample_weights, shard_range
 
@@ -83,9 +83,49 @@ LATE_INPUT_KEYS = frozenset([('rgb', 0, 0), ('rgb', -1, 0), ('rgb', 1, 0), ('rgb
                              ('relative_distance', 0), ('relative_distance', 1)])
 
 
+class _NetSet:
+    """One copy of the four networks with everything derived from it: the flat trainable buffers, the kernel-layout copies
+    of the frozen encoders, the launch plans and their CUDA graphs.  The predictor has one (``models``) or, with
+    ``use_online=True``, two (``online_models``, depth_pose_prediction.py:139-152)."""
+
+    def __init__(self, owner: 'DepthPosePrediction', tag: str):
+        dev = owner.device
+        self.tag = tag
+        self.models: Dict[str, nn.Module] = {}
+        self.models['depth_encoder'] = ResnetEncoder(owner.resnet_depth, owner.resnet_pretrained, device=dev)
+        self.models['depth_decoder'] = DepthDecoder(self.models['depth_encoder'].num_ch_encoder, owner.scales)
+        self.models['pose_encoder'] = ResnetEncoder(owner.resnet_pose, owner.resnet_pretrained, owner.num_pose_frames, device=dev)
+        self.models['pose_decoder'] = PoseDecoder()
+        self.flat = FlatParams(self.models['depth_decoder'], self.models['pose_decoder'], dev)
+        self.models['depth_encoder'].bind(lambda x: owner._run_encoder(self, 'depth_encoder', x))
+        self.models['pose_encoder'].bind(lambda x: owner._run_encoder(self, 'pose_encoder', x))
+        self.parameters: List[nn.Parameter] = []
+        for m in self.models.values():
+            self.parameters += list(m.parameters())
+        trainable = list(self.models['depth_decoder'].parameters()) + list(self.models['pose_decoder'].parameters())
+        self.optimizer = FlatAdam(self.parameters, owner.learning_rate, self.flat, trainable)
+        self.prep: Dict[str, PreparedEncoder] = {}
+        self.engines: Dict[int, AdaptEngine] = {}
+        self.enc_runners: Dict[Tuple[str, int, int, int], EncoderRunner] = {}
+        self.pose_runner = None
+        self.depth_runners: Dict[Tuple[int, int, int], DepthRunner] = {}
+        self.graphs: Dict[Tuple, Any] = {}
+        self.steps_run: Dict[int, int] = {}
+        self.weights_key: Dict[int, Any] = {}
+        self.adapt_flags_set = False
+
+    def drop_plans(self) -> None:
+        """plans hold raw pointers into the prepared encoder tensors: forget them (and everything captured from them)"""
+        self.engines.clear(); self.enc_runners.clear(); self.graphs.clear(); self.depth_runners.clear()
+        self.pose_runner = None
+        self.weights_key.clear()
+        self.steps_run.clear()          # a fresh engine runs its first step eagerly again (loads kernels, builds tensor maps)
+
+
 class DepthPosePrediction:
     def __init__(self, dataset_config, config, use_online: bool = False, *, data_parallel: bool = False,
-                 use_cuda_graph: bool = True, emit_outputs: bool = True, device: Optional[torch.device] = None):
+                 use_cuda_graph: bool = True, emit_outputs: bool = True, copy_outputs: bool = True,
+                 device: Optional[torch.device] = None):
         # Parameters (same names as the reference, :41-68) --------------------------------------
         self.config_file = config.config_file
         self.dataset_type = dataset_config.dataset
@@ -122,8 +162,6 @@ class DepthPosePrediction:
         self.epoch = 0
 
         self._validate_sets(dataset_config)
-        if use_online:
-            raise NotImplementedError('use_online=True (second network copy, :139-152) is SURVEY.md 8(f) row 4')
         if self.mask_dynamic:
             raise NotImplementedError('mask_dynamic=True (pre-training masks, :1064-1068) is SURVEY.md 8(f) row 3')
         if self.multiple_gpus:
@@ -131,9 +169,7 @@ class DepthPosePrediction:
                              'GPU under torch.distributed (SURVEY.md 8e)')
         if self.load_weights_folder is not None:
             self.load_weights_folder = Path(self.load_weights_folder).absolute()
-        self.use_online = False
-        self.online_models: Dict[str, nn.Module] = {}
-        self.online_optimizer = None
+        self.use_online = use_online
 
         # Device / process group ------------------------------------------------------------------
         self.rank, self.world = 0, 1
@@ -146,47 +182,60 @@ class DepthPosePrediction:
         if device is not None:
             self.device = torch.device(device)
         elif torch.cuda.is_available():
+            if self.gpu_ids is not None and not data_parallel:
+                torch.cuda.set_device(self.gpu_ids[0])          # "the main GPU" of :122-124
             self.device = torch.device('cuda', torch.cuda.current_device())
+            if self.gpu_ids is None:
+                self.gpu_ids = (self.device.index,)
         else:
             self.device = torch.device('cpu')      # parameter containers / checkpoints only; compute raises
         self.use_cuda_graph = use_cuda_graph
         self.emit_outputs = emit_outputs
+        # The reference returns fresh tensors from every call (:906-923).  The engine writes its outputs into static buffers,
+        # so the public methods hand out ONE clone of the output arena per call (a single D2D copy).  copy_outputs=False
+        # returns views of the static buffers instead: valid until the next adapt / predict call on this object.
+        self.copy_outputs = copy_outputs
 
         # Networks (parameter containers; arithmetic lives in the CUDA kernels) --------------------
-        self.models: Dict[str, nn.Module] = {}
-        self.models['depth_encoder'] = ResnetEncoder(self.resnet_depth, self.resnet_pretrained, device=self.device)
-        self.models['depth_decoder'] = DepthDecoder(self.models['depth_encoder'].num_ch_encoder, self.scales)
-        self.models['pose_encoder'] = ResnetEncoder(self.resnet_pose, self.resnet_pretrained, self.num_pose_frames,
-                                                    device=self.device)
-        self.models['pose_decoder'] = PoseDecoder()
-        self._flat = FlatParams(self.models['depth_decoder'], self.models['pose_decoder'], self.device)
-        self.models['depth_encoder'].bind(lambda x: self._run_encoder('depth_encoder', x))
-        self.models['pose_encoder'].bind(lambda x: self._run_encoder('pose_encoder', x))
-
-        self.parameters_to_train: List[nn.Parameter] = []
-        for m in self.models.values():
-            self.parameters_to_train += list(m.parameters())
-        trainable = list(self.models['depth_decoder'].parameters()) + list(self.models['pose_decoder'].parameters())
-        self.optimizer = FlatAdam(self.parameters_to_train, self.learning_rate, self._flat, trainable)
+        self._main = _NetSet(self, 'main')
+        self.models: Dict[str, nn.Module] = self._main.models
+        self.parameters_to_train: List[nn.Parameter] = self._main.parameters
+        self.optimizer = self._main.optimizer
         self.lr_scheduler = optim.lr_scheduler.StepLR(self.optimizer.torch_optimizer, self.scheduler_step_size, 0.1)
+        # second copy of the four networks (:139-152, :206-207): evaluated by _process_batch / predict_pose(use_online=True)
+        self._online = _NetSet(self, 'online') if use_online else None
+        self.online_models: Dict[str, nn.Module] = self._online.models if use_online else {}
+        self.online_parameters_to_train: List[nn.Parameter] = self._online.parameters if use_online else []
+        self.online_optimizer = self._online.optimizer if use_online else None
         self.train_loader, self.val_loader = None, None
 
         # Runtime state ---------------------------------------------------------------------------
-        self._prep: Dict[str, PreparedEncoder] = {}
-        self._engines: Dict[int, AdaptEngine] = {}
-        self._enc_runners: Dict[Tuple[str, int, int, int], EncoderRunner] = {}
-        self._pose_runner = None
-        self._graphs: Dict[Tuple, Any] = {}
-        self._steps_run: Dict[int, int] = {}
         self._aux_dev: Dict[Any, Tensor] = {}
         self._deferred: List[Tuple[Tensor, Tensor]] = []
         self._copy_stream = None
-        self._weights_key: Dict[int, Any] = {}
         self.noise_provider: Optional[Callable[[int, Tuple[int, ...]], Tensor]] = None
         self.stage_all_inputs = True          # move every dict value to the device like :916-917
         self._mode = 'eval'
-        self._adapt_flags_set = False
         self._late_event = None
+
+    # the main network set under its round-1 names (tests, bench.py)
+    @property
+    def _flat(self) -> FlatParams:
+        return self._main.flat
+
+    @property
+    def _engines(self) -> Dict[int, AdaptEngine]:
+        return self._main.engines
+
+    def _sets(self) -> List[_NetSet]:
+        return [self._main] + ([self._online] if self._online is not None else [])
+
+    def _set_of(self, use_online: bool) -> _NetSet:
+        if use_online:
+            if self._online is None:
+                raise KeyError('depth_encoder')      # the reference indexes its empty online_models dict (:931)
+            return self._online
+        return self._main
 
     # ------------------------------------------------------------------------------------------
     def _validate_sets(self, dataset_config) -> None:
@@ -240,47 +289,50 @@ class DepthPosePrediction:
 
     def _set_eval(self) -> None:
         if not self._all_eval():
-            for m in self.models.values():
+            for m in self.models.values():      # :802-805 (the online copy is not touched by _set_eval in the reference either)
                 m.eval()
         self._mode = 'eval'
 
     def _set_adapt(self, freeze_encoder: bool = True) -> None:
         if not freeze_encoder:
             raise NotImplementedError('freeze_encoder=False is SURVEY.md 8(f) row 3')
-        if not self._all_eval():
-            for m in self.models.values():
-                m.eval()
-        if not self._adapt_flags_set:
-            # requires_grad=False for BatchNorm and encoder parameters (:813-822); the reference never re-enables them
-            for model_name, model in self.models.items():
-                for name, param in model.named_parameters():
-                    if name.find('bn') != -1 or 'encoder' in model_name:
-                        param.requires_grad = False
-            self._adapt_flags_set = True
+        for ns in self._sets():                 # :813-827: both copies
+            if any(m.training for m in ns.models.values()):
+                for m in ns.models.values():
+                    m.eval()
+            if not ns.adapt_flags_set:
+                # requires_grad=False for BatchNorm and encoder parameters (:813-822); the reference never re-enables them
+                for model_name, model in ns.models.items():
+                    for name, param in model.named_parameters():
+                        if name.find('bn') != -1 or 'encoder' in model_name:
+                            param.requires_grad = False
+                ns.adapt_flags_set = True
         self._mode = 'adapt'
 
     # ------------------------------------------------------------------------------------------
     # engines
-    def _prepared(self, net: str) -> PreparedEncoder:
-        enc = self.models[net]
-        prep = self._prep.get(net)
+    def _prepared(self, net: str, ns: Optional[_NetSet] = None) -> PreparedEncoder:
+        ns = ns or self._main
+        enc = ns.models[net]
+        prep = ns.prep.get(net)
         if prep is None or prep.version != enc.version:
             prep = PreparedEncoder(enc, self.device)
-            self._prep[net] = prep
-            # plans hold raw pointers into the prepared tensors: rebuild them
-            self._engines.clear(); self._enc_runners.clear(); self._graphs.clear(); self._pose_runner = None
-            self._weights_key.clear()
+            ns.prep[net] = prep
+            ns.drop_plans()
+            self._late_event = None
         return prep
 
     def refresh_encoders(self) -> None:
         """Call after modifying encoder weights in place (load_state_dict does it automatically)."""
-        for net in ('depth_encoder', 'pose_encoder'):
-            self.models[net].version += 1
+        for ns in self._sets():
+            for net in ('depth_encoder', 'pose_encoder'):
+                ns.models[net].version += 1
 
-    def _engine(self, batch: int) -> AdaptEngine:
+    def _engine(self, batch: int, ns: Optional[_NetSet] = None) -> AdaptEngine:
         self._require_cuda()
-        dp, pp = self._prepared('depth_encoder'), self._prepared('pose_encoder')
-        eng = self._engines.get(batch)
+        ns = ns or self._main
+        dp, pp = self._prepared('depth_encoder', ns), self._prepared('pose_encoder', ns)
+        eng = ns.engines.get(batch)
         if eng is None:
             L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
             if self.world > 1:
@@ -288,24 +340,25 @@ class DepthPosePrediction:
             else:
                 b_global, has0 = batch, True
             eng = AdaptEngine(batch=batch, height=self.height, width=self.width, batch_global=b_global, has_sample0=has0,
-                              depth_prep=dp, pose_prep=pp, flat=self._flat, min_depth=self.min_depth,
+                              depth_prep=dp, pose_prep=pp, flat=ns.flat, min_depth=self.min_depth,
                               max_depth=self.max_depth, disparity_smoothness=self.disparity_smoothness,
                               velocity_loss_scaling=self.velocity_loss_scaling, device=self.device,
                               emit_outputs=self.emit_outputs)
-            self._engines[batch] = eng
+            eng.net_set = ns
+            ns.engines[batch] = eng
         return eng
 
-    def _run_encoder(self, net: str, x: Tensor) -> List[Tensor]:
+    def _run_encoder(self, ns: _NetSet, net: str, x: Tensor) -> List[Tensor]:
         """``models['depth_encoder'](image)`` (slam/slam.py:146): five NCHW-shaped feature maps."""
         self._require_cuda()
-        prep = self._prepared(net)
+        prep = self._prepared(net, ns)
         n, _, h, w = x.shape
         key = (net, n, h, w)
-        runner = self._enc_runners.get(key)
+        runner = ns.enc_runners.get(key)
         if runner is None:
             L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
-            runner = EncoderRunner(self.models[net], prep, n, h, w, self.device)
-            self._enc_runners[key] = runner
+            runner = EncoderRunner(ns.models[net], prep, n, h, w, self.device)
+            ns.enc_runners[key] = runner
         feats = runner(x.to(self.device, dtype=torch.float32))
         return [f.permute(0, 3, 1, 2).clone() for f in feats]
 
@@ -320,11 +373,14 @@ class DepthPosePrediction:
             m[('rgb', 0, s)] = eng.color[s]
         return m
 
-    def _stage_inputs(self, inputs: Dict[Any, Tensor], defer_unused: bool = False) -> AdaptEngine:
+    def _stage_inputs(self, inputs: Dict[Any, Tensor], defer_unused: bool = False, ns: Optional[_NetSet] = None) -> AdaptEngine:
         """copies the dict to the device in place (:916-917).  With ``defer_unused`` the values the path does not read are
-        only queued (``_flush_deferred`` moves them on a side stream after the step has been launched)."""
+        only queued (``_flush_deferred`` moves them on a side stream after the step has been launched).
+
+        The values the path reads land in the engine's static input buffers and the dict then holds views of those (in the
+        caller's shape): they stay valid until the next call that stages a batch of the same size."""
         batch = inputs[('rgb_aug', 0, 0)].shape[0]
-        eng = self._engine(batch)
+        eng = self._engine(batch, ns)
         smap = self._static_map(eng)
         self._deferred = []
         if defer_unused:
@@ -342,7 +398,7 @@ class DepthPosePrediction:
                         late.append((dst, src))
                     else:
                         dst.copy_(src, non_blocking=True)
-                inputs[key] = dst
+                inputs[key] = dst if (dst.shape == val.shape or dst.numel() != val.numel()) else dst.view(val.shape)
             elif self.stage_all_inputs and isinstance(val, Tensor):
                 # keys the path does not read are still moved like :916-917, into cached device buffers (no allocation per call)
                 buf = self._aux_dev.get(key)
@@ -389,9 +445,10 @@ class DepthPosePrediction:
         b_global = eng.b_global
         # the weights rarely change between calls: upload only when they do (a pageable H2D copy stalls the host)
         key = None if loss_sample_weights is None else tuple(float(v) for v in loss_sample_weights.detach().flatten().tolist())
-        if self._weights_key.get(eng.b, 'unset') == (key, self.batch_size):
+        wk = eng.net_set.weights_key
+        if wk.get(eng.b, 'unset') == (key, self.batch_size):
             return
-        self._weights_key[eng.b] = (key, self.batch_size)
+        wk[eng.b] = (key, self.batch_size)
         if loss_sample_weights is None:
             w = torch.ones(self.batch_size) / self.batch_size          # :1032 (uses config batch_size)
         else:
@@ -422,17 +479,19 @@ class DepthPosePrediction:
     def _collect(self, eng: AdaptEngine, check_nan: bool = True) -> Tuple[Dict[Any, Tensor], Dict[str, Tensor]]:
         b = eng.b
         outputs: Dict[Any, Tensor] = {}
+        arena = eng.out_arena.clone() if self.copy_outputs else None          # fresh tensors per call, like the reference
         for s in self.scales:
-            outputs[('disp', s)] = eng.disp[s]
+            outputs[('disp', s)] = eng.out_view(('disp', s), arena)
         for p, f in ((0, -1), (1, 1)):
             outputs[('axis_angle', 0, f)] = eng.axis_angle[p].reshape(b, 1, 3).clone()
             outputs[('translation', 0, f)] = eng.translation[p].reshape(b, 1, 3).clone()
             outputs[('cam_T_cam', 0, f)] = eng.cam_t_cam[p].clone()
         if self.emit_outputs:
             for s in self.scales:
-                outputs[('depth', s)] = eng.depth[s]
+                outputs[('depth', s)] = eng.out_view(('depth', s), arena)
+                warped = eng.out_view(('warped', s), arena)
                 for p, f in ((0, -1), (1, 1)):
-                    outputs[('rgb', f, s)] = eng.warped[s][p]
+                    outputs[('rgb', f, s)] = warped[p]
         vec = eng.losses.clone()
         if self.world > 1:
             import torch.distributed as dist
@@ -458,18 +517,17 @@ class DepthPosePrediction:
                        use_online: bool = False) -> Tuple[Dict[Any, Tensor], Dict[str, Tensor]]:
         """Forward + losses of one mini-batch (:906-923).  Values of ``inputs`` are replaced by their
         device copies, as in the reference."""
-        if use_online:
-            raise NotImplementedError('use_online')
-        eng = self._stage_inputs(inputs)
+        eng = self._stage_inputs(inputs, ns=self._set_of(use_online))          # online_models when asked (:930-932, :956-958)
         self._set_weights(eng, loss_sample_weights)
         self._draw_noise(eng)
         eng.forward()
+        self._last_engine = eng
         return self._collect(eng)
 
     def backward(self, inputs_engine: Optional[AdaptEngine] = None) -> None:
         """Gradients of the last ``_process_batch`` into the flat gradient buffer (= ``loss.backward()``
         of :312 with the encoders frozen) followed by the data-parallel all-reduce."""
-        eng = inputs_engine or next(iter(self._engines.values()))
+        eng = inputs_engine or self._last_engine
         eng.backward()
         self._allreduce_grads()
 
@@ -487,54 +545,58 @@ class DepthPosePrediction:
     def _step(self, eng: AdaptEngine) -> None:
         """one adaptation iteration on staged inputs: fwd, bwd, (all-reduce), Adam"""
         lr = self._adam_lr()
-        n_run = self._steps_run.get(eng.b, 0)
-        self._steps_run[eng.b] = n_run + 1
+        ns = eng.net_set
+        graphs = ns.graphs
+        n_run = ns.steps_run.get(eng.b, 0)
+        ns.steps_run[eng.b] = n_run + 1
         late_event = getattr(self, '_late_event', None)
         if not self.use_cuda_graph or n_run == 0:       # first step eager: loads every kernel before capture
             if late_event is not None:
                 torch.cuda.current_stream(self.device).wait_event(late_event)
             eng.forward_backward(); self._allreduce_grads(); eng.adam(lr)
             return
-        if self.world == 1 and H2D_OVERLAP:
+        if self.world == 1 and H2D_OVERLAP and late_event is not None:
             # two graphs: the networks (need rgb_aug / intrinsics only) run while the photometric inputs are still in flight
+            # (with nothing in flight -- inputs already resident, second and later iterations of adapt(steps=k) -- the step
+            # is the single graph below)
             ka, kb = (eng.b, 'nets'), (eng.b, 'rest', lr)
-            if ka not in self._graphs:
+            if ka not in graphs:
                 ga = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(ga):
                     eng.networks_forward()
-                self._graphs[ka] = ga
-            if kb not in self._graphs:
+                graphs[ka] = ga
+            if kb not in graphs:
                 gb = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(gb):
                     eng.photometric_and_backward(); eng.adam(lr)
-                self._graphs[kb] = gb
-            self._graphs[ka].replay()
+                graphs[kb] = gb
+            graphs[ka].replay()
             if late_event is not None:
                 torch.cuda.current_stream(self.device).wait_event(late_event)
-            self._graphs[kb].replay()
+            graphs[kb].replay()
             return
         if self.world == 1:
             key = (eng.b, 'step', lr)
-            g = self._graphs.get(key)
+            g = graphs.get(key)
             if g is None:
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     eng.forward_backward(); eng.adam(lr)
-                self._graphs[key] = g
+                graphs[key] = g
             g.replay()
         else:
             k1, k2 = (eng.b, 'fwdbwd'), (eng.b, 'adam', lr)
-            if k1 not in self._graphs:
+            if k1 not in graphs:
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
                     eng.forward_backward()
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2):
                     eng.adam(lr)
-                self._graphs[k1], self._graphs[k2] = g1, g2
-            self._graphs[k1].replay()
+                graphs[k1], graphs[k2] = g1, g2
+            graphs[k1].replay()
             self._allreduce_grads()
-            self._graphs[k2].replay()
+            graphs[k2].replay()
 
     # ------------------------------------------------------------------------------------------
     def adapt(self, online_data: Dict[Any, Tensor], training_data: Optional[Dict[Any, Tensor]] = None,
@@ -551,7 +613,9 @@ class DepthPosePrediction:
             for _ in range(steps):
                 self._draw_noise(eng)
                 self._step(eng)
+                self._late_event = None     # the first iteration waited for the late inputs; the others find them resident
             self._flush_deferred()          # unused dict values move while the step runs
+            self._last_engine = eng
             return self._collect(eng)
         self._set_eval()
         with torch.no_grad():
@@ -562,8 +626,7 @@ class DepthPosePrediction:
                                   'BatchNorm: SURVEY.md 8(f) row 3.  Use adapt().')
 
     # ------------------------------------------------------------------------------------------
-    # inference entry points of the reference that Slam does not call (:530-626).  They reuse the adaptation engine's forward
-    # pass; added after round 1's last GPU run (API completeness, not yet exercised on hardware).
+    # inference entry points of the reference that Slam does not call (:530-626)
     def predict(self, batch) -> Dict[Any, Tensor]:
         """:530-536: eval-mode forward of one batch dict, returns the outputs"""
         if not self.is_trained:
@@ -574,34 +637,22 @@ class DepthPosePrediction:
         return outputs
 
     def _depth_of(self, image: Tensor) -> Tensor:
-        """depth of `image` (n, 3, H, W) from the depth network alone.  The engine evaluates whole triplets, so the image
-        stands in for all three frames with a generic camera; only ('depth', 0) = disp_to_depth(disp_0) is kept, which
-        does not depend on the other frames or the intrinsics."""
-        from . import synthetic
+        """depth of `image` (n, 3, H, W) from the depth network alone (:547-550): encoder, decoder, dispconv_0, disp_to_depth on
+        a plan of its own (no pose network, no losses, no collective; the adaptation engine's state is not touched).  Any
+        H, W that are multiples of 32."""
+        self._require_cuda()
         if image.dim() == 3:
             image = image.unsqueeze(0)
-        n = image.shape[0]
-        img = image.to(dtype=torch.float32)
-        batch: Dict[Any, Tensor] = {}
-        for f in (-1, 0, 1):
-            batch[('rgb', f, 0)] = img
-            batch[('rgb_aug', f, 0)] = img
-        for sc in range(1, 4):
-            batch[('rgb', 0, sc)] = torch.nn.functional.avg_pool2d(img, 2 ** sc)
-        k, ik = synthetic.kitti_intrinsics(self.height, self.width, 0)
-        batch[('camera_matrix', 0)] = torch.from_numpy(k).unsqueeze(0).repeat(n, 1, 1)
-        batch[('inv_camera_matrix', 0)] = torch.from_numpy(ik).unsqueeze(0).repeat(n, 1, 1)
-        for f in (0, 1):
-            batch[('relative_distance', f)] = torch.zeros(n, dtype=torch.float64)
+        n, _, h, w = image.shape
+        ns = self._main
+        prep = self._prepared('depth_encoder', ns)
+        runner = ns.depth_runners.get((n, h, w))
+        if runner is None:
+            L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
+            runner = DepthRunner(prep, ns.flat, n, h, w, self.min_depth, self.max_depth, self.device)
+            ns.depth_runners[(n, h, w)] = runner
         self._set_eval()
-        with torch.no_grad():
-            outputs, _ = self._process_batch(batch, torch.ones(n) / n)
-        if ('depth', 0) in outputs:
-            return outputs[('depth', 0)].clone()
-        disp = outputs[('disp', 0)]                       # emit_outputs=False: depth_pose_prediction/utils.py:120-142
-        if self.max_depth is None:
-            return (self.min_depth if self.min_depth is not None else 1.0) / disp
-        return 1.0 / (1.0 / self.max_depth + (1.0 / self.min_depth - 1.0 / self.max_depth) * disp)
+        return runner(image.to(self.device, dtype=torch.float32))
 
     def predict_from_image(self, image, as_numpy: bool = True):
         """:538-554: one image in, predicted depth out"""
@@ -649,37 +700,44 @@ class DepthPosePrediction:
         """:628-664: pose net forward for a loop-closure pair, invert=False; returns (4x4, eye(6))."""
         if not self.is_trained:
             warnings.warn('The model has not been trained yet.', RuntimeWarning)
-        if use_online:
-            raise NotImplementedError('use_online')
+        ns = self._set_of(use_online)            # :650-652
         self._require_cuda()
         if image_0.dim() == 3:
             image_0 = image_0.unsqueeze(0)
         if image_1.dim() == 3:
             image_1 = image_1.unsqueeze(0)
         self._set_eval()
-        runner = self._get_pose_runner(image_0.shape[0], image_0.shape[2], image_0.shape[3])
+        runner = self._get_pose_runner(image_0.shape[0], image_0.shape[2], image_0.shape[3], ns)
         transformation = runner(image_0.to(self.device, dtype=torch.float32), image_1.to(self.device, dtype=torch.float32))
         cov_matrix = torch.eye(6, device=self.device)
         if as_numpy:
             return transformation.squeeze().cpu().numpy(), cov_matrix.cpu().numpy()
         return transformation, cov_matrix
 
-    def _get_pose_runner(self, n: int, h: int, w: int):
-        prep = self._prepared('pose_encoder')
-        r = self._pose_runner
+    def _get_pose_runner(self, n: int, h: int, w: int, ns: Optional[_NetSet] = None):
+        ns = ns or self._main
+        prep = self._prepared('pose_encoder', ns)
+        r = ns.pose_runner
         if r is None or (r.n, r.h, r.w) != (n, h, w):
             L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
-            r = _PoseRunner(prep, self._flat, n, h, w, self.device)
-            self._pose_runner = r
+            r = _PoseRunner(prep, ns.flat, n, h, w, self.device)
+            ns.pose_runner = r
         return r
 
     # ------------------------------------------------------------------------------------------
     # checkpoints (:669-749): same files, key names and shapes as the reference
     def save_model(self) -> None:
         save_folder = Path(self.log_path) / 'models' / f'weights_{self.epoch:03}'
+        if self.rank != 0:          # data-parallel replicas hold bit-identical weights: one writer
+            return
         save_folder.mkdir(parents=True, exist_ok=True)
         for model_name, model in self.models.items():
             to_save = {k: v.detach().clone().contiguous() for k, v in model.state_dict().items()}
+            if 'encoder' in model_name:
+                # :684-688 writes `Tensor(self.height)` / `Tensor(self.width)`: UNINITIALISED tensors of that many elements
+                # ("the sizes needed at prediction time" of monodepth2-style loaders are their lengths); zeros here
+                to_save['height'] = torch.zeros(self.height)
+                to_save['width'] = torch.zeros(self.width)
             torch.save(to_save, save_folder / f'{model_name}.pth')
         torch.save({'optimizer': self.optimizer.state_dict(), 'scheduler': self.lr_scheduler.state_dict()},
                    save_folder / 'optimizer.pth')
@@ -719,7 +777,33 @@ class DepthPosePrediction:
                 print('Cannot find matching optimizer weights, so the optimizer is randomly initialized.')
 
     def load_online_model(self, load_optimizer: bool = True) -> None:
-        raise NotImplementedError('use_online (SURVEY.md 8(f) row 4)')
+        """:751-792: the checkpoint into the online copy of the networks (and its optimiser)"""
+        if self.load_weights_folder is None:
+            print('Weights folder required to load the model is not specified.')
+        if not self.load_weights_folder.exists():
+            print(f'Cannot find folder: {self.load_weights_folder}')
+        print(f'Load online model from: {self.load_weights_folder}')
+        for model_name, model in self.online_models.items():
+            path = self.load_weights_folder / f'{model_name}.pth'
+            pretrained = torch.load(path, map_location=self.device)
+            own = model.state_dict()
+            pretrained = {k: v for k, v in pretrained.items() if k in own}
+            if len(pretrained) == 0:
+                raise RuntimeError(f'No fitting weights found in: {path}')
+            own.update(pretrained)
+            model.load_state_dict(own)
+        self.refresh_encoders()
+        if load_optimizer:
+            try:
+                optimizer_dict = torch.load(self.load_weights_folder / 'optimizer.pth', map_location=self.device)
+                if 'optimizer' in optimizer_dict:
+                    self.online_optimizer.load_state_dict(optimizer_dict['optimizer'])
+                    print('Restored online optimizer')
+                else:
+                    self.online_optimizer.load_state_dict(optimizer_dict)
+                    print('Restored online optimizer (legacy mode).')
+            except Exception:   # noqa: BLE001  (:789)
+                print('Cannot find matching optimizer weights, so the optimizer is randomly initialized.')
 
 
 class _PoseRunner:

@@ -35,31 +35,37 @@ def conv_out(hi: int, k: int, s: int, p: int) -> int:
     return (hi + 2 * p - k) // s + 1
 
 
-# below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: gather kernels (split-K) instead
+# below this many 16x8 output tiles the persistent TMA kernel cannot fill the GPU: split-K form (or, without it, the gather kernels)
 TMA_MIN_TILES = int(os.environ.get('CLSLAM_TMA_MIN_TILES', '24'))
 TMA_MIN_TILES_BWD = int(os.environ.get('CLSLAM_TMA_MIN_TILES_BWD', '24'))     # dgrad: the gather dgrad is slower, so the bar is lower
-# EXPERIMENTAL (off by default; written after this round's GPU budget was spent, not yet run on hardware): small-map layers
-# with 64-multiple channels also take the TMA kernel, in its split-K form (clslam_conv3x3_tma_ws)
-TMA_SPLITK = os.environ.get('CLSLAM_TMA_SPLITK', '0') == '1'
-# with TMA_SPLITK: also move the weight gradients of those layers to clslam_wgrad3x3_tma (default: they stay on the gather kernel)
-TMA_SPLITK_WGRAD = os.environ.get('CLSLAM_TMA_SPLITK_WGRAD', '0') == '1'
-# EXPERIMENTAL (off by default): the dispconv weight gradients run on lane 1 (ahead of the short pose branch) instead of lane 2,
-# whose wgrad chain is the longest lane of the batch-1 backward pass (profiles/r01_bench_b1.json: 0.51 ms of per-op time
-# against 0.39 ms on lane 0 and 0.19 ms on lane 1)
-DISP_WGRAD_LANE = 1 if os.environ.get('CLSLAM_DISP_WGRAD_LANE1', '0') == '1' else 2
-# EXPERIMENTAL (off by default): the 1x1 / stride-2 down-sampling convolutions of layer2-4 run the TMA kernel (taps = 1) on the
-# (0, 0) channel block of the space-to-depth planes their block's conv1 already reads, instead of the gather kernel
-TMA_DS = os.environ.get('CLSLAM_TMA_DS', '0') == '1'
-# EXPERIMENTAL (off by default): 3x3 launches over several small images walk them as one stack of n * (h + 2) rows (the halo
-# rows between two images are the padding), so a 16-row tile is not wasted on a 6-row map: clslam_conv_tma.flags.  Every
-# planes buffer this engine feeds to a zero-padded launch has an all-zero halo (allocated zeroed, producers write with
-# out_halo = 0); reflection-padded launches read the reflection halo anyway.
-TMA_TALL = os.environ.get('CLSLAM_TMA_TALL', '0') == '1'
-# EXPERIMENTAL (off by default): the step is two graphs.  The first holds everything that only reads the network inputs (rgb_aug,
-# intrinsics); the photometric inputs (rgb target / sources, colour pyramid, distances: half of the H2D bytes) travel on a
-# copy stream meanwhile and the second graph waits for them.  The identity candidates then run at the head of the second
+# Launch-plan switches.  Every one of them was A/B-tested on a B200 at the start of round 2 (tools/ab_round2.sh,
+# profiles/r02_ab_summary.txt: parity-green end to end, batch 1: 1.224 -> 1.017 ms / step, batch 8: 4.010 -> 3.488 ms with all of
+# them on) and is ON by default; set the variable to 0 to get the round-1 plan back.
+def _flag(name: str, default: str = '1') -> bool:
+    return os.environ.get(name, default) == '1'
+
+
+# small-map layers with 64-multiple channels take the TMA kernel in its split-K form (clslam_conv3x3_tma_ws) instead of the
+# round-1a gather kernels
+TMA_SPLITK = _flag('CLSLAM_TMA_SPLITK')
+# with TMA_SPLITK: also move the weight gradients of those layers to clslam_wgrad3x3_tma (measured slower at batch 1: off)
+TMA_SPLITK_WGRAD = _flag('CLSLAM_TMA_SPLITK_WGRAD', '0')
+# the dispconv weight gradients run on lane 1 (ahead of the short pose branch) instead of lane 2, whose wgrad chain is the
+# longest lane of the batch-1 backward pass
+DISP_WGRAD_LANE = 1 if _flag('CLSLAM_DISP_WGRAD_LANE1') else 2
+# the 1x1 / stride-2 down-sampling convolutions of layer2-4 run the TMA kernel (taps = 1) on the (0, 0) channel block of the
+# space-to-depth planes their block's conv1 already reads, instead of the gather kernel
+TMA_DS = _flag('CLSLAM_TMA_DS')
+# 3x3 launches over several small images walk them as one stack of n * (h + 2) rows (the halo rows between two images are the
+# padding), so a 16-row tile is not wasted on a 6-row map: clslam_conv_tma.flags.  Every planes buffer this engine feeds to a
+# zero-padded launch has an all-zero halo (allocated zeroed, producers write with out_halo = 0); reflection-padded launches
+# read the reflection halo anyway.
+TMA_TALL = _flag('CLSLAM_TMA_TALL')
+# the step is two graphs when host inputs are in flight.  The first holds everything that only reads the network inputs
+# (rgb_aug, intrinsics); the photometric inputs (rgb target / sources, colour pyramid, distances: half of the H2D bytes) travel
+# on a copy stream meanwhile and the second graph waits for them.  The identity candidates then run at the head of the second
 # graph instead of on lane 2 next to the encoders.
-H2D_OVERLAP = os.environ.get('CLSLAM_H2D_OVERLAP', '0') == '1'
+H2D_OVERLAP = _flag('CLSLAM_H2D_OVERLAP')
 
 
 def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
@@ -287,17 +293,18 @@ class Plan:
         """dX of a reflection-padded 3x3 layer: full correlation of the dz planes with the flipped weights + fold
         (clslam_conv3x3_tma(PAD_FULL) + clslam_dgrad_fold; with TMA_SPLITK one call, clslam_dgrad3x3_tma_ws, whose fold reads
         the split-K partial sums directly)"""
-        if not TMA_SPLITK:
-            self.conv_tma(f'{name}', dz_pl, L.PAD_FULL, cin_prev, wt_hi, wt_lo, None, None, L.ACT_NONE, y=dxp)
-            self.dgrad_fold(f'{name}.fold', dxp, n, h, w, cin_prev, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, dz_prev_pl)
-            return
         a = L.ConvTma()
         a.inp = dz_pl
         a.pad_mode, a.cout = L.PAD_FULL, cin_prev
         a.w_hi, a.w_lo = _p(wt_hi), _p(wt_lo)
         a.act, a.y, a.out_up, a.taps = L.ACT_NONE, _p(dxp), 1, 3
         self.keep.append(a)
-        self.need_ws(self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a)))
+        ws = self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a)) if TMA_SPLITK else 0
+        if ws == 0:          # no K split for this shape: the same two launches as two plan ops (one kernel per op)
+            self.conv_tma(f'{name}', dz_pl, L.PAD_FULL, cin_prev, wt_hi, wt_lo, None, None, L.ACT_NONE, y=dxp)
+            self.dgrad_fold(f'{name}.fold', dxp, n, h, w, cin_prev, up, y_prev, act_prev, disp_dz, disp_w, dz_prev, dz_prev_pl)
+            return
+        self.need_ws(ws)
         self.add(name, lambda stream, ws, arg, *r: self.lib.clslam_dgrad3x3_tma_ws(
             ctypes.byref(arg), *r[:6], ctypes.byref(r[6]) if r[6] is not None else None, ws, self.ws_bytes, stream),
             a, up, _p(y_prev), act_prev, _p(disp_dz), _p(disp_w), _p(dz_prev), dz_prev_pl)
@@ -353,11 +360,11 @@ class Plan:
             if fn is None and args[0] not in self._events:
                 self._events[args[0]] = torch.cuda.Event()
 
-    def run(self, first: int = 0, last: Optional[int] = None, serial: bool = False) -> None:
+    def run(self, first: int = 0, last: Optional[int] = None, serial: bool = False, timed: bool = False) -> None:
         main = torch.cuda.current_stream(self.device)
         streams = [main] + ([main] * len(self._side) if serial else self._side)
         ptrs = [st.cuda_stream for st in streams]
-        for name, fn, args, lane in self.ops[first:last]:
+        for i, (name, fn, args, lane) in enumerate(self.ops[first:last], start=first):
             if fn is None:
                 if serial:
                     continue
@@ -366,9 +373,33 @@ class Plan:
                 else:
                     streams[lane].wait_event(self._events[args[0]])
                 continue
+            if timed:
+                self.lib.clslam_event_record(self._timers[i][0], ptrs[lane])
             rc = fn(ptrs[lane], self._ws_ptr[lane], *args)
+            if timed:
+                self.lib.clslam_event_record(self._timers[i][1], ptrs[lane])
             if rc != 0:
                 L.check(rc, name)
+
+    # -- measurement (bench.py): per-op durations where the product runs them, i.e. inside the replayed step graph ----------
+    def make_timers(self) -> None:
+        """one (before, after) timing-event pair per op.  ``run(timed=True)`` records them on the op's lane; under stream
+        capture they become event-record nodes of the graph, so every replay stamps them (clslam_event_record)."""
+        if not hasattr(self, '_timers'):
+            self._timers = [None if fn is None else (self.lib.clslam_event_create(), self.lib.clslam_event_create())
+                            for _, fn, _, _ in self.ops]
+
+    def read_timers(self, first: int = 0, last: Optional[int] = None) -> List[Optional[float]]:
+        """milliseconds per op of the last completed timed run (None for fork / join markers)"""
+        out: List[Optional[float]] = []
+        ms = ctypes.c_float(0.0)
+        for t in self._timers[first:last]:
+            if t is None:
+                out.append(None)
+                continue
+            L.check(self.lib.clslam_event_elapsed_ms(t[0], t[1], ctypes.byref(ms)), 'event_elapsed')
+            out.append(float(ms.value))
+        return out
 
 
 def conv1_s2d_ok(n: int, h: int, w: int, cin_pad: int) -> bool:
@@ -504,6 +535,93 @@ class EncoderRunner:
         return self.feats
 
 
+def decoder_geometry(plan: Plan, b: int, h: int, w: int):
+    """which depth-decoder layers run the TMA kernel, and the concat buffers the encoder writes its skip features into
+    (planes inside the decoder's concat buffers: torch.cat of depth_decoder.py:66 without a copy).
+    Returns (u0, u1, cat, skips, feat4_planes, fh, fw)."""
+    fh = [h >> (k + 1) for k in range(5)]
+    fw = [w >> (k + 1) for k in range(5)]
+    u0, u1, cat = {}, {}, {}
+    for i in range(4, -1, -1):
+        hi_, wi_ = (fh[4], fw[4]) if i == 4 else (fh[i], fw[i])          # input of upconv_i_0: feats[4] or y1 of stage i + 1
+        cin0 = ENC_CH[4] if i == 4 else DEC_CH[i + 1]
+        c2 = ENC_CH[i - 1] if i > 0 else 0
+        u0[i] = tma_ok(b, hi_, wi_, cin0, DEC_CH[i])
+        u1[i] = tma_ok(b, 2 * hi_, 2 * wi_, DEC_CH[i] + c2, DEC_CH[i])
+        cat[i] = PlaneBuf(plan, b, 2 * hi_, 2 * wi_, DEC_CH[i] + c2) if u1[i] else None
+    skips = {i - 1: cat[i].view(DEC_CH[i], ENC_CH[i - 1]) for i in range(1, 5) if cat[i] is not None}
+    feat4_pl = PlaneBuf(plan, b, fh[4], fw[4], ENC_CH[4]).view() if u0[4] else None
+    return u0, u1, cat, skips, feat4_pl, fh, fw
+
+
+class DepthRunner:
+    """Depth network alone: encoder + decoder + dispconv_0 + disp_to_depth for ``predict_from_image(s)``
+    (depth_pose_prediction.py:538-554): no pose network, no losses, no collectives.  Keyed by (n, h, w) by the caller."""
+
+    def __init__(self, prep: PreparedEncoder, flat: FlatParams, n: int, h: int, w: int, min_depth, max_depth, device):
+        if h % 32 or w % 32:
+            raise ValueError('height and width must be multiples of 32 (ResNet-18 / 4-scale pyramid)')
+        self.n, self.h, self.w = n, h, w
+        plan = Plan(device)
+        lib = plan.lib
+        self.plan = plan
+        self.image = plan.alloc(n, 3, h, w)
+        staged, s2d = stage_for_encoder(plan, prep, 'stage', [(self.image, None, 0, n)], n, h, w)
+        u0, u1, cat, skips, feat4_pl, fh, fw = decoder_geometry(plan, n, h, w)
+        feats = build_encoder(plan, prep, staged, n, h, w, 'depth_enc', skips=skips, feat4_planes=feat4_pl, x_s2d=s2d)
+        plan.simple('split_weights', lib.clslam_split_bf16, _p(flat.params), _p(flat.params_hi), _p(flat.params_lo), flat.numel)
+        dd = 'depth_decoder'
+        x, x_pl = feats[4], feat4_pl
+        for i in range(4, -1, -1):
+            hi_, wi_ = x.shape[1], x.shape[2]
+            d0 = plan.desc(n, hi_, wi_, x.shape[3], DEC_CH[i], 3, 1, 1, pad_mode=L.PAD_REFLECT, act=L.ACT_ELU)
+            y0 = plan.alloc(n, hi_, wi_, DEC_CH[i])
+            key0 = (dd, f'upconv_{i}_0.conv.conv')
+            y0_up = cat[i].view(0, DEC_CH[i]) if cat[i] is not None else None
+            if u0[i]:
+                plan.conv_tma(f'upconv_{i}_0', x_pl, L.PAD_REFLECT, DEC_CH[i], flat.weight_hi_ptr(key0), flat.weight_lo_ptr(key0),
+                              None, flat.bias_ptr(key0), L.ACT_ELU, y=y0, out=y0_up, out_up=2, out_halo=1)
+            else:
+                plan.conv_fwd(f'upconv_{i}_0', d0, x, None, flat.weight_ptr(key0), None, flat.bias_ptr(key0), None, y0,
+                              flat.weight_hi_ptr(key0), flat.weight_lo_ptr(key0), out=y0_up, out_up=2, out_halo=1)
+            skip = feats[i - 1] if i > 0 else None
+            ho_, wo_ = (skip.shape[1], skip.shape[2]) if i > 0 else (hi_ * 2, wi_ * 2)
+            c2 = skip.shape[3] if i > 0 else 0
+            d1 = plan.desc(n, ho_, wo_, DEC_CH[i] + c2, DEC_CH[i], 3, 1, 1, pad_mode=L.PAD_REFLECT, in_mode=L.IN_UPCAT,
+                           c1=DEC_CH[i], h1=hi_, w1=wi_, act=L.ACT_ELU)
+            y1 = plan.alloc(n, ho_, wo_, DEC_CH[i])
+            key1 = (dd, f'upconv_{i}_1.conv.conv')
+            y1_pl = PlaneBuf(plan, n, ho_, wo_, DEC_CH[i]).view() if (i > 0 and u0[i - 1]) else None
+            if u1[i]:
+                plan.conv_tma(f'upconv_{i}_1', cat[i].view(), L.PAD_REFLECT, DEC_CH[i], flat.weight_hi_ptr(key1),
+                              flat.weight_lo_ptr(key1), None, flat.bias_ptr(key1), L.ACT_ELU, y=y1, out=y1_pl, out_halo=1)
+            else:
+                plan.conv_fwd(f'upconv_{i}_1', d1, y0, skip, flat.weight_ptr(key1), None, flat.bias_ptr(key1), None, y1,
+                              flat.weight_hi_ptr(key1), flat.weight_lo_ptr(key1), out=y1_pl, out_halo=1)
+            x, x_pl = y1, y1_pl
+        keyd = (dd, 'dispconv_0.conv')
+        self.disp = plan.alloc(n, 1, h, w)
+        self.depth = plan.alloc(n, 1, h, w)
+        plan.simple('dispconv_0', lib.clslam_dispconv_fwd, _p(x), flat.weight_ptr(keyd), flat.bias_ptr(keyd), _p(self.disp), n, h, w,
+                    DEC_CH[0])
+        if min_depth is None and max_depth is None:
+            mode = L.DEPTH_INV
+        elif max_depth is None:
+            mode = L.DEPTH_MIN_ONLY
+        elif min_depth is None:
+            raise ValueError('min_depth is None')
+        else:
+            mode = L.DEPTH_MIN_MAX
+        plan.simple('disp_to_depth', lib.clslam_disp_to_depth, _p(self.disp), _p(self.depth), n * h * w, mode,
+                    float(min_depth or 0.0), float(max_depth or 0.0))
+        plan.finalize()
+
+    def __call__(self, image: torch.Tensor) -> torch.Tensor:
+        self.image.copy_(image)
+        self.plan.run()
+        return self.depth.clone()
+
+
 class AdaptEngine:
     """fwd + loss + bwd + Adam of one mini-batch shard."""
 
@@ -539,6 +657,24 @@ class AdaptEngine:
         self.sample_w_global = plan.alloc(batch_global, zero=True)
         self.noise_all = plan.alloc(S, b, 2, h, w, zero=True)          # one buffer: the four per-scale draws are one RNG launch
         self.noise = [self.noise_all[s] for s in range(S)]
+        # ---- the map-sized outputs the caller receives (App. C.2) live in ONE arena: the reference hands out fresh tensors per
+        # call, so the public methods return one clone of the arena (a single D2D copy) carved into the same views
+        self.out_views: Dict[tuple, tuple] = {}
+        off = 0
+        def reserve(key, *shape):
+            nonlocal off
+            nel = 1
+            for d in shape:
+                nel *= d
+            self.out_views[key] = (off, nel, shape)
+            off += (nel + 63) // 64 * 64
+        for s in range(S):
+            reserve(('disp', s), b, 1, h >> s, w >> s)
+        if emit_outputs:
+            for s in range(S):
+                reserve(('depth', s), b, 1, h, w)
+                reserve(('warped', s), 2, b, 3, h, w)
+        self.out_arena = plan.alloc(off)
 
         # ---- depth network (lane 0; pose network on lane 1, identity candidates on lane 2) ------
         plan.fork((1, 2))
@@ -557,19 +693,8 @@ class AdaptEngine:
         plan.set_lane(0)
         self.depth_in, depth_s2d = stage_for_encoder(plan, depth_prep, 'depth.stage', [(self.rgb_aug[1], None, 0, b)], b, h, w)
         # decoder geometry first: which layers run the TMA kernel decides where the encoder writes its skip features
-        # (planes inside the decoder's concat buffers: torch.cat of depth_decoder.py:66 without a copy)
-        fh = [h >> (k + 1) for k in range(5)]
-        fw = [w >> (k + 1) for k in range(5)]
-        u0, u1, cat, y1_pl = {}, {}, {}, {}
-        for i in range(4, -1, -1):
-            hi_, wi_ = (fh[4], fw[4]) if i == 4 else (fh[i], fw[i])          # input of upconv_i_0: feats[4] or y1 of stage i + 1
-            cin0 = ENC_CH[4] if i == 4 else DEC_CH[i + 1]
-            c2 = ENC_CH[i - 1] if i > 0 else 0
-            u0[i] = tma_ok(b, hi_, wi_, cin0, DEC_CH[i])
-            u1[i] = tma_ok(b, 2 * hi_, 2 * wi_, DEC_CH[i] + c2, DEC_CH[i])
-            cat[i] = PlaneBuf(plan, b, 2 * hi_, 2 * wi_, DEC_CH[i] + c2) if u1[i] else None
-        skips = {i - 1: cat[i].view(DEC_CH[i], ENC_CH[i - 1]) for i in range(1, 5) if cat[i] is not None}
-        feat4_pl = PlaneBuf(plan, b, fh[4], fw[4], ENC_CH[4]).view() if u0[4] else None
+        u0, u1, cat, skips, feat4_pl, fh, fw = decoder_geometry(plan, b, h, w)
+        y1_pl = {}
         feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc', skips=skips, feat4_planes=feat4_pl,
                               x_s2d=depth_s2d)
         self.depth_feats = feats
@@ -617,7 +742,7 @@ class AdaptEngine:
             self.y[(i, 1)] = y1; self.dec_desc[(i, 1)] = (d1, y0, skip)
             if i < S:
                 keyd = (dd, f'dispconv_{i}.conv')
-                dsp = plan.alloc(b, 1, ho_, wo_)
+                dsp = self.out_view(('disp', i))
                 if i > 0:                    # only the photometric chain reads disp_i: lane 2, parallel to the next decoder stage
                     plan.record(f'y1_{i}')
                     plan.set_lane(2)
@@ -674,8 +799,8 @@ class AdaptEngine:
 
         # ---- photometric chain + losses -------------------------------------------------------
         self.n_tiles = lib.clslam_photo_tiles(h, w)
-        self.depth = [plan.alloc(b, 1, h, w) for _ in range(S)] if emit_outputs else [None] * S
-        self.warped = [plan.alloc(2, b, 3, h, w) for _ in range(S)] if emit_outputs else [None] * S
+        self.depth = [self.out_view(('depth', s)) for s in range(S)] if emit_outputs else [None] * S
+        self.warped = [self.out_view(('warped', s)) for s in range(S)] if emit_outputs else [None] * S
         self.argmin = [plan.alloc(b, h, w, dtype=torch.uint8) for _ in range(S)]
         self.loss_partials = plan.alloc(S, b, self.n_tiles)
         self.ddisp_full = [plan.alloc(b, h, w) for _ in range(S)]
@@ -876,6 +1001,10 @@ class AdaptEngine:
 
         self._graphs: Dict[str, torch.cuda.CUDAGraph] = {}
 
+    def out_view(self, key, arena: Optional[torch.Tensor] = None) -> torch.Tensor:
+        off, nel, shape = self.out_views[key]
+        return (self.out_arena if arena is None else arena)[off:off + nel].view(*shape)
+
     # ---- flipped weights of the TMA dgrad launches ------------------------------------------------
     _WT_CAP = 4 * 1024 * 1024          # elements per plane reserved up front (the decoder has 3.1 M 3x3 weights)
 
@@ -917,10 +1046,10 @@ class AdaptEngine:
     def backward(self) -> None:
         self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
 
-    def forward_backward(self) -> None:
+    def forward_backward(self, timed: bool = False) -> None:
         """one pass without the forward-only join (the loss assembly overlaps the photometric backward)"""
-        self.plan.run(0, self.n_fwd_core)
-        self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
+        self.plan.run(0, self.n_fwd_core, timed=timed)
+        self.plan.run(self.n_fwd_ops, self.n_bwd_ops, timed=timed)
 
     def networks_forward(self) -> None:
         """first part of forward_backward: both networks (reads rgb_aug and the intrinsics only)"""

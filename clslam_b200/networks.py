@@ -147,6 +147,20 @@ class _FlatConv(nn.Module):
         self.register_parameter('weight', None)
         self.register_parameter('bias', None)
 
+    def _apply(self, fn, recurse=True):
+        """``model.to(...)`` / ``.cuda()`` / ``.float()`` as a no-op is fine (the reference calls ``m.to(self.device)``, :186);
+        a conversion that would move or re-type the tensors is refused: the kernels, Adam and the all-reduce work on the flat
+        buffer these Parameters are views of, and a converted copy would silently detach them from it."""
+        for name in ('weight', 'bias'):
+            p = getattr(self, name)
+            if p is None:
+                continue
+            q = fn(p.data)
+            if q.device != p.device or q.dtype != p.dtype:
+                raise RuntimeError(f'clslam_b200: the decoder parameters are views of the flat parameter buffer on {p.device} '
+                                   f'({p.dtype}); moving / converting them ({q.device}, {q.dtype}) is not supported')
+        return self
+
 
 def depth_decoder_spec() -> List[Tuple[str, int, int, int]]:
     """(module path, cout, cin, k) in the reference's creation order (depth_decoder.py:30-46)."""

@@ -58,6 +58,13 @@ int clslam_abi_version(void);
 long long clslam_launch_count(void);
 /* bind this library's CUDA runtime to `device` on the calling host thread (one process per GPU) */
 int clslam_set_device(int device);
+/* Timing events for the measurement harness (bench.py): cudaEvent_t handles.  clslam_event_record on a stream that is
+ * being captured adds an external event-record node, so the per-kernel durations of the step graph can be read after a
+ * replay (warm, in-graph: the time base of the roofline block).  Not used on the product path. */
+void* clslam_event_create(void);
+int clslam_event_destroy(void* ev);
+int clslam_event_record(void* ev, void* stream);
+int clslam_event_elapsed_ms(void* ev0, void* ev1, float* ms);
 
 /* ---- input staging ------------------------------------------------------------------------
  * (x - 0.45) / 0.225 of networks/resnet_encoder.py:117 fused with NCHW -> NHWC and channel
@@ -327,6 +334,11 @@ int clslam_loss_finalize(const clslam_loss_args* a, void* stream);
  * smoothness terms, times sigmoid'; writes dz of dispconv_s (b,1,h>>s,w>>s). */
 int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* smooth_grad, int b_global,
                      int has_sample0, int b, int h, int w, int scale, float* dz_disp, void* stream);
+
+/* depth = disp_to_depth(disp) (depth_pose_prediction/utils.py:120-142) elementwise over n values; depth_mode as in
+ * clslam_photo_args (CLSLAM_DEPTH_*).  Used by the depth-only inference path (predict_from_image, :538-554). */
+int clslam_disp_to_depth(const float* disp, float* depth, long long n, int depth_mode, float min_depth, float max_depth,
+                         void* stream);
 
 /* ---- optimiser ----------------------------------------------------------------------------
  * torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as built at

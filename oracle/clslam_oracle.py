@@ -185,7 +185,7 @@ def rodrigues(aa: Tensor) -> Tensor:
         [x * (y * big_c) + z * s, y * (y * big_c) + c, y * (z * big_c) - x * s],
         [z * (x * big_c) - y * s, y * (z * big_c) + x * s, z * (z * big_c) + c],
     ]
-    rot = torch.zeros(aa.shape[0], 4, 4, dtype=aa.dtype)
+    rot = torch.zeros(aa.shape[0], 4, 4, dtype=aa.dtype, device=aa.device)
     for r in range(3):
         for col in range(3):
             rot[:, r, col] = rows[r][col].reshape(-1)
@@ -200,7 +200,7 @@ def se3_from_params(aa: Tensor, t: Tensor, invert: bool) -> Tensor:
     if invert:
         rot = rot.transpose(1, 2)
         tv = -tv
-    trans = torch.eye(4, dtype=aa.dtype).repeat(aa.shape[0], 1, 1)
+    trans = torch.eye(4, dtype=aa.dtype, device=aa.device).repeat(aa.shape[0], 1, 1)
     trans = trans.clone()
     trans[:, :3, 3] = tv
     return rot @ trans if invert else trans @ rot
@@ -219,11 +219,12 @@ def disp_to_depth(disp: Tensor, min_depth: Optional[float], max_depth: Optional[
 def reproject_grid(depth: Tensor, k: Tensor, inv_k: Tensor, cam_t: Tensor) -> Tensor:
     """networks/layers.py:74-79 + :93-104 -> normalised sampling grid (B,H,W,2)."""
     b, _, h, w = depth.shape
-    vs, us = torch.meshgrid(torch.arange(h, dtype=depth.dtype), torch.arange(w, dtype=depth.dtype),
+    dev = depth.device
+    vs, us = torch.meshgrid(torch.arange(h, dtype=depth.dtype, device=dev), torch.arange(w, dtype=depth.dtype, device=dev),
                             indexing='ij')
-    pix = torch.stack([us.reshape(-1), vs.reshape(-1), torch.ones(h * w, dtype=depth.dtype)], 0)
+    pix = torch.stack([us.reshape(-1), vs.reshape(-1), torch.ones(h * w, dtype=depth.dtype, device=dev)], 0)
     rays = inv_k[:, :3, :3] @ pix.unsqueeze(0).expand(b, -1, -1)
-    pts = torch.cat([depth.view(b, 1, -1) * rays, torch.ones(b, 1, h * w, dtype=depth.dtype)], 1)
+    pts = torch.cat([depth.view(b, 1, -1) * rays, torch.ones(b, 1, h * w, dtype=depth.dtype, device=dev)], 1)
     proj = (k @ cam_t)[:, :3, :] @ pts
     uv = proj[:, :2, :] / (proj[:, 2:3, :] + 1e-7)
     uv = uv.view(b, 2, h, w).permute(0, 2, 3, 1)
@@ -323,13 +324,14 @@ def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg
     outputs.update(predict_poses(params, batch))
 
     bsz = outputs[('disp', cfg.scales[0])].shape[0]
-    if sample_weights is None:
-        sample_weights = torch.ones(cfg.batch_size) / cfg.batch_size
-    k, inv_k = batch[('camera_matrix', 0)], batch[('inv_camera_matrix', 0)]
     target = batch[('rgb', 0, 0)]
+    dev = target.device          # 'cpu' for the checker; 'cuda' only in bench.py's stock-PyTorch-on-GPU baseline leg
+    if sample_weights is None:
+        sample_weights = torch.ones(cfg.batch_size, device=dev) / cfg.batch_size
+    k, inv_k = batch[('camera_matrix', 0)], batch[('inv_camera_matrix', 0)]
 
     losses: Dict[str, Tensor] = {}
-    total = torch.zeros(1)
+    total = torch.zeros(1, device=dev)
     for si, s in enumerate(cfg.scales):
         disp_full = F.interpolate(outputs[('disp', s)], [h, w], mode='bilinear', align_corners=False)
         depth = disp_to_depth(disp_full, cfg.min_depth, cfg.max_depth)
@@ -348,7 +350,7 @@ def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg
         disp = outputs[('disp', s)]
         norm_disp = disp / (disp.mean(2, True).mean(3, True) + 1e-7)
         if not with_smooth:
-            smooth = torch.zeros(())
+            smooth = torch.zeros((), device=dev)
         elif cfg.smooth_mode == 'reference':
             sw = sample_weights if smooth_weights is None else smooth_weights
             smooth = (smoothness_reference_quirk(norm_disp, batch[('rgb', 0, s)], sw.numel()) * sw).sum()
@@ -362,7 +364,7 @@ def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg
     total = total / len(cfg.scales)
 
     if cfg.velocity_loss_scaling is not None and cfg.velocity_loss_scaling > 0:
-        vel = torch.zeros(bsz)
+        vel = torch.zeros(bsz, device=dev)
         for f_dist, f_pose in ((0, -1), (1, 1)):      # depth_pose_prediction.py:1133-1144
             gt = batch[('relative_distance', f_dist)].abs().reshape(-1)
             pred = torch.linalg.norm(outputs[('translation', 0, f_pose)], dim=-1).reshape(-1)
@@ -416,21 +418,36 @@ class OracleAdapter:
 
 
 def time_adapt_steps(batch_size: int, height: int, width: int, steps: int, warmup: int,
-                     threads: Optional[int] = None) -> Dict[str, float]:
-    """CPU baseline leg of bench.py: the oracle's adapt step (fwd+loss+bwd+Adam) timed with
-    perf_counter on the host cores.  Returns seconds per step (median, best) and threads."""
+                     threads: Optional[int] = None, device: str = 'cpu', allow_tf32: Optional[bool] = None) -> Dict[str, float]:
+    """Baseline legs of bench.py: the oracle's adapt step (fwd+loss+bwd+Adam) timed with perf_counter.  device='cpu': the
+    reference algorithm on the host cores.  device='cuda': the same stock-PyTorch graph dispatched to cuDNN / ATen on the
+    GPU ("the existing Blackwell path to beat"), with TF32 convolutions on or off.  Returns seconds
+    per step (median, best) and threads."""
     if threads is not None:
         torch.set_num_threads(threads)
     cfg = OracleConfig(height, width, batch_size)
-    adapter = OracleAdapter(make_params(0), cfg)
+    params = make_params(0)
     batch = make_batch(batch_size, height, width, seed=1)
     noise = make_noise(batch_size, height, width, seed=1)
+    cuda = device != 'cpu'
+    if cuda:
+        params = {n: {k: v.to(device) for k, v in sd.items()} for n, sd in params.items()}
+        batch = {k: v.to(device) for k, v in batch.items()}
+        noise = [n.to(device) for n in noise]
+        if allow_tf32 is not None:
+            torch.backends.cudnn.allow_tf32 = allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = allow_tf32
+    adapter = OracleAdapter(params, cfg)
     for _ in range(warmup):
         adapter.step(batch, noise)
     times = []
     for _ in range(steps):
+        if cuda:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
-        adapter.step(batch, noise)
+        adapter.step(batch, noise)          # ends with float(loss): one device sync per step, like :1115
+        if cuda:
+            torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     times.sort()
     return {'median_s': times[len(times) // 2], 'best_s': times[0],

@@ -97,11 +97,56 @@ def test_every_public_method_of_the_reference_exists(ref):
     assert not missing, missing
     pred = DepthPosePrediction(*_our_cfg(), device=torch.device('cpu'))
     for name, args in (('validate', ()), ('compute_depth_error', ()), ('compute_pose_error', ()), ('save_prediction', ({}, {})),
-                       ('train', ()), ('load_online_model', ())):
+                       ('train', ())):
         with pytest.raises(NotImplementedError):
             getattr(pred, name)(*args)
     with pytest.raises(RuntimeError, match='no CPU fallback'):          # the compute entry points need the GPU
         pred.predict_from_image(torch.zeros(1, 3, 64, 96))
+
+
+def test_use_online_second_network_copy(ref, tmp_path):
+    """use_online=True (:139-152, :206-207): a second copy of the four networks with its own Adam; load_online_model
+    (:751-792) fills it from a checkpoint written by save_model; without use_online the dict is empty, as in the reference"""
+    from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
+    Dataset, Cfg, RefPred = ref
+    dev = torch.device('cpu')
+    plain = DepthPosePrediction(*_our_cfg(), device=dev)
+    assert plain.online_models == {} and plain.online_optimizer is None
+    with pytest.raises(KeyError):          # the reference indexes the empty dict (:931)
+        plain._process_batch({('rgb_aug', 0, 0): torch.zeros(1, 3, 64, 96)}, use_online=True)
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), Config(batch_size=1, log_path=tmp_path), use_online=True, device=dev)
+    assert list(pred.online_models) == list(pred.models)
+    for name in pred.models:
+        a, b = pred.models[name].state_dict(), pred.online_models[name].state_dict()
+        assert list(a) == list(b) and all(a[k].shape == b[k].shape for k in a)
+        assert all(pa is not pb for pa, pb in zip(pred.models[name].parameters(), pred.online_models[name].parameters()))
+    assert pred.online_optimizer is not pred.optimizer
+    assert len(pred.online_parameters_to_train) == len(pred.parameters_to_train)
+    # checkpoint of the main networks -> online copy
+    pred.save_model()
+    pred.load_weights_folder = tmp_path / 'models' / 'weights_000'
+    pred.load_online_model(load_optimizer=True)
+    for name in pred.models:
+        a, b = pred.models[name].state_dict(), pred.online_models[name].state_dict()
+        assert all(torch.equal(a[k], b[k]) for k in a), name
+    # _set_adapt freezes both copies (:813-827)
+    pred._set_adapt(True)
+    assert not any(p.requires_grad for p in pred.online_models['depth_encoder'].parameters())
+    assert all(p.requires_grad for p in pred.online_models['depth_decoder'].parameters())
+
+
+def test_decoder_parameters_cannot_be_detached_from_the_flat_buffer():
+    """model.to(same device) is a no-op like in the reference (:186); a real move / cast is refused loudly"""
+    from clslam_b200 import DepthPosePrediction
+    pred = DepthPosePrediction(*_our_cfg(), device=torch.device('cpu'))
+    ptr = pred.models['depth_decoder'].upconv_4_0.conv.conv.weight.data_ptr()
+    pred.models['depth_decoder'].to(torch.device('cpu'))
+    pred.models['pose_decoder'].float()
+    assert pred.models['depth_decoder'].upconv_4_0.conv.conv.weight.data_ptr() == ptr
+    with pytest.raises(RuntimeError, match='flat parameter buffer'):
+        pred.models['depth_decoder'].half()
+    with pytest.raises(RuntimeError, match='flat parameter buffer'):
+        pred.models['pose_decoder'].double()
 
 
 def _our_cfg():

@@ -54,10 +54,12 @@ def test_plan_builds_and_is_consistent(b, h, w):
     assert sum(n.endswith('.wgrad') for n in names) == 18
     k = kinds(eng)
     if (b, h, w) == (8, 192, 640):
-        # batch 8: every 3x3 / 7x7 / stride-2 convolution runs the TMA kernels; 1x1 convolutions stay on the gather kernel
-        # (conv1 + 16 3x3 convs) per encoder, 10 decoder + 2 pose-decoder convs, 9 + 2 dgrads
-        assert k['conv_tma'] == 2 * 17 + 10 + 2 + 9 + 2
+        # batch 8: every convolution except the 12-channel pose_2 runs the TMA kernels: (conv1 + 16 3x3 convs + 3 down-sampling
+        # 1x1 convs) per encoder, 10 decoder + 3 pose-decoder convs (squeeze as a one-tap launch), 9 + 2 dgrads
+        assert k['conv_tma'] == 2 * 20 + 10 + 3 + 9 + 2
         assert k['wgrad_tma'] == 12
-        assert k['gather'] <= 2 * 3 + 2 + 3 + 2 + 3               # downsample 1x1, squeeze / pose_2 (+ wgrad / dgrad)
-    if (b, h, w) == (2, 64, 96):
-        assert k.get('conv_tma', 0) == 0 or k['gather'] > 0       # tiny maps: mostly gather kernels
+        assert k['gather'] == 4                                   # pose_2 fwd / wgrad / dgrad and the squeeze wgrad (1x1)
+    if (b, h, w) == (1, 192, 640):
+        # batch 1: the same forward / dgrad plan (small maps in the split-K form); the weight gradients of the small-map
+        # layers stay on the gather kernel (measured faster at batch 1, profiles/r02_ab_summary.txt)
+        assert k['conv_tma'] == 64 and k['gather'] == 11 and k['wgrad_tma'] == 5

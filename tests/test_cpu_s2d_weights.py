@@ -54,8 +54,13 @@ def test_tma_eligibility_rule(monkeypatch):
         def clslam_get_conv_mode(self):
             return 1
     monkeypatch.setattr(eng.L, 'load', lambda: FakeLib())
+    monkeypatch.setattr(eng, 'TMA_SPLITK', False)
     assert tma_ok(8, 6, 20, 512, 512)            # 8 images x 1 x 3 tiles = 24
     assert not tma_ok(1, 24, 80, 128, 128)       # 20 tiles: gather kernels (split-K) instead
+    monkeypatch.setattr(eng, 'TMA_SPLITK', True)
+    assert tma_ok(1, 24, 80, 128, 128)           # default plan: the split-K form of the TMA kernel takes the small maps
+    assert not tma_ok(1, 24, 80, 32, 32)         # ... built for 64-multiple channels only
+    monkeypatch.setattr(eng, 'TMA_SPLITK', False)
     assert tma_ok(1, 48, 160, 64, 64)
     assert not tma_ok(8, 48, 160, 60, 64)        # channels must be multiples of 16
     assert not tma_ok(8, 48, 160, 64, 192)       # cout must be a multiple of its N block (128)

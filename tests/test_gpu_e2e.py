@@ -156,7 +156,10 @@ def test_inference_only_adapt_and_checkpoint_roundtrip(tmp_path):
     folder = tmp_path / 'models' / 'weights_000'
     for n in orc.NET_NAMES:
         sd = torch.load(folder / f'{n}.pth', map_location='cpu')
-        assert list(sd.keys()) == [k for k, _, _ in orc.net_layouts()[n]]
+        extra = ['height', 'width'] if 'encoder' in n else []          # written by the reference's save_model (:684-688)
+        assert list(sd.keys()) == [k for k, _, _ in orc.net_layouts()[n]] + extra
+        if extra:
+            assert sd['height'].shape == (h,) and sd['width'].shape == (w,)
         assert all(v.is_contiguous() for v in sd.values())
     cfg = Config(batch_size=b, max_depth=max_depth, load_weights_folder=folder)
     pred2 = DepthPosePrediction(DatasetConfig(height=h, width=w), cfg)
@@ -166,3 +169,79 @@ def test_inference_only_adapt_and_checkpoint_roundtrip(tmp_path):
     o2, l2 = pred2.adapt(dict(batch), dict(batch), steps=1)
     assert float(l1['loss']) == float(l2['loss'])
     assert torch.equal(pred._flat.params, pred2._flat.params)
+
+
+def test_outputs_are_fresh_tensors_per_call():
+    """the reference returns new tensors from every call; a caller that keeps outputs across two calls (logger, replay
+    buffer) must not see them overwritten.  copy_outputs=False opts into views of the static buffers."""
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build('small_b2')
+    out1, _ = pred.adapt(dict(batch), None)
+    keep = {k: v.clone() for k, v in out1.items()}
+    other = orc.make_batch(b, h, w, seed=99, coherent=True)
+    out2, _ = pred.adapt(dict(other), dict(other), steps=1)
+    torch.cuda.synchronize()
+    for k in keep:
+        assert torch.equal(out1[k], keep[k]), k
+        assert out1[k].data_ptr() != out2[k].data_ptr(), k
+    assert not torch.equal(out1[('disp', 0)], out2[('disp', 0)])
+    # the staged dict keeps the caller's shapes and dtypes (:916-917 is a plain .to(device))
+    staged = dict(batch)
+    pred.adapt(staged, None)
+    for k, v in batch.items():
+        assert staged[k].is_cuda and staged[k].shape == v.shape and staged[k].dtype == v.dtype, k
+    fast = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b), copy_outputs=False)
+    for n in orc.NET_NAMES:
+        fast.models[n].load_state_dict(params[n])
+    fast.noise_provider = pred.noise_provider
+    o1, _ = fast.adapt(dict(batch), None)
+    assert o1[('disp', 0)].data_ptr() == fast._engines[b].disp[0].data_ptr()
+    assert rel(o1[('disp', 0)].cpu().numpy(), rec['disp_0']) < REL_TOL
+
+
+@pytest.mark.parametrize('n,h,w', [(1, 64, 96), (2, 96, 160), (1, 192, 640)])
+def test_predict_from_image_depth_only_path(n, h, w):
+    """predict_from_image(s) (:538-626) on the depth-only plan: any (n, H, W) with H, W % 32 == 0, independent of the
+    predictor's configured size, against the oracle's encoder -> decoder -> disp_to_depth; the adaptation engine's state
+    (outputs a caller may still hold, Adam) is untouched"""
+    rec, pred, params, batch, noise, (b, h0, w0, max_depth) = build('small_b2')
+    pred.is_trained = True
+    out_before, _ = pred.adapt(dict(batch), None)
+    keep = out_before[('depth', 0)].clone()
+    img = torch.rand(n, 3, h, w, generator=torch.Generator().manual_seed(5))
+    depth = pred.predict_from_image(img, as_numpy=False)
+    assert depth.shape == (n, 1, h, w) and depth.is_cuda
+    with torch.no_grad():
+        feats = orc.encoder_forward(params['depth_encoder'], img)
+        disp = orc.depth_decoder_forward(params['depth_decoder'], feats)[('disp', 0)]
+        ref = orc.disp_to_depth(disp, 0.1, max_depth)
+    assert rel(depth.cpu().numpy(), ref.numpy()) < REL_TOL
+    assert torch.equal(out_before[('depth', 0)], keep)
+    got = pred.predict_from_image(img[0], as_numpy=True)             # 3-d input, numpy out (:552-553)
+    assert got.shape == (h, w)
+    d0, d1, tr = pred.predict_from_images(img[:1], img[-1:], as_numpy=True)
+    assert d0.shape == (h, w) and tr.shape == (4, 4)
+    ref_tr = orc.predict_pose(params, img[:1], img[-1:]).numpy()
+    assert rel(tr, ref_tr) < REL_TOL
+
+
+def test_use_online_network_copy_runs_on_its_own_weights():
+    """use_online=True (:139-152): _process_batch / predict_pose(use_online=True) evaluate the second copy of the networks"""
+    rec, pred0, params, batch, noise, (b, h, w, max_depth) = build('small_b2')
+    pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b, max_depth=max_depth), use_online=True)
+    other = orc.make_params(1)
+    for n in orc.NET_NAMES:
+        pred.models[n].load_state_dict(other[n])              # main copy: different weights
+        pred.online_models[n].load_state_dict(params[n])      # online copy: the fixture's weights
+    pred.noise_provider = lambda s, shape: noise[s]
+    pred.is_trained = True
+    pred._set_eval()
+    with torch.no_grad():
+        outputs, losses = pred._process_batch(dict(batch), use_online=True)
+        out_main, losses_main = pred._process_batch(dict(batch), use_online=False)
+    assert rel(outputs[('disp', 0)].cpu().numpy(), rec['disp_0']) < REL_TOL
+    np.testing.assert_allclose(losses['loss'].cpu().numpy(), rec['loss:loss'], rtol=1e-4)
+    assert rel(out_main[('disp', 0)].cpu().numpy(), rec['disp_0']) > 1e-2
+    tr, _ = pred.predict_pose(batch[('rgb', 0, 0)][0], batch[('rgb', 1, 0)][0], as_numpy=True, use_online=True)
+    assert rel(tr, rec['predict_pose']) < REL_TOL
+    tr_main, _ = pred.predict_pose(batch[('rgb', 0, 0)][0], batch[('rgb', 1, 0)][0], as_numpy=True)
+    assert rel(tr_main, rec['predict_pose']) > 1e-3
