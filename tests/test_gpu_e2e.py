@@ -60,7 +60,11 @@ def test_process_batch_matches_reference(name):
     record_achieved(name, err)
     assert max(err['disp']) < REL_TOL and max(err['depth']) < REL_TOL, err
     assert max(err['axis_angle'], err['translation'], err['cam_T_cam']) < REL_TOL, err
-    assert max(err['rgb']) < 5e-4, err        # warped images: see DESIGN.md section 2 (coordinate sensitivity of the bilinear sample)
+    # warped images: a bilinear sample moves by (coordinate error) x (local image gradient).  Measured on a B200 (round 2,
+    # profiles/r02_parity_achieved.jsonl): <= 3.3e-5 on every fixture with temporally coherent frames; 1.7e-4 on full_b1, whose
+    # frames are independent white noise (pixel-to-pixel contrast ~1, coordinates up to 640: 1e-7 relative in the
+    # coordinate is 6e-5 px).  disp / depth / pose are <= 1e-5 / 1e-5 / 7e-5 on all of them.
+    assert max(err['rgb']) < (3e-4 if name == 'full_b1' else 1e-4), err
     keys = [k[5:] for k in rec.files if k.startswith('loss:')]
     assert set(keys) == set(losses.keys()) and len(losses) == 19
     assert losses['depth_loss'] is losses['loss'] and losses['loss'].shape == (1,)

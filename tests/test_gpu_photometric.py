@@ -146,7 +146,20 @@ def test_photo_fwd_bwd(b, h, w, max_depth):
         assert float(((g_got - g_ref) * ok).abs().max() / g_ref.abs().max()) < 2e-3, f'd(loss)/d(disp_full) scale {s}'
     dproj_ref = pr['proj'].grad.reshape(2, b, 12)
     dproj_got = dproj.sum(0).cpu().double()
-    assert cabi.rel_err(dproj_got, dproj_ref) < 3e-2      # includes the contribution of (rounding-level) argmin flips
+    err_dproj = cabi.rel_err(dproj_got, dproj_ref)
+    n_flips = int(sum((bufs['argmin'][s].cpu().long() != ref['argmin'][s]).sum() for s in range(4)))
+    try:          # the achieved number, for DESIGN.md section 2 (gpurun_out/ travels back from the GPU box)
+        import json
+        from pathlib import Path
+        out = Path(__file__).resolve().parent.parent / 'gpurun_out'
+        out.mkdir(exist_ok=True)
+        with open(out / 'parity_achieved.jsonl', 'a') as fh:
+            fh.write(json.dumps({'case': f'photometric_op b={b} {h}x{w}', 'dproj': err_dproj, 'argmin_flips': n_flips}) + '\n')
+    except OSError:
+        pass
+    # the 12 projection gradients are sums over all pixels, so every (rounding-level) argmin flip enters: one flipped pixel
+    # moves a sum of ~h*w terms of alternating sign by one term
+    assert err_dproj < (3e-2 if n_flips else 2e-3)
 
 
 @pytest.mark.parametrize('b,bg,has0,h,w', [(2, 2, 1, 32, 64), (3, 6, 1, 64, 96), (2, 4, 0, 32, 64)])

@@ -23,7 +23,7 @@ REL_TOL = 1e-4          # north_star: disparity and pose within 1e-4 relative of
 NAMES = ['small_b4_replay', 'small_b8_replay', 'full_b8_replay', 'hires_b8_replay', 'hires_b1']
 
 
-WARP_TOL = 1e-3
+WARP_TOL = 1e-4          # measured <= 3.3e-5 on these fixtures (profiles/r02_parity_achieved.jsonl)
 
 
 def record_achieved(name, err):
@@ -64,9 +64,7 @@ def test_replay_batch_outputs_losses_gradients(name):
     assert max(err['disp']) < REL_TOL and max(err['depth']) < REL_TOL, err
     assert max(err['axis_angle'], err['translation'], err['cam_T_cam']) < REL_TOL, err
     assert err['means'] < REL_TOL, err
-    # warped images: per-sample K / inv_K enter here; a sampling coordinate off by 1e-4 relative (= 0.06 px at x = 600)
-    # moves a bilinear sample of white-noise-like replay images by up to that fraction of the local contrast
-    assert max(err['rgb']) < WARP_TOL, err
+    assert max(err['rgb']) < WARP_TOL, err          # warped images: per-sample K / inv_K enter here
     keys = [k[5:] for k in rec.files if k.startswith('loss:')]
     assert set(keys) == set(losses.keys())
     for k in keys:
