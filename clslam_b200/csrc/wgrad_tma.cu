@@ -209,18 +209,20 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 }
 
 // dW[co][r][s][ci] = sum over splits of ws[(cb, chunk, split)][r * CC + ci % CC][s * CO + co % CO]
-// ... and db[o] = sum over the bias_grad_partial blocks (threads past the dW range)
+// ... and db[o] = sum over the bias_grad_partial blocks (the blocks past the dW tiles)
+// One block = one tap x 32 output channels x 32 input channels: the partial sums are read along co (contiguous in the
+// workspace), transposed through shared memory and written along ci (contiguous in dW).  The round-1 kernel wrote dW with a
+// 9 * ci * 4-byte stride between neighbouring threads (one 32-byte sector per element).
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co, int ci, int cc, int cob, int ci_chunks, int splits,
-                    const float* __restrict__ bias_part, int bias_blocks, float* __restrict__ db) {
+                    const float* __restrict__ bias_part, int bias_blocks, float* __restrict__ db, int tiles_o, int tiles_c) {
   pdl_wait();
   pdl_trigger();
-  const int cols = 3 * cob;
-  const size_t cta_stride = (size_t)(3 * cc) * cols;
-  const int total = co * 9 * ci;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total + (db ? co : 0); i += gridDim.x * blockDim.x) {
-    if (i >= total) {
-      const int o = i - total;
+  __shared__ float tile[32][33];
+  const int n_tiles = 9 * tiles_o * tiles_c;
+  if ((int)blockIdx.x >= n_tiles) {          // bias blocks: fixed-order sum of the per-block channel sums
+    const int o = ((int)blockIdx.x - n_tiles) * 256 + threadIdx.x;
+    if (db && o < co) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int b = 0;
       for (; b + 4 <= bias_blocks; b += 4) {
@@ -229,22 +231,41 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
       }
       for (; b < bias_blocks; ++b) a0 += bias_part[(size_t)b * co + o];
       db[o] = (a0 + a1) + (a2 + a3);
-      continue;
     }
-    // work order (tap, ci, co) with co fastest: neighbouring threads read neighbouring workspace columns
-    const int o = i % co, c = (i / co) % ci, tap = i / (co * ci);
-    const int r = tap / 3, s = tap - r * 3;
-    const int pair = (o / cob) * ci_chunks + c / cc;
-    const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
-    // fixed summation order (deterministic), four independent chains so the loads overlap
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int k = 0;
-    for (; k + 4 <= splits; k += 4) {
-      a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride];
-      a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
+    return;
+  }
+  const int cols = 3 * cob;
+  const size_t cta_stride = (size_t)(3 * cc) * cols;
+  const int t = blockIdx.x;
+  const int tc = t % tiles_c, to = (t / tiles_c) % tiles_o, tap = t / (tiles_c * tiles_o);
+  const int r = tap / 3, s = tap - r * 3;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int o = to * 32 + tx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int cl = ty + 8 * j, c = tc * 32 + cl;
+    float v = 0.f;
+    if (o < co && c < ci) {
+      const int pair = (o / cob) * ci_chunks + c / cc;
+      const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
+      // fixed summation order (deterministic), four independent chains so the loads overlap
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 4 <= splits; k += 4) {
+        a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride];
+        a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
+      }
+      for (; k < splits; ++k) a0 += p[(size_t)k * cta_stride];
+      v = (a0 + a1) + (a2 + a3);
     }
-    for (; k < splits; ++k) a0 += p[(size_t)k * cta_stride];
-    dw[((size_t)o * 9 + tap) * ci + c] = (a0 + a1) + (a2 + a3);
+    tile[cl][tx] = v;
+  }
+  __syncthreads();
+  const int c = tc * 32 + tx;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int ol = ty + 8 * j, oo = to * 32 + ol;
+    if (oo < co && c < ci) dw[((size_t)oo * 9 + tap) * ci + c] = tile[tx][ol];
   }
 }
 
@@ -407,11 +428,10 @@ int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_plane
     launch_k(bias_grad_partial_kernel, dim3(kBiasBlocks), dim3(256), 0, st, dz_f32, pixels, dz->c, bias_part);
     if ((rc = finish_launch("bias_grad"))) return rc;
   }
-  const int total = dz->c * 9 * x->c + (db ? dz->c : 0);
-  int blocks = (total + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  const int tiles_o = (dz->c + 31) / 32, tiles_c = (x->c + 31) / 32;
+  const int blocks = 9 * tiles_o * tiles_c + (db ? (dz->c + 255) / 256 : 0);
   launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, g.ws, dw, dz->c, x->c, p.cc, p.cob, p.ci_chunks, p.splits,
-           (const float*)bias_part, (int)kBiasBlocks, db);
+           (const float*)bias_part, (int)kBiasBlocks, db, tiles_o, tiles_c);
   return finish_launch("wgrad_reduce");
 }
 

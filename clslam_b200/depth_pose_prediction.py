@@ -11,6 +11,7 @@ extension is missing.
 """
 from __future__ import annotations
 
+import os
 import shutil
 import warnings
 from pathlib import Path
@@ -23,6 +24,10 @@ from . import _lib as L
 from .engine import H2D_OVERLAP, AdaptEngine, DepthRunner, EncoderRunner, Plan, PreparedEncoder, _p
 from .networks import DepthDecoder, FlatParams, PoseDecoder, ResnetEncoder
 from .sharding import global_sample_weights, shard_range
+
+# data-parallel: all-reduce the gradients in buckets inside the step graph, overlapped with the backward pass (default);
+# CLSLAM_GRAD_BUCKETS=0 restores round 1's graph -> eager all-reduce of the whole buffer -> graph
+GRAD_BUCKETS = os.environ.get('CLSLAM_GRAD_BUCKETS', '1') == '1'
 
 LOSS_SLOTS = {'reprojection_loss': 0, 'smooth_loss': 4, 'reg_loss': 8, 'depth_loss': 12}
 
@@ -343,7 +348,8 @@ class DepthPosePrediction:
                               depth_prep=dp, pose_prep=pp, flat=ns.flat, min_depth=self.min_depth,
                               max_depth=self.max_depth, disparity_smoothness=self.disparity_smoothness,
                               velocity_loss_scaling=self.velocity_loss_scaling, device=self.device,
-                              emit_outputs=self.emit_outputs)
+                              emit_outputs=self.emit_outputs,
+                              grad_allreduce=self._allreduce_tensor if (self.world > 1 and GRAD_BUCKETS) else None)
             eng.net_set = ns
             ns.engines[batch] = eng
         return eng
@@ -529,12 +535,18 @@ class DepthPosePrediction:
         of :312 with the encoders frozen) followed by the data-parallel all-reduce."""
         eng = inputs_engine or self._last_engine
         eng.backward()
-        self._allreduce_grads()
+        self._allreduce_grads(eng)
 
-    def _allreduce_grads(self) -> None:
-        if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self._flat.grads)            # the single exchange step (NCCL over NVLink)
+    @staticmethod
+    def _allreduce_tensor(t: Tensor) -> None:
+        import torch.distributed as dist
+        dist.all_reduce(t)                               # SUM over the replicas (NCCL over NVLink / NVSwitch)
+
+    def _allreduce_grads(self, eng: Optional[AdaptEngine] = None) -> None:
+        """the exchange step of the data-parallel path.  With bucketed synchronisation (default) the engine's backward plan
+        has already issued it, bucket by bucket, overlapped with the remaining weight-gradient kernels."""
+        if self.world > 1 and not (eng is not None and eng.grad_sync_in_plan):
+            self._allreduce_tensor(self._flat.grads)
 
     def gradients(self) -> Dict[Tuple[str, str], Tensor]:
         return self._flat.named_gradients()
@@ -553,7 +565,7 @@ class DepthPosePrediction:
         if not self.use_cuda_graph or n_run == 0:       # first step eager: loads every kernel before capture
             if late_event is not None:
                 torch.cuda.current_stream(self.device).wait_event(late_event)
-            eng.forward_backward(); self._allreduce_grads(); eng.adam(lr)
+            eng.forward_backward(); self._allreduce_grads(eng); eng.adam(lr)
             return
         if self.world == 1 and H2D_OVERLAP and late_event is not None:
             # two graphs: the networks (need rgb_aug / intrinsics only) run while the photometric inputs are still in flight
@@ -575,7 +587,8 @@ class DepthPosePrediction:
                 torch.cuda.current_stream(self.device).wait_event(late_event)
             graphs[kb].replay()
             return
-        if self.world == 1:
+        if self.world == 1 or eng.grad_sync_in_plan:
+            # one graph: forward, backward (data-parallel: with the bucketed NCCL all-reduces inside), Adam
             key = (eng.b, 'step', lr)
             g = graphs.get(key)
             if g is None:
@@ -595,7 +608,7 @@ class DepthPosePrediction:
                     eng.adam(lr)
                 graphs[k1], graphs[k2] = g1, g2
             graphs[k1].replay()
-            self._allreduce_grads()
+            self._allreduce_grads(eng)
             graphs[k2].replay()
 
     # ------------------------------------------------------------------------------------------

@@ -225,6 +225,11 @@ class Plan:
     def wait(self, event: str) -> None:
         self.ops.append(('__wait__', None, (event,), self.lane))
 
+    def call(self, name: str, fn) -> None:
+        """a host callable issued with the lane's stream as torch's current stream (the NCCL all-reduce of a gradient
+        bucket: graph-capturable, stream-ordered, not one of this library's kernels)"""
+        self.ops.append(('__py__', None, (fn, name), self.lane))
+
     def fork(self, lanes=(1, 2)) -> None:
         """side lanes start after everything issued on lane 0 so far"""
         self._n_marks += 1
@@ -351,13 +356,14 @@ class Plan:
     def finalize(self) -> None:
         lanes = sorted({op[3] for op in self.ops})
         n = (max(lanes) + 1) if lanes else 1
-        self._ws = [torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=self.device) for _ in range(n)]
+        busy = {op[3] for op in self.ops if op[1] is not None}          # lanes that launch kernels need a workspace
+        self._ws = [torch.empty(max(self.ws_bytes, 16) if ln in busy else 16, dtype=torch.uint8, device=self.device) for ln in range(n)]
         self._ws_ptr = [t.data_ptr() for t in self._ws]
         if torch.device(self.device).type != 'cuda':
             return          # a plan built on the CPU can be inspected (tests of the wiring) but not run
         self._side = [torch.cuda.Stream(device=self.device) for _ in range(n - 1)]
         for name, fn, args, lane in self.ops:
-            if fn is None and args[0] not in self._events:
+            if fn is None and name != '__py__' and args[0] not in self._events:
                 self._events[args[0]] = torch.cuda.Event()
 
     def run(self, first: int = 0, last: Optional[int] = None, serial: bool = False, timed: bool = False) -> None:
@@ -366,6 +372,10 @@ class Plan:
         ptrs = [st.cuda_stream for st in streams]
         for i, (name, fn, args, lane) in enumerate(self.ops[first:last], start=first):
             if fn is None:
+                if name == '__py__':
+                    with torch.cuda.stream(streams[lane]):
+                        args[0]()
+                    continue
                 if serial:
                     continue
                 if name == '__record__':
@@ -628,7 +638,10 @@ class AdaptEngine:
     def __init__(self, *, batch: int, height: int, width: int, batch_global: int, has_sample0: bool,
                  depth_prep: PreparedEncoder, pose_prep: PreparedEncoder, flat: FlatParams,
                  min_depth: Optional[float], max_depth: Optional[float], disparity_smoothness: float,
-                 velocity_loss_scaling: Optional[float], device, emit_outputs: bool = True):
+                 velocity_loss_scaling: Optional[float], device, emit_outputs: bool = True, grad_allreduce=None):
+        """``grad_allreduce(tensor)``: data-parallel runs pass the SUM all-reduce of a slice of the flat gradient buffer; the
+        backward plan then issues it per bucket on a communication lane as soon as the bucket's weight gradients exist
+        (pose decoder first, ``upconv_4_*`` -- 53 % of the bytes -- last), inside the step graph."""
         if height % 32 or width % 32:
             raise ValueError('height and width must be multiples of 32 (ResNet-18 / 4-scale pyramid)')
         self.b, self.h, self.w = batch, height, width
@@ -861,6 +874,23 @@ class AdaptEngine:
         #      lane 1 = pose branch, lane 2 = weight gradients of the depth decoder ----------------
         plan.add('photo_bwd', lambda stream, ws: lib.clslam_photo_bwd(ctypes.byref(pa), stream))
         plan.fork((1, 2))
+        self.grad_sync_in_plan = grad_allreduce is not None
+        COMM = 3                             # communication lane (data-parallel only)
+
+        def sync_bucket(name, first_key, last_key, *ready_events):
+            """all-reduce flat.grads[first_key .. last_key] on the communication lane once the `ready_events` have fired"""
+            if grad_allreduce is None:
+                return
+            lo = flat.index[first_key]['w_off']
+            li = flat.index[last_key]
+            hi = li['b_off'] + (li['co'] + 63) // 64 * 64
+            view = flat.grads[lo:hi]
+            back = plan.lane
+            plan.set_lane(COMM)
+            for ev in ready_events:
+                plan.wait(ev)
+            plan.call(f'allreduce.{name}', lambda v=view: grad_allreduce(v))
+            plan.set_lane(back)
         self.dz_disp = {}
         plan.wait('lossfin')                 # smooth_grad (lane 0 and, through the fork above, lanes 1 / 2 follow loss_finalize)
         for s in range(S):
@@ -896,6 +926,39 @@ class AdaptEngine:
         scratch_elems = max([b * (self.y[(i, 1)].shape[1] + 2) * (self.y[(i, 1)].shape[2] + 2) * DEC_CH[i] for i in range(5) if ud1[i]] +
                             [b * (self.y[(i, 0)].shape[1] + 2) * (self.y[(i, 0)].shape[2] + 2) * DEC_CH[i + 1] for i in range(4) if ud0[i]] + [4])
         dxp = plan.alloc(scratch_elems)
+        # pose branch first (short, independent of the depth branch): its gradient bucket heads the communication lane
+        plan.set_lane(1)
+        self.dz_pose = {name: plan.alloc(*self.pose_act[name].shape) for name in ('squeeze', 'pose_0', 'pose_1', 'pose_2')}
+        plan.simple('pose_head_bwd', lib.clslam_pose_head_bwd, _p(self.dproj_partials), S * self.n_tiles, _p(self.k_mat),
+                    _p(self.axis_angle), _p(self.translation), _p(self.rel_dist), _p(self.sample_w),
+                    self.vel_scale, b, hp, wp, self.invert_mask, _p(self.dz_pose['pose_2']))
+        prev = {'pose_2': 'pose_1', 'pose_1': 'pose_0', 'pose_0': 'squeeze'}
+        upd = tma_ok(2 * b, hp, wp, 256, 256, TMA_MIN_TILES_BWD)         # pose_1 / pose_0 dgrad (zero padding: one launch, act' fused as a gate)
+        dzp_pl = {name: PlaneBuf(plan, 2 * b, hp, wp, 256).view() for name in ('pose_1', 'pose_0')} if upd else {}
+        for name in ('pose_2', 'pose_1', 'pose_0', 'squeeze'):
+            d, xin = self.pose_desc[name]
+            if name in dzp_pl and self.pose_in_pl.get(name) is not None and (
+                    (not TMA_SPLITK) or TMA_SPLITK_WGRAD or tma_big(2 * b, hp, wp, TMA_MIN_TILES_BWD)):
+                plan.conv_wgrad_tma(f'{name}.wgrad', 2 * b, hp, wp, self.pose_in_pl[name], L.PAD_ZERO, dzp_pl[name], self.dz_pose[name],
+                                    flat.wgrad_ptr((pd, name)), flat.bgrad_ptr((pd, name)))
+            else:
+                plan.conv_wgrad(f'{name}.wgrad', d, xin, None, self.dz_pose[name], flat.wgrad_ptr((pd, name)),
+                                flat.bgrad_ptr((pd, name)))
+            if name in prev:
+                if upd and name in ('pose_1', 'pose_0'):
+                    wt_hi, wt_lo = self._wt_slot((pd, name), 256)
+                    plan.conv_tma(f'{name}.dgrad', dzp_pl[name], L.PAD_ZERO, 256, wt_hi, wt_lo, None, None, L.ACT_NONE,
+                                  y=self.dz_pose[prev[name]], out=dzp_pl.get(prev[name]), gate=self.pose_act[prev[name]],
+                                  gate_act=L.ACT_RELU)
+                else:
+                    plan.conv_dgrad(f'{name}.dgrad', d, self.dz_pose[name], flat.weight_ptr((pd, name)),
+                                    self.pose_act[prev[name]], L.ACT_RELU, None, None, self.dz_pose[prev[name]])
+                    if prev[name] in dzp_pl:
+                        plan.planes_from_f32(f'dz_{prev[name]}.planes', self.dz_pose[prev[name]], dzp_pl[prev[name]])
+        if grad_allreduce is not None:
+            plan.record('grads_pose')
+            sync_bucket('pose_decoder', (pd, 'squeeze'), (pd, 'pose_2'), 'grads_pose')
+        plan.set_lane(0)
         for i in range(0, 5):
             y1 = self.y[(i, 1)]
             hi_, wi_ = y1.shape[1], y1.shape[2]
@@ -906,6 +969,8 @@ class AdaptEngine:
                 plan.wait(f'dzd{i}')
                 plan.with_ws(f'dispconv_{i}.wgrad', lib.clslam_dispconv_wgrad, _p(y1), _p(self.dz_disp[i]),
                              flat.wgrad_ptr(keyd), flat.bgrad_ptr(keyd), b, hi_, wi_, DEC_CH[i])
+                if grad_allreduce is not None and i == S - 1:
+                    plan.record('grads_disp')
                 plan.set_lane(0)
             if i == 0:
                 plan.simple('dispconv_0.dgrad', lib.clslam_dispconv_dgrad_act, _p(self.dz_disp[0]),
@@ -946,6 +1011,15 @@ class AdaptEngine:
                                     L.PAD_REFLECT, dz_pl[(i, 0)], self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
             else:
                 plan.conv_wgrad(f'upconv_{i}_0.wgrad', d0, xin, None, self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
+            if grad_allreduce is not None and i >= 2:
+                # flat-buffer order is upconv_4_0, 4_1, 3_0, ... 0_1, dispconv_0..3, pose decoder; the gradients appear in
+                # reverse.  Buckets: [pose decoder] (above), [upconv_2_0 .. dispconv_3] once the last dispconv weight gradient
+                # (i == 3, its own lane) exists, [upconv_3_*], [upconv_4_*]
+                plan.record(f'grads_{i}')
+                if i == 3:
+                    sync_bucket('upconv_2..0+dispconv', (dd, 'upconv_2_0.conv.conv'), (dd, 'dispconv_3.conv'), 'grads_2', 'grads_disp')
+                if i >= 3:
+                    sync_bucket(f'upconv_{i}', (dd, f'upconv_{i}_0.conv.conv'), (dd, f'upconv_{i}_1.conv.conv'), f'grads_{i}')
             plan.set_lane(0)
             if i < 4:
                 has_disp = (i + 1) < S
@@ -965,36 +1039,7 @@ class AdaptEngine:
                     if nxt is not None:
                         plan.planes_from_f32(f'dz{i + 1}1.planes', self.dz[(i + 1, 1)], nxt)
                 plan.record(f'dz{i + 1}1')
-        # pose branch
-        plan.set_lane(1)
-        self.dz_pose = {name: plan.alloc(*self.pose_act[name].shape) for name in ('squeeze', 'pose_0', 'pose_1', 'pose_2')}
-        plan.simple('pose_head_bwd', lib.clslam_pose_head_bwd, _p(self.dproj_partials), S * self.n_tiles, _p(self.k_mat),
-                    _p(self.axis_angle), _p(self.translation), _p(self.rel_dist), _p(self.sample_w),
-                    self.vel_scale, b, hp, wp, self.invert_mask, _p(self.dz_pose['pose_2']))
-        prev = {'pose_2': 'pose_1', 'pose_1': 'pose_0', 'pose_0': 'squeeze'}
-        upd = tma_ok(2 * b, hp, wp, 256, 256, TMA_MIN_TILES_BWD)         # pose_1 / pose_0 dgrad (zero padding: one launch, act' fused as a gate)
-        dzp_pl = {name: PlaneBuf(plan, 2 * b, hp, wp, 256).view() for name in ('pose_1', 'pose_0')} if upd else {}
-        for name in ('pose_2', 'pose_1', 'pose_0', 'squeeze'):
-            d, xin = self.pose_desc[name]
-            if name in dzp_pl and self.pose_in_pl.get(name) is not None and (
-                    (not TMA_SPLITK) or TMA_SPLITK_WGRAD or tma_big(2 * b, hp, wp, TMA_MIN_TILES_BWD)):
-                plan.conv_wgrad_tma(f'{name}.wgrad', 2 * b, hp, wp, self.pose_in_pl[name], L.PAD_ZERO, dzp_pl[name], self.dz_pose[name],
-                                    flat.wgrad_ptr((pd, name)), flat.bgrad_ptr((pd, name)))
-            else:
-                plan.conv_wgrad(f'{name}.wgrad', d, xin, None, self.dz_pose[name], flat.wgrad_ptr((pd, name)),
-                                flat.bgrad_ptr((pd, name)))
-            if name in prev:
-                if upd and name in ('pose_1', 'pose_0'):
-                    wt_hi, wt_lo = self._wt_slot((pd, name), 256)
-                    plan.conv_tma(f'{name}.dgrad', dzp_pl[name], L.PAD_ZERO, 256, wt_hi, wt_lo, None, None, L.ACT_NONE,
-                                  y=self.dz_pose[prev[name]], out=dzp_pl.get(prev[name]), gate=self.pose_act[prev[name]],
-                                  gate_act=L.ACT_RELU)
-                else:
-                    plan.conv_dgrad(f'{name}.dgrad', d, self.dz_pose[name], flat.weight_ptr((pd, name)),
-                                    self.pose_act[prev[name]], L.ACT_RELU, None, None, self.dz_pose[prev[name]])
-                    if prev[name] in dzp_pl:
-                        plan.planes_from_f32(f'dz_{prev[name]}.planes', self.dz_pose[prev[name]], dzp_pl[prev[name]])
-        plan.join((1, 2))
+        plan.join((1, 2, COMM) if grad_allreduce is not None else (1, 2))
         self.n_bwd_ops = len(plan.ops)
         self._finish_wt_flip()
         plan.finalize()
