@@ -635,8 +635,18 @@ def run_ours(args):
                 line['torch_eager_gpu'] = {'error': str(exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the step graph holds captured NCCL kernels: release it before the communicator goes away, and never let a stuck
+        # teardown keep the job alive after the line has been printed
+        import signal
+        signal.signal(signal.SIGALRM, lambda *_: os._exit(0))
+        signal.alarm(60)
         dist.barrier()
+        try:
+            pred.close()
+        except NameError:
+            pass
         dist.destroy_process_group()
+        signal.alarm(0)
 
 
 def main():

@@ -232,6 +232,22 @@ class DepthPosePrediction:
     def _engines(self) -> Dict[int, AdaptEngine]:
         return self._main.engines
 
+    def close(self) -> None:
+        """release the launch plans and CUDA graphs.  Data-parallel runs must call this before
+        ``torch.distributed.destroy_process_group()``: the step graph holds captured NCCL kernels, and tearing the communicator
+        down underneath a live graph hangs."""
+        for ns in self._sets():
+            for g in ns.graphs.values():
+                try:
+                    g.reset()
+                except Exception:   # noqa: BLE001
+                    pass
+            ns.drop_plans()
+        self._late_event = None
+        self._last_engine = None
+        if self.device.type == 'cuda':
+            torch.cuda.synchronize(self.device)
+
     def _sets(self) -> List[_NetSet]:
         return [self._main] + ([self._online] if self._online is not None else [])
 

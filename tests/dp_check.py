@@ -52,7 +52,8 @@ def main():
     same = all(float(g) == float(gathered[0]) for g in gathered)
     if rank == 0:
         print(f'dp_check: 3 adapt steps ok, loss {float(l3["loss"]):.6f}, replicas identical: {same}')
-        print('DP_CHECK_PASS' if (ok and same) else 'DP_CHECK_FAIL')
+        print('DP_CHECK_PASS' if (ok and same) else 'DP_CHECK_FAIL', flush=True)
+    pred.close()          # the step graph holds captured NCCL kernels: release it before the communicator
     dist.destroy_process_group()
 
 
