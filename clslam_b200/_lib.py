@@ -17,6 +17,7 @@ TMA_IN_HALO_VALID = 1          # clslam_conv_tma.flags
 IN_PLAIN, IN_UPCAT = 0, 1
 DEPTH_INV, DEPTH_MIN_ONLY, DEPTH_MIN_MAX = 0, 1, 2
 N_LOSS_SLOTS = 24
+ADAM_NO_TICK = -1
 
 
 class ConvDesc(Structure):
@@ -124,6 +125,7 @@ SIGNATURES = {
     'clslam_loss_finalize': (c_int, [POINTER(LossArgs), c_void_p]),
     'clslam_disp_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                  c_void_p]),
+    'clslam_adam_tick': (c_int, [c_void_p, c_void_p]),
     'clslam_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double,
                                  c_double, c_int, c_void_p, c_void_p]),
 }

@@ -396,13 +396,19 @@ int clslam_dispconv_dgrad_act(const float* dz, const float* w, const float* y_pr
   return finish_launch("dispconv_dgrad_act");
 }
 
+int clslam_adam_tick(int* step_dev, void* stream) {
+  if (!step_dev) { set_error("adam_tick: null counter"); return -1; }
+  launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, as_stream(stream), step_dev);
+  return finish_launch("adam_tick");
+}
+
 int clslam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, double lr,
                      double beta1, double beta2, double eps, int step, int* step_dev, void* stream) {
   cudaStream_t st = as_stream(stream);
   launch_k(adam_kernel, dim3(grid_for((size_t)n, 256 * 4)), dim3(256), 0, st, param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step,
                                                            step_dev);
   if (int rc = finish_launch("adam")) return rc;
-  if (step_dev) {
+  if (step_dev && step != CLSLAM_ADAM_NO_TICK) {
     launch_k(adam_tick_kernel, dim3(1), dim3(1), 0, st, step_dev);
     return finish_launch("adam_tick");
   }

@@ -573,6 +573,7 @@ class DepthPosePrediction:
     def _step(self, eng: AdaptEngine) -> None:
         """one adaptation iteration on staged inputs: fwd, bwd, (all-reduce), Adam"""
         lr = self._adam_lr()
+        eng.adam_hparams(lr)                 # read by the per-bucket Adam launches of a data-parallel plan (baked into its graph)
         ns = eng.net_set
         graphs = ns.graphs
         n_run = ns.steps_run.get(eng.b, 0)

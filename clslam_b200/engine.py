@@ -366,7 +366,8 @@ class Plan:
             if fn is None and name != '__py__' and args[0] not in self._events:
                 self._events[args[0]] = torch.cuda.Event()
 
-    def run(self, first: int = 0, last: Optional[int] = None, serial: bool = False, timed: bool = False) -> None:
+    def run(self, first: int = 0, last: Optional[int] = None, serial: bool = False, timed: bool = False,
+            skip_prefix: Optional[str] = None) -> None:
         main = torch.cuda.current_stream(self.device)
         streams = [main] + ([main] * len(self._side) if serial else self._side)
         ptrs = [st.cuda_stream for st in streams]
@@ -382,6 +383,8 @@ class Plan:
                     self._events[args[0]].record(streams[lane])
                 else:
                     streams[lane].wait_event(self._events[args[0]])
+                continue
+            if skip_prefix is not None and name.startswith(skip_prefix):
                 continue
             if timed:
                 self.lib.clslam_event_record(self._timers[i][0], ptrs[lane])
@@ -875,6 +878,7 @@ class AdaptEngine:
         plan.add('photo_bwd', lambda stream, ws: lib.clslam_photo_bwd(ctypes.byref(pa), stream))
         plan.fork((1, 2))
         self.grad_sync_in_plan = grad_allreduce is not None
+        self.adam_lr, self.adam_betas, self.adam_eps = 1e-4, (0.9, 0.999), 1e-8          # set by adam_hparams() before a run / capture
         COMM = 3                             # communication lane (data-parallel only)
 
         def sync_bucket(name, first_key, last_key, *ready_events):
@@ -890,6 +894,8 @@ class AdaptEngine:
             for ev in ready_events:
                 plan.wait(ev)
             plan.call(f'allreduce.{name}', lambda v=view: grad_allreduce(v))
+            # Adam on this bucket as soon as its gradients are complete: only the last bucket's update is exposed
+            plan.add(f'adam.{name}', lambda stream, ws, o=lo, n=hi - lo: self._adam_range(o, n, stream))
             plan.set_lane(back)
         self.dz_disp = {}
         plan.wait('lossfin')                 # smooth_grad (lane 0 and, through the fork above, lanes 1 / 2 follow loss_finalize)
@@ -989,6 +995,8 @@ class AdaptEngine:
                                     self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
             else:
                 plan.conv_wgrad(f'upconv_{i}_1.wgrad', d1, y0, skip, self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
+            if grad_allreduce is not None and i == 4:
+                plan.record('grads_41')
             plan.set_lane(0)
             nxt = dz_pl.get((i, 0))
             if ud1[i]:
@@ -1001,6 +1009,11 @@ class AdaptEngine:
                 if nxt is not None:
                     plan.planes_from_f32(f'dz{i}0.planes', self.dz[(i, 0)], nxt)
             plan.record(f'dz{i}0')
+            if grad_allreduce is not None and i == 4:
+                # a bucket is updated in place by its Adam launch: besides its weight gradients ('grads_*') the last READER of
+                # its weights on the dgrad lane must be done ('dz*': the gather dgrad and the dispconv term of the fold read
+                # the fp32 weights).  upconv_4_1: 26 % of the bytes, out before upconv_4_0's weight gradient runs
+                sync_bucket('upconv_4_1', key1, key1, 'grads_41', 'dz40')
             # upconv_i_0: wgrad; dgrad into upconv_{i+1}_1's output (+ dispconv_{i+1} term)
             d0, xin = self.dec_desc[(i, 0)]
             key0 = (dd, f'upconv_{i}_0.conv.conv')
@@ -1016,10 +1029,6 @@ class AdaptEngine:
                 # reverse.  Buckets: [pose decoder] (above), [upconv_2_0 .. dispconv_3] once the last dispconv weight gradient
                 # (i == 3, its own lane) exists, [upconv_3_*], [upconv_4_*]
                 plan.record(f'grads_{i}')
-                if i == 3:
-                    sync_bucket('upconv_2..0+dispconv', (dd, 'upconv_2_0.conv.conv'), (dd, 'dispconv_3.conv'), 'grads_2', 'grads_disp')
-                if i >= 3:
-                    sync_bucket(f'upconv_{i}', (dd, f'upconv_{i}_0.conv.conv'), (dd, f'upconv_{i}_1.conv.conv'), f'grads_{i}')
             plan.set_lane(0)
             if i < 4:
                 has_disp = (i + 1) < S
@@ -1039,6 +1048,13 @@ class AdaptEngine:
                     if nxt is not None:
                         plan.planes_from_f32(f'dz{i + 1}1.planes', self.dz[(i + 1, 1)], nxt)
                 plan.record(f'dz{i + 1}1')
+            if grad_allreduce is not None:
+                if i == 3:
+                    sync_bucket('upconv_2..0+dispconv', (dd, 'upconv_2_0.conv.conv'), (dd, 'dispconv_3.conv'), 'grads_2', 'grads_disp',
+                                'dz31')
+                    sync_bucket('upconv_3', (dd, 'upconv_3_0.conv.conv'), (dd, 'upconv_3_1.conv.conv'), 'grads_3', 'dz41')
+                if i == 4:
+                    sync_bucket('upconv_4_0', key0, key0, 'grads_4')          # its input is a frozen encoder feature: no dgrad
         plan.join((1, 2, COMM) if grad_allreduce is not None else (1, 2))
         self.n_bwd_ops = len(plan.ops)
         self._finish_wt_flip()
@@ -1089,12 +1105,23 @@ class AdaptEngine:
         self.plan.run(0, self.n_fwd_ops)
 
     def backward(self) -> None:
-        self.plan.run(self.n_fwd_ops, self.n_bwd_ops)
+        """gradients only (data-parallel plans: all-reduced, the per-bucket Adam launches skipped)"""
+        self.plan.run(self.n_fwd_ops, self.n_bwd_ops, skip_prefix='adam.')
 
     def forward_backward(self, timed: bool = False) -> None:
-        """one pass without the forward-only join (the loss assembly overlaps the photometric backward)"""
+        """one pass without the forward-only join (the loss assembly overlaps the photometric backward).  Data-parallel plans
+        (grad_sync_in_plan) also all-reduce and apply Adam per gradient bucket in here; adam() then only bumps the counter."""
         self.plan.run(0, self.n_fwd_core, timed=timed)
         self.plan.run(self.n_fwd_ops, self.n_bwd_ops, timed=timed)
+
+    def adam_hparams(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
+        self.adam_lr, self.adam_betas, self.adam_eps = float(lr), (beta1, beta2), eps
+
+    def _adam_range(self, off: int, n: int, stream) -> int:
+        f = self.flat
+        return self.lib.clslam_adam_step(f.params.data_ptr() + 4 * off, f.grads.data_ptr() + 4 * off, f.exp_avg.data_ptr() + 4 * off,
+                                         f.exp_avg_sq.data_ptr() + 4 * off, n, self.adam_lr, self.adam_betas[0], self.adam_betas[1],
+                                         self.adam_eps, L.ADAM_NO_TICK, f.step_dev.data_ptr(), stream)
 
     def networks_forward(self) -> None:
         """first part of forward_backward: both networks (reads rgb_aug and the intrinsics only)"""
@@ -1108,6 +1135,9 @@ class AdaptEngine:
     def adam(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
         f = self.flat
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if self.grad_sync_in_plan:          # the buckets were updated inside forward_backward(): one tick of the step counter
+            L.check(self.lib.clslam_adam_tick(f.step_dev.data_ptr(), stream), 'adam_tick')
+            return
         L.check(self.lib.clslam_adam_step(f.params.data_ptr(), f.grads.data_ptr(), f.exp_avg.data_ptr(),
                                           f.exp_avg_sq.data_ptr(), f.numel, lr, beta1, beta2, eps, 0,
                                           f.step_dev.data_ptr(), stream), 'adam')

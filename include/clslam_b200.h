@@ -344,10 +344,15 @@ int clslam_disp_to_depth(const float* disp, float* depth, long long n, int depth
  * torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as built at
  * depth_pose_prediction.py:203 and stepped at :313, over one flat fp32 buffer.  `step` is the
  * 1-based step number AFTER this update; if step_dev != NULL it is read from (and incremented on)
- * the device instead, which makes the call CUDA-graph replayable. */
+ * the device instead, which makes the call CUDA-graph replayable.
+ * Bucketed use (data-parallel step: one call per gradient bucket as soon as its all-reduce has finished): pass
+ * step = CLSLAM_ADAM_NO_TICK with step_dev, so that every bucket of an iteration reads the same counter, and call
+ * clslam_adam_tick once after the last bucket. */
+#define CLSLAM_ADAM_NO_TICK (-1)
 int clslam_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
                      double lr, double beta1, double beta2, double eps, int step, int* step_dev,
                      void* stream);
+int clslam_adam_tick(int* step_dev, void* stream);
 
 #ifdef __cplusplus
 }
