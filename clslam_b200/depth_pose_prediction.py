@@ -27,7 +27,8 @@ from .sharding import global_sample_weights, shard_range
 
 # data-parallel: all-reduce the gradients in buckets inside the step graph, overlapped with the backward pass (default);
 # CLSLAM_GRAD_BUCKETS=0 restores round 1's graph -> eager all-reduce of the whole buffer -> graph
-GRAD_BUCKETS = os.environ.get('CLSLAM_GRAD_BUCKETS', '1') == '1'
+GRAD_BUCKETS = int(os.environ.get('CLSLAM_GRAD_BUCKETS', '2'))        # 0 / 1 / 2 / 5: see AdaptEngine
+BUCKET_ADAM = os.environ.get('CLSLAM_BUCKET_ADAM', '0') == '1'
 
 LOSS_SLOTS = {'reprojection_loss': 0, 'smooth_loss': 4, 'reg_loss': 8, 'depth_loss': 12}
 
@@ -365,7 +366,8 @@ class DepthPosePrediction:
                               max_depth=self.max_depth, disparity_smoothness=self.disparity_smoothness,
                               velocity_loss_scaling=self.velocity_loss_scaling, device=self.device,
                               emit_outputs=self.emit_outputs,
-                              grad_allreduce=self._allreduce_tensor if (self.world > 1 and GRAD_BUCKETS) else None)
+                              grad_allreduce=self._allreduce_tensor if (self.world > 1 and GRAD_BUCKETS > 0) else None,
+                              grad_buckets=GRAD_BUCKETS, bucket_adam=BUCKET_ADAM)
             eng.net_set = ns
             ns.engines[batch] = eng
         return eng

@@ -641,7 +641,8 @@ class AdaptEngine:
     def __init__(self, *, batch: int, height: int, width: int, batch_global: int, has_sample0: bool,
                  depth_prep: PreparedEncoder, pose_prep: PreparedEncoder, flat: FlatParams,
                  min_depth: Optional[float], max_depth: Optional[float], disparity_smoothness: float,
-                 velocity_loss_scaling: Optional[float], device, emit_outputs: bool = True, grad_allreduce=None):
+                 velocity_loss_scaling: Optional[float], device, emit_outputs: bool = True, grad_allreduce=None,
+                 grad_buckets: int = 2, bucket_adam: bool = False):
         """``grad_allreduce(tensor)``: data-parallel runs pass the SUM all-reduce of a slice of the flat gradient buffer; the
         backward plan then issues it per bucket on a communication lane as soon as the bucket's weight gradients exist
         (pose decoder first, ``upconv_4_*`` -- 53 % of the bytes -- last), inside the step graph."""
@@ -878,6 +879,11 @@ class AdaptEngine:
         plan.add('photo_bwd', lambda stream, ws: lib.clslam_photo_bwd(ctypes.byref(pa), stream))
         plan.fork((1, 2))
         self.grad_sync_in_plan = grad_allreduce is not None
+        # grad_buckets: 1 = one all-reduce of the whole buffer after the backward pass (inside the graph); 2 = everything but
+        # upconv_4_* as soon as it exists, then upconv_4_*; 5 = pose decoder / upconv_2..0 + dispconv / upconv_3 / upconv_4_1 /
+        # upconv_4_0.  bucket_adam: Adam per bucket right after its all-reduce (else one Adam launch after the join)
+        self.adam_in_plan = self.grad_sync_in_plan and bucket_adam and grad_buckets > 1
+        nb = grad_buckets if grad_allreduce is not None else 0
         self.adam_lr, self.adam_betas, self.adam_eps = 1e-4, (0.9, 0.999), 1e-8          # set by adam_hparams() before a run / capture
         COMM = 3                             # communication lane (data-parallel only)
 
@@ -894,8 +900,8 @@ class AdaptEngine:
             for ev in ready_events:
                 plan.wait(ev)
             plan.call(f'allreduce.{name}', lambda v=view: grad_allreduce(v))
-            # Adam on this bucket as soon as its gradients are complete: only the last bucket's update is exposed
-            plan.add(f'adam.{name}', lambda stream, ws, o=lo, n=hi - lo: self._adam_range(o, n, stream))
+            if self.adam_in_plan:      # Adam on this bucket as soon as its gradients are complete: only the last update is exposed
+                plan.add(f'adam.{name}', lambda stream, ws, o=lo, n=hi - lo: self._adam_range(o, n, stream))
             plan.set_lane(back)
         self.dz_disp = {}
         plan.wait('lossfin')                 # smooth_grad (lane 0 and, through the fork above, lanes 1 / 2 follow loss_finalize)
@@ -961,8 +967,9 @@ class AdaptEngine:
                                     self.pose_act[prev[name]], L.ACT_RELU, None, None, self.dz_pose[prev[name]])
                     if prev[name] in dzp_pl:
                         plan.planes_from_f32(f'dz_{prev[name]}.planes', self.dz_pose[prev[name]], dzp_pl[prev[name]])
-        if grad_allreduce is not None:
+        if nb > 1:
             plan.record('grads_pose')
+        if nb == 5:
             sync_bucket('pose_decoder', (pd, 'squeeze'), (pd, 'pose_2'), 'grads_pose')
         plan.set_lane(0)
         for i in range(0, 5):
@@ -975,7 +982,7 @@ class AdaptEngine:
                 plan.wait(f'dzd{i}')
                 plan.with_ws(f'dispconv_{i}.wgrad', lib.clslam_dispconv_wgrad, _p(y1), _p(self.dz_disp[i]),
                              flat.wgrad_ptr(keyd), flat.bgrad_ptr(keyd), b, hi_, wi_, DEC_CH[i])
-                if grad_allreduce is not None and i == S - 1:
+                if nb > 1 and i == S - 1:
                     plan.record('grads_disp')
                 plan.set_lane(0)
             if i == 0:
@@ -995,7 +1002,7 @@ class AdaptEngine:
                                     self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
             else:
                 plan.conv_wgrad(f'upconv_{i}_1.wgrad', d1, y0, skip, self.dz[(i, 1)], flat.wgrad_ptr(key1), flat.bgrad_ptr(key1))
-            if grad_allreduce is not None and i == 4:
+            if nb > 1 and i == 4:
                 plan.record('grads_41')
             plan.set_lane(0)
             nxt = dz_pl.get((i, 0))
@@ -1009,7 +1016,7 @@ class AdaptEngine:
                 if nxt is not None:
                     plan.planes_from_f32(f'dz{i}0.planes', self.dz[(i, 0)], nxt)
             plan.record(f'dz{i}0')
-            if grad_allreduce is not None and i == 4:
+            if nb == 5 and i == 4:
                 # a bucket is updated in place by its Adam launch: besides its weight gradients ('grads_*') the last READER of
                 # its weights on the dgrad lane must be done ('dz*': the gather dgrad and the dispconv term of the fold read
                 # the fp32 weights).  upconv_4_1: 26 % of the bytes, out before upconv_4_0's weight gradient runs
@@ -1024,7 +1031,7 @@ class AdaptEngine:
                                     L.PAD_REFLECT, dz_pl[(i, 0)], self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
             else:
                 plan.conv_wgrad(f'upconv_{i}_0.wgrad', d0, xin, None, self.dz[(i, 0)], flat.wgrad_ptr(key0), flat.bgrad_ptr(key0))
-            if grad_allreduce is not None and i >= 2:
+            if nb > 1 and i >= 2:
                 # flat-buffer order is upconv_4_0, 4_1, 3_0, ... 0_1, dispconv_0..3, pose decoder; the gradients appear in
                 # reverse.  Buckets: [pose decoder] (above), [upconv_2_0 .. dispconv_3] once the last dispconv weight gradient
                 # (i == 3, its own lane) exists, [upconv_3_*], [upconv_4_*]
@@ -1048,14 +1055,25 @@ class AdaptEngine:
                     if nxt is not None:
                         plan.planes_from_f32(f'dz{i + 1}1.planes', self.dz[(i + 1, 1)], nxt)
                 plan.record(f'dz{i + 1}1')
-            if grad_allreduce is not None:
+            if nb == 5:
                 if i == 3:
                     sync_bucket('upconv_2..0+dispconv', (dd, 'upconv_2_0.conv.conv'), (dd, 'dispconv_3.conv'), 'grads_2', 'grads_disp',
                                 'dz31')
                     sync_bucket('upconv_3', (dd, 'upconv_3_0.conv.conv'), (dd, 'upconv_3_1.conv.conv'), 'grads_3', 'dz41')
                 if i == 4:
                     sync_bucket('upconv_4_0', key0, key0, 'grads_4')          # its input is a frozen encoder feature: no dgrad
-        plan.join((1, 2, COMM) if grad_allreduce is not None else (1, 2))
+            if nb == 2:
+                if i == 3:         # 47 % of the bytes: upconv_3_0 .. pose_2 is one contiguous range of the flat buffer
+                    sync_bucket('upconv_3..pose', (dd, 'upconv_3_0.conv.conv'), (pd, 'pose_2'), 'grads_3', 'grads_disp', 'grads_pose',
+                                'dz41')
+                if i == 4:
+                    sync_bucket('upconv_4', key0, key1, 'grads_4', 'dz40')
+        if nb > 1:
+            plan.join((1, 2, COMM))
+        else:
+            plan.join((1, 2))
+            if nb == 1:            # the whole buffer, after the backward pass, still inside the step graph (no host round trip)
+                plan.call('allreduce.all', lambda v=flat.grads: grad_allreduce(v))
         self.n_bwd_ops = len(plan.ops)
         self._finish_wt_flip()
         plan.finalize()
@@ -1135,7 +1153,7 @@ class AdaptEngine:
     def adam(self, lr: float, beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-8) -> None:
         f = self.flat
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        if self.grad_sync_in_plan:          # the buckets were updated inside forward_backward(): one tick of the step counter
+        if self.adam_in_plan:               # the buckets were updated inside forward_backward(): one tick of the step counter
             L.check(self.lib.clslam_adam_tick(f.step_dev.data_ptr(), stream), 'adam_tick')
             return
         L.check(self.lib.clslam_adam_step(f.params.data_ptr(), f.grads.data_ptr(), f.exp_avg.data_ptr(),
