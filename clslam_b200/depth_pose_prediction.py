@@ -27,7 +27,7 @@ from .sharding import global_sample_weights, shard_range
 
 # data-parallel: all-reduce the gradients in buckets inside the step graph, overlapped with the backward pass (default);
 # CLSLAM_GRAD_BUCKETS=0 restores round 1's graph -> eager all-reduce of the whole buffer -> graph
-GRAD_BUCKETS = int(os.environ.get('CLSLAM_GRAD_BUCKETS', '2'))        # 0 / 1 / 2 / 5: see AdaptEngine
+GRAD_BUCKETS = int(os.environ.get('CLSLAM_GRAD_BUCKETS', '1'))        # 0 / 1 / 2 / 5: see AdaptEngine (measured at 2 GPUs, profiles/r02_dp_buckets.md: 1 is fastest)
 BUCKET_ADAM = os.environ.get('CLSLAM_BUCKET_ADAM', '0') == '1'
 
 LOSS_SLOTS = {'reprojection_loss': 0, 'smooth_loss': 4, 'reg_loss': 8, 'depth_loss': 12}
