@@ -201,6 +201,11 @@ class DepthPosePrediction:
         # so the public methods hand out ONE clone of the output arena per call (a single D2D copy).  copy_outputs=False
         # returns views of the static buffers instead: valid until the next adapt / predict call on this object.
         self.copy_outputs = copy_outputs
+        # Slam.step converts every one of the 19 losses with `float(v.squeeze().cpu()...)` (slam/slam.py:186-188): 19 device
+        # syncs per frame.  The class already reads the whole loss vector back once per call for the NaN check (:1115); with
+        # losses_on_host=True the returned loss tensors are views of THAT host copy, so the caller's `.cpu()` calls are free.
+        # Off by default: the reference returns device tensors.
+        self.losses_on_host = False
 
         # Networks (parameter containers; arithmetic lives in the CUDA kernels) --------------------
         self._main = _NetSet(self, 'main')
@@ -381,7 +386,7 @@ class DepthPosePrediction:
         runner = ns.enc_runners.get(key)
         if runner is None:
             L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
-            runner = EncoderRunner(ns.models[net], prep, n, h, w, self.device)
+            runner = EncoderRunner(ns.models[net], prep, n, h, w, self.device, use_graph=self.use_cuda_graph)
             ns.enc_runners[key] = runner
         feats = runner(x.to(self.device, dtype=torch.float32))
         return [f.permute(0, 3, 1, 2).clone() for f in feats]
@@ -407,10 +412,11 @@ class DepthPosePrediction:
         eng = self._engine(batch, ns)
         smap = self._static_map(eng)
         self._deferred = []
-        if defer_unused:
+        cuda = self.device.type == 'cuda'
+        if defer_unused and cuda:
             self._stage_event = torch.cuda.Event()
             self._stage_event.record(torch.cuda.current_stream(self.device))
-        overlap = H2D_OVERLAP and defer_unused and self.world == 1
+        overlap = H2D_OVERLAP and defer_unused and self.world == 1 and cuda
         late: List[Tuple[Tensor, Tensor]] = []
         for key in list(inputs.keys()):
             val = inputs[key]
@@ -454,6 +460,11 @@ class DepthPosePrediction:
     def _flush_deferred(self) -> None:
         """H2D of the unused dict values on a side stream, overlapping the step; the caller's stream waits for them"""
         if not self._deferred:
+            return
+        if self.device.type != 'cuda':          # parameter-container mode (host-logic tests): nothing to overlap
+            for buf, val in self._deferred:
+                buf.copy_(val)
+            self._deferred = []
             return
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -520,6 +531,11 @@ class DepthPosePrediction:
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(vec)
+        host = None
+        if check_nan:
+            host = vec.cpu()                            # the one sync per call (:1115)
+            if self.losses_on_host:
+                vec = host
         losses: Dict[str, Tensor] = {}
         for s in self.scales:
             for name in ('reprojection_loss', 'smooth_loss', 'reg_loss', 'depth_loss'):
@@ -530,7 +546,6 @@ class DepthPosePrediction:
             losses['velocity_loss'] = vec[17]
         losses['loss'] = total
         if check_nan:
-            host = vec.cpu()                            # the one sync per call (:1115)
             if bool(torch.isnan(host[18])):
                 for k, v in losses.items():
                     print(k, float(v.reshape(-1)[0]))
@@ -681,7 +696,8 @@ class DepthPosePrediction:
         runner = ns.depth_runners.get((n, h, w))
         if runner is None:
             L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
-            runner = DepthRunner(prep, ns.flat, n, h, w, self.min_depth, self.max_depth, self.device)
+            runner = DepthRunner(prep, ns.flat, n, h, w, self.min_depth, self.max_depth, self.device,
+                                 use_graph=self.use_cuda_graph)
             ns.depth_runners[(n, h, w)] = runner
         self._set_eval()
         return runner(image.to(self.device, dtype=torch.float32))
@@ -752,7 +768,7 @@ class DepthPosePrediction:
         r = ns.pose_runner
         if r is None or (r.n, r.h, r.w) != (n, h, w):
             L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
-            r = _PoseRunner(prep, ns.flat, n, h, w, self.device)
+            r = _PoseRunner(prep, ns.flat, n, h, w, self.device, use_graph=self.use_cuda_graph)
             ns.pose_runner = r
         return r
 
@@ -841,8 +857,8 @@ class DepthPosePrediction:
 class _PoseRunner:
     """pose encoder + decoder + head for ``predict_pose`` (batch n, both 'passes' carry the same pair)."""
 
-    def __init__(self, prep: PreparedEncoder, flat: FlatParams, n: int, h: int, w: int, device):
-        from .engine import build_encoder
+    def __init__(self, prep: PreparedEncoder, flat: FlatParams, n: int, h: int, w: int, device, use_graph: bool = True):
+        from .engine import GraphedPlan, build_encoder
         self.n, self.h, self.w = n, h, w
         plan = Plan(device)
         lib = plan.lib
@@ -867,8 +883,9 @@ class _PoseRunner:
                     _p(self.cam), _p(self.proj))
         plan.finalize()
         self.plan = plan
+        self.graphed = GraphedPlan(plan, use_graph)
 
     def __call__(self, image_0: Tensor, image_1: Tensor) -> Tensor:
         self.img0.copy_(image_0); self.img1.copy_(image_1)
-        self.plan.run()
+        self.graphed.run()
         return self.cam[0].clone()

@@ -415,6 +415,30 @@ class Plan:
         return out
 
 
+class GraphedPlan:
+    """a forward-only plan replayed from a CUDA graph: first call eager (loads the kernels, builds the tensor maps), second
+    call captures, later calls replay.  The per-frame helper passes Slam.step makes next to adapt() -- the encoder call for
+    the replay-buffer feature (slam/slam.py:143-147), predict_pose for loop closures (:229), predict_from_image -- are 25-60
+    launches of a few microseconds each: launch-bound when issued one by one."""
+
+    def __init__(self, plan: Plan, enabled: bool = True):
+        self.plan, self.enabled = plan, enabled
+        self.calls = 0
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+
+    def run(self) -> None:
+        self.calls += 1
+        if not self.enabled or self.calls == 1:
+            self.plan.run()
+            return
+        if self.graph is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.plan.run()
+            self.graph = g
+        self.graph.replay()
+
+
 def conv1_s2d_ok(n: int, h: int, w: int, cin_pad: int) -> bool:
     return h % 2 == 0 and w % 2 == 0 and tma_ok(n, h // 2, w // 2, 4 * cin_pad, 64)
 
@@ -528,7 +552,7 @@ class EncoderRunner:
     """Encoder-only forward for callers that use ``models['depth_encoder'](image)`` directly
     (slam/slam.py:143-147) and for predict_pose (depth_pose_prediction.py:628-664)."""
 
-    def __init__(self, enc: ResnetEncoder, prep: PreparedEncoder, n: int, h: int, w: int, device):
+    def __init__(self, enc: ResnetEncoder, prep: PreparedEncoder, n: int, h: int, w: int, device, use_graph: bool = True):
         self.plan = Plan(device)
         self.n, self.h, self.w = n, h, w
         self.two = enc.num_input_images == 2
@@ -538,13 +562,14 @@ class EncoderRunner:
         self.feats = build_encoder(self.plan, prep, self.staged, n, h, w, 'enc', x_s2d=s2d)
         self.plan.finalize()
         self.prep = prep
+        self.graphed = GraphedPlan(self.plan, use_graph)
 
     def __call__(self, image: torch.Tensor) -> List[torch.Tensor]:
         if self.two:
             self.img_a.copy_(image[:, :3]); self.img_b.copy_(image[:, 3:6])
         else:
             self.img_a.copy_(image)
-        self.plan.run()
+        self.graphed.run()
         return self.feats
 
 
@@ -571,7 +596,8 @@ class DepthRunner:
     """Depth network alone: encoder + decoder + dispconv_0 + disp_to_depth for ``predict_from_image(s)``
     (depth_pose_prediction.py:538-554): no pose network, no losses, no collectives.  Keyed by (n, h, w) by the caller."""
 
-    def __init__(self, prep: PreparedEncoder, flat: FlatParams, n: int, h: int, w: int, min_depth, max_depth, device):
+    def __init__(self, prep: PreparedEncoder, flat: FlatParams, n: int, h: int, w: int, min_depth, max_depth, device,
+                 use_graph: bool = True):
         if h % 32 or w % 32:
             raise ValueError('height and width must be multiples of 32 (ResNet-18 / 4-scale pyramid)')
         self.n, self.h, self.w = n, h, w
@@ -628,10 +654,11 @@ class DepthRunner:
         plan.simple('disp_to_depth', lib.clslam_disp_to_depth, _p(self.disp), _p(self.depth), n * h * w, mode,
                     float(min_depth or 0.0), float(max_depth or 0.0))
         plan.finalize()
+        self.graphed = GraphedPlan(plan, use_graph)
 
     def __call__(self, image: torch.Tensor) -> torch.Tensor:
         self.image.copy_(image)
-        self.plan.run()
+        self.graphed.run()
         return self.depth.clone()
 
 

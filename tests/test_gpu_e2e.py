@@ -249,3 +249,32 @@ def test_use_online_network_copy_runs_on_its_own_weights():
     assert rel(tr, rec['predict_pose']) < REL_TOL
     tr_main, _ = pred.predict_pose(batch[('rgb', 0, 0)][0], batch[('rgb', 1, 0)][0], as_numpy=True)
     assert rel(tr_main, rec['predict_pose']) > 1e-3
+
+
+def test_per_frame_helper_paths_replay_from_graphs_and_host_losses():
+    """the passes Slam.step makes next to adapt(): encoder call for the buffer feature, predict_pose, predict_from_image.
+    First call eager, second captures a CUDA graph, later ones replay: all three must agree bit for bit.  losses_on_host:
+    the loss tensors are views of the one host read-back, equal to the device values."""
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build('small_b2')
+    pred.is_trained = True
+    img = batch[('rgb', 0, 0)][:1]
+    img2 = batch[('rgb', 1, 0)][:1]
+    feats, poses, depths = [], [], []
+    for k in range(4):
+        x = img if k != 2 else img2          # a different input in between: replays must read the new image
+        pred._set_eval()
+        with torch.no_grad():
+            feats.append(pred.models['depth_encoder'](x.to(pred.device))[4].mean(-1).mean(-1).cpu())
+        poses.append(torch.from_numpy(pred.predict_pose(x[0], img2[0])[0]))
+        depths.append(pred.predict_from_image(x, as_numpy=False).cpu())
+    for seq in (feats, poses, depths):
+        assert torch.equal(seq[0], seq[1]) and torch.equal(seq[0], seq[3])
+        assert not torch.equal(seq[0], seq[2])
+    assert rel(feats[0].numpy(), rec['buffer_feature']) < REL_TOL
+    _, dev_losses = pred.adapt(dict(batch), None)
+    pred.losses_on_host = True
+    _, host_losses = pred.adapt(dict(batch), None)
+    assert all(not v.is_cuda for v in host_losses.values()) and host_losses['loss'].shape == (1,)
+    for k, v in dev_losses.items():
+        assert float(v.reshape(-1)[0]) == float(host_losses[k].reshape(-1)[0]), k
+        _ = float(host_losses[k].squeeze().cpu().detach().numpy())          # slam/slam.py:186-188
