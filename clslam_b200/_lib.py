@@ -125,6 +125,10 @@ SIGNATURES = {
     'clslam_loss_finalize': (c_int, [POINTER(LossArgs), c_void_p]),
     'clslam_disp_grad': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
                                  c_void_p]),
+    'clslam_resample_u8': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'clslam_u8_to_f32_chw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'clslam_color_jitter_workspace_bytes': (c_longlong, [c_int]),
+    'clslam_color_jitter_op': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_longlong, c_void_p]),
     'clslam_adam_tick': (c_int, [c_void_p, c_void_p]),
     'clslam_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double,
                                  c_double, c_int, c_void_p, c_void_p]),

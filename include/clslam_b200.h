@@ -340,6 +340,22 @@ int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* sm
 int clslam_disp_to_depth(const float* disp, float* depth, long long n, int depth_mode, float min_depth, float max_depth,
                          void* stream);
 
+/* ---- replay-sample image path (slam/replay_buffer.py:263-291, datasets/utils.py:236-259) -------
+ * One pass of Pillow's 8-bit ImagingResample over n interleaved uint8 images (n, h_in, w_in, c): horizontal
+ * (vertical = 0: -> (n, h_in, out_size, c)) or vertical (-> (n, out_size, w_in, c)).  bounds (out_size x 2: first source
+ * index, tap count) and kk (out_size x ksize fixed-point coefficients, 22 fractional bits) are device arrays built as
+ * Pillow's precompute_coeffs + normalize_coeffs_8bpc build them (clslam_b200/replay_path.py::pil_coeffs).  Bit-exact. */
+int clslam_resample_u8(const void* src, void* dst, int n, int h_in, int w_in, int c, int out_size, int vertical,
+                       const int* bounds, const int* kk, int ksize, void* stream);
+/* torchvision ToTensor: (n, h, w, 3) uint8 -> (n, 3, h, w) float32 / 255 */
+int clslam_u8_to_f32_chw(const void* hwc, float* chw, int n, int h, int w, void* stream);
+/* One colour-jitter step of torchvision.transforms.functional on n float images (n, 3, h, w) in [0, 1]:
+ * op 0 adjust_brightness, 1 adjust_contrast (per-image grey mean), 2 adjust_saturation, 3 adjust_hue; `factor` is the
+ * sampled factor (a Python float in the reference).  src == dst is allowed.  Workspace: clslam_color_jitter_workspace_bytes(n). */
+long long clslam_color_jitter_workspace_bytes(int n);
+int clslam_color_jitter_op(const float* src, float* dst, int n, int h, int w, int op, double factor, void* workspace,
+                           long long workspace_bytes, void* stream);
+
 /* ---- optimiser ----------------------------------------------------------------------------
  * torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as built at
  * depth_pose_prediction.py:203 and stepped at :313, over one flat fp32 buffer.  `step` is the

@@ -24,39 +24,14 @@ REFERENCE = Path('/root/reference')
 pytestmark = pytest.mark.skipif(not (REFERENCE / 'slam' / 'slam.py').exists(), reason='needs the reference checkout (build container)')
 
 
-class _Stub(types.ModuleType):
-    def __getattr__(self, name):
-        if name.startswith('__'):
-            raise AttributeError(name)
-        child = _Stub(f'{self.__name__}.{name}')
-        setattr(self, name, child)
-        return child
-
-    def __call__(self, *a, **k):
-        return None
-
-    def __mro_entries__(self, bases):          # `class X(g2o.SparseOptimizer)` in slam/pose_graph_optimization.py
-        return (object,)
-
-
 @pytest.fixture(scope='module')
 def slam_module():
-    sys.path.insert(0, str(REFERENCE))
-    added = []
-    for name in ('matplotlib', 'matplotlib.pyplot', 'matplotlib.cm', 'matplotlib.colors', 'colour_demosaicing', 'skimage',
-                 'skimage.transform', 'faiss', 'g2o'):
-        try:
-            __import__(name)
-        except Exception:
-            stub = _Stub(name)
-            stub.__path__ = []          # importable as a package (`import matplotlib.cm`)
-            sys.modules[name] = stub
-            added.append(name)
+    from tests import ref_stubs
+    added = ref_stubs.install()
     import slam.slam as slam_mod
     slam_mod.PLOTTING = False
     yield slam_mod
-    for name in added:
-        sys.modules.pop(name, None)
+    ref_stubs.remove(added)
 
 
 class FakePoseGraph:
