@@ -278,3 +278,19 @@ def test_per_frame_helper_paths_replay_from_graphs_and_host_losses():
     for k, v in dev_losses.items():
         assert float(v.reshape(-1)[0]) == float(host_losses[k].reshape(-1)[0]), k
         _ = float(host_losses[k].squeeze().cpu().detach().numpy())          # slam/slam.py:186-188
+
+
+def test_predict_pose_batches_loop_closure_pairs():
+    """the loop-closure matches of one keyframe (slam/slam.py:226-233 issues one B=1 pose-net forward per
+    match) can go through ONE batched call: predict_pose on stacked (n, 3, H, W) inputs equals n single calls"""
+    rec, pred, params, batch, noise, (b, h, w, max_depth) = build('small_b3_coherent')
+    pred.is_trained = True
+    img0 = torch.stack([batch[('rgb', 0, 0)][k] for k in range(3)])
+    img1 = torch.stack([batch[('rgb', 1, 0)][k] for k in range(3)])
+    many, cov = pred.predict_pose(img0, img1, as_numpy=True)
+    assert many.shape == (3, 4, 4) and cov.shape == (6, 6)
+    for k in range(3):
+        one, _ = pred.predict_pose(img0[k], img1[k], as_numpy=True)
+        assert rel(many[k], one) < 1e-6
+        ref = orc.predict_pose(params, img0[k:k + 1], img1[k:k + 1]).numpy()
+        assert rel(many[k], ref) < REL_TOL
