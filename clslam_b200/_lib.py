@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / 'libclslam_b200.so'
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT, PAD_FULL = 0, 1, 2
 TMA_IN_HALO_VALID = 1          # clslam_conv_tma.flags
+TMA_SPLITK_COUNTERS = 256      # ints behind clslam_conv_tma.splitk_counters
 IN_PLAIN, IN_UPCAT = 0, 1
 DEPTH_INV, DEPTH_MIN_ONLY, DEPTH_MIN_MAX = 0, 1, 2
 N_LOSS_SLOTS = 24
@@ -35,7 +36,8 @@ class ConvTma(Structure):
     """clslam_conv_tma"""
     _fields_ = [('inp', Planes), ('pad_mode', c_int), ('cout', c_int), ('w_hi', c_void_p), ('w_lo', c_void_p),
                 ('scale', c_void_p), ('shift', c_void_p), ('act', c_int), ('residual', POINTER(Planes)), ('gate', c_void_p), ('gate_act', c_int), ('y', c_void_p),
-                ('out', POINTER(Planes)), ('out_up', c_int), ('out_halo', c_int), ('taps', c_int), ('flags', c_int)]
+                ('out', POINTER(Planes)), ('out_up', c_int), ('out_halo', c_int), ('taps', c_int), ('flags', c_int),
+                ('splitk_counters', c_void_p)]
 
 
 class PhotoArgs(Structure):

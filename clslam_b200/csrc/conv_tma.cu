@@ -99,6 +99,11 @@ struct TmaConvArgs {
   FastDiv div_ks;
   float* part;
   long long part_stride;         // elements between two z slices = n_img * ho * wo * cout
+  // fused split-K reduction: one counter per (tile, N block).  The CTA whose atomic increment finds ksplit - 1 is the last
+  // slice of that tile to land: its epilogue warps add the ksplit partial sums (fixed z order: the result does not depend on
+  // which CTA came last) and run the real epilogue, then reset the counter for the next launch.  No second kernel, nobody
+  // spins.  nullptr: partial sums only (tma_splitk_epilogue_kernel / dgrad_fold_splitk_kernel reduce them).
+  int* counters;
   // tall form (TALL instantiations only): the input is addressed as ONE image of tall_n * tall_hp rows -- the images of the
   // planes buffer stacked with their halo rows, which are valid padding (reflection halo, or zeros for a zero-padded layer
   // whose producer left the halo untouched).  A 16-row tile then covers 16 / tall_hp images instead of wasting 16 - h rows:
@@ -126,6 +131,7 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* t_empty = t_full + 4;
   uint64_t* b_res = t_empty + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_res + 1);
+  volatile uint32_t* sk_last = tmem_slot + 2;          // split-K: "this CTA holds the last slice of the tile" (epilogue warps)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TMA_STAMP(0, threadIdx.x == 0);
@@ -346,28 +352,8 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         if (!TMA_DBG(g, 128)) tc_fence_after();
         TMA_STAMP(8, warp == 2 && lane == 0 && it == 0);
-#pragma unroll 1
-        for (int c = slot * 8; c < BN; c += 32) {
-          uint32_t r[8];
-          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + c), r);
-          TMA_STAMP(9, warp == 2 && lane == 0 && it == 0 && c == slot * 8);
-          if constexpr (C::kNcat) {               // + the A_hi.B_lo block
-            uint32_t r2[8];
-            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + BN + c), r2);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-          }
-          const int n = nb * BN + c;
-          if (!ok || n >= g.cout || TMA_DBG(g, 2)) continue;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
-          if constexpr (SK) {                     // raw partial sums; the epilogue proper runs in tma_splitk_epilogue_kernel
-            float* p = part + y_off + n;
-            *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
-            continue;
-          }
+        // scale / shift / residual / activation / gate, then fp32 and / or planes (primary cell, nearest-2x footprint, halo)
+        auto finish = [&](float (&v)[8], int n) {
           if (g.scale) {
             const float4 s0 = ld4(g.scale + n), s1 = ld4(g.scale + n + 4);
             v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
@@ -432,6 +418,69 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 }
               }
             }
+          }
+        };
+#pragma unroll 1
+        for (int c = slot * 8; c < BN; c += 32) {
+          uint32_t r[8];
+          tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + c), r);
+          TMA_STAMP(9, warp == 2 && lane == 0 && it == 0 && c == slot * 8);
+          if constexpr (C::kNcat) {               // + the A_hi.B_lo block
+            uint32_t r2[8];
+            tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + BN + c), r2);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          }
+          const int n = nb * BN + c;
+          if (!ok || n >= g.cout || TMA_DBG(g, 2)) continue;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[j]);
+          if constexpr (SK) {                     // raw partial sums of this K slice
+            float* p = part + y_off + n;
+            *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            continue;
+          }
+          finish(v, n);
+        }
+        if constexpr (SK) {
+          if (g.counters != nullptr) {
+            // the accumulator has been read: hand it back before the (possibly long) reduction below
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[as]);
+            // publish this CTA's slice, then find out whether it was the last one of the tile
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kTmaEpiWarps) : "memory");
+            if (warp == 2 && lane == 0) {
+              const int old = atomicAdd(&g.counters[tq], 1);
+              *sk_last = (old == g.ksplit - 1) ? 1u : 0u;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kTmaEpiWarps) : "memory");
+            if (*sk_last != 0u) {
+              __threadfence();                    // the other slices are visible (their CTAs fenced before incrementing)
+#pragma unroll 1
+              for (int c = slot * 8; c < BN; c += 32) {
+                const int n = nb * BN + c;
+                if (!ok || n >= g.cout) continue;
+                const float* p0 = g.part + y_off + n;
+                float v[8];
+                {
+                  const float4 a = __ldcg(reinterpret_cast<const float4*>(p0)), b = __ldcg(reinterpret_cast<const float4*>(p0 + 4));
+                  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                }
+                for (int z = 1; z < g.ksplit; ++z) {          // fixed order: deterministic whichever CTA reduces
+                  const float* pz = p0 + (size_t)z * g.part_stride;
+                  const float4 a = __ldcg(reinterpret_cast<const float4*>(pz)), b = __ldcg(reinterpret_cast<const float4*>(pz + 4));
+                  v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+                }
+                finish(v, n);
+              }
+              if (warp == 2 && lane == 0) g.counters[tq] = 0;          // ready for the next launch / graph replay
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * kTmaEpiWarps) : "memory");          // sk_last is rewritten by the next item
+            continue;
           }
         }
         if (!TMA_DBG(g, 128)) tc_fence_before();
@@ -831,7 +880,7 @@ using namespace clslam;
 // Tall form (TmaConvArgs::tall_hp): > 0 = number of 16-row tiles when the images are walked as one stack, 0 = not applicable
 // (the caller did not vouch for the halo, other kernel shapes, a single image) or no fewer tiles than one image at a time
 static int tma_tall_tiles_y(const clslam_conv_tma* p, int taps, int kc, int bn) {
-  if (!(p->flags & CLSLAM_TMA_IN_HALO_VALID) || taps != 3 || p->pad_mode == CLSLAM_PAD_FULL || p->in.n < 2) return 0;
+  if (!(p->flags & CLSLAM_TMA_IN_HALO_VALID) || (taps != 3 && taps != 2) || p->pad_mode == CLSLAM_PAD_FULL || p->in.n < 2) return 0;
   if (kc != 64 || bn != 128) return 0;                      // instantiated for the layers that have small maps
   const long long rows = (long long)p->in.n * (p->in.h + 2) - 2;         // output rows of the stack
   const long long tall = (rows + kTmaTH - 1) / kTmaTH;
@@ -940,7 +989,7 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
   }
   const bool padded_view = p->pad_mode == CLSLAM_PAD_REFLECT || tall;
   __nv_bfloat16* abase = reinterpret_cast<__nv_bfloat16*>(in.base) + in.c_off + (padded_view ? 0 : ((size_t)wp + 1) * in.c_total);
-  g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : (taps == 1 ? 0 : -1));      // 4x4: input rows o - 2 .. o + 1; 2x2: o - 1 .. o; 1x1: o
+  g.org = padded_view ? 0 : ((full || taps == 4) ? -2 : (taps == 1 ? 0 : -1));      // (tall 2x2: padded rows v, v + 1 = input rows v - 1, v)      // 4x4: input rows o - 2 .. o + 1; 2x2: o - 1 .. o; 1x1: o
   const cuuint64_t adims[5] = {(cuuint64_t)cin, (cuuint64_t)(padded_view ? wp : in.w),
                                (cuuint64_t)(tall ? (long long)in.n * hp : (padded_view ? hp : in.h)), (cuuint64_t)(tall ? 1 : in.n), 2};
   const cuuint64_t astr[4] = {(cuuint64_t)in.c_total * 2, (cuuint64_t)wp * in.c_total * 2, (cuuint64_t)hp * wp * in.c_total * 2,
@@ -965,17 +1014,25 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
       if (workspace_bytes < sp.ksplit * slice * 4) {
         set_error("conv3x3_tma: workspace too small (%lld < %lld)", workspace_bytes, sp.ksplit * slice * 4); return -2;
       }
-      TmaConvArgs k = g;                    // the main kernel only stores raw partial sums
-      k.scale = nullptr; k.shift = nullptr; k.res = PlaneView{}; k.gate = nullptr; k.y = nullptr; k.out = PlaneView{};
-      k.act = CLSLAM_ACT_NONE;
+      // fused reduction: the CTA holding the last slice of a tile reduces and runs the epilogue (needs the caller's counters;
+      // the dgrad fold keeps its own reduction, and more tiles than counters fall back to the epilogue kernel)
+      const bool fused = p->splitk_counters != nullptr && fold == nullptr && items <= CLSLAM_TMA_SPLITK_COUNTERS;
+      TmaConvArgs k = g;
+      if (!fused) {                         // the main kernel only stores raw partial sums
+        k.scale = nullptr; k.shift = nullptr; k.res = PlaneView{}; k.gate = nullptr; k.y = nullptr; k.out = PlaneView{};
+        k.act = CLSLAM_ACT_NONE;
+      }
+      k.counters = fused ? p->splitk_counters : nullptr;
       k.ksplit = sp.ksplit; k.cs_per = sp.cs_per; k.div_ks = make_fastdiv(sp.ksplit);
       k.part = reinterpret_cast<float*>(workspace); k.part_stride = slice;
       int rc;
-      if (taps == 2) rc = launch_tma_conv<64, 128, 2, true>(ma, mb, k, st);
+      if (taps == 2 && tall) rc = launch_tma_conv<64, 128, 2, true, true>(ma, mb, k, st);
+      else if (taps == 2) rc = launch_tma_conv<64, 128, 2, true>(ma, mb, k, st);
       else if (tall) rc = launch_tma_conv<64, 128, 3, true, true>(ma, mb, k, st);
       else if (bn == 128) rc = launch_tma_conv<64, 128, 3, true>(ma, mb, k, st);
       else rc = launch_tma_conv<64, 64, 3, true>(ma, mb, k, st);
       if (rc) return rc;
+      if (fused) return 0;
       if (fold) {        // dgrad of a reflection-padded layer: the fold adds the slices itself
         if (folded) *folded = true;
         return launch_fold(k.part, sp.ksplit, slice, in.n, in.h, in.w, cout, *fold, st);
@@ -1006,6 +1063,7 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
     return -1;
   }
   if (taps == 2) {
+    if (kc == 64 && bn == 128 && tall) return launch_tma_conv<64, 128, 2, false, true>(ma, mb, g, st);
     if (kc == 64 && bn == 128) return launch_tma_conv<64, 128, 2>(ma, mb, g, st);
     set_error("conv3x3_tma: the 2x2 form is built for input channels %% 64 == 0 and output channels %% 128 == 0");
     return -1;

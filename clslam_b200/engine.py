@@ -48,6 +48,8 @@ def _flag(name: str, default: str = '1') -> bool:
 # small-map layers with 64-multiple channels take the TMA kernel in its split-K form (clslam_conv3x3_tma_ws) instead of the
 # round-1a gather kernels
 TMA_SPLITK = _flag('CLSLAM_TMA_SPLITK')
+# with TMA_SPLITK: the split launches reduce their K slices themselves (last-arriving CTA) instead of a second kernel
+TMA_SPLITK_FUSED = _flag('CLSLAM_TMA_SPLITK_FUSED')
 # with TMA_SPLITK: also move the weight gradients of those layers to clslam_wgrad3x3_tma (measured slower at batch 1: off)
 TMA_SPLITK_WGRAD = _flag('CLSLAM_TMA_SPLITK_WGRAD', '0')
 # the dispconv weight gradients run on lane 1 (ahead of the short pose branch) instead of lane 2, whose wgrad chain is the
@@ -283,11 +285,16 @@ class Plan:
         if out is not None:
             a.out = ctypes.pointer(out)
         a.out_up, a.out_halo, a.taps = out_up, out_halo, taps
-        if TMA_TALL and taps == 3 and pad_mode != L.PAD_FULL:
+        if TMA_TALL and taps in (2, 3) and pad_mode != L.PAD_FULL:          # (2: the space-to-depth planes have an all-zero halo)
             a.flags = L.TMA_IN_HALO_VALID
         self.keep.append(a)
         if TMA_SPLITK:      # small layers split K over the SMs (workspace: raw partial sums); large ones run the plain kernel
-            self.need_ws(self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a)))
+            ws = self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+            self.need_ws(ws)
+            if ws > 0 and TMA_SPLITK_FUSED:
+                # the CTA that delivers the last K slice of a tile reduces and runs the epilogue: no second launch.  The counters
+                # belong to this launch site (the kernel leaves them at zero)
+                a.splitk_counters = self.alloc(L.TMA_SPLITK_COUNTERS, dtype=torch.int32, zero=True).data_ptr()
             self.ops.append((name, lambda stream, ws, arg: self.lib.clslam_conv3x3_tma_ws(ctypes.byref(arg), ws, self.ws_bytes, stream),
                              (a,), self.lane))
             return

@@ -148,7 +148,12 @@ typedef struct clslam_conv_tma {
                               4: 4x4 kernel over input rows / cols o-2 .. o+1, zero padded, weights [cout][4][4][in.c]
                               (the space-to-depth form of the encoders' 7x7 / stride-2 conv1, clslam_stage_images_s2d) */
   int flags;               /* CLSLAM_TMA_* bits, 0 = none */
+  int* splitk_counters;    /* optional, clslam_conv3x3_tma_ws only: CLSLAM_TMA_SPLITK_COUNTERS zero-initialised ints owned by THIS
+                              launch site.  When the launch splits K, the CTA that delivers the last K slice of a tile adds the
+                              slices (fixed order, deterministic) and runs the epilogue itself: no second kernel.  The kernel
+                              leaves the counters at zero.  NULL: separate reduction / epilogue kernel (round-1 form). */
 } clslam_conv_tma;
+#define CLSLAM_TMA_SPLITK_COUNTERS 256
 /* flags bit (experimental): the stored halo ring of `in` is valid padding for this layer -- the reflection halo for
  * CLSLAM_PAD_REFLECT (always required), all zeros for CLSLAM_PAD_ZERO (true when the producer wrote the planes with
  * out_halo = 0 into a zero-initialised buffer).  The kernel may then walk the n images as ONE stack of n * (h + 2) rows, so

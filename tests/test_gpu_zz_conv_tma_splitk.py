@@ -306,3 +306,101 @@ def test_tall_form_is_bit_identical_to_the_plain_kernel(case, split):
     xq = buf.value()
     ref = F.relu(F.conv2d(xq, wt) + shift.view(1, -1, 1, 1) + (rbuf.value()[:, :, 1:-1, 1:-1] if use_res else 0))
     assert cabi.rel_err(cabi.nchw(y1), ref) < TOL
+
+
+FUSED_CASES = [
+    # n, h, w, ci, co, pad_mode, act, use_scale, use_res, up, taps
+    (1, 6, 20, 512, 512, L.PAD_ZERO, L.ACT_RELU, True, True, 1, 3),           # depth layer4 conv2 (BasicBlock tail: BN + residual + ReLU)
+    (2, 6, 20, 512, 512, L.PAD_ZERO, L.ACT_RELU, True, False, 1, 3),
+    (1, 24, 80, 128, 128, L.PAD_ZERO, L.ACT_RELU, True, True, 1, 3),
+    (1, 12, 40, 512, 256, L.PAD_REFLECT, L.ACT_ELU, False, False, 2, 3),      # upconv_4_1 -> nearest 2x + reflection halo on write
+    (1, 24, 80, 128, 64, L.PAD_REFLECT, L.ACT_ELU, False, False, 1, 3),       # N block 64 (N-concatenated weight tile)
+    (1, 7, 19, 64, 64, L.PAD_ZERO, L.ACT_NONE, False, False, 1, 3),           # ragged tiles
+]
+
+
+@pytest.mark.parametrize('case', FUSED_CASES)
+def test_fused_splitk_reduction_matches_the_two_kernel_form(case):
+    """clslam_conv_tma.splitk_counters: the CTA that delivers the last K slice of a tile adds the slices (fixed order) and runs
+    the epilogue itself.  Same partial sums, same summation order as tma_splitk_epilogue_kernel -> bit-identical results; the
+    counters are back at zero afterwards, so the launch can be replayed (CUDA graph) without re-initialising anything."""
+    lib = cabi.lib()
+    n, h, w, ci, co, pad_mode, act, use_scale, use_res, up, taps = case
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    scale = (1.0 + 0.2 * rnd(co, seed=3)) if use_scale else None
+    shift = 0.1 * rnd(co, seed=4)
+    buf = PlaneBuf(n, h, w, ci)
+    buf.set_padded(F.pad(x, (1, 1, 1, 1), mode='reflect' if pad_mode == L.PAD_REFLECT else 'constant'))
+    res_desc = None
+    if use_res:
+        rbuf = PlaneBuf(n, h, w, co)
+        rbuf.set_padded(F.pad(rnd(n, co, h, w, seed=5), (1, 1, 1, 1)))
+        res_desc = rbuf.desc()
+    outs = []
+    counters = torch.zeros(L.TMA_SPLITK_COUNTERS, dtype=torch.int32, device='cuda')
+    for fused in (False, True, True):          # the second fused launch reuses the counters the first one left behind
+        keep = []
+        y = torch.full((n, h, w, co), float('nan'), device='cuda')
+        ob = PlaneBuf(n, h * up, w * up, co, fill=3.0)
+        od = ob.desc()
+        a = _args(buf.desc(), pad_mode, cabi.krsc(wt), scale, shift, act, res_desc, y, od, up, 1, None, L.ACT_NONE, taps, keep)
+        if fused:
+            a.splitk_counters = counters.data_ptr()
+        nbytes = lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+        assert nbytes > 0
+        ws = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device='cuda')
+        n0 = lib.clslam_launch_count()
+        L.check(lib.clslam_conv3x3_tma_ws(ctypes.byref(a), ws.data_ptr(), nbytes, cabi.stream()), 'conv3x3_tma_ws')
+        torch.cuda.synchronize()
+        assert lib.clslam_launch_count() - n0 == (1 if fused else 2)
+        assert int(counters.abs().sum()) == 0
+        outs.append((y, ob))
+    (y0, o0), (y1, o1), (y2, o2) = outs
+    assert not torch.isnan(y1).any()
+    assert torch.equal(y1, y0) and torch.equal(o1.t, o0.t)
+    assert torch.equal(y2, y0) and torch.equal(o2.t, o0.t)
+    xq = buf.value()
+    ref = F.conv2d(xq, wt)
+    if scale is not None:
+        ref = ref * scale.view(1, -1, 1, 1)
+    ref = ref + shift.view(1, -1, 1, 1) + (rbuf.value()[:, :, 1:-1, 1:-1] if use_res else 0)
+    assert cabi.rel_err(cabi.nchw(y1), cabi.act_ref(ref, act)) < TOL
+
+
+@pytest.mark.parametrize('split', [False, True])
+@pytest.mark.parametrize('n,h,w,ci,co', [(8, 12, 40, 256, 512), (16, 12, 40, 256, 512), (2, 12, 40, 256, 512), (8, 24, 80, 128, 256)])
+def test_tall_form_of_the_stride2_space_to_depth_conv(n, h, w, ci, co, split):
+    """taps = 2 with CLSLAM_TMA_IN_HALO_VALID: the 3x3 / stride-2 convolutions (layerX.0.conv1) walk the space-to-depth planes
+    of all images as one stack (their halo is all zeros): 6 x 20 maps put two images into one 16-row tile"""
+    from clslam_b200.engine import s2d_weights_3x3s2
+    lib = cabi.lib()
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    xg = cabi.nhwc(x).float().cuda()
+    s2d = PlaneBuf(n, h // 2, w // 2, 4 * ci)
+    sd = s2d.desc()
+    L.check(lib.clslam_planes_s2d_from_f32(xg.data_ptr(), ctypes.byref(sd), n, h, w, ci, cabi.stream()), 's2d')
+    torch.cuda.synchronize()
+    wk = s2d_weights_3x3s2(wt.float()).contiguous()
+    outs = []
+    for flags in (0, L.TMA_IN_HALO_VALID):
+        keep = []
+        y = torch.full((n, h // 2, w // 2, co), float('nan'), device='cuda')
+        a = _args(sd, L.PAD_ZERO, wk, None, None, L.ACT_RELU, None, y, None, 1, 0, None, L.ACT_NONE, 2, keep)
+        a.flags = flags
+        if split:
+            nbytes = lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+            ws = torch.full((max(nbytes, 16),), 0xFF, dtype=torch.uint8, device='cuda')
+            L.check(lib.clslam_conv3x3_tma_ws(ctypes.byref(a), ws.data_ptr(), nbytes, cabi.stream()), 'conv3x3_tma_ws')
+        else:
+            L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma')
+        torch.cuda.synchronize()
+        outs.append(y)
+    assert not torch.isnan(outs[1]).any()
+    if split:
+        assert cabi.rel_err(outs[1], outs[0]) < SAME_PRODUCTS
+    else:
+        assert torch.equal(outs[1], outs[0])
+    ref = F.relu(F.conv2d(x.float().double(), wt, stride=2, padding=1))
+    assert cabi.rel_err(cabi.nchw(outs[1]), ref) < TOL
