@@ -48,8 +48,14 @@ def _flag(name: str, default: str = '1') -> bool:
 # small-map layers with 64-multiple channels take the TMA kernel in its split-K form (clslam_conv3x3_tma_ws) instead of the
 # round-1a gather kernels
 TMA_SPLITK = _flag('CLSLAM_TMA_SPLITK')
-# with TMA_SPLITK: the split launches reduce their K slices themselves (last-arriving CTA) instead of a second kernel
-TMA_SPLITK_FUSED = _flag('CLSLAM_TMA_SPLITK_FUSED')
+# with TMA_SPLITK: the split launches reduce their K slices themselves (the CTA that delivers the last slice of a tile adds
+# them and runs the epilogue) instead of a second kernel.  Bit-identical, 34 launches fewer at batch 1 -- and measured SLOWER
+# (batch 1: 1.06 -> 1.67 ms / step, profiles/r02_splitk_fused.md): one CTA walks ksplit x 64 KB of partial sums through L2
+# latency that the separate epilogue kernel spreads over the whole GPU.  Off by default.
+TMA_SPLITK_FUSED = _flag('CLSLAM_TMA_SPLITK_FUSED', '0')
+# the 1x1 / stride-2 down-sampling convolution of a BasicBlock runs on a side lane next to the block's conv1 (both only need
+# the block input); conv2 joins them
+DS_SIDE_LANE = _flag('CLSLAM_DS_SIDE_LANE')
 # with TMA_SPLITK: also move the weight gradients of those layers to clslam_wgrad3x3_tma (measured slower at batch 1: off)
 TMA_SPLITK_WGRAD = _flag('CLSLAM_TMA_SPLITK_WGRAD', '0')
 # the dispconv weight gradients run on lane 1 (ahead of the short pose branch) instead of lane 2, whose wgrad chain is the
@@ -452,7 +458,7 @@ def conv1_s2d_ok(n: int, h: int, w: int, cin_pad: int) -> bool:
 
 def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Tensor], n: int, h: int, w: int, tag: str,
                   skips: Optional[Dict[int, L.Planes]] = None, feat4_planes: Optional[L.Planes] = None,
-                  x_s2d: Optional[L.Planes] = None) -> List[torch.Tensor]:
+                  x_s2d: Optional[L.Planes] = None, side_lane: Optional[int] = None) -> List[torch.Tensor]:
     """ResNet-18 trunk (networks/resnet_encoder.py:115-125) over an NHWC staged input; returns the
     five fp32 NHWC feature maps.  3x3 / stride-1 convolutions run the TMA kernel on bf16 hi/lo planes
     (intermediate activations then exist only as planes); conv1, the stride-2 convolutions and the 1x1
@@ -491,6 +497,10 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Te
             mid_pl = PlaneBuf(plan, n, ho, wo, planes).view() if use2 else None
             mid_f32 = plan.alloc(n, ho, wo, planes) if not use2 else None
             use_s2 = stride == 2 and use2 and planes % 128 == 0 and cin % 16 == 0 and hc % 2 == 0 and wc % 2 == 0
+            in_ready = f'{tag}.{p}.in'
+            has_ds = (p + '.ds.w') in t and side_lane is not None and side_lane != plan.lane and DS_SIDE_LANE
+            if has_ds and not use_s2:
+                plan.record(in_ready)
             if use1:
                 plan.conv_tma(f'{tag}.{p}.conv1', x_pl, L.PAD_ZERO, planes, t[p + '.conv1.w_hi'], t[p + '.conv1.w_lo'],
                               t[p + '.bn1.scale'], t[p + '.bn1.shift'], L.ACT_RELU, y=mid_f32, out=mid_pl)
@@ -499,6 +509,8 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Te
                 s2d = s2d_buf.view()
                 plan.add(f'{tag}.{p}.s2d', lambda stream, ws, xp, o, hh, ww, cc: plan.lib.clslam_planes_s2d_from_f32(
                     xp, ctypes.byref(o), n, hh, ww, cc, stream), _p(x_f32), s2d, hc, wc, cin)
+                if has_ds:
+                    plan.record(in_ready)
                 hl = t[p + '.conv1.s2d_hl']
                 plan.conv_tma(f'{tag}.{p}.conv1', s2d, L.PAD_ZERO, planes, hl[0], hl[1], t[p + '.bn1.scale'], t[p + '.bn1.shift'],
                               L.ACT_RELU, y=mid_f32, out=mid_pl, taps=2)
@@ -510,6 +522,12 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Te
                 dd = plan.desc(n, hc, wc, cin, planes, 1, stride, 0, act=L.ACT_NONE)
                 idt_pl = PlaneBuf(plan, n, ho, wo, planes).view() if use2 else None
                 idt_f32 = plan.alloc(n, ho, wo, planes) if not use2 else None
+                home = plan.lane
+                on_side = side_lane is not None and side_lane != home and DS_SIDE_LANE
+                if on_side:          # the block input is complete on `home` at this point in program order... but conv1 was
+                    # issued first: record where the input became available (before conv1) -- see `in_ready` above
+                    plan.set_lane(side_lane)
+                    plan.wait(in_ready)
                 if TMA_DS and use_s2 and cin % 64 == 0:
                     hl = t[p + '.ds.w_hl']          # [2][planes][1][1][cin]
                     plan.conv_tma(f'{tag}.{p}.downsample', s2d_buf.view(0, cin), L.PAD_ZERO, planes, hl[0], hl[1],
@@ -517,6 +535,10 @@ def build_encoder(plan: Plan, prep: PreparedEncoder, x_staged: Optional[torch.Te
                 else:
                     plan.conv_fwd(f'{tag}.{p}.downsample', dd, x_f32, None, t[p + '.ds.w'], t[p + '.dsbn.scale'],
                                   t[p + '.dsbn.shift'], None, idt_f32, t[p + '.ds.w_hi'], t[p + '.ds.w_lo'], out=idt_pl)
+                if on_side:
+                    plan.record(f'{tag}.{p}.ds_done')
+                    plan.set_lane(home)
+                    plan.wait(f'{tag}.{p}.ds_done')
             else:
                 idt_pl, idt_f32 = x_pl, x_f32
             # ---- conv2 (+ identity, ReLU) -> block output.  Block 0 feeds block 1 of the same layer (planes when that
@@ -747,7 +769,7 @@ class AdaptEngine:
         u0, u1, cat, skips, feat4_pl, fh, fw = decoder_geometry(plan, b, h, w)
         y1_pl = {}
         feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc', skips=skips, feat4_planes=feat4_pl,
-                              x_s2d=depth_s2d)
+                              x_s2d=depth_s2d, side_lane=2)
         self.depth_feats = feats
         dd = 'depth_decoder'
         self.y = {}          # decoder activations (ELU outputs), NHWC fp32 (dispconv, backward)
@@ -811,7 +833,10 @@ class AdaptEngine:
                                                                                   (self.rgb_aug[1], self.rgb_aug[2], b, b)], 2 * b, h, w)
         # with TMA_DS the last pose feature is also written as planes: the 1x1 `squeeze` then runs the TMA kernel (taps = 1)
         pf4_pl = PlaneBuf(plan, 2 * b, h >> 5, w >> 5, ENC_CH[4]).view() if (TMA_DS and tma_ok(2 * b, h >> 5, w >> 5, 512, 256)) else None
-        pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc', x_s2d=pose_s2d, feat4_planes=pf4_pl)
+        # (lane 3, not 2: lane 2 holds dispconv_1..3 by now, which wait for late decoder stages -- stream order would park the
+        # pose encoder's down-sampling convolutions behind them)
+        pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc', x_s2d=pose_s2d, feat4_planes=pf4_pl,
+                               side_lane=3)
         pf4 = pfeats[4]
         hp, wp = pf4.shape[1], pf4.shape[2]
         self.pose_hw = (hp, wp)
@@ -891,7 +916,7 @@ class AdaptEngine:
         la.losses, la.smooth_grad = _p(self.losses), _p(self.smooth_grad)
         self.loss_args = la
         plan.keep.append(la)
-        plan.join((1, 2))
+        plan.join((1, 2, 3) if DS_SIDE_LANE else (1, 2))
         self.n_net_ops = len(plan.ops)       # ops [0, n_net_ops) read rgb_aug / intrinsics only: the first graph of H2D_OVERLAP
         if H2D_OVERLAP:
             plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
