@@ -131,6 +131,8 @@ SIGNATURES = {
     'clslam_u8_to_f32_chw': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'clslam_color_jitter_workspace_bytes': (c_longlong, [c_int]),
     'clslam_color_jitter_op': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_longlong, c_void_p]),
+    'clslam_dispconv_dgrad_act_emit': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(Planes), c_int, c_int, c_int,
+                                               c_int, c_void_p]),
     'clslam_adam_tick': (c_int, [c_void_p, c_void_p]),
     'clslam_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double,
                                  c_double, c_int, c_void_p, c_void_p]),

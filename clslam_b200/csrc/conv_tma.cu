@@ -688,6 +688,24 @@ __device__ __forceinline__ void dgrad_fold_body(const float* __restrict__ dxp, i
     const int oh = (int)(p % ho);
     const int img = (int)(p / ho);
     float4 acc = f4zero();
+    const int h0 = oh * up, w0 = ow * up;
+    if (h0 >= 2 && h0 + up <= H - 2 && w0 >= 2 && w0 + up <= W - 2) {
+      // interior: no halo cell mirrors onto this pixel -- the up x up cells, all loads issued before the first add
+      const size_t base = (((size_t)img * (H + 2) + h0 + 1) * Wp + w0 + 1) * c + cc;
+      if constexpr (SK) {
+        for (int z = 0; z < ksplit; ++z) {
+          const float* pz = dxp + (size_t)z * part_stride + base;
+          float4 v0 = ld4(pz), v1 = f4zero(), v2 = f4zero(), v3 = f4zero();
+          if (up == 2) { v1 = ld4(pz + c); v2 = ld4(pz + (size_t)Wp * c); v3 = ld4(pz + (size_t)Wp * c + c); }
+          f4add(v0, v1); f4add(v2, v3); f4add(v0, v2); f4add(acc, v0);
+        }
+      } else {
+        float4 v0 = ld4(dxp + base), v1 = f4zero(), v2 = f4zero(), v3 = f4zero();
+        if (up == 2) { v1 = ld4(dxp + base + c); v2 = ld4(dxp + base + (size_t)Wp * c); v3 = ld4(dxp + base + (size_t)Wp * c + c); }
+        f4add(v0, v1); f4add(v2, v3); f4add(v0, v2);
+        acc = v0;
+      }
+    } else
     for (int a = 0; a < up; ++a) {
       const int hh = oh * up + a;                       // interior row of the layer input
       int rows[3] = {hh + 1, hh == 1 ? 0 : -1, hh == H - 2 ? H + 1 : -1};

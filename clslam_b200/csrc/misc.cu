@@ -104,16 +104,25 @@ dispconv_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, co
     int b = 0, hh = 0, ww = 0;
     if (p < total) {
       tile_order(p, h, wd, b, hh, ww);
+      // one 64-bit base address per pixel, 32-bit row / column offsets per tap (the round-1 kernel redid the full 64-bit index
+      // arithmetic for each of the nine taps: ~1400 thread-instructions per pixel); all nine loads are issued
+      // before the first multiply-add
+      const float* xb = x + (((size_t)b * h + hh) * wd + ww) * CI + sub * 4;
+      int dr[3], dc[3];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const int ih = reflect_idx(hh + r - 1, h);
+        dr[r] = (reflect_idx(hh + r - 1, h) - hh) * wd * CI;
+        dc[r] = (reflect_idx(ww + r - 1, wd) - ww) * CI;
+      }
+      float4 v[9];
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-          const int iw = reflect_idx(ww + s - 1, wd);
-          const float4 v = ld4(x + (((size_t)b * h + ih) * wd + iw) * CI + sub * 4);
-          const float4 k = wr[r * 3 + s];
-          acc = fmaf(v.x, k.x, acc); acc = fmaf(v.y, k.y, acc); acc = fmaf(v.z, k.z, acc); acc = fmaf(v.w, k.w, acc);
-        }
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int s = 0; s < 3; ++s) v[r * 3 + s] = ld4(xb + dr[r] + dc[s]);
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        const float4 k = wr[t];
+        acc = fmaf(v[t].x, k.x, acc); acc = fmaf(v[t].y, k.y, acc); acc = fmaf(v[t].z, k.z, acc); acc = fmaf(v[t].w, k.w, acc);
       }
     }
 #pragma unroll
@@ -238,7 +247,7 @@ dispconv_wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ d
 // ---- dispconv dgrad when it is the only consumer: dz_prev = act'(y_prev) * dX ---------------
 __global__ void __launch_bounds__(256)
 dispconv_dgrad_act_kernel(const float* __restrict__ dz, const float* __restrict__ w, const float* __restrict__ y_prev,
-                          int act_prev, float* __restrict__ dz_prev, int n, int h, int wd, int ci) {
+                          int act_prev, float* __restrict__ dz_prev, int n, int h, int wd, int ci, PlaneView po) {
   pdl_wait();
   pdl_trigger();
   const int c4 = ci / 4;
@@ -256,6 +265,10 @@ dispconv_dgrad_act_kernel(const float* __restrict__ dz, const float* __restrict_
     g.z *= act_grad_from_output(yv.z, act_prev);
     g.w *= act_grad_from_output(yv.w, act_prev);
     *reinterpret_cast<float4*>(dz_prev + i * 4) = g;
+    if (po.base) {
+      const float v[4] = {g.x, g.y, g.z, g.w};
+      planes_emit<4>(po, b, hh, ww, cc, v);
+    }
   }
 }
 
@@ -396,12 +409,25 @@ int clslam_dispconv_wgrad(const float* x, const float* dz, float* dw, float* db,
   return finish_launch("dispconv_wgrad_reduce");
 }
 
+int clslam_dispconv_dgrad_act_emit(const float* dz, const float* w, const float* y_prev, int act_prev, float* dz_prev,
+                                   const clslam_planes* dz_prev_planes, int n, int h, int w_, int ci, void* stream) {
+  if (ci % 4) { set_error("dispconv_dgrad: ci %% 4 != 0"); return -1; }
+  PlaneView po{};
+  if (dz_prev_planes) {
+    const clslam_planes* q = dz_prev_planes;
+    if (!q->base || q->n != n || q->h != h || q->w != w_ || q->c != ci || q->c_total % 8 || q->c_off % 4) {
+      set_error("dispconv_dgrad: planes mismatch"); return -1;
+    }
+    po = make_plane_view(q, 1, 0);
+  }
+  launch_k(dispconv_dgrad_act_kernel, dim3(grid_for((size_t)n * h * w_ * (ci / 4))), dim3(256), 0, as_stream(stream), dz, w, y_prev, act_prev,
+                                                                                                 dz_prev, n, h, w_, ci, po);
+  return finish_launch("dispconv_dgrad_act");
+}
+
 int clslam_dispconv_dgrad_act(const float* dz, const float* w, const float* y_prev, int act_prev, float* dz_prev, int n,
                               int h, int w_, int ci, void* stream) {
-  if (ci % 4) { set_error("dispconv_dgrad: ci %% 4 != 0"); return -1; }
-  launch_k(dispconv_dgrad_act_kernel, dim3(grid_for((size_t)n * h * w_ * (ci / 4))), dim3(256), 0, as_stream(stream), dz, w, y_prev, act_prev,
-                                                                                                 dz_prev, n, h, w_, ci);
-  return finish_launch("dispconv_dgrad_act");
+  return clslam_dispconv_dgrad_act_emit(dz, w, y_prev, act_prev, dz_prev, nullptr, n, h, w_, ci, stream);
 }
 
 int clslam_adam_tick(int* step_dev, void* stream) {

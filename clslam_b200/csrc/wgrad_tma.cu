@@ -241,25 +241,32 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
   const int r = tap / 3, s = tap - r * 3;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int o = to * 32 + tx;
+  // the four rows (c = ty, ty + 8, ..) of a thread are summed side by side, two chains each: eight loads in flight (with 148
+  // splits of a thin layer a single chain is 148 dependent L2 round trips); fixed order per output (deterministic)
+  const float* pj[4];
+  bool okj[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int cl = ty + 8 * j, c = tc * 32 + cl;
-    float v = 0.f;
-    if (o < co && c < ci) {
-      const int pair = (o / cob) * ci_chunks + c / cc;
-      const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
-      // fixed summation order (deterministic), four independent chains so the loads overlap
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int k = 0;
-      for (; k + 4 <= splits; k += 4) {
-        a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride];
-        a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
-      }
-      for (; k < splits; ++k) a0 += p[(size_t)k * cta_stride];
-      v = (a0 + a1) + (a2 + a3);
-    }
-    tile[cl][tx] = v;
+    const int c = tc * 32 + ty + 8 * j;
+    okj[j] = o < co && c < ci;
+    const int cs = okj[j] ? c : 0, os = okj[j] ? o : 0;
+    const int pair = (os / cob) * ci_chunks + cs / cc;
+    pj[j] = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + cs % cc) * cols + s * cob + os % cob;
   }
+  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+  int k = 0;
+  for (; k + 2 <= splits; k += 2) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (okj[j]) { a0[j] += pj[j][(size_t)k * cta_stride]; a1[j] += pj[j][(size_t)(k + 1) * cta_stride]; }
+    }
+  }
+  if (k < splits) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (okj[j]) a0[j] += pj[j][(size_t)k * cta_stride];
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = a0[j] + a1[j];
   __syncthreads();
   const int c = tc * 32 + tx;
 #pragma unroll
@@ -270,7 +277,7 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
 }
 
 // db[c] = sum over pixels of dz[p][c] (fp32 NHWC), deterministic: per-block partial sums, then a fixed-order reduction
-constexpr int kBiasBlocks = 148;
+constexpr int kBiasBlocks = 592;          // 4 per SM: the kernel is a latency-bound streaming sum
 __global__ void __launch_bounds__(256)
 bias_grad_partial_kernel(const float* __restrict__ dz, long long pixels, int c, float* __restrict__ part) {
   pdl_wait();
@@ -282,8 +289,19 @@ bias_grad_partial_kernel(const float* __restrict__ dz, long long pixels, int c, 
   const long long per = (pixels + gridDim.x - 1) / gridDim.x;
   const long long p0 = (long long)blockIdx.x * per, p1 = p0 + per < pixels ? p0 + per : pixels;
   float4 acc = f4zero();
-  if (pl < lanes)
-    for (long long p = p0 + pl; p < p1; p += lanes) f4add(acc, ld4(dz + p * c + qd * 4));
+  if (pl < lanes) {
+    // four independent loads in flight per thread; the four chains are combined in a fixed order (deterministic)
+    float4 a0 = f4zero(), a1 = f4zero(), a2 = f4zero(), a3 = f4zero();
+    long long p = p0 + pl;
+    for (; p + 3LL * lanes < p1; p += 4LL * lanes) {
+      const float4 v0 = ld4(dz + p * c + qd * 4), v1 = ld4(dz + (p + lanes) * c + qd * 4);
+      const float4 v2 = ld4(dz + (p + 2LL * lanes) * c + qd * 4), v3 = ld4(dz + (p + 3LL * lanes) * c + qd * 4);
+      f4add(a0, v0); f4add(a1, v1); f4add(a2, v2); f4add(a3, v3);
+    }
+    for (; p < p1; p += lanes) f4add(a0, ld4(dz + p * c + qd * 4));
+    f4add(a0, a1); f4add(a2, a3); f4add(a0, a2);
+    acc = a0;
+  }
   red[threadIdx.x] = acc;
   __syncthreads();
   if (threadIdx.x < quads) {

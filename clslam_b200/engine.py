@@ -1045,11 +1045,11 @@ class AdaptEngine:
                     plan.record('grads_disp')
                 plan.set_lane(0)
             if i == 0:
-                plan.simple('dispconv_0.dgrad', lib.clslam_dispconv_dgrad_act, _p(self.dz_disp[0]),
-                            flat.weight_ptr((dd, 'dispconv_0.conv')), _p(y1), L.ACT_ELU, _p(self.dz[(0, 1)]), b, hi_, wi_,
-                            DEC_CH[0])
-                if (0, 1) in dz_pl:
-                    plan.planes_from_f32('dz01.planes', self.dz[(0, 1)], dz_pl[(0, 1)])
+                pl01 = dz_pl.get((0, 1))
+                plan.add('dispconv_0.dgrad', lambda stream, ws, *a: lib.clslam_dispconv_dgrad_act_emit(
+                    *a[:5], ctypes.byref(a[5]) if a[5] is not None else None, *a[6:], stream),
+                    _p(self.dz_disp[0]), flat.weight_ptr((dd, 'dispconv_0.conv')), _p(y1), L.ACT_ELU, _p(self.dz[(0, 1)]), pl01,
+                    b, hi_, wi_, DEC_CH[0])          # (fp32 and planes from one launch)
                 plan.record('dz01')
             # upconv_i_1: wgrad + dgrad (to the up-sampled branch only; the skip feeds a frozen encoder)
             d1, y0, skip = self.dec_desc[(i, 1)]

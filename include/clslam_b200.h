@@ -255,6 +255,11 @@ int clslam_dispconv_wgrad(const float* x, const float* dz, float* dw, float* db,
                           void* workspace, long long workspace_bytes, void* stream);
 int clslam_dispconv_dgrad_act(const float* dz, const float* w, const float* y_prev, int act_prev,
                               float* dz_prev, int n, int h, int w_, int ci, void* stream);
+/* the same, additionally writing dz_prev as bf16 hi/lo planes (the operand of the tcgen05 dgrad / wgrad of upconv_0_1):
+ * saves the separate clslam_planes_from_f32 launch on the critical lane */
+int clslam_dispconv_dgrad_act_emit(const float* dz, const float* w, const float* y_prev, int act_prev,
+                                   float* dz_prev, const clslam_planes* dz_prev_planes, int n, int h, int w_, int ci,
+                                   void* stream);
 
 /* ---- pose head ----------------------------------------------------------------------------
  * mean over (W, H) * 0.01 -> (axis_angle, translation) of frame slot 0 (networks/pose_decoder.py:
