@@ -14,6 +14,7 @@ LIB_PATH = Path(__file__).resolve().parent / 'libclslam_b200.so'
 ACT_NONE, ACT_RELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3
 PAD_ZERO, PAD_REFLECT, PAD_FULL = 0, 1, 2
 TMA_IN_HALO_VALID = 1          # clslam_conv_tma.flags
+TMA_SPLITK_CLUSTER = 2         # clslam_conv_tma.flags
 TMA_SPLITK_COUNTERS = 256      # ints behind clslam_conv_tma.splitk_counters
 IN_PLAIN, IN_UPCAT = 0, 1
 DEPTH_INV, DEPTH_MIN_ONLY, DEPTH_MIN_MAX = 0, 1, 2

@@ -104,6 +104,11 @@ struct TmaConvArgs {
   // which CTA came last) and run the real epilogue, then reset the counter for the next launch.  No second kernel, nobody
   // spins.  nullptr: partial sums only (tma_splitk_epilogue_kernel / dgrad_fold_splitk_kernel reduce them).
   int* counters;
+  // cluster split-K: the ksplit slices of a tile are the CTAs of ONE thread-block cluster (launch attribute); every CTA stages
+  // its fp32 accumulator tile in its own shared memory, and after a cluster barrier CTA r adds rows [r, r + 1) * 128 / ksplit
+  // of all ksplit tiles over distributed shared memory (fixed rank order: deterministic) and runs the epilogue for them.  The
+  // partial sums never leave the chip, there is no second kernel and the epilogue is spread over the cluster.  0 = off
+  int cluster_ks;
   // tall form (TALL instantiations only): the input is addressed as ONE image of tall_n * tall_hp rows -- the images of the
   // planes buffer stacked with their halo rows, which are valid padding (reflection halo, or zeros for a zero-padded layer
   // whose producer left the halo untouched).  A 16-row tile then covers 16 / tall_hp images instead of wasting 16 - h rows:
@@ -112,6 +117,59 @@ struct TmaConvArgs {
   int tall_hp, tall_n;
   FastDiv div_hp;
 };
+
+
+// ---- cluster split-K helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem4(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+  return v;
+}
+
+// the epilogue proper for 8 output channels [n, n + 8) of output pixel (img, oh, ow): the same sequence as the fused epilogue
+// of conv3x3_tma_kernel (scale, shift, residual, activation, gate; fp32 and / or planes with nearest-2x footprint and halo)
+__device__ __forceinline__ void tma_epilogue_store(const TmaConvArgs& g, int img, int oh, int ow, int n, float (&v)[8]) {
+  const size_t y_off = (((size_t)img * g.ho + oh) * g.wo + ow) * g.cout;
+  if (g.scale) {
+    const float4 s0 = ld4(g.scale + n), s1 = ld4(g.scale + n + 4);
+    v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w; v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+  }
+  if (g.shift) {
+    const float4 s0 = ld4(g.shift + n), s1 = ld4(g.shift + n + 4);
+    v[0] += s0.x; v[1] += s0.y; v[2] += s0.z; v[3] += s0.w; v[4] += s1.x; v[5] += s1.y; v[6] += s1.z; v[7] += s1.w;
+  }
+  if (g.res.base) {
+    float r[8];
+    planes_load8(g.res, img, oh + 1, ow + 1, n, r);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] += r[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = act_fast(v[j], g.act);
+  if (g.gate) {
+    const float4 g0 = ld4(g.gate + y_off + n), g1 = ld4(g.gate + y_off + n + 4);
+    v[0] *= act_grad_from_output(g0.x, g.gate_act); v[1] *= act_grad_from_output(g0.y, g.gate_act);
+    v[2] *= act_grad_from_output(g0.z, g.gate_act); v[3] *= act_grad_from_output(g0.w, g.gate_act);
+    v[4] *= act_grad_from_output(g1.x, g.gate_act); v[5] *= act_grad_from_output(g1.y, g.gate_act);
+    v[6] *= act_grad_from_output(g1.z, g.gate_act); v[7] *= act_grad_from_output(g1.w, g.gate_act);
+  }
+  if (g.y) {
+    float* p = g.y + y_off + n;
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (g.out.base) planes_emit<8>(g.out, img, oh, ow, n, v);
+}
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 
@@ -352,6 +410,28 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
         if (!TMA_DBG(g, 128)) tc_fence_after();
         TMA_STAMP(8, warp == 2 && lane == 0 && it == 0);
+        if constexpr (SK) {
+          if (g.cluster_ks > 0) {
+            // cluster split-K: the raw accumulator tile of this K slice goes to this CTA's shared memory (the operand rings are
+            // idle: the accumulator is complete, and a clustered launch gives every CTA exactly one work item)
+            float* stage = reinterpret_cast<float*>(a_tiles) + (size_t)l * (BN + 4);
+#pragma unroll 1
+            for (int c = slot * 8; c < BN; c += 32) {
+              uint32_t r[8];
+              tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + c), r);
+              if constexpr (C::kNcat) {
+                uint32_t r2[8];
+                tmem_ld8(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * C::kAccCols + BN + c), r2);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+              }
+              *reinterpret_cast<uint4*>(stage + c) = make_uint4(r[0], r[1], r[2], r[3]);
+              *reinterpret_cast<uint4*>(stage + c + 4) = make_uint4(r[4], r[5], r[6], r[7]);
+            }
+            tc_fence_before();
+            continue;
+          }
+        }
         // scale / shift / residual / activation / gate, then fp32 and / or planes (primary cell, nearest-2x footprint, halo)
         auto finish = [&](float (&v)[8], int n) {
           if (g.scale) {
@@ -488,6 +568,43 @@ conv3x3_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         TMA_STAMP(10, warp == 2 && lane == 0 && it == 0);
         if (lane == 0) mbar_arrive(&t_empty[as]);
       }
+    }
+  }
+  if constexpr (SK) {
+    if (g.cluster_ks > 0) {
+      // every thread of every CTA of the cluster: the staged tiles are complete and visible cluster-wide
+      cluster_sync_all();
+      if (warp >= 2) {
+        const int cks = g.cluster_ks;
+        const uint32_t rank = cluster_ctarank();
+        const int tq = (int)blockIdx.x / cks;
+        const int mt = g.div_nb.quot(tq), nb = tq - mt * g.n_blocks;
+        const int img0 = g.div_tpi.quot(mt), rem = mt - img0 * tiles_per_img;
+        const int ty = g.div_tx.quot(rem);
+        const int rows = kTcBM / cks;                        // accumulator rows (= output pixels) this CTA finishes
+        constexpr int kGroups = BN / 8;
+        const uint32_t stage0 = smem_u32(a_tiles);
+        for (int u = (int)threadIdx.x - 64; u < rows * kGroups; u += 32 * kTmaEpiWarps) {
+          const int px = (int)rank * rows + u / kGroups, c = (u % kGroups) * 8;
+          const int oh0 = ty * kTmaTH + (px >> 3), ow = (rem - ty * g.tiles_x) * kTmaTW + (px & 7);
+          const int img = TALL ? g.div_hp.quot(oh0) : img0;
+          const int oh = TALL ? oh0 - img * g.tall_hp : oh0;
+          const int n = nb * BN + c;
+          if (!(oh < g.ho && ow < g.wo && (!TALL || img < g.tall_n)) || n >= g.cout) continue;
+          const uint32_t addr = stage0 + (uint32_t)((px * (BN + 4) + c) * 4);
+          float v[8];
+          {
+            const float4 a = ld_dsmem4(addr, 0), b = ld_dsmem4(addr + 16, 0);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+          }
+          for (int z = 1; z < cks; ++z) {                    // fixed rank order: the sum does not depend on timing
+            const float4 a = ld_dsmem4(addr, (uint32_t)z), b = ld_dsmem4(addr + 16, (uint32_t)z);
+            v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+          }
+          tma_epilogue_store(g, img, oh, ow, n, v);
+        }
+      }
+      cluster_sync_all();          // nobody leaves while a peer may still read its shared memory
     }
   }
   TMA_STAMP(11, threadIdx.x == 0);
@@ -802,6 +919,17 @@ static int tma_num_sms() {
   return g_tma_sms;
 }
 
+template <class... KArgs, class... Args>
+static void launch_k_cluster(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // errors surface through finish_launch
+}
+
 template <int KC, int BN, int T, bool SK = false, bool TALL = false>
 static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConvArgs g, cudaStream_t st) {
   using C = TmaConvCfg<KC, BN, T>;
@@ -827,6 +955,15 @@ static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConv
   const int smem = (int)(g.na * C::kAStage + b_bytes + 1024 + kTmaBarBytes);
   const long long total = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks * (SK ? g.ksplit : 1);
   const int grid = (int)(total < tma_num_sms() ? total : tma_num_sms());
+  if constexpr (SK) {
+    if (g.cluster_ks > 0) {          // one work item per CTA, the ksplit slices of a tile = one cluster
+      if (total > tma_num_sms() || g.cluster_ks != g.ksplit || g.na * C::kAStage < kTcBM * (BN + 4) * 4) {
+        set_error("conv3x3_tma: cluster split-K plan does not fit (%lld items, ksplit %d)", total, g.ksplit); return -3;
+      }
+      launch_k_cluster(kern, (int)total, kTmaThreads, smem, st, g.cluster_ks, ma, mb, g);
+      return finish_launch("conv3x3_tma (cluster split-K)");
+    }
+  }
   launch_k(kern, dim3(grid), dim3(kTmaThreads), smem, st, ma, mb, g);
   return finish_launch(SK ? "conv3x3_tma (split-K)" : "conv3x3_tma");
 }
@@ -1031,6 +1168,27 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
       const long long slice = (long long)in.n * ho * wo * cout;
       if (workspace_bytes < sp.ksplit * slice * 4) {
         set_error("conv3x3_tma: workspace too small (%lld < %lld)", workspace_bytes, sp.ksplit * slice * 4); return -2;
+      }
+      // cluster form (CLSLAM_TMA_SPLITK_CLUSTER flag): at most 8 slices (portable cluster size), one CTA per work item
+      int cks = 0;
+      if (p->flags & CLSLAM_TMA_SPLITK_CLUSTER) {
+        const int n_cs = g.chunks * taps;
+        for (int c = 8; c >= 2; c >>= 1) {
+          const int per = (n_cs + c - 1) / c;
+          if (c <= sp.ksplit && items * c <= tma_num_sms() && (long long)(c - 1) * per < n_cs) { cks = c; break; }
+        }
+      }
+      if (cks > 0) {
+        TmaConvArgs k = g;                    // full epilogue arguments: the cluster finishes the tile itself
+        k.cluster_ks = cks; k.ksplit = cks; k.cs_per = (g.chunks * taps + cks - 1) / cks; k.div_ks = make_fastdiv(cks);
+        k.part = nullptr; k.part_stride = 0; k.counters = nullptr;
+        int rc;
+        if (taps == 2 && tall) rc = launch_tma_conv<64, 128, 2, true, true>(ma, mb, k, st);
+        else if (taps == 2) rc = launch_tma_conv<64, 128, 2, true>(ma, mb, k, st);
+        else if (tall) rc = launch_tma_conv<64, 128, 3, true, true>(ma, mb, k, st);
+        else if (bn == 128) rc = launch_tma_conv<64, 128, 3, true>(ma, mb, k, st);
+        else rc = launch_tma_conv<64, 64, 3, true>(ma, mb, k, st);
+        return rc;          // (a dgrad caller then runs the plain fold on p->y: `folded` stays false)
       }
       // fused reduction: the CTA holding the last slice of a tile reduces and runs the epilogue (needs the caller's counters;
       // the dgrad fold keeps its own reduction, and more tiles than counters fall back to the epilogue kernel)

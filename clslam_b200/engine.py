@@ -53,6 +53,9 @@ TMA_SPLITK = _flag('CLSLAM_TMA_SPLITK')
 # (batch 1: 1.06 -> 1.67 ms / step, profiles/r02_splitk_fused.md): one CTA walks ksplit x 64 KB of partial sums through L2
 # latency that the separate epilogue kernel spreads over the whole GPU.  Off by default.
 TMA_SPLITK_FUSED = _flag('CLSLAM_TMA_SPLITK_FUSED', '0')
+# with TMA_SPLITK: the K slices of a tile run as one thread-block cluster and are reduced over distributed shared memory (no
+# workspace round trip, no second launch): clslam_conv_tma.flags CLSLAM_TMA_SPLITK_CLUSTER
+TMA_SPLITK_CLUSTER = _flag('CLSLAM_TMA_SPLITK_CLUSTER')
 # the 1x1 / stride-2 down-sampling convolution of a BasicBlock runs on a side lane next to the block's conv1 (both only need
 # the block input); conv2 joins them
 DS_SIDE_LANE = _flag('CLSLAM_DS_SIDE_LANE')
@@ -295,6 +298,8 @@ class Plan:
             a.flags = L.TMA_IN_HALO_VALID
         self.keep.append(a)
         if TMA_SPLITK:      # small layers split K over the SMs (workspace: raw partial sums); large ones run the plain kernel
+            if TMA_SPLITK_CLUSTER:
+                a.flags |= L.TMA_SPLITK_CLUSTER
             ws = self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
             self.need_ws(ws)
             if ws > 0 and TMA_SPLITK_FUSED:
@@ -316,6 +321,8 @@ class Plan:
         a.pad_mode, a.cout = L.PAD_FULL, cin_prev
         a.w_hi, a.w_lo = _p(wt_hi), _p(wt_lo)
         a.act, a.y, a.out_up, a.taps = L.ACT_NONE, _p(dxp), 1, 3
+        if TMA_SPLITK and TMA_SPLITK_CLUSTER:
+            a.flags |= L.TMA_SPLITK_CLUSTER
         self.keep.append(a)
         ws = self.lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a)) if TMA_SPLITK else 0
         if ws == 0:          # no K split for this shape: the same two launches as two plan ops (one kernel per op)

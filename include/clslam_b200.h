@@ -159,6 +159,10 @@ typedef struct clslam_conv_tma {
  * out_halo = 0 into a zero-initialised buffer).  The kernel may then walk the n images as ONE stack of n * (h + 2) rows, so
  * that a 16-row tile covers several small images (6 x 20 maps: half the tiles) instead of padding each image to 16 rows. */
 #define CLSLAM_TMA_IN_HALO_VALID 1
+/* flags bit, clslam_conv3x3_tma_ws / clslam_dgrad3x3_tma_ws only: when the launch splits K, run the (at most 8) K slices of a
+ * tile as the CTAs of one thread-block cluster and reduce them over distributed shared memory: no workspace round trip, no
+ * second kernel, the epilogue spread over the cluster.  Deterministic (fixed rank order). */
+#define CLSLAM_TMA_SPLITK_CLUSTER 2
 int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream);
 /* Split-K form for the layers whose output grid is too small to fill the persistent kernel (the <= 24 x 80 maps of
  * ResNet layer2-4, upconv_4_x .. upconv_2_0 and the pose decoder at batch 1): when the layer has fewer (16 x 8 tile,

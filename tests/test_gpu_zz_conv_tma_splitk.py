@@ -404,3 +404,62 @@ def test_tall_form_of_the_stride2_space_to_depth_conv(n, h, w, ci, co, split):
         assert torch.equal(outs[1], outs[0])
     ref = F.relu(F.conv2d(x.float().double(), wt, stride=2, padding=1))
     assert cabi.rel_err(cabi.nchw(outs[1]), ref) < TOL
+
+
+@pytest.mark.parametrize('case', FUSED_CASES + [(2, 6, 20, 256, 256, L.PAD_ZERO, L.ACT_RELU, False, False, 1, 3),
+                                                (1, 12, 40, 256, 512, L.PAD_FULL, L.ACT_NONE, False, False, 1, 3)])
+def test_cluster_splitk_reduces_over_distributed_shared_memory(case):
+    """flags = CLSLAM_TMA_SPLITK_CLUSTER: the K slices of a tile are the CTAs of one thread-block cluster; the accumulators are
+    staged in shared memory and added over DSMEM in fixed rank order.  One launch, deterministic (two runs are bit-identical),
+    same products as the plain kernel (other summation order), correct against fp64."""
+    lib = cabi.lib()
+    n, h, w, ci, co, pad_mode, act, use_scale, use_res, up, taps = case
+    full = pad_mode == L.PAD_FULL
+    x = rnd(n, ci, h, w, seed=1)
+    wt = rnd(co, ci, 3, 3, seed=2, scale=(ci * 9) ** -0.5)
+    scale = (1.0 + 0.2 * rnd(co, seed=3)) if use_scale else None
+    shift = None if full else 0.1 * rnd(co, seed=4)
+    buf = PlaneBuf(n, h, w, ci)
+    buf.set_padded(F.pad(x, (1, 1, 1, 1), mode='reflect' if pad_mode == L.PAD_REFLECT else 'constant'))
+    res_desc = None
+    if use_res:
+        rbuf = PlaneBuf(n, h, w, co)
+        rbuf.set_padded(F.pad(rnd(n, co, h, w, seed=5), (1, 1, 1, 1)))
+        res_desc = rbuf.desc()
+    ho, wo = h + (2 if full else 0), w + (2 if full else 0)
+    outs = []
+    for mode in ('plain', 'cluster', 'cluster'):
+        keep = []
+        y = torch.full((n, ho, wo, co), float('nan'), device='cuda')
+        ob = None if full else PlaneBuf(n, h * up, w * up, co, fill=3.0)
+        od = ob.desc() if ob else None
+        a = _args(buf.desc(), pad_mode, cabi.krsc(wt), scale, shift, act, res_desc, y, od, up, 0 if full else 1, None, L.ACT_NONE, taps, keep)
+        n0 = lib.clslam_launch_count()
+        if mode == 'plain':
+            L.check(lib.clslam_conv3x3_tma(ctypes.byref(a), cabi.stream()), 'conv3x3_tma')
+        else:
+            a.flags = L.TMA_SPLITK_CLUSTER
+            nbytes = lib.clslam_conv3x3_tma_workspace_bytes(ctypes.byref(a))
+            assert nbytes > 0
+            ws = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device='cuda')
+            L.check(lib.clslam_conv3x3_tma_ws(ctypes.byref(a), ws.data_ptr(), nbytes, cabi.stream()), 'conv3x3_tma_ws')
+            assert lib.clslam_launch_count() - n0 == 1
+        torch.cuda.synchronize()
+        outs.append((y, ob))
+    (y0, o0), (y1, o1), (y2, o2) = outs
+    assert not torch.isnan(y1).any()
+    assert torch.equal(y1, y2) and (o1 is None or torch.equal(o1.t, o2.t))          # deterministic
+    assert cabi.rel_err(y1, y0) < SAME_PRODUCTS
+    if o1 is not None:
+        assert cabi.rel_err(o1.value(), o0.value()) < SAME_PRODUCTS
+    xq = buf.value()
+    ref = F.conv2d(xq, wt, padding=2) if full else F.conv2d(xq, wt)
+    if full:
+        ref = F.conv2d(xq[:, :, 1:-1, 1:-1], wt, padding=2)
+    if scale is not None:
+        ref = ref * scale.view(1, -1, 1, 1)
+    if shift is not None:
+        ref = ref + shift.view(1, -1, 1, 1)
+    if use_res:
+        ref = ref + rbuf.value()[:, :, 1:-1, 1:-1]
+    assert cabi.rel_err(cabi.nchw(y1), cabi.act_ref(ref, act)) < TOL
