@@ -241,32 +241,25 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
   const int r = tap / 3, s = tap - r * 3;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int o = to * 32 + tx;
-  // the four rows (c = ty, ty + 8, ..) of a thread are summed side by side, two chains each: eight loads in flight (with 148
-  // splits of a thin layer a single chain is 148 dependent L2 round trips); fixed order per output (deterministic)
-  const float* pj[4];
-  bool okj[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const int c = tc * 32 + ty + 8 * j;
-    okj[j] = o < co && c < ci;
-    const int cs = okj[j] ? c : 0, os = okj[j] ? o : 0;
-    const int pair = (os / cob) * ci_chunks + cs / cc;
-    pj[j] = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + cs % cc) * cols + s * cob + os % cob;
-  }
-  float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
-  int k = 0;
-  for (; k + 2 <= splits; k += 2) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (okj[j]) { a0[j] += pj[j][(size_t)k * cta_stride]; a1[j] += pj[j][(size_t)(k + 1) * cta_stride]; }
+    const int cl = ty + 8 * j, c = tc * 32 + cl;
+    float v = 0.f;
+    if (o < co && c < ci) {
+      const int pair = (o / cob) * ci_chunks + c / cc;
+      const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
+      // fixed summation order (deterministic), four independent chains so the loads overlap
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      int k = 0;
+      for (; k + 4 <= splits; k += 4) {
+        a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride];
+        a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
+      }
+      for (; k < splits; ++k) a0 += p[(size_t)k * cta_stride];
+      v = (a0 + a1) + (a2 + a3);
     }
+    tile[cl][tx] = v;
   }
-  if (k < splits) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) if (okj[j]) a0[j] += pj[j][(size_t)k * cta_stride];
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j) tile[ty + 8 * j][tx] = a0[j] + a1[j];
   __syncthreads();
   const int c = tc * 32 + tx;
 #pragma unroll
