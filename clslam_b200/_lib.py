@@ -134,6 +134,16 @@ SIGNATURES = {
     'clslam_color_jitter_op': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double, c_void_p, c_longlong, c_void_p]),
     'clslam_dispconv_dgrad_act_emit': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, POINTER(Planes), c_int, c_int, c_int,
                                                c_int, c_void_p]),
+    'clslam_conv_dgrad_ex_workspace_bytes': (c_longlong, [POINTER(ConvDesc), c_int]),
+    'clslam_conv_dgrad_ex': (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                     c_longlong, c_void_p]),
+    'clslam_bn_workspace_bytes': (c_longlong, [c_int, c_int]),
+    'clslam_bn_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_int, c_int, c_int,
+                              c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    'clslam_bn_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
+    'clslam_maxpool3x3s2_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'clslam_add3': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     'clslam_adam_tick': (c_int, [c_void_p, c_void_p]),
     'clslam_adam_step': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double,
                                  c_double, c_int, c_void_p, c_void_p]),

@@ -708,6 +708,7 @@ static void dgrad_dims(const clslam_conv_desc* d, int& M, int& N, int& K, DgradI
   g.dz = dz; g.n = d->n; g.h = d->ho; g.w = d->wo; g.co = d->co;
   g.kh = d->kh; g.kw = d->kw; g.pad = d->pad; g.pad_mode = d->pad_mode;
   g.up = d->in_mode == CLSLAM_IN_UPCAT;
+  g.stride = d->stride;
   g.hl = g.up ? d->h1 : d->hi; g.wl = g.up ? d->w1 : d->wi;
   M = d->n * g.hl * g.wl;
   N = g.up ? d->c1 : d->ci;
@@ -731,6 +732,28 @@ int clslam_conv_dgrad(const clslam_conv_desc* d, const float* dz, const float* w
   BWeightDgradOp b{{w, N, d->ci, d->co, d->kh * d->kw}};
   EpiDgrad e{dz_prev, y_prev, act_prev, disp_dz, disp_w, N, g.hl, g.wl};
   return run_gemm(a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_dgrad");
+}
+
+int clslam_conv_dgrad_ex(const clslam_conv_desc* d, const float* dz, const float* w, int ci_off, int ci_n, const float* y_prev,
+                         int act_prev, float* dx, void* workspace, long long workspace_bytes, void* stream) {
+  if (int rc = check_desc(d, "conv_dgrad_ex")) return rc;
+  if (d->in_mode != CLSLAM_IN_PLAIN && ci_off < d->c1) { set_error("conv_dgrad_ex: an UPCAT layer's up-sampled part goes through conv_dgrad"); return -1; }
+  if (d->stride != 1 && d->pad_mode != CLSLAM_PAD_ZERO) { set_error("conv_dgrad_ex: strided layers are zero padded"); return -1; }
+  if (ci_off < 0 || ci_n < 4 || ci_off % 4 || ci_n % 4 || ci_off + ci_n > d->ci) { set_error("conv_dgrad_ex: bad channel slice"); return -1; }
+  DgradIn g;
+  g.dz = dz; g.n = d->n; g.h = d->ho; g.w = d->wo; g.co = d->co;
+  g.kh = d->kh; g.kw = d->kw; g.pad = d->pad; g.pad_mode = d->pad_mode;
+  g.up = 0; g.stride = d->stride; g.hl = d->hi; g.wl = d->wi;          // the slice lives at the layer's input resolution
+  const int M = d->n * d->hi * d->wi, N = ci_n, K = d->kh * d->kw * d->co;
+  ADgrad a{g, M, K};
+  BWeightDgradOp b{{w + ci_off, N, d->ci, d->co, d->kh * d->kw}};
+  EpiDgrad e{dx, y_prev, act_prev, nullptr, nullptr, N, g.hl, g.wl};
+  return run_gemm(a, b, e, M, N, K, (float*)workspace, workspace_bytes, as_stream(stream), "conv_dgrad_ex");
+}
+
+long long clslam_conv_dgrad_ex_workspace_bytes(const clslam_conv_desc* d, int ci_n) {
+  if (check_desc(d, "conv_dgrad_ex_ws")) return -1;
+  return ws_need(d->n * d->hi * d->wi, ci_n, d->kh * d->kw * d->co, false);
 }
 
 long long clslam_conv_wgrad_workspace_bytes(const clslam_conv_desc* d) {

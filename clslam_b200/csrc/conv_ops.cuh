@@ -97,14 +97,19 @@ struct DgradIn {
   int n, h, w, co;
   int kh, kw, pad, pad_mode;
   int up;            // 1: dX is produced at (hl, wl) = footprint-summed
-  int hl, wl;        // dX spatial dims (== h, w when !up)
+  int hl, wl;        // dX spatial dims (== h, w when !up and stride == 1)
+  int stride;        // convolution stride (zero padding only when > 1): dZ is (h, w), dX is (hl, wl) ~ stride * (h, w)
 };
 
 // calls fn(src) for every dZ coordinate (1-D) that contributes through tap `r` to input
 // coordinate `hh` (input and output have the same size: stride 1, pad = (k-1)/2)
 template <class Fn>
-CLSLAM_HD void dgrad_sources_1d(int hh, int r, int pad, int size, int reflect, Fn&& fn) {
+CLSLAM_HD void dgrad_sources_1d(int hh, int r, int pad, int size, int reflect, Fn&& fn, int stride = 1) {
   const int base = hh + pad - r;
+  if (stride > 1) {                    // output o reads input o * stride + r - pad: o = base / stride when divisible
+    if (base >= 0 && base % stride == 0 && base / stride < size) fn(base / stride);
+    return;
+  }
   if (base >= 0 && base < size) fn(base);
   if (reflect) {                       // 3x3, pad 1 only
     if (hh == 1 && r == 0) fn(0);                    // padded row -1 mirrors row 1
@@ -137,9 +142,9 @@ CLSLAM_HD float4 dgrad_in_load(const DgradIn& g, int n, int oh, int ow, int k) {
       for (int ww = w_lo; ww < w_hi; ++ww) {
         dgrad_sources_1d(ww, s, g.pad, g.w, refl, [&](int sc) {
           f4add(acc, ld4(g.dz + (((size_t)n * g.h + sr) * g.w + sc) * g.co + ch));
-        });
+        }, g.stride);
       }
-    });
+    }, g.stride);
   }
   return acc;
 }
@@ -162,9 +167,9 @@ CLSLAM_HD float4 dgrad_in_gather(const DgradIn& g, const DgradRow& row, const KT
       for (int ww = row.w_lo; ww < row.w_hi; ++ww) {
         dgrad_sources_1d(ww, t.s, g.pad, g.w, refl, [&](int sc) {
           f4add(acc, ld4(g.dz + (((size_t)row.n * g.h + sr) * g.w + sc) * g.co + t.ch));
-        });
+        }, g.stride);
       }
-    });
+    }, g.stride);
   }
   return acc;
 }

@@ -249,6 +249,14 @@ long long clslam_conv_dgrad_workspace_bytes(const clslam_conv_desc* d);
 int clslam_conv_dgrad(const clslam_conv_desc* d, const float* dz, const float* w, const float* y_prev,
                       int act_prev, const float* disp_dz, const float* disp_w, float* dz_prev,
                       void* workspace, long long workspace_bytes, void* stream);
+/* Input gradient of ANY convolution of the path for a slice [ci_off, ci_off + ci_n) of its input channels, at the layer's
+ * input resolution: strided layers (the encoders' 3x3 / stride-2, 1x1 / stride-2 convolutions; zero padding), and the skip
+ * part of an UPCAT layer (ci_off >= c1: the gradient that flows into the ENCODER feature, which the adaptation step -- frozen
+ * encoders -- never needs).  dx (n, hi, wi, ci_n) = sum_taps W^T dz, times act'(y_prev) when y_prev is given.  Used by the
+ * full training path (depth_pose_prediction.py:219-289, :797-800). */
+long long clslam_conv_dgrad_ex_workspace_bytes(const clslam_conv_desc* d, int ci_n);
+int clslam_conv_dgrad_ex(const clslam_conv_desc* d, const float* dz, const float* w, int ci_off, int ci_n, const float* y_prev,
+                         int act_prev, float* dx, void* workspace, long long workspace_bytes, void* stream);
 long long clslam_conv_wgrad_workspace_bytes(const clslam_conv_desc* d);
 int clslam_conv_wgrad(const clslam_conv_desc* d, const float* x, const float* x2, const float* dz,
                       float* dw, float* db, void* workspace, long long workspace_bytes, void* stream);
@@ -369,6 +377,26 @@ int clslam_u8_to_f32_chw(const void* hwc, float* chw, int n, int h, int w, void*
 long long clslam_color_jitter_workspace_bytes(int n);
 int clslam_color_jitter_op(const float* src, float* dst, int n, int h, int w, int op, double factor, void* workspace,
                            long long workspace_bytes, void* stream);
+
+/* ---- full training path: BatchNorm with batch statistics, max-pool backward, accumulation ---------
+ * nn.BatchNorm2d (eps 1e-5, momentum 0.1) over fp32 NHWC (n, hw, c).  `groups` > 1: the n images are that many consecutive
+ * module calls of n / groups images each (the pose encoder's two passes), each with its own batch statistics; the running
+ * statistics are updated once per group, in order.  training = 0: running statistics (eval mode), nothing is updated.
+ * y = act((x - mean) * invstd * gamma + beta (+ residual)); save_mean / save_invstd: (groups, c), kept for the backward. */
+long long clslam_bn_workspace_bytes(int groups, int c);
+int clslam_bn_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var, int training,
+                  float momentum, float eps, const float* residual, int relu, int n, int hw, int c, int groups, float* y,
+                  float* save_mean, float* save_invstd, void* workspace, long long workspace_bytes, void* stream);
+/* backward: g = dy * relu'(y) (relu != 0), dgamma = sum g * xhat, dbeta = sum g, dx = gamma * invstd * (g - mean(g) -
+ * xhat * mean(g * xhat)) with batch statistics, gamma * invstd * g in eval mode.  g_out (optional) receives g: the gradient of
+ * the identity branch of a BasicBlock. */
+int clslam_bn_bwd(const float* x, const float* dy, const float* y, int relu, const float* gamma, const float* save_mean,
+                  const float* save_invstd, int training, int n, int hw, int c, int groups, float* dx, float* dgamma,
+                  float* dbeta, float* g_out, void* workspace, long long workspace_bytes, void* stream);
+/* backward of MaxPool2d(3, 2, 1) (resnet_encoder.py:121), NHWC; ties go to the first maximum like ATen */
+int clslam_maxpool3x3s2_bwd(const float* x, const float* dy, float* dx, int n, int hi, int wi, int c, void* stream);
+/* out = a + b + c (b, c optional), n floats: gradient accumulation where branches of the graph join */
+int clslam_add3(const float* a, const float* b, const float* c, float* out, long long n, void* stream);
 
 /* ---- optimiser ----------------------------------------------------------------------------
  * torch.optim.Adam (lr, betas, eps; no weight decay / amsgrad) as built at
