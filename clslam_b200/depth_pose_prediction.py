@@ -22,7 +22,8 @@ from torch import Tensor, nn, optim
 
 from . import _lib as L
 from .engine import H2D_OVERLAP, AdaptEngine, DepthRunner, EncoderRunner, Plan, PreparedEncoder, _p
-from .networks import DepthDecoder, FlatParams, PoseDecoder, ResnetEncoder
+from .networks import DepthDecoder, EncoderFlat, FlatParams, PoseDecoder, ResnetEncoder
+from .train_engine import TrainEngine
 from .sharding import global_sample_weights, shard_range
 
 # data-parallel: all-reduce the gradients in buckets inside the step graph, overlapped with the backward pass (default);
@@ -38,10 +39,13 @@ class FlatAdam:
     the fused flat-buffer Adam kernel.  The wrapped torch optimiser is never stepped; it only
     carries hyper-parameters and the (de)serialisation format of depth_pose_prediction.py:691-697."""
 
-    def __init__(self, all_params: List[nn.Parameter], lr: float, flat: FlatParams, trainable: List[nn.Parameter]):
+    def __init__(self, all_params: List[nn.Parameter], lr: float, flat: FlatParams, trainable: List[nn.Parameter],
+                 encoder_flats: Optional[List[EncoderFlat]] = None):
         self.torch_optimizer = optim.Adam(all_params, lr)
         self.flat = flat
         self.trainable = trainable      # the 36 decoder tensors, in flat-buffer order (weight, bias, ...)
+        self.encoder_flats = encoder_flats or []          # trained by train() / _set_adapt(freeze_encoder=False) only
+        self.step_fn: Optional[Callable[[], None]] = None
         self._spans = []                # (param, offset, numel, is_weight, info)
         for (net, path), info in flat.index.items():
             self._spans.append((info, True))
@@ -60,11 +64,17 @@ class FlatAdam:
                 out.append(buf[info['b_off']:info['b_off'] + info['co']])
         return out
 
+    def _triples(self):
+        out = list(zip(self.trainable, self._state_views(self.flat.exp_avg), self._state_views(self.flat.exp_avg_sq)))
+        for ef in self.encoder_flats:          # only once the encoders have been trained (their moment buffers exist)
+            out += [(p, m, v) for p, m, v in ef.state_triples() if p.requires_grad]
+        return out
+
     def state_dict(self):
         steps = int(self.flat.step_dev.item())
         st = self.torch_optimizer.state
         if steps > 0:
-            for p, m, v in zip(self.trainable, self._state_views(self.flat.exp_avg), self._state_views(self.flat.exp_avg_sq)):
+            for p, m, v in self._triples():
                 st[p] = {'step': torch.tensor(float(steps)), 'exp_avg': m.detach().clone().contiguous(),
                          'exp_avg_sq': v.detach().clone().contiguous()}
         return self.torch_optimizer.state_dict()
@@ -72,16 +82,28 @@ class FlatAdam:
     def load_state_dict(self, sd) -> None:
         self.torch_optimizer.load_state_dict(sd)
         st = self.torch_optimizer.state
+        if any(p in st for ef in self.encoder_flats for p in ef.enc.parameters()):
+            for ef in self.encoder_flats:      # a checkpoint of a trained encoder: its moments need somewhere to live
+                ef.ensure_training_buffers()
         steps = 0
         with torch.no_grad():
-            for p, m, v in zip(self.trainable, self._state_views(self.flat.exp_avg), self._state_views(self.flat.exp_avg_sq)):
+            for p, m, v in self._triples():
                 if p in st and 'exp_avg' in st[p]:
                     m.copy_(st[p]['exp_avg']); v.copy_(st[p]['exp_avg_sq'])
                     steps = max(steps, int(float(st[p]['step'])))
             self.flat.step_dev.fill_(steps)
 
+    def step(self) -> None:
+        """``optimizer.step()`` of the reference's training loop (:256): Adam on the gradients of the last ``backward()``"""
+        if self.step_fn is None:
+            raise RuntimeError('FlatAdam.step(): no backward pass has been run')
+        self.step_fn()
+
     def zero_grad(self, set_to_none: bool = False) -> None:
         self.flat.grads.zero_()
+        for ef in self.encoder_flats:
+            if ef.grads is not None:
+                ef.grads.zero_()
 
 
 # inputs that only the photometric chain / the losses read (H2D_OVERLAP: they travel on the copy stream while the networks run)
@@ -103,13 +125,16 @@ class _NetSet:
         self.models['pose_encoder'] = ResnetEncoder(owner.resnet_pose, owner.resnet_pretrained, owner.num_pose_frames, device=dev)
         self.models['pose_decoder'] = PoseDecoder()
         self.flat = FlatParams(self.models['depth_decoder'], self.models['pose_decoder'], dev)
+        # encoder weights / BatchNorm affine parameters as views of flat buffers too (the full training path updates them in place)
+        self.enc_flat = {n: EncoderFlat(self.models[n], dev) for n in ('depth_encoder', 'pose_encoder')}
         self.models['depth_encoder'].bind(lambda x: owner._run_encoder(self, 'depth_encoder', x))
         self.models['pose_encoder'].bind(lambda x: owner._run_encoder(self, 'pose_encoder', x))
         self.parameters: List[nn.Parameter] = []
         for m in self.models.values():
             self.parameters += list(m.parameters())
         trainable = list(self.models['depth_decoder'].parameters()) + list(self.models['pose_decoder'].parameters())
-        self.optimizer = FlatAdam(self.parameters, owner.learning_rate, self.flat, trainable)
+        self.optimizer = FlatAdam(self.parameters, owner.learning_rate, self.flat, trainable, list(self.enc_flat.values()))
+        self.train_engines: Dict[Tuple[int, bool], TrainEngine] = {}
         self.prep: Dict[str, PreparedEncoder] = {}
         self.engines: Dict[int, AdaptEngine] = {}
         self.enc_runners: Dict[Tuple[str, int, int, int], EncoderRunner] = {}
@@ -118,11 +143,14 @@ class _NetSet:
         self.graphs: Dict[Tuple, Any] = {}
         self.steps_run: Dict[int, int] = {}
         self.weights_key: Dict[int, Any] = {}
-        self.adapt_flags_set = False
+        self.adapt_flags_set = False          # False | "bn_only" | "frozen" (requires_grad is only ever switched off)
+        self.enc_trainable = True
 
     def drop_plans(self) -> None:
         """plans hold raw pointers into the prepared encoder tensors: forget them (and everything captured from them)"""
         self.engines.clear(); self.enc_runners.clear(); self.graphs.clear(); self.depth_runners.clear()
+        # (the training engines read the encoders' flat buffers and the modules' running statistics, whose addresses never
+        # change: they survive; their graphs went with self.graphs)
         self.pose_runner = None
         self.weights_key.clear()
         self.steps_run.clear()          # a fresh engine runs its first step eagerly again (loads kernels, builds tensor maps)
@@ -304,8 +332,11 @@ class DepthPosePrediction:
     # ------------------------------------------------------------------------------------------
     # modes (:797-827)
     def _set_train(self) -> None:
-        raise NotImplementedError('training-mode BatchNorm / encoder backward is SURVEY.md 8(f) row 3; '
-                                  'use adapt() (encoders frozen)')
+        """:797-800: every network in training mode -- BatchNorm uses batch statistics and updates its running statistics;
+        whatever has requires_grad is trained (the full training plan, clslam_b200/train_engine.py)"""
+        for m in self.models.values():
+            m.train()
+        self._mode = 'train'
 
     # Both mode switches are called once per frame by Slam.step / adapt (slam/slam.py:143, :291-319).  Walking the four module
     # trees costs 0.4-0.6 ms of host time per call, in front of the step's H2D copies and launches, and is idempotent: the
@@ -321,20 +352,23 @@ class DepthPosePrediction:
         self._mode = 'eval'
 
     def _set_adapt(self, freeze_encoder: bool = True) -> None:
-        if not freeze_encoder:
-            raise NotImplementedError('freeze_encoder=False is SURVEY.md 8(f) row 3')
+        """:807-827.  BatchNorm in evaluation mode; 'bn'-named parameters frozen; with ``freeze_encoder`` every encoder
+        parameter frozen too.  requires_grad is only ever switched OFF (the reference never re-enables it).  With trainable
+        encoder convolutions left (freeze_encoder=False on a fresh object) the step runs on the full training plan."""
         for ns in self._sets():                 # :813-827: both copies
             if any(m.training for m in ns.models.values()):
                 for m in ns.models.values():
                     m.eval()
-            if not ns.adapt_flags_set:
-                # requires_grad=False for BatchNorm and encoder parameters (:813-822); the reference never re-enables them
+            key = 'frozen' if freeze_encoder else 'bn_only'
+            if ns.adapt_flags_set != 'frozen' and ns.adapt_flags_set != key:
                 for model_name, model in ns.models.items():
                     for name, param in model.named_parameters():
-                        if name.find('bn') != -1 or 'encoder' in model_name:
+                        if name.find('bn') != -1 or (freeze_encoder and 'encoder' in model_name):
                             param.requires_grad = False
-                ns.adapt_flags_set = True
-        self._mode = 'adapt'
+                ns.adapt_flags_set = key
+                ns.enc_trainable = any(p.requires_grad for n in ('depth_encoder', 'pose_encoder')
+                                       for p in ns.models[n].resnet.parameters() if p.dim() == 4)
+        self._mode = 'adapt_enc' if self._main.enc_trainable else 'adapt'
 
     # ------------------------------------------------------------------------------------------
     # engines
@@ -374,7 +408,30 @@ class DepthPosePrediction:
                               grad_allreduce=self._allreduce_tensor if (self.world > 1 and GRAD_BUCKETS > 0) else None,
                               grad_buckets=GRAD_BUCKETS, bucket_adam=BUCKET_ADAM)
             eng.net_set = ns
+            eng.kind = 'adapt'
             ns.engines[batch] = eng
+        return eng
+
+    def _train_engine(self, batch: int, bn_training: bool, ns: Optional[_NetSet] = None) -> TrainEngine:
+        """the full training plan (encoders trainable, BatchNorm explicit) for this local batch size"""
+        self._require_cuda()
+        ns = ns or self._main
+        eng = ns.train_engines.get((batch, bn_training))
+        if eng is None:
+            L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
+            for ef in ns.enc_flat.values():
+                ef.ensure_training_buffers()
+            b_global, has0 = (batch * self.world, self.rank == 0) if self.world > 1 else (batch, True)
+            eng = TrainEngine(batch=batch, height=self.height, width=self.width, batch_global=b_global, has_sample0=has0,
+                              depth_enc=ns.models['depth_encoder'], pose_enc=ns.models['pose_encoder'],
+                              depth_flat=ns.enc_flat['depth_encoder'], pose_flat=ns.enc_flat['pose_encoder'], flat=ns.flat,
+                              min_depth=self.min_depth, max_depth=self.max_depth, disparity_smoothness=self.disparity_smoothness,
+                              velocity_loss_scaling=self.velocity_loss_scaling, bn_training=bn_training, device=self.device,
+                              emit_outputs=self.emit_outputs)
+            eng.net_set = ns
+            eng.kind = 'train' if bn_training else 'train_bn_eval'
+            ns.train_engines[(batch, bn_training)] = eng
+        eng.set_frozen_masks()          # requires_grad may have changed since the last call
         return eng
 
     def _run_encoder(self, ns: _NetSet, net: str, x: Tensor) -> List[Tensor]:
@@ -409,7 +466,10 @@ class DepthPosePrediction:
         The values the path reads land in the engine's static input buffers and the dict then holds views of those (in the
         caller's shape): they stay valid until the next call that stages a batch of the same size."""
         batch = inputs[('rgb_aug', 0, 0)].shape[0]
-        eng = self._engine(batch, ns)
+        if self._mode in ('train', 'adapt_enc') and (ns is None or ns is self._main):
+            eng = self._train_engine(batch, self._mode == 'train', ns)
+        else:
+            eng = self._engine(batch, ns)
         smap = self._static_map(eng)
         self._deferred = []
         cuda = self.device.type == 'cuda'
@@ -481,9 +541,10 @@ class DepthPosePrediction:
         # the weights rarely change between calls: upload only when they do (a pageable H2D copy stalls the host)
         key = None if loss_sample_weights is None else tuple(float(v) for v in loss_sample_weights.detach().flatten().tolist())
         wk = eng.net_set.weights_key
-        if wk.get(eng.b, 'unset') == (key, self.batch_size):
+        slot = (eng.b, getattr(eng, 'kind', 'adapt'))          # the adaptation and the training engine have their own buffers
+        if wk.get(slot, 'unset') == (key, self.batch_size):
             return
-        wk[eng.b] = (key, self.batch_size)
+        wk[slot] = (key, self.batch_size)
         if loss_sample_weights is None:
             w = torch.ones(self.batch_size) / self.batch_size          # :1032 (uses config batch_size)
         else:
@@ -569,6 +630,7 @@ class DepthPosePrediction:
         eng = inputs_engine or self._last_engine
         eng.backward()
         self._allreduce_grads(eng)
+        eng.net_set.optimizer.step_fn = lambda e=eng: self._apply_adam(e)          # `optimizer.step()` of the reference's loops
 
     @staticmethod
     def _allreduce_tensor(t: Tensor) -> None:
@@ -580,9 +642,28 @@ class DepthPosePrediction:
         has already issued it, bucket by bucket, overlapped with the remaining weight-gradient kernels."""
         if self.world > 1 and not (eng is not None and eng.grad_sync_in_plan):
             self._allreduce_tensor(self._flat.grads)
+            if eng is not None and getattr(eng, 'kind', 'adapt') != 'adapt':          # full training: the encoders' gradients too
+                for ef in eng.net_set.enc_flat.values():
+                    self._allreduce_tensor(ef.grads)
+
+    def _apply_adam(self, eng) -> None:
+        eng.adam(self._adam_lr())
+        if getattr(eng, 'kind', 'adapt') != 'adapt':
+            self.refresh_encoders()          # the kernel-layout copies of the (now changed) encoders are rebuilt on next use
 
     def gradients(self) -> Dict[Tuple[str, str], Tensor]:
         return self._flat.named_gradients()
+
+    def encoder_gradients(self) -> Dict[Tuple[str, str], Tensor]:
+        """gradients of the encoder tensors after a full-training backward pass: {(net, 'resnet.<torchvision key>'): tensor}"""
+        out = {}
+        for net, ef in self._main.enc_flat.items():
+            if ef.grads is None:
+                continue
+            for key, g in ef.named_gradients().items():
+                key = key.replace('.dsbn.', '.downsample.1.').replace('.ds.', '.downsample.0.')
+                out[(net, 'resnet.' + key)] = g
+        return out
 
     def _adam_lr(self) -> float:
         return float(self.optimizer.param_groups[0]['lr'])
@@ -593,13 +674,42 @@ class DepthPosePrediction:
         eng.adam_hparams(lr)                 # read by the per-bucket Adam launches of a data-parallel plan (baked into its graph)
         ns = eng.net_set
         graphs = ns.graphs
-        n_run = ns.steps_run.get(eng.b, 0)
-        ns.steps_run[eng.b] = n_run + 1
+        kind = getattr(eng, 'kind', 'adapt')
+        n_run = ns.steps_run.get((eng.b, kind), 0)
+        ns.steps_run[(eng.b, kind)] = n_run + 1
         late_event = getattr(self, '_late_event', None)
         if not self.use_cuda_graph or n_run == 0:       # first step eager: loads every kernel before capture
             if late_event is not None:
                 torch.cuda.current_stream(self.device).wait_event(late_event)
             eng.forward_backward(); self._allreduce_grads(eng); eng.adam(lr)
+            if kind != 'adapt':
+                self.refresh_encoders()
+            return
+        if kind != 'adapt':
+            # full training step: one graph on a single GPU; data-parallel: graph(fwd + bwd), all-reduce of the three flat
+            # gradient buffers, graph(Adam)
+            if late_event is not None:
+                torch.cuda.current_stream(self.device).wait_event(late_event)
+            if self.world == 1:
+                key = (eng.b, kind, 'step', lr)
+                if key not in graphs:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        eng.forward_backward(); eng.adam(lr)
+                    graphs[key] = g
+                graphs[key].replay()
+            else:
+                k1, k2 = (eng.b, kind, 'fwdbwd'), (eng.b, kind, 'adam', lr)
+                if k1 not in graphs:
+                    g1 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g1):
+                        eng.forward_backward()
+                    g2 = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g2):
+                        eng.adam(lr)
+                    graphs[k1], graphs[k2] = g1, g2
+                graphs[k1].replay(); self._allreduce_grads(eng); graphs[k2].replay()
+            self.refresh_encoders()
             return
         if self.world == 1 and H2D_OVERLAP and late_event is not None:
             # two graphs: the networks (need rgb_aug / intrinsics only) run while the photometric inputs are still in flight
@@ -668,9 +778,43 @@ class DepthPosePrediction:
         with torch.no_grad():
             return self._process_batch(online_data, loss_weights)
 
-    def train(self, *args, **kwargs) -> None:
-        raise NotImplementedError('offline pre-training (train(), :219-289) needs encoder backward + training-mode '
-                                  'BatchNorm: SURVEY.md 8(f) row 3.  Use adapt().')
+    def train(self, validate: bool = False, depth_error: bool = False, pose_error: bool = False, dataloader=None,
+              verbose: bool = True, use_wandb: Optional[bool] = False) -> None:
+        """:219-289.  The training loop over ``dataloader`` (batches in the dataset schema of SURVEY App. C.1): per batch
+        zero_grad / _process_batch / backward / optimizer.step -- here one captured step of the full training plan --
+        ``lr_scheduler.step()`` per epoch, checkpoints every ``save_frequency`` epochs.  Building the reference's own KITTI /
+        Cityscapes loaders (``_create_dataloaders``, :829-904), validation, the depth / pose error tables and wandb logging
+        are outside SURVEY.md section 8: pass the loader."""
+        if use_wandb:
+            raise NotImplementedError('wandb logging (:226-229, :1246-1267) is outside SURVEY.md section 8')
+        if validate or depth_error or pose_error:
+            raise NotImplementedError('validate / depth_error / pose_error need the dataset loaders: outside SURVEY.md section 8')
+        if dataloader is None:
+            raise NotImplementedError('train() needs `dataloader`: the reference builds it from its datasets package '
+                                      '(_create_dataloaders, :829-904), which is outside SURVEY.md section 8')
+        self.train_loader = dataloader
+        print(f'Training samples:   {len(self.train_loader):>5}')
+        starting_epoch = self.epoch + 1
+        for self.epoch in range(starting_epoch, self.num_epochs + 1):
+            self._set_train()
+            loss = []
+            for sample_i in self.train_loader:
+                eng = self._stage_inputs(sample_i)
+                self._set_weights(eng, None)
+                self._draw_noise(eng)
+                self._step(eng)                              # zero_grad, forward, backward, optimizer.step (:251-256)
+                self._last_engine = eng
+                _, losses = self._collect(eng)
+                loss.append(float(losses['loss']))
+            if verbose and loss:
+                print(f'Training epoch {self.epoch}/{self.num_epochs}: loss={sum(loss) / len(loss):.6f}')
+            self.optimizer.torch_optimizer._opt_called = True          # the fused Adam has stepped (silences StepLR's order check)
+            self.lr_scheduler.step()
+            self.is_trained = True
+            if self.save_frequency > 0 and self.epoch % self.save_frequency == 0:
+                self.save_model()
+        if self.save_frequency > -1:
+            self.save_model()
 
     # ------------------------------------------------------------------------------------------
     # inference entry points of the reference that Slam does not call (:530-626)

@@ -279,3 +279,148 @@ class FlatParams:
             out[(net, path + '.weight')] = self.view_weight(self.grads, info)
             out[(net, path + '.bias')] = self.grads[info['b_off']:info['b_off'] + info['co']]
         return out
+
+
+class EncoderFlat:
+    """The trainable tensors of one ResNet-18 encoder in flat fp32 buffers (full training path):
+    convolution weights stored [Cout][kh][kw][Cin] (the kernels' layout; conv1's input channels zero-padded to 4 / 8 like the
+    staged images), BatchNorm weight / bias, plus gradient and Adam-moment buffers of the same layout.  The module's
+    nn.Parameters are re-bound to *views* with the reference's logical shapes, so ``state_dict()`` / ``load_state_dict()`` /
+    the optimiser's parameter list keep speaking the reference's format (resnet_encoder.py:79-113, torchvision key names) while
+    the wgrad kernels, Adam and the all-reduce work on the flat buffers in place.  ``resnet.fc`` (never used, never trained)
+    and the BatchNorm running statistics stay ordinary module tensors."""
+
+    def __init__(self, enc: ResnetEncoder, device):
+        self.enc = enc
+        r = enc.resnet
+        cin_pad = 4 if enc.num_input_images == 1 else 8
+        self.cin_pad = cin_pad
+        items = []          # (name, module, kind, shape info)
+        items.append(('conv1', r.conv1, 'conv', (64, 3 * enc.num_input_images, 7, cin_pad)))
+        items.append(('bn1', r.bn1, 'bn', 64))
+        for li in range(1, 5):
+            for bi, blk in enumerate(getattr(r, f'layer{li}')):
+                p = f'layer{li}.{bi}'
+                for cname in ('conv1', 'conv2'):
+                    conv = getattr(blk, cname)
+                    co, ci, k, _ = conv.weight.shape
+                    items.append((f'{p}.{cname}', conv, 'conv', (co, ci, k, ci)))
+                    items.append((f'{p}.bn{cname[-1]}', getattr(blk, 'bn' + cname[-1]), 'bn', co))
+                if blk.downsample is not None:
+                    conv = blk.downsample[0]
+                    co, ci, k, _ = conv.weight.shape
+                    items.append((f'{p}.ds', conv, 'conv', (co, ci, k, ci)))
+                    items.append((f'{p}.dsbn', blk.downsample[1], 'bn', co))
+
+        def aligned(n):
+            return (n + 63) // 64 * 64
+        total = 0
+        self.index = {}
+        for name, mod, kind, info in items:
+            if kind == 'conv':
+                co, ci, k, cs = info
+                self.index[name] = dict(kind='conv', off=total, co=co, ci=ci, k=k, cs=cs, numel=co * k * k * cs)
+                total += aligned(co * k * k * cs)
+            else:
+                self.index[name] = dict(kind='bn', off=total, c=info, numel=2 * info)
+                total += aligned(2 * info)
+        self.numel = total
+        self.params = torch.zeros(total, device=device)
+        # gradient and Adam-moment buffers (3 x 45 MB per encoder) only exist once the encoder is trained: the per-frame
+        # adaptation path never touches them
+        self.grads: Optional[torch.Tensor] = None
+        self.exp_avg: Optional[torch.Tensor] = None
+        self.exp_avg_sq: Optional[torch.Tensor] = None
+        self.modules = {}
+        with torch.no_grad():
+            for name, mod, kind, info in items:
+                ix = self.index[name]
+                self.modules[name] = mod
+                if kind == 'conv':
+                    old = mod.weight.detach().to(device)
+                    view = self.view_weight(self.params, ix)
+                    view.copy_(old)
+                    mod.weight = nn.Parameter(view)
+                else:
+                    c = ix['c']
+                    wv, bv = self.params[ix['off']:ix['off'] + c], self.params[ix['off'] + c:ix['off'] + 2 * c]
+                    wv.copy_(mod.weight.detach().to(device)); bv.copy_(mod.bias.detach().to(device))
+                    mod.weight = nn.Parameter(wv)
+                    mod.bias = nn.Parameter(bv)
+
+    def ensure_training_buffers(self) -> None:
+        if self.grads is not None:
+            return
+        dev = self.params.device
+        self.grads = torch.zeros(self.numel, device=dev)
+        self.exp_avg = torch.zeros(self.numel, device=dev)
+        self.exp_avg_sq = torch.zeros(self.numel, device=dev)
+        for name, ix in self.index.items():
+            mod = self.modules[name]
+            if ix['kind'] == 'conv':
+                mod.weight.grad = self.view_weight(self.grads, ix)
+            else:
+                c = ix['c']
+                mod.weight.grad = self.grads[ix['off']:ix['off'] + c]
+                mod.bias.grad = self.grads[ix['off'] + c:ix['off'] + 2 * c]
+
+    def state_triples(self):
+        """[(Parameter, exp_avg view, exp_avg_sq view)] in module order, for the optimiser's state dict"""
+        out = []
+        if self.exp_avg is None:
+            return out
+        for name, ix in self.index.items():
+            mod = self.modules[name]
+            if ix['kind'] == 'conv':
+                out.append((mod.weight, self.view_weight(self.exp_avg, ix), self.view_weight(self.exp_avg_sq, ix)))
+            else:
+                c, o = ix['c'], ix['off']
+                out.append((mod.weight, self.exp_avg[o:o + c], self.exp_avg_sq[o:o + c]))
+                out.append((mod.bias, self.exp_avg[o + c:o + 2 * c], self.exp_avg_sq[o + c:o + 2 * c]))
+        return out
+
+    @staticmethod
+    def view_weight(flat: torch.Tensor, ix) -> torch.Tensor:
+        """logical (Cout, Cin, kh, kw) view of the [Cout][kh][kw][Cin_stored] storage"""
+        co, ci, k, cs = ix['co'], ix['ci'], ix['k'], ix['cs']
+        return flat[ix['off']:ix['off'] + ix['numel']].view(co, k, k, cs)[..., :ci].permute(0, 3, 1, 2)
+
+    def w_ptr(self, name: str) -> int:
+        return self.params.data_ptr() + 4 * self.index[name]['off']
+
+    def dw_ptr(self, name: str) -> int:
+        return self.grads.data_ptr() + 4 * self.index[name]['off']
+
+    def bn_ptrs(self, name: str):
+        """(gamma, beta, d gamma, d beta) device addresses"""
+        ix = self.index[name]
+        p, g = self.params.data_ptr() + 4 * ix['off'], self.grads.data_ptr() + 4 * ix['off']
+        return p, p + 4 * ix['c'], g, g + 4 * ix['c']
+
+    def frozen_mask(self) -> torch.Tensor:
+        """1.0 where the element's Parameter has requires_grad, else 0.0 (the reference's optimiser skips parameters without a
+        gradient: _set_adapt(freeze_encoder=False) leaves the 'bn'-named BatchNorm parameters frozen, :813-816)"""
+        m = torch.zeros(self.numel, device=self.params.device)
+        for name, ix in self.index.items():
+            mod = self.modules[name]
+            if ix['kind'] == 'conv':
+                if mod.weight.requires_grad:
+                    m[ix['off']:ix['off'] + ix['numel']] = 1.0
+            else:
+                c = ix['c']
+                if mod.weight.requires_grad:
+                    m[ix['off']:ix['off'] + c] = 1.0
+                if mod.bias.requires_grad:
+                    m[ix['off'] + c:ix['off'] + 2 * c] = 1.0
+        return m
+
+    def named_gradients(self):
+        out = {}
+        for name, ix in self.index.items():
+            if ix['kind'] == 'conv':
+                out[name + '.weight'] = self.view_weight(self.grads, ix)
+            else:
+                c = ix['c']
+                out[name + '.weight'] = self.grads[ix['off']:ix['off'] + c]
+                out[name + '.bias'] = self.grads[ix['off'] + c:ix['off'] + 2 * c]
+        return out

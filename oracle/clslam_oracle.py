@@ -103,32 +103,37 @@ def adapt_loss_weights(batch_size: int, online_loss_weight: Optional[float], onl
 # Networks
 # --------------------------------------------------------------------------------------
 
-def _bn_eval(x: Tensor, sd: StateDict, p: str) -> Tensor:
-    return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'],
-                        sd[p + '.bias'], training=False, momentum=0.1, eps=1e-5)
+def _bn_eval(x: Tensor, sd: StateDict, p: str, training: bool = False) -> Tensor:
+    """nn.BatchNorm2d: running statistics (eval, as in ``adapt``) or batch statistics + in-place running-stat update
+    (``_set_train``, depth_pose_prediction.py:797-800)"""
+    out = F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'], sd[p + '.weight'],
+                       sd[p + '.bias'], training=training, momentum=0.1, eps=1e-5)
+    if training and (p + '.num_batches_tracked') in sd:
+        sd[p + '.num_batches_tracked'] += 1
+    return out
 
 
-def _basic_block(x: Tensor, sd: StateDict, p: str, stride: int) -> Tensor:
+def _basic_block(x: Tensor, sd: StateDict, p: str, stride: int, training: bool = False) -> Tensor:
     """torchvision BasicBlock."""
     y = F.conv2d(x, sd[p + '.conv1.weight'], None, stride, 1)
-    y = F.relu(_bn_eval(y, sd, p + '.bn1'))
+    y = F.relu(_bn_eval(y, sd, p + '.bn1', training))
     y = F.conv2d(y, sd[p + '.conv2.weight'], None, 1, 1)
-    y = _bn_eval(y, sd, p + '.bn2')
+    y = _bn_eval(y, sd, p + '.bn2', training)
     if (p + '.downsample.0.weight') in sd:
         x = _bn_eval(F.conv2d(x, sd[p + '.downsample.0.weight'], None, stride, 0), sd,
-                     p + '.downsample.1')
+                     p + '.downsample.1', training)
     return F.relu(y + x)
 
 
-def encoder_forward(sd: StateDict, image: Tensor) -> List[Tensor]:
-    """networks/resnet_encoder.py:115-125 (BatchNorm in eval mode, as in ``adapt``)."""
+def encoder_forward(sd: StateDict, image: Tensor, training: bool = False) -> List[Tensor]:
+    """networks/resnet_encoder.py:115-125.  ``training``: BatchNorm in training mode (train(), :219-289), else eval (adapt)."""
     x = (image - 0.45) / 0.225
     x = F.conv2d(x, sd['resnet.conv1.weight'], None, 2, 3)
-    feats = [F.relu(_bn_eval(x, sd, 'resnet.bn1'))]
+    feats = [F.relu(_bn_eval(x, sd, 'resnet.bn1', training))]
     x = F.max_pool2d(feats[0], 3, 2, 1)
     for li in range(1, 5):
         for bi in range(2):
-            x = _basic_block(x, sd, f'resnet.layer{li}.{bi}', 2 if (li > 1 and bi == 0) else 1)
+            x = _basic_block(x, sd, f'resnet.layer{li}.{bi}', 2 if (li > 1 and bi == 0) else 1, training)
         feats.append(x)
     return feats
 
@@ -292,13 +297,13 @@ class OracleConfig:
         self.smooth_mode = smooth_mode
 
 
-def predict_poses(params: Dict[str, StateDict], batch: Dict[object, Tensor]) -> Dict[object, Tensor]:
-    """depth_pose_prediction.py:938-974."""
+def predict_poses(params: Dict[str, StateDict], batch: Dict[object, Tensor], training: bool = False) -> Dict[object, Tensor]:
+    """depth_pose_prediction.py:938-974 (two separate pose-net calls: in training mode two BatchNorm updates)."""
     out = {}
     for f in FRAME_IDS[1:]:
         pair = (batch[('rgb_aug', f, 0)], batch[('rgb_aug', 0, 0)]) if f < 0 else \
                (batch[('rgb_aug', 0, 0)], batch[('rgb_aug', f, 0)])
-        f4 = encoder_forward(params['pose_encoder'], torch.cat(pair, 1))[-1]
+        f4 = encoder_forward(params['pose_encoder'], torch.cat(pair, 1), training)[-1]
         aa, t = pose_decoder_forward(params['pose_decoder'], f4)
         aa, t = aa[:, 0], t[:, 0]
         out[('axis_angle', 0, f)] = aa
@@ -309,7 +314,7 @@ def predict_poses(params: Dict[str, StateDict], batch: Dict[object, Tensor]) -> 
 
 def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg: OracleConfig,
                   noise: Sequence[Tensor], sample_weights: Optional[Tensor] = None,
-                  smooth_weights: Optional[Tensor] = None, with_smooth: bool = True,
+                  smooth_weights: Optional[Tensor] = None, with_smooth: bool = True, bn_training: bool = False,
                   ) -> Tuple[Dict[object, Tensor], Dict[str, Tensor]]:
     """depth_pose_prediction.py:906-923 (+ :976-1120).  ``noise[s]`` replaces the
     ``torch.randn`` draw of scale s (unscaled standard normal, (B,2,H,W)).
@@ -319,9 +324,9 @@ def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg
     as ``smooth_weights`` (one quirk term per global sample), the others ``with_smooth=False``."""
     h, w = cfg.height, cfg.width
     outputs: Dict[object, Tensor] = {}
-    feats = encoder_forward(params['depth_encoder'], batch[('rgb_aug', 0, 0)])
+    feats = encoder_forward(params['depth_encoder'], batch[('rgb_aug', 0, 0)], bn_training)
     outputs.update(depth_decoder_forward(params['depth_decoder'], feats, cfg.scales))
-    outputs.update(predict_poses(params, batch))
+    outputs.update(predict_poses(params, batch, bn_training))
 
     bsz = outputs[('disp', cfg.scales[0])].shape[0]
     target = batch[('rgb', 0, 0)]
@@ -394,11 +399,28 @@ class OracleAdapter:
     """``adapt(training_data, steps)`` of depth_pose_prediction.py:291-319 with the encoders
     frozen (:807-827) and torch.optim.Adam over the 36 decoder tensors (:203, :311-313)."""
 
-    def __init__(self, params: Dict[str, StateDict], cfg: OracleConfig) -> None:
+    def __init__(self, params: Dict[str, StateDict], cfg: OracleConfig, mode: str = 'adapt') -> None:
+        """mode 'adapt': encoders frozen, BatchNorm eval (:807-827, freeze_encoder=True).  'train': everything trainable,
+        BatchNorm in training mode (_set_train on a fresh object, :797-800).  'adapt_enc': _set_adapt(freeze_encoder=False) on a
+        fresh object -- BatchNorm eval, every parameter whose name contains 'bn' frozen, the rest (encoder convolutions and,
+        by the reference's substring test, the downsample.1 BatchNorms) trainable."""
         self.cfg = cfg
+        self.mode = mode
         self.params = {n: {k: v.clone() for k, v in sd.items()} for n, sd in params.items()}
         self.trainable = []
-        for net, key in trainable_keys():
+        self.keys = list(trainable_keys())
+        if mode != 'adapt':
+            enc_keys = []
+            for net in ('depth_encoder', 'pose_encoder'):
+                for key, _, kind in net_layouts()[net]:
+                    if kind in ('bn_mean', 'bn_var', 'bn_count', 'fc', 'fc_bias'):          # buffers; resnet.fc never gets a gradient
+                        continue
+                    if mode == 'adapt_enc' and 'bn' in key:
+                        continue
+                    enc_keys.append((net, key))
+            self.keys = enc_keys[:len(enc_keys) // 2] + [k for k in self.keys if k[0] == 'depth_decoder'] + \
+                enc_keys[len(enc_keys) // 2:] + [k for k in self.keys if k[0] == 'pose_decoder']
+        for net, key in self.keys:
             t = self.params[net][key]
             t.requires_grad_(True)
             self.trainable.append(t)
@@ -406,7 +428,7 @@ class OracleAdapter:
 
     def step(self, batch: Dict[object, Tensor], noise: Sequence[Tensor],
              sample_weights: Optional[Tensor] = None, update: bool = True, **kw):
-        outputs, losses = process_batch(self.params, batch, self.cfg, noise, sample_weights, **kw)
+        outputs, losses = process_batch(self.params, batch, self.cfg, noise, sample_weights, bn_training=self.mode == 'train', **kw)
         self.optimizer.zero_grad()
         losses['loss'].backward()
         if update:
@@ -414,7 +436,7 @@ class OracleAdapter:
         return outputs, losses
 
     def grads(self) -> Dict[Tuple[str, str], Tensor]:
-        return {nk: t.grad.detach().clone() for nk, t in zip(trainable_keys(), self.trainable)}
+        return {nk: t.grad.detach().clone() for nk, t in zip(self.keys, self.trainable) if t.grad is not None}
 
 
 def time_adapt_steps(batch_size: int, height: int, width: int, steps: int, warmup: int,

@@ -56,6 +56,12 @@ BIG_REPLAY_CASES = {
 REPLAY_CASES.update({k: v for k, v in BIG_REPLAY_CASES.items() if k.endswith('_replay')})
 CASES.update({k: v for k, v in BIG_REPLAY_CASES.items() if not k.endswith('_replay')})
 ONLINE_LOSS_WEIGHT = {'small_b4_replay': 0.4}
+# full training path: the reference in _set_train() mode (BatchNorm batch statistics, every parameter
+# trainable) and after _set_adapt(freeze_encoder=False) (BatchNorm eval, encoder convolutions trainable): name -> (spec, mode)
+TRAIN_CASES = {
+    'small_b2_train': ((2, 64, 96, True, None, 11), 'train'),
+    'small_b3_adapt_enc': ((3, 64, 96, True, None, 12), 'adapt_enc'),
+}
 # stride of the stored ('disp', s) maps / of the stored depth and warped maps
 DISP_SUB = {'full_b8_replay': (4, 2, 1, 1), 'hires_b8_replay': (8, 4, 2, 1), 'hires_b1': (4, 2, 1, 1)}
 MAP_SUB = {'full_b8_replay': 8, 'hires_b8_replay': 16, 'hires_b1': 8}
@@ -227,6 +233,57 @@ def run_case(name, spec, out_dir: Path):
     print(f'{name}: loss={float(losses["loss"]):.6f} keys={len(rec)}')
 
 
+def run_train_case(name, spec, mode, out_dir: Path):
+    """one step of the reference with trainable encoders: losses, same-weights outputs, gradient norms of EVERY tensor that
+    receives a gradient, BatchNorm running statistics after the forward pass, loss of a second step"""
+    b, h, w, coherent, max_depth, seed = spec
+    torch.manual_seed(0)
+    pred, params = build_reference(b, h, w, max_depth)
+    batch = orc.make_batch(b, h, w, seed=seed, coherent=coherent)
+    noise = orc.make_noise(b, h, w, seed=seed)
+    rec = {'meta': np.array([b, h, w, int(coherent), -1.0 if max_depth is None else max_depth, seed], dtype=np.float64),
+           'train_mode': np.array([1.0 if mode == 'train' else 0.0])}
+    if mode == 'train':
+        pred._set_train()
+    else:
+        pred._set_adapt(freeze_encoder=False)
+    with injected_noise(noise):
+        outputs, losses = pred._process_batch(dict(batch))
+    pred.optimizer.zero_grad()
+    losses['loss'].backward()
+    for s in range(4):
+        rec[f'disp_{s}'] = outputs[('disp', s)].detach().numpy()
+    for f in (-1, 1):
+        rec[f'translation_{f}'] = outputs[('translation', 0, f)].detach().numpy()
+        rec[f'axis_angle_{f}'] = outputs[('axis_angle', 0, f)].detach().numpy()
+    for k, v in losses.items():
+        rec['loss:' + k] = v.detach().reshape(-1).numpy()
+    n_grads = 0
+    for net in orc.NET_NAMES:
+        for key, p in pred.models[net].named_parameters():
+            if p.grad is None:
+                continue
+            n_grads += 1
+            rec[f'grad_norm:{net}:{key}'] = np.array([float(p.grad.double().norm())])
+            rec[f'grad_sample:{net}:{key}'] = sample_flat(p.grad)
+    rec['n_grads'] = np.array([n_grads])
+    for net in ('depth_encoder', 'pose_encoder'):
+        sd = pred.models[net].state_dict()
+        for key in ('resnet.bn1', 'resnet.layer2.0.downsample.1', 'resnet.layer4.1.bn2'):
+            rec[f'running_mean:{net}:{key}'] = sd[key + '.running_mean'].numpy().copy()
+            rec[f'running_var:{net}:{key}'] = sd[key + '.running_var'].numpy().copy()
+    pred.optimizer.step()
+    for net, key in (('depth_encoder', 'resnet.layer1.0.conv1.weight'), ('pose_encoder', 'resnet.conv1.weight'),
+                     ('depth_decoder', 'upconv_0_0.conv.conv.weight')):
+        rec[f'delta1_sample:{net}:{key}'] = sample_flat(pred.models[net].state_dict()[key] - params[net][key])
+    with injected_noise(noise):
+        _, losses2 = pred._process_batch(dict(batch))
+    rec['loss2'] = losses2['loss'].detach().reshape(-1).numpy()
+    out_dir.mkdir(parents=True, exist_ok=True)
+    np.savez_compressed(out_dir / f'{name}.npz', **rec)
+    print(f'{name}: loss={float(losses["loss"].detach()):.6f} grads={n_grads} loss2={float(losses2["loss"].detach()):.6f}')
+
+
 def main():
     out_dir = ROOT / 'tests' / 'golden'
     only = sys.argv[1:]
@@ -234,6 +291,10 @@ def main():
         if only and name not in only:
             continue
         run_case(name, spec, out_dir)
+    for name, (spec, mode) in TRAIN_CASES.items():
+        if only and name not in only:
+            continue
+        run_train_case(name, spec, mode, out_dir)
 
 
 if __name__ == '__main__':

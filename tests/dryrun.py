@@ -23,7 +23,9 @@ def _fill(eng):
 def dry_run_backend():
     from clslam_b200 import _lib as L
     from clslam_b200 import depth_pose_prediction as dpp
-    from clslam_b200 import engine
+    from clslam_b200 import engine, train_engine
+    te = train_engine.TrainEngine
+    saved_te = (te.forward, te.forward_backward, te.backward, te.adam)
     saved = (dpp.DepthPosePrediction._require_cuda, engine.Plan.run, engine.AdaptEngine.forward, engine.AdaptEngine.forward_backward,
              engine.AdaptEngine.backward, engine.AdaptEngine.adam, L.check)
     calls = {'forward': 0, 'forward_backward': 0, 'adam': 0, 'plan_runs': 0}
@@ -41,6 +43,8 @@ def dry_run_backend():
     engine.AdaptEngine.forward_backward = count('forward_backward', _fill)
     engine.AdaptEngine.backward = count('forward_backward')
     engine.AdaptEngine.adam = count('adam')
+    te.forward, te.forward_backward, te.backward, te.adam = (count('forward', _fill), count('forward_backward', _fill),
+                                                             count('forward_backward'), count('adam'))
     L.check = lambda rc, what='': None          # clslam_set_device fails without a GPU
     dpp.L.check = L.check
     try:
@@ -48,4 +52,5 @@ def dry_run_backend():
     finally:
         (dpp.DepthPosePrediction._require_cuda, engine.Plan.run, engine.AdaptEngine.forward, engine.AdaptEngine.forward_backward,
          engine.AdaptEngine.backward, engine.AdaptEngine.adam, L.check) = saved
+        te.forward, te.forward_backward, te.backward, te.adam = saved_te
         dpp.L.check = L.check

@@ -83,8 +83,19 @@ def test_api_surface_and_errors():
     pred._set_adapt(True)
     assert not any(p.requires_grad for n, p in pred.models['depth_encoder'].named_parameters())
     assert all(p.requires_grad for p in pred.models['depth_decoder'].parameters())
-    with pytest.raises(NotImplementedError):
-        pred._set_adapt(freeze_encoder=False)
+    assert pred._mode == 'adapt'
+    pred._set_adapt(freeze_encoder=False)          # the reference never re-enables requires_grad: still everything frozen
+    assert pred._mode == 'adapt'
+    # :807-827 on a fresh object with freeze_encoder=False: 'bn'-named parameters frozen, encoder convolutions (and, by the
+    # reference's substring test, the downsample.1 BatchNorms) trainable -> the step runs on the full training plan
+    fresh = DepthPosePrediction(DatasetConfig(height=64, width=96), Config(batch_size=2), device='cpu')
+    fresh._set_adapt(freeze_encoder=False)
+    assert fresh._mode == 'adapt_enc'
+    names = [n for n, p in fresh.models['depth_encoder'].named_parameters() if p.requires_grad]
+    assert 'resnet.conv1.weight' in names and 'resnet.layer2.0.downsample.1.weight' in names
+    assert not any('bn' in n for n in names) and len(names) == 20 + 2 * 3 + 2          # + resnet.fc (never gets a gradient)
+    fresh._set_train()
+    assert fresh._mode == 'train' and all(m.training for m in fresh.models.values())
 
 
 def test_no_cpu_fallback():
@@ -155,3 +166,30 @@ def test_mode_switches_are_idempotent_and_cheap():
     pred.models['pose_encoder'].train()
     pred._set_eval()
     assert all(not m.training for m in pred.models['pose_encoder'].modules())
+
+
+def test_train_loop_host_logic(tmp_path, capsys):
+    """train() (:219-289) with the kernels replaced by the dry-run stand-in: one step per batch on the full training plan,
+    lr_scheduler.step() per epoch (StepLR, :205), checkpoints every `save_frequency` epochs and at the end, resume from `epoch`"""
+    import torch
+    from tests.dryrun import dry_run_backend
+    from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
+    cfg = Config(batch_size=2, num_epochs=3, scheduler_step_size=2, save_frequency=2, log_path=tmp_path)
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), cfg, device=torch.device('cpu'), use_cuda_graph=False)
+    batch = orc.make_batch(2, 64, 96)
+    with pytest.raises(NotImplementedError):
+        pred.train()                                        # the dataset loaders are outside the path
+    with dry_run_backend() as calls:
+        pred.train(dataloader=[dict(batch), dict(batch)], verbose=False)
+        assert calls['forward_backward'] == 6 and calls['adam'] == 6
+        assert pred._mode == 'train' and pred.epoch == 3 and pred.is_trained
+        assert pred.optimizer.param_groups[0]['lr'] == pytest.approx(1e-5)          # one StepLR decay after epoch 2
+        saved = sorted(p.name for p in (tmp_path / 'models').iterdir())
+        assert saved == ['weights_002', 'weights_003']
+        # resume: nothing left to do at num_epochs, a larger num_epochs continues from epoch 4
+        pred.num_epochs = 4
+        pred.train(dataloader=[dict(batch)], verbose=False)
+        assert calls['forward_backward'] == 7 and pred.epoch == 4
+    # the encoders' Parameters are views of the flat training buffers and carry gradient views
+    g = pred.encoder_gradients()
+    assert len(g) == 2 * 60 and g[('depth_encoder', 'resnet.layer2.0.downsample.0.weight')].shape == (128, 64, 1, 1)

@@ -63,3 +63,34 @@ def test_plan_builds_and_is_consistent(b, h, w):
         # batch 1: the same forward / dgrad plan (small maps in the split-K form); the weight gradients of the small-map
         # layers stay on the gather kernel (measured faster at batch 1, profiles/r02_ab_summary.txt)
         assert k['conv_tma'] == 64 and k['gather'] == 11 and k['wgrad_tma'] == 5
+
+
+@pytest.mark.parametrize('bn_training', [True, False])
+def test_training_plan_builds(bn_training):
+    """the full training plan (encoders trainable, explicit BatchNorm; clslam_b200/train_engine.py) builds on the CPU: one
+    weight gradient per trainable convolution, one BatchNorm backward per BatchNorm, workspace sized"""
+    from clslam_b200.train_engine import TrainEngine
+    dev = torch.device('cpu')
+    b, h, w = 2, 64, 96
+    pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b), device=dev)
+    ns = pred._main
+    for ef in ns.enc_flat.values():
+        ef.ensure_training_buffers()
+    eng = TrainEngine(batch=b, height=h, width=w, batch_global=b, has_sample0=True, depth_enc=ns.models['depth_encoder'],
+                      pose_enc=ns.models['pose_encoder'], depth_flat=ns.enc_flat['depth_encoder'], pose_flat=ns.enc_flat['pose_encoder'],
+                      flat=ns.flat, min_depth=0.1, max_depth=None, disparity_smoothness=1e-3, velocity_loss_scaling=0.05,
+                      bn_training=bn_training, device=dev)
+    names = [o[0] for o in eng.plan.ops if o[1] is not None]
+    assert len(names) == len(set(names)), 'duplicate op names'
+    assert sum(n.endswith('.wgrad') for n in names) == 18 + 2 * 20
+    assert sum(n.endswith('.bn') for n in names) == 2 * 20 and sum(n.endswith('.bwd') and '.bn' in n or n.endswith('bn.bwd') for n in names) >= 2 * 20
+    assert 0 < eng.n_fwd_ops < eng.n_bwd_ops == len(eng.plan.ops)
+    # the encoder Parameters are views of the flat buffers: what Adam updates is what state_dict() saves
+    ef = ns.enc_flat['depth_encoder']
+    wv = ns.models['depth_encoder'].resnet.layer1[0].conv1.weight
+    ix = ef.index['layer1.0.conv1']
+    assert wv.data_ptr() == ef.params.data_ptr() + 4 * ix['off'] and wv.shape == (64, 64, 3, 3)
+    ef.params[ix['off']] += 1.0
+    assert float(wv[0, 0, 0, 0]) == float(ef.params[ix['off']])
+    m = ef.frozen_mask()
+    assert float(m.sum()) == sum(v['numel'] for v in ef.index.values())          # fresh object: everything trainable

@@ -121,3 +121,47 @@ def test_replay_case_really_differs_from_the_plain_one():
     adapter = orc.OracleAdapter(params, cfg)
     _, uniform = adapter.step(batch, noise, None, update=False)
     assert abs(float(uniform['loss']) - float(rec['loss:loss'][0])) > 1e-4 * float(rec['loss:loss'][0])
+
+
+# ---- full training path: the reference in _set_train() / _set_adapt(freeze_encoder=False) mode ----------
+TRAIN = [('small_b2_train', 'train'), ('small_b3_adapt_enc', 'adapt_enc')]
+
+
+def load_train_case(name):
+    rec = np.load(GOLDEN / f'{name}.npz')
+    b, h, w, coherent, max_depth, seed = rec['meta']
+    b, h, w, seed = int(b), int(h), int(w), int(seed)
+    cfg = orc.OracleConfig(h, w, b, max_depth=None if max_depth < 0 else float(max_depth))
+    return rec, cfg, orc.make_params(0), orc.make_batch(b, h, w, seed=seed, coherent=bool(coherent)), orc.make_noise(b, h, w, seed=seed)
+
+
+@pytest.mark.parametrize('name,mode', TRAIN)
+def test_oracle_training_modes_match_reference(name, mode):
+    """BatchNorm with batch statistics (+ running-stat update) and gradients of every encoder tensor, against the reference
+    run in that mode (oracle/make_golden.py::run_train_case)"""
+    rec, cfg, params, batch, noise = load_train_case(name)
+    adapter = orc.OracleAdapter(params, cfg, mode=mode)
+    outputs, losses = adapter.step(batch, noise, None)
+    for s in range(4):
+        assert rel(outputs[('disp', s)].detach().numpy(), rec[f'disp_{s}']) < 5e-6
+    for f in (-1, 1):
+        assert rel(outputs[('translation', 0, f)].detach().numpy(), rec[f'translation_{f}']) < 2e-5
+        assert rel(outputs[('axis_angle', 0, f)].detach().numpy(), rec[f'axis_angle_{f}']) < 2e-5
+    for k in [k[5:] for k in rec.files if k.startswith('loss:')]:
+        np.testing.assert_allclose(losses[k].detach().reshape(-1).numpy(), rec['loss:' + k], rtol=5e-5, atol=1e-9, err_msg=k)
+    grads = adapter.grads()
+    assert len(grads) == int(rec['n_grads'][0]) == (156 if mode == 'train' else 88)
+    for (net, key), g in grads.items():
+        gn = float(rec[f'grad_norm:{net}:{key}'][0])
+        # gradients of a convolution in front of a training-mode BatchNorm are differences of large terms: looser
+        assert abs(float(g.double().norm()) - gn) <= 2e-3 * gn + 1e-9, (net, key)
+    for net in ('depth_encoder', 'pose_encoder'):
+        for key in ('resnet.bn1', 'resnet.layer2.0.downsample.1', 'resnet.layer4.1.bn2'):
+            for stat in ('running_mean', 'running_var'):
+                got = adapter.params[net][f'{key}.{stat}'].numpy()
+                want = rec[f'{stat}:{net}:{key}']
+                assert rel(got, want) < 1e-5, (net, key, stat)
+                if mode != 'train':          # evaluation-mode BatchNorm leaves its statistics alone
+                    assert np.array_equal(got, params[net][f'{key}.{stat}'].numpy())
+    _, losses2 = adapter.step(batch, noise, None)
+    np.testing.assert_allclose(losses2['loss'].detach().numpy(), rec['loss2'], rtol=2e-3)
