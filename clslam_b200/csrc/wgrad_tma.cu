@@ -210,19 +210,24 @@ wgrad3x3_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 
 // dW[co][r][s][ci] = sum over splits of ws[(cb, chunk, split)][r * CC + ci % CC][s * CO + co % CO]
 // ... and db[o] = sum over the bias_grad_partial blocks (the blocks past the dW tiles)
-// One block = one tap x 32 output channels x 32 input channels: the partial sums are read along co (contiguous in the
-// workspace), transposed through shared memory and written along ci (contiguous in dW).  The round-1 kernel wrote dW with a
-// 9 * ci * 4-byte stride between neighbouring threads (one 32-byte sector per element).
-__global__ void __launch_bounds__(256)
+// One block = one tap x 32 output channels x 8 input channels x G groups of partial sums (blockDim = 32 x 8 x G): the partial
+// sums are read along co (contiguous in the workspace), every thread adds its group's share of the `splits` CTA partials with
+// eight independent chains (the kernel is a latency-bound column sum of a [splits][9 ci co] matrix: what counts is loads in
+// flight), the G group sums are added in a fixed order (deterministic), and the result is transposed through shared memory and
+// written along ci (contiguous in dW, one 32-byte sector per 8 threads).  The round-2a kernel used 32 x 32 tiles with one
+// thread per 4 elements and no groups: 9 .. 36 blocks for the thin decoder layers, 25 - 35 us per launch at 0.6 TB/s.
+__global__ void __launch_bounds__(1024)
 wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co, int ci, int cc, int cob, int ci_chunks, int splits,
                     const float* __restrict__ bias_part, int bias_blocks, float* __restrict__ db, int tiles_o, int tiles_c) {
   pdl_wait();
   pdl_trigger();
-  __shared__ float tile[32][33];
+  __shared__ float tile[4][8][33];
+  const int tx = threadIdx.x, ty = threadIdx.y, gz = threadIdx.z, G = blockDim.z;
+  const int tid = ty * 32 + tx;                 // within the group
   const int n_tiles = 9 * tiles_o * tiles_c;
   if ((int)blockIdx.x >= n_tiles) {          // bias blocks: fixed-order sum of the per-block channel sums
-    const int o = ((int)blockIdx.x - n_tiles) * 256 + threadIdx.x;
-    if (db && o < co) {
+    const int o = ((int)blockIdx.x - n_tiles) * 256 + tid;
+    if (gz == 0 && db && o < co) {
       float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
       int b = 0;
       for (; b + 4 <= bias_blocks; b += 4) {
@@ -239,33 +244,34 @@ wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dw, int co
   const int t = blockIdx.x;
   const int tc = t % tiles_c, to = (t / tiles_c) % tiles_o, tap = t / (tiles_c * tiles_o);
   const int r = tap / 3, s = tap - r * 3;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int o = to * 32 + tx;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int cl = ty + 8 * j, c = tc * 32 + cl;
-    float v = 0.f;
-    if (o < co && c < ci) {
-      const int pair = (o / cob) * ci_chunks + c / cc;
-      const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
-      // fixed summation order (deterministic), four independent chains so the loads overlap
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      int k = 0;
-      for (; k + 4 <= splits; k += 4) {
-        a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride];
-        a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
-      }
-      for (; k < splits; ++k) a0 += p[(size_t)k * cta_stride];
-      v = (a0 + a1) + (a2 + a3);
+  const int o = to * 32 + tx, c = tc * 8 + ty;
+  float v = 0.f;
+  if (o < co && c < ci) {
+    const int pair = (o / cob) * ci_chunks + c / cc;
+    const float* p = ws + (size_t)pair * splits * cta_stride + (size_t)(r * cc + c % cc) * cols + s * cob + o % cob;
+    const int k0 = (splits * gz) / G, k1 = (splits * (gz + 1)) / G;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
+      a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride];
+      a2 += p[(size_t)(k + 2) * cta_stride]; a3 += p[(size_t)(k + 3) * cta_stride];
+      a4 += p[(size_t)(k + 4) * cta_stride]; a5 += p[(size_t)(k + 5) * cta_stride];
+      a6 += p[(size_t)(k + 6) * cta_stride]; a7 += p[(size_t)(k + 7) * cta_stride];
     }
-    tile[cl][tx] = v;
+    for (; k + 2 <= k1; k += 2) { a0 += p[(size_t)k * cta_stride]; a1 += p[(size_t)(k + 1) * cta_stride]; }
+    if (k < k1) a2 += p[(size_t)k * cta_stride];
+    v = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
   }
+  tile[gz][ty][tx] = v;
   __syncthreads();
-  const int c = tc * 32 + tx;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int ol = ty + 8 * j, oo = to * 32 + ol;
-    if (oo < co && c < ci) dw[((size_t)oo * 9 + tap) * ci + c] = tile[tx][ol];
+  if (gz == 0) {
+    const int wc = tid & 7, wo = tid >> 3;          // 8 consecutive threads = 8 consecutive input channels of one (co, tap)
+    const int oo = to * 32 + wo, cw = tc * 8 + wc;
+    if (oo < co && cw < ci) {
+      float acc = tile[0][wc][wo];
+      for (int g2 = 1; g2 < G; ++g2) acc += tile[g2][wc][wo];
+      dw[((size_t)oo * 9 + tap) * ci + cw] = acc;
+    }
   }
 }
 
@@ -439,9 +445,10 @@ int clslam_wgrad3x3_tma(const clslam_planes* x, int pad_mode, const clslam_plane
     launch_k(bias_grad_partial_kernel, dim3(kBiasBlocks), dim3(256), 0, st, dz_f32, pixels, dz->c, bias_part);
     if ((rc = finish_launch("bias_grad"))) return rc;
   }
-  const int tiles_o = (dz->c + 31) / 32, tiles_c = (x->c + 31) / 32;
+  const int tiles_o = (dz->c + 31) / 32, tiles_c = (x->c + 7) / 8;
   const int blocks = 9 * tiles_o * tiles_c + (db ? (dz->c + 255) / 256 : 0);
-  launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(256), 0, st, g.ws, dw, dz->c, x->c, p.cc, p.cob, p.ci_chunks, p.splits,
+  const int groups = p.splits >= 32 ? 4 : (p.splits >= 16 ? 2 : 1);          // partial-sum groups per element (loads in flight)
+  launch_k(wgrad_reduce_kernel, dim3(blocks), dim3(32, 8, groups), 0, st, g.ws, dw, dz->c, x->c, p.cc, p.cob, p.ci_chunks, p.splits,
            (const float*)bias_part, (int)kBiasBlocks, db, tiles_o, tiles_c);
   return finish_launch("wgrad_reduce");
 }
