@@ -38,7 +38,7 @@ class ConvTma(Structure):
     _fields_ = [('inp', Planes), ('pad_mode', c_int), ('cout', c_int), ('w_hi', c_void_p), ('w_lo', c_void_p),
                 ('scale', c_void_p), ('shift', c_void_p), ('act', c_int), ('residual', POINTER(Planes)), ('gate', c_void_p), ('gate_act', c_int), ('y', c_void_p),
                 ('out', POINTER(Planes)), ('out_up', c_int), ('out_halo', c_int), ('taps', c_int), ('flags', c_int),
-                ('splitk_counters', c_void_p)]
+                ('splitk_counters', c_void_p), ('sm_budget', c_int)]
 
 
 class PhotoArgs(Structure):

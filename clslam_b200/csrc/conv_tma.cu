@@ -116,6 +116,7 @@ struct TmaConvArgs {
   // stack is row v % tall_hp of image v / tall_hp (valid when < ho)
   int tall_hp, tall_n;
   FastDiv div_hp;
+  int grid_cap;                  // host side only: clslam_conv_tma.sm_budget (0 = every SM)
 };
 
 
@@ -954,7 +955,8 @@ static int launch_tma_conv(const CUtensorMap& ma, const CUtensorMap& mb, TmaConv
   if (g.na < 2) { set_error("conv3x3_tma: shared memory plan failed"); return -3; }
   const int smem = (int)(g.na * C::kAStage + b_bytes + 1024 + kTmaBarBytes);
   const long long total = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks * (SK ? g.ksplit : 1);
-  const int grid = (int)(total < tma_num_sms() ? total : tma_num_sms());
+  const int cap = (g.grid_cap > 0 && g.grid_cap < tma_num_sms()) ? g.grid_cap : tma_num_sms();
+  const int grid = (int)(total < cap ? total : cap);
   if constexpr (SK) {
     if (g.cluster_ks > 0) {          // one work item per CTA, the ksplit slices of a tile = one cluster
       if (total > tma_num_sms() || g.cluster_ks != g.ksplit || g.na * C::kAStage < kTcBM * (BN + 4) * 4) {
@@ -991,11 +993,11 @@ static bool tma_splitk_waves() {
   return v == 1;
 }
 struct TmaSplit { int ksplit, cs_per; };
-static TmaSplit tma_split_plan(long long items, int n_cs, int kc, int bn, int taps) {
+static TmaSplit tma_split_plan(long long items, int n_cs, int kc, int bn, int taps, int budget = 0) {
   TmaSplit sp{1, n_cs};
   const bool built = kc == 64 && ((taps == 3 && (bn == 64 || bn == 128)) || (taps == 2 && bn == 128));
   if (!built || items < 1 || n_cs < 2) return sp;
-  const int sms = tma_num_sms();
+  const int sms = (budget > 0 && budget < tma_num_sms()) ? budget : tma_num_sms();
   if (items > tma_splitk_items()) {
     if (!tma_splitk_waves() || items >= sms) return sp;
     long long best = n_cs;
@@ -1007,7 +1009,7 @@ static TmaSplit tma_split_plan(long long items, int n_cs, int kc, int bn, int ta
     }
     return sp;
   }
-  long long want = tma_num_sms() / items;            // one wave of work items
+  long long want = sms / items;                      // one wave of work items (within the launch's SM budget)
   if (want > n_cs) want = n_cs;
   if (want < 2) return sp;
   sp.cs_per = (int)((n_cs + want - 1) / want);
@@ -1078,7 +1080,7 @@ int clslam_conv3x3_tma(const clslam_conv_tma* p, void* stream) { return conv3x3_
 long long clslam_conv3x3_tma_workspace_bytes(const clslam_conv_tma* p) {
   TmaGeom q{};
   if (tma_geometry(p, q)) return -1;
-  const TmaSplit sp = tma_split_plan(q.items, q.chunks * q.taps, q.kc, q.bn, q.taps);
+  const TmaSplit sp = tma_split_plan(q.items, q.chunks * q.taps, q.kc, q.bn, q.taps, p->sm_budget);
   if (sp.ksplit < 2) return 0;
   return (long long)sp.ksplit * p->in.n * q.ho * q.wo * p->cout * 4;
 }
@@ -1113,6 +1115,7 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
   g.n_blocks = cout / bn; g.chunks = cin / kc;
   g.div_nb = make_fastdiv(g.n_blocks); g.div_tpi = make_fastdiv(g.tiles_x * g.tiles_y); g.div_tx = make_fastdiv(g.tiles_x);
   g.debug = g_tma_debug;
+  g.grid_cap = p->sm_budget;
   g.gate = p->gate; g.gate_act = p->gate_act;
   g.act = p->act; g.scale = p->scale; g.shift = p->shift; g.y = p->y;
   if (p->residual) {
@@ -1163,7 +1166,7 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
   cudaStream_t st = as_stream(stream);
   if (workspace) {
     const long long items = (long long)g.n_img * g.tiles_x * g.tiles_y * g.n_blocks;
-    const TmaSplit sp = tma_split_plan(items, g.chunks * taps, kc, bn, taps);
+    const TmaSplit sp = tma_split_plan(items, g.chunks * taps, kc, bn, taps, p->sm_budget);
     if (sp.ksplit >= 2) {
       const long long slice = (long long)in.n * ho * wo * cout;
       if (workspace_bytes < sp.ksplit * slice * 4) {
@@ -1175,7 +1178,8 @@ static int conv3x3_tma_impl(const clslam_conv_tma* p, void* workspace, long long
         const int n_cs = g.chunks * taps;
         for (int c = 8; c >= 2; c >>= 1) {
           const int per = (n_cs + c - 1) / c;
-          if (c <= sp.ksplit && items * c <= tma_num_sms() && (long long)(c - 1) * per < n_cs) { cks = c; break; }
+          if (c <= sp.ksplit && items * c <= (p->sm_budget > 0 && p->sm_budget < tma_num_sms() ? p->sm_budget : tma_num_sms()) &&
+              (long long)(c - 1) * per < n_cs) { cks = c; break; }
         }
       }
       if (cks > 0) {

@@ -18,6 +18,7 @@
 //
 //   warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: final TMEM -> workspace copy.
 #include <cuda.h>
+#include <cstdlib>
 #include <cudaTypedefs.h>
 
 #include "planes.cuh"
@@ -344,6 +345,9 @@ static int wg_sms() {
   if (sms == 0) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    // CLSLAM_WGRAD_SMS: CTA budget of a weight-gradient launch (default: every SM).  The launches run on a side lane next to the
+    // input-gradient chain; fewer CTAs leave SMs to that chain and mean fewer partial sums for wgrad_reduce_kernel
+    if (const char* e = getenv("CLSLAM_WGRAD_SMS")) { const int v = atoi(e); if (v >= 8 && v < sms) sms = v; }
   }
   return sms;
 }

@@ -77,6 +77,11 @@ TMA_TALL = _flag('CLSLAM_TMA_TALL')
 # on a copy stream meanwhile and the second graph waits for them.  The identity candidates then run at the head of the second
 # graph instead of on lane 2 next to the encoders.
 H2D_OVERLAP = _flag('CLSLAM_H2D_OVERLAP')
+# SM budgets of the two networks' forward launches (clslam_conv_tma.sm_budget).  The depth encoder (lane 0, the critical path:
+# the decoder follows it) and the pose network (lane 1) run side by side, and a CTA of the TMA convolution holds a whole SM:
+# two launches only overlap when their CTA counts fit the 148 SMs together.  0 = no limit.
+DEPTH_ENC_SMS = int(os.environ.get('CLSLAM_DEPTH_ENC_SMS', '0'))
+POSE_NET_SMS = int(os.environ.get('CLSLAM_POSE_NET_SMS', '-1'))          # -1: 64 at batch 1 (measured: 1.032 -> 1.002 ms / step), else 0
 
 
 def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
@@ -211,6 +216,7 @@ class Plan:
         self._events: Dict[str, torch.cuda.Event] = {}
         self._side: List[torch.cuda.Stream] = []
         self._n_marks = 0
+        self.sm_budget = 0          # clslam_conv_tma.sm_budget of the TMA convolutions added from here on (0 = every SM)
 
     def alloc(self, *shape, dtype=torch.float32, zero=False) -> torch.Tensor:
         t = (torch.zeros if zero else torch.empty)(*shape, dtype=dtype, device=self.device)
@@ -294,6 +300,7 @@ class Plan:
         if out is not None:
             a.out = ctypes.pointer(out)
         a.out_up, a.out_halo, a.taps = out_up, out_halo, taps
+        a.sm_budget = self.sm_budget
         if TMA_TALL and taps in (2, 3) and pad_mode != L.PAD_FULL:          # (2: the space-to-depth planes have an all-zero halo)
             a.flags = L.TMA_IN_HALO_VALID
         self.keep.append(a)
@@ -775,8 +782,10 @@ class AdaptEngine:
         # decoder geometry first: which layers run the TMA kernel decides where the encoder writes its skip features
         u0, u1, cat, skips, feat4_pl, fh, fw = decoder_geometry(plan, b, h, w)
         y1_pl = {}
+        plan.sm_budget = DEPTH_ENC_SMS
         feats = build_encoder(plan, depth_prep, self.depth_in, b, h, w, 'depth_enc', skips=skips, feat4_planes=feat4_pl,
                               x_s2d=depth_s2d, side_lane=2)
+        plan.sm_budget = 0
         self.depth_feats = feats
         dd = 'depth_decoder'
         self.y = {}          # decoder activations (ELU outputs), NHWC fp32 (dispconv, backward)
@@ -842,6 +851,7 @@ class AdaptEngine:
         pf4_pl = PlaneBuf(plan, 2 * b, h >> 5, w >> 5, ENC_CH[4]).view() if (TMA_DS and tma_ok(2 * b, h >> 5, w >> 5, 512, 256)) else None
         # (lane 3, not 2: lane 2 holds dispconv_1..3 by now, which wait for late decoder stages -- stream order would park the
         # pose encoder's down-sampling convolutions behind them)
+        plan.sm_budget = POSE_NET_SMS if POSE_NET_SMS >= 0 else (64 if b == 1 else 0)
         pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc', x_s2d=pose_s2d, feat4_planes=pf4_pl,
                                side_lane=3)
         pf4 = pfeats[4]
@@ -879,6 +889,7 @@ class AdaptEngine:
         self.invert_mask = 0b01                                     # pass 0 (frame -1) is inverted (:973)
         plan.simple('pose_head_fwd', lib.clslam_pose_head_fwd, _p(self.pose_act['pose_2']), _p(self.k_mat), b, hp, wp,
                     self.invert_mask, _p(self.axis_angle), _p(self.translation), _p(self.cam_t_cam), _p(self.proj))
+        plan.sm_budget = 0
 
         # ---- photometric chain + losses -------------------------------------------------------
         self.n_tiles = lib.clslam_photo_tiles(h, w)

@@ -152,6 +152,10 @@ typedef struct clslam_conv_tma {
                               launch site.  When the launch splits K, the CTA that delivers the last K slice of a tile adds the
                               slices (fixed order, deterministic) and runs the epilogue itself: no second kernel.  The kernel
                               leaves the counters at zero.  NULL: separate reduction / epilogue kernel (round-1 form). */
+  int sm_budget;           /* 0 = every SM.  > 0: at most this many CTAs (a CTA of this kernel family holds a whole SM: ~200 KB of
+                              shared memory), for launches that run NEXT TO another lane's launches -- two concurrent launches only
+                              overlap when their CTA counts add up to <= the SM count.  Applies to the persistent grid and to the
+                              split-K plan (same value in the workspace query and the launch). */
 } clslam_conv_tma;
 #define CLSLAM_TMA_SPLITK_COUNTERS 256
 /* flags bit (experimental): the stored halo ring of `in` is valid padding for this layer -- the reflection halo for
