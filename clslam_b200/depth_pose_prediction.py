@@ -277,6 +277,7 @@ class DepthPosePrediction:
                 except Exception:   # noqa: BLE001
                     pass
             ns.drop_plans()
+            ns.train_engines.clear()
         self._late_event = None
         self._last_engine = None
         if self.device.type == 'cuda':

@@ -54,6 +54,52 @@ def main():
         print(f'dp_check: 3 adapt steps ok, loss {float(l3["loss"]):.6f}, replicas identical: {same}')
         print('DP_CHECK_PASS' if (ok and same) else 'DP_CHECK_FAIL', flush=True)
     pred.close()          # the step graph holds captured NCCL kernels: release it before the communicator
+
+    # ---- full training plan, sharded (SURVEY 8(f) row 3 x 8(e)): _set_adapt(freeze_encoder=False) -- BatchNorm in evaluation mode,
+    # so the sharded step equals the full-batch step -- decoder AND encoder gradients after the all-reduce of the three flat
+    # buffers against the oracle on the global batch (exact-fp32 convolution mode: tests/test_gpu_train_e2e.py explains why),
+    # then two captured steps: every replica must hold bit-identical encoders
+    from clslam_b200 import _lib as L
+    L.load().clslam_set_conv_mode(0)
+    pred = DepthPosePrediction(DatasetConfig(height=h, width=w), Config(batch_size=b), data_parallel=True)
+    for n in orc.NET_NAMES:
+        pred.models[n].load_state_dict(params[n])
+    pred.noise_provider = lambda s, shape: noise[s]
+    pred._set_adapt(freeze_encoder=False)
+    assert pred._mode == 'adapt_enc'
+    pred.optimizer.zero_grad()
+    _, losses = pred._process_batch(dict(shard))
+    pred.backward()
+    torch.cuda.synchronize()
+    ok2 = True
+    if rank == 0:
+        adapter = orc.OracleAdapter(params, orc.OracleConfig(h, w, b), mode='adapt_enc')
+        _, ref_losses = adapter.step(full, noise, update=False)
+        ref = adapter.grads()
+        grads = dict(pred.gradients()); grads.update(pred.encoder_gradients())
+        worst, wkey = 0.0, None
+        for key, r in ref.items():
+            e = float((grads[key].cpu().double() - r.double()).norm() / (r.double().norm() + 1e-30))
+            if e > worst:
+                worst, wkey = e, key
+        e_loss = abs(float(losses['loss']) - float(ref_losses['loss'])) / abs(float(ref_losses['loss']))
+        print(f'dp_check (encoders trainable) world={world}: loss rel err {e_loss:.2e}, worst grad rel-L2 {worst:.2e} at {wkey} '
+              f'over {len(ref)} tensors')
+        ok2 = e_loss < 1e-4 and worst < 2e-3 and len(ref) == 88
+    pred.optimizer.step()
+    for _ in range(2):
+        eng = pred._stage_inputs(dict(shard)); pred._set_weights(eng, None); pred._draw_noise(eng); pred._step(eng)
+    torch.cuda.synchronize()
+    chk = torch.stack([ef.params.double().sum() for ef in pred._main.enc_flat.values()] + [pred._flat.params.double().sum()])
+    gathered = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(gathered, chk)
+    same2 = all(torch.equal(g, gathered[0]) for g in gathered)
+    moved = not torch.equal(pred.models['depth_encoder'].state_dict()['resnet.conv1.weight'].cpu(), params['depth_encoder']['resnet.conv1.weight'])
+    if rank == 0:
+        print(f'dp_check (encoders trainable): 3 steps ok, replicas identical: {same2}, encoder updated: {moved}')
+        print('DP_TRAIN_CHECK_PASS' if (ok2 and same2 and moved) else 'DP_TRAIN_CHECK_FAIL', flush=True)
+    L.load().clslam_set_conv_mode(1)
+    pred.close()
     dist.destroy_process_group()
 
 
