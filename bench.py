@@ -456,7 +456,7 @@ def dp_parity_check(pred, full, rank, world, b, h, w):
         for key, g in pred.gradients().items():
             ref = ref_grads[key].double()
             worst = max(worst, float((g.detach().cpu().double() - ref).norm() / (ref.norm() + 1e-30)))
-        lr = float(ref_losses['loss'])
+        lr = float(ref_losses['loss'].detach())
         out = {'loss_rel_err': abs(float(losses['loss']) - lr) / abs(lr), 'worst_grad_rel_l2': worst,
                'checker': f'CPU oracle on the global batch of {b_global} (rank 0, outside the timed regions), seeded tie-break noise'}
     return out

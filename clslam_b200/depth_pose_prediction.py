@@ -477,7 +477,8 @@ class DepthPosePrediction:
         if defer_unused and cuda:
             self._stage_event = torch.cuda.Event()
             self._stage_event.record(torch.cuda.current_stream(self.device))
-        overlap = H2D_OVERLAP and defer_unused and self.world == 1 and cuda
+        # (data-parallel: only when the gradient exchange lives inside the plan, i.e. the step is graph-capturable as a whole)
+        overlap = H2D_OVERLAP and defer_unused and cuda and (self.world == 1 or getattr(eng, 'grad_sync_in_plan', False))
         late: List[Tuple[Tensor, Tensor]] = []
         for key in list(inputs.keys()):
             val = inputs[key]
@@ -712,7 +713,7 @@ class DepthPosePrediction:
                 graphs[k1].replay(); self._allreduce_grads(eng); graphs[k2].replay()
             self.refresh_encoders()
             return
-        if self.world == 1 and H2D_OVERLAP and late_event is not None:
+        if (self.world == 1 or eng.grad_sync_in_plan) and H2D_OVERLAP and late_event is not None:
             # two graphs: the networks (need rgb_aug / intrinsics only) run while the photometric inputs are still in flight
             # (with nothing in flight -- inputs already resident, second and later iterations of adapt(steps=k) -- the step
             # is the single graph below)

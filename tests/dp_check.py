@@ -37,7 +37,7 @@ def main():
         adapter = orc.OracleAdapter(params, orc.OracleConfig(h, w, b))
         _, ref_losses = adapter.step(full, noise, update=False)
         ref = adapter.grads()
-        e_loss = abs(float(losses['loss']) - float(ref_losses['loss'])) / abs(float(ref_losses['loss']))
+        e_loss = abs(float(losses['loss']) - float(ref_losses['loss'].detach())) / abs(float(ref_losses['loss'].detach()))
         worst = 0.0
         for key, g in pred.gradients().items():
             r = ref[key]
@@ -82,7 +82,7 @@ def main():
             e = float((grads[key].cpu().double() - r.double()).norm() / (r.double().norm() + 1e-30))
             if e > worst:
                 worst, wkey = e, key
-        e_loss = abs(float(losses['loss']) - float(ref_losses['loss'])) / abs(float(ref_losses['loss']))
+        e_loss = abs(float(losses['loss']) - float(ref_losses['loss'].detach())) / abs(float(ref_losses['loss'].detach()))
         print(f'dp_check (encoders trainable) world={world}: loss rel err {e_loss:.2e}, worst grad rel-L2 {worst:.2e} at {wkey} '
               f'over {len(ref)} tensors')
         ok2 = e_loss < 1e-4 and worst < 2e-3 and len(ref) == 88

@@ -102,7 +102,7 @@ def test_matches_live_oracle_gradients_elementwise(name):
     _, losses = pred._process_batch(dict(batch))
     pred.backward()
     torch.cuda.synchronize()
-    assert abs(float(losses['loss']) - float(ref_losses['loss'])) < 1e-5 * abs(float(ref_losses['loss']))
+    assert abs(float(losses['loss']) - float(ref_losses['loss'].detach())) < 1e-5 * abs(float(ref_losses['loss'].detach()))
     for (net, key), g in pred.gradients().items():
         ref = ref_grads[(net, key)]
         got = g.detach().cpu()

@@ -136,7 +136,7 @@ def test_training_gradients_match_live_oracle_elementwise(name, mode, conv_mode)
     _, losses = pred._process_batch(dict(batch))
     pred.backward()
     torch.cuda.synchronize()
-    assert abs(float(losses['loss']) - float(ref_losses['loss'])) < 2e-5 * abs(float(ref_losses['loss']))
+    assert abs(float(losses['loss']) - float(ref_losses['loss'].detach())) < 2e-5 * abs(float(ref_losses['loss'].detach()))
     grads = dict(pred.gradients())
     grads.update(pred.encoder_gradients())
     worst, worst_key, errs = 0.0, None, []
