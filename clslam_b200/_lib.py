@@ -49,7 +49,7 @@ class PhotoArgs(Structure):
         ('identity', c_void_p), ('sample_w', c_void_p),
         ('disp', c_void_p * 4), ('noise', c_void_p * 4), ('depth', c_void_p * 4), ('warped', c_void_p * 4),
         ('argmin', c_void_p * 4), ('loss_partials', c_void_p), ('ddisp_full', c_void_p * 4),
-        ('dproj_partials', c_void_p),
+        ('dproj_partials', c_void_p), ('dyn_mask', c_void_p), ('reproj_w', c_void_p),
     ]
 
 
@@ -59,12 +59,16 @@ class LossArgs(Structure):
         ('has_sample0', c_int), ('disparity_smoothness', c_float), ('velocity_scale', c_float),
         ('loss_partials', c_void_p), ('sample_w', c_void_p), ('sample_w_global', c_void_p),
         ('disp', c_void_p * 4), ('color', c_void_p * 4), ('translation', c_void_p), ('rel_dist', c_void_p),
-        ('losses', c_void_p), ('smooth_grad', c_void_p),
+        ('losses', c_void_p), ('smooth_grad', c_void_p), ('reproj_w', c_void_p),
     ]
 
 
 # name -> (restype, argtypes); must list every function declared in include/clslam_b200.h
 SIGNATURES = {
+    'clslam_mask_prepare': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'clslam_smooth_masked': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                     c_void_p, c_void_p, c_void_p]),
+    'clslam_smooth_masked_apply': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'clslam_last_error': (c_char_p, []),
     'clslam_abi_version': (c_int, []),
     'clslam_launch_count': (c_longlong, []),

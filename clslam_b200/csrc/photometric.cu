@@ -231,6 +231,8 @@ __device__ __forceinline__ void photo_fwd_body(const clslam_photo_args& a, int t
         if (c1v < best) { best = c1v; arg = 1; }
         if (rep[0][j] < best) { best = rep[0][j]; arg = 2; }
         if (rep[1][j] < best) { best = rep[1][j]; arg = 3; }
+        // mask_dynamic (:1064-1068): a potentially dynamic pixel is not selected -- no loss, and code 4 matches no gradient path
+        if (a.dyn_mask && ld1(a.dyn_mask + (size_t)bb * hw + off) >= 0.5f) { best = 0.f; arg = 4; }
         a.argmin[s][(size_t)bb * hw + off] = (unsigned char)arg;
         local[s] += best;
       }

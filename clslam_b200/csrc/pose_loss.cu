@@ -212,7 +212,7 @@ loss_finalize_kernel(clslam_loss_args a) {
       float t = 0.f;
       for (int i = lane; i < a.n_tiles; i += 32) t += a.loss_partials[((size_t)s * a.b + bb) * a.n_tiles + i];
       t = warp_sum(t);
-      acc += a.sample_w[bb] * (t / hw);
+      acc += (a.reproj_w ? a.reproj_w : a.sample_w)[bb] * (t / hw);
     }
     __syncthreads();
     if (lane == 0) red[warp] = acc;

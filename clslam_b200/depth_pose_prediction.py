@@ -29,6 +29,7 @@ from .sharding import global_sample_weights, shard_range
 # data-parallel: all-reduce the gradients in buckets inside the step graph, overlapped with the backward pass (default);
 # CLSLAM_GRAD_BUCKETS=0 restores round 1's graph -> eager all-reduce of the whole buffer -> graph
 GRAD_BUCKETS = int(os.environ.get('CLSLAM_GRAD_BUCKETS', '1'))        # 0 / 1 / 2 / 5: see AdaptEngine (measured at 2 GPUs, profiles/r02_dp_buckets.md: 1 is fastest)
+LANE0_PRIORITY = int(os.environ.get('CLSLAM_LANE0_PRIORITY', '0'))
 BUCKET_ADAM = os.environ.get('CLSLAM_BUCKET_ADAM', '0') == '1'
 
 LOSS_SLOTS = {'reprojection_loss': 0, 'smooth_loss': 4, 'reg_loss': 8, 'depth_loss': 12}
@@ -196,8 +197,6 @@ class DepthPosePrediction:
         self.epoch = 0
 
         self._validate_sets(dataset_config)
-        if self.mask_dynamic:
-            raise NotImplementedError('mask_dynamic=True (pre-training masks, :1064-1068) is SURVEY.md 8(f) row 3')
         if self.multiple_gpus:
             raise ValueError('nn.DataParallel (multiple_gpus) is replaced by data_parallel=True: one process per '
                              'GPU under torch.distributed (SURVEY.md 8e)')
@@ -395,6 +394,10 @@ class DepthPosePrediction:
         ns = ns or self._main
         dp, pp = self._prepared('depth_encoder', ns), self._prepared('pose_encoder', ns)
         eng = ns.engines.get(batch)
+        if eng is None and self.mask_dynamic:
+            raise NotImplementedError('mask_dynamic=True (pre-training with dynamic-object masks, :1062-1068) runs on the training '
+                                      'plan: _set_train() / train() / _set_adapt(freeze_encoder=False); the frozen-encoder '
+                                      'adaptation and evaluation plans do not read masks')
         if eng is None:
             L.check(L.load().clslam_set_device(self.device.index or 0), 'set_device')
             if self.world > 1:
@@ -428,7 +431,7 @@ class DepthPosePrediction:
                               depth_flat=ns.enc_flat['depth_encoder'], pose_flat=ns.enc_flat['pose_encoder'], flat=ns.flat,
                               min_depth=self.min_depth, max_depth=self.max_depth, disparity_smoothness=self.disparity_smoothness,
                               velocity_loss_scaling=self.velocity_loss_scaling, bn_training=bn_training, device=self.device,
-                              emit_outputs=self.emit_outputs)
+                              emit_outputs=self.emit_outputs, mask_dynamic=self.mask_dynamic)
             eng.net_set = ns
             eng.kind = 'train' if bn_training else 'train_bn_eval'
             ns.train_engines[(batch, bn_training)] = eng
@@ -458,6 +461,9 @@ class DepthPosePrediction:
              ('relative_distance', 0): eng.rel_dist[0], ('relative_distance', 1): eng.rel_dist[1]}
         for s in range(1, 4):
             m[('rgb', 0, s)] = eng.color[s]
+        if getattr(eng, 'mask_dynamic', False):          # pre-training masks (:1066, :1081): training plan only
+            for s in range(4):
+                m[('mask', 0, s)] = eng.dyn_mask[s]
         return m
 
     def _stage_inputs(self, inputs: Dict[Any, Tensor], defer_unused: bool = False, ns: Optional[_NetSet] = None) -> AdaptEngine:
@@ -667,6 +673,16 @@ class DepthPosePrediction:
                 out[(net, 'resnet.' + key)] = g
         return out
 
+    def _graph_ctx(self, g):
+        """capture context of a step graph.  CLSLAM_LANE0_PRIORITY (default 0 = off): capture on a stream of that priority, so
+        that the kernel nodes of lane 0 -- the critical chain of the step -- are scheduled ahead of the side lanes' when both
+        have CTAs waiting for an SM (kernel nodes inherit the priority of the stream they were captured on)"""
+        if LANE0_PRIORITY == 0:
+            return torch.cuda.graph(g)
+        if getattr(self, '_capture_stream', None) is None:
+            self._capture_stream = torch.cuda.Stream(device=self.device, priority=LANE0_PRIORITY)
+        return torch.cuda.graph(g, stream=self._capture_stream)
+
     def _adam_lr(self) -> float:
         return float(self.optimizer.param_groups[0]['lr'])
 
@@ -696,7 +712,7 @@ class DepthPosePrediction:
                 key = (eng.b, kind, 'step', lr)
                 if key not in graphs:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with self._graph_ctx(g):
                         eng.forward_backward(); eng.adam(lr)
                     graphs[key] = g
                 graphs[key].replay()
@@ -704,10 +720,10 @@ class DepthPosePrediction:
                 k1, k2 = (eng.b, kind, 'fwdbwd'), (eng.b, kind, 'adam', lr)
                 if k1 not in graphs:
                     g1 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g1):
+                    with self._graph_ctx(g1):
                         eng.forward_backward()
                     g2 = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g2):
+                    with self._graph_ctx(g2):
                         eng.adam(lr)
                     graphs[k1], graphs[k2] = g1, g2
                 graphs[k1].replay(); self._allreduce_grads(eng); graphs[k2].replay()
@@ -720,12 +736,12 @@ class DepthPosePrediction:
             ka, kb = (eng.b, 'nets'), (eng.b, 'rest', lr)
             if ka not in graphs:
                 ga = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(ga):
+                with self._graph_ctx(ga):
                     eng.networks_forward()
                 graphs[ka] = ga
             if kb not in graphs:
                 gb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gb):
+                with self._graph_ctx(gb):
                     eng.photometric_and_backward(); eng.adam(lr)
                 graphs[kb] = gb
             graphs[ka].replay()
@@ -739,7 +755,7 @@ class DepthPosePrediction:
             g = graphs.get(key)
             if g is None:
                 g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
+                with self._graph_ctx(g):
                     eng.forward_backward(); eng.adam(lr)
                 graphs[key] = g
             g.replay()
@@ -747,10 +763,10 @@ class DepthPosePrediction:
             k1, k2 = (eng.b, 'fwdbwd'), (eng.b, 'adam', lr)
             if k1 not in graphs:
                 g1 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1):
+                with self._graph_ctx(g1):
                     eng.forward_backward()
                 g2 = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g2):
+                with self._graph_ctx(g2):
                     eng.adam(lr)
                 graphs[k1], graphs[k2] = g1, g2
             graphs[k1].replay()

@@ -178,6 +178,27 @@ def make_batch(batch: int, height: int, width: int, seed: int = 0, coherent: boo
     return out
 
 
+def add_dynamic_masks(batch_dict: Dict[object, Tensor], seed: int = 0) -> Dict[object, Tensor]:
+    """('mask', f, s) entries like the reference's datasets produce for ``mask_dynamic`` pre-training (datasets/kitti.py:284,
+    utils.py:158-163, :354): float {0, 1} maps of shape (B, 1, H >> s, W >> s), 1 = potentially dynamic object.  Two rectangles per
+    sample; one of them covers the top-left corner of sample 0, so that the "i-th selected element" of the reference's masked
+    smoothness term is NOT simply element i."""
+    g = torch.Generator().manual_seed(15485863 * seed + 29)
+    b, _, h, w = batch_dict[('rgb', 0, 0)].shape
+    for f in (-1, 0, 1):
+        m = torch.zeros(b, 1, h, w)
+        for i in range(b):
+            for _ in range(2):
+                y0 = int(torch.randint(0, h - h // 4, (1,), generator=g)); x0 = int(torch.randint(0, w - w // 4, (1,), generator=g))
+                hh = int(torch.randint(h // 8, h // 3, (1,), generator=g)); ww = int(torch.randint(w // 8, w // 3, (1,), generator=g))
+                m[i, 0, y0:y0 + hh, x0:x0 + ww] = 1.0
+        m[0, 0, :5, :3] = 1.0
+        m[0, 0, 0, 4] = 1.0
+        for s in range(4):
+            batch_dict[('mask', f, s)] = m if s == 0 else torch.round(F.avg_pool2d(m, 2 ** s))
+    return batch_dict
+
+
 def make_noise(batch: int, height: int, width: int, seed: int = 0, n_scales: int = 4) -> List[Tensor]:
     """Stand-in for the ``torch.randn`` tie-break draws (depth_pose_prediction.py:1055-1056):
     one (B,2,H,W) standard-normal tensor per scale, in scale order."""

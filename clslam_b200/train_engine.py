@@ -29,7 +29,8 @@ class TrainEngine:
     def __init__(self, *, batch: int, height: int, width: int, batch_global: int, has_sample0: bool,
                  depth_enc: ResnetEncoder, pose_enc: ResnetEncoder, depth_flat: EncoderFlat, pose_flat: EncoderFlat,
                  flat: FlatParams, min_depth: Optional[float], max_depth: Optional[float], disparity_smoothness: float,
-                 velocity_loss_scaling: Optional[float], bn_training: bool, device, emit_outputs: bool = True):
+                 velocity_loss_scaling: Optional[float], bn_training: bool, device, emit_outputs: bool = True,
+                 mask_dynamic: bool = False):
         if height % 32 or width % 32:
             raise ValueError('height and width must be multiples of 32 (ResNet-18 / 4-scale pyramid)')
         self.b, self.h, self.w = batch, height, width
@@ -37,6 +38,9 @@ class TrainEngine:
         self.device, self.flat = device, flat
         self.depth_flat, self.pose_flat = depth_flat, pose_flat
         self.bn_training = bn_training
+        self.mask_dynamic = mask_dynamic
+        if mask_dynamic and (batch_global != batch or batch > 64):
+            raise NotImplementedError('mask_dynamic: single process, batch <= 64')
         self.grad_sync_in_plan = False
         self.adam_in_plan = False
         lib = L.load()
@@ -77,6 +81,19 @@ class TrainEngine:
                 reserve(('warped', s), 2, b, 3, h, w)
         self.out_arena = plan.alloc(off)
 
+        if mask_dynamic:
+            # inputs['mask', 0, s] (:1066, :1081), the weights that turn the reprojection term into the mean over the static pixels,
+            # the positions of the b selected gradients per scale, the gradient of the masked smoothness term (csrc/mask.cu)
+            self.dyn_mask = [plan.alloc(b, 1, h >> s, w >> s, zero=True) for s in range(S)]
+            self.reproj_w = plan.alloc(b, zero=True)
+            self.mask_pos = plan.alloc(S, 2, b, dtype=torch.int32, zero=True)
+            self.sm_idx = plan.alloc(S, 4 * b, dtype=torch.int32, zero=True)
+            self.sm_val = plan.alloc(S, 4 * b, zero=True)
+            self.sm_uniform = plan.alloc(S, b, zero=True)
+            self._mask_ptrs = (ctypes.c_void_p * 4)(*[_p(t) for t in self.dyn_mask])
+            plan.keep.append(self._mask_ptrs)
+            plan.simple('mask_prepare', lib.clslam_mask_prepare, ctypes.cast(self._mask_ptrs, ctypes.c_void_p), b, h, w, S, _p(self.reproj_w),
+                        _p(self.mask_pos))
         # =================================== forward =====================================================================
         self.identity = plan.alloc(b, 2, h, w)
         plan.simple('pack_rgba', lib.clslam_pack_rgba, _p(self.sources), _p(self.sources_rgba), 2 * b, h, w)
@@ -169,12 +186,16 @@ class TrainEngine:
             pa.depth[s] = _p(self.depth[s]); pa.warped[s] = _p(self.warped[s])
             pa.argmin[s] = _p(self.argmin[s]); pa.ddisp_full[s] = _p(self.ddisp_full[s])
         pa.loss_partials, pa.dproj_partials = _p(self.loss_partials), _p(self.dproj_partials)
+        if mask_dynamic:
+            pa.dyn_mask, pa.reproj_w = _p(self.dyn_mask[0]), _p(self.reproj_w)
         self.photo_args = pa
         plan.keep.append(pa)
         self.vel_scale = float(velocity_loss_scaling) if (velocity_loss_scaling is not None and velocity_loss_scaling > 0) else 0.0
         la = L.LossArgs()
         la.b, la.b_global, la.h, la.w, la.n_scales, la.n_tiles = b, batch_global, h, w, S, self.n_tiles
-        la.has_sample0 = 1 if has_sample0 else 0
+        la.has_sample0 = 1 if (has_sample0 and not mask_dynamic) else 0          # masked: the smoothness term comes from csrc/mask.cu
+        if mask_dynamic:
+            la.reproj_w = _p(self.reproj_w)
         la.disparity_smoothness, la.velocity_scale = float(disparity_smoothness), self.vel_scale
         la.loss_partials, la.sample_w, la.sample_w_global = _p(self.loss_partials), _p(self.sample_w), _p(self.sample_w_global)
         for s in range(S):
@@ -185,6 +206,13 @@ class TrainEngine:
         plan.keep.append(la)
         plan.add('photo_fwd', lambda stream, ws: lib.clslam_photo_fwd(ctypes.byref(pa), stream))
         plan.add('loss_finalize', lambda stream, ws: lib.clslam_loss_finalize(ctypes.byref(la), stream))
+        if mask_dynamic:
+            self._disp_ptrs = (ctypes.c_void_p * 4)(*[_p(self.disp[s]) for s in range(S)])
+            self._color_ptrs = (ctypes.c_void_p * 4)(*[_p(self.color[s]) for s in range(S)])
+            plan.keep += [self._disp_ptrs, self._color_ptrs]
+            plan.simple('smooth_masked', lib.clslam_smooth_masked, ctypes.cast(self._disp_ptrs, ctypes.c_void_p),
+                        ctypes.cast(self._color_ptrs, ctypes.c_void_p), _p(self.mask_pos), _p(self.sample_w), b, h, w, S,
+                        float(disparity_smoothness), _p(self.losses), _p(self.sm_idx), _p(self.sm_val), _p(self.sm_uniform))
         self.n_fwd_ops = len(plan.ops)
 
         # =================================== backward ====================================================================
@@ -193,7 +221,10 @@ class TrainEngine:
         for s in range(S):
             self.dz_disp[s] = plan.alloc(b, 1, h >> s, w >> s)
             plan.simple(f'disp_grad_{s}', lib.clslam_disp_grad, _p(self.ddisp_full[s]), _p(self.disp[s]), _p(self.smooth_grad), batch_global,
-                        1 if has_sample0 else 0, b, h, w, s, _p(self.dz_disp[s]))
+                        1 if (has_sample0 and not mask_dynamic) else 0, b, h, w, s, _p(self.dz_disp[s]))
+            if mask_dynamic:
+                plan.simple(f'smooth_masked_apply_{s}', lib.clslam_smooth_masked_apply, _p(self.disp[s]), _p(self.sm_idx), _p(self.sm_val),
+                            _p(self.sm_uniform), b, h, w, s, _p(self.dz_disp[s]))
         self.dz = {k: plan.alloc(*v.shape) for k, v in self.y.items()}
         dfeat: Dict[int, torch.Tensor] = {}          # d(loss) / d(encoder feature i) from the decoder
         for i in range(0, 5):

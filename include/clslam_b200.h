@@ -325,6 +325,12 @@ typedef struct clslam_photo_args {
   float* loss_partials;
   float* ddisp_full[4];
   float* dproj_partials;
+  /* mask_dynamic (depth_pose_prediction.py:1062-1075), both NULL otherwise.  dyn_mask: inputs['mask',0,0] as (b,h,w) floats,
+   * >= 0.5 = potentially dynamic: such a pixel contributes nothing (forward: argmin code 4, which no gradient path matches).
+   * reproj_w: (b) weights of the reprojection term in place of sample_w -- H*W / (static pixels of the batch) for every b, which
+   * turns sum_b w_b * mean_hw(.) into the mean over the selected pixels (clslam_mask_prepare writes them). */
+  const float* dyn_mask;
+  const float* reproj_w;
 } clslam_photo_args;
 int clslam_photo_tiles(int h, int w);
 /* (n,3,h,w) planar -> (n,h,w,4) packed (4th component 0): one 16-byte load per bilinear tap in the warp */
@@ -354,8 +360,28 @@ typedef struct clslam_loss_args {
   const double* rel_dist;       /* (2,b): relative_distance 0 and 1 */
   float* losses;                /* (24) */
   float* smooth_grad;           /* (n_scales, 2*(b_global+1)+1) */
+  const float* reproj_w;        /* (b) or NULL: weights of the reprojection term in place of sample_w (mask_dynamic) */
 } clslam_loss_args;
 int clslam_loss_finalize(const clslam_loss_args* a, void* stream);
+
+/* ---- mask_dynamic: pre-training with dynamic-object masks (depth_pose_prediction.py:1062-1068, :1080-1082, :1148-1176) -------
+ * masks[s]: inputs['mask',0,s] as (b,1,h>>s,w>>s) floats, >= 0.5 = dynamic (the reference selects `1 - mask`).  Single GPU.
+ * clslam_mask_prepare: reproj_w[bb] = H*W / (number of static pixels of the whole batch at scale 0), and for every scale the flat
+ *   positions of the first b SELECTED x-gradients (grid (b,h_s,w_s-1), selected by static[..., :-1]) and y-gradients (grid
+ *   (b,h_s-1,w_s), selected by static[..., :-1, :]) in raster order: pos (n_scales, 2, b) ints, -1 where fewer exist.  These are
+ *   the elements the reference's per-sample loop ends up reading: "sample i" gets the i-th selected gradient of the batch.
+ * clslam_smooth_masked: run AFTER clslam_loss_finalize (called with has_sample0 = 0, so that its own smoothness term is zero):
+ *   evaluates the b terms per scale, patches losses (smooth / reg / depth_loss per scale, depth_loss, loss) and writes the
+ *   gradient with respect to the (sigmoid) disparities: direct entries sm_idx / sm_val (n_scales, 4*b) -- pixel index into
+ *   (b,h_s,w_s), -1 = unused -- and the per-sample uniform term of the mean normalisation sm_uniform (n_scales, b).
+ * clslam_smooth_masked_apply: dz_disp[q] += (uniform[sample of q] + sum of the direct entries at q) * disp[q] * (1 - disp[q]),
+ *   after clslam_disp_grad of that scale. */
+int clslam_mask_prepare(const float* const* masks, int b, int h, int w, int n_scales, float* reproj_w, int* pos, void* stream);
+int clslam_smooth_masked(const float* const* disp, const float* const* color, const int* pos, const float* sample_w, int b, int h,
+                         int w, int n_scales, float disparity_smoothness, float* losses, int* sm_idx, float* sm_val,
+                         float* sm_uniform, void* stream);
+int clslam_smooth_masked_apply(const float* disp, const int* sm_idx, const float* sm_val, const float* sm_uniform, int b, int h,
+                               int w, int scale, float* dz_disp, void* stream);
 /* d(loss)/d(disp_s): transpose of the bilinear up-sampling applied to ddisp_full[s], plus the
  * smoothness terms, times sigmoid'; writes dz of dispconv_s (b,1,h>>s,w>>s). */
 int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* smooth_grad, int b_global,

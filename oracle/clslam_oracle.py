@@ -42,8 +42,8 @@ ENC_CH = (64, 64, 128, 256, 512)  # networks/resnet_encoder.py:99
 
 # Seeded inputs and weights (pure data generation, shared with bench.py / smoke()): re-exported so that tests and the
 # golden generator keep addressing them through the oracle module
-from clslam_b200.synthetic import (NET_NAMES, kitti_intrinsics, make_batch, make_noise, make_params,  # noqa: E402,F401
-                                   net_layouts)
+from clslam_b200.synthetic import (NET_NAMES, add_dynamic_masks, kitti_intrinsics, make_batch, make_noise,  # noqa: E402,F401
+                                   make_params, net_layouts)
 
 
 def trainable_keys() -> List[Tuple[str, str]]:
@@ -270,6 +270,27 @@ def smoothness_reference_quirk(norm_disp: Tensor, img: Tensor, n_terms: Optional
     return gx.reshape(-1)[:b] + gy.reshape(-1)[:b]
 
 
+def smoothness_reference_masked(norm_disp: Tensor, img: Tensor, mask: Tensor) -> Tensor:
+    """depth_pose_prediction.py:1148-1176 *as executed* with a real mask (``mask_dynamic``, :1080-1082; True = static pixel).
+    The first pair of masked_select calls flattens the selected edge-weighted gradients of the WHOLE batch to 1-D (raster order
+    over (B, 1, h, w-1) / (B, 1, h-1, w), selected by mask[..., :-1] / mask[..., :-1, :]); the per-sample loop then indexes that
+    flat vector by sample number and broadcasts the scalar against the sample's mask, so "sample i" receives the i-th selected
+    x-gradient plus the i-th selected y-gradient of the batch (NaN when sample i has no static pixel)."""
+    b = norm_disp.shape[0]
+    gx = (norm_disp[:, :, :, :-1] - norm_disp[:, :, :, 1:]).abs()
+    gy = (norm_disp[:, :, :-1, :] - norm_disp[:, :, 1:, :]).abs()
+    gx = gx * torch.exp(-(img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, True))
+    gy = gy * torch.exp(-(img[:, :, :-1, :] - img[:, :, 1:, :]).abs().mean(1, True))
+    fx = torch.masked_select(gx, mask[..., :-1])
+    fy = torch.masked_select(gy, mask[..., :-1, :])
+    out = []
+    for i in range(b):
+        tx = torch.masked_select(fx[i, ...], mask[i, :, :, :-1]).mean()
+        ty = torch.masked_select(fy[i, ...], mask[i, :, :-1, :]).mean()
+        out.append(tx + ty)
+    return torch.stack(out)
+
+
 def smoothness_intended(norm_disp: Tensor, img: Tensor) -> Tensor:
     """The monodepth2 per-sample edge-aware smoothness the reference meant to compute."""
     gx = (norm_disp[:, :, :, :-1] - norm_disp[:, :, :, 1:]).abs()
@@ -287,7 +308,7 @@ class OracleConfig:
     def __init__(self, height: int, width: int, batch_size: int, min_depth: Optional[float] = 0.1,
                  max_depth: Optional[float] = None, disparity_smoothness: float = 1e-3,
                  velocity_loss_scaling: Optional[float] = 0.05, learning_rate: float = 1e-4,
-                 scales: Sequence[int] = (0, 1, 2, 3), smooth_mode: str = 'reference') -> None:
+                 scales: Sequence[int] = (0, 1, 2, 3), smooth_mode: str = 'reference', mask_dynamic: bool = False) -> None:
         self.height, self.width, self.batch_size = height, width, batch_size
         self.min_depth, self.max_depth = min_depth, max_depth
         self.disparity_smoothness = disparity_smoothness
@@ -295,6 +316,7 @@ class OracleConfig:
         self.learning_rate = learning_rate
         self.scales = tuple(scales)
         self.smooth_mode = smooth_mode
+        self.mask_dynamic = mask_dynamic          # pre-training with dynamic-object masks (:1062-1068, :1080-1082)
 
 
 def predict_poses(params: Dict[str, StateDict], batch: Dict[object, Tensor], training: bool = False) -> Dict[object, Tensor]:
@@ -349,13 +371,20 @@ def process_batch(params: Dict[str, StateDict], batch: Dict[object, Tensor], cfg
         ident = torch.cat([photometric_error(batch[('rgb', f, 0)], target) for f in FRAME_IDS[1:]], 1)
         ident = ident + noise[si] * 0.00001
         best, _ = torch.min(torch.cat([ident, reproj], 1), dim=1)
-        reproj_loss = (best.mean(2).mean(1) * sample_weights).sum()
+        if cfg.mask_dynamic:          # :1064-1075: mean over the static pixels of the whole batch, no sample weights
+            static0 = (1 - batch[('mask', 0, 0)].squeeze()).type(torch.bool)
+            reproj_loss = torch.masked_select(best, static0).mean()
+        else:
+            reproj_loss = (best.mean(2).mean(1) * sample_weights).sum()
         losses[f'reprojection_loss/scale_{s}'] = reproj_loss
 
         disp = outputs[('disp', s)]
         norm_disp = disp / (disp.mean(2, True).mean(3, True) + 1e-7)
         if not with_smooth:
             smooth = torch.zeros((), device=dev)
+        elif cfg.mask_dynamic:
+            static_s = (1 - batch[('mask', 0, s)]).type(torch.bool)
+            smooth = (smoothness_reference_masked(norm_disp, batch[('rgb', 0, s)], static_s) * sample_weights).sum()
         elif cfg.smooth_mode == 'reference':
             sw = sample_weights if smooth_weights is None else smooth_weights
             smooth = (smoothness_reference_quirk(norm_disp, batch[('rgb', 0, s)], sw.numel()) * sw).sum()

@@ -61,6 +61,8 @@ ONLINE_LOSS_WEIGHT = {'small_b4_replay': 0.4}
 TRAIN_CASES = {
     'small_b2_train': ((2, 64, 96, True, None, 11), 'train'),
     'small_b3_adapt_enc': ((3, 64, 96, True, None, 12), 'adapt_enc'),
+    # pre-training with dynamic-object masks (config mask_dynamic=True, :1062-1068, :1080-1082), training-mode BatchNorm
+    'small_b3_train_masked': ((3, 64, 96, True, None, 13), 'train_masked'),
 }
 # stride of the stored ('disp', s) maps / of the stored depth and warped maps
 DISP_SUB = {'full_b8_replay': (4, 2, 1, 1), 'hires_b8_replay': (8, 4, 2, 1), 'hires_b1': (4, 2, 1, 1)}
@@ -90,7 +92,7 @@ def import_reference():
     return Dataset, Cfg, DepthPosePrediction
 
 
-def build_reference(batch, height, width, max_depth):
+def build_reference(batch, height, width, max_depth, mask_dynamic=False):
     Dataset, Cfg, DepthPosePrediction = import_reference()
     ds = Dataset(dataset='Kitti', config_file=Path('x'), dataset_path=None, scales=(0, 1, 2, 3),
                  height=height, width=width, frame_ids=(0, -1, 1))
@@ -98,7 +100,7 @@ def build_reference(batch, height, width, max_depth):
               resnet_pretrained=False, scales=(0, 1, 2, 3), learning_rate=1e-4,
               scheduler_step_size=15, batch_size=batch, num_workers=0, num_epochs=1, min_depth=0.1,
               max_depth=max_depth, disparity_smoothness=1e-3, velocity_loss_scaling=0.05,
-              mask_dynamic=False, log_path=Path('/tmp/clslam_golden_log'), save_frequency=-1,
+              mask_dynamic=mask_dynamic, log_path=Path('/tmp/clslam_golden_log'), save_frequency=-1,
               save_val_depth=False, save_val_depth_batches=0, multiple_gpus=False, gpu_ids=None,
               load_weights_folder=None, use_wandb=False)
     pred = DepthPosePrediction(ds, cfg)
@@ -238,12 +240,15 @@ def run_train_case(name, spec, mode, out_dir: Path):
     receives a gradient, BatchNorm running statistics after the forward pass, loss of a second step"""
     b, h, w, coherent, max_depth, seed = spec
     torch.manual_seed(0)
-    pred, params = build_reference(b, h, w, max_depth)
+    masked = mode == 'train_masked'
+    pred, params = build_reference(b, h, w, max_depth, mask_dynamic=masked)
     batch = orc.make_batch(b, h, w, seed=seed, coherent=coherent)
+    if masked:
+        orc.add_dynamic_masks(batch, seed=seed)
     noise = orc.make_noise(b, h, w, seed=seed)
     rec = {'meta': np.array([b, h, w, int(coherent), -1.0 if max_depth is None else max_depth, seed], dtype=np.float64),
-           'train_mode': np.array([1.0 if mode == 'train' else 0.0])}
-    if mode == 'train':
+           'train_mode': np.array([1.0 if mode in ('train', 'train_masked') else 0.0]), 'mask_dynamic': np.array([1.0 if masked else 0.0])}
+    if mode in ('train', 'train_masked'):
         pred._set_train()
     else:
         pred._set_adapt(freeze_encoder=False)

@@ -65,6 +65,29 @@ def test_plan_builds_and_is_consistent(b, h, w):
         assert k['conv_tma'] == 64 and k['gather'] == 11 and k['wgrad_tma'] == 5
 
 
+def test_masked_training_plan_builds():
+    """config mask_dynamic=True: the training plan stages inputs['mask', 0, s] and carries the csrc/mask.cu launches"""
+    dev = torch.device('cpu')
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), Config(batch_size=2, mask_dynamic=True), device=dev)
+    pred._set_train()
+    ns = pred._main
+    for ef in ns.enc_flat.values():
+        ef.ensure_training_buffers()
+    from clslam_b200.train_engine import TrainEngine
+    eng = TrainEngine(batch=2, height=64, width=96, batch_global=2, has_sample0=True, depth_enc=ns.models['depth_encoder'],
+                      pose_enc=ns.models['pose_encoder'], depth_flat=ns.enc_flat['depth_encoder'], pose_flat=ns.enc_flat['pose_encoder'],
+                      flat=ns.flat, min_depth=0.1, max_depth=None, disparity_smoothness=1e-3, velocity_loss_scaling=0.05,
+                      bn_training=True, device=dev, mask_dynamic=True)
+    names = [o[0] for o in eng.plan.ops if o[1] is not None]
+    assert names[0] == 'mask_prepare' and 'smooth_masked' in names
+    assert names.index('loss_finalize') < names.index('smooth_masked') < names.index('photo_bwd')
+    for s in range(4):
+        assert names.index(f'disp_grad_{s}') + 1 == names.index(f'smooth_masked_apply_{s}')
+    smap = pred._static_map(eng)
+    assert all(('mask', 0, s) in smap and smap[('mask', 0, s)].shape == (2, 1, 64 >> s, 96 >> s) for s in range(4))
+    assert eng.loss_args.has_sample0 == 0 and eng.photo_args.dyn_mask == eng.dyn_mask[0].data_ptr()
+
+
 @pytest.mark.parametrize('bn_training', [True, False])
 def test_training_plan_builds(bn_training):
     """the full training plan (encoders trainable, explicit BatchNorm; clslam_b200/train_engine.py) builds on the CPU: one

@@ -96,6 +96,25 @@ def test_oracle_predict_pose_and_buffer_feature(name):
     assert rel(f4.mean(-1).mean(-1).numpy(), rec['buffer_feature']) < 2e-6
 
 
+def test_masked_smoothness_is_the_ith_selected_gradient():
+    """mask_dynamic (:1080-1082, :1166-1174): "sample i" receives the i-th SELECTED x- and y-gradient of the whole batch"""
+    g = torch.Generator().manual_seed(1)
+    nd = torch.rand(3, 1, 8, 12, generator=g)
+    img = torch.rand(3, 3, 8, 12, generator=g)
+    static = torch.ones(3, 1, 8, 12, dtype=torch.bool)
+    static[0, 0, 0, :2] = False          # the first two pixels of sample 0 are dynamic
+    static[0, 0, 0, 3] = False
+    got = orc.smoothness_reference_masked(nd, img, static)
+    gx = (nd[:, :, :, :-1] - nd[:, :, :, 1:]).abs() * torch.exp(-(img[:, :, :, :-1] - img[:, :, :, 1:]).abs().mean(1, True))
+    gy = (nd[:, :, :-1, :] - nd[:, :, 1:, :]).abs() * torch.exp(-(img[:, :, :-1, :] - img[:, :, 1:, :]).abs().mean(1, True))
+    sel = [2, 4, 5]                      # columns of row 0, sample 0 that are static (in both grids here)
+    for i in range(3):
+        assert abs(float(got[i]) - float(gx[0, 0, 0, sel[i]] + gy[0, 0, 0, sel[i]])) < 1e-6
+    # with an all-true mask it is the unmasked quirk
+    full = orc.smoothness_reference_masked(nd, img, torch.ones_like(static))
+    assert torch.allclose(full, orc.smoothness_reference_quirk(nd, img))
+
+
 def test_smoothness_quirk_is_row0_of_sample0():
     """the per-"sample" smoothness terms all come from batch element 0."""
     g = torch.Generator().manual_seed(0)
@@ -124,15 +143,19 @@ def test_replay_case_really_differs_from_the_plain_one():
 
 
 # ---- full training path: the reference in _set_train() / _set_adapt(freeze_encoder=False) mode ----------
-TRAIN = [('small_b2_train', 'train'), ('small_b3_adapt_enc', 'adapt_enc')]
+TRAIN = [('small_b2_train', 'train'), ('small_b3_adapt_enc', 'adapt_enc'), ('small_b3_train_masked', 'train')]
 
 
 def load_train_case(name):
     rec = np.load(GOLDEN / f'{name}.npz')
     b, h, w, coherent, max_depth, seed = rec['meta']
     b, h, w, seed = int(b), int(h), int(w), int(seed)
-    cfg = orc.OracleConfig(h, w, b, max_depth=None if max_depth < 0 else float(max_depth))
-    return rec, cfg, orc.make_params(0), orc.make_batch(b, h, w, seed=seed, coherent=bool(coherent)), orc.make_noise(b, h, w, seed=seed)
+    masked = 'mask_dynamic' in rec.files and float(rec['mask_dynamic'][0]) > 0
+    cfg = orc.OracleConfig(h, w, b, max_depth=None if max_depth < 0 else float(max_depth), mask_dynamic=masked)
+    batch = orc.make_batch(b, h, w, seed=seed, coherent=bool(coherent))
+    if masked:
+        orc.add_dynamic_masks(batch, seed=seed)
+    return rec, cfg, orc.make_params(0), batch, orc.make_noise(b, h, w, seed=seed)
 
 
 @pytest.mark.parametrize('name,mode', TRAIN)
