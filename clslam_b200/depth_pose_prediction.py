@@ -17,6 +17,7 @@ import warnings
 from pathlib import Path
 from typing import Any, Callable, Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 from torch import Tensor, nn, optim
 
@@ -805,8 +806,10 @@ class DepthPosePrediction:
         are outside SURVEY.md section 8: pass the loader."""
         if use_wandb:
             raise NotImplementedError('wandb logging (:226-229, :1246-1267) is outside SURVEY.md section 8')
-        if validate or depth_error or pose_error:
-            raise NotImplementedError('validate / depth_error / pose_error need the dataset loaders: outside SURVEY.md section 8')
+        if depth_error or pose_error:
+            raise NotImplementedError('depth_error / pose_error need the ground truth of the dataset loaders: outside SURVEY.md section 8')
+        if validate and self.val_loader is None:
+            raise NotImplementedError('train(validate=True) needs `val_loader` to be assigned (see validate())')
         if dataloader is None:
             raise NotImplementedError('train() needs `dataloader`: the reference builds it from its datasets package '
                                       '(_create_dataloaders, :829-904), which is outside SURVEY.md section 8')
@@ -831,6 +834,10 @@ class DepthPosePrediction:
             self.is_trained = True
             if self.save_frequency > 0 and self.epoch % self.save_frequency == 0:
                 self.save_model()
+            if validate:
+                validation_loss = self.validate()          # :269-272
+                if verbose:
+                    print(f'Validation epoch {self.epoch}: loss={validation_loss:.6f}')
         if self.save_frequency > -1:
             self.save_model()
 
@@ -894,8 +901,24 @@ class DepthPosePrediction:
             transformation = transformation.squeeze().cpu().detach().numpy()
         return depth_0, depth_1, transformation
 
-    def validate(self) -> float:
-        raise NotImplementedError('validate() (:321-342) iterates the validation DataLoader: datasets are outside SURVEY.md 8')
+    def validate(self, dataloader=None) -> float:
+        """:321-342: mean evaluation-mode loss over the validation loader (``dataloader=`` or a previously assigned
+        ``val_loader``; building the reference's own loaders, :829-904, is outside SURVEY.md section 8).  ``save_val_depth`` plots
+        are not produced."""
+        if not self.is_trained:
+            warnings.warn('The model has not been trained yet.', RuntimeWarning)
+        if dataloader is not None:
+            self.val_loader = dataloader
+        if self.val_loader is None:
+            raise NotImplementedError('validate() needs `dataloader` (or `val_loader`): the reference builds it from its datasets '
+                                      'package (_create_dataloaders, :829-904), which is outside SURVEY.md section 8')
+        self._set_eval()
+        loss = []
+        with torch.no_grad():
+            for sample_i in self.val_loader:
+                _, losses = self._process_batch(sample_i)
+                loss.append(float(losses['loss']))
+        return float(np.mean(loss)) if loss else float('nan')
 
     def compute_depth_error(self, median_scaling: bool = True, print_results: bool = True) -> Dict[str, float]:
         raise NotImplementedError('compute_depth_error() (:344-468) needs the dataset loaders: outside SURVEY.md 8')

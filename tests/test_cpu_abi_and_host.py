@@ -190,6 +190,15 @@ def test_train_loop_host_logic(tmp_path, capsys):
         pred.num_epochs = 4
         pred.train(dataloader=[dict(batch)], verbose=False)
         assert calls['forward_backward'] == 7 and pred.epoch == 4
+        # validate(): evaluation-mode loss over a loader; train(validate=True) runs it once per epoch
+        with pytest.raises(NotImplementedError):
+            pred.validate()
+        n_fwd = calls['forward']
+        assert pred.validate(dataloader=[dict(batch), dict(batch), dict(batch)]) == pytest.approx(0.1) and pred._mode == 'eval'
+        assert calls['forward'] == n_fwd + 3
+        pred.num_epochs = 5
+        pred.train(validate=True, dataloader=[dict(batch)], verbose=False)
+        assert pred.epoch == 5 and calls['forward'] == n_fwd + 3 + 3
     # the encoders' Parameters are views of the flat training buffers and carry gradient views
     g = pred.encoder_gradients()
     assert len(g) == 2 * 60 and g[('depth_encoder', 'resnet.layer2.0.downsample.0.weight')].shape == (128, 64, 1, 1)
