@@ -340,6 +340,49 @@ disp_grad_kernel(const float* __restrict__ ddisp_full, const float* __restrict__
   }
 }
 
+// the same for the coarse scales (s >= 2), one WARP per low-res pixel: its 2f x 2f window (64 / 256 taps) is spread over the
+// lanes and reduced with shuffles.  The thread-per-pixel form above leaves 1920 threads with 256 dependent taps each at scale 3
+// of a 192 x 640 image (33 us at batch 1, on the lane that heads the weight-gradient chain).
+__global__ void __launch_bounds__(256)
+disp_grad_warp_kernel(const float* __restrict__ ddisp_full, const float* __restrict__ disp, const float* __restrict__ smooth_grad,
+                      int b_global, int has_sample0, int b, int h, int w, int scale, float* __restrict__ dz) {
+  pdl_wait();
+  pdl_trigger();
+  const int hs = h >> scale, ws = w >> scale;
+  const int f = 1 << scale;
+  const int lane = threadIdx.x & 31;
+  const size_t total = (size_t)b * hs * ws;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < total; i += n_warps) {
+    const int j = (int)(i % ws);
+    const int r = (int)((i / ws) % hs);
+    const int bb = (int)(i / ((size_t)ws * hs));
+    const float* src = ddisp_full + (size_t)bb * h * w;
+    const int y_lo = max(0, f * r - f / 2), y_hi = min(h, f * r + 3 * f / 2);
+    const int x_lo = max(0, f * j - f / 2), x_hi = min(w, f * j + 3 * f / 2);
+    const int nx = x_hi - x_lo, n = nx * (y_hi - y_lo);
+    float g = 0.f;
+    for (int k = lane; k < n; k += 32) {
+      const int y = y_lo + k / nx, x = x_lo + k % nx;
+      const UpCoef cy = up_coef(y, hs, h);
+      const UpCoef cx = up_coef(x, ws, w);
+      const float wy = (cy.i0 == r ? cy.l0 : 0.f) + (cy.i1 == r ? cy.l1 : 0.f);
+      const float wxv = (cx.i0 == j ? cx.l0 : 0.f) + (cx.i1 == j ? cx.l1 : 0.f);
+      g += wy * wxv * ld1(src + (size_t)y * w + x);
+    }
+    g = warp_sum(g);
+    if (lane == 0) {
+      if (has_sample0 && bb == 0 && smooth_grad) {
+        const float* sg = smooth_grad + (size_t)scale * (2 * (b_global + 1) + 1);
+        g += sg[2 * (b_global + 1)];
+        if (r < 2 && j <= b_global) g += sg[r * (b_global + 1) + j];
+      }
+      const float dv = disp[i];
+      dz[i] = g * dv * (1.f - dv);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 disp_to_depth_kernel(const float* __restrict__ disp, float* __restrict__ depth, long long n, int mode, float min_depth, float max_depth) {
   pdl_wait();
@@ -421,6 +464,13 @@ int clslam_disp_to_depth(const float* disp, float* depth, long long n, int depth
 int clslam_disp_grad(const float* ddisp_full, const float* disp, const float* smooth_grad, int b_global, int has_sample0,
                      int b, int h, int w, int scale, float* dz_disp, void* stream) {
   const size_t total = (size_t)b * (h >> scale) * (w >> scale);
+  if (scale >= 2) {          // one warp per low-res pixel
+    size_t blocks = (total + 7) / 8;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    launch_k(disp_grad_warp_kernel, dim3((unsigned)blocks), dim3(256), 0, as_stream(stream), ddisp_full, disp, smooth_grad, b_global,
+             has_sample0, b, h, w, scale, dz_disp);
+    return finish_launch("disp_grad");
+  }
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   launch_k(disp_grad_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), ddisp_full, disp, smooth_grad, b_global, has_sample0, b, h, w, scale,

@@ -81,7 +81,10 @@ H2D_OVERLAP = _flag('CLSLAM_H2D_OVERLAP')
 # the decoder follows it) and the pose network (lane 1) run side by side, and a CTA of the TMA convolution holds a whole SM:
 # two launches only overlap when their CTA counts fit the 148 SMs together.  0 = no limit.
 DEPTH_ENC_SMS = int(os.environ.get('CLSLAM_DEPTH_ENC_SMS', '0'))
-POSE_NET_SMS = int(os.environ.get('CLSLAM_POSE_NET_SMS', '-1'))          # -1: 64 at batch 1 (measured: 1.032 -> 1.002 ms / step), else 0
+# Measured at batch 1: pose network capped at 64 SMs 1.032 -> 1.002 ms / step -- but a different split-K plan is a different
+# summation order, and on the white-noise fixture full_b1 the pose error moved from 6.8e-5 to 1.07e-4 of the 1e-4 tolerance:
+# OFF by default (parity first); CLSLAM_POSE_NET_SMS=64 turns it on
+POSE_NET_SMS = int(os.environ.get('CLSLAM_POSE_NET_SMS', '0'))
 
 
 def tma_big(n: int, h: int, w: int, min_tiles: Optional[int] = None) -> bool:
@@ -851,7 +854,7 @@ class AdaptEngine:
         pf4_pl = PlaneBuf(plan, 2 * b, h >> 5, w >> 5, ENC_CH[4]).view() if (TMA_DS and tma_ok(2 * b, h >> 5, w >> 5, 512, 256)) else None
         # (lane 3, not 2: lane 2 holds dispconv_1..3 by now, which wait for late decoder stages -- stream order would park the
         # pose encoder's down-sampling convolutions behind them)
-        plan.sm_budget = POSE_NET_SMS if POSE_NET_SMS >= 0 else (64 if b == 1 else 0)
+        plan.sm_budget = POSE_NET_SMS
         pfeats = build_encoder(plan, pose_prep, self.pose_in, 2 * b, h, w, 'pose_enc', x_s2d=pose_s2d, feat4_planes=pf4_pl,
                                side_lane=3)
         pf4 = pfeats[4]

@@ -4,7 +4,7 @@ set -u
 cd "$(dirname "$0")/.."
 T=${1:-q}
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$T.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$T.log | cut -c1-200
+timeout 400 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$T.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_$T.log | cut -c1-200
 B="python bench.py --steps 30 --no-extra-configs --no-cpu-baseline --no-op-profile"
 for cfg in "1 192 640" "8 192 640" "8 384 1280"; do
   set -- $cfg
