@@ -570,6 +570,54 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t[0]), float(t[1])
 
+    # ---- N>1, batch 1 per GPU: the same job with 4 triplets per GPU as an extra key (at N=8 this is BASELINE configs[3]: 1 current +
+    # 31 replay triplets over 8 GPUs).  Every rank runs it; a watchdog keeps the main line if it hangs.
+    extra4 = None
+    if world > 1 and b == 1 and not args.no_extra_configs:
+        import signal
+
+        def _give_up(*_):
+            raise TimeoutError('extra batch-4 measurement timed out')
+        old_handler = signal.signal(signal.SIGALRM, _give_up)
+        signal.alarm(150)
+        try:
+            pred.close()
+            b4 = 4
+            pred4 = build_predictor(b4 * world, h, w, world, not args.no_graph)
+            full4 = synthetic.make_batch(b4 * world, h, w, seed=2, coherent=True)
+            host4 = {k: v[rank * b4:(rank + 1) * b4].contiguous().pin_memory() for k, v in full4.items()}
+            for _ in range(3):
+                pred4.adapt(dict(host4), dict(host4), steps=1)
+            eng4 = pred4._engines[b4]
+            st4 = dict(host4)
+            pred4._stage_inputs(st4)
+            pred4._set_weights(eng4, None)
+            for _ in range(2):
+                pred4._draw_noise(eng4); pred4._step(eng4)
+            ev4 = []
+            barrier()
+            n4 = max(5, args.steps // 3)
+            for _ in range(n4):
+                flush.zero_()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record(); pred4._draw_noise(eng4); pred4._step(eng4); a1.record()
+                ev4.append((a0, a1))
+            barrier()
+            t4 = torch.tensor([sum(x.elapsed_time(y) for x, y in ev4)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+            _, l4 = pred4._collect(eng4)
+            ms4 = float(t4[0]) / n4
+            extra4 = {'workload': f'adapt step, batch={b4} per GPU, global batch {b4 * world} (1 current + {b4 * world - 1} replay), {h}x{w}, '
+                                  f'{world}xB200', 'ms_per_step': ms4, 'value': b4 * world / (ms4 * 1e-3), 'unit': UNIT, 'steps': n4,
+                      'loss': float(l4['loss'])}
+            pred4.close()
+            pred = pred4          # (teardown below closes whatever `pred` is)
+        except Exception as exc:          # never lose the bench line over the extra key
+            extra4 = {'error': str(exc)[:200]}
+        finally:
+            signal.alarm(0)
+            signal.signal(signal.SIGALRM, old_handler)
+
     if rank == 0:
         value = b_global * args.steps / (dev_ms / 1e3)
         e2e = b_global * args.steps / (e2e_ms / 1e3)
@@ -592,6 +640,8 @@ def run_ours(args):
             line['dp_parity'] = dp_parity
         elif replicas_identical is not None:
             line['dp_parity'] = {'replicas_identical': replicas_identical}
+        if extra4 is not None:
+            line['batch4_per_gpu'] = extra4
         hbm_peak, tensor_peak, peak_src = load_peaks()
         traffic_db = load_traffic()
         if world == 1 and not args.no_op_profile and not args.no_graph:
