@@ -94,8 +94,8 @@ def test_reprojection_weights_turn_the_weighted_sum_into_the_masked_mean():
     dyn = (torch.rand(b, h, w, generator=g) < 0.3).double()
     static = dyn < 0.5
     want = torch.masked_select(best, static).mean()
-    reproj_w = h * w / static.sum()
+    reproj_w = h * w / float(static.sum())
     got = sum(reproj_w * (best[i] * static[i]).sum() / (h * w) for i in range(b))
     assert abs(float(got) - float(want)) < 1e-14
     # and the gradient with respect to a selected pixel: reproj_w / (n_scales * H * W) = 1 / (n_scales * count)
-    assert abs(float(reproj_w) / (4 * h * w) - 1.0 / (4 * float(static.sum()))) < 1e-18
+    assert abs(reproj_w / (4 * h * w) - 1.0 / (4 * float(static.sum()))) < 1e-18
