@@ -607,16 +607,18 @@ class DepthPosePrediction:
             if self.losses_on_host:
                 vec = host
         losses: Dict[str, Tensor] = {}
+        slots = vec.unbind(0)                            # one call instead of 17 indexing ops: this runs after the sync, with the GPU idle
         for s in self.scales:
             for name in ('reprojection_loss', 'smooth_loss', 'reg_loss', 'depth_loss'):
-                losses[f'{name}/scale_{s}'] = vec[LOSS_SLOTS[name] + s]
+                losses[f'{name}/scale_{s}'] = slots[LOSS_SLOTS[name] + s]
         total = vec[18:19]
         losses['depth_loss'] = total                     # same tensor as 'loss' 
         if eng.vel_scale > 0:
-            losses['velocity_loss'] = vec[17]
+            losses['velocity_loss'] = slots[17]
         losses['loss'] = total
         if check_nan:
-            if bool(torch.isnan(host[18])):
+            total_host = float(host[18])
+            if total_host != total_host:          # NaN (:1115)
                 for k, v in losses.items():
                     print(k, float(v.reshape(-1)[0]))
                 raise RuntimeError('NaN loss')
