@@ -202,3 +202,29 @@ def test_train_loop_host_logic(tmp_path, capsys):
     # the encoders' Parameters are views of the flat training buffers and carry gradient views
     g = pred.encoder_gradients()
     assert len(g) == 2 * 60 and g[('depth_encoder', 'resnet.layer2.0.downsample.0.weight')].shape == (128, 64, 1, 1)
+
+
+def test_mask_dynamic_host_logic(tmp_path):
+    """config mask_dynamic=True: the training plan stages inputs['mask', 0, s] (a batch without masks is refused with the missing
+    keys named), the frozen-encoder adaptation / evaluation plans refuse the configuration"""
+    import torch
+    from tests.dryrun import dry_run_backend
+    from clslam_b200 import Config, DatasetConfig, DepthPosePrediction
+    cfg = Config(batch_size=2, num_epochs=1, save_frequency=-1, log_path=tmp_path, mask_dynamic=True)
+    pred = DepthPosePrediction(DatasetConfig(height=64, width=96), cfg, device=torch.device('cpu'), use_cuda_graph=False)
+    batch = orc.make_batch(2, 64, 96)
+    with dry_run_backend() as calls:
+        with pytest.raises(KeyError, match='mask'):
+            pred.train(dataloader=[dict(batch)], verbose=False)
+        pred.epoch = 0
+        masked = orc.add_dynamic_masks(dict(batch), seed=1)
+        staged = dict(masked)
+        pred.train(dataloader=[staged], verbose=False)
+        assert calls['forward_backward'] == 1 and pred.epoch == 1
+        eng = pred._last_engine
+        assert eng.mask_dynamic and torch.equal(eng.dyn_mask[2], masked[('mask', 0, 2)])
+        assert staged[('mask', 0, 0)].data_ptr() == eng.dyn_mask[0].data_ptr()          # the dict now holds the staged buffers
+        with pytest.raises(NotImplementedError, match='mask_dynamic'):
+            pred.adapt(dict(masked), dict(masked), steps=1)
+        with pytest.raises(NotImplementedError, match='mask_dynamic'):
+            pred.predict(dict(masked))
